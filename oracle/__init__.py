@@ -1,0 +1,2 @@
+"""Parity oracle (test infrastructure).  Only tests/, __graft_entry__.smoke() and
+bench.py's cpu_baseline / --impl reference legs may import this package."""

@@ -1,0 +1,549 @@
+/*
+ * aln_core.cuh — per-read state machines of the `aln` hot path.
+ *
+ * Everything here is written once and compiled twice: by nvcc for sm_100a (the
+ * product kernels in b200aln.cu) and by g++ for the logic tests in
+ * tests/harness (which run the same state machines on the CPU next to the
+ * oracle).  No warp intrinsics in this file; the warp-level plumbing (work
+ * distribution, launches) lives in b200aln.cu.
+ *
+ * Reference behaviour being re-implemented (file:line under the reference):
+ *   occ / 2occ / 2occ4 ............ bwt.c:81-214
+ *   bwt_match_exact_alt ........... bwt.c:235-250
+ *   bwt_cal_width ................. bwtaln.c:54-78
+ *   bwt_match_gap ................. bwtgap.c:104-264
+ *   gap_push / gap_pop / shadow ... bwtgap.c:45-91
+ *
+ * Device index layout (one 32-byte sector per occ lookup):
+ *   block b covers bases [64b, 64b+64) of the sentinel-free BWT string:
+ *     U4 #0 : L2[c] + (number of c before base 64b), c = A,C,G,T
+ *     U4 #1 : lo0, lo1, hi0, hi1 — two bit planes, base j at bit j%32 of word j/32
+ *   occ_excl(q) (count in [0,q)) therefore needs block q>>6 and q&63 mask bits.
+ *   Row numbers map to q without special cases:
+ *     lower end  occ(k-1): q = k - (k > primary)
+ *     upper end  occ(l)  : q = l + 1 - (l >= primary)
+ *   which also covers k-1 == -1 (q = 0) and l == seq_len.
+ */
+#pragma once
+#include <stdint.h>
+
+#if defined(__CUDACC__)
+#define B2_HD __host__ __device__ __forceinline__
+#define B2_D __device__ __forceinline__
+#else
+#define B2_HD inline
+#define B2_D inline
+#endif
+
+namespace b2 {
+
+struct alignas(16) U4 {
+    uint32_t x, y, z, w;
+};
+
+#if defined(__CUDA_ARCH__)
+B2_D U4 ld_ro(const U4 *p)
+{ /* read-only index data: non-coherent path */
+    uint4 v = __ldg(reinterpret_cast<const uint4 *>(p));
+    U4 r; r.x = v.x; r.y = v.y; r.z = v.z; r.w = v.w;
+    return r;
+}
+B2_D U4 ld_rw(const U4 *p)
+{
+    uint4 v = *reinterpret_cast<const uint4 *>(p);
+    U4 r; r.x = v.x; r.y = v.y; r.z = v.z; r.w = v.w;
+    return r;
+}
+B2_D void st_rw(U4 *p, U4 v) { *reinterpret_cast<uint4 *>(p) = make_uint4(v.x, v.y, v.z, v.w); }
+B2_D int popc32(uint32_t v) { return __popc(v); }
+B2_D int ctz32(uint32_t v) { return __ffs((int)v) - 1; }
+#else
+inline U4 ld_ro(const U4 *p) { return *p; }
+inline U4 ld_rw(const U4 *p) { return *p; }
+inline void st_rw(U4 *p, U4 v) { *p = v; }
+inline int popc32(uint32_t v) { return __builtin_popcount(v); }
+inline int ctz32(uint32_t v) { return __builtin_ctz(v); }
+#endif
+
+enum { MODE_GAPE = 0x01, MODE_COMPREAD = 0x02, MODE_LOGGAP = 0x04, MODE_NONSTOP = 0x10 };
+enum { ST_M = 0, ST_I = 1, ST_D = 2 };
+
+struct FmView {
+    const U4 *blk;    /* 2 x U4 per 64-base block */
+    uint32_t primary; /* row of the sentinel */
+    uint32_t seq_len;
+};
+
+/* Launch-constant search parameters: gap_opt_t after the batch-level clamps of
+ * bwtaln.c:89-92 (max_gapo) — per-read max_diff comes from a table. */
+struct Params {
+    int s_mm, s_gapo, s_gape;
+    int mode;
+    int indel_end_skip, max_del_occ, max_entries;
+    int max_gapo, max_gape, max_seed_diff, seed_len;
+    int max_top2;
+    int n_buckets;
+};
+
+struct Rec { /* == bwt_aln1_t */
+    uint32_t packed, k, l;
+    int32_t score;
+};
+
+/* everything a search lane needs that is constant for a launch */
+struct SearchEnv {
+    FmView fm[2]; /* fm[0] = bwt, fm[1] = rbwt */
+    Params P;
+};
+
+/* ---- packed per-position record Q[a][j] (built by the width pass) -------- */
+/* bits 0-2 base code | 3 eq(w[j-1]==w[j]) | 4 seed eq | 5 seed active (ii>0)
+ * 8-15 seed bid[ii] | 16-23 seed bid[ii-1] | 32-47 bid[j] | 48-63 bid[j-1]      */
+B2_HD uint64_t q_pack(uint32_t base, uint32_t eq, uint32_t seq, uint32_t sact, uint32_t sb, uint32_t sbp, uint32_t bid,
+                      uint32_t bidp)
+{
+    return (uint64_t)(base & 7u) | (uint64_t)(eq & 1u) << 3 | (uint64_t)(seq & 1u) << 4 | (uint64_t)(sact & 1u) << 5 |
+           (uint64_t)(sb > 255u ? 255u : sb) << 8 | (uint64_t)(sbp > 255u ? 255u : sbp) << 16 |
+           (uint64_t)(bid > 65535u ? 65535u : bid) << 32 | (uint64_t)(bidp > 65535u ? 65535u : bidp) << 48;
+}
+B2_HD int q_base(uint64_t q) { return (int)(q & 7u); }
+B2_HD int q_eq(uint64_t q) { return (int)(q >> 3 & 1u); }
+B2_HD int q_seq(uint64_t q) { return (int)(q >> 4 & 1u); }
+B2_HD int q_sact(uint64_t q) { return (int)(q >> 5 & 1u); }
+B2_HD int q_sbid(uint64_t q) { return (int)(q >> 8 & 255u); }
+B2_HD int q_sbidp(uint64_t q) { return (int)(q >> 16 & 255u); }
+B2_HD int q_bid(uint64_t q) { return (int)(q >> 32 & 65535u); }
+B2_HD int q_bidp(uint64_t q) { return (int)(q >> 48 & 65535u); }
+
+/* ------------------------------------------------------------- occ -------- */
+
+B2_HD uint32_t q_lower(const FmView &f, uint32_t k) { return k - (k > f.primary ? 1u : 0u); }
+B2_HD uint32_t q_upper(const FmView &f, uint32_t l) { return l + 1u - (l >= f.primary ? 1u : 0u); }
+
+B2_HD void occ_count4(U4 c, U4 b, uint32_t r, uint32_t o[4])
+{
+    uint32_t m0 = r >= 32u ? 0xffffffffu : ((1u << r) - 1u);
+    uint32_t m1 = r > 32u ? ((1u << (r - 32u)) - 1u) : 0u;
+    uint32_t t = (uint32_t)(popc32(b.x & b.z & m0) + popc32(b.y & b.w & m1));
+    uint32_t g = (uint32_t)(popc32(~b.x & b.z & m0) + popc32(~b.y & b.w & m1));
+    uint32_t cc = (uint32_t)(popc32(b.x & ~b.z & m0) + popc32(b.y & ~b.w & m1));
+    o[0] = c.x + (r - t - g - cc);
+    o[1] = c.y + cc;
+    o[2] = c.z + g;
+    o[3] = c.w + t;
+}
+
+/* counts (with L2 pre-added) at both ends of an interval [k,l]; one sector when
+ * both ends fall in the same 64-base block (cf. bwt.c:125,187) */
+B2_HD void occ2x4(const FmView &f, uint32_t k, uint32_t l, uint32_t ck[4], uint32_t cl[4], uint32_t &n_sectors)
+{
+    uint32_t qa = q_lower(f, k), qb = q_upper(f, l);
+    const U4 *pa = f.blk + 2 * (size_t)(qa >> 6), *pb = f.blk + 2 * (size_t)(qb >> 6);
+    U4 ca = ld_ro(pa), ba = ld_ro(pa + 1);
+    U4 cb = ca, bb = ba;
+    n_sectors = 1;
+    if (pa != pb) {
+        cb = ld_ro(pb);
+        bb = ld_ro(pb + 1);
+        n_sectors = 2;
+    }
+    occ_count4(ca, ba, qa & 63u, ck);
+    occ_count4(cb, bb, qb & 63u, cl);
+}
+
+/* ---------------------------------------------------------- width pass ---- */
+
+/* One chain of bwt_cal_width (bwtaln.c:54-78) advanced one symbol at a time so
+ * that two chains can be interleaved by the caller for memory-level
+ * parallelism. */
+struct WidthChain {
+    uint32_t k, l;
+    int bid;
+    B2_HD void reset(const FmView &f) { k = 0; l = f.seq_len; bid = 0; }
+    /* consumes symbol c; returns the width l-k+1 (and updates bid) */
+    B2_HD uint32_t step(const FmView &f, int c)
+    {
+        bool alive = false;
+        if (c < 4) {
+            uint32_t ck[4], cl[4], ns;
+            occ2x4(f, k, l, ck, cl, ns);
+            k = ck[c] + 1u;
+            l = cl[c];
+            alive = k <= l;
+        }
+        if (!alive) {
+            k = 0;
+            l = f.seq_len;
+            ++bid;
+        }
+        return l - k + 1u;
+    }
+};
+
+/* symbol i of seq[a] as the reference stores it (bwaseqio.c:189-192):
+ * seq[0] = reversed read, seq[1] = reverse-complement (plain reverse with -c) */
+B2_HD int strand_sym(const uint8_t *fwd, int len, int a, int i, bool comp)
+{
+    int c = fwd[len - 1 - i];
+    if (a == 1 && comp && c < 4) c = 3 - c;
+    return c;
+}
+
+/*
+ * Width pass for one (read, strand a): fills W[0..len] (u32 widths), the seed
+ * scratch and the packed records Q[0..len-1].  Uses index fm[a] on seq[a]
+ * (bwtaln.c:123-130).  Returns the number of ambiguous symbols in the strand.
+ */
+B2_HD int width_pass(const FmView &f, const uint8_t *fwd, int len, int a, bool comp, int seed_len, uint32_t *W,
+                     uint64_t *Q, uint32_t *seedW /* [seed_len+1] */, uint16_t *seedB /* [seed_len+1] */)
+{
+    const bool use_seed = len > seed_len;
+    const int shift = len - seed_len; /* ii = j - shift */
+    int n_amb = 0;
+    if (use_seed) {
+        WidthChain s;
+        s.reset(f);
+        for (int t = 0; t < seed_len; ++t) {
+            seedW[t] = s.step(f, strand_sym(fwd, len, a, shift + t, comp));
+            seedB[t] = (uint16_t)(s.bid > 65535 ? 65535 : s.bid);
+        }
+        seedW[seed_len] = 0;
+        seedB[seed_len] = (uint16_t)(s.bid + 1 > 65535 ? 65535 : s.bid + 1);
+    }
+    WidthChain m;
+    m.reset(f);
+    uint32_t w_prev = 0;
+    int bid_prev = 0;
+    for (int j = 0; j < len; ++j) {
+        int c = strand_sym(fwd, len, a, j, comp);
+        n_amb += c > 3;
+        uint32_t w = m.step(f, c);
+        W[j] = w;
+        int ii = j - shift;
+        uint32_t sact = 0, sb = 0, sbp = 0, seq = 0;
+        if (use_seed && ii > 0) {
+            sact = 1;
+            sb = seedB[ii];
+            sbp = seedB[ii - 1];
+            seq = seedW[ii] == seedW[ii - 1];
+        }
+        Q[j] = q_pack((uint32_t)c, j > 0 && w == w_prev, seq, sact, sb, sbp, (uint32_t)m.bid, (uint32_t)bid_prev);
+        w_prev = w;
+        bid_prev = m.bid;
+    }
+    W[len] = 0;
+    return n_amb;
+}
+
+/* gap_shadow (bwtgap.c:81-91) on the split representation, then refresh the
+ * packed records it invalidated.  bid lives in Q; w in W. */
+B2_HD void shadow_update(uint32_t x, uint32_t max, int last_diff_pos, int len, uint32_t *W, uint64_t *Q)
+{
+    int j = 0;
+    for (int i = 0; i < last_diff_pos; ++i) {
+        uint32_t w = W[i];
+        if (w > x) W[i] = w - x;
+        else if (w == x) {
+            W[i] = max - (uint32_t)(++j);
+            Q[i] = (Q[i] & ~((uint64_t)0xffff << 32)) | (uint64_t)1 << 32; /* bid[i] = 1 */
+        }
+    }
+    /* refresh eq / bid[j-1] of records 1..last_diff_pos (record ldp sees W[ldp-1]) */
+    const int last = last_diff_pos < len ? last_diff_pos : len - 1; /* Q has len records */
+    for (int i = 1; i <= last; ++i) {
+        uint64_t q = Q[i];
+        uint64_t bidp = Q[i - 1] >> 32 & 0xffffu;
+        uint64_t eq = W[i] == W[i - 1];
+        q = (q & ~((uint64_t)0xffff << 48 | (uint64_t)1 << 3)) | bidp << 48 | eq << 3;
+        Q[i] = q;
+    }
+}
+
+/* --------------------------------------------------------------- stack ---- */
+
+#define B2_NIL 0xffffffffu
+
+/* per-lane arena in global memory: entries (16 B) + link words, bump allocated
+ * (optionally with a free list through the link words, REUSE) */
+struct Arena {
+    U4 *ent;        /* [cap] k, l, i | ldp<<16, n_mm | n_gapo<<8 | n_gape<<16 | state<<24 | a<<26 */
+    uint32_t *link; /* [cap] previous entry of the same bucket */
+    uint32_t cap;
+};
+
+template <int NB>
+struct BucketHeads {
+    uint32_t head[NB];
+    uint32_t mask[(NB + 31) / 32];
+    B2_HD void clear(int nb)
+    {
+        for (int i = 0; i < nb; ++i) head[i] = B2_NIL;
+        for (int i = 0; i < (NB + 31) / 32; ++i) mask[i] = 0;
+    }
+    B2_HD int lowest(int nb) const
+    { /* lowest non-empty bucket, nb when none */
+        for (int wd = 0; wd < (NB + 31) / 32; ++wd)
+            if (mask[wd]) return wd * 32 + ctz32(mask[wd]);
+        return nb;
+    }
+};
+
+enum LaneStatus { LANE_OK = 0, LANE_ARENA_FULL = 1, LANE_REC_FULL = 2 };
+
+/*
+ * One read's best-first search (bwt_match_gap), advanced one occ lookup per
+ * step() so that the lanes of a warp stay in lock-step on the memory access.
+ *
+ * Exactness notes:
+ *  - bucket order: lowest score first, LIFO inside a bucket, children pushed
+ *    in the reference's order (insertion, deletions 0..3, mismatches j=1..3,
+ *    exact match last).
+ *  - the exact-match child has its parent's score and is pushed last, so it is
+ *    always the next pop; it is kept in registers ("held") instead of going
+ *    through memory, but is still counted in n_entries so that the
+ *    `n_entries > max_entries` cutoff (bwtgap.c:139) fires at the same pop.
+ *  - last_diff_pos: inherited from the parent on non-diff pushes (the slot
+ *    reuse of bwtgap.c:60), which requires positive penalties (checked by the
+ *    host before launch).
+ */
+template <int NB, bool REUSE>
+struct SearchLane {
+    /* constant per read */
+    const SearchEnv *env;
+    Arena ar;
+    uint64_t *Q; /* [2][strideQ] */
+    uint32_t *W; /* [2][strideW] */
+    int strideQ, strideW;
+    Rec *recs;
+    int rec_cap;
+    int len, opt_max_diff;
+    /* mutable */
+    BucketHeads<NB> bk;
+    uint32_t top, free_head; /* bump pointer / free list */
+    int n_entries;           /* the reference's stack->n_entries (memory + held) */
+    int max_diff, best_score, best_diff, best_cnt, n_aln;
+    int status;
+    bool finished;
+    /* current entry */
+    bool have_cur, cur_held, extending;
+    uint32_t ck, cl;
+    int ci, cldp, cmm, cgo, cge, cstate, ca, cscore;
+    uint32_t n_pops, n_lookups; /* instrumentation: pops and 32-byte sectors of this read */
+
+    B2_HD int score_of(int mm, int go, int ge) const
+    {
+        return mm * env->P.s_mm + go * env->P.s_gapo + ge * env->P.s_gape;
+    }
+
+    B2_HD void begin(const SearchEnv *env_, Arena ar_, uint64_t *Q_, uint32_t *W_, int strideQ_,
+                     int strideW_, Rec *recs_, int rec_cap_, int len_, int max_diff_, int n_amb)
+    {
+        const Params *P = &env_->P;
+        const FmView *fm = env_->fm;
+        env = env_; ar = ar_; Q = Q_; W = W_; strideQ = strideQ_; strideW = strideW_;
+        recs = recs_; rec_cap = rec_cap_; len = len_; opt_max_diff = max_diff_;
+        max_diff = max_diff_;
+        best_score = score_of(max_diff_ + 1, P->max_gapo + 1, P->max_gape + 1);
+        best_diff = max_diff_ + 1;
+        best_cnt = 0; n_aln = 0; status = LANE_OK;
+        finished = false; have_cur = false; cur_held = false; extending = false;
+        top = 0; free_head = B2_NIL; n_entries = 0;
+        n_pops = n_lookups = 0;
+        if (n_amb > max_diff_) { finished = true; return; } /* bwtgap.c:117-122 */
+        bk.clear(P->n_buckets);
+        /* roots: strand 0 then strand 1 (bwtgap.c:126-127) -> strand 1 pops first */
+        push(0, len, 0, fm[0].seq_len, 0, 0, 0, ST_M, 0);
+        push(1, len, 0, fm[0].seq_len, 0, 0, 0, ST_M, 0);
+    }
+
+    B2_HD void push(int a, int i, uint32_t k, uint32_t l, int mm, int go, int ge, int state, int ldp)
+    {
+        int sc = score_of(mm, go, ge);
+        uint32_t slot;
+        if (REUSE && free_head != B2_NIL) {
+            slot = free_head;
+            free_head = ar.link[slot];
+        } else {
+            if (top >= ar.cap) { status = LANE_ARENA_FULL; finished = true; return; }
+            slot = top++;
+        }
+        U4 e;
+        e.x = k; e.y = l;
+        e.z = (uint32_t)i | (uint32_t)ldp << 16;
+        e.w = (uint32_t)mm | (uint32_t)go << 8 | (uint32_t)ge << 16 | (uint32_t)state << 24 | (uint32_t)a << 26;
+        st_rw(ar.ent + slot, e);
+        ar.link[slot] = bk.head[sc];
+        bk.head[sc] = slot;
+        bk.mask[sc >> 5] |= 1u << (sc & 31);
+        ++n_entries;
+    }
+
+    B2_HD void pop_mem()
+    {
+        int b = bk.lowest(env->P.n_buckets);
+        uint32_t slot = bk.head[b];
+        U4 e = ld_rw(ar.ent + slot);
+        uint32_t prev = ar.link[slot];
+        bk.head[b] = prev;
+        if (prev == B2_NIL) bk.mask[b >> 5] &= ~(1u << (b & 31));
+        if (REUSE) { ar.link[slot] = free_head; free_head = slot; }
+        --n_entries;
+        ck = e.x; cl = e.y;
+        ci = (int)(e.z & 0xffffu); cldp = (int)(e.z >> 16);
+        cmm = (int)(e.w & 255u); cgo = (int)(e.w >> 8 & 255u); cge = (int)(e.w >> 16 & 255u);
+        cstate = (int)(e.w >> 24 & 3u); ca = (int)(e.w >> 26 & 1u);
+        cscore = b;
+    }
+
+    /* hit bookkeeping, bwtgap.c:165-198; returns false when the search must stop */
+    B2_HD bool on_hit()
+    {
+        const Params *P = &env->P;
+        const FmView &f = env->fm[1 - ca];
+        const bool gape_mode = P->mode & MODE_GAPE;
+        if (n_aln == 0) {
+            best_score = cscore;
+            best_diff = cmm + cgo + (gape_mode ? cge : 0);
+            if (!(P->mode & MODE_NONSTOP)) max_diff = best_diff + 1 > opt_max_diff ? opt_max_diff : best_diff + 1;
+        }
+        if (cscore == best_score) best_cnt = (int)((uint32_t)best_cnt + (cl - ck + 1u));
+        else if (best_cnt > P->max_top2) return false;
+        bool add = true;
+        if (cgo)
+            for (int j = 0; j < n_aln; ++j)
+                if (recs[j].k == ck && recs[j].l == cl) { add = false; break; }
+        if (add) {
+            shadow_update(cl - ck + 1u, f.seq_len, cldp, len, W + (size_t)ca * strideW, Q + (size_t)ca * strideQ);
+            if (n_aln >= rec_cap) { status = LANE_REC_FULL; return false; }
+            Rec r;
+            r.packed = (uint32_t)cmm | (uint32_t)cgo << 8 | (uint32_t)cge << 16 | (uint32_t)ca << 24;
+            r.k = ck; r.l = cl; r.score = cscore;
+            recs[n_aln++] = r;
+        }
+        return true;
+    }
+
+    /* Advance until exactly one occ lookup has been issued (or the search ends). */
+    B2_HD void step()
+    {
+        const Params *P = &env->P;
+        const FmView *fm = env->fm;
+        const bool gape_mode = P->mode & MODE_GAPE, nonstop = P->mode & MODE_NONSTOP;
+        uint64_t q = 0;
+        int m = 0;
+        for (;;) { /* pop until something needs a lookup */
+            if (extending) { q = Q[(size_t)ca * strideQ + (ci - 1)]; break; }
+            if (!have_cur) {
+                if (n_entries == 0) { finished = true; return; }
+                if (n_entries > P->max_entries) { finished = true; return; }
+                pop_mem();
+            } else { /* held exact child: same accounting as a push followed by a pop */
+                if (n_entries > P->max_entries) { finished = true; return; }
+                --n_entries;
+            }
+            have_cur = false;
+            ++n_pops;
+            if (!nonstop && cscore > best_score + P->s_mm) { finished = true; return; }
+            m = max_diff - cmm - cgo - (gape_mode ? cge : 0);
+            if (m < 0) continue;
+            if (ci > 0) {
+                q = Q[(size_t)ca * strideQ + (ci - 1)];
+                if (m < q_bid(q)) continue;
+            }
+            if (ci == 0) {
+                if (!on_hit()) { finished = true; return; }
+                continue;
+            }
+            if (m == 0 && (cstate == ST_M || gape_mode || cge == P->max_gape)) extending = true;
+            break;
+        }
+
+        const FmView &f = fm[1 - ca];
+        const int i = ci - 1;
+        const int base = q_base(q);
+        uint32_t cntk[4], cntl[4], ns;
+
+        if (extending) { /* one step of bwt_match_exact_alt (bwt.c:235-250) */
+            if (base > 3) { extending = false; return; }
+            occ2x4(f, ck, cl, cntk, cntl, ns);
+            n_lookups += ns;
+            ck = cntk[base] + 1u;
+            cl = cntl[base];
+            if (ck > cl) { extending = false; return; }
+            ci = i;
+            if (ci == 0) {
+                extending = false;
+                if (!on_hit()) finished = true;
+            }
+            return;
+        }
+
+        occ2x4(f, ck, cl, cntk, cntl, ns);
+        n_lookups += ns;
+        const uint32_t occ = cl - ck + 1u;
+        bool allow_diff = true, allow_M = true;
+        if (i > 0) {
+            if (q_bidp(q) > m - 1) allow_diff = false;
+            else if (q_bidp(q) == m - 1 && q_bid(q) == m - 1 && q_eq(q)) allow_M = false;
+            if (q_sact(q)) {
+                int m_seed = P->max_seed_diff - cmm - cgo - (gape_mode ? cge : 0);
+                if (q_sbidp(q) > m_seed - 1) allow_diff = false;
+                else if (q_sbidp(q) == m_seed - 1 && q_sbid(q) == m_seed - 1 && q_seq(q)) allow_M = false;
+            }
+        }
+        int gaps;
+        if (P->mode & MODE_LOGGAP) {
+            uint32_t v = (uint32_t)(cge + cgo);
+            int lg = 0;
+            while (v > 1u) { v >>= 1; ++lg; }
+            gaps = lg / 2 + 1;
+        } else gaps = cgo + cge;
+
+        if (allow_diff && i >= P->indel_end_skip + gaps && len - i >= P->indel_end_skip + gaps) {
+            if (cstate == ST_M) {
+                if (cgo < P->max_gapo) {
+                    push(ca, i, ck, cl, cmm, cgo + 1, cge, ST_I, i);
+                    for (int j = 0; j < 4; ++j) {
+                        uint32_t nk = cntk[j] + 1u, nl = cntl[j];
+                        if (nk <= nl) push(ca, i + 1, nk, nl, cmm, cgo + 1, cge, ST_D, i + 1);
+                    }
+                }
+            } else if (cstate == ST_I) {
+                if (cge < P->max_gape) push(ca, i, ck, cl, cmm, cgo, cge + 1, ST_I, i);
+            } else {
+                if (cge < P->max_gape && (cge + cgo < max_diff || occ < (uint32_t)P->max_del_occ))
+                    for (int j = 0; j < 4; ++j) {
+                        uint32_t nk = cntk[j] + 1u, nl = cntl[j];
+                        if (nk <= nl) push(ca, i + 1, nk, nl, cmm, cgo, cge + 1, ST_D, i + 1);
+                    }
+            }
+        }
+        if (finished) return; /* arena overflow */
+
+        bool child = false;
+        if (allow_diff && allow_M) {
+            for (int j = 1; j <= 3; ++j) {
+                int c = (base + j) & 3;
+                uint32_t nk = cntk[c] + 1u, nl = cntl[c];
+                if (nk <= nl) push(ca, i, nk, nl, cmm + 1, cgo, cge, ST_M, i);
+            }
+            if (base > 3) { /* ambiguous base: the j == 4 child is a mismatch too */
+                int c = base & 3;
+                uint32_t nk = cntk[c] + 1u, nl = cntl[c];
+                if (nk <= nl) push(ca, i, nk, nl, cmm + 1, cgo, cge, ST_M, i);
+            } else child = true;
+        } else if (base < 4) child = true;
+        if (finished) return;
+
+        if (child) { /* exact-match child: held in registers, counted like a push */
+            uint32_t nk = cntk[base] + 1u, nl = cntl[base];
+            if (nk <= nl) {
+                ck = nk; cl = nl; ci = i; cstate = ST_M; /* counters, score, ldp, strand inherited */
+                have_cur = true;
+                ++n_entries;
+            }
+        }
+    }
+};
+
+} // namespace b2

@@ -1,0 +1,405 @@
+/*
+ * aln_host.cpp — host side of the drop-in boundary: read input, the batch loop,
+ * the .sai writer, the `aln` command line, and the bwa_seq_t seam.
+ *
+ * Reference interfaces replaced (file:line under the reference tree):
+ *   bwa_aln            bwtaln.c:243-328   -> b200aln_aln_main
+ *   bwa_aln_core       bwtaln.c:173-241   -> b200aln_aln_core
+ *   bwa_read_seq       bwaseqio.c:145-208 -> SeqReader::next_batch (FASTA/FASTQ, gz)
+ *   kseq_read          kseq.h:150-194     -> SeqReader::read_record
+ *   bwa_trim_read      bwaseqio.c:74-87   -> trim_len
+ *   bwa_cal_sa_reg_gap bwtaln.c:80-140    -> b200aln_cal_sa_reg_gap (on bwa_seq_t)
+ * Compute happens in b200aln.cu; nothing here searches the index.
+ */
+#include <ctype.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+#include <time.h>
+#include <unistd.h>
+#include <zlib.h>
+
+#include <string>
+#include <vector>
+
+#include "../../include/b200aln.h"
+#include "host_params.h"
+
+namespace {
+
+enum {
+    BWA_MODE_GAPE = 0x01, BWA_MODE_COMPREAD = 0x02, BWA_MODE_LOGGAP = 0x04, BWA_MODE_NONSTOP = 0x10,
+    BWA_MODE_BAM = 0x20, BWA_MODE_BAM_SE = 0x40, BWA_MODE_BAM_READ1 = 0x80, BWA_MODE_BAM_READ2 = 0x100,
+    BWA_MODE_IL13 = 0x200
+};
+const int BWA_MIN_RDLEN = 35;
+const double BWA_AVG_ERR = 0.02;
+
+/* nt4 code of a character (bntseq.c:39-56): ACGT/acgt -> 0-3, '-' -> 5, other -> 4 */
+struct Nt4Table {
+    uint8_t t[256];
+    Nt4Table()
+    {
+        memset(t, 4, sizeof t);
+        t['A'] = t['a'] = 0; t['C'] = t['c'] = 1; t['G'] = t['g'] = 2; t['T'] = t['t'] = 3;
+        t['-'] = 5;
+    }
+};
+const Nt4Table g_nt4;
+
+/* buffered reader + record parser with the reference parser's observable
+ * behaviour (kseq.h:60-71,150-194): multi-line records, name = first
+ * whitespace-delimited token, only isgraph() characters enter the sequence,
+ * reading stops at the first truncated record. */
+class SeqReader {
+  public:
+    explicit SeqReader(const char *fn) : buf_(1 << 20)
+    {
+        if (strcmp(fn, "-") == 0) f_ = gzdopen(fileno(stdin), "r"); /* utils.c:56-66 */
+        else f_ = gzopen(fn, "r");
+        if (!f_) b2host::fatal("b200aln_aln_core", (std::string("fail to open file '") + fn + "'.").c_str());
+    }
+    ~SeqReader() { if (f_) gzclose(f_); }
+
+    /* returns sequence length, -1 at end of file, -2 on a truncated quality string */
+    int read_record()
+    {
+        int c;
+        if (last_char_ == 0) {
+            while ((c = getc()) != -1 && c != '>' && c != '@') {}
+            if (c == -1) return -1;
+            last_char_ = c;
+        }
+        seq_.clear();
+        qual_.clear();
+        if (get_until(0, name_, &c) < 0) return -1;
+        if (c != '\n') {
+            std::string comment;
+            get_until('\n', comment, nullptr);
+        }
+        while ((c = getc()) != -1 && c != '>' && c != '+' && c != '@')
+            if (isgraph(c)) seq_.push_back((char)c);
+        if (c == '>' || c == '@') last_char_ = c;
+        if (c != '+') return (int)seq_.size();
+        while ((c = getc()) != -1 && c != '\n') {}
+        if (c == -1) return -2;
+        while ((c = getc()) != -1 && qual_.size() < seq_.size())
+            if (c >= 33 && c <= 127) qual_.push_back((char)c);
+        last_char_ = 0;
+        if (seq_.size() != qual_.size()) return -2;
+        return (int)seq_.size();
+    }
+
+    const std::string &seq() const { return seq_; }
+    std::string &seq_mut() { return seq_; }
+    std::string &qual_mut() { return qual_; }
+    const std::string &name() const { return name_; }
+
+  private:
+    int getc()
+    {
+        if (is_eof_ && begin_ >= end_) return -1;
+        if (begin_ >= end_) {
+            begin_ = 0;
+            end_ = gzread(f_, buf_.data(), (unsigned)buf_.size());
+            if (end_ < (int)buf_.size()) is_eof_ = true;
+            if (end_ <= 0) { end_ = 0; return -1; }
+        }
+        return (int)buf_[begin_++];
+    }
+    int get_until(int delim, std::string &str, int *dret)
+    {
+        if (dret) *dret = 0;
+        str.clear();
+        if (begin_ >= end_ && is_eof_) return -1;
+        for (;;) {
+            if (begin_ >= end_) {
+                if (is_eof_) break;
+                begin_ = 0;
+                end_ = gzread(f_, buf_.data(), (unsigned)buf_.size());
+                if (end_ < (int)buf_.size()) is_eof_ = true;
+                if (end_ <= 0) { end_ = 0; break; }
+            }
+            int i = begin_;
+            if (delim) while (i < end_ && buf_[i] != delim) ++i;
+            else while (i < end_ && !isspace(buf_[i])) ++i;
+            str.append((const char *)buf_.data() + begin_, (size_t)(i - begin_));
+            begin_ = i + 1;
+            if (i < end_) {
+                if (dret) *dret = buf_[i];
+                break;
+            }
+        }
+        return (int)str.size();
+    }
+
+    gzFile f_ = nullptr;
+    std::vector<unsigned char> buf_;
+    int begin_ = 0, end_ = 0;
+    bool is_eof_ = false;
+    int last_char_ = 0;
+    std::string name_, seq_, qual_;
+};
+
+/* bwa_trim_read (bwaseqio.c:74-87): length kept */
+int trim_len(int trim_qual, int len, const char *qual)
+{
+    int s = 0, best = 0, best_l = len - 1;
+    if (trim_qual < 1 || qual == nullptr) return len;
+    for (int l = len - 1; l >= BWA_MIN_RDLEN - 1; --l) {
+        s += trim_qual - ((unsigned char)qual[l] - 33);
+        if (s < 0) break;
+        if (s > best) { best = s; best_l = l; }
+    }
+    return best_l + 1;
+}
+
+struct PackedBatch {
+    std::vector<int32_t> lens;
+    std::vector<int64_t> offs;
+    std::vector<uint8_t> codes;
+    long n_trimmed = 0, n_tot = 0;
+    void clear() { lens.clear(); offs.clear(); codes.clear(); n_trimmed = n_tot = 0; }
+};
+
+/* bwa_read_seq (bwaseqio.c:145-208) into the packed form; returns reads stored */
+int next_batch(SeqReader &rd, int n_needed, int mode, int trim_qual, PackedBatch &b)
+{
+    const bool is_64 = mode & BWA_MODE_IL13;
+    const int l_bc = (mode >> 24) & 0xff;
+    b.clear();
+    if (l_bc > 15) {
+        fprintf(stderr, "[bwa_read_seq] the maximum barcode length is 15.\n");
+        return 0;
+    }
+    int l;
+    while ((l = rd.read_record()) >= 0) {
+        std::string &s = rd.seq_mut(), &q = rd.qual_mut();
+        if (is_64) for (char &ch : q) ch = (char)(ch - 31);
+        if ((int)s.size() <= l_bc) continue;
+        if (l_bc) {
+            s.erase(0, (size_t)l_bc);
+            if (!q.empty()) q.erase(0, (size_t)l_bc);
+        }
+        const int full = (int)s.size();
+        int len = full;
+        b.n_tot += full;
+        if (!q.empty() && trim_qual >= 1) {
+            len = trim_len(trim_qual, full, q.data());
+            b.n_trimmed += full - len;
+        }
+        b.offs.push_back((int64_t)b.codes.size());
+        b.lens.push_back(len);
+        for (int i = 0; i < full; ++i) b.codes.push_back(g_nt4.t[(unsigned char)s[i]]);
+        if ((int)b.lens.size() == n_needed) break;
+    }
+    if (!b.lens.empty() && trim_qual >= 1)
+        fprintf(stderr, "[bwa_read_seq] %.1f%% bases are trimmed.\n", 100.0f * b.n_trimmed / b.n_tot);
+    return (int)b.lens.size();
+}
+
+/* mirror of the reference's bwa_seq_t (bwtaln.h:72-104) for the batch seam */
+struct RefAln1 { uint32_t packed, k, l; int32_t score; };
+struct RefSeq {
+    char *name;
+    uint8_t *seq, *rseq, *qual;
+    uint32_t len : 20, strand : 1, type : 2, dummy : 1, extra_flag : 8;
+    uint32_t n_mm : 8, n_gapo : 8, n_gape : 8, mapQ : 8;
+    int score;
+    int clip_len;
+    int n_aln;
+    RefAln1 *aln;
+    int n_multi;
+    void *multi;
+    uint32_t sa;
+    uint64_t pos;
+    uint64_t remapped_pos;
+    uint32_t dbidx;
+    uint32_t remapped_dbidx;
+    int32_t remapped_seqid;
+    int remap_identical;
+    uint64_t c1 : 28, c2 : 28, seQ : 8;
+    int n_cigar;
+    uint32_t *cigar;
+    int tid;
+    char bc[16];
+    uint32_t full_len : 20, nm : 12;
+    char *md;
+};
+static_assert(sizeof(RefSeq) == 176, "bwa_seq_t is 176 bytes on LP64 (bwtaln.h:72-104)");
+
+} // namespace
+
+extern "C" void b200aln_seq_layout(b200aln_seq_layout_t *o)
+{
+    o->size = sizeof(RefSeq);
+    o->off_name = offsetof(RefSeq, name);
+    o->off_seq = offsetof(RefSeq, seq);
+    o->off_rseq = offsetof(RefSeq, rseq);
+    o->off_qual = offsetof(RefSeq, qual);
+    o->off_lenword = offsetof(RefSeq, qual) + sizeof(void *);
+    o->off_n_aln = offsetof(RefSeq, n_aln);
+    o->off_aln = offsetof(RefSeq, aln);
+    o->off_sa = offsetof(RefSeq, sa);
+    o->off_c1c2 = offsetof(RefSeq, remap_identical) + sizeof(int);
+}
+
+extern "C" void b200aln_cal_sa_reg_gap(b200aln_ctx *ctx, int n_seqs, void *seqs_, const b200aln_opt_t *opt)
+{
+    RefSeq *seqs = (RefSeq *)seqs_;
+    std::vector<int32_t> lens((size_t)n_seqs), n_aln((size_t)n_seqs);
+    std::vector<int64_t> offs((size_t)n_seqs);
+    std::vector<uint8_t> codes;
+    for (int r = 0; r < n_seqs; ++r) {
+        RefSeq *p = seqs + r;
+        const int len = (int)p->len;
+        lens[r] = len;
+        offs[r] = (int64_t)codes.size();
+        /* p->seq is the read reversed (bwaseqio.c:190); undo it */
+        for (int j = 0; j < len; ++j) codes.push_back(p->seq[len - 1 - j]);
+    }
+    int64_t total = 0;
+    const b200aln_rec_t *rec = b200aln_batch(ctx, n_seqs, lens.data(), offs.data(), codes.data(), opt, n_aln.data(), &total);
+    int64_t at = 0;
+    for (int r = 0; r < n_seqs; ++r) {
+        RefSeq *p = seqs + r;
+        p->sa = 0; p->type = 0; p->c1 = p->c2 = 0; /* bwtaln.c:114 */
+        p->n_aln = n_aln[r];
+        int cap = 4;
+        while (cap < n_aln[r]) cap <<= 1; /* the reference's growth policy (bwtgap.c:113,187-191) */
+        p->aln = (RefAln1 *)calloc((size_t)cap, sizeof(RefAln1));
+        if (n_aln[r]) memcpy(p->aln, rec + at, sizeof(RefAln1) * (size_t)n_aln[r]);
+        at += n_aln[r];
+        free(p->name); free(p->seq); free(p->rseq); free(p->qual); /* bwtaln.c:134-135 */
+        p->name = nullptr; p->seq = p->rseq = p->qual = nullptr;
+    }
+}
+
+extern "C" int64_t b200aln_aln_core(const char *prefix, const char *fn_fa, const b200aln_opt_t *opt, int out_fd,
+                                    int device)
+{
+    if (opt->mode & BWA_MODE_BAM)
+        b2host::fatal("b200aln_aln_core", "BAM input (-b) is not implemented in this engine; convert to FASTQ.");
+    SeqReader rd(fn_fa);
+    b200aln_ctx *ctx = b200aln_open_prefix(prefix, device < 0 ? 0 : device);
+    FILE *out = fdopen(dup(out_fd), "wb");
+    if (!out) b2host::fatal("b200aln_aln_core", "cannot open the output descriptor.");
+    fwrite(opt, sizeof(b200aln_opt_t), 1, out); /* bwtaln.c:192 */
+    PackedBatch b;
+    std::vector<int32_t> n_aln;
+    int64_t tot_seqs = 0;
+    int n;
+    while ((n = next_batch(rd, 0x40000, opt->mode, opt->trim_qual, b)) != 0) {
+        tot_seqs += n;
+        struct timespec t0, t1;
+        clock_gettime(CLOCK_MONOTONIC, &t0);
+        fprintf(stderr, "[bwa_aln_core] calculate SA coordinate... ");
+        n_aln.resize((size_t)n);
+        int64_t total = 0;
+        const b200aln_rec_t *rec =
+            b200aln_batch(ctx, n, b.lens.data(), b.offs.data(), b.codes.data(), opt, n_aln.data(), &total);
+        clock_gettime(CLOCK_MONOTONIC, &t1);
+        fprintf(stderr, "%.2f sec\n", (t1.tv_sec - t0.tv_sec) + 1e-9 * (t1.tv_nsec - t0.tv_nsec));
+        fprintf(stderr, "[bwa_aln_core] write to the disk... ");
+        clock_gettime(CLOCK_MONOTONIC, &t0);
+        int64_t at = 0;
+        for (int r = 0; r < n; ++r) { /* bwtaln.c:227-231 */
+            fwrite(&n_aln[r], 4, 1, out);
+            if (n_aln[r]) fwrite(rec + at, sizeof(b200aln_rec_t), (size_t)n_aln[r], out);
+            at += n_aln[r];
+        }
+        clock_gettime(CLOCK_MONOTONIC, &t1);
+        fprintf(stderr, "%.2f sec\n", (t1.tv_sec - t0.tv_sec) + 1e-9 * (t1.tv_nsec - t0.tv_nsec));
+        fprintf(stderr, "[bwa_aln_core] %lld sequences have been processed.\n", (long long)tot_seqs);
+    }
+    fclose(out);
+    b200aln_close(ctx);
+    return tot_seqs;
+}
+
+extern "C" int b200aln_aln_main(int argc, char *argv[])
+{ /* bwa_aln, bwtaln.c:243-328 */
+    int c, opte = -1;
+    b200aln_opt_t o;
+    b200aln_opt_init(&o);
+    optind = 1;
+    while ((c = getopt(argc, argv, "n:o:e:i:d:l:k:cLR:m:t:NM:O:E:q:f:b012IB:")) >= 0) {
+        switch (c) {
+        case 'n':
+            if (strstr(optarg, ".")) { o.fnr = (float)atof(optarg); o.max_diff = -1; }
+            else { o.max_diff = atoi(optarg); o.fnr = -1.0f; }
+            break;
+        case 'o': o.max_gapo = atoi(optarg); break;
+        case 'e': opte = atoi(optarg); break;
+        case 'M': o.s_mm = atoi(optarg); break;
+        case 'O': o.s_gapo = atoi(optarg); break;
+        case 'E': o.s_gape = atoi(optarg); break;
+        case 'd': o.max_del_occ = atoi(optarg); break;
+        case 'i': o.indel_end_skip = atoi(optarg); break;
+        case 'l': o.seed_len = atoi(optarg); break;
+        case 'k': o.max_seed_diff = atoi(optarg); break;
+        case 'm': o.max_entries = atoi(optarg); break;
+        case 't': o.n_threads = atoi(optarg); break;
+        case 'L': o.mode |= BWA_MODE_LOGGAP; break;
+        case 'R': o.max_top2 = atoi(optarg); break;
+        case 'q': o.trim_qual = atoi(optarg); break;
+        case 'c': o.mode &= ~BWA_MODE_COMPREAD; break;
+        case 'N': o.mode |= BWA_MODE_NONSTOP; o.max_top2 = 0x7fffffff; break;
+        case 'f':
+            if (freopen(optarg, "wb", stdout) == nullptr) {
+                fprintf(stderr, "[bwa_aln] fail to open file '%s': ", optarg);
+                perror(nullptr);
+                fprintf(stderr, "Abort!\n");
+                abort();
+            }
+            break;
+        case 'b': o.mode |= BWA_MODE_BAM; break;
+        case '0': o.mode |= BWA_MODE_BAM_SE; break;
+        case '1': o.mode |= BWA_MODE_BAM_READ1; break;
+        case '2': o.mode |= BWA_MODE_BAM_READ2; break;
+        case 'I': o.mode |= BWA_MODE_IL13; break;
+        case 'B': o.mode |= atoi(optarg) << 24; break;
+        default: return 1;
+        }
+    }
+    if (opte > 0) {
+        o.max_gape = opte;
+        o.mode &= ~BWA_MODE_GAPE;
+    }
+    if (optind + 2 > argc) {
+        fprintf(stderr, "\nUsage:   b200aln aln [options] <prefix> <in.fq>\n\n");
+        fprintf(stderr, "Options: -n NUM    max #diff (int) or missing prob under %.2f err rate (float) [%.2f]\n", BWA_AVG_ERR, o.fnr);
+        fprintf(stderr, "         -o INT    maximum number or fraction of gap opens [%d]\n", o.max_gapo);
+        fprintf(stderr, "         -e INT    maximum number of gap extensions, -1 for disabling long gaps [-1]\n");
+        fprintf(stderr, "         -i INT    do not put an indel within INT bp towards the ends [%d]\n", o.indel_end_skip);
+        fprintf(stderr, "         -d INT    maximum occurrences for extending a long deletion [%d]\n", o.max_del_occ);
+        fprintf(stderr, "         -l INT    seed length [%d]\n", o.seed_len);
+        fprintf(stderr, "         -k INT    maximum differences in the seed [%d]\n", o.max_seed_diff);
+        fprintf(stderr, "         -m INT    maximum entries in the queue [%d]\n", o.max_entries);
+        fprintf(stderr, "         -t INT    number of threads (recorded in the header; the GPU engine ignores it) [%d]\n", o.n_threads);
+        fprintf(stderr, "         -M INT    mismatch penalty [%d]\n", o.s_mm);
+        fprintf(stderr, "         -O INT    gap open penalty [%d]\n", o.s_gapo);
+        fprintf(stderr, "         -E INT    gap extension penalty [%d]\n", o.s_gape);
+        fprintf(stderr, "         -R INT    stop searching when there are >INT equally best hits [%d]\n", o.max_top2);
+        fprintf(stderr, "         -q INT    quality threshold for read trimming down to %dbp [%d]\n", BWA_MIN_RDLEN, o.trim_qual);
+        fprintf(stderr, "         -f FILE   file to write output to instead of stdout\n");
+        fprintf(stderr, "         -B INT    length of barcode\n");
+        fprintf(stderr, "         -c        input sequences are in the color space\n");
+        fprintf(stderr, "         -L        log-scaled gap penalty for long deletions\n");
+        fprintf(stderr, "         -N        non-iterative mode: search for all n-difference hits (slooow)\n");
+        fprintf(stderr, "         -I        the input is in the Illumina 1.3+ FASTQ-like format\n");
+        fprintf(stderr, "         -b        the input read file is in the BAM format (not implemented)\n\n");
+        return 1;
+    }
+    if (o.fnr > 0.0f) { /* bwtaln.c:317-324 */
+        for (int i = 17, k = 0; i <= 250; ++i) {
+            int l = b200aln_cal_maxdiff(i, BWA_AVG_ERR, o.fnr);
+            if (l != k) fprintf(stderr, "[bwa_aln] %dbp reads: max_diff = %d\n", i, l);
+            k = l;
+        }
+    }
+    fflush(stdout);
+    b200aln_aln_core(argv[optind], argv[optind + 1], &o, fileno(stdout), 0);
+    return 0;
+}

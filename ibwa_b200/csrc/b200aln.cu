@@ -1,0 +1,722 @@
+/*
+ * b200aln.cu — CUDA kernels (sm_100a) and the C ABI of include/b200aln.h.
+ *
+ * Data flow of one batch (replaces bwa_cal_sa_reg_gap, bwtaln.c:80-140):
+ *   H2D (lens, offs, codes)                         pinned/pageable host -> HBM
+ *   k_width   : one thread per (read, strand)       bwt_cal_width x4  -> W, Q
+ *   k_search  : persistent lanes, one read per lane bwt_match_gap     -> record slabs
+ *   k_search (large arena) for flagged reads        same state machine, free-list arena
+ *   k_scan*   : exclusive sum of n_aln              -> record offsets
+ *   k_compact : slabs -> packed records in read order
+ *   D2H (n_aln, records)
+ *
+ * The per-read state machines are in aln_core.cuh (shared with the CPU logic
+ * tests); this file owns memory, launches and warp-level work distribution.
+ * There is no CPU fallback anywhere in this library.
+ */
+#include <cuda_runtime.h>
+#include <stdarg.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+
+#include <string>
+#include <vector>
+
+#include "../../include/b200aln.h"
+#include "aln_core.cuh"
+#include "fm_layout.cuh"
+#include "host_params.h"
+
+using namespace b2;
+
+#define CK(call)                                                                                               \
+    do {                                                                                                       \
+        cudaError_t e_ = (call);                                                                               \
+        if (e_ != cudaSuccess) {                                                                               \
+            fprintf(stderr, "[b200aln] CUDA error %s at %s:%d (%s). Abort!\n", cudaGetErrorString(e_), __FILE__, \
+                    __LINE__, #call);                                                                          \
+            abort();                                                                                           \
+        }                                                                                                      \
+    } while (0)
+
+static_assert(sizeof(b200aln_opt_t) == 64, "gap_opt_t is 64 bytes (bwtaln.h:105-115)");
+static_assert(sizeof(b200aln_rec_t) == 16 && sizeof(Rec) == 16, "bwt_aln1_t is 16 bytes (bwtaln.h:34-38)");
+
+/* ------------------------------------------------------------ kernels ---- */
+
+__global__ void k_convert_index(RefBwt r, U4 *out, uint64_t nb)
+{
+    for (uint64_t b = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; b < nb; b += (uint64_t)gridDim.x * blockDim.x) {
+        U4 t[2];
+        fm_convert_block(r, b, t);
+        out[2 * b] = t[0];
+        out[2 * b + 1] = t[1];
+    }
+}
+
+struct WidthArgs {
+    FmView fm[2];
+    int n_reads;
+    const int32_t *lens;
+    const int64_t *offs;
+    const uint8_t *codes;
+    int comp, seed_len, strideQ, strideW;
+    uint64_t *Q;
+    uint32_t *W;
+    uint32_t *seedW;
+    uint16_t *seedB;
+    int32_t *n_amb;
+};
+
+__global__ void __launch_bounds__(128) k_width(const __grid_constant__ WidthArgs A)
+{
+    const int nthreads = gridDim.x * blockDim.x, tid = blockIdx.x * blockDim.x + threadIdx.x;
+    uint32_t *sW = A.seedW + (size_t)tid * (A.seed_len + 1);
+    uint16_t *sB = A.seedB + (size_t)tid * (A.seed_len + 1);
+    for (int64_t t = tid; t < 2 * (int64_t)A.n_reads; t += nthreads) {
+        const int r = (int)(t >> 1), a = (int)(t & 1);
+        int n = width_pass(A.fm[a], A.codes + A.offs[r], A.lens[r], a, A.comp != 0, A.seed_len,
+                           A.W + (size_t)t * A.strideW, A.Q + (size_t)t * A.strideQ, sW, sB);
+        if (a == 0) A.n_amb[r] = n;
+    }
+}
+
+struct SearchArgs {
+    SearchEnv env;
+    int n_work;
+    const int32_t *work_list; /* null: work item w is read w */
+    const int32_t *lens;
+    const int32_t *n_amb;
+    const int32_t *md; /* max_diff by read length */
+    uint64_t *Q;
+    uint32_t *W;
+    int strideQ, strideW;
+    U4 *ent;
+    uint32_t *link;
+    uint32_t arena_cap;
+    Rec *recs;
+    int rec_cap;
+    int recs_by_work; /* slab index: work item (large pass) or read (fast pass) */
+    int32_t *n_aln;
+    int32_t *over_slot; /* large pass: over_slot[r] = work item */
+    unsigned int *counter;
+    unsigned int *n_over;
+    int32_t *over_list;
+    unsigned long long *stat; /* [0] pops, [1] sectors */
+};
+
+template <int NB, bool REUSE>
+__global__ void __launch_bounds__(128) k_search(const __grid_constant__ SearchArgs A)
+{
+    const unsigned FULL = 0xffffffffu;
+    const int lane = threadIdx.x & 31;
+    const size_t gl = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    Arena ar;
+    ar.ent = A.ent + gl * A.arena_cap;
+    ar.link = A.link + gl * A.arena_cap;
+    ar.cap = A.arena_cap;
+    SearchLane<NB, REUSE> L;
+    L.finished = true;
+    bool alive = true, active = false;
+    int r = -1;
+    unsigned w = 0;
+    unsigned long long pops = 0, sectors = 0;
+
+    while (__any_sync(FULL, alive)) {
+        const bool need = alive && !active;
+        const unsigned m = __ballot_sync(FULL, need);
+        if (m) { /* warp-aggregated claim of the next reads */
+            const int leader = __ffs((int)m) - 1;
+            unsigned base = 0;
+            if (lane == leader) base = atomicAdd(A.counter, (unsigned)__popc(m));
+            base = __shfl_sync(FULL, base, leader);
+            if (need) {
+                w = base + (unsigned)__popc(m & ((1u << lane) - 1u));
+                if (w < (unsigned)A.n_work) {
+                    r = A.work_list ? A.work_list[w] : (int)w;
+                    const int len = A.lens[r];
+                    const size_t slab = A.recs_by_work ? (size_t)w : (size_t)r;
+                    L.begin(&A.env, ar, A.Q + (size_t)2 * r * A.strideQ, A.W + (size_t)2 * r * A.strideW, A.strideQ,
+                            A.strideW, A.recs + slab * A.rec_cap, A.rec_cap, len, A.md[len], A.n_amb[r]);
+                    active = true;
+                } else alive = false;
+            }
+        }
+        if (active) {
+            if (!L.finished) L.step();
+            if (L.finished) {
+                pops += L.n_pops;
+                sectors += L.n_lookups;
+                if (L.status != LANE_OK) {
+                    A.n_aln[r] = 0;
+                    if (A.over_list) {
+                        unsigned idx = atomicAdd(A.n_over, 1u);
+                        A.over_list[idx] = r;
+                    } else A.n_aln[r] = -L.status; /* the large pass overflowed too: reported by the host */
+                } else {
+                    A.n_aln[r] = L.n_aln;
+                    if (A.over_slot) A.over_slot[r] = (int32_t)w;
+                }
+                active = false;
+            }
+        }
+    }
+    if (pops) {
+        atomicAdd(A.stat + 0, pops);
+        atomicAdd(A.stat + 1, sectors);
+    }
+}
+
+/* exclusive prefix sum of n_aln (int32) into int64 offsets: block totals, their scan, then local scans */
+#define SCAN_ITEMS 2048
+__global__ void __launch_bounds__(256) k_scan_totals(const int32_t *in, int n, int64_t *block_tot)
+{
+    __shared__ int64_t sh[256];
+    int64_t s = 0;
+    const int base = blockIdx.x * SCAN_ITEMS;
+    for (int i = threadIdx.x; i < SCAN_ITEMS; i += 256) {
+        int idx = base + i;
+        if (idx < n) s += in[idx] > 0 ? in[idx] : 0;
+    }
+    sh[threadIdx.x] = s;
+    __syncthreads();
+    for (int st = 128; st > 0; st >>= 1) {
+        if (threadIdx.x < st) sh[threadIdx.x] += sh[threadIdx.x + st];
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) block_tot[blockIdx.x] = sh[0];
+}
+__global__ void k_scan_blocks(int64_t *block_tot, int nb, int64_t *total)
+{ /* few thousand values at most: one thread */
+    if (blockIdx.x == 0 && threadIdx.x == 0) {
+        int64_t run = 0;
+        for (int i = 0; i < nb; ++i) {
+            int64_t t = block_tot[i];
+            block_tot[i] = run;
+            run += t;
+        }
+        *total = run;
+    }
+}
+__global__ void __launch_bounds__(256) k_scan_apply(const int32_t *in, int n, const int64_t *block_off, int64_t *out)
+{
+    __shared__ int64_t sh[256];
+    const int per = SCAN_ITEMS / 256, base = blockIdx.x * SCAN_ITEMS + threadIdx.x * per;
+    int64_t loc[SCAN_ITEMS / 256], s = 0;
+    for (int i = 0; i < per; ++i) {
+        int idx = base + i;
+        int v = idx < n ? (in[idx] > 0 ? in[idx] : 0) : 0;
+        loc[i] = s;
+        s += v;
+    }
+    sh[threadIdx.x] = s;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        int64_t run = block_off[blockIdx.x];
+        for (int i = 0; i < 256; ++i) {
+            int64_t t = sh[i];
+            sh[i] = run;
+            run += t;
+        }
+    }
+    __syncthreads();
+    const int64_t off = sh[threadIdx.x];
+    for (int i = 0; i < per; ++i) {
+        int idx = base + i;
+        if (idx < n) out[idx] = off + loc[i];
+    }
+}
+
+__global__ void __launch_bounds__(256) k_compact(int n, const int32_t *n_aln, const int64_t *off, const Rec *recs,
+                                                 int rec_cap, const Rec *recs_big, int rec_cap_big,
+                                                 const int32_t *over_slot, Rec *out)
+{
+    for (int r = blockIdx.x * blockDim.x + threadIdx.x; r < n; r += gridDim.x * blockDim.x) {
+        const int c = n_aln[r];
+        if (c <= 0) continue;
+        const int sl = over_slot[r];
+        const Rec *src = sl >= 0 ? recs_big + (size_t)sl * rec_cap_big : recs + (size_t)r * rec_cap;
+        Rec *dst = out + off[r];
+        for (int j = 0; j < c; ++j) dst[j] = src[j];
+    }
+}
+
+/* random 32-byte-sector gather: the roofline denominator */
+__global__ void __launch_bounds__(256) k_sector_gather(const U4 *blk, uint64_t n_blocks, uint64_t loads_per_thread,
+                                                       unsigned long long *sink)
+{
+    uint64_t s = (blockIdx.x * (uint64_t)blockDim.x + threadIdx.x) * 0x9E3779B97F4A7C15ull + 0x1234567ull;
+    uint32_t acc = 0;
+    for (uint64_t i = 0; i < loads_per_thread; i += 4) {
+        uint64_t idx[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            s ^= s << 13; s ^= s >> 7; s ^= s << 17;
+            idx[j] = (uint64_t)(((unsigned __int128)(s >> 11) * n_blocks) >> 53);
+        }
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            U4 a = ld_ro(blk + 2 * idx[j]), b = ld_ro(blk + 2 * idx[j] + 1);
+            acc += a.x ^ a.w ^ b.y ^ b.z;
+        }
+    }
+    if (acc == 0x7fffffffu) atomicAdd(sink, 1ull);
+}
+
+/* -------------------------------------------------------------- context ---- */
+
+struct DevBuf {
+    void *p = nullptr;
+    size_t cap = 0;
+    void need(size_t bytes)
+    {
+        if (bytes <= cap) return;
+        if (p) CK(cudaFree(p));
+        size_t want = bytes + bytes / 8 + 256;
+        CK(cudaMalloc(&p, want));
+        cap = want;
+    }
+    void release()
+    {
+        if (p) cudaFree(p);
+        p = nullptr;
+        cap = 0;
+    }
+    template <class T> T *as() { return reinterpret_cast<T *>(p); }
+};
+
+struct HostBuf {
+    void *p = nullptr;
+    size_t cap = 0;
+    void need(size_t bytes)
+    {
+        if (bytes <= cap) return;
+        if (p) CK(cudaFreeHost(p));
+        size_t want = bytes + bytes / 8 + 256;
+        CK(cudaHostAlloc(&p, want, cudaHostAllocDefault));
+        cap = want;
+    }
+    void release()
+    {
+        if (p) cudaFreeHost(p);
+        p = nullptr;
+        cap = 0;
+    }
+    template <class T> T *as() { return reinterpret_cast<T *>(p); }
+};
+
+struct b200aln_ctx {
+    int device = 0;
+    int n_sm = 0;
+    FmView fm[2];
+    U4 *d_idx[2] = {nullptr, nullptr};
+    uint64_t n_blk[2] = {0, 0};
+    cudaStream_t st = nullptr;
+    cudaEvent_t ev[8];
+    cudaEvent_t tm[2];
+    /* tuning */
+    int search_blocks_per_sm = 6, width_blocks_per_sm = 8;
+    uint32_t arena_cap = 4096, arena_cap_big = 0; /* 0: max_entries + 64 */
+    int rec_cap = 8, rec_cap_big = 1 << 16, big_lanes = 1024;
+    /* device buffers */
+    DevBuf lens, offs, codes, md, Q, W, seedW, seedB, n_amb, ent, link, recs, n_aln, over_slot, over_list, misc, off64,
+        blk_tot, packed, ent_big, link_big, recs_big;
+    HostBuf h_in, h_out, h_misc;
+    b200aln_stats_t stats;
+};
+
+[[noreturn]] static void die(const char *func, const char *fmt, ...)
+{
+    va_list ap;
+    va_start(ap, fmt);
+    fprintf(stderr, "[%s] ", func);
+    vfprintf(stderr, fmt, ap);
+    fprintf(stderr, " Abort!\n");
+    va_end(ap);
+    abort();
+}
+
+extern "C" const char *b200aln_version(void) { return "b200aln 0.1 (sm_100a; device occ block 32 B / 64 bp)"; }
+
+extern "C" void b200aln_opt_init(b200aln_opt_t *o)
+{ /* gap_init_opt, bwtaln.c:21-37 */
+    memset(o, 0, sizeof *o);
+    o->s_mm = 3; o->s_gapo = 11; o->s_gape = 4;
+    o->max_diff = -1; o->max_gapo = 1; o->max_gape = 6;
+    o->indel_end_skip = 5; o->max_del_occ = 10; o->max_entries = 2000000;
+    o->mode = 0x01 | 0x02; /* GAPE | COMPREAD */
+    o->seed_len = 32; o->max_seed_diff = 2;
+    o->fnr = 0.04f;
+    o->n_threads = 1;
+    o->max_top2 = 30;
+    o->trim_qual = 0;
+}
+
+extern "C" int b200aln_cal_maxdiff(int len, double err, double thres) { return b2host::cal_maxdiff(len, err, thres); }
+
+extern "C" int b200aln_device_count(void)
+{
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) return 0;
+    return n;
+}
+
+static void upload_index(b200aln_ctx *c, int which, const b200aln_bwt_view_t *v)
+{
+    const uint64_t expect = ((uint64_t)v->seq_len + 15) / 16 + 4 * (((uint64_t)v->seq_len + 127) / 128 + 1);
+    if (v->bwt_size != expect)
+        die("b200aln_open", "BWT payload has %llu words, expected %llu for seq_len %u (bwtio.c:51-70).",
+            (unsigned long long)v->bwt_size, (unsigned long long)expect, v->seq_len);
+    uint32_t *d_raw = nullptr;
+    CK(cudaMalloc(&d_raw, v->bwt_size * 4));
+    CK(cudaMemcpyAsync(d_raw, v->bwt, v->bwt_size * 4, cudaMemcpyHostToDevice, c->st));
+    RefBwt r;
+    r.w = d_raw; r.n_words = v->bwt_size; r.seq_len = v->seq_len;
+    for (int i = 0; i < 4; ++i) r.L2[i] = v->L2[i];
+    const uint64_t nb = fm_num_blocks(v->seq_len);
+    CK(cudaMalloc(&c->d_idx[which], nb * 32));
+    k_convert_index<<<c->n_sm * 8, 256, 0, c->st>>>(r, c->d_idx[which], nb);
+    CK(cudaGetLastError());
+    CK(cudaStreamSynchronize(c->st));
+    CK(cudaFree(d_raw));
+    c->n_blk[which] = nb;
+    c->fm[which].blk = c->d_idx[which];
+    c->fm[which].primary = v->primary;
+    c->fm[which].seq_len = v->seq_len;
+}
+
+extern "C" b200aln_ctx *b200aln_open(const b200aln_bwt_view_t *bwt, const b200aln_bwt_view_t *rbwt, int device)
+{
+    int n = b200aln_device_count();
+    if (n <= 0) die("b200aln_open", "no CUDA device available; this engine has no CPU fallback.");
+    if (device < 0 || device >= n) die("b200aln_open", "device %d out of range (%d visible).", device, n);
+    if (bwt->seq_len != rbwt->seq_len) die("b200aln_open", ".bwt and .rbwt describe different lengths.");
+    b200aln_ctx *c = new b200aln_ctx();
+    c->device = device;
+    CK(cudaSetDevice(device));
+    cudaDeviceProp prop;
+    CK(cudaGetDeviceProperties(&prop, device));
+    c->n_sm = prop.multiProcessorCount;
+    CK(cudaStreamCreateWithFlags(&c->st, cudaStreamNonBlocking));
+    for (int i = 0; i < 8; ++i) CK(cudaEventCreate(&c->ev[i]));
+    for (int i = 0; i < 2; ++i) CK(cudaEventCreate(&c->tm[i]));
+    upload_index(c, 0, bwt);
+    upload_index(c, 1, rbwt);
+    memset(&c->stats, 0, sizeof c->stats);
+    return c;
+}
+
+static bool read_bwt_file(const char *fn, std::vector<uint32_t> &words, b200aln_bwt_view_t *v)
+{ /* bwt_restore_bwt, bwtio.c:51-70 */
+    FILE *fp = fopen(fn, "rb");
+    if (!fp) return false;
+    fseek(fp, 0, SEEK_END);
+    long sz = ftell(fp);
+    fseek(fp, 0, SEEK_SET);
+    if (sz < 20) { fclose(fp); return false; }
+    uint32_t hdr[5];
+    if (fread(hdr, 4, 5, fp) != 5) { fclose(fp); return false; }
+    size_t nw = ((size_t)sz - 20) >> 2;
+    words.resize(nw);
+    if (nw && fread(words.data(), 4, nw, fp) != nw) { fclose(fp); return false; }
+    fclose(fp);
+    v->primary = hdr[0];
+    v->L2[0] = 0;
+    for (int i = 0; i < 4; ++i) v->L2[i + 1] = hdr[1 + i];
+    v->seq_len = v->L2[4];
+    v->bwt_size = nw;
+    v->bwt = words.data();
+    return true;
+}
+
+extern "C" b200aln_ctx *b200aln_open_prefix(const char *prefix, int device)
+{
+    std::string p(prefix);
+    std::vector<uint32_t> w0, w1;
+    b200aln_bwt_view_t v0, v1;
+    if (!read_bwt_file((p + ".bwt").c_str(), w0, &v0)) die("b200aln_open_prefix", "fail to open file '%s.bwt'.", prefix);
+    if (!read_bwt_file((p + ".rbwt").c_str(), w1, &v1)) die("b200aln_open_prefix", "fail to open file '%s.rbwt'.", prefix);
+    return b200aln_open(&v0, &v1, device);
+}
+
+extern "C" void b200aln_close(b200aln_ctx *c)
+{
+    if (!c) return;
+    cudaSetDevice(c->device);
+    cudaStreamSynchronize(c->st);
+    DevBuf *bufs[] = {&c->lens, &c->offs, &c->codes, &c->md, &c->Q, &c->W, &c->seedW, &c->seedB, &c->n_amb, &c->ent,
+                      &c->link, &c->recs, &c->n_aln, &c->over_slot, &c->over_list, &c->misc, &c->off64, &c->blk_tot,
+                      &c->packed, &c->ent_big, &c->link_big, &c->recs_big};
+    for (DevBuf *b : bufs) b->release();
+    c->h_in.release(); c->h_out.release(); c->h_misc.release();
+    for (int i = 0; i < 2; ++i) if (c->d_idx[i]) cudaFree(c->d_idx[i]);
+    for (int i = 0; i < 8; ++i) cudaEventDestroy(c->ev[i]);
+    for (int i = 0; i < 2; ++i) cudaEventDestroy(c->tm[i]);
+    cudaStreamDestroy(c->st);
+    delete c;
+}
+
+extern "C" void b200aln_set_int(b200aln_ctx *c, const char *key, int64_t v)
+{
+    if (!strcmp(key, "search_blocks_per_sm")) c->search_blocks_per_sm = (int)v;
+    else if (!strcmp(key, "width_blocks_per_sm")) c->width_blocks_per_sm = (int)v;
+    else if (!strcmp(key, "arena_cap")) c->arena_cap = (uint32_t)v;
+    else if (!strcmp(key, "arena_cap_big")) c->arena_cap_big = (uint32_t)v;
+    else if (!strcmp(key, "rec_cap")) c->rec_cap = (int)v;
+    else if (!strcmp(key, "rec_cap_big")) c->rec_cap_big = (int)v;
+    else if (!strcmp(key, "big_lanes")) c->big_lanes = (int)v;
+    else die("b200aln_set_int", "unknown key '%s'.", key);
+}
+
+extern "C" void b200aln_timer_start(b200aln_ctx *c)
+{
+    CK(cudaSetDevice(c->device));
+    CK(cudaEventRecord(c->tm[0], c->st));
+}
+
+extern "C" double b200aln_timer_stop(b200aln_ctx *c)
+{
+    float ms = 0;
+    CK(cudaSetDevice(c->device));
+    CK(cudaEventRecord(c->tm[1], c->st));
+    CK(cudaEventSynchronize(c->tm[1]));
+    CK(cudaEventElapsedTime(&ms, c->tm[0], c->tm[1]));
+    return (double)ms;
+}
+
+extern "C" void b200aln_last_stats(const b200aln_ctx *c, b200aln_stats_t *out) { *out = c->stats; }
+
+/* misc device words: [0] work counter, [1] n_over, [2] work counter (large pass), [4..5] stat (u64 x2), [8] total (i64) */
+struct Misc {
+    unsigned int counter, n_over, counter_big, pad;
+    unsigned long long stat[2];
+    long long total;
+};
+
+template <bool REUSE>
+static void launch_search(b200aln_ctx *c, const SearchArgs &A, int blocks)
+{
+    if (A.env.P.n_buckets <= 96) k_search<96, REUSE><<<blocks, 128, 0, c->st>>>(A);
+    else if (A.env.P.n_buckets <= 256) k_search<256, REUSE><<<blocks, 128, 0, c->st>>>(A);
+    else k_search<2048, REUSE><<<blocks, 128, 0, c->st>>>(A);
+    CK(cudaGetLastError());
+}
+
+/* the device part of one batch; inputs already on the device */
+static void run_batch_device(b200aln_ctx *c, int n_reads, int max_len, const int32_t *d_lens, const int64_t *d_offs,
+                             const uint8_t *d_codes, const b200aln_opt_t *opt, const std::vector<int> &md,
+                             const Params &P, int64_t *total_out)
+{
+    uint64_t launches = 0;
+    const int strideQ = max_len, strideW = max_len + 1;
+    const int wblocks = c->n_sm * c->width_blocks_per_sm, wthreads = wblocks * 128;
+    const int sblocks = c->n_sm * c->search_blocks_per_sm;
+    const size_t lanes = (size_t)sblocks * 128;
+
+    c->md.need(md.size() * 4);
+    c->Q.need((size_t)n_reads * 2 * strideQ * 8 + 64);
+    c->W.need((size_t)n_reads * 2 * strideW * 4 + 64);
+    c->seedW.need((size_t)wthreads * (opt->seed_len + 1) * 4);
+    c->seedB.need((size_t)wthreads * (opt->seed_len + 1) * 2);
+    c->n_amb.need((size_t)n_reads * 4);
+    c->ent.need(lanes * c->arena_cap * 16);
+    c->link.need(lanes * c->arena_cap * 4);
+    c->recs.need((size_t)n_reads * c->rec_cap * 16);
+    c->n_aln.need((size_t)n_reads * 4);
+    c->over_slot.need((size_t)n_reads * 4);
+    c->over_list.need((size_t)n_reads * 4);
+    c->misc.need(sizeof(Misc));
+    c->off64.need((size_t)n_reads * 8);
+    const int nscan = (n_reads + SCAN_ITEMS - 1) / SCAN_ITEMS;
+    c->blk_tot.need((size_t)nscan * 8 + 8);
+    c->h_misc.need(sizeof(Misc));
+
+    CK(cudaMemcpyAsync(c->md.p, md.data(), md.size() * 4, cudaMemcpyHostToDevice, c->st));
+    CK(cudaMemsetAsync(c->misc.p, 0, sizeof(Misc), c->st));
+    CK(cudaMemsetAsync(c->over_slot.p, 0xff, (size_t)n_reads * 4, c->st));
+    Misc *dm = c->misc.as<Misc>();
+
+    CK(cudaEventRecord(c->ev[1], c->st));
+    WidthArgs WA;
+    WA.fm[0] = c->fm[0]; WA.fm[1] = c->fm[1];
+    WA.n_reads = n_reads; WA.lens = d_lens; WA.offs = d_offs; WA.codes = d_codes;
+    WA.comp = (opt->mode & MODE_COMPREAD) ? 1 : 0; WA.seed_len = opt->seed_len;
+    WA.strideQ = strideQ; WA.strideW = strideW;
+    WA.Q = c->Q.as<uint64_t>(); WA.W = c->W.as<uint32_t>();
+    WA.seedW = c->seedW.as<uint32_t>(); WA.seedB = c->seedB.as<uint16_t>(); WA.n_amb = c->n_amb.as<int32_t>();
+    k_width<<<wblocks, 128, 0, c->st>>>(WA);
+    CK(cudaGetLastError());
+    ++launches;
+    CK(cudaEventRecord(c->ev[2], c->st));
+
+    SearchArgs SA;
+    SA.env.fm[0] = c->fm[0]; SA.env.fm[1] = c->fm[1]; SA.env.P = P;
+    SA.n_work = n_reads; SA.work_list = nullptr;
+    SA.lens = d_lens; SA.n_amb = c->n_amb.as<int32_t>(); SA.md = c->md.as<int32_t>();
+    SA.Q = WA.Q; SA.W = WA.W; SA.strideQ = strideQ; SA.strideW = strideW;
+    SA.ent = c->ent.as<U4>(); SA.link = c->link.as<uint32_t>(); SA.arena_cap = c->arena_cap;
+    SA.recs = c->recs.as<Rec>(); SA.rec_cap = c->rec_cap; SA.recs_by_work = 0;
+    SA.n_aln = c->n_aln.as<int32_t>(); SA.over_slot = nullptr;
+    SA.counter = &dm->counter; SA.n_over = &dm->n_over; SA.over_list = c->over_list.as<int32_t>();
+    SA.stat = dm->stat;
+    launch_search<false>(c, SA, sblocks);
+    ++launches;
+    CK(cudaEventRecord(c->ev[3], c->st));
+
+    /* reads whose stack or record slab outgrew the fast arena: large pass */
+    CK(cudaMemcpyAsync(c->h_misc.p, c->misc.p, sizeof(Misc), cudaMemcpyDeviceToHost, c->st));
+    CK(cudaStreamSynchronize(c->st));
+    unsigned n_over = c->h_misc.as<Misc>()->n_over;
+    c->stats.overflow_reads = n_over;
+    if (n_over) {
+        uint32_t cap_big = c->arena_cap_big ? c->arena_cap_big : (uint32_t)opt->max_entries + 64u;
+        int big_lanes = c->big_lanes;
+        if ((unsigned)big_lanes > ((n_over + 127u) / 128u) * 128u) big_lanes = (int)(((n_over + 127u) / 128u) * 128u);
+        int bblocks = (big_lanes + 127) / 128;
+        c->ent_big.need((size_t)bblocks * 128 * cap_big * 16);
+        c->link_big.need((size_t)bblocks * 128 * cap_big * 4);
+        c->recs_big.need((size_t)n_over * c->rec_cap_big * 16);
+        SearchArgs SB = SA;
+        SB.n_work = (int)n_over; SB.work_list = c->over_list.as<int32_t>();
+        SB.ent = c->ent_big.as<U4>(); SB.link = c->link_big.as<uint32_t>(); SB.arena_cap = cap_big;
+        SB.recs = c->recs_big.as<Rec>(); SB.rec_cap = c->rec_cap_big; SB.recs_by_work = 1;
+        SB.over_slot = c->over_slot.as<int32_t>();
+        SB.counter = &dm->counter_big; SB.n_over = nullptr; SB.over_list = nullptr;
+        launch_search<true>(c, SB, bblocks);
+        ++launches;
+    }
+    CK(cudaEventRecord(c->ev[4], c->st));
+
+    k_scan_totals<<<nscan, 256, 0, c->st>>>(c->n_aln.as<int32_t>(), n_reads, c->blk_tot.as<int64_t>());
+    k_scan_blocks<<<1, 32, 0, c->st>>>(c->blk_tot.as<int64_t>(), nscan, (int64_t *)&dm->total);
+    k_scan_apply<<<nscan, 256, 0, c->st>>>(c->n_aln.as<int32_t>(), n_reads, c->blk_tot.as<int64_t>(),
+                                           c->off64.as<int64_t>());
+    CK(cudaGetLastError());
+    launches += 3;
+    CK(cudaMemcpyAsync(c->h_misc.p, c->misc.p, sizeof(Misc), cudaMemcpyDeviceToHost, c->st));
+    CK(cudaStreamSynchronize(c->st));
+    const Misc hm = *c->h_misc.as<Misc>();
+    const int64_t total = hm.total;
+    c->packed.need((size_t)(total > 0 ? total : 1) * 16);
+    k_compact<<<c->n_sm * 4, 256, 0, c->st>>>(n_reads, c->n_aln.as<int32_t>(), c->off64.as<int64_t>(),
+                                              c->recs.as<Rec>(), c->rec_cap, c->recs_big.as<Rec>(), c->rec_cap_big,
+                                              c->over_slot.as<int32_t>(), c->packed.as<Rec>());
+    CK(cudaGetLastError());
+    ++launches;
+    CK(cudaEventRecord(c->ev[5], c->st));
+    c->stats.kernel_launches = launches;
+    c->stats.pops = hm.stat[0];
+    c->stats.occ_lookups = hm.stat[1];
+    *total_out = total;
+}
+
+static void finish_stats(b200aln_ctx *c, bool with_copies)
+{
+    float ms = 0;
+    CK(cudaEventSynchronize(c->ev[with_copies ? 6 : 5]));
+    CK(cudaEventElapsedTime(&ms, c->ev[1], c->ev[2])); c->stats.ms_width = ms;
+    CK(cudaEventElapsedTime(&ms, c->ev[2], c->ev[4])); c->stats.ms_search = ms;
+    CK(cudaEventElapsedTime(&ms, c->ev[4], c->ev[5])); c->stats.ms_compact = ms;
+    if (with_copies) {
+        CK(cudaEventElapsedTime(&ms, c->ev[0], c->ev[1])); c->stats.ms_h2d = ms;
+        CK(cudaEventElapsedTime(&ms, c->ev[5], c->ev[6])); c->stats.ms_d2h = ms;
+        CK(cudaEventElapsedTime(&ms, c->ev[0], c->ev[6])); c->stats.ms_total = ms;
+    } else {
+        c->stats.ms_h2d = c->stats.ms_d2h = 0;
+        CK(cudaEventElapsedTime(&ms, c->ev[1], c->ev[5])); c->stats.ms_total = ms;
+    }
+}
+
+static void check_overflow_of_large_pass(b200aln_ctx *c, int n_reads, const int32_t *h_n_aln)
+{
+    (void)c;
+    for (int r = 0; r < n_reads; ++r)
+        if (h_n_aln[r] < 0)
+            die("b200aln_batch",
+                "read %d exceeded the large per-read arena or record capacity (raise arena_cap_big / rec_cap_big).", r);
+}
+
+extern "C" const b200aln_rec_t *b200aln_batch(b200aln_ctx *c, int n_reads, const int32_t *lens, const int64_t *offs,
+                                              const uint8_t *codes, const b200aln_opt_t *opt, int32_t *n_aln,
+                                              int64_t *total)
+{
+    CK(cudaSetDevice(c->device));
+    *total = 0;
+    if (n_reads <= 0) return c->h_out.as<b200aln_rec_t>();
+    int max_len = 0;
+    int64_t end = 0;
+    for (int r = 0; r < n_reads; ++r) {
+        if (lens[r] < 1) die("b200aln_batch", "read %d has length %d; the reference never emits empty reads (bwaseqio.c:161).", r, lens[r]);
+        if (lens[r] > max_len) max_len = lens[r];
+        if (offs[r] + lens[r] > end) end = offs[r] + lens[r];
+    }
+    Params P;
+    std::vector<int> md;
+    b2host::make_params(*opt, max_len, lens, n_reads, P, md);
+
+    c->lens.need((size_t)n_reads * 4);
+    c->offs.need((size_t)n_reads * 8);
+    c->codes.need((size_t)end + 16);
+    CK(cudaEventRecord(c->ev[0], c->st));
+    CK(cudaMemcpyAsync(c->lens.p, lens, (size_t)n_reads * 4, cudaMemcpyHostToDevice, c->st));
+    CK(cudaMemcpyAsync(c->offs.p, offs, (size_t)n_reads * 8, cudaMemcpyHostToDevice, c->st));
+    CK(cudaMemcpyAsync(c->codes.p, codes, (size_t)end, cudaMemcpyHostToDevice, c->st));
+    int64_t tot = 0;
+    run_batch_device(c, n_reads, max_len, c->lens.as<int32_t>(), c->offs.as<int64_t>(), c->codes.as<uint8_t>(), opt,
+                     md, P, &tot);
+    c->h_out.need((size_t)(tot > 0 ? tot : 1) * 16);
+    CK(cudaMemcpyAsync(n_aln, c->n_aln.p, (size_t)n_reads * 4, cudaMemcpyDeviceToHost, c->st));
+    if (tot) CK(cudaMemcpyAsync(c->h_out.p, c->packed.p, (size_t)tot * 16, cudaMemcpyDeviceToHost, c->st));
+    CK(cudaEventRecord(c->ev[6], c->st));
+    CK(cudaStreamSynchronize(c->st));
+    finish_stats(c, true);
+    check_overflow_of_large_pass(c, n_reads, n_aln);
+    *total = tot;
+    return c->h_out.as<b200aln_rec_t>();
+}
+
+extern "C" void b200aln_batch_device(b200aln_ctx *c, int n_reads, int max_len, const int32_t *d_lens,
+                                     const int64_t *d_offs, const uint8_t *d_codes, const b200aln_opt_t *opt,
+                                     const int32_t **d_n_aln, const b200aln_rec_t **d_recs, int64_t *total)
+{
+    CK(cudaSetDevice(c->device));
+    Params P;
+    std::vector<int> md;
+    std::vector<int32_t> one(1, max_len);
+    /* all lengths up to max_len are tabulated; reads longer than 1024 bp need the host-buffer entry point */
+    if (max_len > 1024) die("b200aln_batch_device", "max_len > 1024 needs b200aln_batch (per-length max_diff table).");
+    b2host::make_params(*opt, max_len, one.data(), 1, P, md);
+    int64_t tot = 0;
+    run_batch_device(c, n_reads, max_len, d_lens, d_offs, d_codes, opt, md, P, &tot);
+    CK(cudaStreamSynchronize(c->st));
+    finish_stats(c, false);
+    *d_n_aln = c->n_aln.as<int32_t>();
+    *d_recs = c->packed.as<b200aln_rec_t>();
+    *total = tot;
+}
+
+extern "C" double b200aln_sector_roofline(b200aln_ctx *c, uint64_t n_loads, int repeats)
+{
+    CK(cudaSetDevice(c->device));
+    c->misc.need(sizeof(Misc));
+    const int blocks = c->n_sm * 8, threads = 256;
+    uint64_t per = (n_loads / ((uint64_t)blocks * threads) + 3) / 4 * 4;
+    if (per < 4) per = 4;
+    /* both indexes are one allocation each; gather over the larger span: bwt blocks */
+    double best = 0;
+    for (int it = 0; it < repeats + 1; ++it) {
+        CK(cudaEventRecord(c->ev[0], c->st));
+        k_sector_gather<<<blocks, threads, 0, c->st>>>(c->d_idx[it & 1], c->n_blk[it & 1], per,
+                                                       (unsigned long long *)c->misc.p);
+        CK(cudaGetLastError());
+        CK(cudaEventRecord(c->ev[1], c->st));
+        CK(cudaEventSynchronize(c->ev[1]));
+        float ms = 0;
+        CK(cudaEventElapsedTime(&ms, c->ev[0], c->ev[1]));
+        double gbs = (double)per * blocks * threads * 32.0 / (ms * 1e-3) / 1e9;
+        if (it > 0 && gbs > best) best = gbs;
+    }
+    return best;
+}

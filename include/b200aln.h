@@ -1,0 +1,169 @@
+/*
+ * b200aln.h — C ABI of the B200-native `bwa aln` engine (libb200aln.so).
+ *
+ * Drop-in boundary for the one hot path of genome/ibwa: the gapped FM-index
+ * search that turns reads into .sai suffix-array intervals.  Plain C types
+ * only.  Every entry point names the reference interface it replaces
+ * (file:line under the reference tree).
+ *
+ * Error convention (reference: utils.c:35-82): there are no return codes for
+ * fatal conditions.  A CUDA failure, an unsupported option or an internal
+ * overflow prints "[b200aln_*] <message> Abort!" to stderr and calls abort();
+ * a partial result is never returned.  There is no CPU fallback.
+ */
+#ifndef B200ALN_H
+#define B200ALN_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* == gap_opt_t (bwtaln.h:105-115): 16 x 4 bytes, also the .sai header (bwtaln.c:192). */
+typedef struct {
+    int32_t s_mm, s_gapo, s_gape;
+    int32_t mode; /* BWA_MODE_* bits (bwtaln.h:93-101); bits 24-31 = barcode length */
+    int32_t indel_end_skip, max_del_occ, max_entries;
+    float fnr;
+    int32_t max_diff, max_gapo, max_gape;
+    int32_t max_seed_diff, seed_len;
+    int32_t n_threads;
+    int32_t max_top2;
+    int32_t trim_qual;
+} b200aln_opt_t;
+
+/* == bwt_aln1_t (bwtaln.h:34-38): 16 bytes, the .sai record. */
+typedef struct {
+    uint32_t packed; /* n_mm:8 | n_gapo:8 | n_gape:8 | a:1 */
+    uint32_t k, l;   /* SA interval */
+    int32_t score;
+} b200aln_rec_t;
+
+/* A view of one in-memory FM-index exactly as bwt_restore_bwt() leaves it
+ * (bwt.h:42-54, bwtio.c:51-70): `bwt` is the file payload after the 5-word
+ * header, occ checkpoints interleaved every 128 bases. */
+typedef struct {
+    uint32_t primary;
+    uint32_t L2[5];
+    uint32_t seq_len;
+    uint64_t bwt_size; /* number of 32-bit words in `bwt` */
+    const uint32_t *bwt;
+} b200aln_bwt_view_t;
+
+typedef struct b200aln_ctx b200aln_ctx;
+
+/* Library / build identification; usable without a GPU. */
+const char *b200aln_version(void);
+
+/* gap_init_opt (bwtaln.c:21-37): fill *opt with the reference defaults. */
+void b200aln_opt_init(b200aln_opt_t *opt);
+
+/* bwa_cal_maxdiff (bwtaln.c:39-51). */
+int b200aln_cal_maxdiff(int len, double err, double thres);
+
+/* Number of CUDA devices visible (0 when none / no driver). */
+int b200aln_device_count(void);
+
+/*
+ * Replaces the two bwt_restore_bwt() results held by bwa_aln_core
+ * (bwtaln.c:184-189): uploads both indexes to `device`, re-laid out as one
+ * 32-byte occ block per 64 bases, and creates streams, pinned staging buffers
+ * and search scratch.  The caller keeps ownership of the host arrays and may
+ * free them after the call returns.
+ */
+b200aln_ctx *b200aln_open(const b200aln_bwt_view_t *bwt, const b200aln_bwt_view_t *rbwt, int device);
+
+/* Convenience: bwt_restore_bwt(prefix.bwt / prefix.rbwt) + b200aln_open (bwtaln.c:184-189). */
+b200aln_ctx *b200aln_open_prefix(const char *prefix, int device);
+
+/* bwt_destroy x2 (bwtaln.c:238) plus device teardown. */
+void b200aln_close(b200aln_ctx *ctx);
+
+/*
+ * Replaces bwa_cal_sa_reg_gap (bwtaln.c:80-140, declared bwtaln.h:148) for one
+ * reference batch, on packed HOST buffers.  Read r is codes[offs[r] ..
+ * offs[r]+lens[r]) in sequencing orientation, nt4 codes (0-3 = ACGT, >3 =
+ * ambiguous; bntseq.c:39-56) after trimming; the reversed / reverse-
+ * complemented forms the reference keeps (bwaseqio.c:189-192) are derived on
+ * the device.  Batch-level semantics (max_len -> max_diff -> max_gapo clamp,
+ * bwtaln.c:89-92) apply to exactly the reads of this call.
+ *
+ * n_aln[r] receives the record count of read r.  The records of all reads, in
+ * read order, are returned in a buffer owned by the context, valid until the
+ * next batch call on it; *total receives their number.  Host<->device copies
+ * happen inside the call (pinned staging, asynchronous streams).
+ */
+const b200aln_rec_t *b200aln_batch(b200aln_ctx *ctx, int n_reads, const int32_t *lens, const int64_t *offs,
+                                   const uint8_t *codes, const b200aln_opt_t *opt, int32_t *n_aln, int64_t *total);
+
+/*
+ * Same operator with inputs already resident on the device (d_lens, d_offs,
+ * d_codes are device pointers on ctx's device; max_len and codes_bytes describe
+ * them) and results left on the device: *d_n_aln (int32[n_reads]) and
+ * *d_recs (b200aln_rec_t[*total]) point into context-owned device memory valid
+ * until the next batch call.  Used to time the kernels without PCIe traffic.
+ */
+void b200aln_batch_device(b200aln_ctx *ctx, int n_reads, int max_len, const int32_t *d_lens, const int64_t *d_offs,
+                          const uint8_t *d_codes, const b200aln_opt_t *opt, const int32_t **d_n_aln,
+                          const b200aln_rec_t **d_recs, int64_t *total);
+
+/* Per-call counters of the last batch on this context (instrumentation). */
+typedef struct {
+    double ms_h2d, ms_width, ms_search, ms_compact, ms_d2h, ms_total; /* CUDA-event times */
+    uint64_t kernel_launches; /* kernels of this library launched by the call */
+    uint64_t overflow_reads;  /* reads re-run with the large per-read arena */
+    uint64_t pops, occ_lookups; /* only filled when built with B200ALN_COUNTERS */
+} b200aln_stats_t;
+void b200aln_last_stats(const b200aln_ctx *ctx, b200aln_stats_t *out);
+
+/* CUDA-event stopwatch on the stream the engine launches on: start records an
+ * event; stop records another, waits for it and returns the milliseconds
+ * between them.  bench.py brackets its timed region with these. */
+void b200aln_timer_start(b200aln_ctx *ctx);
+double b200aln_timer_stop(b200aln_ctx *ctx);
+
+/* Tuning knobs (optional; call before the first batch).  Unknown keys abort. */
+void b200aln_set_int(b200aln_ctx *ctx, const char *key, int64_t value);
+
+/*
+ * Drop-in for the reference's batch seam on its own structures:
+ *   void bwa_cal_sa_reg_gap(int tid, bwt_t *const bwt[2], int n_seqs,
+ *                           bwa_seq_t *seqs, const gap_opt_t *opt)   (bwtaln.h:148)
+ * `seqs` is the reference's bwa_seq_t array (bwtaln.h:72-104; sizeof == 176 on
+ * LP64, see b200aln_seq_layout_check).  Contract kept: fills n_aln and aln
+ * (malloc'ed, freed by bwa_free_read_seq, bwaseqio.c:218), zeroes sa/type/c1/c2
+ * (bwtaln.c:114), frees and nulls name/seq/rseq/qual (bwtaln.c:134-135).  The
+ * context replaces the bwt[2] argument; tid is ignored (called once per batch).
+ */
+void b200aln_cal_sa_reg_gap(b200aln_ctx *ctx, int n_seqs, void *seqs, const b200aln_opt_t *opt);
+
+/* sizeof / offsets this library assumes for bwa_seq_t; INTEGRATION.md shows the
+ * static asserts a reference-side binding adds. */
+typedef struct {
+    size_t size, off_name, off_seq, off_rseq, off_qual, off_lenword, off_n_aln, off_aln, off_sa, off_c1c2;
+} b200aln_seq_layout_t;
+void b200aln_seq_layout(b200aln_seq_layout_t *out);
+
+/*
+ * Replaces bwa_aln_core (bwtaln.c:173-241, declared bwtaln.h:138): reads
+ * `fn_fa` (FASTA/FASTQ, plain or gzip, "-" = stdin), writes the 64-byte header
+ * and the per-read records to `out_fd` in 0x40000-read batches.  `device` < 0
+ * uses every visible GPU with the index replicated and each batch sharded.
+ * Returns the number of reads processed.
+ */
+int64_t b200aln_aln_core(const char *prefix, const char *fn_fa, const b200aln_opt_t *opt, int out_fd, int device);
+
+/* Replaces bwa_aln (bwtaln.c:243-328): same getopt string and semantics. */
+int b200aln_aln_main(int argc, char *argv[]);
+
+/* Random 32-byte-sector gather micro-benchmark over the device index (the
+ * roofline denominator of SURVEY.md §8d): n_loads independent uniformly random
+ * sector reads; returns GB/s (sectors * 32 B / CUDA-event time). */
+double b200aln_sector_roofline(b200aln_ctx *ctx, uint64_t n_loads, int repeats);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* B200ALN_H */

@@ -1,0 +1,96 @@
+// host_harness.cpp — TEST INFRASTRUCTURE: compiles the product's per-read state
+// machines (ibwa_b200/csrc/aln_core.cuh, fm_layout.cuh) with g++ and runs them
+// read by read on the CPU, so that tests can check the kernel LOGIC against the
+// oracle in a container without a GPU.  Not part of libb200aln.so and never
+// used by the product path.
+#include <cstdint>
+#include <cstdlib>
+#include <cstring>
+#include <vector>
+
+#include "../../include/b200aln.h"
+#include "../../ibwa_b200/csrc/aln_core.cuh"
+#include "../../ibwa_b200/csrc/fm_layout.cuh"
+#include "../../ibwa_b200/csrc/host_params.h"
+
+using namespace b2;
+
+static std::vector<U4> convert(const b200aln_bwt_view_t *v)
+{
+    RefBwt r;
+    r.w = v->bwt; r.n_words = v->bwt_size; r.seq_len = v->seq_len;
+    for (int c = 0; c < 4; ++c) r.L2[c] = v->L2[c];
+    uint64_t nb = fm_num_blocks(v->seq_len);
+    std::vector<U4> out(2 * nb);
+    for (uint64_t b = 0; b < nb; ++b) fm_convert_block(r, b, &out[2 * b]);
+    return out;
+}
+
+template <int NB, bool REUSE>
+static int64_t run(const SearchEnv &env, const std::vector<int> &md, int n_reads, const int32_t *lens,
+                   const int64_t *offs, const uint8_t *codes, bool comp, int seed_len, uint32_t arena_cap, int rec_cap,
+                   int32_t *n_aln, std::vector<Rec> &all, uint64_t *counters)
+{
+    int max_len = 0;
+    for (int r = 0; r < n_reads; ++r) if (lens[r] > max_len) max_len = lens[r];
+    const int strideQ = max_len, strideW = max_len + 1;
+    std::vector<uint64_t> Q(2 * (size_t)strideQ + 2);
+    std::vector<uint32_t> W(2 * (size_t)strideW);
+    std::vector<uint32_t> seedW(seed_len + 1);
+    std::vector<uint16_t> seedB(seed_len + 1);
+    std::vector<U4> ent(arena_cap);
+    std::vector<uint32_t> link(arena_cap);
+    std::vector<Rec> recs(rec_cap);
+    int64_t n_status = 0;
+    for (int r = 0; r < n_reads; ++r) {
+        const uint8_t *fwd = codes + offs[r];
+        int len = lens[r];
+        const FmView *fm = env.fm;
+        int n_amb = width_pass(fm[0], fwd, len, 0, comp, seed_len, W.data(), Q.data(), seedW.data(), seedB.data());
+        width_pass(fm[1], fwd, len, 1, comp, seed_len, W.data() + strideW, Q.data() + strideQ, seedW.data(),
+                   seedB.data());
+        SearchLane<NB, REUSE> lane;
+        Arena ar; ar.ent = ent.data(); ar.link = link.data(); ar.cap = arena_cap;
+        lane.begin(&env, ar, Q.data(), W.data(), strideQ, strideW, recs.data(), rec_cap, len, md[len], n_amb);
+        while (!lane.finished) lane.step();
+        if (lane.status != LANE_OK) { ++n_status; n_aln[r] = -lane.status; continue; }
+        n_aln[r] = lane.n_aln;
+        all.insert(all.end(), recs.begin(), recs.begin() + lane.n_aln);
+        if (counters) { counters[0] += lane.n_pops; counters[1] += lane.n_lookups; }
+    }
+    return n_status;
+}
+
+extern "C" int64_t hh_aln_batch(const b200aln_bwt_view_t *bwt, const b200aln_bwt_view_t *rbwt, int n_reads,
+                                const int32_t *lens, const int64_t *offs, const uint8_t *codes,
+                                const b200aln_opt_t *opt, uint32_t arena_cap, int rec_cap, int reuse, int32_t *n_aln,
+                                Rec **records, int64_t *n_overflow, uint64_t *counters)
+{
+    std::vector<U4> i0 = convert(bwt), i1 = convert(rbwt);
+    SearchEnv env;
+    FmView *fm = env.fm;
+    fm[0].blk = i0.data(); fm[0].primary = bwt->primary; fm[0].seq_len = bwt->seq_len;
+    fm[1].blk = i1.data(); fm[1].primary = rbwt->primary; fm[1].seq_len = rbwt->seq_len;
+    int max_len = 0;
+    for (int r = 0; r < n_reads; ++r) if (lens[r] > max_len) max_len = lens[r];
+    Params &P = env.P;
+    std::vector<int> md;
+    b2host::make_params(*opt, max_len, lens, n_reads, P, md);
+    std::vector<Rec> all;
+    bool comp = opt->mode & MODE_COMPREAD;
+    int64_t ov;
+    if (P.n_buckets <= 128) {
+        ov = reuse ? run<128, true>(env, md, n_reads, lens, offs, codes, comp, opt->seed_len, arena_cap, rec_cap, n_aln, all, counters)
+                   : run<128, false>(env, md, n_reads, lens, offs, codes, comp, opt->seed_len, arena_cap, rec_cap, n_aln, all, counters);
+    } else {
+        ov = reuse ? run<2048, true>(env, md, n_reads, lens, offs, codes, comp, opt->seed_len, arena_cap, rec_cap, n_aln, all, counters)
+                   : run<2048, false>(env, md, n_reads, lens, offs, codes, comp, opt->seed_len, arena_cap, rec_cap, n_aln, all, counters);
+    }
+    *n_overflow = ov;
+    Rec *out = (Rec *)malloc(sizeof(Rec) * (all.size() + 1));
+    memcpy(out, all.data(), sizeof(Rec) * all.size());
+    *records = out;
+    return (int64_t)all.size();
+}
+
+extern "C" void hh_free(void *p) { free(p); }

@@ -1,0 +1,71 @@
+"""ctypes binding of tests/harness/libhostharness.so: the product's per-read state
+machines (ibwa_b200/csrc/aln_core.cuh) compiled for the CPU.  Test-only."""
+import ctypes
+import os
+import subprocess
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(os.path.dirname(HERE))
+LIB = os.path.join(HERE, "libhostharness.so")
+SRCS = [os.path.join(HERE, "host_harness.cpp"), os.path.join(ROOT, "ibwa_b200", "csrc", "aln_core.cuh"),
+        os.path.join(ROOT, "ibwa_b200", "csrc", "fm_layout.cuh"), os.path.join(ROOT, "ibwa_b200", "csrc", "host_params.h")]
+ALN_DTYPE = np.dtype([("packed", "<u4"), ("k", "<u4"), ("l", "<u4"), ("score", "<i4")])
+
+
+class BwtView(ctypes.Structure):
+    _fields_ = [("primary", ctypes.c_uint32), ("L2", ctypes.c_uint32 * 5), ("seq_len", ctypes.c_uint32),
+                ("bwt_size", ctypes.c_uint64), ("bwt", ctypes.c_void_p)]
+
+
+def view(b):
+    v = BwtView()
+    v.primary = b.primary
+    for i in range(5):
+        v.L2[i] = int(b.L2[i])
+    v.seq_len = b.seq_len
+    arr = np.ascontiguousarray(b.bwt, dtype=np.uint32)
+    v._keep = arr
+    v.bwt_size = arr.shape[0]
+    v.bwt = arr.ctypes.data
+    return v
+
+
+def build():
+    if not os.path.exists(LIB) or any(os.path.getmtime(s) > os.path.getmtime(LIB) for s in SRCS):
+        subprocess.check_call(["g++", "-O2", "-g", "-std=c++17", "-fPIC", "-shared", "-DB200ALN_COUNTERS", "-o", LIB,
+                               SRCS[0]])
+    return LIB
+
+
+_lib = None
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        _lib = ctypes.CDLL(build())
+        _lib.hh_aln_batch.restype = ctypes.c_int64
+    return _lib
+
+
+def aln_batch(bwt, rbwt, lens, offs, codes, opt_c, arena_cap=1 << 16, rec_cap=256, reuse=False):
+    L = lib()
+    lens = np.ascontiguousarray(lens, np.int32)
+    offs = np.ascontiguousarray(offs, np.int64)
+    codes = np.ascontiguousarray(codes, np.uint8)
+    n = len(lens)
+    n_aln = np.zeros(n, np.int32)
+    rec_p = ctypes.c_void_p()
+    nov = ctypes.c_int64()
+    counters = (ctypes.c_uint64 * 2)()
+    v0, v1 = view(bwt), view(rbwt)
+    tot = L.hh_aln_batch(ctypes.byref(v0), ctypes.byref(v1), ctypes.c_int(n), ctypes.c_void_p(lens.ctypes.data),
+                         ctypes.c_void_p(offs.ctypes.data), ctypes.c_void_p(codes.ctypes.data), ctypes.byref(opt_c),
+                         ctypes.c_uint32(arena_cap), ctypes.c_int(rec_cap), ctypes.c_int(int(reuse)),
+                         ctypes.c_void_p(n_aln.ctypes.data), ctypes.byref(rec_p), ctypes.byref(nov), counters)
+    rec = np.frombuffer((ctypes.c_uint8 * (16 * tot)).from_address(rec_p.value), dtype=ALN_DTYPE).copy() if tot \
+        else np.empty(0, ALN_DTYPE)
+    L.hh_free(rec_p)
+    return n_aln, rec, nov.value, {"pops": counters[0], "sectors": counters[1]}

@@ -1,0 +1,53 @@
+"""The product's per-read state machines (aln_core.cuh), compiled for the CPU by
+tests/harness, against the reference's golden .sai files.  This checks the
+kernel LOGIC where no GPU exists; the -m gpu tests check the kernels proper."""
+import io
+import os
+
+import numpy as np
+import pytest
+
+from ibwa_b200 import parse_aln_args, sai, seqio
+from harness import pyharness
+from cases import CASES
+
+
+def harness_sai(bwt, rbwt, args, fq, **kw):
+    opt, _, _, _ = parse_aln_args(args + ["prefix", fq])
+    buf = io.BytesIO()
+    sai.write_header(buf, opt)
+    nov_total = 0
+    for batch in seqio.read_batches(fq, opt.mode, opt.trim_qual):
+        n_aln, rec, nov, _ = pyharness.aln_batch(bwt, rbwt, batch.lens, batch.offs, batch.codes, opt.to_c(), **kw)
+        nov_total += nov
+        sai.write_batch(buf, np.maximum(n_aln, 0), rec)
+    return buf.getvalue(), nov_total
+
+
+@pytest.mark.parametrize("tag", sorted(CASES))
+def test_core_matches_reference(tag, golden_dir, g1_index):
+    args, fq = CASES[tag]
+    got, nov = harness_sai(g1_index[0], g1_index[1], args, os.path.join(golden_dir, fq + ".fq.gz"),
+                           arena_cap=1 << 22, rec_cap=4096)
+    want = open(os.path.join(golden_dir, f"g1_{tag}.sai"), "rb").read()
+    assert nov == 0
+    assert got == want
+
+
+@pytest.mark.parametrize("tag", ["default", "stress", "m200"])
+def test_core_free_list_variant(tag, golden_dir, g1_index):
+    args, fq = CASES[tag]
+    got, nov = harness_sai(g1_index[0], g1_index[1], args, os.path.join(golden_dir, fq + ".fq.gz"),
+                           arena_cap=1 << 22, rec_cap=4096, reuse=True)
+    want = open(os.path.join(golden_dir, f"g1_{tag}.sai"), "rb").read()
+    assert nov == 0 and got == want
+
+
+def test_small_arena_flags_overflow(golden_dir, g1_index):
+    """A read whose stack outgrows the fast arena must be flagged, never truncated."""
+    args, fq = CASES["default"]
+    opt, _, _, _ = parse_aln_args(args + ["p", "q"])
+    batch = next(seqio.read_batches(os.path.join(golden_dir, fq + ".fq.gz"), opt.mode, opt.trim_qual))
+    n_aln, rec, nov, _ = pyharness.aln_batch(g1_index[0], g1_index[1], batch.lens, batch.offs, batch.codes,
+                                             opt.to_c(), arena_cap=256, rec_cap=4)
+    assert nov > 0 and (n_aln < 0).sum() == nov

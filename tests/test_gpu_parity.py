@@ -1,0 +1,148 @@
+"""Parity tests proper: the CUDA path, called through the C ABI, against the
+reference's golden .sai files, the CPU oracle and (where oracle/_ref travelled
+to the box) the unmodified reference binary.  Bit-exact: integer / byte work."""
+import ctypes
+import io
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+from ibwa_b200 import engine, fmbuild, gap_init_opt, parse_aln_args, sai, seqio, synth
+from ibwa_b200.bwtio import bwt_dump_bwt
+from oracle import pyoracle
+from cases import CASES
+
+pytestmark = pytest.mark.gpu
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+@pytest.fixture(scope="module")
+def eng(g1_index):
+    e = engine.Engine(g1_index[0], g1_index[1], 0)
+    yield e
+    e.close()
+
+
+def engine_sai(e, args, fq):
+    opt, _, _, _ = parse_aln_args(args + ["prefix", fq])
+    buf = io.BytesIO()
+    sai.write_header(buf, opt)
+    for batch in seqio.read_batches(fq, opt.mode, opt.trim_qual):
+        n_aln, rec = e.cal_sa_reg_gap(batch.lens, batch.offs, batch.codes, opt)
+        sai.write_batch(buf, n_aln, rec)
+    return buf.getvalue()
+
+
+@pytest.mark.parametrize("tag", sorted(CASES))
+def test_golden_sai(tag, eng, golden_dir):
+    args, fq = CASES[tag]
+    got = engine_sai(eng, args, os.path.join(golden_dir, fq + ".fq.gz"))
+    want = open(os.path.join(golden_dir, f"g1_{tag}.sai"), "rb").read()
+    assert got == want
+    if tag == "m200":
+        assert eng.stats()["overflow_reads"] == 0
+
+
+@pytest.mark.parametrize("tag", ["default", "stress", "N_n2"])
+def test_overflow_path_is_exact(tag, g1_index, golden_dir):
+    """Tiny fast arenas force most reads through the large-arena pass; bytes must not change."""
+    args, fq = CASES[tag]
+    with engine.Engine(g1_index[0], g1_index[1], 0) as e:
+        e.set("arena_cap", 64)
+        e.set("rec_cap", 1)
+        got = engine_sai(e, args, os.path.join(golden_dir, fq + ".fq.gz"))
+        assert e.stats()["overflow_reads"] > 0
+    assert got == open(os.path.join(golden_dir, f"g1_{tag}.sai"), "rb").read()
+
+
+@pytest.mark.parametrize("tag", ["default", "q20", "stress"])
+def test_cli_binary(tag, golden_dir, tmp_path):
+    """The `b200aln aln` command line: same options in, same .sai bytes out (bwtaln.c:243-328)."""
+    args, fq = CASES[tag]
+    prefix = str(tmp_path / "g1")
+    os.symlink(os.path.join(golden_dir, "g1.bwt"), prefix + ".bwt")
+    os.symlink(os.path.join(golden_dir, "g1.rbwt"), prefix + ".rbwt")
+    out = str(tmp_path / "out.sai")
+    exe = os.path.join(ROOT, "ibwa_b200", "b200aln")
+    subprocess.check_call([exe, "aln"] + args + ["-f", out, prefix, os.path.join(golden_dir, fq + ".fq.gz")],
+                          stderr=subprocess.DEVNULL)
+    assert open(out, "rb").read() == open(os.path.join(golden_dir, f"g1_{tag}.sai"), "rb").read()
+    # stdout variant
+    p = subprocess.run([exe, "aln"] + args + [prefix, os.path.join(golden_dir, fq + ".fq.gz")],
+                       stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, check=True)
+    assert p.stdout == open(os.path.join(golden_dir, f"g1_{tag}.sai"), "rb").read()
+
+
+@pytest.fixture(scope="module")
+def rand_index():
+    g = synth.random_genome(2_000_000, 20260101)
+    bwt, rbwt = fmbuild.build_index_numpy(g)
+    return g, bwt, rbwt
+
+
+@pytest.mark.parametrize("model,args,length,n", [("default", [], 100, 20000),
+                                                 ("stress", ["-n", "4", "-o", "2", "-e", "10", "-l", "32", "-k", "2"], 150, 4000)])
+def test_random_genome_vs_oracle(rand_index, model, args, length, n):
+    g, bwt, rbwt = rand_index
+    if model == "default":
+        reads = synth.simulate_reads_fast(g, n, length, 20260112)
+    else:
+        reads = np.stack(synth.simulate_reads(g, n, length, 20260103, model="stress"))
+    lens = np.full(n, length, np.int32)
+    offs = np.arange(n, dtype=np.int64) * length
+    opt, _, _, _ = parse_aln_args(args + ["p", "q"])
+    with engine.Engine(bwt, rbwt, 0) as e:
+        n_aln, rec = e.cal_sa_reg_gap(lens, offs, reads.reshape(-1), opt)
+        st = e.stats()
+    o_n, o_rec, ost = pyoracle.aln_batch(pyoracle.as_orc_bwt(bwt), pyoracle.as_orc_bwt(rbwt), lens, offs,
+                                         reads.reshape(-1), opt.to_c())
+    assert np.array_equal(n_aln, o_n)
+    assert rec.tobytes() == o_rec.tobytes()
+    assert st["pops"] == ost["pops"]          # same search, pop for pop
+    assert (n_aln > 0).mean() > 0.8
+
+
+def test_device_resident_entry_point(rand_index):
+    import torch
+    g, bwt, rbwt = rand_index
+    n, length = 5000, 100
+    reads = synth.simulate_reads_fast(g, n, length, 5)
+    lens = np.full(n, length, np.int32)
+    offs = np.arange(n, dtype=np.int64) * length
+    opt = gap_init_opt()
+    with engine.Engine(bwt, rbwt, 0) as e:
+        n_aln, rec = e.cal_sa_reg_gap(lens, offs, reads.reshape(-1), opt)
+        d_l, d_o, d_c = (torch.from_numpy(x).cuda() for x in (lens, offs, reads.reshape(-1)))
+        torch.cuda.synchronize()
+        pn, pr, total = e.batch_device(d_l.data_ptr(), d_o.data_ptr(), d_c.data_ptr(), n, length, opt)
+        assert total == len(rec)
+        out_n = torch.empty(n, dtype=torch.int32, device="cuda")
+        out_r = torch.empty(total * 4, dtype=torch.int32, device="cuda")
+        torch.cuda.synchronize()
+        import ibwa_b200.devcopy as devcopy
+        devcopy.d2d(out_n.data_ptr(), pn, n * 4)
+        devcopy.d2d(out_r.data_ptr(), pr, total * 16)
+        torch.cuda.synchronize()
+        assert np.array_equal(out_n.cpu().numpy(), n_aln)
+        assert out_r.cpu().numpy().tobytes() == rec.tobytes()
+
+
+def test_reference_binary_on_box(rand_index, tmp_path):
+    """If the unmodified reference binary travelled with the repo, run it here on fresh inputs."""
+    if not pyoracle.have_ref():
+        pytest.skip("oracle/_ref/ibwa not present")
+    g, bwt, rbwt = rand_index
+    prefix = str(tmp_path / "r2m")
+    bwt_dump_bwt(prefix + ".bwt", bwt)
+    bwt_dump_bwt(prefix + ".rbwt", rbwt)
+    reads = synth.simulate_reads_fast(g, 8000, 100, 99)
+    fq = str(tmp_path / "r.fq")
+    synth.write_fastq(fq, list(reads))
+    ref_out = str(tmp_path / "ref.sai")
+    pyoracle.run_ref(["aln", "-t", "4", prefix, fq], stdout_path=ref_out)
+    out = str(tmp_path / "gpu.sai")
+    engine.bwa_aln_core(prefix, fq, gap_init_opt(), out, 0)
+    a, b = open(ref_out, "rb").read(), open(out, "rb").read()
+    assert a[:52] == b[:52] and a[56:] == b[56:]      # byte 52..55 = n_threads

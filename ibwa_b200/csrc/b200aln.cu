@@ -58,7 +58,8 @@ __global__ void k_convert_index(RefBwt r, U4 *out, uint64_t nb)
 
 struct WidthArgs {
     FmView fm[2];
-    int n_reads;
+    int n_reads;               /* number of work items */
+    const int32_t *work_list;  /* null: work item w is read w */
     const int32_t *lens;
     const int64_t *offs;
     const uint8_t *codes;
@@ -76,9 +77,11 @@ __global__ void __launch_bounds__(128) k_width(const __grid_constant__ WidthArgs
     uint32_t *sW = A.seedW + (size_t)tid * (A.seed_len + 1);
     uint16_t *sB = A.seedB + (size_t)tid * (A.seed_len + 1);
     for (int64_t t = tid; t < 2 * (int64_t)A.n_reads; t += nthreads) {
-        const int r = (int)(t >> 1), a = (int)(t & 1);
+        const int wi = (int)(t >> 1), a = (int)(t & 1);
+        const int r = A.work_list ? A.work_list[wi] : wi;
+        const size_t slot = (size_t)2 * r + a;
         int n = width_pass(A.fm[a], A.codes + A.offs[r], A.lens[r], a, A.comp != 0, A.seed_len,
-                           A.W + (size_t)t * A.strideW, A.Q + (size_t)t * A.strideQ, sW, sB);
+                           A.W + slot * A.strideW, A.Q + slot * A.strideQ, sW, sB);
         if (a == 0) A.n_amb[r] = n;
     }
 }
@@ -541,7 +544,7 @@ static void run_batch_device(b200aln_ctx *c, int n_reads, int max_len, const int
     CK(cudaEventRecord(c->ev[1], c->st));
     WidthArgs WA;
     WA.fm[0] = c->fm[0]; WA.fm[1] = c->fm[1];
-    WA.n_reads = n_reads; WA.lens = d_lens; WA.offs = d_offs; WA.codes = d_codes;
+    WA.n_reads = n_reads; WA.work_list = nullptr; WA.lens = d_lens; WA.offs = d_offs; WA.codes = d_codes;
     WA.comp = (opt->mode & MODE_COMPREAD) ? 1 : 0; WA.seed_len = opt->seed_len;
     WA.strideQ = strideQ; WA.strideW = strideW;
     WA.Q = c->Q.as<uint64_t>(); WA.W = c->W.as<uint32_t>();
@@ -578,6 +581,12 @@ static void run_batch_device(b200aln_ctx *c, int n_reads, int max_len, const int
         c->ent_big.need((size_t)bblocks * 128 * cap_big * 16);
         c->link_big.need((size_t)bblocks * 128 * cap_big * 4);
         c->recs_big.need((size_t)n_over * c->rec_cap_big * 16);
+        /* the aborted fast pass may have edited W/Q in place (gap_shadow): rebuild them first */
+        WidthArgs WB = WA;
+        WB.n_reads = (int)n_over; WB.work_list = c->over_list.as<int32_t>();
+        k_width<<<wblocks, 128, 0, c->st>>>(WB);
+        CK(cudaGetLastError());
+        ++launches;
         SearchArgs SB = SA;
         SB.n_work = (int)n_over; SB.work_list = c->over_list.as<int32_t>();
         SB.ent = c->ent_big.as<U4>(); SB.link = c->link_big.as<uint32_t>(); SB.arena_cap = cap_big;

@@ -29,7 +29,7 @@ static std::vector<U4> convert(const b200aln_bwt_view_t *v)
 template <int NB, bool REUSE>
 static int64_t run(const SearchEnv &env, const std::vector<int> &md, int n_reads, const int32_t *lens,
                    const int64_t *offs, const uint8_t *codes, bool comp, int seed_len, uint32_t arena_cap, int rec_cap,
-                   int32_t *n_aln, std::vector<Rec> &all, uint64_t *counters)
+                   int32_t *n_aln, std::vector<Rec> &all, uint64_t *counters, uint32_t big_cap)
 {
     int max_len = 0;
     for (int r = 0; r < n_reads; ++r) if (lens[r] > max_len) max_len = lens[r];
@@ -42,6 +42,9 @@ static int64_t run(const SearchEnv &env, const std::vector<int> &md, int n_reads
     std::vector<uint32_t> link(arena_cap);
     std::vector<Rec> recs(rec_cap);
     int64_t n_status = 0;
+    std::vector<U4> ent2;
+    std::vector<uint32_t> link2;
+    std::vector<Rec> recs2;
     for (int r = 0; r < n_reads; ++r) {
         const uint8_t *fwd = codes + offs[r];
         int len = lens[r];
@@ -53,6 +56,23 @@ static int64_t run(const SearchEnv &env, const std::vector<int> &md, int n_reads
         Arena ar; ar.ent = ent.data(); ar.link = link.data(); ar.cap = arena_cap;
         lane.begin(&env, ar, Q.data(), W.data(), strideQ, strideW, recs.data(), rec_cap, len, md[len], n_amb);
         while (!lane.finished) lane.step();
+        if (lane.status != LANE_OK && big_cap) {
+            /* the product's large pass: widths rebuilt (the aborted pass shadowed them), free-list arena */
+            ++n_status;
+            if (ent2.size() < big_cap) { ent2.resize(big_cap); link2.resize(big_cap); recs2.resize(1 << 16); }
+            n_amb = width_pass(fm[0], fwd, len, 0, comp, seed_len, W.data(), Q.data(), seedW.data(), seedB.data());
+            width_pass(fm[1], fwd, len, 1, comp, seed_len, W.data() + strideW, Q.data() + strideQ, seedW.data(),
+                       seedB.data());
+            SearchLane<NB, true> big;
+            Arena ar2; ar2.ent = ent2.data(); ar2.link = link2.data(); ar2.cap = big_cap;
+            big.begin(&env, ar2, Q.data(), W.data(), strideQ, strideW, recs2.data(), 1 << 16, len, md[len], n_amb);
+            while (!big.finished) big.step();
+            if (big.status != LANE_OK) { n_aln[r] = -big.status; continue; }
+            n_aln[r] = big.n_aln;
+            all.insert(all.end(), recs2.begin(), recs2.begin() + big.n_aln);
+            if (counters) { counters[0] += big.n_pops; counters[1] += big.n_lookups; }
+            continue;
+        }
         if (lane.status != LANE_OK) { ++n_status; n_aln[r] = -lane.status; continue; }
         n_aln[r] = lane.n_aln;
         all.insert(all.end(), recs.begin(), recs.begin() + lane.n_aln);
@@ -63,7 +83,8 @@ static int64_t run(const SearchEnv &env, const std::vector<int> &md, int n_reads
 
 extern "C" int64_t hh_aln_batch(const b200aln_bwt_view_t *bwt, const b200aln_bwt_view_t *rbwt, int n_reads,
                                 const int32_t *lens, const int64_t *offs, const uint8_t *codes,
-                                const b200aln_opt_t *opt, uint32_t arena_cap, int rec_cap, int reuse, int32_t *n_aln,
+                                const b200aln_opt_t *opt, uint32_t arena_cap, int rec_cap, int reuse, uint32_t big_cap,
+                                int32_t *n_aln,
                                 Rec **records, int64_t *n_overflow, uint64_t *counters)
 {
     std::vector<U4> i0 = convert(bwt), i1 = convert(rbwt);
@@ -80,11 +101,11 @@ extern "C" int64_t hh_aln_batch(const b200aln_bwt_view_t *bwt, const b200aln_bwt
     bool comp = opt->mode & MODE_COMPREAD;
     int64_t ov;
     if (P.n_buckets <= 128) {
-        ov = reuse ? run<128, true>(env, md, n_reads, lens, offs, codes, comp, opt->seed_len, arena_cap, rec_cap, n_aln, all, counters)
-                   : run<128, false>(env, md, n_reads, lens, offs, codes, comp, opt->seed_len, arena_cap, rec_cap, n_aln, all, counters);
+        ov = reuse ? run<128, true>(env, md, n_reads, lens, offs, codes, comp, opt->seed_len, arena_cap, rec_cap, n_aln, all, counters, big_cap)
+                   : run<128, false>(env, md, n_reads, lens, offs, codes, comp, opt->seed_len, arena_cap, rec_cap, n_aln, all, counters, big_cap);
     } else {
-        ov = reuse ? run<2048, true>(env, md, n_reads, lens, offs, codes, comp, opt->seed_len, arena_cap, rec_cap, n_aln, all, counters)
-                   : run<2048, false>(env, md, n_reads, lens, offs, codes, comp, opt->seed_len, arena_cap, rec_cap, n_aln, all, counters);
+        ov = reuse ? run<2048, true>(env, md, n_reads, lens, offs, codes, comp, opt->seed_len, arena_cap, rec_cap, n_aln, all, counters, big_cap)
+                   : run<2048, false>(env, md, n_reads, lens, offs, codes, comp, opt->seed_len, arena_cap, rec_cap, n_aln, all, counters, big_cap);
     }
     *n_overflow = ov;
     Rec *out = (Rec *)malloc(sizeof(Rec) * (all.size() + 1));

@@ -51,3 +51,14 @@ def test_small_arena_flags_overflow(golden_dir, g1_index):
     n_aln, rec, nov, _ = pyharness.aln_batch(g1_index[0], g1_index[1], batch.lens, batch.offs, batch.codes,
                                              opt.to_c(), arena_cap=256, rec_cap=4)
     assert nov > 0 and (n_aln < 0).sum() == nov
+
+
+@pytest.mark.parametrize("tag", ["default", "L_e3", "stress"])
+def test_two_pass_flow_is_exact(tag, golden_dir, g1_index):
+    """Fast pass with a tiny arena / record slab, flagged reads re-run with rebuilt widths (the
+    product's large pass): bytes must equal the reference's."""
+    args, fq = CASES[tag]
+    got, nov = harness_sai(g1_index[0], g1_index[1], args, os.path.join(golden_dir, fq + ".fq.gz"),
+                           arena_cap=64, rec_cap=1, big_cap=1 << 22)
+    assert nov > 0
+    assert got == open(os.path.join(golden_dir, f"g1_{tag}.sai"), "rb").read()

@@ -98,24 +98,34 @@ struct SearchEnv {
 
 /* ---- packed per-position record Q[a][j] (built by the width pass) -------- */
 /* bits 0-2 base code | 3 eq(w[j-1]==w[j]) | 4 seed eq | 5 seed active (ii>0)
- * 8-15 seed bid[ii] | 16-23 seed bid[ii-1] | 32-47 bid[j] | 48-63 bid[j-1]      */
-B2_HD uint64_t q_pack(uint32_t base, uint32_t eq, uint32_t seq, uint32_t sact, uint32_t sb, uint32_t sbp, uint32_t bid,
-                      uint32_t bidp)
+ * 6-10 seed bid[ii] | 11-15 seed bid[ii-1] | 16-23 bid[j] | 24-31 bid[j-1]
+ * The bid fields saturate (255 / 31); every comparison in the search is against
+ * m <= max_diff resp. m_seed <= max_seed_diff, so saturation is exact as long as
+ * max_diff < 255 and max_seed_diff < 31 (checked by the host).                  */
+typedef uint32_t QRec;
+B2_HD QRec q_pack(uint32_t base, uint32_t eq, uint32_t seq, uint32_t sact, uint32_t sb, uint32_t sbp, uint32_t bid,
+                  uint32_t bidp)
 {
-    return (uint64_t)(base & 7u) | (uint64_t)(eq & 1u) << 3 | (uint64_t)(seq & 1u) << 4 | (uint64_t)(sact & 1u) << 5 |
-           (uint64_t)(sb > 255u ? 255u : sb) << 8 | (uint64_t)(sbp > 255u ? 255u : sbp) << 16 |
-           (uint64_t)(bid > 65535u ? 65535u : bid) << 32 | (uint64_t)(bidp > 65535u ? 65535u : bidp) << 48;
+    return (base & 7u) | (eq & 1u) << 3 | (seq & 1u) << 4 | (sact & 1u) << 5 | (sb > 31u ? 31u : sb) << 6 |
+           (sbp > 31u ? 31u : sbp) << 11 | (bid > 255u ? 255u : bid) << 16 | (bidp > 255u ? 255u : bidp) << 24;
 }
-B2_HD int q_base(uint64_t q) { return (int)(q & 7u); }
-B2_HD int q_eq(uint64_t q) { return (int)(q >> 3 & 1u); }
-B2_HD int q_seq(uint64_t q) { return (int)(q >> 4 & 1u); }
-B2_HD int q_sact(uint64_t q) { return (int)(q >> 5 & 1u); }
-B2_HD int q_sbid(uint64_t q) { return (int)(q >> 8 & 255u); }
-B2_HD int q_sbidp(uint64_t q) { return (int)(q >> 16 & 255u); }
-B2_HD int q_bid(uint64_t q) { return (int)(q >> 32 & 65535u); }
-B2_HD int q_bidp(uint64_t q) { return (int)(q >> 48 & 65535u); }
+B2_HD int q_base(QRec q) { return (int)(q & 7u); }
+B2_HD int q_eq(QRec q) { return (int)(q >> 3 & 1u); }
+B2_HD int q_seq(QRec q) { return (int)(q >> 4 & 1u); }
+B2_HD int q_sact(QRec q) { return (int)(q >> 5 & 1u); }
+B2_HD int q_sbid(QRec q) { return (int)(q >> 6 & 31u); }
+B2_HD int q_sbidp(QRec q) { return (int)(q >> 11 & 31u); }
+B2_HD int q_bid(QRec q) { return (int)(q >> 16 & 255u); }
+B2_HD int q_bidp(QRec q) { return (int)(q >> 24); }
 
 /* ------------------------------------------------------------- occ -------- */
+
+/* v[c] for a runtime c without forcing the array into local memory */
+B2_HD uint32_t pick4(const uint32_t v[4], int c)
+{
+    uint32_t lo = (c & 1) ? v[1] : v[0], hi = (c & 1) ? v[3] : v[2];
+    return (c & 2) ? hi : lo;
+}
 
 B2_HD uint32_t q_lower(const FmView &f, uint32_t k) { return k - (k > f.primary ? 1u : 0u); }
 B2_HD uint32_t q_upper(const FmView &f, uint32_t l) { return l + 1u - (l >= f.primary ? 1u : 0u); }
@@ -167,8 +177,8 @@ struct WidthChain {
         if (c < 4) {
             uint32_t ck[4], cl[4], ns;
             occ2x4(f, k, l, ck, cl, ns);
-            k = ck[c] + 1u;
-            l = cl[c];
+            k = pick4(ck, c) + 1u;
+            l = pick4(cl, c);
             alive = k <= l;
         }
         if (!alive) {
@@ -195,7 +205,7 @@ B2_HD int strand_sym(const uint8_t *fwd, int len, int a, int i, bool comp)
  * (bwtaln.c:123-130).  Returns the number of ambiguous symbols in the strand.
  */
 B2_HD int width_pass(const FmView &f, const uint8_t *fwd, int len, int a, bool comp, int seed_len, uint32_t *W,
-                     uint64_t *Q, uint32_t *seedW /* [seed_len+1] */, uint16_t *seedB /* [seed_len+1] */)
+                     QRec *Q, uint32_t *seedW /* [seed_len+1] */, uint16_t *seedB /* [seed_len+1] */)
 {
     const bool use_seed = len > seed_len;
     const int shift = len - seed_len; /* ii = j - shift */
@@ -237,7 +247,7 @@ B2_HD int width_pass(const FmView &f, const uint8_t *fwd, int len, int a, bool c
 
 /* gap_shadow (bwtgap.c:81-91) on the split representation, then refresh the
  * packed records it invalidated.  bid lives in Q; w in W. */
-B2_HD void shadow_update(uint32_t x, uint32_t max, int last_diff_pos, int len, uint32_t *W, uint64_t *Q)
+B2_HD void shadow_update(uint32_t x, uint32_t max, int last_diff_pos, int len, uint32_t *W, QRec *Q)
 {
     int j = 0;
     for (int i = 0; i < last_diff_pos; ++i) {
@@ -245,23 +255,29 @@ B2_HD void shadow_update(uint32_t x, uint32_t max, int last_diff_pos, int len, u
         if (w > x) W[i] = w - x;
         else if (w == x) {
             W[i] = max - (uint32_t)(++j);
-            Q[i] = (Q[i] & ~((uint64_t)0xffff << 32)) | (uint64_t)1 << 32; /* bid[i] = 1 */
+            Q[i] = (Q[i] & ~(0xffu << 16)) | 1u << 16; /* bid[i] = 1 */
         }
     }
     /* refresh eq / bid[j-1] of records 1..last_diff_pos (record ldp sees W[ldp-1]) */
     const int last = last_diff_pos < len ? last_diff_pos : len - 1; /* Q has len records */
     for (int i = 1; i <= last; ++i) {
-        uint64_t q = Q[i];
-        uint64_t bidp = Q[i - 1] >> 32 & 0xffffu;
-        uint64_t eq = W[i] == W[i - 1];
-        q = (q & ~((uint64_t)0xffff << 48 | (uint64_t)1 << 3)) | bidp << 48 | eq << 3;
-        Q[i] = q;
+        QRec q = Q[i];
+        uint32_t bidp = Q[i - 1] >> 16 & 0xffu;
+        uint32_t eq = W[i] == W[i - 1];
+        Q[i] = (q & ~(0xffu << 24 | 1u << 3)) | bidp << 24 | eq << 3;
     }
 }
 
 /* --------------------------------------------------------------- stack ---- */
 
 #define B2_NIL 0xffffffffu
+
+#ifdef B2_DEBUG_COUNTS /* logic-test instrumentation (tests/harness only) */
+extern uint64_t b2_dbg[16];
+#define B2_DBG(i) (++b2_dbg[i])
+#else
+#define B2_DBG(i) ((void)0)
+#endif
 
 /* per-lane arena in global memory: entries (16 B) + link words, bump allocated
  * (optionally with a free list through the link words, REUSE) */
@@ -271,6 +287,8 @@ struct Arena {
     uint32_t cap;
 };
 
+/* bucket heads: link-list tops by score.  The non-empty set is kept in
+ * registers for the common score ranges (<= 128 buckets). */
 template <int NB>
 struct BucketHeads {
     uint32_t head[NB];
@@ -280,10 +298,42 @@ struct BucketHeads {
         for (int i = 0; i < nb; ++i) head[i] = B2_NIL;
         for (int i = 0; i < (NB + 31) / 32; ++i) mask[i] = 0;
     }
+    B2_HD void mark(int sc) { mask[sc >> 5] |= 1u << (sc & 31); }
+    B2_HD void unmark(int sc) { mask[sc >> 5] &= ~(1u << (sc & 31)); }
     B2_HD int lowest(int nb) const
     { /* lowest non-empty bucket, nb when none */
         for (int wd = 0; wd < (NB + 31) / 32; ++wd)
             if (mask[wd]) return wd * 32 + ctz32(mask[wd]);
+        return nb;
+    }
+};
+template <>
+struct BucketHeads<128> {
+    uint32_t head[128];
+    uint32_t m0, m1, m2, m3;
+    B2_HD void clear(int nb)
+    {
+        for (int i = 0; i < nb; ++i) head[i] = B2_NIL;
+        m0 = m1 = m2 = m3 = 0;
+    }
+    B2_HD void mark(int sc)
+    {
+        const uint32_t bit = 1u << (sc & 31);
+        const int wd = sc >> 5;
+        m0 |= wd == 0 ? bit : 0u; m1 |= wd == 1 ? bit : 0u; m2 |= wd == 2 ? bit : 0u; m3 |= wd == 3 ? bit : 0u;
+    }
+    B2_HD void unmark(int sc)
+    {
+        const uint32_t bit = ~(1u << (sc & 31));
+        const int wd = sc >> 5;
+        m0 &= wd == 0 ? bit : ~0u; m1 &= wd == 1 ? bit : ~0u; m2 &= wd == 2 ? bit : ~0u; m3 &= wd == 3 ? bit : ~0u;
+    }
+    B2_HD int lowest(int nb) const
+    {
+        if (m0) return ctz32(m0);
+        if (m1) return 32 + ctz32(m1);
+        if (m2) return 64 + ctz32(m2);
+        if (m3) return 96 + ctz32(m3);
         return nb;
     }
 };
@@ -311,7 +361,7 @@ struct SearchLane {
     /* constant per read */
     const SearchEnv *env;
     Arena ar;
-    uint64_t *Q; /* [2][strideQ] */
+    QRec *Q; /* [2][strideQ] */
     uint32_t *W; /* [2][strideW] */
     int strideQ, strideW;
     Rec *recs;
@@ -328,6 +378,7 @@ struct SearchLane {
     bool have_cur, cur_held, extending;
     uint32_t ck, cl;
     int ci, cldp, cmm, cgo, cge, cstate, ca, cscore;
+    int cdmask; /* family record: which deletions exist */
     uint32_t n_pops, n_lookups; /* instrumentation: pops and 32-byte sectors of this read */
 
     B2_HD int score_of(int mm, int go, int ge) const
@@ -335,7 +386,7 @@ struct SearchLane {
         return mm * env->P.s_mm + go * env->P.s_gapo + ge * env->P.s_gape;
     }
 
-    B2_HD void begin(const SearchEnv *env_, Arena ar_, uint64_t *Q_, uint32_t *W_, int strideQ_,
+    B2_HD void begin(const SearchEnv *env_, Arena ar_, QRec *Q_, uint32_t *W_, int strideQ_,
                      int strideW_, Rec *recs_, int rec_cap_, int len_, int max_diff_, int n_amb)
     {
         const Params *P = &env_->P;
@@ -374,18 +425,45 @@ struct SearchLane {
         st_rw(ar.ent + slot, e);
         ar.link[slot] = bk.head[sc];
         bk.head[sc] = slot;
-        bk.mask[sc >> 5] |= 1u << (sc & 31);
+        bk.mark(sc);
         ++n_entries;
+    }
+
+    /* The gap-open children of one expansion (insertion + existing deletions, bwtgap.c:218-228)
+     * as ONE record in their common bucket.  They are pushed consecutively, so they sit
+     * contiguously in the bucket; the record is expanded in place into the real entries only
+     * if the search ever reaches it (step(), mode 2).  It counts as 1 + popc(dmask) entries. */
+    B2_HD void push_family(int a, int i, uint32_t k, uint32_t l, int mm, int go, int ge, int dmask)
+    {
+        int sc = score_of(mm, go + 1, ge);
+        uint32_t slot;
+        if (REUSE && free_head != B2_NIL) {
+            slot = free_head;
+            free_head = ar.link[slot];
+        } else {
+            if (top >= ar.cap) { status = LANE_ARENA_FULL; finished = true; return; }
+            slot = top++;
+        }
+        U4 e;
+        e.x = k; e.y = l;
+        e.z = (uint32_t)i | (uint32_t)dmask << 16;
+        e.w = (uint32_t)mm | (uint32_t)go << 8 | (uint32_t)ge << 16 | 3u << 24 | (uint32_t)a << 26;
+        st_rw(ar.ent + slot, e);
+        ar.link[slot] = bk.head[sc];
+        bk.head[sc] = slot;
+        bk.mark(sc);
+        n_entries += 1 + popc32((uint32_t)dmask);
     }
 
     B2_HD void pop_mem()
     {
+        B2_DBG(0);
         int b = bk.lowest(env->P.n_buckets);
         uint32_t slot = bk.head[b];
         U4 e = ld_rw(ar.ent + slot);
         uint32_t prev = ar.link[slot];
         bk.head[b] = prev;
-        if (prev == B2_NIL) bk.mask[b >> 5] &= ~(1u << (b & 31));
+        if (prev == B2_NIL) bk.unmark(b);
         if (REUSE) { ar.link[slot] = free_head; free_head = slot; }
         --n_entries;
         ck = e.x; cl = e.y;
@@ -393,6 +471,11 @@ struct SearchLane {
         cmm = (int)(e.w & 255u); cgo = (int)(e.w >> 8 & 255u); cge = (int)(e.w >> 16 & 255u);
         cstate = (int)(e.w >> 24 & 3u); ca = (int)(e.w >> 26 & 1u);
         cscore = b;
+        cdmask = 0;
+        if (cstate == 3) { /* family record: i in the low half, deletion mask in the high half */
+            cdmask = cldp;
+            n_entries -= popc32((uint32_t)cdmask);
+        }
     }
 
     /* hit bookkeeping, bwtgap.c:165-198; returns false when the search must stop */
@@ -423,21 +506,31 @@ struct SearchLane {
         return true;
     }
 
-    /* Advance until exactly one occ lookup has been issued (or the search ends). */
+    /* Advance until exactly one occ lookup has been issued (or the search ends).
+     * All three kinds of work share ONE lookup site so that the lanes of a warp meet there. */
     B2_HD void step()
     {
         const Params *P = &env->P;
         const FmView *fm = env->fm;
         const bool gape_mode = P->mode & MODE_GAPE, nonstop = P->mode & MODE_NONSTOP;
-        uint64_t q = 0;
-        int m = 0;
+        enum { EXPAND = 0, EXTEND = 1, MATERIALIZE = 2 };
+        QRec q = 0;
+        int m = 0, mode = EXPAND;
         for (;;) { /* pop until something needs a lookup */
-            if (extending) { q = Q[(size_t)ca * strideQ + (ci - 1)]; break; }
+            if (extending) { q = Q[(size_t)ca * strideQ + (ci - 1)]; mode = EXTEND; break; }
             if (!have_cur) {
                 if (n_entries == 0) { finished = true; return; }
                 if (n_entries > P->max_entries) { finished = true; return; }
                 pop_mem();
+                if (cstate == 3) {
+                    /* its members are checked one by one when they are popped; only the score
+                     * break (bwtgap.c:143) can be anticipated: the first member would trigger it */
+                    if (!nonstop && cscore > best_score + P->s_mm) { ++n_pops; finished = true; return; }
+                    mode = MATERIALIZE;
+                    break;
+                }
             } else { /* held exact child: same accounting as a push followed by a pop */
+                B2_DBG(4);
                 if (n_entries > P->max_entries) { finished = true; return; }
                 --n_entries;
             }
@@ -454,21 +547,31 @@ struct SearchLane {
                 if (!on_hit()) { finished = true; return; }
                 continue;
             }
-            if (m == 0 && (cstate == ST_M || gape_mode || cge == P->max_gape)) extending = true;
+            if (m == 0 && (cstate == ST_M || gape_mode || cge == P->max_gape)) { extending = true; mode = EXTEND; }
             break;
         }
 
-        const FmView &f = fm[1 - ca];
+        /* ---- the lookup ---- */
+        uint32_t cntk[4], cntl[4], ns;
+        occ2x4(fm[1 - ca], ck, cl, cntk, cntl, ns);
+        n_lookups += ns;
+
+        if (mode == MATERIALIZE) { /* expand a family record in place, in the reference's push order */
+            have_cur = false;
+            const int i = ci;
+            push(ca, i, ck, cl, cmm, cgo + 1, cge, ST_I, i);
+            for (int j = 0; j < 4; ++j)
+                if (cdmask >> j & 1) push(ca, i + 1, cntk[j] + 1u, cntl[j], cmm, cgo + 1, cge, ST_D, i + 1);
+            return;
+        }
+
         const int i = ci - 1;
         const int base = q_base(q);
-        uint32_t cntk[4], cntl[4], ns;
-
-        if (extending) { /* one step of bwt_match_exact_alt (bwt.c:235-250) */
+        if (mode == EXTEND) { /* one step of bwt_match_exact_alt (bwt.c:235-250) */
+            B2_DBG(5);
             if (base > 3) { extending = false; return; }
-            occ2x4(f, ck, cl, cntk, cntl, ns);
-            n_lookups += ns;
-            ck = cntk[base] + 1u;
-            cl = cntl[base];
+            ck = pick4(cntk, base) + 1u;
+            cl = pick4(cntl, base);
             if (ck > cl) { extending = false; return; }
             ci = i;
             if (ci == 0) {
@@ -478,8 +581,7 @@ struct SearchLane {
             return;
         }
 
-        occ2x4(f, ck, cl, cntk, cntl, ns);
-        n_lookups += ns;
+        B2_DBG(6);
         const uint32_t occ = cl - ck + 1u;
         bool allow_diff = true, allow_M = true;
         if (i > 0) {
@@ -501,12 +603,11 @@ struct SearchLane {
 
         if (allow_diff && i >= P->indel_end_skip + gaps && len - i >= P->indel_end_skip + gaps) {
             if (cstate == ST_M) {
-                if (cgo < P->max_gapo) {
-                    push(ca, i, ck, cl, cmm, cgo + 1, cge, ST_I, i);
-                    for (int j = 0; j < 4; ++j) {
-                        uint32_t nk = cntk[j] + 1u, nl = cntl[j];
-                        if (nk <= nl) push(ca, i + 1, nk, nl, cmm, cgo + 1, cge, ST_D, i + 1);
-                    }
+                if (cgo < P->max_gapo) { /* gap open: insertion + deletions as one family record */
+                    int dmask = 0;
+                    for (int j = 0; j < 4; ++j) dmask |= (cntk[j] + 1u <= cntl[j] ? 1 : 0) << j;
+                    B2_DBG(1);
+                    push_family(ca, i, ck, cl, cmm, cgo, cge, dmask);
                 }
             } else if (cstate == ST_I) {
                 if (cge < P->max_gape) push(ca, i, ck, cl, cmm, cgo, cge + 1, ST_I, i);
@@ -524,19 +625,20 @@ struct SearchLane {
         if (allow_diff && allow_M) {
             for (int j = 1; j <= 3; ++j) {
                 int c = (base + j) & 3;
-                uint32_t nk = cntk[c] + 1u, nl = cntl[c];
+                uint32_t nk = pick4(cntk, c) + 1u, nl = pick4(cntl, c);
+                if (nk <= nl) B2_DBG(3);
                 if (nk <= nl) push(ca, i, nk, nl, cmm + 1, cgo, cge, ST_M, i);
             }
             if (base > 3) { /* ambiguous base: the j == 4 child is a mismatch too */
                 int c = base & 3;
-                uint32_t nk = cntk[c] + 1u, nl = cntl[c];
+                uint32_t nk = pick4(cntk, c) + 1u, nl = pick4(cntl, c);
                 if (nk <= nl) push(ca, i, nk, nl, cmm + 1, cgo, cge, ST_M, i);
             } else child = true;
         } else if (base < 4) child = true;
         if (finished) return;
 
         if (child) { /* exact-match child: held in registers, counted like a push */
-            uint32_t nk = cntk[base] + 1u, nl = cntl[base];
+            uint32_t nk = pick4(cntk, base) + 1u, nl = pick4(cntl, base);
             if (nk <= nl) {
                 ck = nk; cl = nl; ci = i; cstate = ST_M; /* counters, score, ldp, strand inherited */
                 have_cur = true;

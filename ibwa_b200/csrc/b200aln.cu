@@ -64,7 +64,7 @@ struct WidthArgs {
     const int64_t *offs;
     const uint8_t *codes;
     int comp, seed_len, strideQ, strideW;
-    uint64_t *Q;
+    QRec *Q;
     uint32_t *W;
     uint32_t *seedW;
     uint16_t *seedB;
@@ -93,7 +93,7 @@ struct SearchArgs {
     const int32_t *lens;
     const int32_t *n_amb;
     const int32_t *md; /* max_diff by read length */
-    uint64_t *Q;
+    QRec *Q;
     uint32_t *W;
     int strideQ, strideW;
     U4 *ent;
@@ -501,7 +501,7 @@ struct Misc {
 template <bool REUSE>
 static void launch_search(b200aln_ctx *c, const SearchArgs &A, int blocks)
 {
-    if (A.env.P.n_buckets <= 96) k_search<96, REUSE><<<blocks, 128, 0, c->st>>>(A);
+    if (A.env.P.n_buckets <= 128) k_search<128, REUSE><<<blocks, 128, 0, c->st>>>(A);
     else if (A.env.P.n_buckets <= 256) k_search<256, REUSE><<<blocks, 128, 0, c->st>>>(A);
     else k_search<2048, REUSE><<<blocks, 128, 0, c->st>>>(A);
     CK(cudaGetLastError());
@@ -519,7 +519,7 @@ static void run_batch_device(b200aln_ctx *c, int n_reads, int max_len, const int
     const size_t lanes = (size_t)sblocks * 128;
 
     c->md.need(md.size() * 4);
-    c->Q.need((size_t)n_reads * 2 * strideQ * 8 + 64);
+    c->Q.need((size_t)n_reads * 2 * strideQ * sizeof(QRec) + 64);
     c->W.need((size_t)n_reads * 2 * strideW * 4 + 64);
     c->seedW.need((size_t)wthreads * (opt->seed_len + 1) * 4);
     c->seedB.need((size_t)wthreads * (opt->seed_len + 1) * 2);
@@ -547,7 +547,7 @@ static void run_batch_device(b200aln_ctx *c, int n_reads, int max_len, const int
     WA.n_reads = n_reads; WA.work_list = nullptr; WA.lens = d_lens; WA.offs = d_offs; WA.codes = d_codes;
     WA.comp = (opt->mode & MODE_COMPREAD) ? 1 : 0; WA.seed_len = opt->seed_len;
     WA.strideQ = strideQ; WA.strideW = strideW;
-    WA.Q = c->Q.as<uint64_t>(); WA.W = c->W.as<uint32_t>();
+    WA.Q = c->Q.as<QRec>(); WA.W = c->W.as<uint32_t>();
     WA.seedW = c->seedW.as<uint32_t>(); WA.seedB = c->seedB.as<uint16_t>(); WA.n_amb = c->n_amb.as<int32_t>();
     k_width<<<wblocks, 128, 0, c->st>>>(WA);
     CK(cudaGetLastError());

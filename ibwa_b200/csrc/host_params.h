@@ -58,6 +58,8 @@ inline void make_params(const b200aln_opt_t &o, int max_len, const int32_t *lens
     if (P.n_buckets < 1 || P.n_buckets > 2048)
         fatal("b200aln_batch", "score range outside [1,2048] (bwtgap.c:54 packs the score in 11 bits).");
     if (o.seed_len < 0) fatal("b200aln_batch", "negative seed length.");
+    if (batch_max_diff >= 255 || o.max_diff >= 255 || o.max_seed_diff >= 31)
+        fatal("b200aln_batch", "max_diff >= 255 or max_seed_diff >= 31 exceed the packed width-record fields.");
     md.assign((size_t)max_len + 1, o.max_diff);
     if (o.fnr > 0.0f) {
         if (max_len <= 1024) {

@@ -8,6 +8,11 @@
 #include <cstring>
 #include <vector>
 
+#ifdef B2_DEBUG_COUNTS
+#include <cstdint>
+namespace b2 { uint64_t b2_dbg[16]; }
+extern "C" uint64_t *hh_dbg() { return b2::b2_dbg; }
+#endif
 #include "../../include/b200aln.h"
 #include "../../ibwa_b200/csrc/aln_core.cuh"
 #include "../../ibwa_b200/csrc/fm_layout.cuh"
@@ -34,7 +39,7 @@ static int64_t run(const SearchEnv &env, const std::vector<int> &md, int n_reads
     int max_len = 0;
     for (int r = 0; r < n_reads; ++r) if (lens[r] > max_len) max_len = lens[r];
     const int strideQ = max_len, strideW = max_len + 1;
-    std::vector<uint64_t> Q(2 * (size_t)strideQ + 2);
+    std::vector<QRec> Q(2 * (size_t)strideQ + 2);
     std::vector<uint32_t> W(2 * (size_t)strideW);
     std::vector<uint32_t> seedW(seed_len + 1);
     std::vector<uint16_t> seedB(seed_len + 1);

@@ -43,18 +43,24 @@ struct alignas(16) U4 {
 
 #if defined(__CUDA_ARCH__)
 B2_D U4 ld_ro(const U4 *p)
-{ /* read-only index data: non-coherent path */
-    uint4 v = __ldg(reinterpret_cast<const uint4 *>(p));
-    U4 r; r.x = v.x; r.y = v.y; r.z = v.z; r.w = v.w;
+{ /* read-only index data: non-coherent path, not allocated in L1 (no reuse; keeps L1 for the
+     per-read width records that ARE re-read along a chain) */
+    U4 r;
+    asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0,%1,%2,%3}, [%4];"
+                 : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "l"(p));
     return r;
 }
 B2_D U4 ld_rw(const U4 *p)
-{
-    uint4 v = *reinterpret_cast<const uint4 *>(p);
-    U4 r; r.x = v.x; r.y = v.y; r.z = v.z; r.w = v.w;
+{ /* stack entries: written once, read at most once -> L2 only */
+    U4 r;
+    asm volatile("ld.global.cg.v4.u32 {%0,%1,%2,%3}, [%4];"
+                 : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "l"(p) : "memory");
     return r;
 }
-B2_D void st_rw(U4 *p, U4 v) { *reinterpret_cast<uint4 *>(p) = make_uint4(v.x, v.y, v.z, v.w); }
+B2_D void st_rw(U4 *p, U4 v)
+{
+    asm volatile("st.global.cg.v4.u32 [%0], {%1,%2,%3,%4};" :: "l"(p), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
+}
 B2_D int popc32(uint32_t v) { return __popc(v); }
 B2_D int ctz32(uint32_t v) { return __ffs((int)v) - 1; }
 #else
@@ -287,35 +293,31 @@ struct Arena {
     uint32_t cap;
 };
 
-/* bucket heads: link-list tops by score.  The non-empty set is kept in
- * registers for the common score ranges (<= 128 buckets). */
-template <int NB>
-struct BucketHeads {
-    uint32_t head[NB];
-    uint32_t mask[(NB + 31) / 32];
-    B2_HD void clear(int nb)
-    {
-        for (int i = 0; i < nb; ++i) head[i] = B2_NIL;
-        for (int i = 0; i < (NB + 31) / 32; ++i) mask[i] = 0;
-    }
-    B2_HD void mark(int sc) { mask[sc >> 5] |= 1u << (sc & 31); }
-    B2_HD void unmark(int sc) { mask[sc >> 5] &= ~(1u << (sc & 31)); }
-    B2_HD int lowest(int nb) const
-    { /* lowest non-empty bucket, nb when none */
-        for (int wd = 0; wd < (NB + 31) / 32; ++wd)
-            if (mask[wd]) return wd * 32 + ctz32(mask[wd]);
-        return nb;
-    }
-};
-template <>
-struct BucketHeads<128> {
-    uint32_t head[128];
+/* Bucket heads (top slot of each score bucket's linked list) and the set of
+ * non-empty buckets.  Two storage policies; both keep the lane's scalar state
+ * out of local memory (no dynamically indexed member arrays in SearchLane).
+ *
+ * HeadsStrided16: 16-bit heads at h[sc * stride] — the fast kernel points h at a
+ *   shared-memory column (stride = threads per block, conflict free), the CPU
+ *   harness at a plain array (stride 1).  Needs n_buckets <= 128 and arena
+ *   capacity < 65535; the non-empty set lives in four registers.
+ * HeadsWide32: 32-bit heads and mask words in global memory — the large-arena
+ *   pass and exotic score ranges (up to 2048 buckets). */
+struct HeadsStrided16 {
+    uint16_t *h;
+    int stride;
     uint32_t m0, m1, m2, m3;
     B2_HD void clear(int nb)
     {
-        for (int i = 0; i < nb; ++i) head[i] = B2_NIL;
+        for (int i = 0; i < nb; ++i) h[(size_t)i * stride] = 0xffffu;
         m0 = m1 = m2 = m3 = 0;
     }
+    B2_HD uint32_t get(int sc) const
+    {
+        uint32_t v = h[(size_t)sc * stride];
+        return v == 0xffffu ? B2_NIL : v;
+    }
+    B2_HD void set(int sc, uint32_t slot) { h[(size_t)sc * stride] = (uint16_t)slot; }
     B2_HD void mark(int sc)
     {
         const uint32_t bit = 1u << (sc & 31);
@@ -338,6 +340,26 @@ struct BucketHeads<128> {
     }
 };
 
+struct HeadsWide32 {
+    uint32_t *h;    /* [n_buckets] */
+    uint32_t *mask; /* [(n_buckets + 31) / 32] */
+    B2_HD void clear(int nb)
+    {
+        for (int i = 0; i < nb; ++i) h[i] = B2_NIL;
+        for (int i = 0; i < (nb + 31) / 32; ++i) mask[i] = 0;
+    }
+    B2_HD uint32_t get(int sc) const { return h[sc]; }
+    B2_HD void set(int sc, uint32_t slot) { h[sc] = slot; }
+    B2_HD void mark(int sc) { mask[sc >> 5] |= 1u << (sc & 31); }
+    B2_HD void unmark(int sc) { mask[sc >> 5] &= ~(1u << (sc & 31)); }
+    B2_HD int lowest(int nb) const
+    {
+        for (int wd = 0; wd < (nb + 31) / 32; ++wd)
+            if (mask[wd]) return wd * 32 + ctz32(mask[wd]);
+        return nb;
+    }
+};
+
 enum LaneStatus { LANE_OK = 0, LANE_ARENA_FULL = 1, LANE_REC_FULL = 2 };
 
 /*
@@ -356,7 +378,7 @@ enum LaneStatus { LANE_OK = 0, LANE_ARENA_FULL = 1, LANE_REC_FULL = 2 };
  *    reuse of bwtgap.c:60), which requires positive penalties (checked by the
  *    host before launch).
  */
-template <int NB, bool REUSE>
+template <class Heads, bool REUSE>
 struct SearchLane {
     /* constant per read */
     const SearchEnv *env;
@@ -368,7 +390,7 @@ struct SearchLane {
     int rec_cap;
     int len, opt_max_diff;
     /* mutable */
-    BucketHeads<NB> bk;
+    Heads bk;
     uint32_t top, free_head; /* bump pointer / free list */
     int n_entries;           /* the reference's stack->n_entries (memory + held) */
     int max_diff, best_score, best_diff, best_cnt, n_aln;
@@ -386,9 +408,10 @@ struct SearchLane {
         return mm * env->P.s_mm + go * env->P.s_gapo + ge * env->P.s_gape;
     }
 
-    B2_HD void begin(const SearchEnv *env_, Arena ar_, QRec *Q_, uint32_t *W_, int strideQ_,
+    B2_HD void begin(const SearchEnv *env_, Arena ar_, Heads heads_, QRec *Q_, uint32_t *W_, int strideQ_,
                      int strideW_, Rec *recs_, int rec_cap_, int len_, int max_diff_, int n_amb)
     {
+        bk = heads_;
         const Params *P = &env_->P;
         const FmView *fm = env_->fm;
         env = env_; ar = ar_; Q = Q_; W = W_; strideQ = strideQ_; strideW = strideW_;
@@ -423,8 +446,8 @@ struct SearchLane {
         e.z = (uint32_t)i | (uint32_t)ldp << 16;
         e.w = (uint32_t)mm | (uint32_t)go << 8 | (uint32_t)ge << 16 | (uint32_t)state << 24 | (uint32_t)a << 26;
         st_rw(ar.ent + slot, e);
-        ar.link[slot] = bk.head[sc];
-        bk.head[sc] = slot;
+        ar.link[slot] = bk.get(sc);
+        bk.set(sc, slot);
         bk.mark(sc);
         ++n_entries;
     }
@@ -449,8 +472,8 @@ struct SearchLane {
         e.z = (uint32_t)i | (uint32_t)dmask << 16;
         e.w = (uint32_t)mm | (uint32_t)go << 8 | (uint32_t)ge << 16 | 3u << 24 | (uint32_t)a << 26;
         st_rw(ar.ent + slot, e);
-        ar.link[slot] = bk.head[sc];
-        bk.head[sc] = slot;
+        ar.link[slot] = bk.get(sc);
+        bk.set(sc, slot);
         bk.mark(sc);
         n_entries += 1 + popc32((uint32_t)dmask);
     }
@@ -459,10 +482,10 @@ struct SearchLane {
     {
         B2_DBG(0);
         int b = bk.lowest(env->P.n_buckets);
-        uint32_t slot = bk.head[b];
+        uint32_t slot = bk.get(b);
         U4 e = ld_rw(ar.ent + slot);
         uint32_t prev = ar.link[slot];
-        bk.head[b] = prev;
+        bk.set(b, prev);
         if (prev == B2_NIL) bk.unmark(b);
         if (REUSE) { ar.link[slot] = free_head; free_head = slot; }
         --n_entries;

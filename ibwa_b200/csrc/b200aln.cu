@@ -108,10 +108,34 @@ struct SearchArgs {
     unsigned int *n_over;
     int32_t *over_list;
     unsigned long long *stat; /* [0] pops, [1] sectors */
+    uint32_t *heads_wide;     /* HeadsWide32 only: per lane n_buckets heads + mask words */
+    int heads_wide_stride;
 };
 
-template <int NB, bool REUSE>
-__global__ void __launch_bounds__(128) k_search(const __grid_constant__ SearchArgs A)
+template <class Heads> struct HeadsFactory;
+template <> struct HeadsFactory<HeadsStrided16> {
+    static __device__ __forceinline__ HeadsStrided16 make(const SearchArgs &, size_t)
+    {
+        extern __shared__ uint16_t sm_heads[]; /* [n_buckets][blockDim.x] */
+        HeadsStrided16 hd;
+        hd.h = sm_heads + threadIdx.x;
+        hd.stride = (int)blockDim.x;
+        hd.m0 = hd.m1 = hd.m2 = hd.m3 = 0;
+        return hd;
+    }
+};
+template <> struct HeadsFactory<HeadsWide32> {
+    static __device__ __forceinline__ HeadsWide32 make(const SearchArgs &A, size_t gl)
+    {
+        HeadsWide32 hd;
+        hd.h = A.heads_wide + gl * (size_t)A.heads_wide_stride;
+        hd.mask = hd.h + A.env.P.n_buckets;
+        return hd;
+    }
+};
+
+template <class Heads, bool REUSE, int MINB>
+__global__ void __launch_bounds__(128, MINB) k_search(const __grid_constant__ SearchArgs A)
 {
     const unsigned FULL = 0xffffffffu;
     const int lane = threadIdx.x & 31;
@@ -120,8 +144,9 @@ __global__ void __launch_bounds__(128) k_search(const __grid_constant__ SearchAr
     ar.ent = A.ent + gl * A.arena_cap;
     ar.link = A.link + gl * A.arena_cap;
     ar.cap = A.arena_cap;
-    SearchLane<NB, REUSE> L;
+    SearchLane<Heads, REUSE> L;
     L.finished = true;
+    const Heads heads = HeadsFactory<Heads>::make(A, gl);
     bool alive = true, active = false;
     int r = -1;
     unsigned w = 0;
@@ -141,7 +166,7 @@ __global__ void __launch_bounds__(128) k_search(const __grid_constant__ SearchAr
                     r = A.work_list ? A.work_list[w] : (int)w;
                     const int len = A.lens[r];
                     const size_t slab = A.recs_by_work ? (size_t)w : (size_t)r;
-                    L.begin(&A.env, ar, A.Q + (size_t)2 * r * A.strideQ, A.W + (size_t)2 * r * A.strideW, A.strideQ,
+                    L.begin(&A.env, ar, heads, A.Q + (size_t)2 * r * A.strideQ, A.W + (size_t)2 * r * A.strideW, A.strideQ,
                             A.strideW, A.recs + slab * A.rec_cap, A.rec_cap, len, A.md[len], A.n_amb[r]);
                     active = true;
                 } else alive = false;
@@ -320,12 +345,12 @@ struct b200aln_ctx {
     cudaEvent_t ev[8];
     cudaEvent_t tm[2];
     /* tuning */
-    int search_blocks_per_sm = 6, width_blocks_per_sm = 8;
+    int search_blocks_per_sm = 5, width_blocks_per_sm = 8;
     uint32_t arena_cap = 4096, arena_cap_big = 0; /* 0: max_entries + 64 */
     int rec_cap = 8, rec_cap_big = 1 << 16, big_lanes = 1024;
     /* device buffers */
     DevBuf lens, offs, codes, md, Q, W, seedW, seedB, n_amb, ent, link, recs, n_aln, over_slot, over_list, misc, off64,
-        blk_tot, packed, ent_big, link_big, recs_big;
+        blk_tot, packed, ent_big, link_big, recs_big, heads_wide, heads_wide_big;
     HostBuf h_in, h_out, h_misc;
     b200aln_stats_t stats;
 };
@@ -451,7 +476,7 @@ extern "C" void b200aln_close(b200aln_ctx *c)
     cudaStreamSynchronize(c->st);
     DevBuf *bufs[] = {&c->lens, &c->offs, &c->codes, &c->md, &c->Q, &c->W, &c->seedW, &c->seedB, &c->n_amb, &c->ent,
                       &c->link, &c->recs, &c->n_aln, &c->over_slot, &c->over_list, &c->misc, &c->off64, &c->blk_tot,
-                      &c->packed, &c->ent_big, &c->link_big, &c->recs_big};
+                      &c->packed, &c->ent_big, &c->link_big, &c->recs_big, &c->heads_wide, &c->heads_wide_big};
     for (DevBuf *b : bufs) b->release();
     c->h_in.release(); c->h_out.release(); c->h_misc.release();
     for (int i = 0; i < 2; ++i) if (c->d_idx[i]) cudaFree(c->d_idx[i]);
@@ -498,12 +523,31 @@ struct Misc {
     long long total;
 };
 
-template <bool REUSE>
-static void launch_search(b200aln_ctx *c, const SearchArgs &A, int blocks)
+/* fast pass: 16-bit heads in shared memory when the score range and the arena allow it */
+static bool fast_heads_ok(const b200aln_ctx *c, const Params &P) { return P.n_buckets <= 128 && c->arena_cap < 65535u; }
+
+static void launch_search_fast(b200aln_ctx *c, SearchArgs &A, int blocks)
 {
-    if (A.env.P.n_buckets <= 128) k_search<128, REUSE><<<blocks, 128, 0, c->st>>>(A);
-    else if (A.env.P.n_buckets <= 256) k_search<256, REUSE><<<blocks, 128, 0, c->st>>>(A);
-    else k_search<2048, REUSE><<<blocks, 128, 0, c->st>>>(A);
+    if (fast_heads_ok(c, A.env.P)) {
+        const size_t smem = (size_t)A.env.P.n_buckets * 128 * sizeof(uint16_t);
+        if (c->search_blocks_per_sm > 6) k_search<HeadsStrided16, false, 8><<<blocks, 128, smem, c->st>>>(A);
+        else if (c->search_blocks_per_sm == 6) k_search<HeadsStrided16, false, 6><<<blocks, 128, smem, c->st>>>(A);
+        else k_search<HeadsStrided16, false, 1><<<blocks, 128, smem, c->st>>>(A);
+    } else {
+        A.heads_wide_stride = A.env.P.n_buckets + (A.env.P.n_buckets + 31) / 32;
+        c->heads_wide.need((size_t)blocks * 128 * A.heads_wide_stride * 4);
+        A.heads_wide = c->heads_wide.as<uint32_t>();
+        k_search<HeadsWide32, false, 1><<<blocks, 128, 0, c->st>>>(A);
+    }
+    CK(cudaGetLastError());
+}
+
+static void launch_search_big(b200aln_ctx *c, SearchArgs &A, int blocks)
+{
+    A.heads_wide_stride = A.env.P.n_buckets + (A.env.P.n_buckets + 31) / 32;
+    c->heads_wide_big.need((size_t)blocks * 128 * A.heads_wide_stride * 4);
+    A.heads_wide = c->heads_wide_big.as<uint32_t>();
+    k_search<HeadsWide32, true, 1><<<blocks, 128, 0, c->st>>>(A);
     CK(cudaGetLastError());
 }
 
@@ -564,7 +608,8 @@ static void run_batch_device(b200aln_ctx *c, int n_reads, int max_len, const int
     SA.n_aln = c->n_aln.as<int32_t>(); SA.over_slot = nullptr;
     SA.counter = &dm->counter; SA.n_over = &dm->n_over; SA.over_list = c->over_list.as<int32_t>();
     SA.stat = dm->stat;
-    launch_search<false>(c, SA, sblocks);
+    SA.heads_wide = nullptr; SA.heads_wide_stride = 0;
+    launch_search_fast(c, SA, sblocks);
     ++launches;
     CK(cudaEventRecord(c->ev[3], c->st));
 
@@ -593,7 +638,7 @@ static void run_batch_device(b200aln_ctx *c, int n_reads, int max_len, const int
         SB.recs = c->recs_big.as<Rec>(); SB.rec_cap = c->rec_cap_big; SB.recs_by_work = 1;
         SB.over_slot = c->over_slot.as<int32_t>();
         SB.counter = &dm->counter_big; SB.n_over = nullptr; SB.over_list = nullptr;
-        launch_search<true>(c, SB, bblocks);
+        launch_search_big(c, SB, bblocks);
         ++launches;
     }
     CK(cudaEventRecord(c->ev[4], c->st));

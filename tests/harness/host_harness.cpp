@@ -31,7 +31,24 @@ static std::vector<U4> convert(const b200aln_bwt_view_t *v)
     return out;
 }
 
-template <int NB, bool REUSE>
+template <class Heads> static Heads make_heads(std::vector<uint32_t> &store);
+template <> HeadsStrided16 make_heads<HeadsStrided16>(std::vector<uint32_t> &store)
+{
+    HeadsStrided16 hd;
+    hd.h = reinterpret_cast<uint16_t *>(store.data());
+    hd.stride = 1;
+    hd.m0 = hd.m1 = hd.m2 = hd.m3 = 0;
+    return hd;
+}
+template <> HeadsWide32 make_heads<HeadsWide32>(std::vector<uint32_t> &store)
+{
+    HeadsWide32 hd;
+    hd.h = store.data();
+    hd.mask = store.data() + 2048;
+    return hd;
+}
+
+template <class Heads, bool REUSE>
 static int64_t run(const SearchEnv &env, const std::vector<int> &md, int n_reads, const int32_t *lens,
                    const int64_t *offs, const uint8_t *codes, bool comp, int seed_len, uint32_t arena_cap, int rec_cap,
                    int32_t *n_aln, std::vector<Rec> &all, uint64_t *counters, uint32_t big_cap)
@@ -47,6 +64,7 @@ static int64_t run(const SearchEnv &env, const std::vector<int> &md, int n_reads
     std::vector<uint32_t> link(arena_cap);
     std::vector<Rec> recs(rec_cap);
     int64_t n_status = 0;
+    std::vector<uint32_t> hstore(2048 + 64);
     std::vector<U4> ent2;
     std::vector<uint32_t> link2;
     std::vector<Rec> recs2;
@@ -57,9 +75,9 @@ static int64_t run(const SearchEnv &env, const std::vector<int> &md, int n_reads
         int n_amb = width_pass(fm[0], fwd, len, 0, comp, seed_len, W.data(), Q.data(), seedW.data(), seedB.data());
         width_pass(fm[1], fwd, len, 1, comp, seed_len, W.data() + strideW, Q.data() + strideQ, seedW.data(),
                    seedB.data());
-        SearchLane<NB, REUSE> lane;
+        SearchLane<Heads, REUSE> lane;
         Arena ar; ar.ent = ent.data(); ar.link = link.data(); ar.cap = arena_cap;
-        lane.begin(&env, ar, Q.data(), W.data(), strideQ, strideW, recs.data(), rec_cap, len, md[len], n_amb);
+        lane.begin(&env, ar, make_heads<Heads>(hstore), Q.data(), W.data(), strideQ, strideW, recs.data(), rec_cap, len, md[len], n_amb);
         while (!lane.finished) lane.step();
         if (lane.status != LANE_OK && big_cap) {
             /* the product's large pass: widths rebuilt (the aborted pass shadowed them), free-list arena */
@@ -68,9 +86,9 @@ static int64_t run(const SearchEnv &env, const std::vector<int> &md, int n_reads
             n_amb = width_pass(fm[0], fwd, len, 0, comp, seed_len, W.data(), Q.data(), seedW.data(), seedB.data());
             width_pass(fm[1], fwd, len, 1, comp, seed_len, W.data() + strideW, Q.data() + strideQ, seedW.data(),
                        seedB.data());
-            SearchLane<NB, true> big;
+            SearchLane<HeadsWide32, true> big;
             Arena ar2; ar2.ent = ent2.data(); ar2.link = link2.data(); ar2.cap = big_cap;
-            big.begin(&env, ar2, Q.data(), W.data(), strideQ, strideW, recs2.data(), 1 << 16, len, md[len], n_amb);
+            big.begin(&env, ar2, make_heads<HeadsWide32>(hstore), Q.data(), W.data(), strideQ, strideW, recs2.data(), 1 << 16, len, md[len], n_amb);
             while (!big.finished) big.step();
             if (big.status != LANE_OK) { n_aln[r] = -big.status; continue; }
             n_aln[r] = big.n_aln;
@@ -105,12 +123,12 @@ extern "C" int64_t hh_aln_batch(const b200aln_bwt_view_t *bwt, const b200aln_bwt
     std::vector<Rec> all;
     bool comp = opt->mode & MODE_COMPREAD;
     int64_t ov;
-    if (P.n_buckets <= 128) {
-        ov = reuse ? run<128, true>(env, md, n_reads, lens, offs, codes, comp, opt->seed_len, arena_cap, rec_cap, n_aln, all, counters, big_cap)
-                   : run<128, false>(env, md, n_reads, lens, offs, codes, comp, opt->seed_len, arena_cap, rec_cap, n_aln, all, counters, big_cap);
+    if (P.n_buckets <= 128 && arena_cap < 65535) {
+        ov = reuse ? run<HeadsStrided16, true>(env, md, n_reads, lens, offs, codes, comp, opt->seed_len, arena_cap, rec_cap, n_aln, all, counters, big_cap)
+                   : run<HeadsStrided16, false>(env, md, n_reads, lens, offs, codes, comp, opt->seed_len, arena_cap, rec_cap, n_aln, all, counters, big_cap);
     } else {
-        ov = reuse ? run<2048, true>(env, md, n_reads, lens, offs, codes, comp, opt->seed_len, arena_cap, rec_cap, n_aln, all, counters, big_cap)
-                   : run<2048, false>(env, md, n_reads, lens, offs, codes, comp, opt->seed_len, arena_cap, rec_cap, n_aln, all, counters, big_cap);
+        ov = reuse ? run<HeadsWide32, true>(env, md, n_reads, lens, offs, codes, comp, opt->seed_len, arena_cap, rec_cap, n_aln, all, counters, big_cap)
+                   : run<HeadsWide32, false>(env, md, n_reads, lens, offs, codes, comp, opt->seed_len, arena_cap, rec_cap, n_aln, all, counters, big_cap);
     }
     *n_overflow = ov;
     Rec *out = (Rec *)malloc(sizeof(Rec) * (all.size() + 1));

@@ -28,17 +28,26 @@ def harness_sai(bwt, rbwt, args, fq, **kw):
 def test_core_matches_reference(tag, golden_dir, g1_index):
     args, fq = CASES[tag]
     got, nov = harness_sai(g1_index[0], g1_index[1], args, os.path.join(golden_dir, fq + ".fq.gz"),
-                           arena_cap=1 << 22, rec_cap=4096)
+                           arena_cap=65000, rec_cap=4096)
     want = open(os.path.join(golden_dir, f"g1_{tag}.sai"), "rb").read()
     assert nov == 0
     assert got == want
+
+
+@pytest.mark.parametrize("tag", sorted(CASES))
+def test_core_wide_heads_variant(tag, golden_dir, g1_index):
+    """The large-pass configuration (32-bit heads in memory, big arena) on every case."""
+    args, fq = CASES[tag]
+    got, nov = harness_sai(g1_index[0], g1_index[1], args, os.path.join(golden_dir, fq + ".fq.gz"),
+                           arena_cap=1 << 22, rec_cap=4096, reuse=True)
+    assert nov == 0 and got == open(os.path.join(golden_dir, f"g1_{tag}.sai"), "rb").read()
 
 
 @pytest.mark.parametrize("tag", ["default", "stress", "m200"])
 def test_core_free_list_variant(tag, golden_dir, g1_index):
     args, fq = CASES[tag]
     got, nov = harness_sai(g1_index[0], g1_index[1], args, os.path.join(golden_dir, fq + ".fq.gz"),
-                           arena_cap=1 << 22, rec_cap=4096, reuse=True)
+                           arena_cap=65000, rec_cap=4096, reuse=True)
     want = open(os.path.join(golden_dir, f"g1_{tag}.sai"), "rb").read()
     assert nov == 0 and got == want
 

@@ -416,12 +416,13 @@ def main():
         else:
             peak, which = 6650.0, "fallback (B200_PROFILING.md)"
         sector_roof = eng.sector_roofline(1 << 28, 3)
+        pair_roof = eng.sector_roofline(1 << 27, -3)
         out["roofline"] = {"bound": "hbm", "kernel": "k_search", "achieved": achieved, "peak": peak, "unit": "GB/s",
                            "frac": achieved / peak, "traffic": None, "peak_source": which,
                            "algorithmic_bytes_per_read": bytes_per_read,
                            "oracle_lookups_per_read": lookups_per_read,
                            "oracle_pops_per_read": port["stats"]["pops"] / port["n"],
-                           "random_sector_roof_gbs": sector_roof,
+                           "random_sector_roof_gbs": sector_roof, "random_64B_pair_roof_gbs": pair_roof,
                            "frac_of_random_sector_roof": achieved / sector_roof if sector_roof else None,
                            "occ_sectors_per_s": last["occ_lookups"] / (ms_search * 1e-3)}
         # parity of this very run against the oracle port on the sample

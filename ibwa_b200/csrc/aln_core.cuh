@@ -41,32 +41,49 @@ struct alignas(16) U4 {
     uint32_t x, y, z, w;
 };
 
+/* one occ block = one 32-byte sector: checkpoint counts + two bit planes of 64 bases */
+struct alignas(32) OccBlk {
+    U4 cnt;  /* L2[c] + occurrences of c before the block */
+    U4 bits; /* lo0, lo1, hi0, hi1 */
+};
+
+/* one stack entry = one 32-byte sector, written and read with single 256-bit accesses */
+struct alignas(32) StackEnt {
+    U4 e;          /* k, l, i | ldp<<16, n_mm | n_gapo<<8 | n_gape<<16 | state<<24 | a<<26 */
+    uint32_t link; /* previous entry of the same bucket (or next free slot) */
+    uint32_t pad[3];
+};
+
 #if defined(__CUDA_ARCH__)
-B2_D U4 ld_ro(const U4 *p)
-{ /* read-only index data: non-coherent path, not allocated in L1 (no reuse; keeps L1 for the
-     per-read width records that ARE re-read along a chain) */
-    U4 r;
-    asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0,%1,%2,%3}, [%4];"
-                 : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "l"(p));
+B2_D OccBlk ld_blk(const OccBlk *p)
+{ /* read-only index data: one 256-bit load on the non-coherent path, not allocated in L1
+     (no reuse; keeps L1 for the per-read width records that ARE re-read along a chain) */
+    OccBlk r;
+    asm volatile("ld.global.nc.L1::no_allocate.v8.u32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                 : "=r"(r.cnt.x), "=r"(r.cnt.y), "=r"(r.cnt.z), "=r"(r.cnt.w), "=r"(r.bits.x), "=r"(r.bits.y),
+                   "=r"(r.bits.z), "=r"(r.bits.w)
+                 : "l"(p));
     return r;
 }
-B2_D U4 ld_rw(const U4 *p)
+B2_D void ld_ent(const StackEnt *p, U4 &e, uint32_t &link)
 { /* stack entries: written once, read at most once -> L2 only */
-    U4 r;
-    asm volatile("ld.global.cg.v4.u32 {%0,%1,%2,%3}, [%4];"
-                 : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "l"(p) : "memory");
-    return r;
+    uint32_t p0, p1, p2;
+    asm volatile("ld.global.cg.v8.u32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                 : "=r"(e.x), "=r"(e.y), "=r"(e.z), "=r"(e.w), "=r"(link), "=r"(p0), "=r"(p1), "=r"(p2)
+                 : "l"(p) : "memory");
+    (void)p0; (void)p1; (void)p2;
 }
-B2_D void st_rw(U4 *p, U4 v)
-{
-    asm volatile("st.global.cg.v4.u32 [%0], {%1,%2,%3,%4};" :: "l"(p), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
+B2_D void st_ent(StackEnt *p, U4 e, uint32_t link)
+{ /* a full sector per store: no read-modify-write in the memory system */
+    asm volatile("st.global.cg.v8.u32 [%0], {%1,%2,%3,%4,%5,%6,%6,%6};"
+                 :: "l"(p), "r"(e.x), "r"(e.y), "r"(e.z), "r"(e.w), "r"(link), "r"(0u) : "memory");
 }
 B2_D int popc32(uint32_t v) { return __popc(v); }
 B2_D int ctz32(uint32_t v) { return __ffs((int)v) - 1; }
 #else
-inline U4 ld_ro(const U4 *p) { return *p; }
-inline U4 ld_rw(const U4 *p) { return *p; }
-inline void st_rw(U4 *p, U4 v) { *p = v; }
+inline OccBlk ld_blk(const OccBlk *p) { return *p; }
+inline void ld_ent(const StackEnt *p, U4 &e, uint32_t &link) { e = p->e; link = p->link; }
+inline void st_ent(StackEnt *p, U4 e, uint32_t link) { p->e = e; p->link = link; p->pad[0] = p->pad[1] = p->pad[2] = 0; }
 inline int popc32(uint32_t v) { return __builtin_popcount(v); }
 inline int ctz32(uint32_t v) { return __builtin_ctz(v); }
 #endif
@@ -75,7 +92,7 @@ enum { MODE_GAPE = 0x01, MODE_COMPREAD = 0x02, MODE_LOGGAP = 0x04, MODE_NONSTOP 
 enum { ST_M = 0, ST_I = 1, ST_D = 2 };
 
 struct FmView {
-    const U4 *blk;    /* 2 x U4 per 64-base block */
+    const OccBlk *blk; /* one per 64 bases */
     uint32_t primary; /* row of the sentinel */
     uint32_t seq_len;
 };
@@ -154,17 +171,15 @@ B2_HD void occ_count4(U4 c, U4 b, uint32_t r, uint32_t o[4])
 B2_HD void occ2x4(const FmView &f, uint32_t k, uint32_t l, uint32_t ck[4], uint32_t cl[4], uint32_t &n_sectors)
 {
     uint32_t qa = q_lower(f, k), qb = q_upper(f, l);
-    const U4 *pa = f.blk + 2 * (size_t)(qa >> 6), *pb = f.blk + 2 * (size_t)(qb >> 6);
-    U4 ca = ld_ro(pa), ba = ld_ro(pa + 1);
-    U4 cb = ca, bb = ba;
+    const OccBlk *pa = f.blk + (qa >> 6), *pb = f.blk + (qb >> 6);
+    OccBlk ba = ld_blk(pa), bb = ba;
     n_sectors = 1;
     if (pa != pb) {
-        cb = ld_ro(pb);
-        bb = ld_ro(pb + 1);
+        bb = ld_blk(pb);
         n_sectors = 2;
     }
-    occ_count4(ca, ba, qa & 63u, ck);
-    occ_count4(cb, bb, qb & 63u, cl);
+    occ_count4(ba.cnt, ba.bits, qa & 63u, ck);
+    occ_count4(bb.cnt, bb.bits, qb & 63u, cl);
 }
 
 /* ---------------------------------------------------------- width pass ---- */
@@ -285,11 +300,10 @@ extern uint64_t b2_dbg[16];
 #define B2_DBG(i) ((void)0)
 #endif
 
-/* per-lane arena in global memory: entries (16 B) + link words, bump allocated
- * (optionally with a free list through the link words, REUSE) */
+/* per-lane arena in global memory: 32-byte entries, bump allocated (optionally with a
+ * free list through the link words, REUSE) */
 struct Arena {
-    U4 *ent;        /* [cap] k, l, i | ldp<<16, n_mm | n_gapo<<8 | n_gape<<16 | state<<24 | a<<26 */
-    uint32_t *link; /* [cap] previous entry of the same bucket */
+    StackEnt *ent; /* [cap] */
     uint32_t cap;
 };
 
@@ -381,7 +395,6 @@ enum LaneStatus { LANE_OK = 0, LANE_ARENA_FULL = 1, LANE_REC_FULL = 2 };
 template <class Heads, bool REUSE>
 struct SearchLane {
     /* constant per read */
-    const SearchEnv *env;
     Arena ar;
     QRec *Q; /* [2][strideQ] */
     uint32_t *W; /* [2][strideW] */
@@ -403,21 +416,23 @@ struct SearchLane {
     int cdmask; /* family record: which deletions exist */
     uint32_t n_pops, n_lookups; /* instrumentation: pops and 32-byte sectors of this read */
 
-    B2_HD int score_of(int mm, int go, int ge) const
+    static B2_HD int score_of(const Params &P, int mm, int go, int ge)
     {
-        return mm * env->P.s_mm + go * env->P.s_gapo + ge * env->P.s_gape;
+        return mm * P.s_mm + go * P.s_gapo + ge * P.s_gape;
     }
 
-    B2_HD void begin(const SearchEnv *env_, Arena ar_, Heads heads_, QRec *Q_, uint32_t *W_, int strideQ_,
+    /* E: the launch constants, passed by reference at every call so that on the device they stay
+     * in the kernel-parameter constant bank instead of being re-loaded through a pointer */
+    B2_HD void begin(const SearchEnv &E, Arena ar_, Heads heads_, QRec *Q_, uint32_t *W_, int strideQ_,
                      int strideW_, Rec *recs_, int rec_cap_, int len_, int max_diff_, int n_amb)
     {
         bk = heads_;
-        const Params *P = &env_->P;
-        const FmView *fm = env_->fm;
-        env = env_; ar = ar_; Q = Q_; W = W_; strideQ = strideQ_; strideW = strideW_;
+        const Params *P = &E.P;
+        const FmView *fm = E.fm;
+        ar = ar_; Q = Q_; W = W_; strideQ = strideQ_; strideW = strideW_;
         recs = recs_; rec_cap = rec_cap_; len = len_; opt_max_diff = max_diff_;
         max_diff = max_diff_;
-        best_score = score_of(max_diff_ + 1, P->max_gapo + 1, P->max_gape + 1);
+        best_score = score_of(E.P, max_diff_ + 1, P->max_gapo + 1, P->max_gape + 1);
         best_diff = max_diff_ + 1;
         best_cnt = 0; n_aln = 0; status = LANE_OK;
         finished = false; have_cur = false; cur_held = false; extending = false;
@@ -426,17 +441,18 @@ struct SearchLane {
         if (n_amb > max_diff_) { finished = true; return; } /* bwtgap.c:117-122 */
         bk.clear(P->n_buckets);
         /* roots: strand 0 then strand 1 (bwtgap.c:126-127) -> strand 1 pops first */
-        push(0, len, 0, fm[0].seq_len, 0, 0, 0, ST_M, 0);
-        push(1, len, 0, fm[0].seq_len, 0, 0, 0, ST_M, 0);
+        push(E, 0, len, 0, fm[0].seq_len, 0, 0, 0, ST_M, 0);
+        push(E, 1, len, 0, fm[0].seq_len, 0, 0, 0, ST_M, 0);
     }
 
-    B2_HD void push(int a, int i, uint32_t k, uint32_t l, int mm, int go, int ge, int state, int ldp)
+    B2_HD void push(const SearchEnv &E, int a, int i, uint32_t k, uint32_t l, int mm, int go, int ge, int state,
+                    int ldp)
     {
-        int sc = score_of(mm, go, ge);
+        int sc = score_of(E.P, mm, go, ge);
         uint32_t slot;
         if (REUSE && free_head != B2_NIL) {
             slot = free_head;
-            free_head = ar.link[slot];
+            free_head = ar.ent[slot].link;
         } else {
             if (top >= ar.cap) { status = LANE_ARENA_FULL; finished = true; return; }
             slot = top++;
@@ -445,8 +461,7 @@ struct SearchLane {
         e.x = k; e.y = l;
         e.z = (uint32_t)i | (uint32_t)ldp << 16;
         e.w = (uint32_t)mm | (uint32_t)go << 8 | (uint32_t)ge << 16 | (uint32_t)state << 24 | (uint32_t)a << 26;
-        st_rw(ar.ent + slot, e);
-        ar.link[slot] = bk.get(sc);
+        st_ent(ar.ent + slot, e, bk.get(sc));
         bk.set(sc, slot);
         bk.mark(sc);
         ++n_entries;
@@ -456,13 +471,14 @@ struct SearchLane {
      * as ONE record in their common bucket.  They are pushed consecutively, so they sit
      * contiguously in the bucket; the record is expanded in place into the real entries only
      * if the search ever reaches it (step(), mode 2).  It counts as 1 + popc(dmask) entries. */
-    B2_HD void push_family(int a, int i, uint32_t k, uint32_t l, int mm, int go, int ge, int dmask)
+    B2_HD void push_family(const SearchEnv &E, int a, int i, uint32_t k, uint32_t l, int mm, int go, int ge,
+                           int dmask)
     {
-        int sc = score_of(mm, go + 1, ge);
+        int sc = score_of(E.P, mm, go + 1, ge);
         uint32_t slot;
         if (REUSE && free_head != B2_NIL) {
             slot = free_head;
-            free_head = ar.link[slot];
+            free_head = ar.ent[slot].link;
         } else {
             if (top >= ar.cap) { status = LANE_ARENA_FULL; finished = true; return; }
             slot = top++;
@@ -471,23 +487,23 @@ struct SearchLane {
         e.x = k; e.y = l;
         e.z = (uint32_t)i | (uint32_t)dmask << 16;
         e.w = (uint32_t)mm | (uint32_t)go << 8 | (uint32_t)ge << 16 | 3u << 24 | (uint32_t)a << 26;
-        st_rw(ar.ent + slot, e);
-        ar.link[slot] = bk.get(sc);
+        st_ent(ar.ent + slot, e, bk.get(sc));
         bk.set(sc, slot);
         bk.mark(sc);
         n_entries += 1 + popc32((uint32_t)dmask);
     }
 
-    B2_HD void pop_mem()
+    B2_HD void pop_mem(const SearchEnv &E)
     {
         B2_DBG(0);
-        int b = bk.lowest(env->P.n_buckets);
+        int b = bk.lowest(E.P.n_buckets);
         uint32_t slot = bk.get(b);
-        U4 e = ld_rw(ar.ent + slot);
-        uint32_t prev = ar.link[slot];
+        U4 e;
+        uint32_t prev;
+        ld_ent(ar.ent + slot, e, prev);
         bk.set(b, prev);
         if (prev == B2_NIL) bk.unmark(b);
-        if (REUSE) { ar.link[slot] = free_head; free_head = slot; }
+        if (REUSE) { ar.ent[slot].link = free_head; free_head = slot; }
         --n_entries;
         ck = e.x; cl = e.y;
         ci = (int)(e.z & 0xffffu); cldp = (int)(e.z >> 16);
@@ -502,10 +518,10 @@ struct SearchLane {
     }
 
     /* hit bookkeeping, bwtgap.c:165-198; returns false when the search must stop */
-    B2_HD bool on_hit()
+    B2_HD bool on_hit(const SearchEnv &E)
     {
-        const Params *P = &env->P;
-        const FmView &f = env->fm[1 - ca];
+        const Params *P = &E.P;
+        const FmView &f = E.fm[1 - ca];
         const bool gape_mode = P->mode & MODE_GAPE;
         if (n_aln == 0) {
             best_score = cscore;
@@ -531,10 +547,10 @@ struct SearchLane {
 
     /* Advance until exactly one occ lookup has been issued (or the search ends).
      * All three kinds of work share ONE lookup site so that the lanes of a warp meet there. */
-    B2_HD void step()
+    B2_HD void step(const SearchEnv &E)
     {
-        const Params *P = &env->P;
-        const FmView *fm = env->fm;
+        const Params *P = &E.P;
+        const FmView *fm = E.fm;
         const bool gape_mode = P->mode & MODE_GAPE, nonstop = P->mode & MODE_NONSTOP;
         enum { EXPAND = 0, EXTEND = 1, MATERIALIZE = 2 };
         QRec q = 0;
@@ -544,7 +560,7 @@ struct SearchLane {
             if (!have_cur) {
                 if (n_entries == 0) { finished = true; return; }
                 if (n_entries > P->max_entries) { finished = true; return; }
-                pop_mem();
+                pop_mem(E);
                 if (cstate == 3) {
                     /* its members are checked one by one when they are popped; only the score
                      * break (bwtgap.c:143) can be anticipated: the first member would trigger it */
@@ -567,7 +583,7 @@ struct SearchLane {
                 if (m < q_bid(q)) continue;
             }
             if (ci == 0) {
-                if (!on_hit()) { finished = true; return; }
+                if (!on_hit(E)) { finished = true; return; }
                 continue;
             }
             if (m == 0 && (cstate == ST_M || gape_mode || cge == P->max_gape)) { extending = true; mode = EXTEND; }
@@ -582,9 +598,9 @@ struct SearchLane {
         if (mode == MATERIALIZE) { /* expand a family record in place, in the reference's push order */
             have_cur = false;
             const int i = ci;
-            push(ca, i, ck, cl, cmm, cgo + 1, cge, ST_I, i);
+            push(E, ca, i, ck, cl, cmm, cgo + 1, cge, ST_I, i);
             for (int j = 0; j < 4; ++j)
-                if (cdmask >> j & 1) push(ca, i + 1, cntk[j] + 1u, cntl[j], cmm, cgo + 1, cge, ST_D, i + 1);
+                if (cdmask >> j & 1) push(E, ca, i + 1, cntk[j] + 1u, cntl[j], cmm, cgo + 1, cge, ST_D, i + 1);
             return;
         }
 
@@ -599,7 +615,7 @@ struct SearchLane {
             ci = i;
             if (ci == 0) {
                 extending = false;
-                if (!on_hit()) finished = true;
+                if (!on_hit(E)) finished = true;
             }
             return;
         }
@@ -630,15 +646,15 @@ struct SearchLane {
                     int dmask = 0;
                     for (int j = 0; j < 4; ++j) dmask |= (cntk[j] + 1u <= cntl[j] ? 1 : 0) << j;
                     B2_DBG(1);
-                    push_family(ca, i, ck, cl, cmm, cgo, cge, dmask);
+                    push_family(E, ca, i, ck, cl, cmm, cgo, cge, dmask);
                 }
             } else if (cstate == ST_I) {
-                if (cge < P->max_gape) push(ca, i, ck, cl, cmm, cgo, cge + 1, ST_I, i);
+                if (cge < P->max_gape) push(E, ca, i, ck, cl, cmm, cgo, cge + 1, ST_I, i);
             } else {
                 if (cge < P->max_gape && (cge + cgo < max_diff || occ < (uint32_t)P->max_del_occ))
                     for (int j = 0; j < 4; ++j) {
                         uint32_t nk = cntk[j] + 1u, nl = cntl[j];
-                        if (nk <= nl) push(ca, i + 1, nk, nl, cmm, cgo, cge + 1, ST_D, i + 1);
+                        if (nk <= nl) push(E, ca, i + 1, nk, nl, cmm, cgo, cge + 1, ST_D, i + 1);
                     }
             }
         }
@@ -650,12 +666,12 @@ struct SearchLane {
                 int c = (base + j) & 3;
                 uint32_t nk = pick4(cntk, c) + 1u, nl = pick4(cntl, c);
                 if (nk <= nl) B2_DBG(3);
-                if (nk <= nl) push(ca, i, nk, nl, cmm + 1, cgo, cge, ST_M, i);
+                if (nk <= nl) push(E, ca, i, nk, nl, cmm + 1, cgo, cge, ST_M, i);
             }
             if (base > 3) { /* ambiguous base: the j == 4 child is a mismatch too */
                 int c = base & 3;
                 uint32_t nk = pick4(cntk, c) + 1u, nl = pick4(cntl, c);
-                if (nk <= nl) push(ca, i, nk, nl, cmm + 1, cgo, cge, ST_M, i);
+                if (nk <= nl) push(E, ca, i, nk, nl, cmm + 1, cgo, cge, ST_M, i);
             } else child = true;
         } else if (base < 4) child = true;
         if (finished) return;

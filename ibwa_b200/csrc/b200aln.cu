@@ -46,14 +46,10 @@ static_assert(sizeof(b200aln_rec_t) == 16 && sizeof(Rec) == 16, "bwt_aln1_t is 1
 
 /* ------------------------------------------------------------ kernels ---- */
 
-__global__ void k_convert_index(RefBwt r, U4 *out, uint64_t nb)
+__global__ void k_convert_index(RefBwt r, OccBlk *out, uint64_t nb)
 {
-    for (uint64_t b = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; b < nb; b += (uint64_t)gridDim.x * blockDim.x) {
-        U4 t[2];
-        fm_convert_block(r, b, t);
-        out[2 * b] = t[0];
-        out[2 * b + 1] = t[1];
-    }
+    for (uint64_t b = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; b < nb; b += (uint64_t)gridDim.x * blockDim.x)
+        out[b] = fm_convert_block(r, b);
 }
 
 struct WidthArgs {
@@ -96,8 +92,7 @@ struct SearchArgs {
     QRec *Q;
     uint32_t *W;
     int strideQ, strideW;
-    U4 *ent;
-    uint32_t *link;
+    StackEnt *ent;
     uint32_t arena_cap;
     Rec *recs;
     int rec_cap;
@@ -142,7 +137,6 @@ __global__ void __launch_bounds__(128, MINB) k_search(const __grid_constant__ Se
     const size_t gl = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     Arena ar;
     ar.ent = A.ent + gl * A.arena_cap;
-    ar.link = A.link + gl * A.arena_cap;
     ar.cap = A.arena_cap;
     SearchLane<Heads, REUSE> L;
     L.finished = true;
@@ -166,14 +160,14 @@ __global__ void __launch_bounds__(128, MINB) k_search(const __grid_constant__ Se
                     r = A.work_list ? A.work_list[w] : (int)w;
                     const int len = A.lens[r];
                     const size_t slab = A.recs_by_work ? (size_t)w : (size_t)r;
-                    L.begin(&A.env, ar, heads, A.Q + (size_t)2 * r * A.strideQ, A.W + (size_t)2 * r * A.strideW, A.strideQ,
+                    L.begin(A.env, ar, heads, A.Q + (size_t)2 * r * A.strideQ, A.W + (size_t)2 * r * A.strideW, A.strideQ,
                             A.strideW, A.recs + slab * A.rec_cap, A.rec_cap, len, A.md[len], A.n_amb[r]);
                     active = true;
                 } else alive = false;
             }
         }
         if (active) {
-            if (!L.finished) L.step();
+            if (!L.finished) L.step(A.env);
             if (L.finished) {
                 pops += L.n_pops;
                 sectors += L.n_lookups;
@@ -271,23 +265,30 @@ __global__ void __launch_bounds__(256) k_compact(int n, const int32_t *n_aln, co
     }
 }
 
-/* random 32-byte-sector gather: the roofline denominator */
-__global__ void __launch_bounds__(256) k_sector_gather(const U4 *blk, uint64_t n_blocks, uint64_t loads_per_thread,
-                                                       unsigned long long *sink)
+/* random sector gather: the roofline denominator.  span = 1: independent random
+ * 32-byte sectors; span = 2: random 64-byte aligned pairs of sectors (tells whether the memory
+ * system moves 64 B per miss anyway). */
+__global__ void __launch_bounds__(256) k_sector_gather(const OccBlk *blk, uint64_t n_blocks, uint64_t loads_per_thread,
+                                                       int span, unsigned long long *sink)
 {
     uint64_t s = (blockIdx.x * (uint64_t)blockDim.x + threadIdx.x) * 0x9E3779B97F4A7C15ull + 0x1234567ull;
     uint32_t acc = 0;
-    for (uint64_t i = 0; i < loads_per_thread; i += 4) {
-        uint64_t idx[4];
+    const uint64_t units = n_blocks / (uint64_t)span;
+    for (uint64_t i = 0; i < loads_per_thread; i += 8) {
+        uint64_t idx[8];
 #pragma unroll
-        for (int j = 0; j < 4; ++j) {
+        for (int j = 0; j < 8; ++j) {
             s ^= s << 13; s ^= s >> 7; s ^= s << 17;
-            idx[j] = (uint64_t)(((unsigned __int128)(s >> 11) * n_blocks) >> 53);
+            idx[j] = (uint64_t)(((unsigned __int128)(s >> 11) * units) >> 53) * (uint64_t)span;
         }
 #pragma unroll
-        for (int j = 0; j < 4; ++j) {
-            U4 a = ld_ro(blk + 2 * idx[j]), b = ld_ro(blk + 2 * idx[j] + 1);
-            acc += a.x ^ a.w ^ b.y ^ b.z;
+        for (int j = 0; j < 8; ++j) {
+            OccBlk a = ld_blk(blk + idx[j]);
+            acc += a.cnt.x ^ a.bits.w;
+            if (span == 2) {
+                OccBlk b = ld_blk(blk + idx[j] + 1);
+                acc += b.cnt.y ^ b.bits.z;
+            }
         }
     }
     if (acc == 0x7fffffffu) atomicAdd(sink, 1ull);
@@ -339,7 +340,7 @@ struct b200aln_ctx {
     int device = 0;
     int n_sm = 0;
     FmView fm[2];
-    U4 *d_idx[2] = {nullptr, nullptr};
+    OccBlk *d_idx[2] = {nullptr, nullptr};
     uint64_t n_blk[2] = {0, 0};
     cudaStream_t st = nullptr;
     cudaEvent_t ev[8];
@@ -349,8 +350,8 @@ struct b200aln_ctx {
     uint32_t arena_cap = 4096, arena_cap_big = 0; /* 0: max_entries + 64 */
     int rec_cap = 8, rec_cap_big = 1 << 16, big_lanes = 1024;
     /* device buffers */
-    DevBuf lens, offs, codes, md, Q, W, seedW, seedB, n_amb, ent, link, recs, n_aln, over_slot, over_list, misc, off64,
-        blk_tot, packed, ent_big, link_big, recs_big, heads_wide, heads_wide_big;
+    DevBuf lens, offs, codes, md, Q, W, seedW, seedB, n_amb, ent, recs, n_aln, over_slot, over_list, misc, off64,
+        blk_tot, packed, ent_big, recs_big, heads_wide, heads_wide_big;
     HostBuf h_in, h_out, h_misc;
     b200aln_stats_t stats;
 };
@@ -404,7 +405,7 @@ static void upload_index(b200aln_ctx *c, int which, const b200aln_bwt_view_t *v)
     r.w = d_raw; r.n_words = v->bwt_size; r.seq_len = v->seq_len;
     for (int i = 0; i < 4; ++i) r.L2[i] = v->L2[i];
     const uint64_t nb = fm_num_blocks(v->seq_len);
-    CK(cudaMalloc(&c->d_idx[which], nb * 32));
+    CK(cudaMalloc(&c->d_idx[which], nb * sizeof(OccBlk)));
     k_convert_index<<<c->n_sm * 8, 256, 0, c->st>>>(r, c->d_idx[which], nb);
     CK(cudaGetLastError());
     CK(cudaStreamSynchronize(c->st));
@@ -427,6 +428,18 @@ extern "C" b200aln_ctx *b200aln_open(const b200aln_bwt_view_t *bwt, const b200al
     cudaDeviceProp prop;
     CK(cudaGetDeviceProperties(&prop, device));
     c->n_sm = prop.multiProcessorCount;
+    {   /* Random 32-byte occ sectors are the dominant traffic: ask the L2 to fetch 32 B per miss
+         * instead of its 64-B default, which would double the DRAM traffic of every lookup. */
+        const char *e = getenv("B200ALN_L2_FETCH");
+        size_t gran = e ? (size_t)atoi(e) : 32;
+        if (gran) {
+            cudaError_t le = cudaDeviceSetLimit(cudaLimitMaxL2FetchGranularity, gran);
+            if (le != cudaSuccess) { (void)cudaGetLastError(); fprintf(stderr, "[b200aln_open] note: L2 fetch granularity hint refused\n"); }
+            size_t got = 0;
+            if (cudaDeviceGetLimit(&got, cudaLimitMaxL2FetchGranularity) == cudaSuccess && getenv("B200ALN_VERBOSE"))
+                fprintf(stderr, "[b200aln_open] L2 fetch granularity: asked %zu, device reports %zu\n", gran, got);
+        }
+    }
     CK(cudaStreamCreateWithFlags(&c->st, cudaStreamNonBlocking));
     for (int i = 0; i < 8; ++i) CK(cudaEventCreate(&c->ev[i]));
     for (int i = 0; i < 2; ++i) CK(cudaEventCreate(&c->tm[i]));
@@ -475,8 +488,8 @@ extern "C" void b200aln_close(b200aln_ctx *c)
     cudaSetDevice(c->device);
     cudaStreamSynchronize(c->st);
     DevBuf *bufs[] = {&c->lens, &c->offs, &c->codes, &c->md, &c->Q, &c->W, &c->seedW, &c->seedB, &c->n_amb, &c->ent,
-                      &c->link, &c->recs, &c->n_aln, &c->over_slot, &c->over_list, &c->misc, &c->off64, &c->blk_tot,
-                      &c->packed, &c->ent_big, &c->link_big, &c->recs_big, &c->heads_wide, &c->heads_wide_big};
+                      &c->recs, &c->n_aln, &c->over_slot, &c->over_list, &c->misc, &c->off64, &c->blk_tot,
+                      &c->packed, &c->ent_big, &c->recs_big, &c->heads_wide, &c->heads_wide_big};
     for (DevBuf *b : bufs) b->release();
     c->h_in.release(); c->h_out.release(); c->h_misc.release();
     for (int i = 0; i < 2; ++i) if (c->d_idx[i]) cudaFree(c->d_idx[i]);
@@ -568,8 +581,7 @@ static void run_batch_device(b200aln_ctx *c, int n_reads, int max_len, const int
     c->seedW.need((size_t)wthreads * (opt->seed_len + 1) * 4);
     c->seedB.need((size_t)wthreads * (opt->seed_len + 1) * 2);
     c->n_amb.need((size_t)n_reads * 4);
-    c->ent.need(lanes * c->arena_cap * 16);
-    c->link.need(lanes * c->arena_cap * 4);
+    c->ent.need(lanes * c->arena_cap * sizeof(StackEnt));
     c->recs.need((size_t)n_reads * c->rec_cap * 16);
     c->n_aln.need((size_t)n_reads * 4);
     c->over_slot.need((size_t)n_reads * 4);
@@ -603,7 +615,7 @@ static void run_batch_device(b200aln_ctx *c, int n_reads, int max_len, const int
     SA.n_work = n_reads; SA.work_list = nullptr;
     SA.lens = d_lens; SA.n_amb = c->n_amb.as<int32_t>(); SA.md = c->md.as<int32_t>();
     SA.Q = WA.Q; SA.W = WA.W; SA.strideQ = strideQ; SA.strideW = strideW;
-    SA.ent = c->ent.as<U4>(); SA.link = c->link.as<uint32_t>(); SA.arena_cap = c->arena_cap;
+    SA.ent = c->ent.as<StackEnt>(); SA.arena_cap = c->arena_cap;
     SA.recs = c->recs.as<Rec>(); SA.rec_cap = c->rec_cap; SA.recs_by_work = 0;
     SA.n_aln = c->n_aln.as<int32_t>(); SA.over_slot = nullptr;
     SA.counter = &dm->counter; SA.n_over = &dm->n_over; SA.over_list = c->over_list.as<int32_t>();
@@ -623,8 +635,7 @@ static void run_batch_device(b200aln_ctx *c, int n_reads, int max_len, const int
         int big_lanes = c->big_lanes;
         if ((unsigned)big_lanes > ((n_over + 127u) / 128u) * 128u) big_lanes = (int)(((n_over + 127u) / 128u) * 128u);
         int bblocks = (big_lanes + 127) / 128;
-        c->ent_big.need((size_t)bblocks * 128 * cap_big * 16);
-        c->link_big.need((size_t)bblocks * 128 * cap_big * 4);
+        c->ent_big.need((size_t)bblocks * 128 * cap_big * sizeof(StackEnt));
         c->recs_big.need((size_t)n_over * c->rec_cap_big * 16);
         /* the aborted fast pass may have edited W/Q in place (gap_shadow): rebuild them first */
         WidthArgs WB = WA;
@@ -634,7 +645,7 @@ static void run_batch_device(b200aln_ctx *c, int n_reads, int max_len, const int
         ++launches;
         SearchArgs SB = SA;
         SB.n_work = (int)n_over; SB.work_list = c->over_list.as<int32_t>();
-        SB.ent = c->ent_big.as<U4>(); SB.link = c->link_big.as<uint32_t>(); SB.arena_cap = cap_big;
+        SB.ent = c->ent_big.as<StackEnt>(); SB.arena_cap = cap_big;
         SB.recs = c->recs_big.as<Rec>(); SB.rec_cap = c->rec_cap_big; SB.recs_by_work = 1;
         SB.over_slot = c->over_slot.as<int32_t>();
         SB.counter = &dm->counter_big; SB.n_over = nullptr; SB.over_list = nullptr;
@@ -753,23 +764,26 @@ extern "C" void b200aln_batch_device(b200aln_ctx *c, int n_reads, int max_len, c
 
 extern "C" double b200aln_sector_roofline(b200aln_ctx *c, uint64_t n_loads, int repeats)
 {
+    /* repeats > 0: independent random 32-byte sectors; repeats < 0: random 64-byte pairs (|repeats| runs).
+     * Returns GB/s of the bytes asked for (best run). */
     CK(cudaSetDevice(c->device));
     c->misc.need(sizeof(Misc));
+    const int span = repeats < 0 ? 2 : 1;
+    if (repeats < 0) repeats = -repeats;
     const int blocks = c->n_sm * 8, threads = 256;
-    uint64_t per = (n_loads / ((uint64_t)blocks * threads) + 3) / 4 * 4;
-    if (per < 4) per = 4;
-    /* both indexes are one allocation each; gather over the larger span: bwt blocks */
+    uint64_t per = (n_loads / ((uint64_t)blocks * threads) + 7) / 8 * 8;
+    if (per < 8) per = 8;
     double best = 0;
     for (int it = 0; it < repeats + 1; ++it) {
         CK(cudaEventRecord(c->ev[0], c->st));
-        k_sector_gather<<<blocks, threads, 0, c->st>>>(c->d_idx[it & 1], c->n_blk[it & 1], per,
+        k_sector_gather<<<blocks, threads, 0, c->st>>>(c->d_idx[it & 1], c->n_blk[it & 1], per, span,
                                                        (unsigned long long *)c->misc.p);
         CK(cudaGetLastError());
         CK(cudaEventRecord(c->ev[1], c->st));
         CK(cudaEventSynchronize(c->ev[1]));
         float ms = 0;
         CK(cudaEventElapsedTime(&ms, c->ev[0], c->ev[1]));
-        double gbs = (double)per * blocks * threads * 32.0 / (ms * 1e-3) / 1e9;
+        double gbs = (double)per * blocks * threads * 32.0 * span / (ms * 1e-3) / 1e9;
         if (it > 0 && gbs > best) best = gbs;
     }
     return best;

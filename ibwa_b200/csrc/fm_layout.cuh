@@ -31,8 +31,8 @@ B2_HD void fm_spread16(uint32_t word, int sh, uint32_t &lo, uint32_t &hi)
     }
 }
 
-/* device block `b` (bases [64b, 64b+64)) -> out[0] = counts, out[1] = planes */
-B2_HD void fm_convert_block(const RefBwt &r, uint64_t b, U4 out[2])
+/* device block `b` (bases [64b, 64b+64)) */
+B2_HD OccBlk fm_convert_block(const RefBwt &r, uint64_t b)
 {
     const uint64_t base0 = b * 64u;
     uint32_t cnt[4], wd[4] = {0, 0, 0, 0};
@@ -67,8 +67,10 @@ B2_HD void fm_convert_block(const RefBwt &r, uint64_t b, U4 out[2])
     fm_spread16(wd[2], 0, lo1, hi1);
     fm_spread16(wd[3], 16, lo1, hi1);
     pl.x = lo0; pl.y = lo1; pl.z = hi0; pl.w = hi1;
-    out[0] = c4;
-    out[1] = pl;
+    OccBlk o;
+    o.cnt = c4;
+    o.bits = pl;
+    return o;
 }
 
 } // namespace b2

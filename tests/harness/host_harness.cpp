@@ -20,14 +20,14 @@ extern "C" uint64_t *hh_dbg() { return b2::b2_dbg; }
 
 using namespace b2;
 
-static std::vector<U4> convert(const b200aln_bwt_view_t *v)
+static std::vector<OccBlk> convert(const b200aln_bwt_view_t *v)
 {
     RefBwt r;
     r.w = v->bwt; r.n_words = v->bwt_size; r.seq_len = v->seq_len;
     for (int c = 0; c < 4; ++c) r.L2[c] = v->L2[c];
     uint64_t nb = fm_num_blocks(v->seq_len);
-    std::vector<U4> out(2 * nb);
-    for (uint64_t b = 0; b < nb; ++b) fm_convert_block(r, b, &out[2 * b]);
+    std::vector<OccBlk> out(nb);
+    for (uint64_t b = 0; b < nb; ++b) out[b] = fm_convert_block(r, b);
     return out;
 }
 
@@ -60,13 +60,11 @@ static int64_t run(const SearchEnv &env, const std::vector<int> &md, int n_reads
     std::vector<uint32_t> W(2 * (size_t)strideW);
     std::vector<uint32_t> seedW(seed_len + 1);
     std::vector<uint16_t> seedB(seed_len + 1);
-    std::vector<U4> ent(arena_cap);
-    std::vector<uint32_t> link(arena_cap);
+    std::vector<StackEnt> ent(arena_cap);
     std::vector<Rec> recs(rec_cap);
     int64_t n_status = 0;
     std::vector<uint32_t> hstore(2048 + 64);
-    std::vector<U4> ent2;
-    std::vector<uint32_t> link2;
+    std::vector<StackEnt> ent2;
     std::vector<Rec> recs2;
     for (int r = 0; r < n_reads; ++r) {
         const uint8_t *fwd = codes + offs[r];
@@ -76,20 +74,20 @@ static int64_t run(const SearchEnv &env, const std::vector<int> &md, int n_reads
         width_pass(fm[1], fwd, len, 1, comp, seed_len, W.data() + strideW, Q.data() + strideQ, seedW.data(),
                    seedB.data());
         SearchLane<Heads, REUSE> lane;
-        Arena ar; ar.ent = ent.data(); ar.link = link.data(); ar.cap = arena_cap;
-        lane.begin(&env, ar, make_heads<Heads>(hstore), Q.data(), W.data(), strideQ, strideW, recs.data(), rec_cap, len, md[len], n_amb);
-        while (!lane.finished) lane.step();
+        Arena ar; ar.ent = ent.data(); ar.cap = arena_cap;
+        lane.begin(env, ar, make_heads<Heads>(hstore), Q.data(), W.data(), strideQ, strideW, recs.data(), rec_cap, len, md[len], n_amb);
+        while (!lane.finished) lane.step(env);
         if (lane.status != LANE_OK && big_cap) {
             /* the product's large pass: widths rebuilt (the aborted pass shadowed them), free-list arena */
             ++n_status;
-            if (ent2.size() < big_cap) { ent2.resize(big_cap); link2.resize(big_cap); recs2.resize(1 << 16); }
+            if (ent2.size() < big_cap) { ent2.resize(big_cap); recs2.resize(1 << 16); }
             n_amb = width_pass(fm[0], fwd, len, 0, comp, seed_len, W.data(), Q.data(), seedW.data(), seedB.data());
             width_pass(fm[1], fwd, len, 1, comp, seed_len, W.data() + strideW, Q.data() + strideQ, seedW.data(),
                        seedB.data());
             SearchLane<HeadsWide32, true> big;
-            Arena ar2; ar2.ent = ent2.data(); ar2.link = link2.data(); ar2.cap = big_cap;
-            big.begin(&env, ar2, make_heads<HeadsWide32>(hstore), Q.data(), W.data(), strideQ, strideW, recs2.data(), 1 << 16, len, md[len], n_amb);
-            while (!big.finished) big.step();
+            Arena ar2; ar2.ent = ent2.data(); ar2.cap = big_cap;
+            big.begin(env, ar2, make_heads<HeadsWide32>(hstore), Q.data(), W.data(), strideQ, strideW, recs2.data(), 1 << 16, len, md[len], n_amb);
+            while (!big.finished) big.step(env);
             if (big.status != LANE_OK) { n_aln[r] = -big.status; continue; }
             n_aln[r] = big.n_aln;
             all.insert(all.end(), recs2.begin(), recs2.begin() + big.n_aln);
@@ -110,7 +108,7 @@ extern "C" int64_t hh_aln_batch(const b200aln_bwt_view_t *bwt, const b200aln_bwt
                                 int32_t *n_aln,
                                 Rec **records, int64_t *n_overflow, uint64_t *counters)
 {
-    std::vector<U4> i0 = convert(bwt), i1 = convert(rbwt);
+    std::vector<OccBlk> i0 = convert(bwt), i1 = convert(rbwt);
     SearchEnv env;
     FmView *fm = env.fm;
     fm[0].blk = i0.data(); fm[0].primary = bwt->primary; fm[0].seq_len = bwt->seq_len;

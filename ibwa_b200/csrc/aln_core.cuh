@@ -67,7 +67,7 @@ B2_D OccBlk ld_blk(const OccBlk *p)
 }
 B2_D void ld_ent(const StackEnt *p, U4 &e, uint32_t &link)
 { /* stack entries: written once, read at most once -> L2 only */
-    uint32_t p0, p1, p2;
+    [[maybe_unused]] uint32_t p0, p1, p2;
     asm volatile("ld.global.cg.v8.u32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
                  : "=r"(e.x), "=r"(e.y), "=r"(e.z), "=r"(e.w), "=r"(link), "=r"(p0), "=r"(p1), "=r"(p2)
                  : "l"(p) : "memory");
@@ -545,54 +545,62 @@ struct SearchLane {
         return true;
     }
 
-    /* Advance until exactly one occ lookup has been issued (or the search ends).
-     * All three kinds of work share ONE lookup site so that the lanes of a warp meet there. */
-    B2_HD void step(const SearchEnv &E)
+    /*
+     * One step = prepare() -> one occ lookup -> apply().  The three phases are separate so that
+     * the kernel can re-converge the warp between them (all lanes issue their lookup loads
+     * together); step() chains them for callers that do not care (CPU logic tests).
+     */
+    enum { NONE = -1, EXPAND = 0, EXTEND = 1, MATERIALIZE = 2 };
+    QRec pq; /* width record of the position being worked on (prepare -> apply) */
+    int pm;  /* differences still allowed for the current entry */
+
+    /* pop until something needs a lookup; returns its kind or NONE (search ended) */
+    B2_HD int prepare(const SearchEnv &E)
     {
         const Params *P = &E.P;
-        const FmView *fm = E.fm;
         const bool gape_mode = P->mode & MODE_GAPE, nonstop = P->mode & MODE_NONSTOP;
-        enum { EXPAND = 0, EXTEND = 1, MATERIALIZE = 2 };
-        QRec q = 0;
-        int m = 0, mode = EXPAND;
-        for (;;) { /* pop until something needs a lookup */
-            if (extending) { q = Q[(size_t)ca * strideQ + (ci - 1)]; mode = EXTEND; break; }
+        for (;;) {
+            if (extending) { pq = Q[(size_t)ca * strideQ + (ci - 1)]; return EXTEND; }
             if (!have_cur) {
-                if (n_entries == 0) { finished = true; return; }
-                if (n_entries > P->max_entries) { finished = true; return; }
+                if (n_entries == 0) { finished = true; return NONE; }
+                if (n_entries > P->max_entries) { finished = true; return NONE; }
                 pop_mem(E);
                 if (cstate == 3) {
                     /* its members are checked one by one when they are popped; only the score
                      * break (bwtgap.c:143) can be anticipated: the first member would trigger it */
-                    if (!nonstop && cscore > best_score + P->s_mm) { ++n_pops; finished = true; return; }
-                    mode = MATERIALIZE;
-                    break;
+                    if (!nonstop && cscore > best_score + P->s_mm) { ++n_pops; finished = true; return NONE; }
+                    return MATERIALIZE;
                 }
             } else { /* held exact child: same accounting as a push followed by a pop */
                 B2_DBG(4);
-                if (n_entries > P->max_entries) { finished = true; return; }
+                if (n_entries > P->max_entries) { finished = true; return NONE; }
                 --n_entries;
             }
             have_cur = false;
             ++n_pops;
-            if (!nonstop && cscore > best_score + P->s_mm) { finished = true; return; }
-            m = max_diff - cmm - cgo - (gape_mode ? cge : 0);
-            if (m < 0) continue;
+            if (!nonstop && cscore > best_score + P->s_mm) { finished = true; return NONE; }
+            pm = max_diff - cmm - cgo - (gape_mode ? cge : 0);
+            if (pm < 0) continue;
             if (ci > 0) {
-                q = Q[(size_t)ca * strideQ + (ci - 1)];
-                if (m < q_bid(q)) continue;
+                pq = Q[(size_t)ca * strideQ + (ci - 1)];
+                if (pm < q_bid(pq)) continue;
             }
             if (ci == 0) {
-                if (!on_hit(E)) { finished = true; return; }
+                if (!on_hit(E)) { finished = true; return NONE; }
                 continue;
             }
-            if (m == 0 && (cstate == ST_M || gape_mode || cge == P->max_gape)) { extending = true; mode = EXTEND; }
-            break;
+            if (pm == 0 && (cstate == ST_M || gape_mode || cge == P->max_gape)) { extending = true; return EXTEND; }
+            return EXPAND;
         }
+    }
 
-        /* ---- the lookup ---- */
-        uint32_t cntk[4], cntl[4], ns;
-        occ2x4(fm[1 - ca], ck, cl, cntk, cntl, ns);
+    /* consume the counts of the lookup issued for `mode` on interval [ck, cl] of fm[1 - ca] */
+    B2_HD void apply(const SearchEnv &E, int mode, const uint32_t cntk[4], const uint32_t cntl[4], uint32_t ns)
+    {
+        const Params *P = &E.P;
+        const bool gape_mode = P->mode & MODE_GAPE;
+        const QRec q = pq;
+        const int m = pm;
         n_lookups += ns;
 
         if (mode == MATERIALIZE) { /* expand a family record in place, in the reference's push order */
@@ -684,6 +692,15 @@ struct SearchLane {
                 ++n_entries;
             }
         }
+    }
+
+    B2_HD void step(const SearchEnv &E)
+    {
+        const int mode = prepare(E);
+        if (mode == NONE) return;
+        uint32_t cntk[4], cntl[4], ns;
+        occ2x4(E.fm[1 - ca], ck, cl, cntk, cntl, ns);
+        apply(E, mode, cntk, cntl, ns);
     }
 };
 

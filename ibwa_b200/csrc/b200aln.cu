@@ -166,8 +166,17 @@ __global__ void __launch_bounds__(128, MINB) k_search(const __grid_constant__ Se
                 } else alive = false;
             }
         }
+        /* one search step per lane, the warp re-converged around the lookup so that all of its
+         * loads are issued together */
+        int mode = L.NONE;
+        if (active && !L.finished) mode = L.prepare(A.env);
+        __syncwarp();
+        uint32_t cntk[4], cntl[4], ns = 0;
+        if (mode != L.NONE) occ2x4(A.env.fm[1 - L.ca], L.ck, L.cl, cntk, cntl, ns);
+        __syncwarp();
+        if (mode != L.NONE) L.apply(A.env, mode, cntk, cntl, ns);
+        __syncwarp();
         if (active) {
-            if (!L.finished) L.step(A.env);
             if (L.finished) {
                 pops += L.n_pops;
                 sectors += L.n_lookups;

@@ -355,7 +355,7 @@ struct b200aln_ctx {
     cudaEvent_t ev[8];
     cudaEvent_t tm[2];
     /* tuning */
-    int search_blocks_per_sm = 5, width_blocks_per_sm = 8;
+    int search_blocks_per_sm = 6, width_blocks_per_sm = 8;
     uint32_t arena_cap = 4096, arena_cap_big = 0; /* 0: max_entries + 64 */
     int rec_cap = 8, rec_cap_big = 1 << 16, big_lanes = 1024;
     /* device buffers */

@@ -99,10 +99,10 @@ def test_random_genome_vs_oracle(rand_index, model, args, length, n):
     assert np.array_equal(n_aln, o_n)
     assert rec.tobytes() == o_rec.tobytes()
     if st["overflow_reads"] == 0:
-        assert st["pops"] == ost["pops"]      # same search, pop for pop
+        assert st["pops"] == ost["pops"], (st, ost)      # same search, pop for pop
     else:
-        assert st["pops"] > ost["pops"]       # flagged reads are searched twice
-    assert (n_aln > 0).mean() > 0.8
+        assert st["pops"] > ost["pops"], (st, ost)       # flagged reads are searched twice
+    assert (n_aln > 0).mean() > (0.8 if model == "default" else 0.3)
 
 
 def test_device_resident_entry_point(rand_index):

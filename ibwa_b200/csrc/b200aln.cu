@@ -358,6 +358,7 @@ struct b200aln_ctx {
     int search_blocks_per_sm = 6, width_blocks_per_sm = 8;
     uint32_t arena_cap = 4096, arena_cap_big = 0; /* 0: max_entries + 64 */
     int rec_cap = 8, rec_cap_big = 1 << 16, big_lanes = 1024;
+    int batch_max_len = 0; /* > 0: the reference batch this call is a shard of has this longest read */
     /* device buffers */
     DevBuf lens, offs, codes, md, Q, W, seedW, seedB, n_amb, ent, recs, n_aln, over_slot, over_list, misc, off64,
         blk_tot, packed, ent_big, recs_big, heads_wide, heads_wide_big;
@@ -517,6 +518,7 @@ extern "C" void b200aln_set_int(b200aln_ctx *c, const char *key, int64_t v)
     else if (!strcmp(key, "rec_cap")) c->rec_cap = (int)v;
     else if (!strcmp(key, "rec_cap_big")) c->rec_cap_big = (int)v;
     else if (!strcmp(key, "big_lanes")) c->big_lanes = (int)v;
+    else if (!strcmp(key, "batch_max_len")) c->batch_max_len = (int)v;
     else die("b200aln_set_int", "unknown key '%s'.", key);
 }
 
@@ -728,7 +730,11 @@ extern "C" const b200aln_rec_t *b200aln_batch(b200aln_ctx *c, int n_reads, const
     }
     Params P;
     std::vector<int> md;
-    b2host::make_params(*opt, max_len, lens, n_reads, P, md);
+    if (c->batch_max_len > 0 && c->batch_max_len < max_len)
+        die("b200aln_batch", "batch_max_len %d is smaller than a read of this shard (%d).", c->batch_max_len, max_len);
+    /* a shard of a larger reference batch: the batch-level clamp (bwtaln.c:89-92) uses the whole batch's longest read */
+    b2host::make_params(*opt, c->batch_max_len > 0 ? c->batch_max_len : max_len, lens, n_reads, P, md);
+    if ((int)md.size() < max_len + 1) md.resize((size_t)max_len + 1, opt->max_diff);
 
     c->lens.need((size_t)n_reads * 4);
     c->offs.need((size_t)n_reads * 8);

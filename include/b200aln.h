@@ -124,7 +124,12 @@ void b200aln_last_stats(const b200aln_ctx *ctx, b200aln_stats_t *out);
 void b200aln_timer_start(b200aln_ctx *ctx);
 double b200aln_timer_stop(b200aln_ctx *ctx);
 
-/* Tuning knobs (optional; call before the first batch).  Unknown keys abort. */
+/* Tuning knobs (optional; call before the first batch).  Unknown keys abort.
+ *   batch_max_len  > 0: this context processes a SHARD of a reference batch whose longest read has this
+ *                  length; the batch-level max_gapo clamp (bwtaln.c:89-92) is then taken from it, so that
+ *                  shards on several GPUs reproduce the single-batch result.  0 = the call is the batch.
+ *   search_blocks_per_sm, width_blocks_per_sm, arena_cap, arena_cap_big, rec_cap, rec_cap_big, big_lanes:
+ *                  launch geometry and per-lane capacities. */
 void b200aln_set_int(b200aln_ctx *ctx, const char *key, int64_t value);
 
 /*

@@ -105,7 +105,7 @@ static int64_t run(const SearchEnv &env, const std::vector<int> &md, int n_reads
 extern "C" int64_t hh_aln_batch(const b200aln_bwt_view_t *bwt, const b200aln_bwt_view_t *rbwt, int n_reads,
                                 const int32_t *lens, const int64_t *offs, const uint8_t *codes,
                                 const b200aln_opt_t *opt, uint32_t arena_cap, int rec_cap, int reuse, uint32_t big_cap,
-                                int32_t *n_aln,
+                                int batch_max_len, int32_t *n_aln,
                                 Rec **records, int64_t *n_overflow, uint64_t *counters)
 {
     std::vector<OccBlk> i0 = convert(bwt), i1 = convert(rbwt);
@@ -117,7 +117,7 @@ extern "C" int64_t hh_aln_batch(const b200aln_bwt_view_t *bwt, const b200aln_bwt
     for (int r = 0; r < n_reads; ++r) if (lens[r] > max_len) max_len = lens[r];
     Params &P = env.P;
     std::vector<int> md;
-    b2host::make_params(*opt, max_len, lens, n_reads, P, md);
+    b2host::make_params(*opt, batch_max_len > 0 ? batch_max_len : max_len, lens, n_reads, P, md);
     std::vector<Rec> all;
     bool comp = opt->mode & MODE_COMPREAD;
     int64_t ov;

@@ -50,7 +50,7 @@ def lib():
     return _lib
 
 
-def aln_batch(bwt, rbwt, lens, offs, codes, opt_c, arena_cap=1 << 16, rec_cap=256, reuse=False, big_cap=0):
+def aln_batch(bwt, rbwt, lens, offs, codes, opt_c, arena_cap=1 << 16, rec_cap=256, reuse=False, big_cap=0, batch_max_len=0):
     L = lib()
     lens = np.ascontiguousarray(lens, np.int32)
     offs = np.ascontiguousarray(offs, np.int64)
@@ -63,7 +63,7 @@ def aln_batch(bwt, rbwt, lens, offs, codes, opt_c, arena_cap=1 << 16, rec_cap=25
     v0, v1 = view(bwt), view(rbwt)
     tot = L.hh_aln_batch(ctypes.byref(v0), ctypes.byref(v1), ctypes.c_int(n), ctypes.c_void_p(lens.ctypes.data),
                          ctypes.c_void_p(offs.ctypes.data), ctypes.c_void_p(codes.ctypes.data), ctypes.byref(opt_c),
-                         ctypes.c_uint32(arena_cap), ctypes.c_int(rec_cap), ctypes.c_int(int(reuse)), ctypes.c_uint32(big_cap),
+                         ctypes.c_uint32(arena_cap), ctypes.c_int(rec_cap), ctypes.c_int(int(reuse)), ctypes.c_uint32(big_cap), ctypes.c_int(batch_max_len),
                          ctypes.c_void_p(n_aln.ctypes.data), ctypes.byref(rec_p), ctypes.byref(nov), counters)
     rec = np.frombuffer((ctypes.c_uint8 * (16 * tot)).from_address(rec_p.value), dtype=ALN_DTYPE).copy() if tot \
         else np.empty(0, ALN_DTYPE)

@@ -78,9 +78,26 @@ B2_D void st_ent(StackEnt *p, U4 e, uint32_t link)
     asm volatile("st.global.cg.v8.u32 [%0], {%1,%2,%3,%4,%5,%6,%6,%6};"
                  :: "l"(p), "r"(e.x), "r"(e.y), "r"(e.z), "r"(e.w), "r"(link), "r"(0u) : "memory");
 }
+B2_D void st8(uint32_t *p, const uint32_t v[8])
+{ /* eight consecutive words as one full 32-byte sector (p is 32-byte aligned) */
+    asm volatile("st.global.cg.v8.u32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};"
+                 :: "l"(p), "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7]) : "memory");
+}
+B2_D uint32_t ld_q(const uint32_t *p)
+{ /* width records: re-read along a chain (8 per sector) -> keep them in L1 */
+#ifdef B2_Q_EVICT_LAST
+    uint32_t v;
+    asm volatile("ld.global.L1::evict_last.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+#else
+    return *p;
+#endif
+}
 B2_D int popc32(uint32_t v) { return __popc(v); }
 B2_D int ctz32(uint32_t v) { return __ffs((int)v) - 1; }
 #else
+inline uint32_t ld_q(const uint32_t *p) { return *p; }
+inline void st8(uint32_t *p, const uint32_t v[8]) { for (int i = 0; i < 8; ++i) p[i] = v[i]; }
 inline OccBlk ld_blk(const OccBlk *p) { return *p; }
 inline void ld_ent(const StackEnt *p, U4 &e, uint32_t &link) { e = p->e; link = p->link; }
 inline void st_ent(StackEnt *p, U4 e, uint32_t link) { p->e = e; p->link = link; p->pad[0] = p->pad[1] = p->pad[2] = 0; }
@@ -184,20 +201,16 @@ B2_HD void occ2x4(const FmView &f, uint32_t k, uint32_t l, uint32_t ck[4], uint3
 
 /* ---------------------------------------------------------- width pass ---- */
 
-/* One chain of bwt_cal_width (bwtaln.c:54-78) advanced one symbol at a time so
- * that two chains can be interleaved by the caller for memory-level
- * parallelism. */
+/* One chain of bwt_cal_width (bwtaln.c:54-78): the interval and the restart counter. */
 struct WidthChain {
     uint32_t k, l;
     int bid;
     B2_HD void reset(const FmView &f) { k = 0; l = f.seq_len; bid = 0; }
-    /* consumes symbol c; returns the width l-k+1 (and updates bid) */
-    B2_HD uint32_t step(const FmView &f, int c)
+    /* finish one symbol given the counts at both interval ends; returns the width l-k+1 */
+    B2_HD uint32_t advance(const FmView &f, int c, const uint32_t ck[4], const uint32_t cl[4])
     {
         bool alive = false;
         if (c < 4) {
-            uint32_t ck[4], cl[4], ns;
-            occ2x4(f, k, l, ck, cl, ns);
             k = pick4(ck, c) + 1u;
             l = pick4(cl, c);
             alive = k <= l;
@@ -220,49 +233,86 @@ B2_HD int strand_sym(const uint8_t *fwd, int len, int a, int i, bool comp)
     return c;
 }
 
+B2_HD int round_up8(int v) { return (v + 7) & ~7; }
+
 /*
- * Width pass for one (read, strand a): fills W[0..len] (u32 widths), the seed
- * scratch and the packed records Q[0..len-1].  Uses index fm[a] on seq[a]
- * (bwtaln.c:123-130).  Returns the number of ambiguous symbols in the strand.
+ * Width pass for one (read, strand a): fills W[0..len] (u32 widths) and the packed records
+ * Q[0..len-1], using index fm[a] on seq[a] (bwtaln.c:123-130).  The seed chain
+ * (bwt_cal_width on the last seed_len symbols, bwtaln.c:127-130) consumes the same symbols
+ * as the tail of the main chain, so both advance in the same iteration: no scratch, and
+ * their lookups overlap.  Rows are written eight words (one sector) at a time; W and Q rows
+ * must be 32-byte aligned with a stride that is a multiple of 8.
+ * Returns the number of ambiguous symbols in the strand.
  */
 B2_HD int width_pass(const FmView &f, const uint8_t *fwd, int len, int a, bool comp, int seed_len, uint32_t *W,
-                     QRec *Q, uint32_t *seedW /* [seed_len+1] */, uint16_t *seedB /* [seed_len+1] */)
+                     QRec *Q)
 {
     const bool use_seed = len > seed_len;
     const int shift = len - seed_len; /* ii = j - shift */
     int n_amb = 0;
-    if (use_seed) {
-        WidthChain s;
-        s.reset(f);
-        for (int t = 0; t < seed_len; ++t) {
-            seedW[t] = s.step(f, strand_sym(fwd, len, a, shift + t, comp));
-            seedB[t] = (uint16_t)(s.bid > 65535 ? 65535 : s.bid);
-        }
-        seedW[seed_len] = 0;
-        seedB[seed_len] = (uint16_t)(s.bid + 1 > 65535 ? 65535 : s.bid + 1);
-    }
-    WidthChain m;
+    WidthChain m, s;
     m.reset(f);
-    uint32_t w_prev = 0;
-    int bid_prev = 0;
-    for (int j = 0; j < len; ++j) {
-        int c = strand_sym(fwd, len, a, j, comp);
-        n_amb += c > 3;
-        uint32_t w = m.step(f, c);
-        W[j] = w;
-        int ii = j - shift;
-        uint32_t sact = 0, sb = 0, sbp = 0, seq = 0;
-        if (use_seed && ii > 0) {
-            sact = 1;
-            sb = seedB[ii];
-            sbp = seedB[ii - 1];
-            seq = seedW[ii] == seedW[ii - 1];
+    s.reset(f);
+    uint32_t w_prev = 0, sw_prev = 0;
+    int bid_prev = 0, sbid_prev = 0;
+    for (int j0 = 0; j0 <= len; j0 += 8) {
+        uint32_t qb[8], wb[8];
+#if defined(__CUDA_ARCH__)
+#pragma unroll
+#endif
+        for (int t = 0; t < 8; ++t) {
+            const int j = j0 + t;
+            qb[t] = 0;
+            wb[t] = 0;
+            if (j < len) {
+                const int c = strand_sym(fwd, len, a, j, comp);
+                const bool seed_on = use_seed && j >= shift;
+                n_amb += c > 3;
+                uint32_t mk[4], ml[4], sk[4], sl[4];
+                if (c < 4) { /* issue the loads of both chains before using either */
+                    const uint32_t qa = q_lower(f, m.k), qb_ = q_upper(f, m.l);
+                    const OccBlk *pa = f.blk + (qa >> 6), *pb = f.blk + (qb_ >> 6);
+                    OccBlk ba = ld_blk(pa), bb = ba, ca_ = ba, cb = ba;
+                    if (pa != pb) bb = ld_blk(pb);
+                    uint32_t ra = 0, rb = 0;
+                    if (seed_on) {
+                        ra = q_lower(f, s.k);
+                        rb = q_upper(f, s.l);
+                        const OccBlk *sa = f.blk + (ra >> 6), *sb = f.blk + (rb >> 6);
+                        ca_ = ld_blk(sa);
+                        cb = ca_;
+                        if (sa != sb) cb = ld_blk(sb);
+                    }
+                    occ_count4(ba.cnt, ba.bits, qa & 63u, mk);
+                    occ_count4(bb.cnt, bb.bits, qb_ & 63u, ml);
+                    if (seed_on) {
+                        occ_count4(ca_.cnt, ca_.bits, ra & 63u, sk);
+                        occ_count4(cb.cnt, cb.bits, rb & 63u, sl);
+                    }
+                }
+                const uint32_t w = m.advance(f, c, mk, ml);
+                uint32_t sact = 0, sb2 = 0, sbp = 0, seq = 0;
+                if (seed_on) {
+                    const uint32_t sw = s.advance(f, c, sk, sl);
+                    if (j > shift) { /* ii > 0 */
+                        sact = 1;
+                        sb2 = (uint32_t)s.bid;
+                        sbp = (uint32_t)sbid_prev;
+                        seq = sw == sw_prev;
+                    }
+                    sw_prev = sw;
+                    sbid_prev = s.bid;
+                }
+                qb[t] = q_pack((uint32_t)c, j > 0 && w == w_prev, seq, sact, sb2, sbp, (uint32_t)m.bid,
+                               (uint32_t)bid_prev);
+                wb[t] = w;
+                w_prev = w;
+                bid_prev = m.bid;
+            }
         }
-        Q[j] = q_pack((uint32_t)c, j > 0 && w == w_prev, seq, sact, sb, sbp, (uint32_t)m.bid, (uint32_t)bid_prev);
-        w_prev = w;
-        bid_prev = m.bid;
+        if (j0 < len) st8(Q + j0, qb);
+        st8(W + j0, wb); /* includes the W[len] = 0 sentinel */
     }
-    W[len] = 0;
     return n_amb;
 }
 
@@ -560,7 +610,7 @@ struct SearchLane {
         const Params *P = &E.P;
         const bool gape_mode = P->mode & MODE_GAPE, nonstop = P->mode & MODE_NONSTOP;
         for (;;) {
-            if (extending) { pq = Q[(size_t)ca * strideQ + (ci - 1)]; return EXTEND; }
+            if (extending) { pq = ld_q(Q + (size_t)ca * strideQ + (ci - 1)); return EXTEND; }
             if (!have_cur) {
                 if (n_entries == 0) { finished = true; return NONE; }
                 if (n_entries > P->max_entries) { finished = true; return NONE; }
@@ -582,7 +632,7 @@ struct SearchLane {
             pm = max_diff - cmm - cgo - (gape_mode ? cge : 0);
             if (pm < 0) continue;
             if (ci > 0) {
-                pq = Q[(size_t)ca * strideQ + (ci - 1)];
+                pq = ld_q(Q + (size_t)ca * strideQ + (ci - 1));
                 if (pm < q_bid(pq)) continue;
             }
             if (ci == 0) {

@@ -62,22 +62,18 @@ struct WidthArgs {
     int comp, seed_len, strideQ, strideW;
     QRec *Q;
     uint32_t *W;
-    uint32_t *seedW;
-    uint16_t *seedB;
     int32_t *n_amb;
 };
 
 __global__ void __launch_bounds__(128) k_width(const __grid_constant__ WidthArgs A)
 {
     const int nthreads = gridDim.x * blockDim.x, tid = blockIdx.x * blockDim.x + threadIdx.x;
-    uint32_t *sW = A.seedW + (size_t)tid * (A.seed_len + 1);
-    uint16_t *sB = A.seedB + (size_t)tid * (A.seed_len + 1);
     for (int64_t t = tid; t < 2 * (int64_t)A.n_reads; t += nthreads) {
         const int wi = (int)(t >> 1), a = (int)(t & 1);
         const int r = A.work_list ? A.work_list[wi] : wi;
         const size_t slot = (size_t)2 * r + a;
         int n = width_pass(A.fm[a], A.codes + A.offs[r], A.lens[r], a, A.comp != 0, A.seed_len,
-                           A.W + slot * A.strideW, A.Q + slot * A.strideQ, sW, sB);
+                           A.W + slot * A.strideW, A.Q + slot * A.strideQ);
         if (a == 0) A.n_amb[r] = n;
     }
 }
@@ -360,7 +356,7 @@ struct b200aln_ctx {
     int rec_cap = 8, rec_cap_big = 1 << 16, big_lanes = 1024;
     int batch_max_len = 0; /* > 0: the reference batch this call is a shard of has this longest read */
     /* device buffers */
-    DevBuf lens, offs, codes, md, Q, W, seedW, seedB, n_amb, ent, recs, n_aln, over_slot, over_list, misc, off64,
+    DevBuf lens, offs, codes, md, Q, W, n_amb, ent, recs, n_aln, over_slot, over_list, misc, off64,
         blk_tot, packed, ent_big, recs_big, heads_wide, heads_wide_big;
     HostBuf h_in, h_out, h_misc;
     b200aln_stats_t stats;
@@ -497,7 +493,7 @@ extern "C" void b200aln_close(b200aln_ctx *c)
     if (!c) return;
     cudaSetDevice(c->device);
     cudaStreamSynchronize(c->st);
-    DevBuf *bufs[] = {&c->lens, &c->offs, &c->codes, &c->md, &c->Q, &c->W, &c->seedW, &c->seedB, &c->n_amb, &c->ent,
+    DevBuf *bufs[] = {&c->lens, &c->offs, &c->codes, &c->md, &c->Q, &c->W, &c->n_amb, &c->ent,
                       &c->recs, &c->n_aln, &c->over_slot, &c->over_list, &c->misc, &c->off64, &c->blk_tot,
                       &c->packed, &c->ent_big, &c->recs_big, &c->heads_wide, &c->heads_wide_big};
     for (DevBuf *b : bufs) b->release();
@@ -581,16 +577,14 @@ static void run_batch_device(b200aln_ctx *c, int n_reads, int max_len, const int
                              const Params &P, int64_t *total_out)
 {
     uint64_t launches = 0;
-    const int strideQ = max_len, strideW = max_len + 1;
-    const int wblocks = c->n_sm * c->width_blocks_per_sm, wthreads = wblocks * 128;
+    const int strideQ = round_up8(max_len), strideW = round_up8(max_len + 1); /* 32-byte aligned rows */
+    const int wblocks = c->n_sm * c->width_blocks_per_sm;
     const int sblocks = c->n_sm * c->search_blocks_per_sm;
     const size_t lanes = (size_t)sblocks * 128;
 
     c->md.need(md.size() * 4);
     c->Q.need((size_t)n_reads * 2 * strideQ * sizeof(QRec) + 64);
     c->W.need((size_t)n_reads * 2 * strideW * 4 + 64);
-    c->seedW.need((size_t)wthreads * (opt->seed_len + 1) * 4);
-    c->seedB.need((size_t)wthreads * (opt->seed_len + 1) * 2);
     c->n_amb.need((size_t)n_reads * 4);
     c->ent.need(lanes * c->arena_cap * sizeof(StackEnt));
     c->recs.need((size_t)n_reads * c->rec_cap * 16);
@@ -615,7 +609,7 @@ static void run_batch_device(b200aln_ctx *c, int n_reads, int max_len, const int
     WA.comp = (opt->mode & MODE_COMPREAD) ? 1 : 0; WA.seed_len = opt->seed_len;
     WA.strideQ = strideQ; WA.strideW = strideW;
     WA.Q = c->Q.as<QRec>(); WA.W = c->W.as<uint32_t>();
-    WA.seedW = c->seedW.as<uint32_t>(); WA.seedB = c->seedB.as<uint16_t>(); WA.n_amb = c->n_amb.as<int32_t>();
+    WA.n_amb = c->n_amb.as<int32_t>();
     k_width<<<wblocks, 128, 0, c->st>>>(WA);
     CK(cudaGetLastError());
     ++launches;

@@ -20,7 +20,7 @@ from .opts import GapOpt, GapOptC, UsageError, parse_aln_args
 from .sai import ALN_DTYPE
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libb200aln.so")
+LIB_PATH = os.environ.get("B200ALN_LIB", os.path.join(_HERE, "libb200aln.so"))   # override: kernel A/B experiments
 
 
 class BwtView(ctypes.Structure):

@@ -55,11 +55,9 @@ static int64_t run(const SearchEnv &env, const std::vector<int> &md, int n_reads
 {
     int max_len = 0;
     for (int r = 0; r < n_reads; ++r) if (lens[r] > max_len) max_len = lens[r];
-    const int strideQ = max_len, strideW = max_len + 1;
-    std::vector<QRec> Q(2 * (size_t)strideQ + 2);
-    std::vector<uint32_t> W(2 * (size_t)strideW);
-    std::vector<uint32_t> seedW(seed_len + 1);
-    std::vector<uint16_t> seedB(seed_len + 1);
+    const int strideQ = round_up8(max_len), strideW = round_up8(max_len + 1);
+    std::vector<QRec> Q(2 * (size_t)strideQ + 8);
+    std::vector<uint32_t> W(2 * (size_t)strideW + 8);
     std::vector<StackEnt> ent(arena_cap);
     std::vector<Rec> recs(rec_cap);
     int64_t n_status = 0;
@@ -70,9 +68,8 @@ static int64_t run(const SearchEnv &env, const std::vector<int> &md, int n_reads
         const uint8_t *fwd = codes + offs[r];
         int len = lens[r];
         const FmView *fm = env.fm;
-        int n_amb = width_pass(fm[0], fwd, len, 0, comp, seed_len, W.data(), Q.data(), seedW.data(), seedB.data());
-        width_pass(fm[1], fwd, len, 1, comp, seed_len, W.data() + strideW, Q.data() + strideQ, seedW.data(),
-                   seedB.data());
+        int n_amb = width_pass(fm[0], fwd, len, 0, comp, seed_len, W.data(), Q.data());
+        width_pass(fm[1], fwd, len, 1, comp, seed_len, W.data() + strideW, Q.data() + strideQ);
         SearchLane<Heads, REUSE> lane;
         Arena ar; ar.ent = ent.data(); ar.cap = arena_cap;
         lane.begin(env, ar, make_heads<Heads>(hstore), Q.data(), W.data(), strideQ, strideW, recs.data(), rec_cap, len, md[len], n_amb);
@@ -81,9 +78,8 @@ static int64_t run(const SearchEnv &env, const std::vector<int> &md, int n_reads
             /* the product's large pass: widths rebuilt (the aborted pass shadowed them), free-list arena */
             ++n_status;
             if (ent2.size() < big_cap) { ent2.resize(big_cap); recs2.resize(1 << 16); }
-            n_amb = width_pass(fm[0], fwd, len, 0, comp, seed_len, W.data(), Q.data(), seedW.data(), seedB.data());
-            width_pass(fm[1], fwd, len, 1, comp, seed_len, W.data() + strideW, Q.data() + strideQ, seedW.data(),
-                       seedB.data());
+            n_amb = width_pass(fm[0], fwd, len, 0, comp, seed_len, W.data(), Q.data());
+            width_pass(fm[1], fwd, len, 1, comp, seed_len, W.data() + strideW, Q.data() + strideQ);
             SearchLane<HeadsWide32, true> big;
             Arena ar2; ar2.ent = ent2.data(); ar2.cap = big_cap;
             big.begin(env, ar2, make_heads<HeadsWide32>(hstore), Q.data(), W.data(), strideQ, strideW, recs2.data(), 1 << 16, len, md[len], n_amb);

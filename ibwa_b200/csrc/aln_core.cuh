@@ -51,7 +51,7 @@ struct alignas(32) OccBlk {
 struct alignas(32) StackEnt {
     U4 e;          /* k, l, i | ldp<<16, n_mm | n_gapo<<8 | n_gape<<16 | state<<24 | a<<26 */
     uint32_t link; /* previous entry of the same bucket (or next free slot) */
-    uint32_t pad[3];
+    uint32_t pad[3]; /* pad[0]: path word (depth | k-mer << 5) while the entry is inside the interval table */
 };
 
 #if defined(__CUDA_ARCH__)
@@ -65,18 +65,27 @@ B2_D OccBlk ld_blk(const OccBlk *p)
                  : "l"(p));
     return r;
 }
-B2_D void ld_ent(const StackEnt *p, U4 &e, uint32_t &link)
+B2_D void ld_ent(const StackEnt *p, U4 &e, uint32_t &link, uint32_t &path)
 { /* stack entries: written once, read at most once -> L2 only */
-    [[maybe_unused]] uint32_t p0, p1, p2;
+    [[maybe_unused]] uint32_t p1, p2;
     asm volatile("ld.global.cg.v8.u32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
-                 : "=r"(e.x), "=r"(e.y), "=r"(e.z), "=r"(e.w), "=r"(link), "=r"(p0), "=r"(p1), "=r"(p2)
+                 : "=r"(e.x), "=r"(e.y), "=r"(e.z), "=r"(e.w), "=r"(link), "=r"(path), "=r"(p1), "=r"(p2)
                  : "l"(p) : "memory");
-    (void)p0; (void)p1; (void)p2;
 }
-B2_D void st_ent(StackEnt *p, U4 e, uint32_t link)
+B2_D void st_ent(StackEnt *p, U4 e, uint32_t link, uint32_t path)
 { /* a full sector per store: no read-modify-write in the memory system */
-    asm volatile("st.global.cg.v8.u32 [%0], {%1,%2,%3,%4,%5,%6,%6,%6};"
-                 :: "l"(p), "r"(e.x), "r"(e.y), "r"(e.z), "r"(e.w), "r"(link), "r"(0u) : "memory");
+    asm volatile("st.global.cg.v8.u32 [%0], {%1,%2,%3,%4,%5,%6,%7,%7};"
+                 :: "l"(p), "r"(e.x), "r"(e.y), "r"(e.z), "r"(e.w), "r"(link), "r"(path), "r"(0u) : "memory");
+}
+struct alignas(32) U8x { uint32_t v[8]; };
+B2_D U8x ld_lut8(const void *p)
+{ /* the four children intervals of a node: one sector of the interval table (hot levels live in L2) */
+    U8x r;
+    asm volatile("ld.global.nc.L1::no_allocate.v8.u32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                 : "=r"(r.v[0]), "=r"(r.v[1]), "=r"(r.v[2]), "=r"(r.v[3]), "=r"(r.v[4]), "=r"(r.v[5]), "=r"(r.v[6]),
+                   "=r"(r.v[7])
+                 : "l"(p));
+    return r;
 }
 B2_D void st8(uint32_t *p, const uint32_t v[8])
 { /* eight consecutive words as one full 32-byte sector (p is 32-byte aligned) */
@@ -99,8 +108,10 @@ B2_D int ctz32(uint32_t v) { return __ffs((int)v) - 1; }
 inline uint32_t ld_q(const uint32_t *p) { return *p; }
 inline void st8(uint32_t *p, const uint32_t v[8]) { for (int i = 0; i < 8; ++i) p[i] = v[i]; }
 inline OccBlk ld_blk(const OccBlk *p) { return *p; }
-inline void ld_ent(const StackEnt *p, U4 &e, uint32_t &link) { e = p->e; link = p->link; }
-inline void st_ent(StackEnt *p, U4 e, uint32_t link) { p->e = e; p->link = link; p->pad[0] = p->pad[1] = p->pad[2] = 0; }
+inline void ld_ent(const StackEnt *p, U4 &e, uint32_t &link, uint32_t &path) { e = p->e; link = p->link; path = p->pad[0]; }
+inline void st_ent(StackEnt *p, U4 e, uint32_t link, uint32_t path) { p->e = e; p->link = link; p->pad[0] = path; p->pad[1] = p->pad[2] = 0; }
+struct alignas(32) U8x { uint32_t v[8]; };
+inline U8x ld_lut8(const void *p) { return *reinterpret_cast<const U8x *>(p); }
 inline int popc32(uint32_t v) { return __builtin_popcount(v); }
 inline int ctz32(uint32_t v) { return __builtin_ctz(v); }
 #endif
@@ -112,7 +123,25 @@ struct FmView {
     const OccBlk *blk; /* one per 64 bases */
     uint32_t primary; /* row of the sentinel */
     uint32_t seq_len;
+    /* Interval table of the first lut_k search levels (0 = none): level L (1..lut_k) holds, for every
+     * L-mer X (the characters prepended so far, first one most significant), the SA interval
+     * (k, l) of X as two u32, empty = (1, 0).  The four children X*4+c of a node are one 32-byte
+     * sector, so an expansion above level lut_k costs ONE request instead of two occ sectors,
+     * and the small top levels stay L2 resident. */
+    const uint32_t *lut;
+    int lut_k;
 };
+
+#define B2_PATH_DEAD 31u /* depth field value of an entry that left the interval table */
+B2_HD uint64_t lut_level_off(int level) { return (((uint64_t)1 << (2 * level)) - 4u) / 3u; } /* in (k,l) pairs */
+B2_HD uint32_t path_root() { return 0u; }
+/* path of the child reached by prepending character c to a node with path p */
+B2_HD uint32_t path_ext(uint32_t p, int c, int lut_k)
+{
+    const uint32_t d = p & 31u;
+    if (d == B2_PATH_DEAD || (int)d + 1 >= lut_k) return B2_PATH_DEAD;
+    return (d + 1u) | (((p >> 5) << 2 | (uint32_t)c) << 5);
+}
 
 /* Launch-constant search parameters: gap_opt_t after the batch-level clamps of
  * bwtaln.c:89-92 (max_gapo) — per-read max_diff comes from a table. */
@@ -199,25 +228,99 @@ B2_HD void occ2x4(const FmView &f, uint32_t k, uint32_t l, uint32_t ck[4], uint3
     occ_count4(bb.cnt, bb.bits, qb & 63u, cl);
 }
 
+/* The SA intervals of the four one-character extensions of [k, l] (node `path` of index f):
+ * nk[c] = L2[c] + occ(k-1, c) + 1, nl[c] = L2[c] + occ(l, c) (bwt.c:177-214, bwtgap.c:222-223),
+ * read from the interval table while the node is inside it, from the occ blocks otherwise. */
+B2_HD void children4(const FmView &f, uint32_t path, uint32_t k, uint32_t l, uint32_t nk[4], uint32_t nl[4],
+                     uint32_t &n_sectors)
+{
+    const uint32_t d = path & 31u;
+    if (d != B2_PATH_DEAD && (int)d < f.lut_k) {
+        const uint32_t *p = f.lut + 2 * (lut_level_off((int)d + 1) + ((uint64_t)(path >> 5) << 2));
+        const U8x v = ld_lut8(p);
+        nk[0] = v.v[0]; nl[0] = v.v[1]; nk[1] = v.v[2]; nl[1] = v.v[3];
+        nk[2] = v.v[4]; nl[2] = v.v[5]; nk[3] = v.v[6]; nl[3] = v.v[7];
+        n_sectors = 1;
+        return;
+    }
+    uint32_t ck[4], cl[4];
+    occ2x4(f, k, l, ck, cl, n_sectors);
+    for (int c = 0; c < 4; ++c) { nk[c] = ck[c] + 1u; nl[c] = cl[c]; }
+}
+
+/* Builds the four children of table node X of level `level` (level 0 = the root) into level + 1.
+ * lut is the table being built (levels <= level complete); f.lut_k is ignored here. */
+B2_HD void lut_build_node(const FmView &f, uint32_t *lut, int level, uint64_t X)
+{
+    uint32_t k = 0, l = f.seq_len;
+    if (level > 0) {
+        const uint32_t *p = lut + 2 * (lut_level_off(level) + X);
+        k = p[0];
+        l = p[1];
+    }
+    uint32_t *o = lut + 2 * (lut_level_off(level + 1) + (X << 2));
+    if (k <= l) {
+        uint32_t ck[4], cl[4], ns;
+        occ2x4(f, k, l, ck, cl, ns);
+        for (int c = 0; c < 4; ++c) { o[2 * c] = ck[c] + 1u; o[2 * c + 1] = cl[c]; }
+    } else {
+        for (int c = 0; c < 4; ++c) { o[2 * c] = 1u; o[2 * c + 1] = 0u; }
+    }
+}
+B2_HD uint64_t lut_total_pairs(int lut_k) { return lut_k > 0 ? lut_level_off(lut_k + 1) : 0; }
+
 /* ---------------------------------------------------------- width pass ---- */
 
-/* One chain of bwt_cal_width (bwtaln.c:54-78): the interval and the restart counter. */
+/* One chain of bwt_cal_width (bwtaln.c:54-78): the interval, the restart counter and the chain's
+ * position in the interval table.  A symbol is consumed in two halves — issue() starts the
+ * memory reads, advance() uses them — so that two chains can overlap their latencies. */
 struct WidthChain {
-    uint32_t k, l;
+    uint32_t k, l, path;
     int bid;
-    B2_HD void reset(const FmView &f) { k = 0; l = f.seq_len; bid = 0; }
-    /* finish one symbol given the counts at both interval ends; returns the width l-k+1 */
-    B2_HD uint32_t advance(const FmView &f, int c, const uint32_t ck[4], const uint32_t cl[4])
+    /* in flight */
+    bool use_lut;
+    OccBlk ba, bb;
+    uint32_t qa, qb, lk, ll;
+    B2_HD void reset(const FmView &f) { k = 0; l = f.seq_len; bid = 0; path = path_root(); }
+    B2_HD void issue(const FmView &f, int c)
+    {
+        const uint32_t d = path & 31u;
+        use_lut = d != B2_PATH_DEAD && (int)d < f.lut_k;
+        if (use_lut) {
+            const uint32_t *p = f.lut + 2 * (lut_level_off((int)d + 1) + ((uint64_t)(path >> 5) << 2) + (uint32_t)c);
+            lk = ld_q(p);
+            ll = ld_q(p + 1);
+        } else {
+            qa = q_lower(f, k);
+            qb = q_upper(f, l);
+            const OccBlk *pa = f.blk + (qa >> 6), *pb = f.blk + (qb >> 6);
+            ba = ld_blk(pa);
+            bb = ba;
+            if (pa != pb) bb = ld_blk(pb);
+        }
+    }
+    /* finish symbol c (c > 3: ambiguous, nothing was issued); returns the width l-k+1 */
+    B2_HD uint32_t advance(const FmView &f, int c)
     {
         bool alive = false;
         if (c < 4) {
-            k = pick4(ck, c) + 1u;
-            l = pick4(cl, c);
+            if (use_lut) {
+                k = lk;
+                l = ll;
+            } else {
+                uint32_t ck[4], cl[4];
+                occ_count4(ba.cnt, ba.bits, qa & 63u, ck);
+                occ_count4(bb.cnt, bb.bits, qb & 63u, cl);
+                k = pick4(ck, c) + 1u;
+                l = pick4(cl, c);
+            }
             alive = k <= l;
+            path = path_ext(path, c, f.lut_k);
         }
         if (!alive) {
             k = 0;
             l = f.seq_len;
+            path = path_root();
             ++bid;
         }
         return l - k + 1u;
@@ -268,32 +371,14 @@ B2_HD int width_pass(const FmView &f, const uint8_t *fwd, int len, int a, bool c
                 const int c = strand_sym(fwd, len, a, j, comp);
                 const bool seed_on = use_seed && j >= shift;
                 n_amb += c > 3;
-                uint32_t mk[4], ml[4], sk[4], sl[4];
-                if (c < 4) { /* issue the loads of both chains before using either */
-                    const uint32_t qa = q_lower(f, m.k), qb_ = q_upper(f, m.l);
-                    const OccBlk *pa = f.blk + (qa >> 6), *pb = f.blk + (qb_ >> 6);
-                    OccBlk ba = ld_blk(pa), bb = ba, ca_ = ba, cb = ba;
-                    if (pa != pb) bb = ld_blk(pb);
-                    uint32_t ra = 0, rb = 0;
-                    if (seed_on) {
-                        ra = q_lower(f, s.k);
-                        rb = q_upper(f, s.l);
-                        const OccBlk *sa = f.blk + (ra >> 6), *sb = f.blk + (rb >> 6);
-                        ca_ = ld_blk(sa);
-                        cb = ca_;
-                        if (sa != sb) cb = ld_blk(sb);
-                    }
-                    occ_count4(ba.cnt, ba.bits, qa & 63u, mk);
-                    occ_count4(bb.cnt, bb.bits, qb_ & 63u, ml);
-                    if (seed_on) {
-                        occ_count4(ca_.cnt, ca_.bits, ra & 63u, sk);
-                        occ_count4(cb.cnt, cb.bits, rb & 63u, sl);
-                    }
+                if (c < 4) { /* start the reads of both chains before using either */
+                    m.issue(f, c);
+                    if (seed_on) s.issue(f, c);
                 }
-                const uint32_t w = m.advance(f, c, mk, ml);
+                const uint32_t w = m.advance(f, c);
                 uint32_t sact = 0, sb2 = 0, sbp = 0, seq = 0;
                 if (seed_on) {
-                    const uint32_t sw = s.advance(f, c, sk, sl);
+                    const uint32_t sw = s.advance(f, c);
                     if (j > shift) { /* ii > 0 */
                         sact = 1;
                         sb2 = (uint32_t)s.bid;
@@ -464,6 +549,7 @@ struct SearchLane {
     uint32_t ck, cl;
     int ci, cldp, cmm, cgo, cge, cstate, ca, cscore;
     int cdmask; /* family record: which deletions exist */
+    uint32_t cpath; /* position of the current entry in the interval table */
     uint32_t n_pops, n_lookups; /* instrumentation: pops and 32-byte sectors of this read */
 
     static B2_HD int score_of(const Params &P, int mm, int go, int ge)
@@ -491,12 +577,12 @@ struct SearchLane {
         if (n_amb > max_diff_) { finished = true; return; } /* bwtgap.c:117-122 */
         bk.clear(P->n_buckets);
         /* roots: strand 0 then strand 1 (bwtgap.c:126-127) -> strand 1 pops first */
-        push(E, 0, len, 0, fm[0].seq_len, 0, 0, 0, ST_M, 0);
-        push(E, 1, len, 0, fm[0].seq_len, 0, 0, 0, ST_M, 0);
+        push(E, 0, len, 0, fm[0].seq_len, 0, 0, 0, ST_M, 0, path_root());
+        push(E, 1, len, 0, fm[0].seq_len, 0, 0, 0, ST_M, 0, path_root());
     }
 
     B2_HD void push(const SearchEnv &E, int a, int i, uint32_t k, uint32_t l, int mm, int go, int ge, int state,
-                    int ldp)
+                    int ldp, uint32_t path)
     {
         int sc = score_of(E.P, mm, go, ge);
         uint32_t slot;
@@ -511,7 +597,7 @@ struct SearchLane {
         e.x = k; e.y = l;
         e.z = (uint32_t)i | (uint32_t)ldp << 16;
         e.w = (uint32_t)mm | (uint32_t)go << 8 | (uint32_t)ge << 16 | (uint32_t)state << 24 | (uint32_t)a << 26;
-        st_ent(ar.ent + slot, e, bk.get(sc));
+        st_ent(ar.ent + slot, e, bk.get(sc), path);
         bk.set(sc, slot);
         bk.mark(sc);
         ++n_entries;
@@ -522,7 +608,7 @@ struct SearchLane {
      * contiguously in the bucket; the record is expanded in place into the real entries only
      * if the search ever reaches it (step(), mode 2).  It counts as 1 + popc(dmask) entries. */
     B2_HD void push_family(const SearchEnv &E, int a, int i, uint32_t k, uint32_t l, int mm, int go, int ge,
-                           int dmask)
+                           int dmask, uint32_t path)
     {
         int sc = score_of(E.P, mm, go + 1, ge);
         uint32_t slot;
@@ -537,7 +623,7 @@ struct SearchLane {
         e.x = k; e.y = l;
         e.z = (uint32_t)i | (uint32_t)dmask << 16;
         e.w = (uint32_t)mm | (uint32_t)go << 8 | (uint32_t)ge << 16 | 3u << 24 | (uint32_t)a << 26;
-        st_ent(ar.ent + slot, e, bk.get(sc));
+        st_ent(ar.ent + slot, e, bk.get(sc), path);
         bk.set(sc, slot);
         bk.mark(sc);
         n_entries += 1 + popc32((uint32_t)dmask);
@@ -550,7 +636,7 @@ struct SearchLane {
         uint32_t slot = bk.get(b);
         U4 e;
         uint32_t prev;
-        ld_ent(ar.ent + slot, e, prev);
+        ld_ent(ar.ent + slot, e, prev, cpath);
         bk.set(b, prev);
         if (prev == B2_NIL) bk.unmark(b);
         if (REUSE) { ar.ent[slot].link = free_head; free_head = slot; }
@@ -644,10 +730,11 @@ struct SearchLane {
         }
     }
 
-    /* consume the counts of the lookup issued for `mode` on interval [ck, cl] of fm[1 - ca] */
-    B2_HD void apply(const SearchEnv &E, int mode, const uint32_t cntk[4], const uint32_t cntl[4], uint32_t ns)
+    /* consume the children intervals (children4) of the current entry [ck, cl] on fm[1 - ca] */
+    B2_HD void apply(const SearchEnv &E, int mode, const uint32_t nk4[4], const uint32_t nl4[4], uint32_t ns)
     {
         const Params *P = &E.P;
+        const int K = E.fm[1 - ca].lut_k;
         const bool gape_mode = P->mode & MODE_GAPE;
         const QRec q = pq;
         const int m = pm;
@@ -656,9 +743,10 @@ struct SearchLane {
         if (mode == MATERIALIZE) { /* expand a family record in place, in the reference's push order */
             have_cur = false;
             const int i = ci;
-            push(E, ca, i, ck, cl, cmm, cgo + 1, cge, ST_I, i);
+            push(E, ca, i, ck, cl, cmm, cgo + 1, cge, ST_I, i, cpath);
             for (int j = 0; j < 4; ++j)
-                if (cdmask >> j & 1) push(E, ca, i + 1, cntk[j] + 1u, cntl[j], cmm, cgo + 1, cge, ST_D, i + 1);
+                if (cdmask >> j & 1)
+                    push(E, ca, i + 1, nk4[j], nl4[j], cmm, cgo + 1, cge, ST_D, i + 1, path_ext(cpath, j, K));
             return;
         }
 
@@ -667,9 +755,10 @@ struct SearchLane {
         if (mode == EXTEND) { /* one step of bwt_match_exact_alt (bwt.c:235-250) */
             B2_DBG(5);
             if (base > 3) { extending = false; return; }
-            ck = pick4(cntk, base) + 1u;
-            cl = pick4(cntl, base);
+            ck = pick4(nk4, base);
+            cl = pick4(nl4, base);
             if (ck > cl) { extending = false; return; }
+            cpath = path_ext(cpath, base, K);
             ci = i;
             if (ci == 0) {
                 extending = false;
@@ -702,18 +791,17 @@ struct SearchLane {
             if (cstate == ST_M) {
                 if (cgo < P->max_gapo) { /* gap open: insertion + deletions as one family record */
                     int dmask = 0;
-                    for (int j = 0; j < 4; ++j) dmask |= (cntk[j] + 1u <= cntl[j] ? 1 : 0) << j;
+                    for (int j = 0; j < 4; ++j) dmask |= (nk4[j] <= nl4[j] ? 1 : 0) << j;
                     B2_DBG(1);
-                    push_family(E, ca, i, ck, cl, cmm, cgo, cge, dmask);
+                    push_family(E, ca, i, ck, cl, cmm, cgo, cge, dmask, cpath);
                 }
             } else if (cstate == ST_I) {
-                if (cge < P->max_gape) push(E, ca, i, ck, cl, cmm, cgo, cge + 1, ST_I, i);
+                if (cge < P->max_gape) push(E, ca, i, ck, cl, cmm, cgo, cge + 1, ST_I, i, cpath);
             } else {
                 if (cge < P->max_gape && (cge + cgo < max_diff || occ < (uint32_t)P->max_del_occ))
-                    for (int j = 0; j < 4; ++j) {
-                        uint32_t nk = cntk[j] + 1u, nl = cntl[j];
-                        if (nk <= nl) push(E, ca, i + 1, nk, nl, cmm, cgo, cge + 1, ST_D, i + 1);
-                    }
+                    for (int j = 0; j < 4; ++j)
+                        if (nk4[j] <= nl4[j])
+                            push(E, ca, i + 1, nk4[j], nl4[j], cmm, cgo, cge + 1, ST_D, i + 1, path_ext(cpath, j, K));
             }
         }
         if (finished) return; /* arena overflow */
@@ -722,22 +810,23 @@ struct SearchLane {
         if (allow_diff && allow_M) {
             for (int j = 1; j <= 3; ++j) {
                 int c = (base + j) & 3;
-                uint32_t nk = pick4(cntk, c) + 1u, nl = pick4(cntl, c);
+                uint32_t nk = pick4(nk4, c), nl = pick4(nl4, c);
                 if (nk <= nl) B2_DBG(3);
-                if (nk <= nl) push(E, ca, i, nk, nl, cmm + 1, cgo, cge, ST_M, i);
+                if (nk <= nl) push(E, ca, i, nk, nl, cmm + 1, cgo, cge, ST_M, i, path_ext(cpath, c, K));
             }
             if (base > 3) { /* ambiguous base: the j == 4 child is a mismatch too */
                 int c = base & 3;
-                uint32_t nk = pick4(cntk, c) + 1u, nl = pick4(cntl, c);
-                if (nk <= nl) push(E, ca, i, nk, nl, cmm + 1, cgo, cge, ST_M, i);
+                uint32_t nk = pick4(nk4, c), nl = pick4(nl4, c);
+                if (nk <= nl) push(E, ca, i, nk, nl, cmm + 1, cgo, cge, ST_M, i, path_ext(cpath, c, K));
             } else child = true;
         } else if (base < 4) child = true;
         if (finished) return;
 
         if (child) { /* exact-match child: held in registers, counted like a push */
-            uint32_t nk = pick4(cntk, base) + 1u, nl = pick4(cntl, base);
+            uint32_t nk = pick4(nk4, base), nl = pick4(nl4, base);
             if (nk <= nl) {
                 ck = nk; cl = nl; ci = i; cstate = ST_M; /* counters, score, ldp, strand inherited */
+                cpath = path_ext(cpath, base, K);
                 have_cur = true;
                 ++n_entries;
             }
@@ -748,9 +837,9 @@ struct SearchLane {
     {
         const int mode = prepare(E);
         if (mode == NONE) return;
-        uint32_t cntk[4], cntl[4], ns;
-        occ2x4(E.fm[1 - ca], ck, cl, cntk, cntl, ns);
-        apply(E, mode, cntk, cntl, ns);
+        uint32_t nk4[4], nl4[4], ns;
+        children4(E.fm[1 - ca], cpath, ck, cl, nk4, nl4, ns);
+        apply(E, mode, nk4, nl4, ns);
     }
 };
 

@@ -52,6 +52,12 @@ __global__ void k_convert_index(RefBwt r, OccBlk *out, uint64_t nb)
         out[b] = fm_convert_block(r, b);
 }
 
+__global__ void k_lut_build(FmView f, uint32_t *lut, int level, uint64_t n_nodes)
+{ /* children of every node of `level` -> level + 1 of the interval table */
+    for (uint64_t X = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; X < n_nodes; X += (uint64_t)gridDim.x * blockDim.x)
+        lut_build_node(f, lut, level, X);
+}
+
 struct WidthArgs {
     FmView fm[2];
     int n_reads;               /* number of work items */
@@ -167,10 +173,10 @@ __global__ void __launch_bounds__(128, MINB) k_search(const __grid_constant__ Se
         int mode = L.NONE;
         if (active && !L.finished) mode = L.prepare(A.env);
         __syncwarp();
-        uint32_t cntk[4], cntl[4], ns = 0;
-        if (mode != L.NONE) occ2x4(A.env.fm[1 - L.ca], L.ck, L.cl, cntk, cntl, ns);
+        uint32_t nk4[4], nl4[4], ns = 0;
+        if (mode != L.NONE) children4(A.env.fm[1 - L.ca], L.cpath, L.ck, L.cl, nk4, nl4, ns);
         __syncwarp();
-        if (mode != L.NONE) L.apply(A.env, mode, cntk, cntl, ns);
+        if (mode != L.NONE) L.apply(A.env, mode, nk4, nl4, ns);
         __syncwarp();
         if (active) {
             if (L.finished) {
@@ -354,6 +360,8 @@ struct b200aln_ctx {
     int search_blocks_per_sm = 6, width_blocks_per_sm = 8;
     uint32_t arena_cap = 4096, arena_cap_big = 0; /* 0: max_entries + 64 */
     int rec_cap = 8, rec_cap_big = 1 << 16, big_lanes = 1024;
+    int lut_k = 12;        /* levels of the path-k-mer interval table (0 = off) */
+    uint32_t *d_lut[2] = {nullptr, nullptr};
     int batch_max_len = 0; /* > 0: the reference batch this call is a shard of has this longest read */
     /* device buffers */
     DevBuf lens, offs, codes, md, Q, W, n_amb, ent, recs, n_aln, over_slot, over_list, misc, off64,
@@ -420,7 +428,11 @@ static void upload_index(b200aln_ctx *c, int which, const b200aln_bwt_view_t *v)
     c->fm[which].blk = c->d_idx[which];
     c->fm[which].primary = v->primary;
     c->fm[which].seq_len = v->seq_len;
+    c->fm[which].lut = nullptr;
+    c->fm[which].lut_k = 0;
 }
+
+static void build_luts(b200aln_ctx *c);
 
 extern "C" b200aln_ctx *b200aln_open(const b200aln_bwt_view_t *bwt, const b200aln_bwt_view_t *rbwt, int device)
 {
@@ -451,8 +463,38 @@ extern "C" b200aln_ctx *b200aln_open(const b200aln_bwt_view_t *bwt, const b200al
     for (int i = 0; i < 2; ++i) CK(cudaEventCreate(&c->tm[i]));
     upload_index(c, 0, bwt);
     upload_index(c, 1, rbwt);
+    {
+        const char *e = getenv("B200ALN_LUT_K");
+        if (e) c->lut_k = atoi(e);
+    }
+    build_luts(c);
     memset(&c->stats, 0, sizeof c->stats);
     return c;
+}
+
+/* (re)builds the interval tables of both indexes for c->lut_k levels (clamped to the index size) */
+static void build_luts(b200aln_ctx *c)
+{
+    int k = c->lut_k;
+    if (k > 13) k = 13;
+    while (k > 0 && ((uint64_t)1 << (2 * k)) > 4ull * ((uint64_t)c->fm[0].seq_len + 1)) --k; /* tiny indexes */
+    for (int w = 0; w < 2; ++w) {
+        if (c->d_lut[w]) { CK(cudaFree(c->d_lut[w])); c->d_lut[w] = nullptr; }
+        c->fm[w].lut = nullptr;
+        c->fm[w].lut_k = 0;
+        if (k <= 0) continue;
+        CK(cudaMalloc(&c->d_lut[w], lut_total_pairs(k) * 8 + 64));
+        FmView f = c->fm[w];
+        for (int level = 0; level < k; ++level) {
+            const uint64_t n = (uint64_t)1 << (2 * level);
+            const int blocks = (int)((n + 255) / 256 < (uint64_t)c->n_sm * 16 ? (n + 255) / 256 : (uint64_t)c->n_sm * 16);
+            k_lut_build<<<blocks, 256, 0, c->st>>>(f, c->d_lut[w], level, n);
+            CK(cudaGetLastError());
+        }
+        c->fm[w].lut = c->d_lut[w];
+        c->fm[w].lut_k = k;
+    }
+    CK(cudaStreamSynchronize(c->st));
 }
 
 static bool read_bwt_file(const char *fn, std::vector<uint32_t> &words, b200aln_bwt_view_t *v)
@@ -499,6 +541,7 @@ extern "C" void b200aln_close(b200aln_ctx *c)
     for (DevBuf *b : bufs) b->release();
     c->h_in.release(); c->h_out.release(); c->h_misc.release();
     for (int i = 0; i < 2; ++i) if (c->d_idx[i]) cudaFree(c->d_idx[i]);
+    for (int i = 0; i < 2; ++i) if (c->d_lut[i]) cudaFree(c->d_lut[i]);
     for (int i = 0; i < 8; ++i) cudaEventDestroy(c->ev[i]);
     for (int i = 0; i < 2; ++i) cudaEventDestroy(c->tm[i]);
     cudaStreamDestroy(c->st);
@@ -515,6 +558,7 @@ extern "C" void b200aln_set_int(b200aln_ctx *c, const char *key, int64_t v)
     else if (!strcmp(key, "rec_cap_big")) c->rec_cap_big = (int)v;
     else if (!strcmp(key, "big_lanes")) c->big_lanes = (int)v;
     else if (!strcmp(key, "batch_max_len")) c->batch_max_len = (int)v;
+    else if (!strcmp(key, "lut_k")) { c->lut_k = (int)v; build_luts(c); }
     else die("b200aln_set_int", "unknown key '%s'.", key);
 }
 

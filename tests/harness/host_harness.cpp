@@ -98,6 +98,19 @@ static int64_t run(const SearchEnv &env, const std::vector<int> &md, int n_reads
     return n_status;
 }
 
+static std::vector<uint32_t> build_lut(FmView &f, int lut_k)
+{
+    std::vector<uint32_t> lut(2 * lut_total_pairs(lut_k) + 8);
+    f.lut = nullptr;
+    f.lut_k = 0;
+    for (int level = 0; level < lut_k; ++level)
+        for (uint64_t X = 0; X < ((uint64_t)1 << (2 * level)); ++X) lut_build_node(f, lut.data(), level, X);
+    return lut;
+}
+
+static int g_lut_k = 0;
+extern "C" void hh_set_lut_k(int k) { g_lut_k = k; }
+
 extern "C" int64_t hh_aln_batch(const b200aln_bwt_view_t *bwt, const b200aln_bwt_view_t *rbwt, int n_reads,
                                 const int32_t *lens, const int64_t *offs, const uint8_t *codes,
                                 const b200aln_opt_t *opt, uint32_t arena_cap, int rec_cap, int reuse, uint32_t big_cap,
@@ -109,6 +122,9 @@ extern "C" int64_t hh_aln_batch(const b200aln_bwt_view_t *bwt, const b200aln_bwt
     FmView *fm = env.fm;
     fm[0].blk = i0.data(); fm[0].primary = bwt->primary; fm[0].seq_len = bwt->seq_len;
     fm[1].blk = i1.data(); fm[1].primary = rbwt->primary; fm[1].seq_len = rbwt->seq_len;
+    std::vector<uint32_t> lut0 = build_lut(fm[0], g_lut_k), lut1 = build_lut(fm[1], g_lut_k);
+    fm[0].lut = lut0.data(); fm[1].lut = lut1.data();
+    fm[0].lut_k = fm[1].lut_k = g_lut_k;
     int max_len = 0;
     for (int r = 0; r < n_reads; ++r) if (lens[r] > max_len) max_len = lens[r];
     Params &P = env.P;

@@ -50,8 +50,10 @@ def lib():
     return _lib
 
 
-def aln_batch(bwt, rbwt, lens, offs, codes, opt_c, arena_cap=1 << 16, rec_cap=256, reuse=False, big_cap=0, batch_max_len=0):
+def aln_batch(bwt, rbwt, lens, offs, codes, opt_c, arena_cap=1 << 16, rec_cap=256, reuse=False, big_cap=0, batch_max_len=0,
+              lut_k=0):
     L = lib()
+    L.hh_set_lut_k(ctypes.c_int(lut_k))
     lens = np.ascontiguousarray(lens, np.int32)
     offs = np.ascontiguousarray(offs, np.int64)
     codes = np.ascontiguousarray(codes, np.uint8)

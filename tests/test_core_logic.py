@@ -71,3 +71,14 @@ def test_two_pass_flow_is_exact(tag, golden_dir, g1_index):
                            arena_cap=64, rec_cap=1, big_cap=1 << 22)
     assert nov > 0
     assert got == open(os.path.join(golden_dir, f"g1_{tag}.sai"), "rb").read()
+
+
+@pytest.mark.parametrize("lut_k", [1, 3, 6, 9])
+@pytest.mark.parametrize("tag", ["default", "stress", "N_n2", "short_o3", "m200", "c"])
+def test_interval_table_is_exact(tag, lut_k, golden_dir, g1_index):
+    """The path-k-mer interval table replaces occ lookups for the first lut_k levels; bytes must not change."""
+    args, fq = CASES[tag]
+    got, nov = harness_sai(g1_index[0], g1_index[1], args, os.path.join(golden_dir, fq + ".fq.gz"),
+                           arena_cap=65000, rec_cap=4096, lut_k=lut_k)
+    assert nov == 0
+    assert got == open(os.path.join(golden_dir, f"g1_{tag}.sai"), "rb").read()

@@ -138,8 +138,8 @@ B2_HD uint32_t path_root() { return 0u; }
 /* path of the child reached by prepending character c to a node with path p */
 B2_HD uint32_t path_ext(uint32_t p, int c, int lut_k)
 {
-    const uint32_t d = p & 31u;
-    if (d == B2_PATH_DEAD || (int)d + 1 >= lut_k) return B2_PATH_DEAD;
+    const uint32_t d = p & 31u; /* B2_PATH_DEAD = 31 >= any lut_k, so one comparison covers both cases */
+    if ((int)d + 1 >= lut_k) return B2_PATH_DEAD;
     return (d + 1u) | (((p >> 5) << 2 | (uint32_t)c) << 5);
 }
 
@@ -577,14 +577,14 @@ struct SearchLane {
         if (n_amb > max_diff_) { finished = true; return; } /* bwtgap.c:117-122 */
         bk.clear(P->n_buckets);
         /* roots: strand 0 then strand 1 (bwtgap.c:126-127) -> strand 1 pops first */
-        push(E, 0, len, 0, fm[0].seq_len, 0, 0, 0, ST_M, 0, path_root());
-        push(E, 1, len, 0, fm[0].seq_len, 0, 0, 0, ST_M, 0, path_root());
+        push(E, 0, len, 0, fm[0].seq_len, 0, 0, 0, ST_M, 0, path_root(), 0);
+        push(E, 1, len, 0, fm[0].seq_len, 0, 0, 0, ST_M, 0, path_root(), 0);
     }
 
     B2_HD void push(const SearchEnv &E, int a, int i, uint32_t k, uint32_t l, int mm, int go, int ge, int state,
-                    int ldp, uint32_t path)
+                    int ldp, uint32_t path, int sc)
     {
-        int sc = score_of(E.P, mm, go, ge);
+        (void)E;
         uint32_t slot;
         if (REUSE && free_head != B2_NIL) {
             slot = free_head;
@@ -608,9 +608,9 @@ struct SearchLane {
      * contiguously in the bucket; the record is expanded in place into the real entries only
      * if the search ever reaches it (step(), mode 2).  It counts as 1 + popc(dmask) entries. */
     B2_HD void push_family(const SearchEnv &E, int a, int i, uint32_t k, uint32_t l, int mm, int go, int ge,
-                           int dmask, uint32_t path)
+                           int dmask, uint32_t path, int sc)
     {
-        int sc = score_of(E.P, mm, go + 1, ge);
+        (void)E;
         uint32_t slot;
         if (REUSE && free_head != B2_NIL) {
             slot = free_head;
@@ -734,7 +734,7 @@ struct SearchLane {
     B2_HD void apply(const SearchEnv &E, int mode, const uint32_t nk4[4], const uint32_t nl4[4], uint32_t ns)
     {
         const Params *P = &E.P;
-        const int K = E.fm[1 - ca].lut_k;
+        const int K = E.fm[0].lut_k; /* same for both indexes */
         const bool gape_mode = P->mode & MODE_GAPE;
         const QRec q = pq;
         const int m = pm;
@@ -743,10 +743,11 @@ struct SearchLane {
         if (mode == MATERIALIZE) { /* expand a family record in place, in the reference's push order */
             have_cur = false;
             const int i = ci;
-            push(E, ca, i, ck, cl, cmm, cgo + 1, cge, ST_I, i, cpath);
+            /* a family record sits in the bucket of its members: cscore is their score */
+            push(E, ca, i, ck, cl, cmm, cgo + 1, cge, ST_I, i, cpath, cscore);
             for (int j = 0; j < 4; ++j)
                 if (cdmask >> j & 1)
-                    push(E, ca, i + 1, nk4[j], nl4[j], cmm, cgo + 1, cge, ST_D, i + 1, path_ext(cpath, j, K));
+                    push(E, ca, i + 1, nk4[j], nl4[j], cmm, cgo + 1, cge, ST_D, i + 1, path_ext(cpath, j, K), cscore);
             return;
         }
 
@@ -793,15 +794,16 @@ struct SearchLane {
                     int dmask = 0;
                     for (int j = 0; j < 4; ++j) dmask |= (nk4[j] <= nl4[j] ? 1 : 0) << j;
                     B2_DBG(1);
-                    push_family(E, ca, i, ck, cl, cmm, cgo, cge, dmask, cpath);
+                    push_family(E, ca, i, ck, cl, cmm, cgo, cge, dmask, cpath, cscore + P->s_gapo);
                 }
             } else if (cstate == ST_I) {
-                if (cge < P->max_gape) push(E, ca, i, ck, cl, cmm, cgo, cge + 1, ST_I, i, cpath);
+                if (cge < P->max_gape) push(E, ca, i, ck, cl, cmm, cgo, cge + 1, ST_I, i, cpath, cscore + P->s_gape);
             } else {
                 if (cge < P->max_gape && (cge + cgo < max_diff || occ < (uint32_t)P->max_del_occ))
                     for (int j = 0; j < 4; ++j)
                         if (nk4[j] <= nl4[j])
-                            push(E, ca, i + 1, nk4[j], nl4[j], cmm, cgo, cge + 1, ST_D, i + 1, path_ext(cpath, j, K));
+                            push(E, ca, i + 1, nk4[j], nl4[j], cmm, cgo, cge + 1, ST_D, i + 1, path_ext(cpath, j, K),
+                                 cscore + P->s_gape);
             }
         }
         if (finished) return; /* arena overflow */
@@ -812,12 +814,12 @@ struct SearchLane {
                 int c = (base + j) & 3;
                 uint32_t nk = pick4(nk4, c), nl = pick4(nl4, c);
                 if (nk <= nl) B2_DBG(3);
-                if (nk <= nl) push(E, ca, i, nk, nl, cmm + 1, cgo, cge, ST_M, i, path_ext(cpath, c, K));
+                if (nk <= nl) push(E, ca, i, nk, nl, cmm + 1, cgo, cge, ST_M, i, path_ext(cpath, c, K), cscore + P->s_mm);
             }
             if (base > 3) { /* ambiguous base: the j == 4 child is a mismatch too */
                 int c = base & 3;
                 uint32_t nk = pick4(nk4, c), nl = pick4(nl4, c);
-                if (nk <= nl) push(E, ca, i, nk, nl, cmm + 1, cgo, cge, ST_M, i, path_ext(cpath, c, K));
+                if (nk <= nl) push(E, ca, i, nk, nl, cmm + 1, cgo, cge, ST_M, i, path_ext(cpath, c, K), cscore + P->s_mm);
             } else child = true;
         } else if (base < 4) child = true;
         if (finished) return;

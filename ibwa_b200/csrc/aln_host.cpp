@@ -20,7 +20,11 @@
 #include <unistd.h>
 #include <zlib.h>
 
+#include <deque>
+#include <future>
+#include <memory>
 #include <string>
+#include <thread>
 #include <vector>
 
 #include "../../include/b200aln.h"
@@ -276,45 +280,112 @@ extern "C" void b200aln_cal_sa_reg_gap(b200aln_ctx *ctx, int n_seqs, void *seqs_
     }
 }
 
+namespace {
+
+struct BatchResult {
+    std::vector<int32_t> n_aln;
+    std::vector<b200aln_rec_t> recs;
+    double seconds = 0;
+};
+
+/* one reference batch on `ctxs` (one context per GPU): contiguous shards, concatenated in input order */
+BatchResult process_batch(const std::vector<b200aln_ctx *> &ctxs, const PackedBatch &b, const b200aln_opt_t *opt)
+{
+    struct timespec t0, t1;
+    clock_gettime(CLOCK_MONOTONIC, &t0);
+    const int n = (int)b.lens.size(), g = (int)ctxs.size();
+    int max_len = 0;
+    for (int r = 0; r < n; ++r) if (b.lens[r] > max_len) max_len = b.lens[r];
+    BatchResult out;
+    out.n_aln.resize((size_t)n);
+    std::vector<std::vector<b200aln_rec_t>> part((size_t)g);
+    auto run = [&](int gi) {
+        const int base = n / g, rem = n % g;
+        const int lo = gi * base + (gi < rem ? gi : rem), hi = lo + base + (gi < rem ? 1 : 0);
+        if (hi <= lo) return;
+        /* shards keep the batch-level max_gapo clamp of the whole batch (bwtaln.c:89-92) */
+        b200aln_set_int(ctxs[gi], "batch_max_len", max_len);
+        const int64_t start = b.offs[lo];
+        std::vector<int64_t> offs((size_t)(hi - lo));
+        for (int r = lo; r < hi; ++r) offs[r - lo] = b.offs[r] - start;
+        int64_t total = 0;
+        const b200aln_rec_t *rec = b200aln_batch(ctxs[gi], hi - lo, b.lens.data() + lo, offs.data(),
+                                                 b.codes.data() + start, opt, out.n_aln.data() + lo, &total);
+        part[gi].assign(rec, rec + total);
+    };
+    if (g == 1) run(0);
+    else {
+        std::vector<std::thread> th;
+        for (int gi = 0; gi < g; ++gi) th.emplace_back(run, gi);
+        for (auto &t : th) t.join();
+    }
+    for (int gi = 0; gi < g; ++gi) out.recs.insert(out.recs.end(), part[gi].begin(), part[gi].end());
+    clock_gettime(CLOCK_MONOTONIC, &t1);
+    out.seconds = (t1.tv_sec - t0.tv_sec) + 1e-9 * (t1.tv_nsec - t0.tv_nsec);
+    return out;
+}
+
+} // namespace
+
 extern "C" int64_t b200aln_aln_core(const char *prefix, const char *fn_fa, const b200aln_opt_t *opt, int out_fd,
                                     int device)
 {
     if (opt->mode & BWA_MODE_BAM)
         b2host::fatal("b200aln_aln_core", "BAM input (-b) is not implemented in this engine; convert to FASTQ.");
     SeqReader rd(fn_fa);
-    b200aln_ctx *ctx = b200aln_open_prefix(prefix, device < 0 ? 0 : device);
+    /* devices: one, or all visible; per device two contexts (index shared) so that two batches are in
+     * flight: the copies and host work of one overlap the kernels of the other */
+    std::vector<int> devs;
+    if (device >= 0) devs.push_back(device);
+    else for (int d = 0; d < b200aln_device_count(); ++d) devs.push_back(d);
+    if (devs.empty()) b2host::fatal("b200aln_aln_core", "no CUDA device available; this engine has no CPU fallback.");
+    std::vector<b200aln_ctx *> slot_ctx[2];
+    for (int d : devs) {
+        b200aln_ctx *c = b200aln_open_prefix(prefix, d);
+        slot_ctx[0].push_back(c);
+        slot_ctx[1].push_back(b200aln_clone(c));
+    }
     FILE *out = fdopen(dup(out_fd), "wb");
     if (!out) b2host::fatal("b200aln_aln_core", "cannot open the output descriptor.");
     fwrite(opt, sizeof(b200aln_opt_t), 1, out); /* bwtaln.c:192 */
-    PackedBatch b;
-    std::vector<int32_t> n_aln;
-    int64_t tot_seqs = 0;
-    int n;
-    while ((n = next_batch(rd, 0x40000, opt->mode, opt->trim_qual, b)) != 0) {
-        tot_seqs += n;
+
+    int64_t tot_seqs = 0, written = 0;
+    std::deque<std::future<BatchResult>> inflight;
+    auto drain_one = [&]() {
+        BatchResult r = inflight.front().get();
+        inflight.pop_front();
+        fprintf(stderr, "[bwa_aln_core] calculate SA coordinate... %.2f sec\n", r.seconds);
+        fprintf(stderr, "[bwa_aln_core] write to the disk... ");
         struct timespec t0, t1;
         clock_gettime(CLOCK_MONOTONIC, &t0);
-        fprintf(stderr, "[bwa_aln_core] calculate SA coordinate... ");
-        n_aln.resize((size_t)n);
-        int64_t total = 0;
-        const b200aln_rec_t *rec =
-            b200aln_batch(ctx, n, b.lens.data(), b.offs.data(), b.codes.data(), opt, n_aln.data(), &total);
-        clock_gettime(CLOCK_MONOTONIC, &t1);
-        fprintf(stderr, "%.2f sec\n", (t1.tv_sec - t0.tv_sec) + 1e-9 * (t1.tv_nsec - t0.tv_nsec));
-        fprintf(stderr, "[bwa_aln_core] write to the disk... ");
-        clock_gettime(CLOCK_MONOTONIC, &t0);
-        int64_t at = 0;
-        for (int r = 0; r < n; ++r) { /* bwtaln.c:227-231 */
-            fwrite(&n_aln[r], 4, 1, out);
-            if (n_aln[r]) fwrite(rec + at, sizeof(b200aln_rec_t), (size_t)n_aln[r], out);
-            at += n_aln[r];
+        size_t at = 0;
+        for (size_t i = 0; i < r.n_aln.size(); ++i) { /* bwtaln.c:227-231 */
+            fwrite(&r.n_aln[i], 4, 1, out);
+            if (r.n_aln[i]) fwrite(r.recs.data() + at, sizeof(b200aln_rec_t), (size_t)r.n_aln[i], out);
+            at += (size_t)r.n_aln[i];
         }
         clock_gettime(CLOCK_MONOTONIC, &t1);
+        written += (int64_t)r.n_aln.size();
         fprintf(stderr, "%.2f sec\n", (t1.tv_sec - t0.tv_sec) + 1e-9 * (t1.tv_nsec - t0.tv_nsec));
-        fprintf(stderr, "[bwa_aln_core] %lld sequences have been processed.\n", (long long)tot_seqs);
+        fprintf(stderr, "[bwa_aln_core] %lld sequences have been processed.\n", (long long)written);
+    };
+    int seq = 0;
+    for (;;) {
+        auto b = std::make_shared<PackedBatch>();
+        const int n = next_batch(rd, 0x40000, opt->mode, opt->trim_qual, *b);
+        if (n == 0) break;
+        tot_seqs += n;
+        const std::vector<b200aln_ctx *> *ctxs = &slot_ctx[seq & 1];
+        if (inflight.size() == 2) drain_one(); /* the slot's previous batch is finished and written */
+        inflight.push_back(std::async(std::launch::async, [ctxs, b, opt]() { return process_batch(*ctxs, *b, opt); }));
+        ++seq;
     }
+    while (!inflight.empty()) drain_one();
     fclose(out);
-    b200aln_close(ctx);
+    for (size_t i = 0; i < devs.size(); ++i) {
+        b200aln_close(slot_ctx[1][i]);
+        b200aln_close(slot_ctx[0][i]);
+    }
     return tot_seqs;
 }
 
@@ -400,6 +471,9 @@ extern "C" int b200aln_aln_main(int argc, char *argv[])
         }
     }
     fflush(stdout);
-    b200aln_aln_core(argv[optind], argv[optind + 1], &o, fileno(stdout), 0);
+    {
+        const char *e = getenv("B200ALN_DEVICE"); /* default: every visible GPU */
+        b200aln_aln_core(argv[optind], argv[optind + 1], &o, fileno(stdout), e ? atoi(e) : -1);
+    }
     return 0;
 }

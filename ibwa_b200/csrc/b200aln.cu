@@ -350,6 +350,7 @@ struct HostBuf {
 struct b200aln_ctx {
     int device = 0;
     int n_sm = 0;
+    bool owns_index = true; /* false for b200aln_clone()d contexts */
     FmView fm[2];
     OccBlk *d_idx[2] = {nullptr, nullptr};
     uint64_t n_blk[2] = {0, 0};
@@ -357,10 +358,10 @@ struct b200aln_ctx {
     cudaEvent_t ev[8];
     cudaEvent_t tm[2];
     /* tuning */
-    int search_blocks_per_sm = 6, width_blocks_per_sm = 8;
+    int search_blocks_per_sm = 6, width_blocks_per_sm = 5;
     uint32_t arena_cap = 4096, arena_cap_big = 0; /* 0: max_entries + 64 */
     int rec_cap = 8, rec_cap_big = 1 << 16, big_lanes = 1024;
-    int lut_k = 12;        /* levels of the path-k-mer interval table (0 = off) */
+    int lut_k = 13;        /* levels of the path-k-mer interval table (0 = off) */
     uint32_t *d_lut[2] = {nullptr, nullptr};
     int batch_max_len = 0; /* > 0: the reference batch this call is a shard of has this longest read */
     /* device buffers */
@@ -476,7 +477,7 @@ extern "C" b200aln_ctx *b200aln_open(const b200aln_bwt_view_t *bwt, const b200al
 static void build_luts(b200aln_ctx *c)
 {
     int k = c->lut_k;
-    if (k > 13) k = 13;
+    if (k > 14) k = 14; /* path word: 5 bits depth + 2 * (k - 1) bits k-mer */
     while (k > 0 && ((uint64_t)1 << (2 * k)) > 4ull * ((uint64_t)c->fm[0].seq_len + 1)) --k; /* tiny indexes */
     for (int w = 0; w < 2; ++w) {
         if (c->d_lut[w]) { CK(cudaFree(c->d_lut[w])); c->d_lut[w] = nullptr; }
@@ -495,6 +496,30 @@ static void build_luts(b200aln_ctx *c)
         c->fm[w].lut_k = k;
     }
     CK(cudaStreamSynchronize(c->st));
+}
+
+extern "C" b200aln_ctx *b200aln_clone(b200aln_ctx *p)
+{ /* a second in-flight batch on the same GPU: own stream, staging and scratch, shared index */
+    b200aln_ctx *c = new b200aln_ctx();
+    c->device = p->device;
+    c->n_sm = p->n_sm;
+    c->owns_index = false;
+    CK(cudaSetDevice(c->device));
+    for (int i = 0; i < 2; ++i) {
+        c->fm[i] = p->fm[i];
+        c->d_idx[i] = p->d_idx[i];
+        c->n_blk[i] = p->n_blk[i];
+        c->d_lut[i] = p->d_lut[i];
+    }
+    c->lut_k = p->lut_k;
+    c->search_blocks_per_sm = p->search_blocks_per_sm; c->width_blocks_per_sm = p->width_blocks_per_sm;
+    c->arena_cap = p->arena_cap; c->arena_cap_big = p->arena_cap_big;
+    c->rec_cap = p->rec_cap; c->rec_cap_big = p->rec_cap_big; c->big_lanes = p->big_lanes;
+    CK(cudaStreamCreateWithFlags(&c->st, cudaStreamNonBlocking));
+    for (int i = 0; i < 8; ++i) CK(cudaEventCreate(&c->ev[i]));
+    for (int i = 0; i < 2; ++i) CK(cudaEventCreate(&c->tm[i]));
+    memset(&c->stats, 0, sizeof c->stats);
+    return c;
 }
 
 static bool read_bwt_file(const char *fn, std::vector<uint32_t> &words, b200aln_bwt_view_t *v)
@@ -540,8 +565,10 @@ extern "C" void b200aln_close(b200aln_ctx *c)
                       &c->packed, &c->ent_big, &c->recs_big, &c->heads_wide, &c->heads_wide_big};
     for (DevBuf *b : bufs) b->release();
     c->h_in.release(); c->h_out.release(); c->h_misc.release();
-    for (int i = 0; i < 2; ++i) if (c->d_idx[i]) cudaFree(c->d_idx[i]);
-    for (int i = 0; i < 2; ++i) if (c->d_lut[i]) cudaFree(c->d_lut[i]);
+    if (c->owns_index) {
+        for (int i = 0; i < 2; ++i) if (c->d_idx[i]) cudaFree(c->d_idx[i]);
+        for (int i = 0; i < 2; ++i) if (c->d_lut[i]) cudaFree(c->d_lut[i]);
+    }
     for (int i = 0; i < 8; ++i) cudaEventDestroy(c->ev[i]);
     for (int i = 0; i < 2; ++i) cudaEventDestroy(c->tm[i]);
     cudaStreamDestroy(c->st);
@@ -558,7 +585,11 @@ extern "C" void b200aln_set_int(b200aln_ctx *c, const char *key, int64_t v)
     else if (!strcmp(key, "rec_cap_big")) c->rec_cap_big = (int)v;
     else if (!strcmp(key, "big_lanes")) c->big_lanes = (int)v;
     else if (!strcmp(key, "batch_max_len")) c->batch_max_len = (int)v;
-    else if (!strcmp(key, "lut_k")) { c->lut_k = (int)v; build_luts(c); }
+    else if (!strcmp(key, "lut_k")) {
+        if (!c->owns_index) die("b200aln_set_int", "lut_k must be set on the context that owns the index.");
+        c->lut_k = (int)v;
+        build_luts(c);
+    }
     else die("b200aln_set_int", "unknown key '%s'.", key);
 }
 

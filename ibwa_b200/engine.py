@@ -44,7 +44,7 @@ class SeqLayout(ctypes.Structure):
 
 
 EXPORTS = ["b200aln_version", "b200aln_opt_init", "b200aln_cal_maxdiff", "b200aln_device_count", "b200aln_open",
-           "b200aln_open_prefix", "b200aln_close", "b200aln_batch", "b200aln_batch_device", "b200aln_last_stats",
+           "b200aln_open_prefix", "b200aln_clone", "b200aln_close", "b200aln_batch", "b200aln_batch_device", "b200aln_last_stats",
            "b200aln_set_int", "b200aln_timer_start", "b200aln_timer_stop", "b200aln_cal_sa_reg_gap", "b200aln_seq_layout", "b200aln_aln_core", "b200aln_aln_main",
            "b200aln_sector_roofline"]
 
@@ -68,6 +68,8 @@ def load_library():
     L.b200aln_open.argtypes = [ctypes.POINTER(BwtView), ctypes.POINTER(BwtView), ctypes.c_int]
     L.b200aln_open_prefix.restype = ctypes.c_void_p
     L.b200aln_open_prefix.argtypes = [ctypes.c_char_p, ctypes.c_int]
+    L.b200aln_clone.restype = ctypes.c_void_p
+    L.b200aln_clone.argtypes = [ctypes.c_void_p]
     L.b200aln_close.argtypes = [ctypes.c_void_p]
     L.b200aln_batch.restype = ctypes.c_void_p
     L.b200aln_batch.argtypes = [ctypes.c_void_p, ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p,
@@ -113,6 +115,16 @@ class Engine:
         self._ctx = self._L.b200aln_open(ctypes.byref(v0), ctypes.byref(v1), device)
         self.device = device
         self.seq_len = bwt.seq_len
+
+    def clone(self) -> "Engine":
+        """A sibling on the same GPU sharing the device index (own stream and buffers): lets a second
+        batch be in flight from another host thread.  Close it before this engine."""
+        other = object.__new__(Engine)
+        other._L = self._L
+        other._ctx = self._L.b200aln_clone(self._ctx)
+        other.device = self.device
+        other.seq_len = self.seq_len
+        return other
 
     @classmethod
     def from_prefix(cls, prefix: str, device: int = 0) -> "Engine":

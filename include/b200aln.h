@@ -78,6 +78,12 @@ b200aln_ctx *b200aln_open(const b200aln_bwt_view_t *bwt, const b200aln_bwt_view_
 /* Convenience: bwt_restore_bwt(prefix.bwt / prefix.rbwt) + b200aln_open (bwtaln.c:184-189). */
 b200aln_ctx *b200aln_open_prefix(const char *prefix, int device);
 
+/* A sibling context on the same GPU that shares ctx's device index but has its own stream, pinned
+ * staging and scratch: two batches can then be in flight at once (one host thread per context), so the
+ * H2D / D2H copies and host work of one overlap the kernels of the other — the double buffering that
+ * replaces the reference's per-batch pthread fan-out (bwtaln.c:199-218).  Close clones before `ctx`. */
+b200aln_ctx *b200aln_clone(b200aln_ctx *ctx);
+
 /* bwt_destroy x2 (bwtaln.c:238) plus device teardown. */
 void b200aln_close(b200aln_ctx *ctx);
 
@@ -128,7 +134,7 @@ double b200aln_timer_stop(b200aln_ctx *ctx);
  *   batch_max_len  > 0: this context processes a SHARD of a reference batch whose longest read has this
  *                  length; the batch-level max_gapo clamp (bwtaln.c:89-92) is then taken from it, so that
  *                  shards on several GPUs reproduce the single-batch result.  0 = the call is the batch.
- *   lut_k          levels of the path-k-mer interval table built at open (default 12, 0 = off).
+ *   lut_k          levels of the path-k-mer interval table built at open (default 13, max 14, 0 = off).
  *   search_blocks_per_sm, width_blocks_per_sm, arena_cap, arena_cap_big, rec_cap, rec_cap_big, big_lanes:
  *                  launch geometry and per-lane capacities. */
 void b200aln_set_int(b200aln_ctx *ctx, const char *key, int64_t value);

@@ -84,6 +84,8 @@ __global__ void __launch_bounds__(128) k_width(const __grid_constant__ WidthArgs
     }
 }
 
+#define WIDE_TAG 0x40000000
+
 struct SearchArgs {
     SearchEnv env;
     int n_work;
@@ -100,7 +102,8 @@ struct SearchArgs {
     int rec_cap;
     int recs_by_work; /* slab index: work item (large pass) or read (fast pass) */
     int32_t *n_aln;
-    int32_t *over_slot; /* large pass: over_slot[r] = work item */
+    int32_t *over_slot; /* re-run passes: over_slot[r] = work item | slot_tag */
+    int32_t slot_tag;   /* 0 = middle pass, WIDE_TAG = wide pass */
     unsigned int *counter;
     unsigned int *n_over;
     int32_t *over_list;
@@ -190,7 +193,7 @@ __global__ void __launch_bounds__(128, MINB) k_search(const __grid_constant__ Se
                     } else A.n_aln[r] = -L.status; /* the large pass overflowed too: reported by the host */
                 } else {
                     A.n_aln[r] = L.n_aln;
-                    if (A.over_slot) A.over_slot[r] = (int32_t)w;
+                    if (A.over_slot) A.over_slot[r] = (int32_t)w | A.slot_tag;
                 }
                 active = false;
             }
@@ -263,14 +266,17 @@ __global__ void __launch_bounds__(256) k_scan_apply(const int32_t *in, int n, co
 }
 
 __global__ void __launch_bounds__(256) k_compact(int n, const int32_t *n_aln, const int64_t *off, const Rec *recs,
-                                                 int rec_cap, const Rec *recs_big, int rec_cap_big,
-                                                 const int32_t *over_slot, Rec *out)
+                                                 int rec_cap, const Rec *recs_mid, int rec_cap_mid,
+                                                 const Rec *recs_big, int rec_cap_big, const int32_t *over_slot,
+                                                 Rec *out)
 {
     for (int r = blockIdx.x * blockDim.x + threadIdx.x; r < n; r += gridDim.x * blockDim.x) {
         const int c = n_aln[r];
         if (c <= 0) continue;
         const int sl = over_slot[r];
-        const Rec *src = sl >= 0 ? recs_big + (size_t)sl * rec_cap_big : recs + (size_t)r * rec_cap;
+        const Rec *src = sl < 0 ? recs + (size_t)r * rec_cap
+                         : (sl & WIDE_TAG) ? recs_big + (size_t)(sl & ~WIDE_TAG) * rec_cap_big
+                                           : recs_mid + (size_t)sl * rec_cap_mid;
         Rec *dst = out + off[r];
         for (int j = 0; j < c; ++j) dst[j] = src[j];
     }
@@ -361,12 +367,14 @@ struct b200aln_ctx {
     int search_blocks_per_sm = 6, width_blocks_per_sm = 5;
     uint32_t arena_cap = 4096, arena_cap_big = 0; /* 0: max_entries + 64 */
     int rec_cap = 8, rec_cap_big = 1 << 16, big_lanes = 1024;
-    int lut_k = 13;        /* levels of the path-k-mer interval table (0 = off) */
+    uint32_t arena_cap_mid = 32768; /* middle pass: still 16-bit heads in shared memory */
+    int rec_cap_mid = 512, mid_lanes = 148 * 128;
+    int lut_k = 14;        /* levels of the path-k-mer interval table (0 = off) */
     uint32_t *d_lut[2] = {nullptr, nullptr};
     int batch_max_len = 0; /* > 0: the reference batch this call is a shard of has this longest read */
     /* device buffers */
     DevBuf lens, offs, codes, md, Q, W, n_amb, ent, recs, n_aln, over_slot, over_list, misc, off64,
-        blk_tot, packed, ent_big, recs_big, heads_wide, heads_wide_big;
+        blk_tot, packed, ent_big, recs_big, heads_wide, heads_wide_big, ent_mid, recs_mid, over_list2;
     HostBuf h_in, h_out, h_misc;
     b200aln_stats_t stats;
 };
@@ -515,6 +523,7 @@ extern "C" b200aln_ctx *b200aln_clone(b200aln_ctx *p)
     c->search_blocks_per_sm = p->search_blocks_per_sm; c->width_blocks_per_sm = p->width_blocks_per_sm;
     c->arena_cap = p->arena_cap; c->arena_cap_big = p->arena_cap_big;
     c->rec_cap = p->rec_cap; c->rec_cap_big = p->rec_cap_big; c->big_lanes = p->big_lanes;
+    c->arena_cap_mid = p->arena_cap_mid; c->rec_cap_mid = p->rec_cap_mid; c->mid_lanes = p->mid_lanes;
     CK(cudaStreamCreateWithFlags(&c->st, cudaStreamNonBlocking));
     for (int i = 0; i < 8; ++i) CK(cudaEventCreate(&c->ev[i]));
     for (int i = 0; i < 2; ++i) CK(cudaEventCreate(&c->tm[i]));
@@ -562,7 +571,8 @@ extern "C" void b200aln_close(b200aln_ctx *c)
     cudaStreamSynchronize(c->st);
     DevBuf *bufs[] = {&c->lens, &c->offs, &c->codes, &c->md, &c->Q, &c->W, &c->n_amb, &c->ent,
                       &c->recs, &c->n_aln, &c->over_slot, &c->over_list, &c->misc, &c->off64, &c->blk_tot,
-                      &c->packed, &c->ent_big, &c->recs_big, &c->heads_wide, &c->heads_wide_big};
+                      &c->packed, &c->ent_big, &c->recs_big, &c->heads_wide, &c->heads_wide_big, &c->ent_mid, &c->recs_mid,
+                      &c->over_list2};
     for (DevBuf *b : bufs) b->release();
     c->h_in.release(); c->h_out.release(); c->h_misc.release();
     if (c->owns_index) {
@@ -584,6 +594,9 @@ extern "C" void b200aln_set_int(b200aln_ctx *c, const char *key, int64_t v)
     else if (!strcmp(key, "rec_cap")) c->rec_cap = (int)v;
     else if (!strcmp(key, "rec_cap_big")) c->rec_cap_big = (int)v;
     else if (!strcmp(key, "big_lanes")) c->big_lanes = (int)v;
+    else if (!strcmp(key, "arena_cap_mid")) c->arena_cap_mid = (uint32_t)v;
+    else if (!strcmp(key, "rec_cap_mid")) c->rec_cap_mid = (int)v;
+    else if (!strcmp(key, "mid_lanes")) c->mid_lanes = (int)v;
     else if (!strcmp(key, "batch_max_len")) c->batch_max_len = (int)v;
     else if (!strcmp(key, "lut_k")) {
         if (!c->owns_index) die("b200aln_set_int", "lut_k must be set on the context that owns the index.");
@@ -611,21 +624,22 @@ extern "C" double b200aln_timer_stop(b200aln_ctx *c)
 
 extern "C" void b200aln_last_stats(const b200aln_ctx *c, b200aln_stats_t *out) { *out = c->stats; }
 
-/* misc device words: [0] work counter, [1] n_over, [2] work counter (large pass), [4..5] stat (u64 x2), [8] total (i64) */
+/* device-side counters of one batch */
 struct Misc {
-    unsigned int counter, n_over, counter_big, pad;
+    unsigned int counter, n_over, counter_big, counter_mid, n_over2, pad[3];
     unsigned long long stat[2];
     long long total;
 };
 
 /* fast pass: 16-bit heads in shared memory when the score range and the arena allow it */
-static bool fast_heads_ok(const b200aln_ctx *c, const Params &P) { return P.n_buckets <= 128 && c->arena_cap < 65535u; }
+static bool fast_heads_ok(const Params &P, uint32_t arena_cap) { return P.n_buckets <= 128 && arena_cap < 65535u; }
 
 static void launch_search_fast(b200aln_ctx *c, SearchArgs &A, int blocks)
 {
-    if (fast_heads_ok(c, A.env.P)) {
+    if (fast_heads_ok(A.env.P, A.arena_cap)) {
         const size_t smem = (size_t)A.env.P.n_buckets * 128 * sizeof(uint16_t);
-        if (c->search_blocks_per_sm > 6) k_search<HeadsStrided16, false, 8><<<blocks, 128, smem, c->st>>>(A);
+        if (c->search_blocks_per_sm > 7) k_search<HeadsStrided16, false, 8><<<blocks, 128, smem, c->st>>>(A);
+        else if (c->search_blocks_per_sm == 7) k_search<HeadsStrided16, false, 7><<<blocks, 128, smem, c->st>>>(A);
         else if (c->search_blocks_per_sm == 6) k_search<HeadsStrided16, false, 6><<<blocks, 128, smem, c->st>>>(A);
         else k_search<HeadsStrided16, false, 1><<<blocks, 128, smem, c->st>>>(A);
     } else {
@@ -697,7 +711,7 @@ static void run_batch_device(b200aln_ctx *c, int n_reads, int max_len, const int
     SA.Q = WA.Q; SA.W = WA.W; SA.strideQ = strideQ; SA.strideW = strideW;
     SA.ent = c->ent.as<StackEnt>(); SA.arena_cap = c->arena_cap;
     SA.recs = c->recs.as<Rec>(); SA.rec_cap = c->rec_cap; SA.recs_by_work = 0;
-    SA.n_aln = c->n_aln.as<int32_t>(); SA.over_slot = nullptr;
+    SA.n_aln = c->n_aln.as<int32_t>(); SA.over_slot = nullptr; SA.slot_tag = 0;
     SA.counter = &dm->counter; SA.n_over = &dm->n_over; SA.over_list = c->over_list.as<int32_t>();
     SA.stat = dm->stat;
     SA.heads_wide = nullptr; SA.heads_wide_stride = 0;
@@ -705,29 +719,59 @@ static void run_batch_device(b200aln_ctx *c, int n_reads, int max_len, const int
     ++launches;
     CK(cudaEventRecord(c->ev[3], c->st));
 
-    /* reads whose stack or record slab outgrew the fast arena: large pass */
+    /* Reads whose stack or record slab outgrew the fast pass are searched again from scratch:
+     * middle pass = the same fast kernel with a larger arena / record slab (repeat-rich reads with
+     * many hits land here), then the wide pass (arena of max_entries, 32-bit heads in memory).
+     * An aborted attempt may have edited W/Q in place (gap_shadow), so the widths are rebuilt first. */
     CK(cudaMemcpyAsync(c->h_misc.p, c->misc.p, sizeof(Misc), cudaMemcpyDeviceToHost, c->st));
     CK(cudaStreamSynchronize(c->st));
     unsigned n_over = c->h_misc.as<Misc>()->n_over;
     c->stats.overflow_reads = n_over;
-    if (n_over) {
+    const int32_t *wide_list = c->over_list.as<int32_t>();
+    unsigned n_wide = n_over;
+    if (n_over && fast_heads_ok(P, c->arena_cap_mid) &&
+        (c->arena_cap_mid > c->arena_cap || c->rec_cap_mid > c->rec_cap)) {
+        int lanes_mid = c->mid_lanes;
+        if ((unsigned)lanes_mid > ((n_over + 127u) / 128u) * 128u) lanes_mid = (int)(((n_over + 127u) / 128u) * 128u);
+        const int mblocks = (lanes_mid + 127) / 128;
+        c->ent_mid.need((size_t)mblocks * 128 * c->arena_cap_mid * sizeof(StackEnt));
+        c->recs_mid.need((size_t)n_over * c->rec_cap_mid * 16);
+        c->over_list2.need((size_t)n_over * 4);
+        WidthArgs WM = WA;
+        WM.n_reads = (int)n_over; WM.work_list = c->over_list.as<int32_t>();
+        k_width<<<wblocks, 128, 0, c->st>>>(WM);
+        CK(cudaGetLastError());
+        ++launches;
+        SearchArgs SM = SA;
+        SM.n_work = (int)n_over; SM.work_list = c->over_list.as<int32_t>();
+        SM.ent = c->ent_mid.as<StackEnt>(); SM.arena_cap = c->arena_cap_mid;
+        SM.recs = c->recs_mid.as<Rec>(); SM.rec_cap = c->rec_cap_mid; SM.recs_by_work = 1;
+        SM.over_slot = c->over_slot.as<int32_t>(); SM.slot_tag = 0;
+        SM.counter = &dm->counter_mid; SM.n_over = &dm->n_over2; SM.over_list = c->over_list2.as<int32_t>();
+        launch_search_fast(c, SM, mblocks);
+        ++launches;
+        CK(cudaMemcpyAsync(c->h_misc.p, c->misc.p, sizeof(Misc), cudaMemcpyDeviceToHost, c->st));
+        CK(cudaStreamSynchronize(c->st));
+        n_wide = c->h_misc.as<Misc>()->n_over2;
+        wide_list = c->over_list2.as<int32_t>();
+    }
+    if (n_wide) {
         uint32_t cap_big = c->arena_cap_big ? c->arena_cap_big : (uint32_t)opt->max_entries + 64u;
         int big_lanes = c->big_lanes;
-        if ((unsigned)big_lanes > ((n_over + 127u) / 128u) * 128u) big_lanes = (int)(((n_over + 127u) / 128u) * 128u);
+        if ((unsigned)big_lanes > ((n_wide + 127u) / 128u) * 128u) big_lanes = (int)(((n_wide + 127u) / 128u) * 128u);
         int bblocks = (big_lanes + 127) / 128;
         c->ent_big.need((size_t)bblocks * 128 * cap_big * sizeof(StackEnt));
-        c->recs_big.need((size_t)n_over * c->rec_cap_big * 16);
-        /* the aborted fast pass may have edited W/Q in place (gap_shadow): rebuild them first */
+        c->recs_big.need((size_t)n_wide * c->rec_cap_big * 16);
         WidthArgs WB = WA;
-        WB.n_reads = (int)n_over; WB.work_list = c->over_list.as<int32_t>();
+        WB.n_reads = (int)n_wide; WB.work_list = wide_list;
         k_width<<<wblocks, 128, 0, c->st>>>(WB);
         CK(cudaGetLastError());
         ++launches;
         SearchArgs SB = SA;
-        SB.n_work = (int)n_over; SB.work_list = c->over_list.as<int32_t>();
+        SB.n_work = (int)n_wide; SB.work_list = wide_list;
         SB.ent = c->ent_big.as<StackEnt>(); SB.arena_cap = cap_big;
         SB.recs = c->recs_big.as<Rec>(); SB.rec_cap = c->rec_cap_big; SB.recs_by_work = 1;
-        SB.over_slot = c->over_slot.as<int32_t>();
+        SB.over_slot = c->over_slot.as<int32_t>(); SB.slot_tag = WIDE_TAG;
         SB.counter = &dm->counter_big; SB.n_over = nullptr; SB.over_list = nullptr;
         launch_search_big(c, SB, bblocks);
         ++launches;
@@ -746,8 +790,9 @@ static void run_batch_device(b200aln_ctx *c, int n_reads, int max_len, const int
     const int64_t total = hm.total;
     c->packed.need((size_t)(total > 0 ? total : 1) * 16);
     k_compact<<<c->n_sm * 4, 256, 0, c->st>>>(n_reads, c->n_aln.as<int32_t>(), c->off64.as<int64_t>(),
-                                              c->recs.as<Rec>(), c->rec_cap, c->recs_big.as<Rec>(), c->rec_cap_big,
-                                              c->over_slot.as<int32_t>(), c->packed.as<Rec>());
+                                              c->recs.as<Rec>(), c->rec_cap, c->recs_mid.as<Rec>(), c->rec_cap_mid,
+                                              c->recs_big.as<Rec>(), c->rec_cap_big, c->over_slot.as<int32_t>(),
+                                              c->packed.as<Rec>());
     CK(cudaGetLastError());
     ++launches;
     CK(cudaEventRecord(c->ev[5], c->st));

@@ -134,8 +134,9 @@ double b200aln_timer_stop(b200aln_ctx *ctx);
  *   batch_max_len  > 0: this context processes a SHARD of a reference batch whose longest read has this
  *                  length; the batch-level max_gapo clamp (bwtaln.c:89-92) is then taken from it, so that
  *                  shards on several GPUs reproduce the single-batch result.  0 = the call is the batch.
- *   lut_k          levels of the path-k-mer interval table built at open (default 13, max 14, 0 = off).
- *   search_blocks_per_sm, width_blocks_per_sm, arena_cap, arena_cap_big, rec_cap, rec_cap_big, big_lanes:
+ *   lut_k          levels of the path-k-mer interval table built at open (default 14 = max, 0 = off).
+ *   search_blocks_per_sm, width_blocks_per_sm, arena_cap, arena_cap_mid, arena_cap_big, rec_cap, rec_cap_mid,
+ *   rec_cap_big, mid_lanes, big_lanes:
  *                  launch geometry and per-lane capacities. */
 void b200aln_set_int(b200aln_ctx *ctx, const char *key, int64_t value);
 

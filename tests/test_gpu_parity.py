@@ -55,6 +55,19 @@ def test_overflow_path_is_exact(tag, g1_index, golden_dir):
     assert got == open(os.path.join(golden_dir, f"g1_{tag}.sai"), "rb").read()
 
 
+@pytest.mark.parametrize("tag", ["default", "stress"])
+def test_all_three_passes_are_exact(tag, g1_index, golden_dir):
+    """Tiny fast AND middle capacities: some reads need the wide pass (32-bit heads in memory)."""
+    args, fq = CASES[tag]
+    with engine.Engine(g1_index[0], g1_index[1], 0) as e:
+        e.set("arena_cap", 64)
+        e.set("rec_cap", 1)
+        e.set("arena_cap_mid", 256)
+        e.set("rec_cap_mid", 3)
+        got = engine_sai(e, args, os.path.join(golden_dir, fq + ".fq.gz"))
+    assert got == open(os.path.join(golden_dir, f"g1_{tag}.sai"), "rb").read()
+
+
 @pytest.mark.parametrize("tag", ["default", "q20", "stress"])
 def test_cli_binary(tag, golden_dir, tmp_path):
     """The `b200aln aln` command line: same options in, same .sai bytes out (bwtaln.c:243-328)."""

@@ -690,8 +690,11 @@ struct SearchLane {
     QRec pq; /* width record of the position being worked on (prepare -> apply) */
     int pm;  /* differences still allowed for the current entry */
 
-    /* pop until something needs a lookup; returns its kind or NONE (search ended) */
-    B2_HD int prepare(const SearchEnv &E)
+    /* pop until something needs a lookup; returns its kind, or NONE when the search ended
+     * (finished is set) or when the next entry has to come from memory and allow_pop is false:
+     * the kernel lets the lanes of a warp take their memory pops in batches, so that the extra
+     * dependent load and the pop code are paid once for several lanes instead of every iteration. */
+    B2_HD int prepare(const SearchEnv &E, bool allow_pop = true)
     {
         const Params *P = &E.P;
         const bool gape_mode = P->mode & MODE_GAPE, nonstop = P->mode & MODE_NONSTOP;
@@ -700,6 +703,7 @@ struct SearchLane {
             if (!have_cur) {
                 if (n_entries == 0) { finished = true; return NONE; }
                 if (n_entries > P->max_entries) { finished = true; return NONE; }
+                if (!allow_pop) return NONE;
                 pop_mem(E);
                 if (cstate == 3) {
                     /* its members are checked one by one when they are popped; only the score
@@ -716,16 +720,16 @@ struct SearchLane {
             ++n_pops;
             if (!nonstop && cscore > best_score + P->s_mm) { finished = true; return NONE; }
             pm = max_diff - cmm - cgo - (gape_mode ? cge : 0);
-            if (pm < 0) continue;
+            if (pm < 0) { B2_DBG(8); continue; }
             if (ci > 0) {
                 pq = ld_q(Q + (size_t)ca * strideQ + (ci - 1));
-                if (pm < q_bid(pq)) continue;
+                if (pm < q_bid(pq)) { B2_DBG(9); continue; }
             }
             if (ci == 0) {
                 if (!on_hit(E)) { finished = true; return NONE; }
                 continue;
             }
-            if (pm == 0 && (cstate == ST_M || gape_mode || cge == P->max_gape)) { extending = true; return EXTEND; }
+            if (pm == 0 && (cstate == ST_M || gape_mode || cge == P->max_gape)) { B2_DBG(10); extending = true; return EXTEND; }
             return EXPAND;
         }
     }

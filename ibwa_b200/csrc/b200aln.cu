@@ -110,6 +110,7 @@ struct SearchArgs {
     unsigned long long *stat; /* [0] pops, [1] sectors */
     uint32_t *heads_wide;     /* HeadsWide32 only: per lane n_buckets heads + mask words */
     int heads_wide_stride;
+    int pop_batch; /* lanes of a warp that must wait for a memory pop before the warp takes them */
 };
 
 template <class Heads> struct HeadsFactory;
@@ -173,8 +174,14 @@ __global__ void __launch_bounds__(128, MINB) k_search(const __grid_constant__ Se
         }
         /* one search step per lane, the warp re-converged around the lookup so that all of its
          * loads are issued together */
+        const bool running = active && !L.finished;
+        const bool ready = running && (L.have_cur || L.extending);
+        const unsigned wait_mask = __ballot_sync(FULL, running && !ready);
+        const unsigned ready_mask = __ballot_sync(FULL, ready);
+        /* memory pops are taken in batches: when enough lanes wait for one, or nobody else can move */
+        const bool allow_pop = __popc(wait_mask) >= A.pop_batch || ready_mask == 0;
         int mode = L.NONE;
-        if (active && !L.finished) mode = L.prepare(A.env);
+        if (running && (ready || allow_pop)) mode = L.prepare(A.env, allow_pop);
         __syncwarp();
         uint32_t nk4[4], nl4[4], ns = 0;
         if (mode != L.NONE) children4(A.env.fm[1 - L.ca], L.cpath, L.ck, L.cl, nk4, nl4, ns);
@@ -369,6 +376,7 @@ struct b200aln_ctx {
     int rec_cap = 8, rec_cap_big = 1 << 16, big_lanes = 1024;
     uint32_t arena_cap_mid = 32768; /* middle pass: still 16-bit heads in shared memory */
     int rec_cap_mid = 512, mid_lanes = 148 * 128;
+    int pop_batch = 8;     /* memory pops are taken when this many lanes of a warp wait for one */
     int lut_k = 14;        /* levels of the path-k-mer interval table (0 = off) */
     uint32_t *d_lut[2] = {nullptr, nullptr};
     int batch_max_len = 0; /* > 0: the reference batch this call is a shard of has this longest read */
@@ -524,6 +532,7 @@ extern "C" b200aln_ctx *b200aln_clone(b200aln_ctx *p)
     c->arena_cap = p->arena_cap; c->arena_cap_big = p->arena_cap_big;
     c->rec_cap = p->rec_cap; c->rec_cap_big = p->rec_cap_big; c->big_lanes = p->big_lanes;
     c->arena_cap_mid = p->arena_cap_mid; c->rec_cap_mid = p->rec_cap_mid; c->mid_lanes = p->mid_lanes;
+    c->pop_batch = p->pop_batch;
     CK(cudaStreamCreateWithFlags(&c->st, cudaStreamNonBlocking));
     for (int i = 0; i < 8; ++i) CK(cudaEventCreate(&c->ev[i]));
     for (int i = 0; i < 2; ++i) CK(cudaEventCreate(&c->tm[i]));
@@ -594,6 +603,7 @@ extern "C" void b200aln_set_int(b200aln_ctx *c, const char *key, int64_t v)
     else if (!strcmp(key, "rec_cap")) c->rec_cap = (int)v;
     else if (!strcmp(key, "rec_cap_big")) c->rec_cap_big = (int)v;
     else if (!strcmp(key, "big_lanes")) c->big_lanes = (int)v;
+    else if (!strcmp(key, "pop_batch")) c->pop_batch = (int)v;
     else if (!strcmp(key, "arena_cap_mid")) c->arena_cap_mid = (uint32_t)v;
     else if (!strcmp(key, "rec_cap_mid")) c->rec_cap_mid = (int)v;
     else if (!strcmp(key, "mid_lanes")) c->mid_lanes = (int)v;
@@ -715,6 +725,7 @@ static void run_batch_device(b200aln_ctx *c, int n_reads, int max_len, const int
     SA.counter = &dm->counter; SA.n_over = &dm->n_over; SA.over_list = c->over_list.as<int32_t>();
     SA.stat = dm->stat;
     SA.heads_wide = nullptr; SA.heads_wide_stride = 0;
+    SA.pop_batch = c->pop_batch;
     launch_search_fast(c, SA, sblocks);
     ++launches;
     CK(cudaEventRecord(c->ev[3], c->st));

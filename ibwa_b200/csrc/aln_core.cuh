@@ -133,7 +133,8 @@ struct FmView {
 };
 
 #define B2_PATH_DEAD 31u /* depth field value of an entry that left the interval table */
-B2_HD uint64_t lut_level_off(int level) { return (((uint64_t)1 << (2 * level)) - 4u) / 3u; } /* in (k,l) pairs */
+/* first (k,l) pair of a level: (4^level - 4) / 3; (4^L - 1) / 3 is the bit pattern 0101..01 with L ones */
+B2_HD uint64_t lut_level_off(int level) { return (0x5555555555555555ull >> (64 - 2 * level)) - 1u; }
 B2_HD uint32_t path_root() { return 0u; }
 /* path of the child reached by prepending character c to a node with path p */
 B2_HD uint32_t path_ext(uint32_t p, int c, int lut_k)
@@ -448,65 +449,32 @@ struct Arena {
  *
  * HeadsStrided16: 16-bit heads at h[sc * stride] — the fast kernel points h at a
  *   shared-memory column (stride = threads per block, conflict free), the CPU
- *   harness at a plain array (stride 1).  Needs n_buckets <= 128 and arena
- *   capacity < 65535; the non-empty set lives in four registers.
- * HeadsWide32: 32-bit heads and mask words in global memory — the large-arena
- *   pass and exotic score ranges (up to 2048 buckets). */
+ *   harness at a plain array (stride 1).  Needs arena capacity < 65535 (0xffff = empty).
+ * HeadsWide32: 32-bit heads in global memory — the large-arena pass and exotic score
+ *   ranges (up to 2048 buckets).
+ * The lowest non-empty bucket is tracked by the lane like the reference does (bwtgap.c:63,73-78):
+ * lowered on push, found by scanning upwards when a pop empties its bucket. */
 struct HeadsStrided16 {
     uint16_t *h;
     int stride;
-    uint32_t m0, m1, m2, m3;
+    static B2_HD uint32_t nil() { return 0xffffu; }
     B2_HD void clear(int nb)
     {
         for (int i = 0; i < nb; ++i) h[(size_t)i * stride] = 0xffffu;
-        m0 = m1 = m2 = m3 = 0;
     }
-    B2_HD uint32_t get(int sc) const
-    {
-        uint32_t v = h[(size_t)sc * stride];
-        return v == 0xffffu ? B2_NIL : v;
-    }
+    B2_HD uint32_t get(int sc) const { return h[(size_t)sc * stride]; }
     B2_HD void set(int sc, uint32_t slot) { h[(size_t)sc * stride] = (uint16_t)slot; }
-    B2_HD void mark(int sc)
-    {
-        const uint32_t bit = 1u << (sc & 31);
-        const int wd = sc >> 5;
-        m0 |= wd == 0 ? bit : 0u; m1 |= wd == 1 ? bit : 0u; m2 |= wd == 2 ? bit : 0u; m3 |= wd == 3 ? bit : 0u;
-    }
-    B2_HD void unmark(int sc)
-    {
-        const uint32_t bit = ~(1u << (sc & 31));
-        const int wd = sc >> 5;
-        m0 &= wd == 0 ? bit : ~0u; m1 &= wd == 1 ? bit : ~0u; m2 &= wd == 2 ? bit : ~0u; m3 &= wd == 3 ? bit : ~0u;
-    }
-    B2_HD int lowest(int nb) const
-    {
-        if (m0) return ctz32(m0);
-        if (m1) return 32 + ctz32(m1);
-        if (m2) return 64 + ctz32(m2);
-        if (m3) return 96 + ctz32(m3);
-        return nb;
-    }
 };
 
 struct HeadsWide32 {
-    uint32_t *h;    /* [n_buckets] */
-    uint32_t *mask; /* [(n_buckets + 31) / 32] */
+    uint32_t *h; /* [n_buckets] */
+    static B2_HD uint32_t nil() { return B2_NIL; }
     B2_HD void clear(int nb)
     {
         for (int i = 0; i < nb; ++i) h[i] = B2_NIL;
-        for (int i = 0; i < (nb + 31) / 32; ++i) mask[i] = 0;
     }
     B2_HD uint32_t get(int sc) const { return h[sc]; }
     B2_HD void set(int sc, uint32_t slot) { h[sc] = slot; }
-    B2_HD void mark(int sc) { mask[sc >> 5] |= 1u << (sc & 31); }
-    B2_HD void unmark(int sc) { mask[sc >> 5] &= ~(1u << (sc & 31)); }
-    B2_HD int lowest(int nb) const
-    {
-        for (int wd = 0; wd < (nb + 31) / 32; ++wd)
-            if (mask[wd]) return wd * 32 + ctz32(mask[wd]);
-        return nb;
-    }
 };
 
 enum LaneStatus { LANE_OK = 0, LANE_ARENA_FULL = 1, LANE_REC_FULL = 2 };
@@ -540,6 +508,7 @@ struct SearchLane {
     /* mutable */
     Heads bk;
     uint32_t top, free_head; /* bump pointer / free list */
+    int best, n_mem;         /* lowest non-empty bucket (n_buckets when none); records in memory */
     int n_entries;           /* the reference's stack->n_entries (memory + held) */
     int max_diff, best_score, best_diff, best_cnt, n_aln;
     int status;
@@ -573,6 +542,7 @@ struct SearchLane {
         best_cnt = 0; n_aln = 0; status = LANE_OK;
         finished = false; have_cur = false; cur_held = false; extending = false;
         top = 0; free_head = B2_NIL; n_entries = 0;
+        best = P->n_buckets; n_mem = 0;
         n_pops = n_lookups = 0;
         if (n_amb > max_diff_) { finished = true; return; } /* bwtgap.c:117-122 */
         bk.clear(P->n_buckets);
@@ -599,7 +569,8 @@ struct SearchLane {
         e.w = (uint32_t)mm | (uint32_t)go << 8 | (uint32_t)ge << 16 | (uint32_t)state << 24 | (uint32_t)a << 26;
         st_ent(ar.ent + slot, e, bk.get(sc), path);
         bk.set(sc, slot);
-        bk.mark(sc);
+        best = sc < best ? sc : best;
+        ++n_mem;
         ++n_entries;
     }
 
@@ -625,20 +596,29 @@ struct SearchLane {
         e.w = (uint32_t)mm | (uint32_t)go << 8 | (uint32_t)ge << 16 | 3u << 24 | (uint32_t)a << 26;
         st_ent(ar.ent + slot, e, bk.get(sc), path);
         bk.set(sc, slot);
-        bk.mark(sc);
+        best = sc < best ? sc : best;
+        ++n_mem;
         n_entries += 1 + popc32((uint32_t)dmask);
     }
 
     B2_HD void pop_mem(const SearchEnv &E)
     {
         B2_DBG(0);
-        int b = bk.lowest(E.P.n_buckets);
+        int b = best;
         uint32_t slot = bk.get(b);
         U4 e;
         uint32_t prev;
         ld_ent(ar.ent + slot, e, prev, cpath);
         bk.set(b, prev);
-        if (prev == B2_NIL) bk.unmark(b);
+        --n_mem;
+        if (prev == Heads::nil()) { /* bucket emptied: next non-empty one upwards (bwtgap.c:73-78) */
+            if (n_mem == 0) best = E.P.n_buckets;
+            else {
+                int nb = b + 1;
+                while (bk.get(nb) == Heads::nil()) ++nb;
+                best = nb;
+            }
+        }
         if (REUSE) { ar.ent[slot].link = free_head; free_head = slot; }
         --n_entries;
         ck = e.x; cl = e.y;
@@ -775,14 +755,17 @@ struct SearchLane {
         B2_DBG(6);
         const uint32_t occ = cl - ck + 1u;
         bool allow_diff = true, allow_M = true;
-        if (i > 0) {
-            if (q_bidp(q) > m - 1) allow_diff = false;
-            else if (q_bidp(q) == m - 1 && q_bid(q) == m - 1 && q_eq(q)) allow_M = false;
-            if (q_sact(q)) {
-                int m_seed = P->max_seed_diff - cmm - cgo - (gape_mode ? cge : 0);
-                if (q_sbidp(q) > m_seed - 1) allow_diff = false;
-                else if (q_sbidp(q) == m_seed - 1 && q_sbid(q) == m_seed - 1 && q_seq(q)) allow_M = false;
-            }
+        if (i > 0) { /* bwtgap.c:205-214, written without short-circuits to keep the lanes together */
+            const int bp = q_bidp(q), bd = q_bid(q);
+            const bool d1 = bp > m - 1;
+            const bool e1 = (bp == m - 1) & (bd == m - 1) & (q_eq(q) != 0);
+            const int m_seed = P->max_seed_diff - cmm - cgo - (gape_mode ? cge : 0);
+            const int sp = q_sbidp(q), sd = q_sbid(q);
+            const bool sa = q_sact(q) != 0;
+            const bool d2 = sa & (sp > m_seed - 1);
+            const bool e2 = sa & (sp == m_seed - 1) & (sd == m_seed - 1) & (q_seq(q) != 0);
+            allow_diff = !(d1 | d2);
+            allow_M = !((!d1 & e1) | (!d2 & e2));
         }
         int gaps;
         if (P->mode & MODE_LOGGAP) {

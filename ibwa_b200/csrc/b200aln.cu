@@ -121,7 +121,6 @@ template <> struct HeadsFactory<HeadsStrided16> {
         HeadsStrided16 hd;
         hd.h = sm_heads + threadIdx.x;
         hd.stride = (int)blockDim.x;
-        hd.m0 = hd.m1 = hd.m2 = hd.m3 = 0;
         return hd;
     }
 };
@@ -130,7 +129,6 @@ template <> struct HeadsFactory<HeadsWide32> {
     {
         HeadsWide32 hd;
         hd.h = A.heads_wide + gl * (size_t)A.heads_wide_stride;
-        hd.mask = hd.h + A.env.P.n_buckets;
         return hd;
     }
 };
@@ -376,7 +374,7 @@ struct b200aln_ctx {
     int rec_cap = 8, rec_cap_big = 1 << 16, big_lanes = 1024;
     uint32_t arena_cap_mid = 32768; /* middle pass: still 16-bit heads in shared memory */
     int rec_cap_mid = 512, mid_lanes = 148 * 128;
-    int pop_batch = 8;     /* memory pops are taken when this many lanes of a warp wait for one */
+    int pop_batch = 1;     /* memory pops are taken when this many lanes of a warp wait for one */
     int lut_k = 14;        /* levels of the path-k-mer interval table (0 = off) */
     uint32_t *d_lut[2] = {nullptr, nullptr};
     int batch_max_len = 0; /* > 0: the reference batch this call is a shard of has this longest read */
@@ -642,7 +640,8 @@ struct Misc {
 };
 
 /* fast pass: 16-bit heads in shared memory when the score range and the arena allow it */
-static bool fast_heads_ok(const Params &P, uint32_t arena_cap) { return P.n_buckets <= 128 && arena_cap < 65535u; }
+/* 16-bit heads in shared memory: arena slots must fit 16 bits and n_buckets columns the shared memory */
+static bool fast_heads_ok(const Params &P, uint32_t arena_cap) { return P.n_buckets <= 160 && arena_cap < 65535u; }
 
 static void launch_search_fast(b200aln_ctx *c, SearchArgs &A, int blocks)
 {

@@ -37,14 +37,12 @@ template <> HeadsStrided16 make_heads<HeadsStrided16>(std::vector<uint32_t> &sto
     HeadsStrided16 hd;
     hd.h = reinterpret_cast<uint16_t *>(store.data());
     hd.stride = 1;
-    hd.m0 = hd.m1 = hd.m2 = hd.m3 = 0;
     return hd;
 }
 template <> HeadsWide32 make_heads<HeadsWide32>(std::vector<uint32_t> &store)
 {
     HeadsWide32 hd;
     hd.h = store.data();
-    hd.mask = store.data() + 2048;
     return hd;
 }
 

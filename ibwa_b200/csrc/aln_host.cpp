@@ -30,6 +30,8 @@
 #include "../../include/b200aln.h"
 #include "host_params.h"
 
+struct b200aln_reader;
+
 namespace {
 
 enum {
@@ -58,7 +60,7 @@ const Nt4Table g_nt4;
  * reading stops at the first truncated record. */
 class SeqReader {
   public:
-    explicit SeqReader(const char *fn) : buf_(1 << 20)
+    explicit SeqReader(const char *fn) : buf_(1 << 22)
     {
         if (strcmp(fn, "-") == 0) f_ = gzdopen(fileno(stdin), "r"); /* utils.c:56-66 */
         else f_ = gzopen(fn, "r");
@@ -68,6 +70,58 @@ class SeqReader {
 
     /* returns sequence length, -1 at end of file, -2 on a truncated quality string */
     int read_record()
+    {
+        int fast = read_record_fast();
+        if (fast != -3) return fast;
+        return read_record_exact();
+    }
+
+    /* Fast path for the ordinary 4-line FASTQ record lying whole in the buffer.  It is taken only when
+     * the exact state machine below would provably produce the same record: header '@' is the next
+     * byte, the sequence line holds only graphic characters other than '>', '+', '@', the separator
+     * line starts with '+', the quality line has exactly as many characters (all in 33..127) and is
+     * followed by a newline.  Anything else returns -3 and the exact parser runs from the same state. */
+    int read_record_fast()
+    {
+        if (last_char_ != 0) return -3;
+        refill_keep_tail();
+        const unsigned char *b = buf_.data();
+        const int e = end_;
+        int p = begin_;
+        if (p >= e || b[p] != '@') return -3;
+        const unsigned char *nl1 = (const unsigned char *)memchr(b + p + 1, '\n', (size_t)(e - p - 1));
+        if (!nl1) return -3;
+        int name_end = p + 1;
+        while (name_end < (int)(nl1 - b) && !isspace(b[name_end])) ++name_end;
+        if (name_end == p + 1) return -3; /* empty name: let the exact parser decide */
+        const int s0 = (int)(nl1 - b) + 1;
+        const unsigned char *nl2 = (const unsigned char *)memchr(b + s0, '\n', (size_t)(e - s0));
+        if (!nl2) return -3;
+        const int L = (int)(nl2 - b) - s0;
+        if (L <= 0) return -3;
+        for (int i = 0; i < L; ++i) {
+            const unsigned char ch = b[s0 + i];
+            if (ch <= 32 || ch >= 127 || ch == '>' || ch == '+' || ch == '@') return -3;
+        }
+        const int q_plus = s0 + L + 1;
+        if (q_plus >= e || b[q_plus] != '+') return -3;
+        const unsigned char *nl3 = (const unsigned char *)memchr(b + q_plus, '\n', (size_t)(e - q_plus));
+        if (!nl3) return -3;
+        const int q0 = (int)(nl3 - b) + 1;
+        if (q0 + L >= e) return -3; /* need the byte after the quality string too */
+        for (int i = 0; i < L; ++i) {
+            const unsigned char ch = b[q0 + i];
+            if (ch < 33 || ch > 127) return -3;
+        }
+        if (b[q0 + L] != '\n') return -3; /* the exact parser swallows exactly one more byte here */
+        name_.assign((const char *)b + p + 1, (size_t)(name_end - p - 1));
+        seq_.assign((const char *)b + s0, (size_t)L);
+        qual_.assign((const char *)b + q0, (size_t)L);
+        begin_ = q0 + L + 1;
+        return L;
+    }
+
+    int read_record_exact()
     {
         int c;
         if (last_char_ == 0) {
@@ -101,6 +155,19 @@ class SeqReader {
     const std::string &name() const { return name_; }
 
   private:
+    /* keep at least one large record's worth of bytes contiguous for the fast path */
+    void refill_keep_tail()
+    {
+        if (is_eof_ || end_ - begin_ >= (1 << 16)) return;
+        const int tail = end_ - begin_;
+        if (tail > 0 && begin_ > 0) memmove(buf_.data(), buf_.data() + begin_, (size_t)tail);
+        begin_ = 0;
+        end_ = tail;
+        const int want = (int)buf_.size() - end_;
+        const int got = gzread(f_, buf_.data() + end_, (unsigned)want);
+        if (got < want) is_eof_ = true;
+        if (got > 0) end_ += got;
+    }
     int getc()
     {
         if (is_eof_ && begin_ >= end_) return -1;
@@ -195,7 +262,9 @@ int next_batch(SeqReader &rd, int n_needed, int mode, int trim_qual, PackedBatch
         }
         b.offs.push_back((int64_t)b.codes.size());
         b.lens.push_back(len);
-        for (int i = 0; i < full; ++i) b.codes.push_back(g_nt4.t[(unsigned char)s[i]]);
+        const size_t at = b.codes.size();
+        b.codes.resize(at + (size_t)full);
+        for (int i = 0; i < full; ++i) b.codes[at + (size_t)i] = g_nt4.t[(unsigned char)s[i]];
         if ((int)b.lens.size() == n_needed) break;
     }
     if (!b.lens.empty() && trim_qual >= 1)
@@ -234,6 +303,27 @@ struct RefSeq {
 static_assert(sizeof(RefSeq) == 176, "bwa_seq_t is 176 bytes on LP64 (bwtaln.h:72-104)");
 
 } // namespace
+
+struct b200aln_reader {
+    SeqReader rd;
+    PackedBatch batch;
+    explicit b200aln_reader(const char *fn) : rd(fn) {}
+};
+
+extern "C" b200aln_reader *b200aln_reader_open(const char *fn) { return new b200aln_reader(fn); }
+
+extern "C" int b200aln_reader_next(b200aln_reader *r, int n_needed, int mode, int trim_qual, const int32_t **lens,
+                                   const int64_t **offs, const uint8_t **codes, int64_t *codes_bytes)
+{
+    const int n = next_batch(r->rd, n_needed, mode, trim_qual, r->batch);
+    *lens = r->batch.lens.data();
+    *offs = r->batch.offs.data();
+    *codes = r->batch.codes.data();
+    *codes_bytes = (int64_t)r->batch.codes.size();
+    return n;
+}
+
+extern "C" void b200aln_reader_close(b200aln_reader *r) { delete r; }
 
 extern "C" void b200aln_seq_layout(b200aln_seq_layout_t *o)
 {

@@ -45,7 +45,7 @@ class SeqLayout(ctypes.Structure):
 
 EXPORTS = ["b200aln_version", "b200aln_opt_init", "b200aln_cal_maxdiff", "b200aln_device_count", "b200aln_open",
            "b200aln_open_prefix", "b200aln_clone", "b200aln_close", "b200aln_batch", "b200aln_batch_device", "b200aln_last_stats",
-           "b200aln_set_int", "b200aln_timer_start", "b200aln_timer_stop", "b200aln_cal_sa_reg_gap", "b200aln_seq_layout", "b200aln_aln_core", "b200aln_aln_main",
+           "b200aln_set_int", "b200aln_timer_start", "b200aln_timer_stop", "b200aln_cal_sa_reg_gap", "b200aln_seq_layout", "b200aln_aln_core", "b200aln_aln_main", "b200aln_reader_open", "b200aln_reader_next", "b200aln_reader_close",
            "b200aln_sector_roofline"]
 
 _lib = None
@@ -88,6 +88,13 @@ def load_library():
     L.b200aln_sector_roofline.restype = ctypes.c_double
     L.b200aln_sector_roofline.argtypes = [ctypes.c_void_p, ctypes.c_uint64, ctypes.c_int]
     L.b200aln_seq_layout.argtypes = [ctypes.POINTER(SeqLayout)]
+    L.b200aln_reader_open.restype = ctypes.c_void_p
+    L.b200aln_reader_open.argtypes = [ctypes.c_char_p]
+    L.b200aln_reader_next.restype = ctypes.c_int
+    L.b200aln_reader_next.argtypes = [ctypes.c_void_p, ctypes.c_int, ctypes.c_int, ctypes.c_int,
+                                      ctypes.POINTER(ctypes.c_void_p), ctypes.POINTER(ctypes.c_void_p),
+                                      ctypes.POINTER(ctypes.c_void_p), ctypes.POINTER(ctypes.c_int64)]
+    L.b200aln_reader_close.argtypes = [ctypes.c_void_p]
     _lib = L
     return L
 
@@ -192,6 +199,26 @@ class Engine:
 
     def sector_roofline(self, n_loads: int = 1 << 28, repeats: int = 3) -> float:
         return self._L.b200aln_sector_roofline(self._ctx, n_loads, repeats)
+
+
+def read_batches_native(path: str, mode: int, trim_qual: int, n_needed: int = 0x40000):
+    """bwa_read_seq through the native reader (b200aln_reader_*): yields (lens, offs, codes) numpy copies."""
+    L = load_library()
+    r = L.b200aln_reader_open(path.encode())
+    try:
+        while True:
+            pl, po, pc, nb = ctypes.c_void_p(), ctypes.c_void_p(), ctypes.c_void_p(), ctypes.c_int64()
+            n = L.b200aln_reader_next(r, n_needed, mode, trim_qual, ctypes.byref(pl), ctypes.byref(po),
+                                      ctypes.byref(pc), ctypes.byref(nb))
+            if n == 0:
+                break
+            lens = np.frombuffer((ctypes.c_int32 * n).from_address(pl.value), dtype=np.int32).copy()
+            offs = np.frombuffer((ctypes.c_int64 * n).from_address(po.value), dtype=np.int64).copy()
+            codes = np.frombuffer((ctypes.c_uint8 * nb.value).from_address(pc.value), dtype=np.uint8).copy() \
+                if nb.value else np.empty(0, np.uint8)
+            yield lens, offs, codes
+    finally:
+        L.b200aln_reader_close(r)
 
 
 def bwa_aln_core(prefix: str, fn_fa: str, opt: GapOpt, out_path: str, device: int = 0) -> int:

@@ -168,6 +168,20 @@ void b200aln_seq_layout(b200aln_seq_layout_t *out);
  */
 int64_t b200aln_aln_core(const char *prefix, const char *fn_fa, const b200aln_opt_t *opt, int out_fd, int device);
 
+/*
+ * Replaces bwa_seq_open / bwa_read_seq / bwa_seq_close (bwaseqio.c:33-52,145-208) for FASTA / FASTQ input,
+ * plain or gzip ("-" = stdin), with the reference parser's behaviour (kseq.h:150-194): multi-line records,
+ * name = first token, only graphic characters enter the sequence, reading stops at the first truncated
+ * record; -q trimming (bwaseqio.c:74-87), -B barcode strip and -I quality offset applied like the reference.
+ * b200aln_reader_next returns the number of reads (0 at the end) and views, valid until the next call, of
+ * the packed batch that b200aln_batch takes: lens (after trimming), offs and nt4 codes (full reads).
+ */
+typedef struct b200aln_reader b200aln_reader;
+b200aln_reader *b200aln_reader_open(const char *fn);
+int b200aln_reader_next(b200aln_reader *r, int n_needed, int mode, int trim_qual, const int32_t **lens,
+                        const int64_t **offs, const uint8_t **codes, int64_t *codes_bytes);
+void b200aln_reader_close(b200aln_reader *r);
+
 /* Replaces bwa_aln (bwtaln.c:243-328): same getopt string and semantics. */
 int b200aln_aln_main(int argc, char *argv[]);
 

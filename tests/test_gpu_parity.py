@@ -160,3 +160,85 @@ def test_reference_binary_on_box(rand_index, tmp_path):
     engine.bwa_aln_core(prefix, fq, gap_init_opt(), out, 0)
     a, b = open(ref_out, "rb").read(), open(out, "rb").read()
     assert a[:52] == b[:52] and a[56:] == b[56:]      # byte 52..55 = n_threads
+
+
+def _ref_index(tmp_path, genome, name, contig_len=None):
+    """Index a synthetic genome with the unmodified reference (`ibwa index -a is`)."""
+    fa = str(tmp_path / f"{name}.fa")
+    synth.write_fasta(fa, genome, contig_len=contig_len)
+    pyoracle.run_ref(["index", "-a", "is", fa])
+    return fa
+
+
+def test_paired_end_and_downstream_sam(tmp_path):
+    """BASELINE config 4 at reduced size: aln on both mates, .sai identity, and equality of the SAM that
+    the UNCHANGED reference `sampe -R` / `samse` produce from the engine's .sai and from its own."""
+    if not pyoracle.have_ref():
+        pytest.skip("oracle/_ref/ibwa not present")
+    g = synth.random_genome(300_000, 20260104)
+    fa = _ref_index(tmp_path, g, "pe")
+    rng = np.random.default_rng(4)
+    n, L = 3000, 100
+    starts = rng.integers(0, len(g) - 700, size=n)
+    isz = np.clip(rng.normal(400, 40, size=n).astype(int), 220, 600)
+    r1 = np.stack([g[s:s + L] for s in starts]).copy()
+    r2 = np.stack([synth.revcomp(g[s + i - L:s + i]) for s, i in zip(starts, isz)]).copy()
+    for r in (r1, r2):
+        sub = rng.random(r.shape) < 0.01
+        r[sub] = (r[sub] + rng.integers(1, 4, size=int(sub.sum()))) & 3
+    names = [f"p{i}" for i in range(n)]
+    fq1, fq2 = str(tmp_path / "r1.fq"), str(tmp_path / "r2.fq")
+    synth.write_fastq(fq1, list(r1), names=[x + "/1" for x in names])
+    synth.write_fastq(fq2, list(r2), names=[x + "/2" for x in names])
+    sais = {}
+    for tag, fq in (("1", fq1), ("2", fq2)):
+        ref_sai, gpu_sai = str(tmp_path / f"ref{tag}.sai"), str(tmp_path / f"gpu{tag}.sai")
+        pyoracle.run_ref(["aln", fa, fq], stdout_path=ref_sai)
+        engine.bwa_aln_core(fa, fq, gap_init_opt(), gpu_sai, 0)
+        assert open(ref_sai, "rb").read() == open(gpu_sai, "rb").read()
+        sais[tag] = (ref_sai, gpu_sai)
+    ref_sam, gpu_sam = str(tmp_path / "ref.sam"), str(tmp_path / "gpu.sam")
+    pyoracle.run_ref(["sampe", "-R", fa, sais["1"][0], sais["2"][0], fq1, fq2], stdout_path=ref_sam)
+    pyoracle.run_ref(["sampe", "-R", fa, sais["1"][1], sais["2"][1], fq1, fq2], stdout_path=gpu_sam)
+    a, b = open(ref_sam, "rb").read(), open(gpu_sam, "rb").read()
+    assert a == b and a.count(b"\n") > 2 * n
+    se_ref, se_gpu = str(tmp_path / "se_ref.sam"), str(tmp_path / "se_gpu.sam")
+    pyoracle.run_ref(["samse", fa, sais["1"][0], fq1], stdout_path=se_ref)
+    pyoracle.run_ref(["samse", fa, sais["1"][1], fq1], stdout_path=se_gpu)
+    assert open(se_ref, "rb").read() == open(se_gpu, "rb").read()
+
+
+def test_multi_contig_alt_index(tmp_path):
+    """BASELINE config 5 at reduced size: aln against a many-contig index (primary + 200 alt contigs cut from
+    it with SNPs / indels).  The concatenated-contig BWT is consumed like any other; .sai must be identical."""
+    if not pyoracle.have_ref():
+        pytest.skip("oracle/_ref/ibwa not present")
+    rng = np.random.default_rng(5)
+    pri = synth.random_genome(400_000, 20260105)
+    alts = []
+    for j in range(200):
+        s = int(rng.integers(0, len(pri) - 2100))
+        a = pri[s:s + 2000].copy()
+        snp = np.arange(150, 2000, 300)
+        a[snp] = (a[snp] + 1) & 3
+        a = np.concatenate([a[:1000], rng.integers(0, 4, size=5, dtype=np.uint8), a[1000:]]) if j % 2 == 0 \
+            else np.concatenate([a[:1000], a[1007:]])
+        alts.append(a)
+    genome = np.concatenate([pri] + alts)
+    fa = str(tmp_path / "alt.fa")
+    with open(fa, "wb") as f:      # contigs of different lengths
+        nt = np.frombuffer(b"ACGT", dtype=np.uint8)
+        f.write(b">chr1\n" + nt[pri].tobytes() + b"\n")
+        for j, a in enumerate(alts):
+            f.write(b">alt%d\n" % j + nt[a].tobytes() + b"\n")
+    pyoracle.run_ref(["index", "-a", "is", fa])
+    reads = synth.simulate_reads_fast(genome, 6000, 100, 20260105)
+    fq = str(tmp_path / "r.fq")
+    synth.write_fastq(fq, list(reads))
+    ref_sai, gpu_sai = str(tmp_path / "ref.sai"), str(tmp_path / "gpu.sai")
+    pyoracle.run_ref(["aln", "-t", "3", fa, fq], stdout_path=ref_sai)
+    engine.bwa_aln_core(fa, fq, gap_init_opt(), gpu_sai, 0)
+    a, b = open(ref_sai, "rb").read(), open(gpu_sai, "rb").read()
+    assert a[:52] == b[:52] and a[56:] == b[56:]
+    _, n_aln, _ = sai.read_sai(gpu_sai)
+    assert (n_aln >= 2).mean() > 0.05          # reads from duplicated (alt) sequence have several records

@@ -20,6 +20,7 @@
 #include <unistd.h>
 #include <zlib.h>
 
+#include <algorithm>
 #include <deque>
 #include <future>
 #include <memory>
@@ -272,6 +273,99 @@ int next_batch(SeqReader &rd, int n_needed, int mode, int trim_qual, PackedBatch
     return (int)b.lens.size();
 }
 
+/* BAM input (bwa_bam_open / bwa_read_bam, bwaseqio.c:21-31,89-141; record layout bamlite.c:76-104).
+ * BGZF blocks are gzip members, so zlib's gzread delivers the plain BAM stream like bamlite does. */
+class BamReader {
+  public:
+    BamReader(const char *fn, int which) : which_(which ? which : 7)
+    {
+        f_ = strcmp(fn, "-") == 0 ? gzdopen(fileno(stdin), "r") : gzopen(fn, "r");
+        if (!f_) b2host::fatal("b200aln_aln_core", (std::string("fail to open file '") + fn + "'.").c_str());
+        gzbuffer(f_, 1 << 20);
+        char magic[4];
+        int32_t l_text = 0, n_ref = 0;
+        if (gzread(f_, magic, 4) != 4 || memcmp(magic, "BAM\001", 4) != 0)
+            b2host::fatal("bam_header_read", "invalid BAM binary header (this is not a BAM file).");
+        rd(&l_text, 4);
+        skip(l_text);
+        rd(&n_ref, 4);
+        for (int i = 0; i < n_ref; ++i) {
+            int32_t l_name = 0, l_ref;
+            rd(&l_name, 4);
+            skip(l_name);
+            rd(&l_ref, 4);
+        }
+    }
+    ~BamReader() { if (f_) gzclose(f_); }
+
+    /* bwa_read_bam: up to n_needed reads into the packed form */
+    int next_batch(int n_needed, int trim_qual, PackedBatch &b)
+    {
+        static const uint8_t nt16_nt4[16] = {4, 0, 1, 4, 2, 4, 4, 4, 3, 4, 4, 4, 4, 4, 4, 4}; /* bwaseqio.c:11 */
+        b.clear();
+        for (;;) {
+            int32_t block_len;
+            if (gzread(f_, &block_len, 4) != 4) break;
+            uint32_t x[8];
+            if (gzread(f_, x, 32) != 32) break;
+            const int data_len = block_len - 32;
+            data_.resize((size_t)(data_len > 0 ? data_len : 0));
+            if (data_len > 0 && gzread(f_, data_.data(), (unsigned)data_len) != data_len) break;
+            const uint32_t flag = x[3] >> 16, n_cigar = x[3] & 0xffff, l_qname = x[2] & 0xff;
+            const int l = (int)x[4];
+            bool go = false;
+            if ((which_ & 1) && (flag & 64)) go = true;
+            if ((which_ & 2) && (flag & 128)) go = true;
+            if ((which_ & 4) && !(flag & 64) && !(flag & 128)) go = true;
+            if (!go) continue;
+            const uint8_t *sq = data_.data() + n_cigar * 4 + l_qname, *ql = sq + ((l + 1) >> 1);
+            seq_.resize((size_t)l);
+            qual_.resize((size_t)l);
+            for (int i = 0; i < l; ++i) {
+                seq_[i] = nt16_nt4[sq[i / 2] >> 4 * (1 - i % 2) & 0xf];
+                qual_[i] = (uint8_t)(ql[i] + 33 < 126 ? ql[i] + 33 : 126);
+            }
+            if (flag & 16) { /* reverse strand: back to sequencing orientation (bwaseqio.c:123-126) */
+                for (int i = 0; i < l / 2; ++i) {
+                    uint8_t t1 = seq_[l - 1 - i], t2 = seq_[i];
+                    seq_[i] = t1 < 4 ? (uint8_t)(3 - t1) : t1;
+                    seq_[l - 1 - i] = t2 < 4 ? (uint8_t)(3 - t2) : t2;
+                    std::swap(qual_[i], qual_[l - 1 - i]);
+                }
+                if (l & 1) seq_[l / 2] = seq_[l / 2] < 4 ? (uint8_t)(3 - seq_[l / 2]) : seq_[l / 2];
+            }
+            int len = l;
+            b.n_tot += l;
+            if (trim_qual >= 1) {
+                len = trim_len(trim_qual, l, (const char *)qual_.data());
+                b.n_trimmed += l - len;
+            }
+            b.offs.push_back((int64_t)b.codes.size());
+            b.lens.push_back(len);
+            b.codes.insert(b.codes.end(), seq_.begin(), seq_.end());
+            if ((int)b.lens.size() == n_needed) break;
+        }
+        if (!b.lens.empty() && trim_qual >= 1)
+            fprintf(stderr, "[bwa_read_seq] %.1f%% bases are trimmed.\n", 100.0f * b.n_trimmed / b.n_tot);
+        return (int)b.lens.size();
+    }
+
+  private:
+    void rd(void *p, int n) { if (gzread(f_, p, (unsigned)n) != n) b2host::fatal("bam_header_read", "truncated BAM header."); }
+    void skip(int n)
+    {
+        char tmp[4096];
+        while (n > 0) {
+            int k = n < 4096 ? n : 4096;
+            rd(tmp, k);
+            n -= k;
+        }
+    }
+    gzFile f_ = nullptr;
+    int which_;
+    std::vector<uint8_t> data_, seq_, qual_;
+};
+
 /* mirror of the reference's bwa_seq_t (bwtaln.h:72-104) for the batch seam */
 struct RefAln1 { uint32_t packed, k, l; int32_t score; };
 struct RefSeq {
@@ -304,18 +398,40 @@ static_assert(sizeof(RefSeq) == 176, "bwa_seq_t is 176 bytes on LP64 (bwtaln.h:7
 
 } // namespace
 
+/* bwa_open_reads (bwtaln.c:159-171): FASTA/FASTQ or, with BWA_MODE_BAM, BAM filtered by -0/-1/-2 */
 struct b200aln_reader {
-    SeqReader rd;
+    std::unique_ptr<SeqReader> fq;
+    std::unique_ptr<BamReader> bam;
     PackedBatch batch;
-    explicit b200aln_reader(const char *fn) : rd(fn) {}
+    b200aln_reader(const char *fn, int mode)
+    {
+        if (mode & BWA_MODE_BAM) {
+            int which = 0;
+            if (mode & BWA_MODE_BAM_SE) which |= 4;
+            if (mode & BWA_MODE_BAM_READ1) which |= 1;
+            if (mode & BWA_MODE_BAM_READ2) which |= 2;
+            bam.reset(new BamReader(fn, which));
+        } else fq.reset(new SeqReader(fn));
+    }
+    int next(int n_needed, int mode, int trim_qual, PackedBatch &b)
+    {
+        if (bam) {
+            if ((mode >> 24 & 0xff) > 15) {
+                fprintf(stderr, "[bwa_read_seq] the maximum barcode length is 15.\n");
+                return 0;
+            }
+            return bam->next_batch(n_needed, trim_qual, b);
+        }
+        return next_batch(*fq, n_needed, mode, trim_qual, b);
+    }
 };
 
-extern "C" b200aln_reader *b200aln_reader_open(const char *fn) { return new b200aln_reader(fn); }
+extern "C" b200aln_reader *b200aln_reader_open(const char *fn, int mode) { return new b200aln_reader(fn, mode); }
 
 extern "C" int b200aln_reader_next(b200aln_reader *r, int n_needed, int mode, int trim_qual, const int32_t **lens,
                                    const int64_t **offs, const uint8_t **codes, int64_t *codes_bytes)
 {
-    const int n = next_batch(r->rd, n_needed, mode, trim_qual, r->batch);
+    const int n = r->next(n_needed, mode, trim_qual, r->batch);
     *lens = r->batch.lens.data();
     *offs = r->batch.offs.data();
     *codes = r->batch.codes.data();
@@ -420,9 +536,7 @@ BatchResult process_batch(const std::vector<b200aln_ctx *> &ctxs, const PackedBa
 extern "C" int64_t b200aln_aln_core(const char *prefix, const char *fn_fa, const b200aln_opt_t *opt, int out_fd,
                                     int device)
 {
-    if (opt->mode & BWA_MODE_BAM)
-        b2host::fatal("b200aln_aln_core", "BAM input (-b) is not implemented in this engine; convert to FASTQ.");
-    SeqReader rd(fn_fa);
+    b200aln_reader rd(fn_fa, opt->mode);
     /* devices: one, or all visible; per device two contexts (index shared) so that two batches are in
      * flight: the copies and host work of one overlap the kernels of the other */
     std::vector<int> devs;
@@ -462,7 +576,7 @@ extern "C" int64_t b200aln_aln_core(const char *prefix, const char *fn_fa, const
     int seq = 0;
     for (;;) {
         auto b = std::make_shared<PackedBatch>();
-        const int n = next_batch(rd, 0x40000, opt->mode, opt->trim_qual, *b);
+        const int n = rd.next(0x40000, opt->mode, opt->trim_qual, *b);
         if (n == 0) break;
         tot_seqs += n;
         const std::vector<b200aln_ctx *> *ctxs = &slot_ctx[seq & 1];
@@ -550,7 +664,10 @@ extern "C" int b200aln_aln_main(int argc, char *argv[])
         fprintf(stderr, "         -L        log-scaled gap penalty for long deletions\n");
         fprintf(stderr, "         -N        non-iterative mode: search for all n-difference hits (slooow)\n");
         fprintf(stderr, "         -I        the input is in the Illumina 1.3+ FASTQ-like format\n");
-        fprintf(stderr, "         -b        the input read file is in the BAM format (not implemented)\n\n");
+        fprintf(stderr, "         -b        the input read file is in the BAM format\n");
+        fprintf(stderr, "         -0        use single-end reads only (effective with -b)\n");
+        fprintf(stderr, "         -1        use the 1st read in a pair (effective with -b)\n");
+        fprintf(stderr, "         -2        use the 2nd read in a pair (effective with -b)\n\n");
         return 1;
     }
     if (o.fnr > 0.0f) { /* bwtaln.c:317-324 */

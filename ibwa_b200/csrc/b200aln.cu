@@ -675,7 +675,7 @@ static void run_batch_device(b200aln_ctx *c, int n_reads, int max_len, const int
                              const Params &P, int64_t *total_out)
 {
     uint64_t launches = 0;
-    const int strideQ = round_up8(max_len), strideW = round_up8(max_len + 1); /* 32-byte aligned rows */
+    const int strideQ = round_up8(max_len > 0 ? max_len : 1), strideW = round_up8(max_len + 1); /* 32-byte aligned rows */
     const int wblocks = c->n_sm * c->width_blocks_per_sm;
     const int sblocks = c->n_sm * c->search_blocks_per_sm;
     const size_t lanes = (size_t)sblocks * 128;
@@ -848,7 +848,7 @@ extern "C" const b200aln_rec_t *b200aln_batch(b200aln_ctx *c, int n_reads, const
     int max_len = 0;
     int64_t end = 0;
     for (int r = 0; r < n_reads; ++r) {
-        if (lens[r] < 1) die("b200aln_batch", "read %d has length %d; the reference never emits empty reads (bwaseqio.c:161).", r, lens[r]);
+        if (lens[r] < 0) die("b200aln_batch", "read %d has negative length %d.", r, lens[r]);
         if (lens[r] > max_len) max_len = lens[r];
         if (offs[r] + lens[r] > end) end = offs[r] + lens[r];
     }

@@ -89,7 +89,7 @@ def load_library():
     L.b200aln_sector_roofline.argtypes = [ctypes.c_void_p, ctypes.c_uint64, ctypes.c_int]
     L.b200aln_seq_layout.argtypes = [ctypes.POINTER(SeqLayout)]
     L.b200aln_reader_open.restype = ctypes.c_void_p
-    L.b200aln_reader_open.argtypes = [ctypes.c_char_p]
+    L.b200aln_reader_open.argtypes = [ctypes.c_char_p, ctypes.c_int]
     L.b200aln_reader_next.restype = ctypes.c_int
     L.b200aln_reader_next.argtypes = [ctypes.c_void_p, ctypes.c_int, ctypes.c_int, ctypes.c_int,
                                       ctypes.POINTER(ctypes.c_void_p), ctypes.POINTER(ctypes.c_void_p),
@@ -204,7 +204,7 @@ class Engine:
 def read_batches_native(path: str, mode: int, trim_qual: int, n_needed: int = 0x40000):
     """bwa_read_seq through the native reader (b200aln_reader_*): yields (lens, offs, codes) numpy copies."""
     L = load_library()
-    r = L.b200aln_reader_open(path.encode())
+    r = L.b200aln_reader_open(path.encode(), mode)
     try:
         while True:
             pl, po, pc, nb = ctypes.c_void_p(), ctypes.c_void_p(), ctypes.c_void_p(), ctypes.c_int64()

@@ -169,7 +169,8 @@ void b200aln_seq_layout(b200aln_seq_layout_t *out);
 int64_t b200aln_aln_core(const char *prefix, const char *fn_fa, const b200aln_opt_t *opt, int out_fd, int device);
 
 /*
- * Replaces bwa_seq_open / bwa_read_seq / bwa_seq_close (bwaseqio.c:33-52,145-208) for FASTA / FASTQ input,
+ * Replaces bwa_open_reads / bwa_read_seq / bwa_seq_close (bwtaln.c:159-171, bwaseqio.c:21-52,89-208): BAM with
+ * -b (filtered by -0/-1/-2, bwaseqio.c:89-141) or FASTA / FASTQ input,
  * plain or gzip ("-" = stdin), with the reference parser's behaviour (kseq.h:150-194): multi-line records,
  * name = first token, only graphic characters enter the sequence, reading stops at the first truncated
  * record; -q trimming (bwaseqio.c:74-87), -B barcode strip and -I quality offset applied like the reference.
@@ -177,7 +178,7 @@ int64_t b200aln_aln_core(const char *prefix, const char *fn_fa, const b200aln_op
  * the packed batch that b200aln_batch takes: lens (after trimming), offs and nt4 codes (full reads).
  */
 typedef struct b200aln_reader b200aln_reader;
-b200aln_reader *b200aln_reader_open(const char *fn);
+b200aln_reader *b200aln_reader_open(const char *fn, int mode); /* mode & BWA_MODE_BAM (0x20): BAM input, -0/-1/-2 bits */
 int b200aln_reader_next(b200aln_reader *r, int n_needed, int mode, int trim_qual, const int32_t **lens,
                         const int64_t **offs, const uint8_t **codes, int64_t *codes_bytes);
 void b200aln_reader_close(b200aln_reader *r);

@@ -242,3 +242,24 @@ def test_multi_contig_alt_index(tmp_path):
     assert a[:52] == b[:52] and a[56:] == b[56:]
     _, n_aln, _ = sai.read_sai(gpu_sai)
     assert (n_aln >= 2).mean() > 0.05          # reads from duplicated (alt) sequence have several records
+
+
+def test_cli_bam_input(tmp_path, golden_dir):
+    """`b200aln aln -b -1 ...` on a BAM file against the reference binary (bwaseqio.c:89-141)."""
+    if not pyoracle.have_ref():
+        pytest.skip("oracle/_ref/ibwa not present")
+    import gzip as gz
+    from test_bam import make_bam
+    txt = gz.open(os.path.join(golden_dir, "g1.fa.gz")).read().split(b"\n", 1)[1].replace(b"\n", b"")
+    genome = seqio.NT4[np.frombuffer(txt, dtype=np.uint8)]
+    bam = str(tmp_path / "in.bam")
+    make_bam(bam, genome, np.random.default_rng(11))
+    prefix = str(tmp_path / "g1")
+    os.symlink(os.path.join(golden_dir, "g1.bwt"), prefix + ".bwt")
+    os.symlink(os.path.join(golden_dir, "g1.rbwt"), prefix + ".rbwt")
+    exe = os.path.join(ROOT, "ibwa_b200", "b200aln")
+    for flags in (["-b"], ["-b", "-1", "-q", "15"]):
+        ref_out, out = str(tmp_path / "ref.sai"), str(tmp_path / "gpu.sai")
+        pyoracle.run_ref(["aln"] + flags + [prefix, bam], stdout_path=ref_out)
+        subprocess.check_call([exe, "aln"] + flags + ["-f", out, prefix, bam], stderr=subprocess.DEVNULL)
+        assert open(out, "rb").read() == open(ref_out, "rb").read()

@@ -95,6 +95,52 @@ def synth_reads_torch(text, n_reads: int, length: int, seed: int):
     return out
 
 
+def synth_stress_reads_torch(text, n_reads: int, length: int, seed: int):
+    """SURVEY.md §8d stress read model (config 3) on the GPU: per base 2 % substitutions, deletion-open
+    0.001 and insertion-open 0.001 with geometric extension p = 0.3; 50 % reverse-complemented."""
+    import torch
+    dev = text.device
+    g = torch.Generator(device=dev)
+    g.manual_seed(seed)
+    n = text.numel()
+    out = torch.zeros((n_reads, length), dtype=torch.uint8, device=dev)
+    j = torch.randint(0, n - 2 * length - 64, (n_reads,), device=dev, generator=g)      # source pointer
+    p = torch.zeros(n_reads, dtype=torch.int64, device=dev)                             # bases emitted
+    ins_left = torch.zeros(n_reads, dtype=torch.int64, device=dev)
+    rows = torch.arange(n_reads, device=dev)
+    log03 = float(np.log(0.3))
+    for _ in range(length * 2 + 64):
+        active = p < length
+        if not bool(active.any()):
+            break
+        u = torch.rand(n_reads, device=dev, generator=g)
+        geo = torch.floor(torch.log(torch.rand(n_reads, device=dev, generator=g).clamp_min(1e-12)) / log03).long()
+        inserting = ins_left > 0
+        is_del = active & ~inserting & (u < 0.001)
+        is_ins = active & ~inserting & (u >= 0.001) & (u < 0.002)
+        emit_src = active & ~inserting & (u >= 0.002)
+        j = j + torch.where(is_del, 1 + geo, torch.zeros_like(geo))
+        ins_left = torch.where(is_ins, 1 + geo, ins_left)
+        inserting = ins_left > 0
+        base = text[j.clamp_max(n - 1)]
+        sub = torch.rand(n_reads, device=dev, generator=g) < 0.02
+        inc = torch.randint(1, 4, (n_reads,), dtype=torch.uint8, device=dev, generator=g)
+        base = torch.where(sub, (base + inc) & 3, base)
+        rnd = torch.randint(0, 4, (n_reads,), dtype=torch.uint8, device=dev, generator=g)
+        emit_ins = active & inserting
+        val = torch.where(emit_ins, rnd, base)
+        do = emit_src | emit_ins
+        idx = p.clamp_max(length - 1)
+        cur = out[rows, idx]
+        out[rows, idx] = torch.where(do, val, cur)
+        p = p + do.long()
+        j = j + emit_src.long()
+        ins_left = ins_left - emit_ins.long()
+    rc = torch.rand(n_reads, device=dev, generator=g) < 0.5
+    rcv = 3 - torch.flip(out, dims=[1])
+    return torch.where(rc[:, None], rcv, out)
+
+
 def cache_dir(genome_bp: int, seed: int) -> str:
     return os.path.join(CACHE_ROOT, f"g{genome_bp}_s{seed}")
 
@@ -190,7 +236,7 @@ class ClockSampler(threading.Thread):
 # ------------------------------------------------------ reference (CPU) ------
 
 def time_reference(prefix: str, reads: np.ndarray, threads: int, work_dir: str, target_s: float = 15.0,
-                   max_reads: int = 2_000_000):
+                   max_reads: int = 2_000_000, aln_args=()):
     """Times `ibwa aln -t threads` on a bounded sample; returns dict(reads/s, sample, sai path, ...)."""
     os.makedirs(work_dir, exist_ok=True)
     empty = os.path.join(work_dir, "empty.fq")
@@ -199,8 +245,8 @@ def time_reference(prefix: str, reads: np.ndarray, threads: int, work_dir: str, 
     def run(fq, out):
         t0 = time.perf_counter()
         with open(out, "wb") as fo:
-            subprocess.run([REF_BIN, "aln", "-t", str(threads), prefix, fq], stdout=fo, stderr=subprocess.DEVNULL,
-                           check=True)
+            subprocess.run([REF_BIN, "aln", "-t", str(threads)] + list(aln_args) + [prefix, fq], stdout=fo,
+                           stderr=subprocess.DEVNULL, check=True)
         return time.perf_counter() - t0
 
     run(empty, os.path.join(work_dir, "empty.sai"))          # page cache warm
@@ -246,6 +292,9 @@ def main():
     ap.add_argument("--read-len", type=int, default=100)
     ap.add_argument("--seed", type=int, default=20260102)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--model", default="default", choices=["default", "stress"],
+                    help="read model (SURVEY §8d); 'stress' + --read-len 150 + --aln-args = BASELINE configs[2]")
+    ap.add_argument("--aln-args", default="", help="aln options for the run, e.g. '-n 4 -o 2 -e 10 -l 32 -k 2'")
     ap.add_argument("--set", action="append", default=[], help="engine knob key=value")
     args = ap.parse_args()
 
@@ -272,8 +321,13 @@ def main():
     from ibwa_b200 import engine, gap_init_opt
 
     opt = gap_init_opt()
-    workload = (f"bwa aln {args.reads} simulated {args.read_len}bp reads/GPU vs {args.genome_bp / 1e9:.2f} Gbp "
-                f"synthetic genome, defaults (-n 0.04), index replicated")
+    aln_args = args.aln_args.split()
+    if aln_args:
+        from ibwa_b200 import parse_aln_args
+        opt, _, _, _ = parse_aln_args(aln_args + ["prefix", "reads"])
+    workload = (f"bwa aln {args.reads} simulated {args.read_len}bp reads/GPU ({args.model} model) vs "
+                f"{args.genome_bp / 1e9:.2f} Gbp synthetic genome, {args.aln_args or 'defaults (-n 0.04)'}, "
+                f"index replicated")
     config = {"workload": workload, "genome_bp": args.genome_bp, "reads_per_gpu": args.reads,
               "read_len": args.read_len, "parallelism": f"replicated index, reads sharded x{world}",
               "l2": "inputs larger than L2 (index 3.1 GB + per-read state); no flush"}
@@ -285,7 +339,8 @@ def main():
     bwt, rbwt, text, prefix = load_or_build_index(args.genome_bp, args.seed, dev, is_writer=(local_rank == 0))
     if use_dist and local_rank == 0:
         dist.barrier()
-    reads_d = synth_reads_torch(text, args.reads, args.read_len, args.seed + 1000 + rank)
+    synth_fn = synth_reads_torch if args.model == "default" else synth_stress_reads_torch
+    reads_d = synth_fn(text, args.reads, args.read_len, args.seed + 1000 + rank)
     del text
     torch.cuda.empty_cache()
     log(f"[bench r{rank}] inputs ready in {time.time() - t_setup:.1f} s")
@@ -303,7 +358,7 @@ def main():
             vals = []
             res = None
             for i in range(args.warmup + args.steps):
-                res = time_reference(prefix, sample_h, nproc, work_dir, target_s=8.0)
+                res = time_reference(prefix, sample_h, nproc, work_dir, target_s=8.0, aln_args=aln_args)
                 if i >= args.warmup:
                     vals.append(res["reads_per_s"])
                 if i == 0 and args.warmup > 1:
@@ -462,13 +517,14 @@ def main():
                                                 rec_d.tobytes() == port["rec"].tobytes())}
         if world == 1 and not args.no_cpu_baseline:
             if os.path.exists(REF_BIN):
-                res = time_reference(prefix, sample_h, nproc, work_dir, target_s=15.0)
+                res = time_reference(prefix, sample_h, nproc, work_dir, target_s=15.0, aln_args=aln_args)
                 out["cpu_baseline"] = {"value": res["reads_per_s"], "unit": "reads/s", "cores": nproc,
                                        "kind": "reference",
                                        "sample": f"{res['n']} reads of the workload, `ibwa aln -t {nproc}`, wall "
                                                  f"{res['wall_s']:.2f} s minus {res['index_load_s']:.2f} s index load"}
                 from ibwa_b200 import sai
                 _, r_n, r_rec = sai.read_sai(res["sai"])
+                r_n = r_n[:res["n"]]
                 k = res["n"]
                 g_n, g_rec = eng.cal_sa_reg_gap(np.full(k, L, np.int32), np.arange(k, dtype=np.int64) * L,
                                                 sample_h[:k].reshape(-1), opt)

@@ -325,8 +325,16 @@ struct DevBuf {
     {
         if (bytes <= cap) return;
         if (p) CK(cudaFree(p));
+        p = nullptr;
         size_t want = bytes + bytes / 8 + 256;
-        CK(cudaMalloc(&p, want));
+        cudaError_t e = cudaMalloc(&p, want);
+        if (e != cudaSuccess) {
+            size_t fr = 0, tot = 0;
+            cudaMemGetInfo(&fr, &tot);
+            fprintf(stderr, "[b200aln] cannot allocate %.2f GB of device memory (%.2f GB free of %.2f GB): %s. Abort!\n",
+                    want / 1e9, fr / 1e9, tot / 1e9, cudaGetErrorString(e));
+            abort();
+        }
         cap = want;
     }
     void release()
@@ -371,7 +379,7 @@ struct b200aln_ctx {
     /* tuning */
     int search_blocks_per_sm = 6, width_blocks_per_sm = 5;
     uint32_t arena_cap = 4096, arena_cap_big = 0; /* 0: max_entries + 64 */
-    int rec_cap = 8, rec_cap_big = 1 << 16, big_lanes = 1024;
+    int rec_cap = 8, rec_cap_big = 1 << 13, big_lanes = 256; /* wide pass: 256 lanes x (max_entries+64) x 32 B = 16 GB */
     uint32_t arena_cap_mid = 32768; /* middle pass: still 16-bit heads in shared memory */
     int rec_cap_mid = 512, mid_lanes = 148 * 128;
     int pop_batch = 1;     /* memory pops are taken when this many lanes of a warp wait for one */

@@ -466,6 +466,20 @@ struct HeadsStrided16 {
     B2_HD void set(int sc, uint32_t slot) { h[(size_t)sc * stride] = (uint16_t)slot; }
 };
 
+/* 32-bit heads at h[sc * stride]: the wide pass with its heads in shared memory (stride = threads per
+ * block), or in global memory for score ranges that do not fit (stride 1) */
+struct HeadsStrided32 {
+    uint32_t *h;
+    int stride;
+    static B2_HD uint32_t nil() { return B2_NIL; }
+    B2_HD void clear(int nb)
+    {
+        for (int i = 0; i < nb; ++i) h[(size_t)i * stride] = B2_NIL;
+    }
+    B2_HD uint32_t get(int sc) const { return h[(size_t)sc * stride]; }
+    B2_HD void set(int sc, uint32_t slot) { h[(size_t)sc * stride] = slot; }
+};
+
 struct HeadsWide32 {
     uint32_t *h; /* [n_buckets] */
     static B2_HD uint32_t nil() { return B2_NIL; }

@@ -20,6 +20,7 @@
 #include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
+#include <time.h>
 
 #include <string>
 #include <vector>
@@ -120,6 +121,16 @@ template <> struct HeadsFactory<HeadsStrided16> {
         extern __shared__ uint16_t sm_heads[]; /* [n_buckets][blockDim.x] */
         HeadsStrided16 hd;
         hd.h = sm_heads + threadIdx.x;
+        hd.stride = (int)blockDim.x;
+        return hd;
+    }
+};
+template <> struct HeadsFactory<HeadsStrided32> {
+    static __device__ __forceinline__ HeadsStrided32 make(const SearchArgs &, size_t)
+    {
+        extern __shared__ uint32_t sm_heads32[]; /* [n_buckets][blockDim.x] */
+        HeadsStrided32 hd;
+        hd.h = sm_heads32 + threadIdx.x;
         hd.stride = (int)blockDim.x;
         return hd;
     }
@@ -380,8 +391,8 @@ struct b200aln_ctx {
     int search_blocks_per_sm = 6, width_blocks_per_sm = 5;
     uint32_t arena_cap = 4096, arena_cap_big = 0; /* 0: max_entries + 64 */
     int rec_cap = 8, rec_cap_big = 1 << 13, big_lanes = 256; /* wide pass: 256 lanes x (max_entries+64) x 32 B = 16 GB */
-    uint32_t arena_cap_mid = 32768; /* middle pass: still 16-bit heads in shared memory */
-    int rec_cap_mid = 512, mid_lanes = 148 * 128;
+    uint32_t arena_cap_mid = 16384; /* middle pass: 16-bit heads in shared memory, free-list arena */
+    int rec_cap_mid = 512, mid_lanes = 148 * 128 * 2;
     int pop_batch = 1;     /* memory pops are taken when this many lanes of a warp wait for one */
     int lut_k = 14;        /* levels of the path-k-mer interval table (0 = off) */
     uint32_t *d_lut[2] = {nullptr, nullptr};
@@ -651,6 +662,13 @@ struct Misc {
 /* 16-bit heads in shared memory: arena slots must fit 16 bits and n_buckets columns the shared memory */
 static bool fast_heads_ok(const Params &P, uint32_t arena_cap) { return P.n_buckets <= 160 && arena_cap < 65535u; }
 
+static void launch_search_mid(b200aln_ctx *c, SearchArgs &A, int blocks)
+{ /* middle pass: 16-bit shared-memory heads, free-list arena (capacity = stack high-water, not total pushes) */
+    const size_t smem = (size_t)A.env.P.n_buckets * 128 * sizeof(uint16_t);
+    k_search<HeadsStrided16, true, 1><<<blocks, 128, smem, c->st>>>(A);
+    CK(cudaGetLastError());
+}
+
 static void launch_search_fast(b200aln_ctx *c, SearchArgs &A, int blocks)
 {
     if (fast_heads_ok(A.env.P, A.arena_cap)) {
@@ -670,6 +688,12 @@ static void launch_search_fast(b200aln_ctx *c, SearchArgs &A, int blocks)
 
 static void launch_search_big(b200aln_ctx *c, SearchArgs &A, int blocks)
 {
+    const size_t smem32 = (size_t)A.env.P.n_buckets * 128 * sizeof(uint32_t);
+    if (smem32 <= 48 * 1024) { /* 32-bit heads still fit in shared memory */
+        k_search<HeadsStrided32, true, 1><<<blocks, 128, smem32, c->st>>>(A);
+        CK(cudaGetLastError());
+        return;
+    }
     A.heads_wide_stride = A.env.P.n_buckets + (A.env.P.n_buckets + 31) / 32;
     c->heads_wide_big.need((size_t)blocks * 128 * A.heads_wide_stride * 4);
     A.heads_wide = c->heads_wide_big.as<uint32_t>();
@@ -745,6 +769,15 @@ static void run_batch_device(b200aln_ctx *c, int n_reads, int max_len, const int
     CK(cudaStreamSynchronize(c->st));
     unsigned n_over = c->h_misc.as<Misc>()->n_over;
     c->stats.overflow_reads = n_over;
+    const bool verbose = getenv("B200ALN_VERBOSE") != nullptr;
+    struct timespec tv0;
+    clock_gettime(CLOCK_MONOTONIC, &tv0);
+    auto since = [&]() { struct timespec t; clock_gettime(CLOCK_MONOTONIC, &t); return (t.tv_sec - tv0.tv_sec) * 1e3 + (t.tv_nsec - tv0.tv_nsec) * 1e-6; };
+    if (verbose) {
+        float ms = 0;
+        cudaEventElapsedTime(&ms, c->ev[2], c->ev[3]);
+        fprintf(stderr, "[b200aln] fast pass %.1f ms, %u of %d reads flagged\n", ms, n_over, n_reads);
+    }
     const int32_t *wide_list = c->over_list.as<int32_t>();
     unsigned n_wide = n_over;
     if (n_over && fast_heads_ok(P, c->arena_cap_mid) &&
@@ -766,12 +799,13 @@ static void run_batch_device(b200aln_ctx *c, int n_reads, int max_len, const int
         SM.recs = c->recs_mid.as<Rec>(); SM.rec_cap = c->rec_cap_mid; SM.recs_by_work = 1;
         SM.over_slot = c->over_slot.as<int32_t>(); SM.slot_tag = 0;
         SM.counter = &dm->counter_mid; SM.n_over = &dm->n_over2; SM.over_list = c->over_list2.as<int32_t>();
-        launch_search_fast(c, SM, mblocks);
+        launch_search_mid(c, SM, mblocks);
         ++launches;
         CK(cudaMemcpyAsync(c->h_misc.p, c->misc.p, sizeof(Misc), cudaMemcpyDeviceToHost, c->st));
         CK(cudaStreamSynchronize(c->st));
         n_wide = c->h_misc.as<Misc>()->n_over2;
         wide_list = c->over_list2.as<int32_t>();
+        if (verbose) fprintf(stderr, "[b200aln] middle pass %.1f ms (%d lanes), %u reads left for the wide pass\n", since(), lanes_mid, n_wide);
     }
     if (n_wide) {
         uint32_t cap_big = c->arena_cap_big ? c->arena_cap_big : (uint32_t)opt->max_entries + 64u;
@@ -793,6 +827,10 @@ static void run_batch_device(b200aln_ctx *c, int n_reads, int max_len, const int
         SB.counter = &dm->counter_big; SB.n_over = nullptr; SB.over_list = nullptr;
         launch_search_big(c, SB, bblocks);
         ++launches;
+        if (verbose) {
+            CK(cudaStreamSynchronize(c->st));
+            fprintf(stderr, "[b200aln] wide pass done at %.1f ms (%d lanes)\n", since(), bblocks * 128);
+        }
     }
     CK(cudaEventRecord(c->ev[4], c->st));
 

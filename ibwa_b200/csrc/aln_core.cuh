@@ -102,9 +102,11 @@ B2_D uint32_t ld_q(const uint32_t *p)
     return *p;
 #endif
 }
+B2_D void prefetch_l2(const void *p) { asm volatile("prefetch.global.L2 [%0];" :: "l"(p)); }
 B2_D int popc32(uint32_t v) { return __popc(v); }
 B2_D int ctz32(uint32_t v) { return __ffs((int)v) - 1; }
 #else
+inline void prefetch_l2(const void *) {}
 inline uint32_t ld_q(const uint32_t *p) { return *p; }
 inline void st8(uint32_t *p, const uint32_t v[8]) { for (int i = 0; i < 8; ++i) p[i] = v[i]; }
 inline OccBlk ld_blk(const OccBlk *p) { return *p; }
@@ -128,13 +130,17 @@ struct FmView {
      * (k, l) of X as two u32, empty = (1, 0).  The four children X*4+c of a node are one 32-byte
      * sector, so an expansion above level lut_k costs ONE request instead of two occ sectors,
      * and the small top levels stay L2 resident. */
-    const uint32_t *lut;
+    const uint32_t *lut; /* shared by both indexes: level L = [index 0: 4^L pairs][index 1: 4^L pairs] */
     int lut_k;
+    int lut_w;           /* which half of every level is this index's (0 = bwt, 1 = rbwt) */
 };
 
 #define B2_PATH_DEAD 31u /* depth field value of an entry that left the interval table */
 /* first (k,l) pair of a level: (4^level - 4) / 3; (4^L - 1) / 3 is the bit pattern 0101..01 with L ones */
 B2_HD uint64_t lut_level_off(int level) { return (0x5555555555555555ull >> (64 - 2 * level)) - 1u; }
+/* pair index of node X of `level` for index half w.  The levels of BOTH indexes are interleaved so that
+ * the small, hot top of the table is one contiguous range (pinned in L2 with an access-policy window). */
+B2_HD uint64_t lut_pair(int w, int level, uint64_t X) { return 2u * lut_level_off(level) + ((uint64_t)w << (2 * level)) + X; }
 B2_HD uint32_t path_root() { return 0u; }
 /* path of the child reached by prepending character c to a node with path p */
 B2_HD uint32_t path_ext(uint32_t p, int c, int lut_k)
@@ -164,6 +170,7 @@ struct Rec { /* == bwt_aln1_t */
 struct SearchEnv {
     FmView fm[2]; /* fm[0] = bwt, fm[1] = rbwt */
     Params P;
+    int prefetch_next; /* 1: prefetch the next pop candidate into L2 (helps when few, long reads are left) */
 };
 
 /* ---- packed per-position record Q[a][j] (built by the width pass) -------- */
@@ -237,7 +244,7 @@ B2_HD void children4(const FmView &f, uint32_t path, uint32_t k, uint32_t l, uin
 {
     const uint32_t d = path & 31u;
     if (d != B2_PATH_DEAD && (int)d < f.lut_k) {
-        const uint32_t *p = f.lut + 2 * (lut_level_off((int)d + 1) + ((uint64_t)(path >> 5) << 2));
+        const uint32_t *p = f.lut + 2 * lut_pair(f.lut_w, (int)d + 1, (uint64_t)(path >> 5) << 2);
         const U8x v = ld_lut8(p);
         nk[0] = v.v[0]; nl[0] = v.v[1]; nk[1] = v.v[2]; nl[1] = v.v[3];
         nk[2] = v.v[4]; nl[2] = v.v[5]; nk[3] = v.v[6]; nl[3] = v.v[7];
@@ -250,16 +257,16 @@ B2_HD void children4(const FmView &f, uint32_t path, uint32_t k, uint32_t l, uin
 }
 
 /* Builds the four children of table node X of level `level` (level 0 = the root) into level + 1.
- * lut is the table being built (levels <= level complete); f.lut_k is ignored here. */
+ * lut is the table being built (levels <= level complete); f.lut_k is ignored here, f.lut_w selects the half. */
 B2_HD void lut_build_node(const FmView &f, uint32_t *lut, int level, uint64_t X)
 {
     uint32_t k = 0, l = f.seq_len;
     if (level > 0) {
-        const uint32_t *p = lut + 2 * (lut_level_off(level) + X);
+        const uint32_t *p = lut + 2 * lut_pair(f.lut_w, level, X);
         k = p[0];
         l = p[1];
     }
-    uint32_t *o = lut + 2 * (lut_level_off(level + 1) + (X << 2));
+    uint32_t *o = lut + 2 * lut_pair(f.lut_w, level + 1, X << 2);
     if (k <= l) {
         uint32_t ck[4], cl[4], ns;
         occ2x4(f, k, l, ck, cl, ns);
@@ -268,7 +275,7 @@ B2_HD void lut_build_node(const FmView &f, uint32_t *lut, int level, uint64_t X)
         for (int c = 0; c < 4; ++c) { o[2 * c] = 1u; o[2 * c + 1] = 0u; }
     }
 }
-B2_HD uint64_t lut_total_pairs(int lut_k) { return lut_k > 0 ? lut_level_off(lut_k + 1) : 0; }
+B2_HD uint64_t lut_total_pairs(int lut_k) { return lut_k > 0 ? 2u * lut_level_off(lut_k + 1) : 0; } /* both indexes */
 
 /* ---------------------------------------------------------- width pass ---- */
 
@@ -288,7 +295,7 @@ struct WidthChain {
         const uint32_t d = path & 31u;
         use_lut = d != B2_PATH_DEAD && (int)d < f.lut_k;
         if (use_lut) {
-            const uint32_t *p = f.lut + 2 * (lut_level_off((int)d + 1) + ((uint64_t)(path >> 5) << 2) + (uint32_t)c);
+            const uint32_t *p = f.lut + 2 * lut_pair(f.lut_w, (int)d + 1, ((uint64_t)(path >> 5) << 2) + (uint32_t)c);
             lk = ld_q(p);
             ll = ld_q(p + 1);
         } else {
@@ -523,6 +530,7 @@ struct SearchLane {
     Heads bk;
     uint32_t top, free_head; /* bump pointer / free list */
     int best, n_mem;         /* lowest non-empty bucket (n_buckets when none); records in memory */
+    bool prefetch_next;      /* L2 prefetch of the next pop candidate (latency-bound passes) */
     int n_entries;           /* the reference's stack->n_entries (memory + held) */
     int max_diff, best_score, best_diff, best_cnt, n_aln;
     int status;
@@ -557,6 +565,7 @@ struct SearchLane {
         finished = false; have_cur = false; cur_held = false; extending = false;
         top = 0; free_head = B2_NIL; n_entries = 0;
         best = P->n_buckets; n_mem = 0;
+        prefetch_next = E.prefetch_next != 0;
         n_pops = n_lookups = 0;
         if (n_amb > max_diff_) { finished = true; return; } /* bwtgap.c:117-122 */
         bk.clear(P->n_buckets);
@@ -625,14 +634,18 @@ struct SearchLane {
         ld_ent(ar.ent + slot, e, prev, cpath);
         bk.set(b, prev);
         --n_mem;
+        uint32_t next_top = prev;
         if (prev == Heads::nil()) { /* bucket emptied: next non-empty one upwards (bwtgap.c:73-78) */
             if (n_mem == 0) best = E.P.n_buckets;
             else {
                 int nb = b + 1;
-                while (bk.get(nb) == Heads::nil()) ++nb;
+                while ((next_top = bk.get(nb)) == Heads::nil()) ++nb;
                 best = nb;
             }
         }
+        /* the entry that will most likely be popped next: start bringing it into L2 while this
+         * entry's lookup is in flight (a hint only; pushes of this step may still overtake it) */
+        if (prefetch_next && n_mem > 0) prefetch_l2(ar.ent + next_top);
         if (REUSE) { ar.ent[slot].link = free_head; free_head = slot; }
         --n_entries;
         ck = e.x; cl = e.y;

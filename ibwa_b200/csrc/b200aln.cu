@@ -393,9 +393,12 @@ struct b200aln_ctx {
     int rec_cap = 8, rec_cap_big = 1 << 13, big_lanes = 256; /* wide pass: 256 lanes x (max_entries+64) x 32 B = 16 GB */
     uint32_t arena_cap_mid = 16384; /* middle pass: 16-bit heads in shared memory, free-list arena */
     int rec_cap_mid = 512, mid_lanes = 148 * 128 * 2;
+    int prefetch_fast = 0, prefetch_mid = 1; /* L2 prefetch of the next pop candidate, per pass */
     int pop_batch = 1;     /* memory pops are taken when this many lanes of a warp wait for one */
     int lut_k = 14;        /* levels of the path-k-mer interval table (0 = off) */
-    uint32_t *d_lut[2] = {nullptr, nullptr};
+    uint32_t *d_lut[2] = {nullptr, nullptr}; /* [0]: the table of both indexes */
+    int lut_pin_levels = 10; /* top levels of the table kept persisting in L2 (0 = no window) */
+    size_t lut_pin_bytes = 0;
     int batch_max_len = 0; /* > 0: the reference batch this call is a shard of has this longest read */
     /* device buffers */
     DevBuf lens, offs, codes, md, Q, W, n_amb, ent, recs, n_aln, over_slot, over_list, misc, off64,
@@ -468,6 +471,29 @@ static void upload_index(b200aln_ctx *c, int which, const b200aln_bwt_view_t *v)
 
 static void build_luts(b200aln_ctx *c);
 
+/* levels <= lut_pin_levels of the interval table (contiguous at its start, both indexes) persist in L2 */
+static void apply_l2_window(b200aln_ctx *c)
+{
+    if (!c->lut_pin_bytes || !c->d_lut[0]) return;
+    cudaDeviceProp prop;
+    CK(cudaGetDeviceProperties(&prop, c->device));
+    size_t bytes = c->lut_pin_bytes;
+    if (prop.persistingL2CacheMaxSize <= 0 || prop.accessPolicyMaxWindowSize <= 0) return;
+    if (bytes > (size_t)prop.accessPolicyMaxWindowSize) bytes = (size_t)prop.accessPolicyMaxWindowSize;
+    size_t carve = bytes < (size_t)prop.persistingL2CacheMaxSize ? bytes : (size_t)prop.persistingL2CacheMaxSize;
+    if (cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, carve) != cudaSuccess) { (void)cudaGetLastError(); return; }
+    cudaStreamAttrValue attr;
+    memset(&attr, 0, sizeof attr);
+    attr.accessPolicyWindow.base_ptr = c->d_lut[0];
+    attr.accessPolicyWindow.num_bytes = bytes;
+    attr.accessPolicyWindow.hitRatio = carve >= bytes ? 1.0f : (float)carve / (float)bytes;
+    attr.accessPolicyWindow.hitProp = cudaAccessPropertyPersisting;
+    attr.accessPolicyWindow.missProp = cudaAccessPropertyStreaming;
+    if (cudaStreamSetAttribute(c->st, cudaStreamAttributeAccessPolicyWindow, &attr) != cudaSuccess) (void)cudaGetLastError();
+    if (getenv("B200ALN_VERBOSE"))
+        fprintf(stderr, "[b200aln] L2 window: %.1f MB of the interval table persisting (carve-out %.1f MB)\n", bytes / 1e6, carve / 1e6);
+}
+
 extern "C" b200aln_ctx *b200aln_open(const b200aln_bwt_view_t *bwt, const b200aln_bwt_view_t *rbwt, int device)
 {
     int n = b200aln_device_count();
@@ -500,35 +526,42 @@ extern "C" b200aln_ctx *b200aln_open(const b200aln_bwt_view_t *bwt, const b200al
     {
         const char *e = getenv("B200ALN_LUT_K");
         if (e) c->lut_k = atoi(e);
+        e = getenv("B200ALN_LUT_PIN");
+        if (e) c->lut_pin_levels = atoi(e);
     }
     build_luts(c);
     memset(&c->stats, 0, sizeof c->stats);
     return c;
 }
 
-/* (re)builds the interval tables of both indexes for c->lut_k levels (clamped to the index size) */
+/* (re)builds the interval table of both indexes for c->lut_k levels (clamped to the index size) and pins
+ * its small, hot top levels in L2 with an access-policy window on the engine's stream */
 static void build_luts(b200aln_ctx *c)
 {
     int k = c->lut_k;
     if (k > 14) k = 14; /* path word: 5 bits depth + 2 * (k - 1) bits k-mer */
     while (k > 0 && ((uint64_t)1 << (2 * k)) > 4ull * ((uint64_t)c->fm[0].seq_len + 1)) --k; /* tiny indexes */
+    if (c->d_lut[0]) { CK(cudaFree(c->d_lut[0])); c->d_lut[0] = nullptr; }
+    for (int w = 0; w < 2; ++w) { c->fm[w].lut = nullptr; c->fm[w].lut_k = 0; c->fm[w].lut_w = w; }
+    if (k <= 0) return;
+    CK(cudaMalloc(&c->d_lut[0], lut_total_pairs(k) * 8 + 64));
     for (int w = 0; w < 2; ++w) {
-        if (c->d_lut[w]) { CK(cudaFree(c->d_lut[w])); c->d_lut[w] = nullptr; }
-        c->fm[w].lut = nullptr;
-        c->fm[w].lut_k = 0;
-        if (k <= 0) continue;
-        CK(cudaMalloc(&c->d_lut[w], lut_total_pairs(k) * 8 + 64));
         FmView f = c->fm[w];
         for (int level = 0; level < k; ++level) {
             const uint64_t n = (uint64_t)1 << (2 * level);
             const int blocks = (int)((n + 255) / 256 < (uint64_t)c->n_sm * 16 ? (n + 255) / 256 : (uint64_t)c->n_sm * 16);
-            k_lut_build<<<blocks, 256, 0, c->st>>>(f, c->d_lut[w], level, n);
+            k_lut_build<<<blocks, 256, 0, c->st>>>(f, c->d_lut[0], level, n);
             CK(cudaGetLastError());
         }
-        c->fm[w].lut = c->d_lut[w];
-        c->fm[w].lut_k = k;
     }
+    for (int w = 0; w < 2; ++w) { c->fm[w].lut = c->d_lut[0]; c->fm[w].lut_k = k; }
     CK(cudaStreamSynchronize(c->st));
+    c->lut_pin_bytes = 0;
+    if (c->lut_pin_levels > 0) {
+        const int pl = c->lut_pin_levels < k ? c->lut_pin_levels : k;
+        c->lut_pin_bytes = lut_total_pairs(pl) * 8;
+        apply_l2_window(c);
+    }
 }
 
 extern "C" b200aln_ctx *b200aln_clone(b200aln_ctx *p)
@@ -545,15 +578,18 @@ extern "C" b200aln_ctx *b200aln_clone(b200aln_ctx *p)
         c->d_lut[i] = p->d_lut[i];
     }
     c->lut_k = p->lut_k;
+    c->lut_pin_levels = p->lut_pin_levels; c->lut_pin_bytes = p->lut_pin_bytes;
     c->search_blocks_per_sm = p->search_blocks_per_sm; c->width_blocks_per_sm = p->width_blocks_per_sm;
     c->arena_cap = p->arena_cap; c->arena_cap_big = p->arena_cap_big;
     c->rec_cap = p->rec_cap; c->rec_cap_big = p->rec_cap_big; c->big_lanes = p->big_lanes;
     c->arena_cap_mid = p->arena_cap_mid; c->rec_cap_mid = p->rec_cap_mid; c->mid_lanes = p->mid_lanes;
     c->pop_batch = p->pop_batch;
+    c->prefetch_fast = p->prefetch_fast; c->prefetch_mid = p->prefetch_mid;
     CK(cudaStreamCreateWithFlags(&c->st, cudaStreamNonBlocking));
     for (int i = 0; i < 8; ++i) CK(cudaEventCreate(&c->ev[i]));
     for (int i = 0; i < 2; ++i) CK(cudaEventCreate(&c->tm[i]));
     memset(&c->stats, 0, sizeof c->stats);
+    apply_l2_window(c); /* same window on the clone's stream */
     return c;
 }
 
@@ -621,6 +657,8 @@ extern "C" void b200aln_set_int(b200aln_ctx *c, const char *key, int64_t v)
     else if (!strcmp(key, "rec_cap_big")) c->rec_cap_big = (int)v;
     else if (!strcmp(key, "big_lanes")) c->big_lanes = (int)v;
     else if (!strcmp(key, "pop_batch")) c->pop_batch = (int)v;
+    else if (!strcmp(key, "prefetch_fast")) c->prefetch_fast = (int)v;
+    else if (!strcmp(key, "prefetch_mid")) c->prefetch_mid = (int)v;
     else if (!strcmp(key, "arena_cap_mid")) c->arena_cap_mid = (uint32_t)v;
     else if (!strcmp(key, "rec_cap_mid")) c->rec_cap_mid = (int)v;
     else if (!strcmp(key, "mid_lanes")) c->mid_lanes = (int)v;
@@ -747,6 +785,7 @@ static void run_batch_device(b200aln_ctx *c, int n_reads, int max_len, const int
 
     SearchArgs SA;
     SA.env.fm[0] = c->fm[0]; SA.env.fm[1] = c->fm[1]; SA.env.P = P;
+    SA.env.prefetch_next = c->prefetch_fast;
     SA.n_work = n_reads; SA.work_list = nullptr;
     SA.lens = d_lens; SA.n_amb = c->n_amb.as<int32_t>(); SA.md = c->md.as<int32_t>();
     SA.Q = WA.Q; SA.W = WA.W; SA.strideQ = strideQ; SA.strideW = strideW;
@@ -798,6 +837,7 @@ static void run_batch_device(b200aln_ctx *c, int n_reads, int max_len, const int
         SM.ent = c->ent_mid.as<StackEnt>(); SM.arena_cap = c->arena_cap_mid;
         SM.recs = c->recs_mid.as<Rec>(); SM.rec_cap = c->rec_cap_mid; SM.recs_by_work = 1;
         SM.over_slot = c->over_slot.as<int32_t>(); SM.slot_tag = 0;
+        SM.env.prefetch_next = c->prefetch_mid;
         SM.counter = &dm->counter_mid; SM.n_over = &dm->n_over2; SM.over_list = c->over_list2.as<int32_t>();
         launch_search_mid(c, SM, mblocks);
         ++launches;
@@ -824,6 +864,7 @@ static void run_batch_device(b200aln_ctx *c, int n_reads, int max_len, const int
         SB.ent = c->ent_big.as<StackEnt>(); SB.arena_cap = cap_big;
         SB.recs = c->recs_big.as<Rec>(); SB.rec_cap = c->rec_cap_big; SB.recs_by_work = 1;
         SB.over_slot = c->over_slot.as<int32_t>(); SB.slot_tag = WIDE_TAG;
+        SB.env.prefetch_next = c->prefetch_mid;
         SB.counter = &dm->counter_big; SB.n_over = nullptr; SB.over_list = nullptr;
         launch_search_big(c, SB, bblocks);
         ++launches;

@@ -96,13 +96,16 @@ static int64_t run(const SearchEnv &env, const std::vector<int> &md, int n_reads
     return n_status;
 }
 
-static std::vector<uint32_t> build_lut(FmView &f, int lut_k)
+static std::vector<uint32_t> build_lut(FmView fm[2], int lut_k)
 {
     std::vector<uint32_t> lut(2 * lut_total_pairs(lut_k) + 8);
-    f.lut = nullptr;
-    f.lut_k = 0;
-    for (int level = 0; level < lut_k; ++level)
-        for (uint64_t X = 0; X < ((uint64_t)1 << (2 * level)); ++X) lut_build_node(f, lut.data(), level, X);
+    for (int w = 0; w < 2; ++w) {
+        fm[w].lut = nullptr;
+        fm[w].lut_k = 0;
+        fm[w].lut_w = w;
+        for (int level = 0; level < lut_k; ++level)
+            for (uint64_t X = 0; X < ((uint64_t)1 << (2 * level)); ++X) lut_build_node(fm[w], lut.data(), level, X);
+    }
     return lut;
 }
 
@@ -117,11 +120,12 @@ extern "C" int64_t hh_aln_batch(const b200aln_bwt_view_t *bwt, const b200aln_bwt
 {
     std::vector<OccBlk> i0 = convert(bwt), i1 = convert(rbwt);
     SearchEnv env;
+    env.prefetch_next = 0;
     FmView *fm = env.fm;
     fm[0].blk = i0.data(); fm[0].primary = bwt->primary; fm[0].seq_len = bwt->seq_len;
     fm[1].blk = i1.data(); fm[1].primary = rbwt->primary; fm[1].seq_len = rbwt->seq_len;
-    std::vector<uint32_t> lut0 = build_lut(fm[0], g_lut_k), lut1 = build_lut(fm[1], g_lut_k);
-    fm[0].lut = lut0.data(); fm[1].lut = lut1.data();
+    std::vector<uint32_t> lut = build_lut(fm, g_lut_k);
+    fm[0].lut = fm[1].lut = lut.data();
     fm[0].lut_k = fm[1].lut_k = g_lut_k;
     int max_len = 0;
     for (int r = 0; r < n_reads; ++r) if (lens[r] > max_len) max_len = lens[r];

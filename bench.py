@@ -498,10 +498,16 @@ def main():
             peak, which = float(json.load(open(peaks_path))["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
         else:
             peak, which = 6650.0, "fallback (B200_PROFILING.md)"
+        traffic = None                      # DRAM bytes of the dominant kernel per launch, from the committed ncu capture
+        tpath = os.path.join(ROOT, "profiles", "r1_traffic.json")
+        if os.path.exists(tpath):
+            traffic = float(json.load(open(tpath))["k_search"]["dram_bytes_per_read"]) * n
         sector_roof = eng.sector_roofline(1 << 28, 3)
         pair_roof = eng.sector_roofline(1 << 27, -3)
         out["roofline"] = {"bound": "hbm", "kernel": "k_search", "achieved": achieved, "peak": peak, "unit": "GB/s",
-                           "frac": achieved / peak, "traffic": None, "peak_source": which,
+                           "frac": achieved / peak, "traffic": traffic, "peak_source": which,
+                           "traffic_source": "profiles/r1_traffic.json (ncu dram__bytes_read+write per read x reads)",
+                           "algorithmic_bytes": bytes_per_read * n,
                            "algorithmic_bytes_per_read": bytes_per_read,
                            "oracle_lookups_per_read": lookups_per_read,
                            "oracle_pops_per_read": port["stats"]["pops"] / port["n"],

@@ -61,7 +61,7 @@ const Nt4Table g_nt4;
  * reading stops at the first truncated record. */
 class SeqReader {
   public:
-    explicit SeqReader(const char *fn) : buf_(1 << 22)
+    explicit SeqReader(const char *fn) : buf_((size_t)160 << 20)
     {
         if (strcmp(fn, "-") == 0) f_ = gzdopen(fileno(stdin), "r"); /* utils.c:56-66 */
         else f_ = gzopen(fn, "r");
@@ -85,7 +85,7 @@ class SeqReader {
     int read_record_fast()
     {
         if (last_char_ != 0) return -3;
-        refill_keep_tail();
+        refill_keep_tail(1 << 16);
         const unsigned char *b = buf_.data();
         const int e = end_;
         int p = begin_;
@@ -150,6 +150,73 @@ class SeqReader {
         return (int)seq_.size();
     }
 
+    /* One ordinary 4-line record found by the structural scan: offsets into the buffer. */
+    struct Extent { int start, seq, len, qual, next; };
+
+    /* Structural scan (newline positions only) of up to max_records consecutive ordinary records from the
+     * cursor.  Does NOT move the cursor and does not look at the characters: convert_extent() validates them.
+     * Stops at the first record that is not of the plain 4-line shape or not wholly in the buffer. */
+    int scan_fast(int max_records, std::vector<Extent> &out)
+    {
+        out.clear();
+        if (last_char_ != 0) return 0;
+        refill_keep_tail(1 << 26);
+        const unsigned char *b = buf_.data();
+        const int e = end_;
+        int p = begin_;
+        while ((int)out.size() < max_records) {
+            if (p >= e || b[p] != '@') break;
+            const unsigned char *nl1 = (const unsigned char *)memchr(b + p + 1, '\n', (size_t)(e - p - 1));
+            if (!nl1 || nl1 == b + p + 1 || isspace(b[p + 1])) break;
+            const int s0 = (int)(nl1 - b) + 1;
+            const unsigned char *nl2 = (const unsigned char *)memchr(b + s0, '\n', (size_t)(e - s0));
+            if (!nl2) break;
+            const int L = (int)(nl2 - b) - s0;
+            const int q_plus = s0 + L + 1;
+            if (L <= 0 || q_plus >= e || b[q_plus] != '+') break;
+            const unsigned char *nl3 = (const unsigned char *)memchr(b + q_plus, '\n', (size_t)(e - q_plus));
+            if (!nl3) break;
+            const int q0 = (int)(nl3 - b) + 1;
+            if (q0 + L >= e || b[q0 + L] != '\n') break;
+            Extent x;
+            x.start = p; x.seq = s0; x.len = L; x.qual = q0; x.next = q0 + L + 1;
+            out.push_back(x);
+            p = x.next;
+        }
+        return (int)out.size();
+    }
+    /* character checks of the fast path (see read_record_fast) + conversion; false = let the exact parser decide */
+    bool convert_extent(const Extent &x, uint8_t *codes, bool is_64, int trim_qual, int *len_out) const
+    {
+        const unsigned char *b = buf_.data();
+        unsigned bad = 0;
+        for (int i = 0; i < x.len; ++i) {
+            const unsigned char ch = b[x.seq + i];
+            bad |= (unsigned)(ch <= 32) | (unsigned)(ch >= 127) | (unsigned)(ch == '>') | (unsigned)(ch == '+') |
+                   (unsigned)(ch == '@');
+            codes[i] = g_nt4.t[ch];
+        }
+        for (int i = 0; i < x.len; ++i) {
+            const unsigned char ch = b[x.qual + i];
+            bad |= (unsigned)(ch < 33) | (unsigned)(ch > 127);
+        }
+        if (bad) return false;
+        int len = x.len;
+        if (trim_qual >= 1) { /* bwa_trim_read on the (offset-corrected) qualities */
+            int sc = 0, best = 0, best_l = x.len - 1;
+            for (int l = x.len - 1; l >= BWA_MIN_RDLEN - 1; --l) {
+                const int q = (int)(unsigned char)(char)(b[x.qual + l] - (is_64 ? 31 : 0));
+                sc += trim_qual - (q - 33);
+                if (sc < 0) break;
+                if (sc > best) { best = sc; best_l = l; }
+            }
+            len = best_l + 1;
+        }
+        *len_out = len;
+        return true;
+    }
+    void set_cursor(int pos) { begin_ = pos; }
+
     const std::string &seq() const { return seq_; }
     std::string &seq_mut() { return seq_; }
     std::string &qual_mut() { return qual_; }
@@ -157,9 +224,9 @@ class SeqReader {
 
   private:
     /* keep at least one large record's worth of bytes contiguous for the fast path */
-    void refill_keep_tail()
+    void refill_keep_tail(int want_bytes)
     {
-        if (is_eof_ || end_ - begin_ >= (1 << 16)) return;
+        if (is_eof_ || end_ - begin_ >= want_bytes) return;
         const int tail = end_ - begin_;
         if (tail > 0 && begin_ > 0) memmove(buf_.data(), buf_.data() + begin_, (size_t)tail);
         begin_ = 0;
@@ -235,7 +302,36 @@ struct PackedBatch {
     void clear() { lens.clear(); offs.clear(); codes.clear(); n_trimmed = n_tot = 0; }
 };
 
-/* bwa_read_seq (bwaseqio.c:145-208) into the packed form; returns reads stored */
+/* appends the record the reader currently holds (exact or single fast path), bwaseqio.c:158-192 */
+static void append_current(SeqReader &rd, bool is_64, int l_bc, int trim_qual, PackedBatch &b)
+{
+    std::string &s = rd.seq_mut(), &q = rd.qual_mut();
+    if (is_64) for (char &ch : q) ch = (char)(ch - 31);
+    if ((int)s.size() <= l_bc) return;
+    if (l_bc) {
+        s.erase(0, (size_t)l_bc);
+        if (!q.empty()) q.erase(0, (size_t)l_bc);
+    }
+    const int full = (int)s.size();
+    int len = full;
+    b.n_tot += full;
+    if (!q.empty() && trim_qual >= 1) {
+        len = trim_len(trim_qual, full, q.data());
+        b.n_trimmed += full - len;
+    }
+    b.offs.push_back((int64_t)b.codes.size());
+    b.lens.push_back(len);
+    const size_t at = b.codes.size();
+    b.codes.resize(at + (size_t)full);
+    for (int i = 0; i < full; ++i) b.codes[at + (size_t)i] = g_nt4.t[(unsigned char)s[i]];
+}
+
+/*
+ * bwa_read_seq (bwaseqio.c:145-208) into the packed form; returns reads stored.
+ * Runs of ordinary 4-line FASTQ records are located by a serial structural scan (newlines only) and
+ * validated + converted by worker threads; any record that is not provably parsed identically by the
+ * reference's state machine (kseq.h:150-194) goes through the exact parser, one record at a time.
+ */
 int next_batch(SeqReader &rd, int n_needed, int mode, int trim_qual, PackedBatch &b)
 {
     const bool is_64 = mode & BWA_MODE_IL13;
@@ -245,28 +341,58 @@ int next_batch(SeqReader &rd, int n_needed, int mode, int trim_qual, PackedBatch
         fprintf(stderr, "[bwa_read_seq] the maximum barcode length is 15.\n");
         return 0;
     }
-    int l;
-    while ((l = rd.read_record()) >= 0) {
-        std::string &s = rd.seq_mut(), &q = rd.qual_mut();
-        if (is_64) for (char &ch : q) ch = (char)(ch - 31);
-        if ((int)s.size() <= l_bc) continue;
-        if (l_bc) {
-            s.erase(0, (size_t)l_bc);
-            if (!q.empty()) q.erase(0, (size_t)l_bc);
+    static const unsigned n_workers = [] {
+        const char *e = getenv("B200ALN_PARSE_THREADS");
+        unsigned t = e ? (unsigned)atoi(e) : std::thread::hardware_concurrency();
+        return t < 1 ? 1u : (t > 16 ? 16u : t);
+    }();
+    std::vector<SeqReader::Extent> ext;
+    bool eof = false;
+    while (!eof && (int)b.lens.size() < n_needed) {
+        int n = l_bc == 0 ? rd.scan_fast(n_needed - (int)b.lens.size(), ext) : 0;
+        if (n >= 64) {
+            const size_t base_reads = b.lens.size();
+            size_t total = b.codes.size();
+            b.offs.resize(base_reads + (size_t)n);
+            b.lens.resize(base_reads + (size_t)n);
+            for (int i = 0; i < n; ++i) { b.offs[base_reads + i] = (int64_t)total; total += (size_t)ext[i].len; }
+            const size_t codes_base = b.codes.size();
+            b.codes.resize(total);
+            std::vector<int> first_bad(n_workers, n);
+            auto work = [&](unsigned t) {
+                const int lo = (int)((int64_t)n * t / n_workers), hi = (int)((int64_t)n * (t + 1) / n_workers);
+                for (int i = lo; i < hi; ++i) {
+                    int len;
+                    if (!rd.convert_extent(ext[i], b.codes.data() + b.offs[base_reads + i], is_64, trim_qual, &len)) {
+                        first_bad[t] = i;
+                        return;
+                    }
+                    b.lens[base_reads + i] = len;
+                }
+            };
+            std::vector<std::thread> th;
+            for (unsigned t = 1; t < n_workers; ++t) th.emplace_back(work, t);
+            work(0);
+            for (auto &x : th) x.join();
+            int ok = n;
+            for (unsigned t = 0; t < n_workers; ++t) if (first_bad[t] < ok) ok = first_bad[t];
+            /* keep records [0, ok); the one at `ok` (if any) goes to the exact parser below */
+            size_t kept_codes = codes_base;
+            for (int i = 0; i < ok; ++i) {
+                kept_codes += (size_t)ext[i].len;
+                b.n_tot += ext[i].len;
+                b.n_trimmed += ext[i].len - b.lens[base_reads + i];
+            }
+            b.offs.resize(base_reads + (size_t)ok);
+            b.lens.resize(base_reads + (size_t)ok);
+            b.codes.resize(kept_codes);
+            rd.set_cursor(ok > 0 ? ext[ok - 1].next : ext[0].start);
+            if (ok == n) continue;
         }
-        const int full = (int)s.size();
-        int len = full;
-        b.n_tot += full;
-        if (!q.empty() && trim_qual >= 1) {
-            len = trim_len(trim_qual, full, q.data());
-            b.n_trimmed += full - len;
-        }
-        b.offs.push_back((int64_t)b.codes.size());
-        b.lens.push_back(len);
-        const size_t at = b.codes.size();
-        b.codes.resize(at + (size_t)full);
-        for (int i = 0; i < full; ++i) b.codes[at + (size_t)i] = g_nt4.t[(unsigned char)s[i]];
-        if ((int)b.lens.size() == n_needed) break;
+        /* one record through the reference-exact path (also refills the buffer / detects the end) */
+        const int l = rd.read_record();
+        if (l < 0) eof = true;
+        else append_current(rd, is_64, l_bc, trim_qual, b);
     }
     if (!b.lens.empty() && trim_qual >= 1)
         fprintf(stderr, "[bwa_read_seq] %.1f%% bases are trimmed.\n", 100.0f * b.n_trimmed / b.n_tot);

@@ -95,3 +95,24 @@ def test_hostile_inputs_against_reference_binary(tmp_path, golden_dir, g1_index,
         n_aln, rec, _ = pyoracle.aln_batch(ob, orb, b.lens, b.offs, b.codes, opt.to_c())
         sai.write_batch(buf, n_aln, rec)
     assert buf.getvalue() == open(ref_sai, "rb").read()
+
+
+def test_parallel_path_falls_back_on_odd_records(tmp_path):
+    """Long runs of ordinary records (parallel scan + convert) interrupted by records only the exact state
+    machine may parse: multi-line, CRLF, '@'-leading quality, lower case, a FASTA record."""
+    rng = np.random.default_rng(2)
+    p = str(tmp_path / "mixed.fq")
+    nt = np.frombuffer(b"ACGTN", dtype=np.uint8)
+    odd = [b"@odd1\nACGT\nACGT\n+\nIIII\nIIII\n", b"@odd2\r\nACGTAC\r\n+\r\nIIIIII\r\n", b"@odd3\nACGTACGT\n+\n@@IIIIII\n",
+           b">fa1 x\nacgtnACGT\n", b"@odd4 c\nAC GT\n+\nIIII\n"]
+    with open(p, "wb") as f:
+        for i in range(30000):
+            if i % 4100 == 4099:
+                f.write(odd[(i // 4100) % len(odd)])
+            L = int(rng.integers(36, 120))
+            s = nt[rng.integers(0, 5, size=L)].tobytes()
+            q = bytes(rng.integers(35, 74, size=L).astype(np.uint8))
+            f.write(b"@r%d/1\n" % i + s + b"\n+\n" + q + b"\n")
+    assert both(p) > 30000
+    assert both(p, trim_qual=25) > 30000
+    assert both(p, mode=3 | 0x200, trim_qual=10, n_needed=9973) > 30000

@@ -1,0 +1,49 @@
+#!/usr/bin/env python
+"""Process-seam end-to-end check on the GPU box: `b200aln aln` vs `ibwa aln -t <cores>` on the same FASTQ
+and the cached 3.1 Gbp bench index (run bench.py once before).  Wall clock includes index load, parsing,
+the search and writing the .sai; the outputs must be byte-identical except header bytes 52..55.
+usage: python scripts/cli_e2e.py [n_reads] [ref_reads]"""
+import os
+import subprocess
+import sys
+import time
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+import bench  # noqa: E402
+
+
+def main():
+    import torch
+    n = int(sys.argv[1]) if len(sys.argv) > 1 else 4_000_000
+    n_ref = int(sys.argv[2]) if len(sys.argv) > 2 else 500_000
+    genome_bp, seed = 3_100_000_000, 20260102
+    dev = torch.device("cuda", 0)
+    bwt, rbwt, text, prefix = bench.load_or_build_index(genome_bp, seed, dev, True)
+    reads = bench.synth_reads_torch(text, n, 100, seed + 7).cpu().numpy()
+    del text, bwt, rbwt
+    torch.cuda.empty_cache()
+    fq, fq_ref = "/tmp/cli_e2e.fq", "/tmp/cli_e2e_ref.fq"
+    bench.write_fastq(fq, reads)
+    bench.write_fastq(fq_ref, reads[:n_ref])
+    exe = os.path.join(ROOT, "ibwa_b200", "b200aln")
+    cores = os.cpu_count()
+    for label, path, cnt in (("full", fq, n), ("ref-sized", fq_ref, n_ref)):
+        t0 = time.perf_counter()
+        subprocess.run([exe, "aln", "-f", f"/tmp/gpu_{label}.sai", prefix, path], stderr=subprocess.DEVNULL, check=True)
+        dt = time.perf_counter() - t0
+        print(f"b200aln aln ({label}: {cnt} reads): {dt:.2f} s wall = {cnt / dt / 1e6:.2f} M reads/s incl. index load")
+    t0 = time.perf_counter()
+    with open("/tmp/ref.sai", "wb") as fo:
+        subprocess.run([bench.REF_BIN, "aln", "-t", str(cores), prefix, fq_ref], stdout=fo, stderr=subprocess.DEVNULL,
+                       check=True)
+    dt = time.perf_counter() - t0
+    print(f"ibwa aln -t {cores} ({n_ref} reads): {dt:.2f} s wall = {n_ref / dt / 1e6:.3f} M reads/s incl. index load")
+    a, b = open("/tmp/ref.sai", "rb").read(), open("/tmp/gpu_ref-sized.sai", "rb").read()
+    same = a[:52] == b[:52] and a[56:] == b[56:]
+    print("byte-identical .sai (except n_threads):", same)
+    return 0 if same else 1
+
+
+if __name__ == "__main__":
+    sys.exit(main())

@@ -12,7 +12,7 @@ in include/b200aln.h.  There is no CPU fallback: importing ibwa_b200.engine and
 opening a context fails loudly when libb200aln.so is missing.
 """
 from .opts import GapOpt, gap_init_opt, parse_aln_args  # noqa: F401
-from .bwtio import Bwt, bwt_restore_bwt, bwt_dump_bwt   # noqa: F401
+from .bwtio import Bwt, Sa, bwt_restore_bwt, bwt_dump_bwt, bwt_restore_sa, bwt_dump_sa   # noqa: F401
 from . import sai                                        # noqa: F401
 
 __all__ = ["GapOpt", "gap_init_opt", "parse_aln_args", "Bwt", "bwt_restore_bwt", "bwt_dump_bwt", "sai"]

@@ -44,3 +44,34 @@ def bwt_dump_bwt(path: str, b: Bwt) -> None:
 def expected_words(seq_len: int) -> int:
     """Word count of the payload for a text of seq_len bases."""
     return (seq_len + 15) // 16 + 4 * ((seq_len + 127) // 128 + 1)
+
+
+@dataclass
+class Sa:
+    """Sampled suffix array as bwt_restore_sa leaves it (bwtio.c:29-49): sa[0] = 0xffffffff, sa[j] = SA(j * sa_intv)."""
+    primary: int
+    L2: np.ndarray
+    seq_len: int
+    sa_intv: int
+    sa: np.ndarray      # uint32[n_sa]
+
+
+def bwt_restore_sa(path: str) -> Sa:
+    raw = np.fromfile(path, dtype=np.uint32)
+    L2 = np.zeros(5, dtype=np.uint32)
+    L2[1:] = raw[1:5]
+    sa_intv, seq_len = int(raw[5]), int(raw[6])
+    n_sa = (seq_len + sa_intv) // sa_intv
+    sa = np.empty(n_sa, dtype=np.uint32)
+    sa[0] = 0xFFFFFFFF
+    sa[1:] = raw[7:7 + n_sa - 1]
+    return Sa(primary=int(raw[0]), L2=L2, seq_len=seq_len, sa_intv=sa_intv, sa=sa)
+
+
+def bwt_dump_sa(path: str, s: Sa) -> None:
+    """bwt_dump_sa (bwtio.c:17-27)."""
+    with open(path, "wb") as f:
+        np.array([s.primary], dtype=np.uint32).tofile(f)
+        np.asarray(s.L2[1:5], dtype=np.uint32).tofile(f)
+        np.array([s.sa_intv, s.seq_len], dtype=np.uint32).tofile(f)
+        np.asarray(s.sa[1:], dtype=np.uint32).tofile(f)

@@ -236,6 +236,39 @@ B2_HD void occ2x4(const FmView &f, uint32_t k, uint32_t l, uint32_t ck[4], uint3
     occ_count4(bb.cnt, bb.bits, qb & 63u, cl);
 }
 
+/* ---- SA row -> text position (scope row N2): bwt_sa / bwt_invPsi (bwt.c:69-79, bwt.h:66-70) -------------- */
+
+/* inverse Psi: row of the suffix one position to the left.  One occ block gives both the BWT character at
+ * the row and its count. */
+B2_HD uint32_t inv_psi(const FmView &f, uint32_t k)
+{
+    if (k == f.primary) return 0;
+    const uint32_t p = (k < f.primary ? k : k - 1u); /* index in the sentinel-free BWT string */
+    const OccBlk b = ld_blk(f.blk + (p >> 6));
+    const uint32_t j = p & 63u, wd = j >> 5, bit = j & 31u;
+    const uint32_t lo = wd ? b.bits.y : b.bits.x, hi = wd ? b.bits.w : b.bits.z;
+    const int c = (int)((lo >> bit & 1u) | (hi >> bit & 1u) << 1);
+    /* occurrences of c among the first j + 1 bases of the block */
+    const uint32_t sel_lo0 = (c & 1) ? b.bits.x : ~b.bits.x, sel_hi0 = (c & 2) ? b.bits.z : ~b.bits.z;
+    const uint32_t sel_lo1 = (c & 1) ? b.bits.y : ~b.bits.y, sel_hi1 = (c & 2) ? b.bits.w : ~b.bits.w;
+    const uint32_t m_in = bit == 31u ? 0xffffffffu : ((2u << bit) - 1u); /* bits 0..bit */
+    const uint32_t m0 = wd ? 0xffffffffu : m_in, m1 = wd ? m_in : 0u;
+    const uint32_t n = (uint32_t)(popc32(sel_lo0 & sel_hi0 & m0) + popc32(sel_lo1 & sel_hi1 & m1));
+    const uint32_t base = c == 0 ? b.cnt.x : c == 1 ? b.cnt.y : c == 2 ? b.cnt.z : b.cnt.w; /* L2[c] + before block */
+    return base + n;
+}
+
+/* bwt_sa: walk left until a sampled row (sa[0] == (uint32_t)-1 as in bwt_restore_sa, bwtio.c:45) */
+B2_HD uint32_t sa_of_row(const FmView &f, const uint32_t *sa, uint32_t sa_intv, uint32_t k)
+{
+    uint32_t steps = 0;
+    while (k % sa_intv != 0) {
+        ++steps;
+        k = inv_psi(f, k);
+    }
+    return steps + sa[k / sa_intv];
+}
+
 /* The SA intervals of the four one-character extensions of [k, l] (node `path` of index f):
  * nk[c] = L2[c] + occ(k-1, c) + 1, nl[c] = L2[c] + occ(l, c) (bwt.c:177-214, bwtgap.c:222-223),
  * read from the interval table while the node is inside it, from the occ blocks otherwise. */

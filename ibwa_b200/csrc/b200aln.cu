@@ -59,6 +59,24 @@ __global__ void k_lut_build(FmView f, uint32_t *lut, int level, uint64_t n_nodes
         lut_build_node(f, lut, level, X);
 }
 
+__global__ void __launch_bounds__(256) k_bwt_sa(FmView f, const uint32_t *sa, uint32_t sa_intv, int64_t n,
+                                                const uint32_t *rows, uint32_t *out)
+{ /* bwt_sa (bwt.c:69-79) for a batch of rows: one row per thread, ~sa_intv/2 dependent sector reads each */
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
+        out[i] = sa_of_row(f, sa, sa_intv, rows[i]);
+}
+
+__global__ void __launch_bounds__(256) k_sa2seq(FmView f0, const uint32_t *sa0, FmView f1, const uint32_t *sa1,
+                                                uint32_t sa_intv0, uint32_t sa_intv1, int64_t n,
+                                                const uint8_t *strand, const uint32_t *rows, const int32_t *lens,
+                                                uint64_t *out)
+{ /* bwtdb_sa2seq with offset 0 (dbset.c:240-245) */
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+        if (strand[i]) out[i] = (uint64_t)sa_of_row(f0, sa0, sa_intv0, rows[i]);
+        else out[i] = (uint64_t)(uint32_t)(f1.seq_len - (sa_of_row(f1, sa1, sa_intv1, rows[i]) + (uint32_t)lens[i]));
+    }
+}
+
 struct WidthArgs {
     FmView fm[2];
     int n_reads;               /* number of work items */
@@ -397,12 +415,15 @@ struct b200aln_ctx {
     int pop_batch = 1;     /* memory pops are taken when this many lanes of a warp wait for one */
     int lut_k = 14;        /* levels of the path-k-mer interval table (0 = off) */
     uint32_t *d_lut[2] = {nullptr, nullptr}; /* [0]: the table of both indexes */
+    uint32_t *d_sa[2] = {nullptr, nullptr}; /* sampled suffix arrays (.sa / .rsa), row N2 */
+    uint32_t sa_intv[2] = {0, 0};
+    uint64_t n_sa[2] = {0, 0};
     int lut_pin_levels = 10; /* top levels of the table kept persisting in L2 (0 = no window) */
     size_t lut_pin_bytes = 0;
     int batch_max_len = 0; /* > 0: the reference batch this call is a shard of has this longest read */
     /* device buffers */
     DevBuf lens, offs, codes, md, Q, W, n_amb, ent, recs, n_aln, over_slot, over_list, misc, off64,
-        blk_tot, packed, ent_big, recs_big, heads_wide, heads_wide_big, ent_mid, recs_mid, over_list2;
+        blk_tot, packed, ent_big, recs_big, heads_wide, heads_wide_big, ent_mid, recs_mid, over_list2, sa_in, sa_out;
     HostBuf h_in, h_out, h_misc;
     b200aln_stats_t stats;
 };
@@ -634,10 +655,11 @@ extern "C" void b200aln_close(b200aln_ctx *c)
     DevBuf *bufs[] = {&c->lens, &c->offs, &c->codes, &c->md, &c->Q, &c->W, &c->n_amb, &c->ent,
                       &c->recs, &c->n_aln, &c->over_slot, &c->over_list, &c->misc, &c->off64, &c->blk_tot,
                       &c->packed, &c->ent_big, &c->recs_big, &c->heads_wide, &c->heads_wide_big, &c->ent_mid, &c->recs_mid,
-                      &c->over_list2};
+                      &c->over_list2, &c->sa_in, &c->sa_out};
     for (DevBuf *b : bufs) b->release();
     c->h_in.release(); c->h_out.release(); c->h_misc.release();
     if (c->owns_index) {
+        for (int i = 0; i < 2; ++i) if (c->d_sa[i]) cudaFree(c->d_sa[i]);
         for (int i = 0; i < 2; ++i) if (c->d_idx[i]) cudaFree(c->d_idx[i]);
         for (int i = 0; i < 2; ++i) if (c->d_lut[i]) cudaFree(c->d_lut[i]);
     }
@@ -986,6 +1008,60 @@ extern "C" void b200aln_batch_device(b200aln_ctx *c, int n_reads, int max_len, c
     *d_n_aln = c->n_aln.as<int32_t>();
     *d_recs = c->packed.as<b200aln_rec_t>();
     *total = tot;
+}
+
+/* ---- row N2: SA row -> position ---------------------------------------------------------------------- */
+
+extern "C" void b200aln_sa_load(b200aln_ctx *c, int which, const b200aln_sa_view_t *v)
+{ /* bwt_restore_sa (bwtio.c:29-49) onto the device */
+    CK(cudaSetDevice(c->device));
+    if (which < 0 || which > 1) die("b200aln_sa_load", "which must be 0 (.sa) or 1 (.rsa).");
+    if (v->primary != c->fm[which].primary) die("b200aln_sa_load", "SA-BWT inconsistency: primary is not the same.");
+    if (v->seq_len != c->fm[which].seq_len) die("b200aln_sa_load", "SA-BWT inconsistency: seq_len is not the same.");
+    if (v->sa_intv <= 0) die("b200aln_sa_load", "bad SA interval.");
+    const uint64_t n_sa = ((uint64_t)v->seq_len + (uint64_t)v->sa_intv) / (uint64_t)v->sa_intv;
+    if (v->n_sa != n_sa) die("b200aln_sa_load", "SA has %llu samples, expected %llu.", (unsigned long long)v->n_sa, (unsigned long long)n_sa);
+    if (c->d_sa[which]) CK(cudaFree(c->d_sa[which]));
+    CK(cudaMalloc(&c->d_sa[which], n_sa * 4));
+    CK(cudaMemcpy(c->d_sa[which], v->sa, n_sa * 4, cudaMemcpyHostToDevice));
+    c->sa_intv[which] = (uint32_t)v->sa_intv;
+    c->n_sa[which] = n_sa;
+}
+
+extern "C" void b200aln_bwt_sa(b200aln_ctx *c, int which, int64_t n, const uint32_t *rows, uint32_t *pos)
+{
+    CK(cudaSetDevice(c->device));
+    if (which < 0 || which > 1 || !c->d_sa[which]) die("b200aln_bwt_sa", "no suffix array loaded for index %d.", which);
+    if (n <= 0) return;
+    c->sa_in.need((size_t)n * 4);
+    c->sa_out.need((size_t)n * 8);
+    CK(cudaMemcpyAsync(c->sa_in.p, rows, (size_t)n * 4, cudaMemcpyHostToDevice, c->st));
+    k_bwt_sa<<<c->n_sm * 8, 256, 0, c->st>>>(c->fm[which], c->d_sa[which], c->sa_intv[which], n, c->sa_in.as<uint32_t>(),
+                                            c->sa_out.as<uint32_t>());
+    CK(cudaGetLastError());
+    CK(cudaMemcpyAsync(pos, c->sa_out.p, (size_t)n * 4, cudaMemcpyDeviceToHost, c->st));
+    CK(cudaStreamSynchronize(c->st));
+}
+
+extern "C" void b200aln_sa2seq(b200aln_ctx *c, int64_t n, const uint8_t *strand, const uint32_t *rows, const int32_t *lens,
+                               uint64_t *pos)
+{
+    CK(cudaSetDevice(c->device));
+    if (!c->d_sa[0] || !c->d_sa[1]) die("b200aln_sa2seq", "both suffix arrays (.sa and .rsa) must be loaded.");
+    if (n <= 0) return;
+    c->sa_in.need((size_t)n * 9 + 64);
+    c->sa_out.need((size_t)n * 8);
+    uint32_t *d_rows = c->sa_in.as<uint32_t>();
+    int32_t *d_lens = (int32_t *)(d_rows + n);
+    uint8_t *d_strand = (uint8_t *)(d_lens + n);
+    CK(cudaMemcpyAsync(d_rows, rows, (size_t)n * 4, cudaMemcpyHostToDevice, c->st));
+    CK(cudaMemcpyAsync(d_lens, lens, (size_t)n * 4, cudaMemcpyHostToDevice, c->st));
+    CK(cudaMemcpyAsync(d_strand, strand, (size_t)n, cudaMemcpyHostToDevice, c->st));
+    k_sa2seq<<<c->n_sm * 8, 256, 0, c->st>>>(c->fm[0], c->d_sa[0], c->fm[1], c->d_sa[1], c->sa_intv[0], c->sa_intv[1], n,
+                                            d_strand, d_rows, d_lens, c->sa_out.as<uint64_t>());
+    CK(cudaGetLastError());
+    CK(cudaMemcpyAsync(pos, c->sa_out.p, (size_t)n * 8, cudaMemcpyDeviceToHost, c->st));
+    CK(cudaStreamSynchronize(c->st));
 }
 
 extern "C" double b200aln_sector_roofline(b200aln_ctx *c, uint64_t n_loads, int repeats)

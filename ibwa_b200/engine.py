@@ -38,6 +38,11 @@ class Stats(ctypes.Structure):
         return {n: getattr(self, n) for n, _ in self._fields_}
 
 
+class SaView(ctypes.Structure):
+    _fields_ = [("primary", ctypes.c_uint32), ("seq_len", ctypes.c_uint32), ("sa_intv", ctypes.c_int32),
+                ("n_sa", ctypes.c_uint64), ("sa", ctypes.c_void_p)]
+
+
 class SeqLayout(ctypes.Structure):
     _fields_ = [(n, ctypes.c_size_t) for n in ("size", "off_name", "off_seq", "off_rseq", "off_qual", "off_lenword",
                                                  "off_n_aln", "off_aln", "off_sa", "off_c1c2")]
@@ -46,7 +51,7 @@ class SeqLayout(ctypes.Structure):
 EXPORTS = ["b200aln_version", "b200aln_opt_init", "b200aln_cal_maxdiff", "b200aln_device_count", "b200aln_open",
            "b200aln_open_prefix", "b200aln_clone", "b200aln_close", "b200aln_batch", "b200aln_batch_device", "b200aln_last_stats",
            "b200aln_set_int", "b200aln_timer_start", "b200aln_timer_stop", "b200aln_cal_sa_reg_gap", "b200aln_seq_layout", "b200aln_aln_core", "b200aln_aln_main", "b200aln_reader_open", "b200aln_reader_next", "b200aln_reader_close",
-           "b200aln_sector_roofline"]
+           "b200aln_sector_roofline", "b200aln_sa_load", "b200aln_bwt_sa", "b200aln_sa2seq"]
 
 _lib = None
 
@@ -88,6 +93,10 @@ def load_library():
     L.b200aln_sector_roofline.restype = ctypes.c_double
     L.b200aln_sector_roofline.argtypes = [ctypes.c_void_p, ctypes.c_uint64, ctypes.c_int]
     L.b200aln_seq_layout.argtypes = [ctypes.POINTER(SeqLayout)]
+    L.b200aln_sa_load.argtypes = [ctypes.c_void_p, ctypes.c_int, ctypes.POINTER(SaView)]
+    L.b200aln_bwt_sa.argtypes = [ctypes.c_void_p, ctypes.c_int, ctypes.c_int64, ctypes.c_void_p, ctypes.c_void_p]
+    L.b200aln_sa2seq.argtypes = [ctypes.c_void_p, ctypes.c_int64, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p,
+                                 ctypes.c_void_p]
     L.b200aln_reader_open.restype = ctypes.c_void_p
     L.b200aln_reader_open.argtypes = [ctypes.c_char_p, ctypes.c_int]
     L.b200aln_reader_next.restype = ctypes.c_int
@@ -184,6 +193,32 @@ class Engine:
         self._L.b200aln_batch_device(self._ctx, n, max_len, d_lens, d_offs, d_codes, ctypes.byref(oc),
                                      ctypes.byref(pn), ctypes.byref(pr), ctypes.byref(total))
         return pn.value, pr.value, total.value
+
+    def load_sa(self, which: int, sa) -> None:
+        """bwt_restore_sa onto the device; sa: ibwa_b200.bwtio.Sa, which = 0 (.sa) or 1 (.rsa)."""
+        v = SaView()
+        v.primary, v.seq_len, v.sa_intv = sa.primary, sa.seq_len, sa.sa_intv
+        arr = np.ascontiguousarray(sa.sa, dtype=np.uint32)
+        v.n_sa = arr.shape[0]
+        v.sa = arr.ctypes.data
+        self._L.b200aln_sa_load(self._ctx, which, ctypes.byref(v))
+
+    def bwt_sa(self, which: int, rows) -> np.ndarray:
+        """bwt_sa (bwt.c:69-79) for a batch of SA rows."""
+        rows = np.ascontiguousarray(rows, dtype=np.uint32)
+        out = np.empty(len(rows), dtype=np.uint32)
+        self._L.b200aln_bwt_sa(self._ctx, which, len(rows), rows.ctypes.data, out.ctypes.data)
+        return out
+
+    def sa2seq(self, strand, rows, lens) -> np.ndarray:
+        """bwtdb_sa2seq with offset 0 (dbset.c:240-245)."""
+        strand = np.ascontiguousarray(strand, dtype=np.uint8)
+        rows = np.ascontiguousarray(rows, dtype=np.uint32)
+        lens = np.ascontiguousarray(lens, dtype=np.int32)
+        out = np.empty(len(rows), dtype=np.uint64)
+        self._L.b200aln_sa2seq(self._ctx, len(rows), strand.ctypes.data, rows.ctypes.data, lens.ctypes.data,
+                               out.ctypes.data)
+        return out
 
     def timer_start(self) -> None:
         self._L.b200aln_timer_start(self._ctx)

@@ -78,6 +78,25 @@ def build_bwt_numpy(text: np.ndarray) -> Bwt:
     return pack_reference_layout(b0, primary, counts)
 
 
+def build_bwt_sa_numpy(text: np.ndarray, sa_intv: int = 32):
+    """(Bwt, Sa) of a text: the .bwt payload and the sampled suffix array the reference's bwt_cal_sa /
+    `bwt2sa` produce (bwt.c:48-67: SA of every sa_intv-th row, row 0 = the sentinel suffix)."""
+    from .bwtio import Sa
+    t = np.ascontiguousarray(text, dtype=np.uint8)
+    n = len(t)
+    sa = _suffix_array_numpy(t)
+    primary = int(np.nonzero(sa == 0)[0][0]) + 1
+    prev = t[sa - 1]
+    keep = sa != 0
+    b0 = np.concatenate([[t[n - 1]], prev[keep]]).astype(np.uint8)
+    counts = np.bincount(t, minlength=4)[:4]
+    bwt = pack_reference_layout(b0, primary, counts)
+    rows = np.concatenate([[n], sa]).astype(np.uint64)          # SA over rows 0..n
+    samples = rows[::sa_intv].astype(np.uint32)
+    samples[0] = 0xFFFFFFFF
+    return bwt, Sa(primary=primary, L2=bwt.L2.copy(), seq_len=n, sa_intv=sa_intv, sa=samples)
+
+
 def build_index_numpy(text: np.ndarray):
     """(.bwt, .rbwt) of a text: the BWT of the text and of the reversed text (bwtindex.c:102-140)."""
     return build_bwt_numpy(text), build_bwt_numpy(np.ascontiguousarray(text[::-1]))

@@ -186,6 +186,27 @@ void b200aln_reader_close(b200aln_reader *r);
 /* Replaces bwa_aln (bwtaln.c:243-328): same getopt string and semantics. */
 int b200aln_aln_main(int argc, char *argv[]);
 
+/*
+ * Scope row N2 (next after the aln path): suffix-array row -> text position, the random-access step of
+ * samse / sampe (bwa_cal_pac_pos, bwase.c:136-161) on the same device index.
+ *   b200aln_sa_load   bwt_restore_sa (bwtio.c:29-49): `sa` is the array as restored (sa[0] = 0xffffffff,
+ *                     sa[j] = SA(j * sa_intv)), which = 0 for <prefix>.sa (with .bwt), 1 for .rsa (with .rbwt)
+ *   b200aln_bwt_sa    bwt_sa (bwt.c:69-79) for n rows at once (host buffers)
+ *   b200aln_sa2seq    bwtdb_sa2seq with offset 0 (dbset.c:240-245): strand != 0 -> bwt_sa(bwt, row),
+ *                     else rbwt.seq_len - (bwt_sa(rbwt, row) + len)
+ */
+typedef struct {
+    uint32_t primary;
+    uint32_t seq_len;
+    int32_t sa_intv;
+    uint64_t n_sa;
+    const uint32_t *sa;
+} b200aln_sa_view_t;
+void b200aln_sa_load(b200aln_ctx *ctx, int which, const b200aln_sa_view_t *sa);
+void b200aln_bwt_sa(b200aln_ctx *ctx, int which, int64_t n, const uint32_t *rows, uint32_t *pos);
+void b200aln_sa2seq(b200aln_ctx *ctx, int64_t n, const uint8_t *strand, const uint32_t *rows, const int32_t *lens,
+                    uint64_t *pos);
+
 /* Random 32-byte-sector gather micro-benchmark over the device index (the
  * roofline denominator of SURVEY.md §8d): n_loads independent uniformly random
  * sector reads; returns GB/s (sectors * 32 B / CUDA-event time). */

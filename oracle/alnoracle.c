@@ -21,6 +21,7 @@
  *   per-batch driver ............................ bwtaln.c:80-140
  *   read orientation (reverse / rev-comp) ....... bwaseqio.c:55-72,189-192
  *   quality trimming ............................ bwaseqio.c:74-87
+ *   SA row -> text position (row N2 of the scope) bwt.c:69-79, bwt.h:58-70, dbset.c:240-245
  *
  * Written from the behaviour described there, with its own data structures; it
  * additionally counts pops / occ lookups, which bench.py uses as the roofline
@@ -539,3 +540,47 @@ int64_t orc_aln_batch(const orc_bwt_t *bwt, const orc_bwt_t *rbwt, int n_reads, 
 }
 
 void orc_free(void *p) { free(p); }
+
+/* ------------------------------------------ SA row -> position (N2) ---- */
+
+typedef struct { /* bwt_restore_sa, bwtio.c:29-49: sa[0] = -1, sa[j] = SA(j * sa_intv) */
+    int32_t sa_intv;
+    uint64_t n_sa;
+    const uint32_t *sa;
+} orc_sa_t;
+
+/* character of the sentinel-free BWT string at index p (bwt.h:58-63) */
+static int bwt_char(const orc_bwt_t *b, uint32_t p)
+{
+    const uint32_t *blk = b->bwt + (uint64_t)(p / ORC_BLOCK) * ORC_BLOCK_WORDS;
+    uint32_t in = p % ORC_BLOCK;
+    return (int)(blk[4 + in / 16] >> (2 * (15 - in % 16)) & 3u);
+}
+
+/* inverse Psi (bwt.h:66-70): the row of the suffix one position to the left */
+static uint32_t inv_psi(const orc_bwt_t *b, uint32_t k)
+{
+    int c;
+    if (k == b->primary) return 0;
+    c = bwt_char(b, k < b->primary ? k : k - 1);
+    return b->L2[c] + orc_occ(b, k, c);
+}
+
+/* bwt_sa (bwt.c:69-79): walk left until a sampled row; note sa[0] == (uint32_t)-1 */
+uint32_t orc_bwt_sa(const orc_bwt_t *b, const orc_sa_t *s, uint32_t k)
+{
+    uint32_t steps = 0;
+    while (k % (uint32_t)s->sa_intv != 0) {
+        ++steps;
+        k = inv_psi(b, k);
+    }
+    return steps + s->sa[k / (uint32_t)s->sa_intv];
+}
+
+/* bwtdb_sa2seq with offset 0 (dbset.c:240-245): strand != 0 uses (bwt, sa), else (rbwt, rsa) */
+uint64_t orc_sa2seq(const orc_bwt_t *bwt, const orc_sa_t *sa, const orc_bwt_t *rbwt, const orc_sa_t *rsa, int strand,
+                    uint32_t row, int seq_len)
+{
+    if (strand) return (uint64_t)orc_bwt_sa(bwt, sa, row);
+    return (uint64_t)(uint32_t)(rbwt->seq_len - (orc_bwt_sa(rbwt, rsa, row) + (uint32_t)seq_len));
+}

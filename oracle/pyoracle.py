@@ -18,6 +18,10 @@ class OrcBwt(ctypes.Structure):
                 ("n_words", ctypes.c_uint64), ("bwt", ctypes.c_void_p)]
 
 
+class OrcSa(ctypes.Structure):
+    _fields_ = [("sa_intv", ctypes.c_int32), ("n_sa", ctypes.c_uint64), ("sa", ctypes.c_void_p)]
+
+
 class OrcStats(ctypes.Structure):
     _fields_ = [(n, ctypes.c_uint64) for n in
                 ("pops", "pushes", "lookups", "occ1_calls", "occ4_calls", "hits", "stack_hwm", "cutoff_reads",
@@ -57,6 +61,11 @@ def lib():
                                     ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p,
                                     ctypes.POINTER(ctypes.c_void_p)]
         L.orc_free.argtypes = [ctypes.c_void_p]
+        L.orc_bwt_sa.restype = ctypes.c_uint32
+        L.orc_bwt_sa.argtypes = [ctypes.POINTER(OrcBwt), ctypes.POINTER(OrcSa), ctypes.c_uint32]
+        L.orc_sa2seq.restype = ctypes.c_uint64
+        L.orc_sa2seq.argtypes = [ctypes.POINTER(OrcBwt), ctypes.POINTER(OrcSa), ctypes.POINTER(OrcBwt),
+                                 ctypes.POINTER(OrcSa), ctypes.c_int, ctypes.c_uint32, ctypes.c_int]
         L.orc_stats_get.argtypes = [ctypes.POINTER(OrcStats)]
         _lib = L
     return _lib
@@ -74,6 +83,23 @@ def as_orc_bwt(b) -> OrcBwt:
     o._keep = arr
     o.bwt = arr.ctypes.data
     return o
+
+
+def as_orc_sa(s) -> OrcSa:
+    """s: ibwa_b200.bwtio.Sa"""
+    o = OrcSa()
+    o.sa_intv = s.sa_intv
+    arr = np.ascontiguousarray(s.sa, dtype=np.uint32)
+    o._keep = arr
+    o.n_sa = arr.shape[0]
+    o.sa = arr.ctypes.data
+    return o
+
+
+def bwt_sa(ob: OrcBwt, osa: OrcSa, rows) -> np.ndarray:
+    L = lib()
+    return np.array([L.orc_bwt_sa(ctypes.byref(ob), ctypes.byref(osa), int(k) & 0xFFFFFFFF) for k in rows],
+                    dtype=np.uint32)
 
 
 def occ(ob: OrcBwt, k: int, c: int) -> int:

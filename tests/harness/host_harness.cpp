@@ -149,4 +149,14 @@ extern "C" int64_t hh_aln_batch(const b200aln_bwt_view_t *bwt, const b200aln_bwt
     return (int64_t)all.size();
 }
 
+/* row N2: the device inv_psi / sa_of_row code on the CPU */
+extern "C" void hh_bwt_sa(const b200aln_bwt_view_t *bwt, const uint32_t *sa, uint32_t sa_intv, int64_t n,
+                          const uint32_t *rows, uint32_t *out)
+{
+    std::vector<OccBlk> idx = convert(bwt);
+    FmView f;
+    f.blk = idx.data(); f.primary = bwt->primary; f.seq_len = bwt->seq_len; f.lut = nullptr; f.lut_k = 0; f.lut_w = 0;
+    for (int64_t i = 0; i < n; ++i) out[i] = sa_of_row(f, sa, sa_intv, rows[i]);
+}
+
 extern "C" void hh_free(void *p) { free(p); }

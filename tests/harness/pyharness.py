@@ -71,3 +71,14 @@ def aln_batch(bwt, rbwt, lens, offs, codes, opt_c, arena_cap=1 << 16, rec_cap=25
         else np.empty(0, ALN_DTYPE)
     L.hh_free(rec_p)
     return n_aln, rec, nov.value, {"pops": counters[0], "sectors": counters[1]}
+
+
+def bwt_sa(bwt, sa, rows):
+    L = lib()
+    rows = np.ascontiguousarray(rows, np.uint32)
+    arr = np.ascontiguousarray(sa.sa, np.uint32)
+    out = np.empty(len(rows), np.uint32)
+    v = view(bwt)
+    L.hh_bwt_sa(ctypes.byref(v), ctypes.c_void_p(arr.ctypes.data), ctypes.c_uint32(sa.sa_intv),
+                ctypes.c_int64(len(rows)), ctypes.c_void_p(rows.ctypes.data), ctypes.c_void_p(out.ctypes.data))
+    return out

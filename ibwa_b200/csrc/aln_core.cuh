@@ -55,27 +55,62 @@ struct alignas(32) StackEnt {
 };
 
 #if defined(__CUDA_ARCH__)
+#ifdef B2_L2_HINTS
+/* L2 eviction priorities: the 3 GB of occ blocks and the stack entries stream through (evict_first), so
+ * that the small per-read width records (evict_last) survive in L2 between the steps of a search */
+B2_D uint64_t pol_evict_first()
+{
+    uint64_t p;
+    asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(p));
+    return p;
+}
+B2_D uint64_t pol_evict_last()
+{
+    uint64_t p;
+    asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(p));
+    return p;
+}
+#endif
 B2_D OccBlk ld_blk(const OccBlk *p)
 { /* read-only index data: one 256-bit load on the non-coherent path, not allocated in L1
      (no reuse; keeps L1 for the per-read width records that ARE re-read along a chain) */
     OccBlk r;
+#ifdef B2_L2_HINTS
+    asm volatile("ld.global.nc.L1::no_allocate.L2::cache_hint.v8.u32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8], %9;"
+                 : "=r"(r.cnt.x), "=r"(r.cnt.y), "=r"(r.cnt.z), "=r"(r.cnt.w), "=r"(r.bits.x), "=r"(r.bits.y),
+                   "=r"(r.bits.z), "=r"(r.bits.w)
+                 : "l"(p), "l"(pol_evict_first()));
+#else
     asm volatile("ld.global.nc.L1::no_allocate.v8.u32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
                  : "=r"(r.cnt.x), "=r"(r.cnt.y), "=r"(r.cnt.z), "=r"(r.cnt.w), "=r"(r.bits.x), "=r"(r.bits.y),
                    "=r"(r.bits.z), "=r"(r.bits.w)
                  : "l"(p));
+#endif
     return r;
 }
 B2_D void ld_ent(const StackEnt *p, U4 &e, uint32_t &link, uint32_t &path)
 { /* stack entries: written once, read at most once -> L2 only */
     [[maybe_unused]] uint32_t p1, p2;
+#ifdef B2_L2_HINTS
+    asm volatile("ld.global.cg.L2::cache_hint.v8.u32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8], %9;"
+                 : "=r"(e.x), "=r"(e.y), "=r"(e.z), "=r"(e.w), "=r"(link), "=r"(path), "=r"(p1), "=r"(p2)
+                 : "l"(p), "l"(pol_evict_first()) : "memory");
+#else
     asm volatile("ld.global.cg.v8.u32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
                  : "=r"(e.x), "=r"(e.y), "=r"(e.z), "=r"(e.w), "=r"(link), "=r"(path), "=r"(p1), "=r"(p2)
                  : "l"(p) : "memory");
+#endif
 }
 B2_D void st_ent(StackEnt *p, U4 e, uint32_t link, uint32_t path)
 { /* a full sector per store: no read-modify-write in the memory system */
+#ifdef B2_L2_HINTS
+    asm volatile("st.global.cg.L2::cache_hint.v8.u32 [%0], {%1,%2,%3,%4,%5,%6,%7,%7}, %8;"
+                 :: "l"(p), "r"(e.x), "r"(e.y), "r"(e.z), "r"(e.w), "r"(link), "r"(path), "r"(0u), "l"(pol_evict_first())
+                 : "memory");
+#else
     asm volatile("st.global.cg.v8.u32 [%0], {%1,%2,%3,%4,%5,%6,%7,%7};"
                  :: "l"(p), "r"(e.x), "r"(e.y), "r"(e.z), "r"(e.w), "r"(link), "r"(path), "r"(0u) : "memory");
+#endif
 }
 struct alignas(32) U8x { uint32_t v[8]; };
 B2_D U8x ld_lut8(const void *p)
@@ -94,7 +129,11 @@ B2_D void st8(uint32_t *p, const uint32_t v[8])
 }
 B2_D uint32_t ld_q(const uint32_t *p)
 { /* width records: re-read along a chain (8 per sector) -> keep them in L1 */
-#ifdef B2_Q_EVICT_LAST
+#if defined(B2_Q_EVICT_LAST) && defined(B2_L2_HINTS)
+    uint32_t v;
+    asm volatile("ld.global.L1::evict_last.L2::cache_hint.u32 %0, [%1], %2;" : "=r"(v) : "l"(p), "l"(pol_evict_last()) : "memory");
+    return v;
+#elif defined(B2_Q_EVICT_LAST)
     uint32_t v;
     asm volatile("ld.global.L1::evict_last.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
     return v;

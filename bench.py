@@ -281,7 +281,17 @@ def time_port(bwt, rbwt, reads: np.ndarray, opt, n: int = 3000):
 
 # ----------------------------------------------------------------- main ------
 
+def _claim_stdout():
+    """Libraries (NCCL's version banner, for one) print to stdout; the contract is ONE JSON line there.
+    Keep the real stdout for that line and send everything else written to fd 1 to stderr."""
+    real = os.dup(1)
+    os.dup2(2, 1)
+    sys.stdout = os.fdopen(os.dup(2), "w", buffering=1)
+    return os.fdopen(real, "w", buffering=1)
+
+
 def main():
+    json_out = _claim_stdout()
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=5)
@@ -310,7 +320,8 @@ def main():
     use_dist = world > 1 and args.impl == "ours"
     if not torch.cuda.is_available():
         if args.impl == "reference":
-            print(json.dumps({"impl": "reference", "unavailable": "no CUDA device to synthesise the index with"}))
+            print(json.dumps({"impl": "reference", "unavailable": "no CUDA device to synthesise the index with"}),
+                  file=json_out, flush=True)
             return 0
         raise SystemExit("bench.py needs a CUDA device: the engine has no CPU fallback")
     torch.cuda.set_device(local_rank)
@@ -379,7 +390,7 @@ def main():
                 "cpu_baseline": {"value": v, "unit": "reads/s", "cores": nproc, "kind": kind, "sample": sample},
                 "e2e": {"value": v, "unit": "reads/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
                 "gpu_launches": 0}
-        print(json.dumps(line))
+        print(json.dumps(line), file=json_out, flush=True)
         return 0
 
     # ---- our arm ------------------------------------------------------------
@@ -541,7 +552,7 @@ def main():
                 out["cpu_baseline"] = {"value": port["reads_per_s"], "unit": "reads/s", "cores": 1, "kind": "port",
                                        "sample": f"{port['n']} reads, single-thread oracle port"}
         out["parity"] = parity
-        print(json.dumps(out))
+        print(json.dumps(out), file=json_out, flush=True)
     eng2.close()
     eng.close()
     if use_dist:

@@ -670,10 +670,39 @@ extern "C" int64_t b200aln_aln_core(const char *prefix, const char *fn_fa, const
     else for (int d = 0; d < b200aln_device_count(); ++d) devs.push_back(d);
     if (devs.empty()) b2host::fatal("b200aln_aln_core", "no CUDA device available; this engine has no CPU fallback.");
     std::vector<b200aln_ctx *> slot_ctx[2];
-    for (int d : devs) {
-        b200aln_ctx *c = b200aln_open_prefix(prefix, d);
-        slot_ctx[0].push_back(c);
-        slot_ctx[1].push_back(b200aln_clone(c));
+    {   /* bwt_restore_bwt x2 once (bwtio.c:51-70), then one upload per GPU in parallel */
+        std::vector<uint32_t> w[2];
+        b200aln_bwt_view_t v[2];
+        const char *ext[2] = {".bwt", ".rbwt"};
+        for (int j = 0; j < 2; ++j) {
+            const std::string fn = std::string(prefix) + ext[j];
+            FILE *fp = fopen(fn.c_str(), "rb");
+            if (!fp) b2host::fatal("b200aln_aln_core", (std::string("fail to open file '") + fn + "'.").c_str());
+            fseek(fp, 0, SEEK_END);
+            const long sz = ftell(fp);
+            fseek(fp, 0, SEEK_SET);
+            uint32_t hdr[5];
+            if (sz < 20 || fread(hdr, 4, 5, fp) != 5) b2host::fatal("b200aln_aln_core", "truncated BWT file.");
+            const size_t nw = ((size_t)sz - 20) >> 2;
+            w[j].resize(nw);
+            if (nw && fread(w[j].data(), 4, nw, fp) != nw) b2host::fatal("b200aln_aln_core", "truncated BWT file.");
+            fclose(fp);
+            v[j].primary = hdr[0];
+            v[j].L2[0] = 0;
+            for (int i = 0; i < 4; ++i) v[j].L2[i + 1] = hdr[1 + i];
+            v[j].seq_len = v[j].L2[4];
+            v[j].bwt_size = nw;
+            v[j].bwt = w[j].data();
+        }
+        slot_ctx[0].resize(devs.size());
+        slot_ctx[1].resize(devs.size());
+        std::vector<std::thread> th;
+        for (size_t i = 0; i < devs.size(); ++i)
+            th.emplace_back([&, i]() {
+                slot_ctx[0][i] = b200aln_open(&v[0], &v[1], devs[i]);
+                slot_ctx[1][i] = b200aln_clone(slot_ctx[0][i]);
+            });
+        for (auto &t : th) t.join();
     }
     FILE *out = fdopen(dup(out_fd), "wb");
     if (!out) b2host::fatal("b200aln_aln_core", "cannot open the output descriptor.");

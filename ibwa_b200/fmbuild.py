@@ -120,7 +120,7 @@ def _kmer31_chunk(t, s: int, e: int, n: int):
     return key
 
 
-def build_bwt_torch(t, bucket_bits: int = 4, chunk: int = 1 << 26) -> Bwt:
+def build_bwt_torch(t, bucket_bits: int = 4, chunk: int = 1 << 26, sa_intv: int = 0):
     """BWT of a near-random text on the GPU: sort suffixes by their first 31 bases (62-bit keys,
     one radix sort per leading-bases bucket), resolve the few remaining ties exactly.
     t: torch uint8 tensor (values 0..3), normally on a CUDA device."""
@@ -154,6 +154,12 @@ def build_bwt_torch(t, bucket_bits: int = 4, chunk: int = 1 << 26) -> Bwt:
     del k31
     assert at == n
     primary = int(torch.nonzero(sa == 0).reshape(-1)[0].item()) + 1
+    sa_obj = None
+    if sa_intv:                                   # sampled suffix array like bwt_cal_sa (bwt.c:48-67)
+        from .bwtio import Sa
+        samples = torch.cat([torch.tensor([0xFFFFFFFF], dtype=torch.int64, device=dev), sa[sa_intv - 1::sa_intv]])
+        sa_obj = Sa(primary=primary, L2=None, seq_len=n, sa_intv=sa_intv,
+                    sa=samples.cpu().numpy().astype(np.uint32))
     sa -= 1
     sa[primary - 1] = n - 1                       # placeholder for the dropped row
     prev = t[sa]
@@ -161,7 +167,11 @@ def build_bwt_torch(t, bucket_bits: int = 4, chunk: int = 1 << 26) -> Bwt:
     keep[primary - 1] = False
     b0 = torch.cat([t[n - 1:n], prev[keep]])
     del sa, prev, keep
-    return _pack_reference_layout_torch(b0, primary, counts)
+    bwt = _pack_reference_layout_torch(b0, primary, counts)
+    if sa_obj is not None:
+        sa_obj.L2 = bwt.L2.copy()
+        return bwt, sa_obj
+    return bwt
 
 
 def _fix_ties(t, seg, skeys, n):

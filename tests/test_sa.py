@@ -83,3 +83,48 @@ def test_gpu_bwt_sa_and_sa2seq():
     want_pos = np.where(strand != 0, got0.astype(np.uint64),
                         ((np.uint64(len(t)) - (got1.astype(np.uint64) + lens.astype(np.uint64))) & np.uint64(0xFFFFFFFF)))
     assert np.array_equal(pos, want_pos)
+
+
+@pytest.mark.gpu
+def test_full_pipeline_property_at_scale():
+    """Size-independent property at a larger size (no oracle): reads cut from a 50 Mbp genome without
+    errors must come back from aln with a score-0 record whose SA interval, mapped through row N2
+    (bwt_sa / sa2seq), contains the position they were cut from — on the right strand."""
+    import torch
+    from ibwa_b200 import engine, gap_init_opt, sai
+    n_g, n, L = 50_000_000, 200_000, 100
+    dev = torch.device("cuda", 0)
+    g = torch.Generator(device=dev)
+    g.manual_seed(123)
+    text = torch.randint(0, 4, (n_g,), dtype=torch.uint8, device=dev, generator=g)
+    bwt, sa = fmbuild.build_bwt_torch(text, sa_intv=32)
+    rbwt, rsa = fmbuild.build_bwt_torch(torch.flip(text, dims=[0]), sa_intv=32)
+    start = torch.randint(0, n_g - L, (n,), device=dev, generator=g)
+    reads = text[start[:, None] + torch.arange(L, device=dev)[None, :]]
+    rc = torch.rand(n, device=dev, generator=g) < 0.5
+    reads = torch.where(rc[:, None], 3 - torch.flip(reads, dims=[1]), reads)
+    reads_h, start_h, rc_h = reads.cpu().numpy(), start.cpu().numpy(), rc.cpu().numpy()
+    del text, reads, start
+    torch.cuda.empty_cache()
+    lens = np.full(n, L, np.int32)
+    offs = np.arange(n, dtype=np.int64) * L
+    with engine.Engine(bwt, rbwt, 0) as e:
+        n_aln, rec = e.cal_sa_reg_gap(lens, offs, reads_h.reshape(-1), gap_init_opt())
+        e.load_sa(0, sa)
+        e.load_sa(1, rsa)
+        assert (n_aln >= 1).all()
+        first = np.concatenate([[0], np.cumsum(n_aln)[:-1]])
+        u = sai.unpack(rec)
+        # records of a read come out in non-decreasing score order (bwase.c:39-42 relies on it)
+        read_of = np.repeat(np.arange(n), n_aln)
+        same_read = read_of[1:] == read_of[:-1]
+        assert (u["score"][1:][same_read] >= u["score"][:-1][same_read]).all()
+        best = rec[first]
+        bu = sai.unpack(best)
+        assert (bu["score"] == 0).all() and (bu["n_mm"] == 0).all() and (bu["n_gapo"] == 0).all()
+        assert np.array_equal(bu["a"].astype(bool), rc_h)        # strand 1 <=> the read was reverse-complemented
+        width = bu["l"].astype(np.int64) - bu["k"].astype(np.int64) + 1
+        assert (width >= 1).all() and (width == 1).mean() > 0.999     # 100-mers of a random 50 Mbp text are unique
+        uniq = width == 1
+        pos = e.sa2seq(bu["a"][uniq].astype(np.uint8), bu["k"][uniq], lens[uniq])
+    assert np.array_equal(pos.astype(np.int64), start_h[uniq])

@@ -305,6 +305,8 @@ def main():
     ap.add_argument("--model", default="default", choices=["default", "stress"],
                     help="read model (SURVEY §8d); 'stress' + --read-len 150 + --aln-args = BASELINE configs[2]")
     ap.add_argument("--aln-args", default="", help="aln options for the run, e.g. '-n 4 -o 2 -e 10 -l 32 -k 2'")
+    ap.add_argument("--in-flight", type=int, default=2,
+                    help="batches in flight in the e2e measurement (contexts sharing the device index)")
     ap.add_argument("--set", action="append", default=[], help="engine knob key=value")
     args = ap.parse_args()
 
@@ -422,11 +424,12 @@ def main():
 
     # end-to-end: two batches in flight (engine + clone sharing the device index, one host thread each),
     # so the H2D / D2H copies of one step overlap the kernels of the other (double buffering)
-    eng2 = eng.clone()
-    h_naln2 = torch.empty(n, dtype=torch.int32).pin_memory()
+    K = max(1, args.in_flight)
+    engines = [eng] + [eng.clone() for _ in range(K - 1)]
+    outs = [h_naln] + [torch.empty(n, dtype=torch.int32).pin_memory() for _ in range(K - 1)]
 
     def step_e2e(which=0):
-        e, out = (eng, h_naln) if which == 0 else (eng2, h_naln2)
+        e, out = engines[which], outs[which]
         _, total = e.batch_pinned(h_lens.data_ptr(), h_offs.data_ptr(), h_codes.data_ptr(), n, opt, out.data_ptr())
         return total, e.stats()
 
@@ -434,12 +437,12 @@ def main():
         results = [None] * steps
 
         def worker(which):
-            for i in range(which, steps, 2):
+            for i in range(which, steps, K):
                 results[i] = step_e2e(which)
 
         barrier()
         eng.timer_start()
-        th = [threading.Thread(target=worker, args=(w,)) for w in (0, 1)]
+        th = [threading.Thread(target=worker, args=(w,)) for w in range(K)]
         for t in th:
             t.start()
         for t in th:
@@ -472,7 +475,7 @@ def main():
     sampler.start()
     ms_dev, st_dev = timed(step_device, args.steps)
     clocks = sampler.stop()
-    for w in range(2):          # both in-flight engines allocate their buffers outside the timed region
+    for w in range(K):          # every in-flight engine allocates its buffers outside the timed region
         step_e2e(w)
     ms_e2e, st_e2e = timed_e2e(args.steps)
 
@@ -489,7 +492,7 @@ def main():
            "config": config, "clocks": clocks,
            "e2e": {"value": e2e_value, "unit": "reads/s", "h2d_bytes_per_step": int(n * 12 + n * L),
                    "d2h_bytes_per_step": int(n * 4 + total_rec * 16), "ms_per_step": ms_e2e / args.steps,
-                   "in_flight": 2},
+                   "in_flight": K},
            "gpu_launches": launches,
            "kernel_ms": {k: float(np.mean([s[k] for s in st_dev])) for k in
                          ("ms_width", "ms_search", "ms_compact", "ms_total")},
@@ -553,7 +556,8 @@ def main():
                                        "sample": f"{port['n']} reads, single-thread oracle port"}
         out["parity"] = parity
         print(json.dumps(out), file=json_out, flush=True)
-    eng2.close()
+    for e in engines[1:]:
+        e.close()
     eng.close()
     if use_dist:
         dist.destroy_process_group()

@@ -669,7 +669,14 @@ extern "C" int64_t b200aln_aln_core(const char *prefix, const char *fn_fa, const
     if (device >= 0) devs.push_back(device);
     else for (int d = 0; d < b200aln_device_count(); ++d) devs.push_back(d);
     if (devs.empty()) b2host::fatal("b200aln_aln_core", "no CUDA device available; this engine has no CPU fallback.");
-    std::vector<b200aln_ctx *> slot_ctx[2];
+    int n_slots = 2; /* batches in flight per GPU; more hide the long tail of heavy option sets (B200ALN_INFLIGHT) */
+    {
+        const char *e = getenv("B200ALN_INFLIGHT");
+        if (e) n_slots = atoi(e);
+        if (n_slots < 1) n_slots = 1;
+        if (n_slots > 8) n_slots = 8;
+    }
+    std::vector<std::vector<b200aln_ctx *>> slot_ctx((size_t)n_slots);
     {   /* bwt_restore_bwt x2 once (bwtio.c:51-70), then one upload per GPU in parallel */
         std::vector<uint32_t> w[2];
         b200aln_bwt_view_t v[2];
@@ -694,13 +701,12 @@ extern "C" int64_t b200aln_aln_core(const char *prefix, const char *fn_fa, const
             v[j].bwt_size = nw;
             v[j].bwt = w[j].data();
         }
-        slot_ctx[0].resize(devs.size());
-        slot_ctx[1].resize(devs.size());
+        for (auto &sc : slot_ctx) sc.resize(devs.size());
         std::vector<std::thread> th;
         for (size_t i = 0; i < devs.size(); ++i)
             th.emplace_back([&, i]() {
                 slot_ctx[0][i] = b200aln_open(&v[0], &v[1], devs[i]);
-                slot_ctx[1][i] = b200aln_clone(slot_ctx[0][i]);
+                for (int sl = 1; sl < n_slots; ++sl) slot_ctx[(size_t)sl][i] = b200aln_clone(slot_ctx[0][i]);
             });
         for (auto &t : th) t.join();
     }
@@ -734,17 +740,15 @@ extern "C" int64_t b200aln_aln_core(const char *prefix, const char *fn_fa, const
         const int n = rd.next(0x40000, opt->mode, opt->trim_qual, *b);
         if (n == 0) break;
         tot_seqs += n;
-        const std::vector<b200aln_ctx *> *ctxs = &slot_ctx[seq & 1];
-        if (inflight.size() == 2) drain_one(); /* the slot's previous batch is finished and written */
+        const std::vector<b200aln_ctx *> *ctxs = &slot_ctx[(size_t)(seq % n_slots)];
+        if ((int)inflight.size() == n_slots) drain_one(); /* the slot's previous batch is finished and written */
         inflight.push_back(std::async(std::launch::async, [ctxs, b, opt]() { return process_batch(*ctxs, *b, opt); }));
         ++seq;
     }
     while (!inflight.empty()) drain_one();
     fclose(out);
-    for (size_t i = 0; i < devs.size(); ++i) {
-        b200aln_close(slot_ctx[1][i]);
-        b200aln_close(slot_ctx[0][i]);
-    }
+    for (size_t i = 0; i < devs.size(); ++i)
+        for (int sl = n_slots - 1; sl >= 0; --sl) b200aln_close(slot_ctx[(size_t)sl][i]);
     return tot_seqs;
 }
 

@@ -142,9 +142,16 @@ B2_D uint32_t ld_q(const uint32_t *p)
 #endif
 }
 B2_D void prefetch_l2(const void *p) { asm volatile("prefetch.global.L2 [%0];" :: "l"(p)); }
+B2_D void ld8(const uint32_t *p, uint32_t v[8])
+{ /* eight consecutive words of a 32-byte aligned row */
+    asm volatile("ld.global.v8.u32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                 : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7])
+                 : "l"(p) : "memory");
+}
 B2_D int popc32(uint32_t v) { return __popc(v); }
 B2_D int ctz32(uint32_t v) { return __ffs((int)v) - 1; }
 #else
+inline void ld8(const uint32_t *p, uint32_t v[8]) { for (int i = 0; i < 8; ++i) v[i] = p[i]; }
 inline void prefetch_l2(const void *) {}
 inline uint32_t ld_q(const uint32_t *p) { return *p; }
 inline void st8(uint32_t *p, const uint32_t v[8]) { for (int i = 0; i < 8; ++i) p[i] = v[i]; }
@@ -481,26 +488,42 @@ B2_HD int width_pass(const FmView &f, const uint8_t *fwd, int len, int a, bool c
     return n_amb;
 }
 
-/* gap_shadow (bwtgap.c:81-91) on the split representation, then refresh the
- * packed records it invalidated.  bid lives in Q; w in W. */
+/* gap_shadow (bwtgap.c:81-91) on the split representation (bid lives in Q, w in W), fused with the
+ * refresh of the packed fields it invalidates (bid[j-1] and w[j-1]==w[j] of records 1..last_diff_pos).
+ * Rows are walked one 32-byte sector at a time: W and Q rows are 32-byte aligned and padded to a
+ * multiple of eight entries, so whole sectors can be read and written back. */
 B2_HD void shadow_update(uint32_t x, uint32_t max, int last_diff_pos, int len, uint32_t *W, QRec *Q)
 {
+    if (last_diff_pos <= 0) return;
+    const int last = last_diff_pos < len ? last_diff_pos : len - 1; /* last record whose packed fields can change */
     int j = 0;
-    for (int i = 0; i < last_diff_pos; ++i) {
-        uint32_t w = W[i];
-        if (w > x) W[i] = w - x;
-        else if (w == x) {
-            W[i] = max - (uint32_t)(++j);
-            Q[i] = (Q[i] & ~(0xffu << 16)) | 1u << 16; /* bid[i] = 1 */
+    uint32_t prev_w = 0, prev_bid = 0;
+    for (int i0 = 0; i0 <= last; i0 += 8) {
+        uint32_t w8[8], q8[8];
+        ld8(W + i0, w8);
+        ld8(Q + i0, q8);
+#if defined(__CUDA_ARCH__)
+#pragma unroll
+#endif
+        for (int t = 0; t < 8; ++t) {
+            const int i = i0 + t;
+            uint32_t w = w8[t], q = q8[t];
+            if (i < last_diff_pos) { /* bwtgap.c:84-89 */
+                if (w > x) w -= x;
+                else if (w == x) {
+                    w = max - (uint32_t)(++j);
+                    q = (q & ~(0xffu << 16)) | 1u << 16; /* bid[i] = 1 */
+                }
+            }
+            if (i >= 1 && i <= last) /* bid[i-1] and the equal-width flag as the search reads them */
+                q = (q & ~(0xffu << 24 | 1u << 3)) | prev_bid << 24 | (uint32_t)(w == prev_w) << 3;
+            prev_w = w;
+            prev_bid = q >> 16 & 0xffu;
+            w8[t] = w;
+            q8[t] = q;
         }
-    }
-    /* refresh eq / bid[j-1] of records 1..last_diff_pos (record ldp sees W[ldp-1]) */
-    const int last = last_diff_pos < len ? last_diff_pos : len - 1; /* Q has len records */
-    for (int i = 1; i <= last; ++i) {
-        QRec q = Q[i];
-        uint32_t bidp = Q[i - 1] >> 16 & 0xffu;
-        uint32_t eq = W[i] == W[i - 1];
-        Q[i] = (q & ~(0xffu << 24 | 1u << 3)) | bidp << 24 | eq << 3;
+        st8(W + i0, w8);
+        st8(Q + i0, q8);
     }
 }
 

@@ -82,3 +82,37 @@ def test_interval_table_is_exact(tag, lut_k, golden_dir, g1_index):
                            arena_cap=65000, rec_cap=4096, lut_k=lut_k)
     assert nov == 0
     assert got == open(os.path.join(golden_dir, f"g1_{tag}.sai"), "rb").read()
+
+
+def _vs_oracle(bwt, rbwt, reads, args, **kw):
+    from oracle import pyoracle
+    opt, _, _, _ = parse_aln_args(args + ["p", "q"])
+    lens = np.array([len(r) for r in reads], np.int32)
+    offs = np.concatenate([[0], np.cumsum(lens)[:-1]]).astype(np.int64)
+    codes = np.concatenate(reads) if len(reads) and lens.sum() else np.empty(0, np.uint8)
+    o_n, o_rec, _ = pyoracle.aln_batch(pyoracle.as_orc_bwt(bwt), pyoracle.as_orc_bwt(rbwt), lens, offs, codes, opt.to_c())
+    h_n, h_rec, nov, _ = pyharness.aln_batch(bwt, rbwt, lens, offs, codes, opt.to_c(), **kw)
+    assert nov == 0
+    assert np.array_equal(o_n, h_n) and o_rec.tobytes() == h_rec.tobytes()
+    return o_n
+
+
+def test_long_reads_and_wide_score_ranges(golden_dir, g1_index):
+    """1 kbp and 3 kbp reads: max_diff 23 / 75, i.e. 143 and 275 score buckets (the second needs the wide
+    heads); also an empty read, which BAM input can deliver (the reference then reports the whole index)."""
+    import gzip
+    txt = gzip.open(os.path.join(golden_dir, "g1.fa.gz")).read().split(b"\n", 1)[1].replace(b"\n", b"")
+    g = seqio.NT4[np.frombuffer(txt, dtype=np.uint8)]
+    rng = np.random.default_rng(3)
+    reads = []
+    for L in (1000, 1000, 3000, 3000, 0, 7):
+        s = int(rng.integers(50_000, len(g) - L - 1))
+        r = g[s:s + L].copy()
+        if L > 100:
+            sub = rng.random(L) < 0.004
+            r[sub] = (r[sub] + 1) & 3
+        reads.append(r)
+    n_aln = _vs_oracle(g1_index[0], g1_index[1], reads[:2], [], arena_cap=60000, rec_cap=64, lut_k=5)
+    assert (n_aln > 0).all()
+    _vs_oracle(g1_index[0], g1_index[1], reads, [], arena_cap=1 << 20, rec_cap=64, lut_k=5)
+    _vs_oracle(g1_index[0], g1_index[1], reads, ["-n", "9", "-o", "2"], arena_cap=1 << 20, rec_cap=64)

@@ -263,3 +263,30 @@ def test_cli_bam_input(tmp_path, golden_dir):
         pyoracle.run_ref(["aln"] + flags + [prefix, bam], stdout_path=ref_out)
         subprocess.check_call([exe, "aln"] + flags + ["-f", out, prefix, bam], stderr=subprocess.DEVNULL)
         assert open(out, "rb").read() == open(ref_out, "rb").read()
+
+
+def test_long_reads_wide_heads_and_empty_read(g1_index, golden_dir):
+    """3 kbp reads (275 score buckets: 32-bit heads in global memory on the fast pass), 1 kbp reads, an empty
+    read and a 7-bp read in one batch, against the oracle."""
+    import gzip as gz
+    txt = gz.open(os.path.join(golden_dir, "g1.fa.gz")).read().split(b"\n", 1)[1].replace(b"\n", b"")
+    g = seqio.NT4[np.frombuffer(txt, dtype=np.uint8)]
+    rng = np.random.default_rng(3)
+    reads = []
+    for L in (1000, 1000, 3000, 3000, 0, 7) * 20:
+        s = int(rng.integers(50_000, len(g) - L - 1))
+        r = g[s:s + L].copy()
+        if L > 100:
+            sub = rng.random(L) < 0.004
+            r[sub] = (r[sub] + 1) & 3
+        reads.append(r)
+    lens = np.array([len(r) for r in reads], np.int32)
+    offs = np.concatenate([[0], np.cumsum(lens)[:-1]]).astype(np.int64)
+    codes = np.concatenate(reads)
+    for args in ([], ["-n", "9", "-o", "2"]):
+        opt, _, _, _ = parse_aln_args(args + ["p", "q"])
+        with engine.Engine(g1_index[0], g1_index[1], 0) as e:
+            n_aln, rec = e.cal_sa_reg_gap(lens, offs, codes, opt)
+        o_n, o_rec, _ = pyoracle.aln_batch(pyoracle.as_orc_bwt(g1_index[0]), pyoracle.as_orc_bwt(g1_index[1]), lens, offs,
+                                           codes, opt.to_c())
+        assert np.array_equal(n_aln, o_n) and rec.tobytes() == o_rec.tobytes()

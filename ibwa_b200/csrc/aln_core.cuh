@@ -47,11 +47,24 @@ struct alignas(32) OccBlk {
     U4 bits; /* lo0, lo1, hi0, hi1 */
 };
 
-/* one stack entry = one 32-byte sector, written and read with single 256-bit accesses */
-struct alignas(32) StackEnt {
-    U4 e;          /* k, l, i | ldp<<16, n_mm | n_gapo<<8 | n_gape<<16 | state<<24 | a<<26 */
-    uint32_t link; /* previous entry of the same bucket (or next free slot) */
-    uint32_t pad[3]; /* pad[0]: path word (depth | k-mer << 5) while the entry is inside the interval table */
+/*
+ * One stack record = the children of ONE expansion (bwtgap.c:216-258), 64 bytes = one aligned pair of
+ * sectors (one DRAM transaction: L2 fills are 64 bytes wide).  The reference pushes the children of an
+ * expansion as two runs of consecutive entries: the gap group (insertion + deletions, or one gap
+ * extension) into bucket score + s_gapo / s_gape and the mismatch group into bucket score + s_mm.  All
+ * of them are the parent's interval or one of the same four child intervals, so the record stores the
+ * parent and the four children once and is linked into both buckets.
+ *   w[0] link of the gap group   w[1] link of the mismatch group   (bucket lists; w[0] = free list)
+ *   w[2] parent's position in the interval table (path word)
+ *   w[3] i | base << 16 | parent state << 19 | strand << 21 | gap mask << 22 | mismatch mask << 27
+ *        (masks: bit c = child c is a member, bit 4 of the gap mask = the insertion)
+ *   w[4] parent's n_mm | n_gapo << 8 | n_gape << 16      w[5], w[6] parent's k, l
+ *   w[7] set once one of the two groups has been taken (free-list arenas only)
+ *   w[8..15] children: k0, l0, k1, l1, k2, l2, k3, l3
+ * A bucket head or link is (slot << 1 | group), group 0 = gap, 1 = mismatch.
+ */
+struct alignas(64) StackRec {
+    uint32_t w[16];
 };
 
 #if defined(__CUDA_ARCH__)
@@ -88,29 +101,11 @@ B2_D OccBlk ld_blk(const OccBlk *p)
 #endif
     return r;
 }
-B2_D void ld_ent(const StackEnt *p, U4 &e, uint32_t &link, uint32_t &path)
-{ /* stack entries: written once, read at most once -> L2 only */
-    [[maybe_unused]] uint32_t p1, p2;
-#ifdef B2_L2_HINTS
-    asm volatile("ld.global.cg.L2::cache_hint.v8.u32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8], %9;"
-                 : "=r"(e.x), "=r"(e.y), "=r"(e.z), "=r"(e.w), "=r"(link), "=r"(path), "=r"(p1), "=r"(p2)
-                 : "l"(p), "l"(pol_evict_first()) : "memory");
-#else
+B2_D void ld8cg(const uint32_t *p, uint32_t v[8])
+{ /* stack records: written once, read at most twice -> L2 only */
     asm volatile("ld.global.cg.v8.u32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
-                 : "=r"(e.x), "=r"(e.y), "=r"(e.z), "=r"(e.w), "=r"(link), "=r"(path), "=r"(p1), "=r"(p2)
+                 : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7])
                  : "l"(p) : "memory");
-#endif
-}
-B2_D void st_ent(StackEnt *p, U4 e, uint32_t link, uint32_t path)
-{ /* a full sector per store: no read-modify-write in the memory system */
-#ifdef B2_L2_HINTS
-    asm volatile("st.global.cg.L2::cache_hint.v8.u32 [%0], {%1,%2,%3,%4,%5,%6,%7,%7}, %8;"
-                 :: "l"(p), "r"(e.x), "r"(e.y), "r"(e.z), "r"(e.w), "r"(link), "r"(path), "r"(0u), "l"(pol_evict_first())
-                 : "memory");
-#else
-    asm volatile("st.global.cg.v8.u32 [%0], {%1,%2,%3,%4,%5,%6,%7,%7};"
-                 :: "l"(p), "r"(e.x), "r"(e.y), "r"(e.z), "r"(e.w), "r"(link), "r"(path), "r"(0u) : "memory");
-#endif
 }
 struct alignas(32) U8x { uint32_t v[8]; };
 B2_D U8x ld_lut8(const void *p)
@@ -156,8 +151,7 @@ inline void prefetch_l2(const void *) {}
 inline uint32_t ld_q(const uint32_t *p) { return *p; }
 inline void st8(uint32_t *p, const uint32_t v[8]) { for (int i = 0; i < 8; ++i) p[i] = v[i]; }
 inline OccBlk ld_blk(const OccBlk *p) { return *p; }
-inline void ld_ent(const StackEnt *p, U4 &e, uint32_t &link, uint32_t &path) { e = p->e; link = p->link; path = p->pad[0]; }
-inline void st_ent(StackEnt *p, U4 e, uint32_t link, uint32_t path) { p->e = e; p->link = link; p->pad[0] = path; p->pad[1] = p->pad[2] = 0; }
+inline void ld8cg(const uint32_t *p, uint32_t v[8]) { for (int i = 0; i < 8; ++i) v[i] = p[i]; }
 struct alignas(32) U8x { uint32_t v[8]; };
 inline U8x ld_lut8(const void *p) { return *reinterpret_cast<const U8x *>(p); }
 inline int popc32(uint32_t v) { return __builtin_popcount(v); }
@@ -538,12 +532,24 @@ extern uint64_t b2_dbg[16];
 #define B2_DBG(i) ((void)0)
 #endif
 
-/* per-lane arena in global memory: 32-byte entries, bump allocated (optionally with a
- * free list through the link words, REUSE) */
+/* per-lane arena in global memory: 64-byte records, bump allocated (optionally with a
+ * free list through w[0], REUSE) */
 struct Arena {
-    StackEnt *ent; /* [cap] */
+    StackRec *ent; /* [cap] */
     uint32_t cap;
 };
+
+/* The open group of a lane — the members of the group popped last that have not been taken yet — lives
+ * outside the lane's registers: words at p[w * stride] (a shared-memory column on the device, a plain
+ * array in the CPU harness).  Words 0-7 the four child intervals, 8-9 the parent's interval, 10 its path. */
+struct GroupStore {
+    uint32_t *p;
+    int stride;
+    B2_HD uint32_t get(int w) const { return p[(size_t)w * stride]; }
+    B2_HD void set(int w, uint32_t v) { p[(size_t)w * stride] = v; }
+};
+enum { OG_PK = 8, OG_PL = 9, OG_PATH = 10, OG_WORDS = 11 };
+enum { GRP_NONE = 0, GRP_X = 1, GRP_G = 2, GRP_ROOT = 3 };
 
 /* Bucket heads (top slot of each score bucket's linked list) and the set of
  * non-empty buckets.  Two storage policies; both keep the lane's scalar state
@@ -551,7 +557,8 @@ struct Arena {
  *
  * HeadsStrided16: 16-bit heads at h[sc * stride] — the fast kernel points h at a
  *   shared-memory column (stride = threads per block, conflict free), the CPU
- *   harness at a plain array (stride 1).  Needs arena capacity < 65535 (0xffff = empty).
+ *   harness at a plain array (stride 1).  A head is slot << 1 | group, so the arena holds at most
+ *   32767 records (0xffff = empty).
  * HeadsWide32: 32-bit heads in global memory — the large-arena pass and exotic score
  *   ranges (up to 2048 buckets).
  * The lowest non-empty bucket is tracked by the lane like the reference does (bwtgap.c:63,73-78):
@@ -600,21 +607,27 @@ enum LaneStatus { LANE_OK = 0, LANE_ARENA_FULL = 1, LANE_REC_FULL = 2 };
  * step() so that the lanes of a warp stay in lock-step on the memory access.
  *
  * Exactness notes:
- *  - bucket order: lowest score first, LIFO inside a bucket, children pushed
- *    in the reference's order (insertion, deletions 0..3, mismatches j=1..3,
- *    exact match last).
- *  - the exact-match child has its parent's score and is pushed last, so it is
- *    always the next pop; it is kept in registers ("held") instead of going
- *    through memory, but is still counted in n_entries so that the
- *    `n_entries > max_entries` cutoff (bwtgap.c:139) fires at the same pop.
- *  - last_diff_pos: inherited from the parent on non-diff pushes (the slot
- *    reuse of bwtgap.c:60), which requires positive penalties (checked by the
- *    host before launch).
+ *  - bucket order: lowest score first, LIFO inside a bucket, children taken in the reverse of the
+ *    reference's push order (insertion, deletions 0..3, mismatches j=1..3(4), exact match last).
+ *  - the exact-match child has its parent's score and is pushed last, so it is always the next pop;
+ *    it is kept in registers ("held") instead of going through memory, but is still counted in
+ *    n_entries so that the `n_entries > max_entries` cutoff (bwtgap.c:139) fires at the same pop.
+ *  - the other children of an expansion go to memory as ONE record linked into (at most) two buckets
+ *    (StackRec above).  When a group is popped it becomes the lane's open group and its members are
+ *    taken one by one.  While members of a group of score B are left, B is the lowest non-empty
+ *    bucket and everything pushed meanwhile scores more than B (positive penalties), so the next pop
+ *    of the reference is always the next member of the open group: no other group can be opened
+ *    before it is exhausted.  n_entries counts members, as the reference's stack does.
+ *  - the two root entries (bwtgap.c:126-127) never touch memory: strand 1 starts as the held entry,
+ *    strand 0 as a one-member open group (bucket 0 holds nothing else but held children).
+ *  - last_diff_pos: inherited from the parent on non-diff pushes (the slot reuse of bwtgap.c:60),
+ *    which requires positive penalties (checked by the host before launch).
  */
 template <class Heads, bool REUSE>
 struct SearchLane {
     /* constant per read */
     Arena ar;
+    GroupStore gs;
     QRec *Q; /* [2][strideQ] */
     uint32_t *W; /* [2][strideW] */
     int strideQ, strideW;
@@ -624,18 +637,21 @@ struct SearchLane {
     /* mutable */
     Heads bk;
     uint32_t top, free_head; /* bump pointer / free list */
-    int best, n_mem;         /* lowest non-empty bucket (n_buckets when none); records in memory */
+    int best, n_mem;         /* lowest non-empty bucket (n_buckets when none); groups linked in memory */
     bool prefetch_next;      /* L2 prefetch of the next pop candidate (latency-bound passes) */
-    int n_entries;           /* the reference's stack->n_entries (memory + held) */
+    int n_entries;           /* the reference's stack->n_entries (members in memory + open group + held) */
     int max_diff, best_score, best_diff, best_cnt, n_aln;
     int status;
     bool finished;
     /* current entry */
-    bool have_cur, cur_held, extending;
+    bool have_cur, extending;
     uint32_t ck, cl;
     int ci, cldp, cmm, cgo, cge, cstate, ca, cscore;
-    int cdmask; /* family record: which deletions exist */
     uint32_t cpath; /* position of the current entry in the interval table */
+    /* open group: member mask (bits 0-3 children, bit 4 insertion / root) | kind << 5 | base << 7 | i << 16;
+     * 0 = none.  Its members share score (cscore), strand (ca) and counters (cmm, cgo, cge) with the
+     * entries being worked on in between, so those registers simply stay. */
+    uint32_t og;
     uint32_t n_pops, n_lookups; /* instrumentation: pops and 32-byte sectors of this read */
 
     static B2_HD int score_of(const Params &P, int mm, int go, int ge)
@@ -645,10 +661,11 @@ struct SearchLane {
 
     /* E: the launch constants, passed by reference at every call so that on the device they stay
      * in the kernel-parameter constant bank instead of being re-loaded through a pointer */
-    B2_HD void begin(const SearchEnv &E, Arena ar_, Heads heads_, QRec *Q_, uint32_t *W_, int strideQ_,
+    B2_HD void begin(const SearchEnv &E, Arena ar_, Heads heads_, GroupStore gs_, QRec *Q_, uint32_t *W_, int strideQ_,
                      int strideW_, Rec *recs_, int rec_cap_, int len_, int max_diff_, int n_amb)
     {
         bk = heads_;
+        gs = gs_;
         const Params *P = &E.P;
         const FmView *fm = E.fm;
         ar = ar_; Q = Q_; W = W_; strideQ = strideQ_; strideW = strideW_;
@@ -657,7 +674,9 @@ struct SearchLane {
         best_score = score_of(E.P, max_diff_ + 1, P->max_gapo + 1, P->max_gape + 1);
         best_diff = max_diff_ + 1;
         best_cnt = 0; n_aln = 0; status = LANE_OK;
-        finished = false; have_cur = false; cur_held = false; extending = false;
+        finished = false; have_cur = false; extending = false;
+        og = 0;
+        pq = 0;
         top = 0; free_head = B2_NIL; n_entries = 0;
         best = P->n_buckets; n_mem = 0;
         prefetch_next = E.prefetch_next != 0;
@@ -665,68 +684,66 @@ struct SearchLane {
         if (n_amb > max_diff_) { finished = true; return; } /* bwtgap.c:117-122 */
         bk.clear(P->n_buckets);
         /* roots: strand 0 then strand 1 (bwtgap.c:126-127) -> strand 1 pops first */
-        push(E, 0, len, 0, fm[0].seq_len, 0, 0, 0, ST_M, 0, path_root(), 0);
-        push(E, 1, len, 0, fm[0].seq_len, 0, 0, 0, ST_M, 0, path_root(), 0);
+        n_entries = 2;
+        og = 16u | (uint32_t)GRP_ROOT << 5;
+        ck = 0; cl = fm[0].seq_len; ci = len; cldp = 0; cmm = cgo = cge = 0; cstate = ST_M; ca = 1; cscore = 0;
+        cpath = path_root();
+        have_cur = true;
     }
 
-    B2_HD void push(const SearchEnv &E, int a, int i, uint32_t k, uint32_t l, int mm, int go, int ge, int state,
-                    int ldp, uint32_t path, int sc)
+    /* The children of the expansion of the current entry (position i, intervals nk4/nl4) that go to
+     * memory: gap group `gmask` into bucket sg, mismatch group `xmask` into bucket sx. */
+    B2_HD void push_groups(const SearchEnv &E, int i, int base, uint32_t gmask, int sg, uint32_t xmask, int sx,
+                           const uint32_t nk4[4], const uint32_t nl4[4])
     {
         (void)E;
         uint32_t slot;
         if (REUSE && free_head != B2_NIL) {
             slot = free_head;
-            free_head = ar.ent[slot].link;
+            free_head = ar.ent[slot].w[0];
         } else {
             if (top >= ar.cap) { status = LANE_ARENA_FULL; finished = true; return; }
             slot = top++;
         }
-        U4 e;
-        e.x = k; e.y = l;
-        e.z = (uint32_t)i | (uint32_t)ldp << 16;
-        e.w = (uint32_t)mm | (uint32_t)go << 8 | (uint32_t)ge << 16 | (uint32_t)state << 24 | (uint32_t)a << 26;
-        st_ent(ar.ent + slot, e, bk.get(sc), path);
-        bk.set(sc, slot);
-        best = sc < best ? sc : best;
-        ++n_mem;
-        ++n_entries;
-    }
-
-    /* The gap-open children of one expansion (insertion + existing deletions, bwtgap.c:218-228)
-     * as ONE record in their common bucket.  They are pushed consecutively, so they sit
-     * contiguously in the bucket; the record is expanded in place into the real entries only
-     * if the search ever reaches it (step(), mode 2).  It counts as 1 + popc(dmask) entries. */
-    B2_HD void push_family(const SearchEnv &E, int a, int i, uint32_t k, uint32_t l, int mm, int go, int ge,
-                           int dmask, uint32_t path, int sc)
-    {
-        (void)E;
-        uint32_t slot;
-        if (REUSE && free_head != B2_NIL) {
-            slot = free_head;
-            free_head = ar.ent[slot].link;
-        } else {
-            if (top >= ar.cap) { status = LANE_ARENA_FULL; finished = true; return; }
-            slot = top++;
+        uint32_t h[8];
+        h[0] = h[1] = Heads::nil();
+        if (gmask) { /* gap group first: when both share a bucket the mismatches are on top (pushed later) */
+            h[0] = bk.get(sg);
+            bk.set(sg, slot << 1);
+            best = sg < best ? sg : best;
+            ++n_mem;
         }
-        U4 e;
-        e.x = k; e.y = l;
-        e.z = (uint32_t)i | (uint32_t)dmask << 16;
-        e.w = (uint32_t)mm | (uint32_t)go << 8 | (uint32_t)ge << 16 | 3u << 24 | (uint32_t)a << 26;
-        st_ent(ar.ent + slot, e, bk.get(sc), path);
-        bk.set(sc, slot);
-        best = sc < best ? sc : best;
-        ++n_mem;
-        n_entries += 1 + popc32((uint32_t)dmask);
+        if (xmask) {
+            h[1] = bk.get(sx);
+            bk.set(sx, slot << 1 | 1u);
+            best = sx < best ? sx : best;
+            ++n_mem;
+        }
+        h[2] = cpath;
+        h[3] = (uint32_t)i | (uint32_t)base << 16 | (uint32_t)cstate << 19 | (uint32_t)ca << 21 | gmask << 22 | xmask << 27;
+        h[4] = (uint32_t)cmm | (uint32_t)cgo << 8 | (uint32_t)cge << 16;
+        h[5] = ck; h[6] = cl; h[7] = 0;
+        uint32_t *rec = ar.ent[slot].w;
+        st8(rec, h);
+        if ((gmask & 15u) | xmask) { /* a lone insertion does not need the children's sector */
+            uint32_t c8[8] = {nk4[0], nl4[0], nk4[1], nl4[1], nk4[2], nl4[2], nk4[3], nl4[3]};
+            st8(rec + 8, c8);
+        }
+        n_entries += popc32(gmask) + popc32(xmask);
     }
 
-    B2_HD void pop_mem(const SearchEnv &E)
+    /* take the top group of the lowest bucket out of memory: it becomes the open group */
+    B2_HD void pop_group(const SearchEnv &E)
     {
         B2_DBG(0);
-        int b = best;
-        uint32_t slot = bk.get(b);
-        U4 e;
-        uint32_t prev;
-        ld_ent(ar.ent + slot, e, prev, cpath);
+        const int b = best;
+        const uint32_t ref = bk.get(b);
+        const uint32_t slot = ref >> 1, which = ref & 1u;
+        uint32_t h[8], c8[8];
+        const uint32_t *rec = ar.ent[slot].w;
+        ld8cg(rec, h);
+        ld8cg(rec + 8, c8);
+        const uint32_t prev = which ? h[1] : h[0];
         bk.set(b, prev);
         --n_mem;
         uint32_t next_top = prev;
@@ -738,21 +755,103 @@ struct SearchLane {
                 best = nb;
             }
         }
-        /* the entry that will most likely be popped next: start bringing it into L2 while this
-         * entry's lookup is in flight (a hint only; pushes of this step may still overtake it) */
-        if (prefetch_next && n_mem > 0) prefetch_l2(ar.ent + next_top);
-        if (REUSE) { ar.ent[slot].link = free_head; free_head = slot; }
-        --n_entries;
-        ck = e.x; cl = e.y;
-        ci = (int)(e.z & 0xffffu); cldp = (int)(e.z >> 16);
-        cmm = (int)(e.w & 255u); cgo = (int)(e.w >> 8 & 255u); cge = (int)(e.w >> 16 & 255u);
-        cstate = (int)(e.w >> 24 & 3u); ca = (int)(e.w >> 26 & 1u);
-        cscore = b;
-        cdmask = 0;
-        if (cstate == 3) { /* family record: i in the low half, deletion mask in the high half */
-            cdmask = cldp;
-            n_entries -= popc32((uint32_t)cdmask);
+        /* the record that will most likely be popped next: start bringing it into L2 while this
+         * group is worked on (a hint only; pushes may still overtake it) */
+        if (prefetch_next && n_mem > 0) prefetch_l2(ar.ent + (next_top >> 1));
+        const uint32_t info = h[3];
+        const uint32_t gmask = info >> 22 & 31u, xmask = info >> 27 & 15u;
+        if (REUSE) { /* the slot is free once both of its groups have been taken */
+            if ((which ? gmask : xmask) == 0 || h[7] != 0) {
+                ar.ent[slot].w[0] = free_head;
+                free_head = slot;
+            } else ar.ent[slot].w[7] = 1u;
         }
+        const int pstate = (int)(info >> 19 & 3u);
+        ca = (int)(info >> 21 & 1u);
+        cscore = b;
+        cmm = (int)(h[4] & 255u); cgo = (int)(h[4] >> 8 & 255u); cge = (int)(h[4] >> 16 & 255u);
+        uint32_t mask;
+        if (which) { ++cmm; mask = xmask; }
+        else {
+            if (pstate == ST_M) ++cgo; else ++cge;
+            mask = gmask;
+        }
+        og = mask | (which ? (uint32_t)GRP_X : (uint32_t)GRP_G) << 5 | (info >> 16 & 7u) << 7 | (info & 0xffffu) << 16;
+        for (int w = 0; w < 8; ++w) gs.set(w, c8[w]);
+        gs.set(OG_PK, h[5]);
+        gs.set(OG_PL, h[6]);
+        gs.set(OG_PATH, h[2]);
+    }
+
+    /*
+     * Next member of the open group, in the reverse of the reference's push order, becomes the current
+     * entry (with pq = the width record of its position).  The mismatch members of a group share position
+     * and counters, and so do its deletion members: the pruning tests of bwtgap.c:146-158 (m < 0,
+     * m < width[i-1].bid) give the same answer for all of them.  When that answer is "skip", the whole run
+     * is dropped at once — the reference would pop them one after the other and `continue` each time;
+     * n_entries only falls meanwhile, so its cutoff test cannot fire in between.  Returns false when
+     * nothing was taken (the members dropped are counted in n_entries / n_pops).
+     */
+    B2_HD bool take_member(const SearchEnv &E)
+    {
+        const Params *P = &E.P;
+        const int K = E.fm[0].lut_k;
+        const uint32_t kind = og >> 5 & 3u, mask = og & 31u;
+        const int i = (int)(og >> 16), base = (int)(og >> 7 & 7u);
+        const QRec *q = Q + (size_t)ca * strideQ;
+        if (kind == GRP_ROOT) { /* the strand-0 root */
+            og = 0;
+            ck = 0; cl = E.fm[0].seq_len; ci = len; cldp = 0; cmm = cgo = cge = 0; cstate = ST_M; ca = 0; cscore = 0;
+            cpath = path_root();
+            if (len > 0) pq = ld_q(Q + len - 1);
+            --n_entries;
+            ++n_pops;
+            return true;
+        }
+        const uint32_t run = mask & 15u; /* members that are child intervals: mismatches, or deletions */
+        const int m = max_diff - cmm - cgo - ((P->mode & MODE_GAPE) ? cge : 0);
+        if (run) {
+            const int pos = kind == GRP_X ? i : i + 1; /* their position; pos > 0 for deletions */
+            if (pos > 0) pq = ld_q(q + pos - 1);
+            const bool stop = !(P->mode & MODE_NONSTOP) && cscore > best_score + P->s_mm; /* bwtgap.c:143: the first one ends the search */
+            if (!stop && (m < 0 || (pos > 0 && m < q_bid(pq)))) {
+                const int n = popc32(run);
+                n_entries -= n;
+                n_pops += (uint32_t)n;
+                og &= ~15u;
+                if (!(og & 31u)) og = 0;
+                B2_DBG(9);
+                return false;
+            }
+            int c;
+            if (kind == GRP_X) { /* pushed j = 1..3 (then j = 4 for an ambiguous base): (base + j) & 3 */
+                c = base & 3;
+                if (!(base > 3 && (mask >> c & 1u))) {
+                    c = (base + 3) & 3;
+                    if (!(mask >> c & 1u)) {
+                        c = (base + 2) & 3;
+                        if (!(mask >> c & 1u)) c = (base + 1) & 3;
+                    }
+                }
+                ci = i; cldp = i; cstate = ST_M;
+            } else { /* pushed insertion, deletions 0..3 */
+                c = (mask & 8u) ? 3 : (mask & 4u) ? 2 : (mask & 2u) ? 1 : 0;
+                ci = i + 1; cldp = i + 1; cstate = ST_D;
+            }
+            og &= ~(1u << c);
+            if (!(og & 31u)) og = 0;
+            ck = gs.get(2 * c); cl = gs.get(2 * c + 1);
+            cpath = path_ext(gs.get(OG_PATH), c, K);
+        } else { /* insertion / insertion extension: the parent's interval, one read base consumed */
+            og = 0;
+            ck = gs.get(OG_PK); cl = gs.get(OG_PL);
+            cpath = gs.get(OG_PATH);
+            ci = i; cldp = i; cstate = ST_I;
+            if (i > 0) pq = ld_q(q + i - 1);
+        }
+        --n_entries;
+        ++n_pops;
+        return true;
     }
 
     /* hit bookkeeping, bwtgap.c:165-198; returns false when the search must stop */
@@ -788,9 +887,12 @@ struct SearchLane {
      * the kernel can re-converge the warp between them (all lanes issue their lookup loads
      * together); step() chains them for callers that do not care (CPU logic tests).
      */
-    enum { NONE = -1, EXPAND = 0, EXTEND = 1, MATERIALIZE = 2 };
+    enum { NONE = -1, EXPAND = 0, EXTEND = 1 };
     QRec pq; /* width record of the position being worked on (prepare -> apply) */
     int pm;  /* differences still allowed for the current entry */
+
+    /* true when the next entry does not have to come from memory */
+    B2_HD bool ready() const { return have_cur || extending || og != 0; }
 
     /* pop until something needs a lookup; returns its kind, or NONE when the search ended
      * (finished is set) or when the next entry has to come from memory and allow_pop is false:
@@ -802,31 +904,24 @@ struct SearchLane {
         const bool gape_mode = P->mode & MODE_GAPE, nonstop = P->mode & MODE_NONSTOP;
         for (;;) {
             if (extending) { pq = ld_q(Q + (size_t)ca * strideQ + (ci - 1)); return EXTEND; }
+            if (n_entries == 0) { finished = true; return NONE; }
+            if (n_entries > P->max_entries) { finished = true; return NONE; } /* bwtgap.c:139 */
             if (!have_cur) {
-                if (n_entries == 0) { finished = true; return NONE; }
-                if (n_entries > P->max_entries) { finished = true; return NONE; }
-                if (!allow_pop) return NONE;
-                pop_mem(E);
-                if (cstate == 3) {
-                    /* its members are checked one by one when they are popped; only the score
-                     * break (bwtgap.c:143) can be anticipated: the first member would trigger it */
-                    if (!nonstop && cscore > best_score + P->s_mm) { ++n_pops; finished = true; return NONE; }
-                    return MATERIALIZE;
+                if (og == 0) {
+                    if (!allow_pop) return NONE;
+                    pop_group(E);
                 }
+                if (!take_member(E)) continue;
             } else { /* held exact child: same accounting as a push followed by a pop */
-                B2_DBG(4);
-                if (n_entries > P->max_entries) { finished = true; return NONE; }
                 --n_entries;
+                ++n_pops;
+                have_cur = false;
+                if (ci > 0) pq = ld_q(Q + (size_t)ca * strideQ + (ci - 1));
             }
-            have_cur = false;
-            ++n_pops;
             if (!nonstop && cscore > best_score + P->s_mm) { finished = true; return NONE; }
             pm = max_diff - cmm - cgo - (gape_mode ? cge : 0);
             if (pm < 0) { B2_DBG(8); continue; }
-            if (ci > 0) {
-                pq = ld_q(Q + (size_t)ca * strideQ + (ci - 1));
-                if (pm < q_bid(pq)) { B2_DBG(9); continue; }
-            }
+            if (ci > 0 && pm < q_bid(pq)) { B2_DBG(9); continue; } /* pq = record of position ci - 1 */
             if (ci == 0) {
                 if (!on_hit(E)) { finished = true; return NONE; }
                 continue;
@@ -845,17 +940,6 @@ struct SearchLane {
         const QRec q = pq;
         const int m = pm;
         n_lookups += ns;
-
-        if (mode == MATERIALIZE) { /* expand a family record in place, in the reference's push order */
-            have_cur = false;
-            const int i = ci;
-            /* a family record sits in the bucket of its members: cscore is their score */
-            push(E, ca, i, ck, cl, cmm, cgo + 1, cge, ST_I, i, cpath, cscore);
-            for (int j = 0; j < 4; ++j)
-                if (cdmask >> j & 1)
-                    push(E, ca, i + 1, nk4[j], nl4[j], cmm, cgo + 1, cge, ST_D, i + 1, path_ext(cpath, j, K), cscore);
-            return;
-        }
 
         const int i = ci - 1;
         const int base = q_base(q);
@@ -897,41 +981,29 @@ struct SearchLane {
             gaps = lg / 2 + 1;
         } else gaps = cgo + cge;
 
-        if (allow_diff && i >= P->indel_end_skip + gaps && len - i >= P->indel_end_skip + gaps) {
+        uint32_t live = 0; /* which of the four children exist */
+        for (int j = 0; j < 4; ++j) live |= (nk4[j] <= nl4[j] ? 1u : 0u) << j;
+        uint32_t gmask = 0, xmask = 0;
+        int sg = 0;
+        if (allow_diff && i >= P->indel_end_skip + gaps && len - i >= P->indel_end_skip + gaps) { /* bwtgap.c:217-243 */
             if (cstate == ST_M) {
-                if (cgo < P->max_gapo) { /* gap open: insertion + deletions as one family record */
-                    int dmask = 0;
-                    for (int j = 0; j < 4; ++j) dmask |= (nk4[j] <= nl4[j] ? 1 : 0) << j;
-                    B2_DBG(1);
-                    push_family(E, ca, i, ck, cl, cmm, cgo, cge, dmask, cpath, cscore + P->s_gapo);
-                }
+                if (cgo < P->max_gapo) { gmask = 16u | live; sg = cscore + P->s_gapo; B2_DBG(1); }
             } else if (cstate == ST_I) {
-                if (cge < P->max_gape) push(E, ca, i, ck, cl, cmm, cgo, cge + 1, ST_I, i, cpath, cscore + P->s_gape);
+                if (cge < P->max_gape) { gmask = 16u; sg = cscore + P->s_gape; }
             } else {
-                if (cge < P->max_gape && (cge + cgo < max_diff || occ < (uint32_t)P->max_del_occ))
-                    for (int j = 0; j < 4; ++j)
-                        if (nk4[j] <= nl4[j])
-                            push(E, ca, i + 1, nk4[j], nl4[j], cmm, cgo, cge + 1, ST_D, i + 1, path_ext(cpath, j, K),
-                                 cscore + P->s_gape);
+                if (cge < P->max_gape && (cge + cgo < max_diff || occ < (uint32_t)P->max_del_occ)) {
+                    gmask = live;
+                    sg = cscore + P->s_gape;
+                }
             }
         }
-        if (finished) return; /* arena overflow */
-
-        bool child = false;
-        if (allow_diff && allow_M) {
-            for (int j = 1; j <= 3; ++j) {
-                int c = (base + j) & 3;
-                uint32_t nk = pick4(nk4, c), nl = pick4(nl4, c);
-                if (nk <= nl) B2_DBG(3);
-                if (nk <= nl) push(E, ca, i, nk, nl, cmm + 1, cgo, cge, ST_M, i, path_ext(cpath, c, K), cscore + P->s_mm);
-            }
-            if (base > 3) { /* ambiguous base: the j == 4 child is a mismatch too */
-                int c = base & 3;
-                uint32_t nk = pick4(nk4, c), nl = pick4(nl4, c);
-                if (nk <= nl) push(E, ca, i, nk, nl, cmm + 1, cgo, cge, ST_M, i, path_ext(cpath, c, K), cscore + P->s_mm);
-            } else child = true;
-        } else if (base < 4) child = true;
-        if (finished) return;
+        bool child = base < 4;
+        if (allow_diff && allow_M) /* bwtgap.c:245-253; for an ambiguous base the j == 4 child is a mismatch too */
+            xmask = base > 3 ? live : live & ~(1u << base);
+        if (gmask | xmask) {
+            push_groups(E, i, base, gmask, sg, xmask, cscore + P->s_mm, nk4, nl4);
+            if (finished) return; /* arena overflow */
+        }
 
         if (child) { /* exact-match child: held in registers, counted like a push */
             uint32_t nk = pick4(nk4, base), nl = pick4(nl4, base);

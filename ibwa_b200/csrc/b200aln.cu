@@ -115,7 +115,7 @@ struct SearchArgs {
     QRec *Q;
     uint32_t *W;
     int strideQ, strideW;
-    StackEnt *ent;
+    StackRec *ent;
     uint32_t arena_cap;
     Rec *recs;
     int rec_cap;
@@ -174,6 +174,10 @@ __global__ void __launch_bounds__(128, MINB) k_search(const __grid_constant__ Se
     SearchLane<Heads, REUSE> L;
     L.finished = true;
     const Heads heads = HeadsFactory<Heads>::make(A, gl);
+    __shared__ uint32_t sm_group[OG_WORDS * 128]; /* the lanes' open groups, one conflict-free column each */
+    GroupStore gs;
+    gs.p = sm_group + threadIdx.x;
+    gs.stride = 128;
     bool alive = true, active = false;
     int r = -1;
     unsigned w = 0;
@@ -193,7 +197,7 @@ __global__ void __launch_bounds__(128, MINB) k_search(const __grid_constant__ Se
                     r = A.work_list ? A.work_list[w] : (int)w;
                     const int len = A.lens[r];
                     const size_t slab = A.recs_by_work ? (size_t)w : (size_t)r;
-                    L.begin(A.env, ar, heads, A.Q + (size_t)2 * r * A.strideQ, A.W + (size_t)2 * r * A.strideW, A.strideQ,
+                    L.begin(A.env, ar, heads, gs, A.Q + (size_t)2 * r * A.strideQ, A.W + (size_t)2 * r * A.strideW, A.strideQ,
                             A.strideW, A.recs + slab * A.rec_cap, A.rec_cap, len, A.md[len], A.n_amb[r]);
                     active = true;
                 } else alive = false;
@@ -202,7 +206,7 @@ __global__ void __launch_bounds__(128, MINB) k_search(const __grid_constant__ Se
         /* one search step per lane, the warp re-converged around the lookup so that all of its
          * loads are issued together */
         const bool running = active && !L.finished;
-        const bool ready = running && (L.have_cur || L.extending);
+        const bool ready = running && L.ready();
         const unsigned wait_mask = __ballot_sync(FULL, running && !ready);
         const unsigned ready_mask = __ballot_sync(FULL, ready);
         /* memory pops are taken in batches: when enough lanes wait for one, or nobody else can move */
@@ -407,9 +411,9 @@ struct b200aln_ctx {
     cudaEvent_t tm[2];
     /* tuning */
     int search_blocks_per_sm = 6, width_blocks_per_sm = 5;
-    uint32_t arena_cap = 4096, arena_cap_big = 0; /* 0: max_entries + 64 */
+    uint32_t arena_cap = 2048, arena_cap_big = 0; /* 64-byte records per lane; big 0: max_entries + 64 */
     int rec_cap = 8, rec_cap_big = 1 << 13, big_lanes = 256; /* wide pass: 256 lanes x (max_entries+64) x 32 B = 16 GB */
-    uint32_t arena_cap_mid = 16384; /* middle pass: 16-bit heads in shared memory, free-list arena */
+    uint32_t arena_cap_mid = 8192; /* middle pass: 16-bit heads in shared memory, free-list arena */
     int rec_cap_mid = 512, mid_lanes = 148 * 128 * 2;
     int prefetch_fast = 0, prefetch_mid = 1; /* L2 prefetch of the next pop candidate, per pass */
     int pop_batch = 1;     /* memory pops are taken when this many lanes of a warp wait for one */
@@ -719,8 +723,8 @@ struct Misc {
 };
 
 /* fast pass: 16-bit heads in shared memory when the score range and the arena allow it */
-/* 16-bit heads in shared memory: arena slots must fit 16 bits and n_buckets columns the shared memory */
-static bool fast_heads_ok(const Params &P, uint32_t arena_cap) { return P.n_buckets <= 160 && arena_cap < 65535u; }
+/* 16-bit heads in shared memory: slot << 1 | group must fit 16 bits and n_buckets columns the shared memory */
+static bool fast_heads_ok(const Params &P, uint32_t arena_cap) { return P.n_buckets <= 160 && arena_cap <= 32767u; }
 
 static void launch_search_mid(b200aln_ctx *c, SearchArgs &A, int blocks)
 { /* middle pass: 16-bit shared-memory heads, free-list arena (capacity = stack high-water, not total pushes) */
@@ -749,7 +753,7 @@ static void launch_search_fast(b200aln_ctx *c, SearchArgs &A, int blocks)
 static void launch_search_big(b200aln_ctx *c, SearchArgs &A, int blocks)
 {
     const size_t smem32 = (size_t)A.env.P.n_buckets * 128 * sizeof(uint32_t);
-    if (smem32 <= 48 * 1024) { /* 32-bit heads still fit in shared memory */
+    if (smem32 + OG_WORDS * 128 * sizeof(uint32_t) <= 48 * 1024) { /* 32-bit heads still fit in shared memory (next to the open groups) */
         k_search<HeadsStrided32, true, 1><<<blocks, 128, smem32, c->st>>>(A);
         CK(cudaGetLastError());
         return;
@@ -776,7 +780,7 @@ static void run_batch_device(b200aln_ctx *c, int n_reads, int max_len, const int
     c->Q.need((size_t)n_reads * 2 * strideQ * sizeof(QRec) + 64);
     c->W.need((size_t)n_reads * 2 * strideW * 4 + 64);
     c->n_amb.need((size_t)n_reads * 4);
-    c->ent.need(lanes * c->arena_cap * sizeof(StackEnt));
+    c->ent.need(lanes * c->arena_cap * sizeof(StackRec));
     c->recs.need((size_t)n_reads * c->rec_cap * 16);
     c->n_aln.need((size_t)n_reads * 4);
     c->over_slot.need((size_t)n_reads * 4);
@@ -811,7 +815,7 @@ static void run_batch_device(b200aln_ctx *c, int n_reads, int max_len, const int
     SA.n_work = n_reads; SA.work_list = nullptr;
     SA.lens = d_lens; SA.n_amb = c->n_amb.as<int32_t>(); SA.md = c->md.as<int32_t>();
     SA.Q = WA.Q; SA.W = WA.W; SA.strideQ = strideQ; SA.strideW = strideW;
-    SA.ent = c->ent.as<StackEnt>(); SA.arena_cap = c->arena_cap;
+    SA.ent = c->ent.as<StackRec>(); SA.arena_cap = c->arena_cap;
     SA.recs = c->recs.as<Rec>(); SA.rec_cap = c->rec_cap; SA.recs_by_work = 0;
     SA.n_aln = c->n_aln.as<int32_t>(); SA.over_slot = nullptr; SA.slot_tag = 0;
     SA.counter = &dm->counter; SA.n_over = &dm->n_over; SA.over_list = c->over_list.as<int32_t>();
@@ -846,7 +850,7 @@ static void run_batch_device(b200aln_ctx *c, int n_reads, int max_len, const int
         int lanes_mid = c->mid_lanes;
         if ((unsigned)lanes_mid > ((n_over + 127u) / 128u) * 128u) lanes_mid = (int)(((n_over + 127u) / 128u) * 128u);
         const int mblocks = (lanes_mid + 127) / 128;
-        c->ent_mid.need((size_t)mblocks * 128 * c->arena_cap_mid * sizeof(StackEnt));
+        c->ent_mid.need((size_t)mblocks * 128 * c->arena_cap_mid * sizeof(StackRec));
         c->recs_mid.need((size_t)n_over * c->rec_cap_mid * 16);
         c->over_list2.need((size_t)n_over * 4);
         WidthArgs WM = WA;
@@ -856,7 +860,7 @@ static void run_batch_device(b200aln_ctx *c, int n_reads, int max_len, const int
         ++launches;
         SearchArgs SM = SA;
         SM.n_work = (int)n_over; SM.work_list = c->over_list.as<int32_t>();
-        SM.ent = c->ent_mid.as<StackEnt>(); SM.arena_cap = c->arena_cap_mid;
+        SM.ent = c->ent_mid.as<StackRec>(); SM.arena_cap = c->arena_cap_mid;
         SM.recs = c->recs_mid.as<Rec>(); SM.rec_cap = c->rec_cap_mid; SM.recs_by_work = 1;
         SM.over_slot = c->over_slot.as<int32_t>(); SM.slot_tag = 0;
         SM.env.prefetch_next = c->prefetch_mid;
@@ -874,7 +878,7 @@ static void run_batch_device(b200aln_ctx *c, int n_reads, int max_len, const int
         int big_lanes = c->big_lanes;
         if ((unsigned)big_lanes > ((n_wide + 127u) / 128u) * 128u) big_lanes = (int)(((n_wide + 127u) / 128u) * 128u);
         int bblocks = (big_lanes + 127) / 128;
-        c->ent_big.need((size_t)bblocks * 128 * cap_big * sizeof(StackEnt));
+        c->ent_big.need((size_t)bblocks * 128 * cap_big * sizeof(StackRec));
         c->recs_big.need((size_t)n_wide * c->rec_cap_big * 16);
         WidthArgs WB = WA;
         WB.n_reads = (int)n_wide; WB.work_list = wide_list;
@@ -883,7 +887,7 @@ static void run_batch_device(b200aln_ctx *c, int n_reads, int max_len, const int
         ++launches;
         SearchArgs SB = SA;
         SB.n_work = (int)n_wide; SB.work_list = wide_list;
-        SB.ent = c->ent_big.as<StackEnt>(); SB.arena_cap = cap_big;
+        SB.ent = c->ent_big.as<StackRec>(); SB.arena_cap = cap_big;
         SB.recs = c->recs_big.as<Rec>(); SB.rec_cap = c->rec_cap_big; SB.recs_by_work = 1;
         SB.over_slot = c->over_slot.as<int32_t>(); SB.slot_tag = WIDE_TAG;
         SB.env.prefetch_next = c->prefetch_mid;

@@ -18,6 +18,19 @@ __device__ __forceinline__ uint32_t ld32(const S32 *p)
                  : "=r"(a), "=r"(b), "=r"(c), "=r"(d), "=r"(e), "=r"(f), "=r"(g), "=r"(h) : "l"(p));
     return a ^ b ^ c ^ d ^ e ^ f ^ g ^ h;
 }
+__device__ __forceinline__ uint32_t ld32ca(const S32 *p)
+{ /* same sector through L1 (allocating) */
+    uint32_t a, b, c, d, e, f, g, h;
+    asm volatile("ld.global.ca.v8.u32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                 : "=r"(a), "=r"(b), "=r"(c), "=r"(d), "=r"(e), "=r"(f), "=r"(g), "=r"(h) : "l"(p));
+    return a ^ b ^ c ^ d ^ e ^ f ^ g ^ h;
+}
+__device__ __forceinline__ uint32_t ld4(const S32 *p)
+{ /* one word of a random sector, L1 allocating (the width-record access) */
+    uint32_t a;
+    asm volatile("ld.global.ca.u32 %0, [%1];" : "=r"(a) : "l"(p));
+    return a;
+}
 template <int MODE, int MLP>
 __global__ void __launch_bounds__(256) gather(const S32 *t, uint64_t n_sectors, int iters, unsigned long long *sink)
 {
@@ -38,6 +51,8 @@ __global__ void __launch_bounds__(256) gather(const S32 *t, uint64_t n_sectors, 
         for (int j = 0; j < MLP; ++j) {
             if (MODE == 0) acc += ld32(t + idx[j]);
             else if (MODE == 1) { acc += ld32(t + idx[j]); acc += ld32(t + idx[j] + 1); }
+            else if (MODE == 4) acc += ld32ca(t + idx[j]);
+            else if (MODE == 5) acc += ld4(t + idx[j]);
             else if (MODE == 2) acc += ld32(t + idx[j] + (lane & 1));
             else acc += ld32(t + idx[j] + (lane & 3));
         }
@@ -80,5 +95,7 @@ int main(int argc, char **argv)
     run<1, 8>("B 64B pair by one thread (2 loads)", t, n_sectors, sink, p.multiProcessorCount, 64);
     run<2, 8>("C 64B pair by two lanes", t, n_sectors, sink, p.multiProcessorCount, 32);
     run<3, 8>("D 128B line by four lanes", t, n_sectors, sink, p.multiProcessorCount, 32);
+    run<4, 8>("E one 32B sector / thread, ld.ca", t, n_sectors, sink, p.multiProcessorCount, 32);
+    run<5, 8>("F one 4B word / thread, ld.ca", t, n_sectors, sink, p.multiProcessorCount, 4);
     return 0;
 }

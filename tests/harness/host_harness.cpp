@@ -56,11 +56,13 @@ static int64_t run(const SearchEnv &env, const std::vector<int> &md, int n_reads
     const int strideQ = round_up8(max_len), strideW = round_up8(max_len + 1);
     std::vector<QRec> Q(2 * (size_t)strideQ + 8);
     std::vector<uint32_t> W(2 * (size_t)strideW + 8);
-    std::vector<StackEnt> ent(arena_cap);
+    std::vector<StackRec> ent(arena_cap);
     std::vector<Rec> recs(rec_cap);
     int64_t n_status = 0;
     std::vector<uint32_t> hstore(2048 + 64);
-    std::vector<StackEnt> ent2;
+    uint32_t gstore[OG_WORDS];
+    GroupStore gs; gs.p = gstore; gs.stride = 1;
+    std::vector<StackRec> ent2;
     std::vector<Rec> recs2;
     for (int r = 0; r < n_reads; ++r) {
         const uint8_t *fwd = codes + offs[r];
@@ -70,7 +72,7 @@ static int64_t run(const SearchEnv &env, const std::vector<int> &md, int n_reads
         width_pass(fm[1], fwd, len, 1, comp, seed_len, W.data() + strideW, Q.data() + strideQ);
         SearchLane<Heads, REUSE> lane;
         Arena ar; ar.ent = ent.data(); ar.cap = arena_cap;
-        lane.begin(env, ar, make_heads<Heads>(hstore), Q.data(), W.data(), strideQ, strideW, recs.data(), rec_cap, len, md[len], n_amb);
+        lane.begin(env, ar, make_heads<Heads>(hstore), gs, Q.data(), W.data(), strideQ, strideW, recs.data(), rec_cap, len, md[len], n_amb);
         while (!lane.finished) lane.step(env);
         if (lane.status != LANE_OK && big_cap) {
             /* the product's large pass: widths rebuilt (the aborted pass shadowed them), free-list arena */
@@ -80,7 +82,7 @@ static int64_t run(const SearchEnv &env, const std::vector<int> &md, int n_reads
             width_pass(fm[1], fwd, len, 1, comp, seed_len, W.data() + strideW, Q.data() + strideQ);
             SearchLane<HeadsWide32, true> big;
             Arena ar2; ar2.ent = ent2.data(); ar2.cap = big_cap;
-            big.begin(env, ar2, make_heads<HeadsWide32>(hstore), Q.data(), W.data(), strideQ, strideW, recs2.data(), 1 << 16, len, md[len], n_amb);
+            big.begin(env, ar2, make_heads<HeadsWide32>(hstore), gs, Q.data(), W.data(), strideQ, strideW, recs2.data(), 1 << 16, len, md[len], n_amb);
             while (!big.finished) big.step(env);
             if (big.status != LANE_OK) { n_aln[r] = -big.status; continue; }
             n_aln[r] = big.n_aln;
@@ -135,7 +137,7 @@ extern "C" int64_t hh_aln_batch(const b200aln_bwt_view_t *bwt, const b200aln_bwt
     std::vector<Rec> all;
     bool comp = opt->mode & MODE_COMPREAD;
     int64_t ov;
-    if (P.n_buckets <= 128 && arena_cap < 65535) {
+    if (P.n_buckets <= 128 && arena_cap <= 32767) {
         ov = reuse ? run<HeadsStrided16, true>(env, md, n_reads, lens, offs, codes, comp, opt->seed_len, arena_cap, rec_cap, n_aln, all, counters, big_cap)
                    : run<HeadsStrided16, false>(env, md, n_reads, lens, offs, codes, comp, opt->seed_len, arena_cap, rec_cap, n_aln, all, counters, big_cap);
     } else {

@@ -28,7 +28,7 @@ def harness_sai(bwt, rbwt, args, fq, **kw):
 def test_core_matches_reference(tag, golden_dir, g1_index):
     args, fq = CASES[tag]
     got, nov = harness_sai(g1_index[0], g1_index[1], args, os.path.join(golden_dir, fq + ".fq.gz"),
-                           arena_cap=65000, rec_cap=4096)
+                           arena_cap=32000, rec_cap=4096)
     want = open(os.path.join(golden_dir, f"g1_{tag}.sai"), "rb").read()
     assert nov == 0
     assert got == want
@@ -47,7 +47,7 @@ def test_core_wide_heads_variant(tag, golden_dir, g1_index):
 def test_core_free_list_variant(tag, golden_dir, g1_index):
     args, fq = CASES[tag]
     got, nov = harness_sai(g1_index[0], g1_index[1], args, os.path.join(golden_dir, fq + ".fq.gz"),
-                           arena_cap=65000, rec_cap=4096, reuse=True)
+                           arena_cap=32000, rec_cap=4096, reuse=True)
     want = open(os.path.join(golden_dir, f"g1_{tag}.sai"), "rb").read()
     assert nov == 0 and got == want
 
@@ -79,7 +79,7 @@ def test_interval_table_is_exact(tag, lut_k, golden_dir, g1_index):
     """The path-k-mer interval table replaces occ lookups for the first lut_k levels; bytes must not change."""
     args, fq = CASES[tag]
     got, nov = harness_sai(g1_index[0], g1_index[1], args, os.path.join(golden_dir, fq + ".fq.gz"),
-                           arena_cap=65000, rec_cap=4096, lut_k=lut_k)
+                           arena_cap=32000, rec_cap=4096, lut_k=lut_k)
     assert nov == 0
     assert got == open(os.path.join(golden_dir, f"g1_{tag}.sai"), "rb").read()
 
@@ -112,7 +112,20 @@ def test_long_reads_and_wide_score_ranges(golden_dir, g1_index):
             sub = rng.random(L) < 0.004
             r[sub] = (r[sub] + 1) & 3
         reads.append(r)
-    n_aln = _vs_oracle(g1_index[0], g1_index[1], reads[:2], [], arena_cap=60000, rec_cap=64, lut_k=5)
+    n_aln = _vs_oracle(g1_index[0], g1_index[1], reads[:2], [], arena_cap=32000, rec_cap=64, lut_k=5)
     assert (n_aln > 0).all()
     _vs_oracle(g1_index[0], g1_index[1], reads, [], arena_cap=1 << 20, rec_cap=64, lut_k=5)
     _vs_oracle(g1_index[0], g1_index[1], reads, ["-n", "9", "-o", "2"], arena_cap=1 << 20, rec_cap=64)
+
+
+@pytest.mark.parametrize("args", [["-M", "3", "-O", "3", "-E", "2"], ["-M", "4", "-O", "4", "-E", "4", "-o", "2"],
+                                  ["-M", "1", "-O", "2", "-E", "1", "-n", "3"]])
+def test_equal_penalties_share_a_bucket(args, golden_dir, g1_index):
+    """With s_mm == s_gapo (or s_gape) the gap group and the mismatch group of one expansion land in the same
+    bucket: the record is linked twice into it, mismatches on top; other unusual penalty mixes for good measure.
+    Checked against the oracle, on the bump arena, the free-list arena and the 32-bit heads."""
+    opt, _, _, _ = parse_aln_args(args + ["p", "q"])
+    batch = next(seqio.read_batches(os.path.join(golden_dir, "g1_reads.fq.gz"), opt.mode, opt.trim_qual))
+    reads = [batch.codes[o:o + l] for o, l in zip(batch.offs[:500], batch.lens[:500])]
+    _vs_oracle(g1_index[0], g1_index[1], reads, args, arena_cap=1 << 22, rec_cap=4096, reuse=True, lut_k=4)
+    _vs_oracle(g1_index[0], g1_index[1], reads[:200], args, arena_cap=1 << 22, rec_cap=4096, lut_k=2)

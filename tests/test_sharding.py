@@ -38,7 +38,7 @@ def _worker(rank, world, port, tag, out_path):
     batch = next(seqio.read_batches(os.path.join(GOLDEN, fq + ".fq.gz"), opt.mode, opt.trim_qual))
     lo, hi = shard.shard_range(len(batch), world, rank)
     lens, offs, codes = shard.take_shard(batch.lens, batch.offs, batch.codes, lo, hi)
-    n_aln, rec, nov, _ = pyharness.aln_batch(bwt, rbwt, lens, offs, codes, opt.to_c(), arena_cap=65000, rec_cap=4096,
+    n_aln, rec, nov, _ = pyharness.aln_batch(bwt, rbwt, lens, offs, codes, opt.to_c(), arena_cap=32000, rec_cap=4096,
                                              batch_max_len=int(batch.lens.max()))
     assert nov == 0
     parts = [None] * world if rank == 0 else None

@@ -479,6 +479,10 @@ def main():
         step_e2e(w)
     ms_e2e, st_e2e = timed_e2e(args.steps)
 
+    eng.set("count", 1)         # one untimed step with the pop / sector counters compiled in
+    counted = step_device()
+    eng.set("count", 0)
+
     total_reads = world * n * args.steps
     value = total_reads / (ms_dev * 1e-3)
     e2e_value = total_reads / (ms_e2e * 1e-3)
@@ -497,7 +501,7 @@ def main():
            "kernel_ms": {k: float(np.mean([s[k] for s in st_dev])) for k in
                          ("ms_width", "ms_search", "ms_compact", "ms_total")},
            "overflow_reads_per_step": int(last["overflow_reads"]),
-           "device_pops_per_read": last["pops"] / n, "device_sectors_per_read": last["occ_lookups"] / n}
+           "device_pops_per_read": counted["pops"] / n, "device_sectors_per_read": counted["occ_lookups"] / n}
 
     if rank == 0:
         # roofline: algorithmic bytes = 32 B x occ lookups of the REFERENCE algorithm (oracle-counted on a sample)
@@ -527,7 +531,7 @@ def main():
                            "oracle_pops_per_read": port["stats"]["pops"] / port["n"],
                            "random_sector_roof_gbs": sector_roof, "random_64B_pair_roof_gbs": pair_roof,
                            "frac_of_random_sector_roof": achieved / sector_roof if sector_roof else None,
-                           "occ_sectors_per_s": last["occ_lookups"] / (ms_search * 1e-3)}
+                           "occ_sectors_per_s": counted["occ_lookups"] / (ms_search * 1e-3)}
         # parity of this very run against the oracle port on the sample
         m = port["n"]
         n_aln_d, rec_d = eng.cal_sa_reg_gap(np.full(m, L, np.int32), np.arange(m, dtype=np.int64) * L,

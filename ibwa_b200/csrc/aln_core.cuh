@@ -206,11 +206,20 @@ struct Rec { /* == bwt_aln1_t */
     int32_t score;
 };
 
-/* everything a search lane needs that is constant for a launch */
+/* everything a search lane needs that is constant for a launch.  The per-read buffers are addressed from
+ * these bases with small per-lane indexes (row, slab, lane number), so that a lane carries no pointers: on
+ * the device the bases stay in the kernel-parameter constant bank. */
 struct SearchEnv {
     FmView fm[2]; /* fm[0] = bwt, fm[1] = rbwt */
     Params P;
     int prefetch_next; /* 1: prefetch the next pop candidate into L2 (helps when few, long reads are left) */
+    uint32_t *Q;  /* width records: row 2 * read + strand, strideQ words each (QRec) */
+    uint32_t *W;  /* widths: row 2 * read + strand, strideW words each */
+    int strideQ, strideW;
+    Rec *recs;    /* record slabs, rec_cap each */
+    int rec_cap;
+    StackRec *ent; /* arenas, arena_cap records per lane */
+    uint32_t arena_cap;
 };
 
 /* ---- packed per-position record Q[a][j] (built by the width pass) -------- */
@@ -532,12 +541,8 @@ extern uint64_t b2_dbg[16];
 #define B2_DBG(i) ((void)0)
 #endif
 
-/* per-lane arena in global memory: 64-byte records, bump allocated (optionally with a
+/* per-lane arena in global memory (SearchEnv::ent): 64-byte records, bump allocated (optionally with a
  * free list through w[0], REUSE) */
-struct Arena {
-    StackRec *ent; /* [cap] */
-    uint32_t cap;
-};
 
 /* The open group of a lane — the members of the group popped last that have not been taken yet — lives
  * outside the lane's registers: words at p[w * stride] (a shared-memory column on the device, a plain
@@ -623,16 +628,13 @@ enum LaneStatus { LANE_OK = 0, LANE_ARENA_FULL = 1, LANE_REC_FULL = 2 };
  *  - last_diff_pos: inherited from the parent on non-diff pushes (the slot reuse of bwtgap.c:60),
  *    which requires positive penalties (checked by the host before launch).
  */
-template <class Heads, bool REUSE>
+template <class Heads, bool REUSE, bool STATS = true>
 struct SearchLane {
     /* constant per read */
-    Arena ar;
     GroupStore gs;
-    QRec *Q; /* [2][strideQ] */
-    uint32_t *W; /* [2][strideW] */
-    int strideQ, strideW;
-    Rec *recs;
-    int rec_cap;
+    uint32_t lane_no; /* which arena */
+    uint32_t row;     /* 2 * read: rows row (strand 0) and row + 1 (strand 1) of Q and W */
+    uint32_t slab;    /* which record slab */
     int len, opt_max_diff;
     /* mutable */
     Heads bk;
@@ -661,15 +663,20 @@ struct SearchLane {
 
     /* E: the launch constants, passed by reference at every call so that on the device they stay
      * in the kernel-parameter constant bank instead of being re-loaded through a pointer */
-    B2_HD void begin(const SearchEnv &E, Arena ar_, Heads heads_, GroupStore gs_, QRec *Q_, uint32_t *W_, int strideQ_,
-                     int strideW_, Rec *recs_, int rec_cap_, int len_, int max_diff_, int n_amb)
+    B2_HD const QRec *qrow(const SearchEnv &E, int a) const { return E.Q + (size_t)(row + (uint32_t)a) * E.strideQ; }
+    B2_HD StackRec *arena(const SearchEnv &E) const { return E.ent + (size_t)lane_no * E.arena_cap; }
+    B2_HD Rec *records(const SearchEnv &E) const { return E.recs + (size_t)slab * E.rec_cap; }
+
+    /* heads_clean: the caller has already emptied the bucket heads (the kernel does it with the whole warp) */
+    B2_HD void begin(const SearchEnv &E, Heads heads_, GroupStore gs_, uint32_t lane_no_, uint32_t read, uint32_t slab_,
+                     int len_, int max_diff_, int n_amb, bool heads_clean = false)
     {
         bk = heads_;
         gs = gs_;
         const Params *P = &E.P;
         const FmView *fm = E.fm;
-        ar = ar_; Q = Q_; W = W_; strideQ = strideQ_; strideW = strideW_;
-        recs = recs_; rec_cap = rec_cap_; len = len_; opt_max_diff = max_diff_;
+        lane_no = lane_no_; row = 2u * read; slab = slab_;
+        len = len_; opt_max_diff = max_diff_;
         max_diff = max_diff_;
         best_score = score_of(E.P, max_diff_ + 1, P->max_gapo + 1, P->max_gape + 1);
         best_diff = max_diff_ + 1;
@@ -682,7 +689,7 @@ struct SearchLane {
         prefetch_next = E.prefetch_next != 0;
         n_pops = n_lookups = 0;
         if (n_amb > max_diff_) { finished = true; return; } /* bwtgap.c:117-122 */
-        bk.clear(P->n_buckets);
+        if (!heads_clean) bk.clear(P->n_buckets);
         /* roots: strand 0 then strand 1 (bwtgap.c:126-127) -> strand 1 pops first */
         n_entries = 2;
         og = 16u | (uint32_t)GRP_ROOT << 5;
@@ -696,13 +703,13 @@ struct SearchLane {
     B2_HD void push_groups(const SearchEnv &E, int i, int base, uint32_t gmask, int sg, uint32_t xmask, int sx,
                            const uint32_t nk4[4], const uint32_t nl4[4])
     {
-        (void)E;
+        StackRec *ent = arena(E);
         uint32_t slot;
         if (REUSE && free_head != B2_NIL) {
             slot = free_head;
-            free_head = ar.ent[slot].w[0];
+            free_head = ent[slot].w[0];
         } else {
-            if (top >= ar.cap) { status = LANE_ARENA_FULL; finished = true; return; }
+            if (top >= E.arena_cap) { status = LANE_ARENA_FULL; finished = true; return; }
             slot = top++;
         }
         uint32_t h[8];
@@ -723,7 +730,7 @@ struct SearchLane {
         h[3] = (uint32_t)i | (uint32_t)base << 16 | (uint32_t)cstate << 19 | (uint32_t)ca << 21 | gmask << 22 | xmask << 27;
         h[4] = (uint32_t)cmm | (uint32_t)cgo << 8 | (uint32_t)cge << 16;
         h[5] = ck; h[6] = cl; h[7] = 0;
-        uint32_t *rec = ar.ent[slot].w;
+        uint32_t *rec = ent[slot].w;
         st8(rec, h);
         if ((gmask & 15u) | xmask) { /* a lone insertion does not need the children's sector */
             uint32_t c8[8] = {nk4[0], nl4[0], nk4[1], nl4[1], nk4[2], nl4[2], nk4[3], nl4[3]};
@@ -740,7 +747,8 @@ struct SearchLane {
         const uint32_t ref = bk.get(b);
         const uint32_t slot = ref >> 1, which = ref & 1u;
         uint32_t h[8], c8[8];
-        const uint32_t *rec = ar.ent[slot].w;
+        StackRec *ent = arena(E);
+        const uint32_t *rec = ent[slot].w;
         ld8cg(rec, h);
         ld8cg(rec + 8, c8);
         const uint32_t prev = which ? h[1] : h[0];
@@ -757,14 +765,14 @@ struct SearchLane {
         }
         /* the record that will most likely be popped next: start bringing it into L2 while this
          * group is worked on (a hint only; pushes may still overtake it) */
-        if (prefetch_next && n_mem > 0) prefetch_l2(ar.ent + (next_top >> 1));
+        if (prefetch_next && n_mem > 0) prefetch_l2(ent + (next_top >> 1));
         const uint32_t info = h[3];
         const uint32_t gmask = info >> 22 & 31u, xmask = info >> 27 & 15u;
         if (REUSE) { /* the slot is free once both of its groups have been taken */
             if ((which ? gmask : xmask) == 0 || h[7] != 0) {
-                ar.ent[slot].w[0] = free_head;
+                ent[slot].w[0] = free_head;
                 free_head = slot;
-            } else ar.ent[slot].w[7] = 1u;
+            } else ent[slot].w[7] = 1u;
         }
         const int pstate = (int)(info >> 19 & 3u);
         ca = (int)(info >> 21 & 1u);
@@ -798,16 +806,16 @@ struct SearchLane {
         const int K = E.fm[0].lut_k;
         const uint32_t kind = og >> 5 & 3u, mask = og & 31u;
         const int i = (int)(og >> 16), base = (int)(og >> 7 & 7u);
-        const QRec *q = Q + (size_t)ca * strideQ;
         if (kind == GRP_ROOT) { /* the strand-0 root */
             og = 0;
             ck = 0; cl = E.fm[0].seq_len; ci = len; cldp = 0; cmm = cgo = cge = 0; cstate = ST_M; ca = 0; cscore = 0;
             cpath = path_root();
-            if (len > 0) pq = ld_q(Q + len - 1);
+            if (len > 0) pq = ld_q(qrow(E, 0) + len - 1);
             --n_entries;
-            ++n_pops;
+            if (STATS) ++n_pops;
             return true;
         }
+        const QRec *q = qrow(E, ca);
         const uint32_t run = mask & 15u; /* members that are child intervals: mismatches, or deletions */
         const int m = max_diff - cmm - cgo - ((P->mode & MODE_GAPE) ? cge : 0);
         if (run) {
@@ -817,7 +825,7 @@ struct SearchLane {
             if (!stop && (m < 0 || (pos > 0 && m < q_bid(pq)))) {
                 const int n = popc32(run);
                 n_entries -= n;
-                n_pops += (uint32_t)n;
+                if (STATS) n_pops += (uint32_t)n;
                 og &= ~15u;
                 if (!(og & 31u)) og = 0;
                 B2_DBG(9);
@@ -850,7 +858,7 @@ struct SearchLane {
             if (i > 0) pq = ld_q(q + i - 1);
         }
         --n_entries;
-        ++n_pops;
+        if (STATS) ++n_pops;
         return true;
     }
 
@@ -868,12 +876,14 @@ struct SearchLane {
         if (cscore == best_score) best_cnt = (int)((uint32_t)best_cnt + (cl - ck + 1u));
         else if (best_cnt > P->max_top2) return false;
         bool add = true;
+        Rec *recs = records(E);
         if (cgo)
             for (int j = 0; j < n_aln; ++j)
                 if (recs[j].k == ck && recs[j].l == cl) { add = false; break; }
         if (add) {
-            shadow_update(cl - ck + 1u, f.seq_len, cldp, len, W + (size_t)ca * strideW, Q + (size_t)ca * strideQ);
-            if (n_aln >= rec_cap) { status = LANE_REC_FULL; return false; }
+            shadow_update(cl - ck + 1u, f.seq_len, cldp, len, E.W + (size_t)(row + (uint32_t)ca) * E.strideW,
+                          E.Q + (size_t)(row + (uint32_t)ca) * E.strideQ);
+            if (n_aln >= E.rec_cap) { status = LANE_REC_FULL; return false; }
             Rec r;
             r.packed = (uint32_t)cmm | (uint32_t)cgo << 8 | (uint32_t)cge << 16 | (uint32_t)ca << 24;
             r.k = ck; r.l = cl; r.score = cscore;
@@ -903,7 +913,7 @@ struct SearchLane {
         const Params *P = &E.P;
         const bool gape_mode = P->mode & MODE_GAPE, nonstop = P->mode & MODE_NONSTOP;
         for (;;) {
-            if (extending) { pq = ld_q(Q + (size_t)ca * strideQ + (ci - 1)); return EXTEND; }
+            if (extending) { pq = ld_q(qrow(E, ca) + (ci - 1)); return EXTEND; }
             if (n_entries == 0) { finished = true; return NONE; }
             if (n_entries > P->max_entries) { finished = true; return NONE; } /* bwtgap.c:139 */
             if (!have_cur) {
@@ -914,9 +924,9 @@ struct SearchLane {
                 if (!take_member(E)) continue;
             } else { /* held exact child: same accounting as a push followed by a pop */
                 --n_entries;
-                ++n_pops;
+                if (STATS) ++n_pops;
                 have_cur = false;
-                if (ci > 0) pq = ld_q(Q + (size_t)ca * strideQ + (ci - 1));
+                if (ci > 0) pq = ld_q(qrow(E, ca) + (ci - 1));
             }
             if (!nonstop && cscore > best_score + P->s_mm) { finished = true; return NONE; }
             pm = max_diff - cmm - cgo - (gape_mode ? cge : 0);
@@ -939,7 +949,7 @@ struct SearchLane {
         const bool gape_mode = P->mode & MODE_GAPE;
         const QRec q = pq;
         const int m = pm;
-        n_lookups += ns;
+        if (STATS) n_lookups += ns;
 
         const int i = ci - 1;
         const int base = q_base(q);

@@ -112,13 +112,6 @@ struct SearchArgs {
     const int32_t *lens;
     const int32_t *n_amb;
     const int32_t *md; /* max_diff by read length */
-    QRec *Q;
-    uint32_t *W;
-    int strideQ, strideW;
-    StackRec *ent;
-    uint32_t arena_cap;
-    Rec *recs;
-    int rec_cap;
     int recs_by_work; /* slab index: work item (large pass) or read (fast pass) */
     int32_t *n_aln;
     int32_t *over_slot; /* re-run passes: over_slot[r] = work item | slot_tag */
@@ -162,16 +155,34 @@ template <> struct HeadsFactory<HeadsWide32> {
     }
 };
 
-template <class Heads, bool REUSE, int MINB>
+template <class Heads> struct HeadsClear { /* all lanes of the warp empty the bucket heads of lane `src` */
+    static __device__ __forceinline__ void run(const Heads &, int, int, int) {}
+    static constexpr bool cooperative = false;
+};
+template <> struct HeadsClear<HeadsStrided16> {
+    static __device__ __forceinline__ void run(const HeadsStrided16 &hd, int nb, int lane, int src)
+    { /* hd.h is this lane's column; column of lane src = hd.h - lane + src */
+        uint16_t *col = hd.h - lane + src;
+        for (int b = lane; b < nb; b += 32) col[(size_t)b * hd.stride] = 0xffffu;
+    }
+    static constexpr bool cooperative = true;
+};
+template <> struct HeadsClear<HeadsStrided32> {
+    static __device__ __forceinline__ void run(const HeadsStrided32 &hd, int nb, int lane, int src)
+    {
+        uint32_t *col = hd.h - lane + src;
+        for (int b = lane; b < nb; b += 32) col[(size_t)b * hd.stride] = B2_NIL;
+    }
+    static constexpr bool cooperative = true;
+};
+
+template <class Heads, bool REUSE, int MINB, bool STATS>
 __global__ void __launch_bounds__(128, MINB) k_search(const __grid_constant__ SearchArgs A)
 {
     const unsigned FULL = 0xffffffffu;
     const int lane = threadIdx.x & 31;
     const size_t gl = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-    Arena ar;
-    ar.ent = A.ent + gl * A.arena_cap;
-    ar.cap = A.arena_cap;
-    SearchLane<Heads, REUSE> L;
+    SearchLane<Heads, REUSE, STATS> L;
     L.finished = true;
     const Heads heads = HeadsFactory<Heads>::make(A, gl);
     __shared__ uint32_t sm_group[OG_WORDS * 128]; /* the lanes' open groups, one conflict-free column each */
@@ -191,14 +202,17 @@ __global__ void __launch_bounds__(128, MINB) k_search(const __grid_constant__ Se
             unsigned base = 0;
             if (lane == leader) base = atomicAdd(A.counter, (unsigned)__popc(m));
             base = __shfl_sync(FULL, base, leader);
+            if (HeadsClear<Heads>::cooperative) { /* shared-memory heads of the claiming lanes, emptied by the whole warp */
+                for (unsigned mm = m; mm; mm &= mm - 1u) HeadsClear<Heads>::run(heads, A.env.P.n_buckets, lane, __ffs((int)mm) - 1);
+                __syncwarp();
+            }
             if (need) {
                 w = base + (unsigned)__popc(m & ((1u << lane) - 1u));
                 if (w < (unsigned)A.n_work) {
                     r = A.work_list ? A.work_list[w] : (int)w;
                     const int len = A.lens[r];
-                    const size_t slab = A.recs_by_work ? (size_t)w : (size_t)r;
-                    L.begin(A.env, ar, heads, gs, A.Q + (size_t)2 * r * A.strideQ, A.W + (size_t)2 * r * A.strideW, A.strideQ,
-                            A.strideW, A.recs + slab * A.rec_cap, A.rec_cap, len, A.md[len], A.n_amb[r]);
+                    L.begin(A.env, heads, gs, (uint32_t)gl, (uint32_t)r, A.recs_by_work ? w : (uint32_t)r, len, A.md[len],
+                            A.n_amb[r], HeadsClear<Heads>::cooperative);
                     active = true;
                 } else alive = false;
             }
@@ -221,8 +235,10 @@ __global__ void __launch_bounds__(128, MINB) k_search(const __grid_constant__ Se
         __syncwarp();
         if (active) {
             if (L.finished) {
-                pops += L.n_pops;
-                sectors += L.n_lookups;
+                if (STATS) {
+                    pops += L.n_pops;
+                    sectors += L.n_lookups;
+                }
                 if (L.status != LANE_OK) {
                     A.n_aln[r] = 0;
                     if (A.over_list) {
@@ -237,7 +253,7 @@ __global__ void __launch_bounds__(128, MINB) k_search(const __grid_constant__ Se
             }
         }
     }
-    if (pops) {
+    if (STATS && pops) {
         atomicAdd(A.stat + 0, pops);
         atomicAdd(A.stat + 1, sectors);
     }
@@ -416,6 +432,7 @@ struct b200aln_ctx {
     uint32_t arena_cap_mid = 8192; /* middle pass: 16-bit heads in shared memory, free-list arena */
     int rec_cap_mid = 512, mid_lanes = 148 * 128 * 2;
     int prefetch_fast = 0, prefetch_mid = 1; /* L2 prefetch of the next pop candidate, per pass */
+    int count = 0;         /* 1: fast pass with the pop / sector counters (b200aln_stats_t pops, occ_lookups) */
     int pop_batch = 1;     /* memory pops are taken when this many lanes of a warp wait for one */
     int lut_k = 14;        /* levels of the path-k-mer interval table (0 = off) */
     uint32_t *d_lut[2] = {nullptr, nullptr}; /* [0]: the table of both indexes */
@@ -608,7 +625,7 @@ extern "C" b200aln_ctx *b200aln_clone(b200aln_ctx *p)
     c->arena_cap = p->arena_cap; c->arena_cap_big = p->arena_cap_big;
     c->rec_cap = p->rec_cap; c->rec_cap_big = p->rec_cap_big; c->big_lanes = p->big_lanes;
     c->arena_cap_mid = p->arena_cap_mid; c->rec_cap_mid = p->rec_cap_mid; c->mid_lanes = p->mid_lanes;
-    c->pop_batch = p->pop_batch;
+    c->pop_batch = p->pop_batch; c->count = p->count;
     c->prefetch_fast = p->prefetch_fast; c->prefetch_mid = p->prefetch_mid;
     CK(cudaStreamCreateWithFlags(&c->st, cudaStreamNonBlocking));
     for (int i = 0; i < 8; ++i) CK(cudaEventCreate(&c->ev[i]));
@@ -683,6 +700,7 @@ extern "C" void b200aln_set_int(b200aln_ctx *c, const char *key, int64_t v)
     else if (!strcmp(key, "rec_cap_big")) c->rec_cap_big = (int)v;
     else if (!strcmp(key, "big_lanes")) c->big_lanes = (int)v;
     else if (!strcmp(key, "pop_batch")) c->pop_batch = (int)v;
+    else if (!strcmp(key, "count")) c->count = (int)v;
     else if (!strcmp(key, "prefetch_fast")) c->prefetch_fast = (int)v;
     else if (!strcmp(key, "prefetch_mid")) c->prefetch_mid = (int)v;
     else if (!strcmp(key, "arena_cap_mid")) c->arena_cap_mid = (uint32_t)v;
@@ -729,23 +747,24 @@ static bool fast_heads_ok(const Params &P, uint32_t arena_cap) { return P.n_buck
 static void launch_search_mid(b200aln_ctx *c, SearchArgs &A, int blocks)
 { /* middle pass: 16-bit shared-memory heads, free-list arena (capacity = stack high-water, not total pushes) */
     const size_t smem = (size_t)A.env.P.n_buckets * 128 * sizeof(uint16_t);
-    k_search<HeadsStrided16, true, 1><<<blocks, 128, smem, c->st>>>(A);
+    k_search<HeadsStrided16, true, 1, true><<<blocks, 128, smem, c->st>>>(A);
     CK(cudaGetLastError());
 }
 
 static void launch_search_fast(b200aln_ctx *c, SearchArgs &A, int blocks)
 {
-    if (fast_heads_ok(A.env.P, A.arena_cap)) {
+    if (fast_heads_ok(A.env.P, A.env.arena_cap)) {
         const size_t smem = (size_t)A.env.P.n_buckets * 128 * sizeof(uint16_t);
-        if (c->search_blocks_per_sm > 7) k_search<HeadsStrided16, false, 8><<<blocks, 128, smem, c->st>>>(A);
-        else if (c->search_blocks_per_sm == 7) k_search<HeadsStrided16, false, 7><<<blocks, 128, smem, c->st>>>(A);
-        else if (c->search_blocks_per_sm == 6) k_search<HeadsStrided16, false, 6><<<blocks, 128, smem, c->st>>>(A);
-        else k_search<HeadsStrided16, false, 1><<<blocks, 128, smem, c->st>>>(A);
+        if (c->count) k_search<HeadsStrided16, false, 6, true><<<blocks, 128, smem, c->st>>>(A); /* with pop / sector counters */
+        else if (c->search_blocks_per_sm > 7) k_search<HeadsStrided16, false, 8, false><<<blocks, 128, smem, c->st>>>(A);
+        else if (c->search_blocks_per_sm == 7) k_search<HeadsStrided16, false, 7, false><<<blocks, 128, smem, c->st>>>(A);
+        else if (c->search_blocks_per_sm == 6) k_search<HeadsStrided16, false, 6, false><<<blocks, 128, smem, c->st>>>(A);
+        else k_search<HeadsStrided16, false, 1, false><<<blocks, 128, smem, c->st>>>(A);
     } else {
         A.heads_wide_stride = A.env.P.n_buckets + (A.env.P.n_buckets + 31) / 32;
         c->heads_wide.need((size_t)blocks * 128 * A.heads_wide_stride * 4);
         A.heads_wide = c->heads_wide.as<uint32_t>();
-        k_search<HeadsWide32, false, 1><<<blocks, 128, 0, c->st>>>(A);
+        k_search<HeadsWide32, false, 1, true><<<blocks, 128, 0, c->st>>>(A);
     }
     CK(cudaGetLastError());
 }
@@ -754,14 +773,14 @@ static void launch_search_big(b200aln_ctx *c, SearchArgs &A, int blocks)
 {
     const size_t smem32 = (size_t)A.env.P.n_buckets * 128 * sizeof(uint32_t);
     if (smem32 + OG_WORDS * 128 * sizeof(uint32_t) <= 48 * 1024) { /* 32-bit heads still fit in shared memory (next to the open groups) */
-        k_search<HeadsStrided32, true, 1><<<blocks, 128, smem32, c->st>>>(A);
+        k_search<HeadsStrided32, true, 1, true><<<blocks, 128, smem32, c->st>>>(A);
         CK(cudaGetLastError());
         return;
     }
     A.heads_wide_stride = A.env.P.n_buckets + (A.env.P.n_buckets + 31) / 32;
     c->heads_wide_big.need((size_t)blocks * 128 * A.heads_wide_stride * 4);
     A.heads_wide = c->heads_wide_big.as<uint32_t>();
-    k_search<HeadsWide32, true, 1><<<blocks, 128, 0, c->st>>>(A);
+    k_search<HeadsWide32, true, 1, true><<<blocks, 128, 0, c->st>>>(A);
     CK(cudaGetLastError());
 }
 
@@ -814,9 +833,9 @@ static void run_batch_device(b200aln_ctx *c, int n_reads, int max_len, const int
     SA.env.prefetch_next = c->prefetch_fast;
     SA.n_work = n_reads; SA.work_list = nullptr;
     SA.lens = d_lens; SA.n_amb = c->n_amb.as<int32_t>(); SA.md = c->md.as<int32_t>();
-    SA.Q = WA.Q; SA.W = WA.W; SA.strideQ = strideQ; SA.strideW = strideW;
-    SA.ent = c->ent.as<StackRec>(); SA.arena_cap = c->arena_cap;
-    SA.recs = c->recs.as<Rec>(); SA.rec_cap = c->rec_cap; SA.recs_by_work = 0;
+    SA.env.Q = WA.Q; SA.env.W = WA.W; SA.env.strideQ = strideQ; SA.env.strideW = strideW;
+    SA.env.ent = c->ent.as<StackRec>(); SA.env.arena_cap = c->arena_cap;
+    SA.env.recs = c->recs.as<Rec>(); SA.env.rec_cap = c->rec_cap; SA.recs_by_work = 0;
     SA.n_aln = c->n_aln.as<int32_t>(); SA.over_slot = nullptr; SA.slot_tag = 0;
     SA.counter = &dm->counter; SA.n_over = &dm->n_over; SA.over_list = c->over_list.as<int32_t>();
     SA.stat = dm->stat;
@@ -860,8 +879,8 @@ static void run_batch_device(b200aln_ctx *c, int n_reads, int max_len, const int
         ++launches;
         SearchArgs SM = SA;
         SM.n_work = (int)n_over; SM.work_list = c->over_list.as<int32_t>();
-        SM.ent = c->ent_mid.as<StackRec>(); SM.arena_cap = c->arena_cap_mid;
-        SM.recs = c->recs_mid.as<Rec>(); SM.rec_cap = c->rec_cap_mid; SM.recs_by_work = 1;
+        SM.env.ent = c->ent_mid.as<StackRec>(); SM.env.arena_cap = c->arena_cap_mid;
+        SM.env.recs = c->recs_mid.as<Rec>(); SM.env.rec_cap = c->rec_cap_mid; SM.recs_by_work = 1;
         SM.over_slot = c->over_slot.as<int32_t>(); SM.slot_tag = 0;
         SM.env.prefetch_next = c->prefetch_mid;
         SM.counter = &dm->counter_mid; SM.n_over = &dm->n_over2; SM.over_list = c->over_list2.as<int32_t>();
@@ -887,8 +906,8 @@ static void run_batch_device(b200aln_ctx *c, int n_reads, int max_len, const int
         ++launches;
         SearchArgs SB = SA;
         SB.n_work = (int)n_wide; SB.work_list = wide_list;
-        SB.ent = c->ent_big.as<StackRec>(); SB.arena_cap = cap_big;
-        SB.recs = c->recs_big.as<Rec>(); SB.rec_cap = c->rec_cap_big; SB.recs_by_work = 1;
+        SB.env.ent = c->ent_big.as<StackRec>(); SB.env.arena_cap = cap_big;
+        SB.env.recs = c->recs_big.as<Rec>(); SB.env.rec_cap = c->rec_cap_big; SB.recs_by_work = 1;
         SB.over_slot = c->over_slot.as<int32_t>(); SB.slot_tag = WIDE_TAG;
         SB.env.prefetch_next = c->prefetch_mid;
         SB.counter = &dm->counter_big; SB.n_over = nullptr; SB.over_list = nullptr;

@@ -120,7 +120,7 @@ typedef struct {
     double ms_h2d, ms_width, ms_search, ms_compact, ms_d2h, ms_total; /* CUDA-event times */
     uint64_t kernel_launches; /* kernels of this library launched by the call */
     uint64_t overflow_reads;  /* reads re-run with the large per-read arena */
-    uint64_t pops, occ_lookups; /* only filled when built with B200ALN_COUNTERS */
+    uint64_t pops, occ_lookups; /* stack pops / 32-byte index sectors of the fast pass; filled when the knob `count` is 1 */
 } b200aln_stats_t;
 void b200aln_last_stats(const b200aln_ctx *ctx, b200aln_stats_t *out);
 
@@ -137,7 +137,8 @@ double b200aln_timer_stop(b200aln_ctx *ctx);
  *   lut_k          levels of the path-k-mer interval table built at open (default 14 = max, 0 = off).
  *   search_blocks_per_sm, width_blocks_per_sm, arena_cap, arena_cap_mid, arena_cap_big, rec_cap, rec_cap_mid,
  *   rec_cap_big, mid_lanes, big_lanes:
- *                  launch geometry and per-lane capacities. */
+ *                  launch geometry and per-lane capacities; arena capacities count 64-byte records.
+ *   count          1: the fast pass runs with its pop / sector counters (b200aln_stats_t pops, occ_lookups). */
 void b200aln_set_int(b200aln_ctx *ctx, const char *key, int64_t value);
 
 /*

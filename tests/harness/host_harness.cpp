@@ -71,9 +71,11 @@ static int64_t run(const SearchEnv &env, const std::vector<int> &md, int n_reads
         int n_amb = width_pass(fm[0], fwd, len, 0, comp, seed_len, W.data(), Q.data());
         width_pass(fm[1], fwd, len, 1, comp, seed_len, W.data() + strideW, Q.data() + strideQ);
         SearchLane<Heads, REUSE> lane;
-        Arena ar; ar.ent = ent.data(); ar.cap = arena_cap;
-        lane.begin(env, ar, make_heads<Heads>(hstore), gs, Q.data(), W.data(), strideQ, strideW, recs.data(), rec_cap, len, md[len], n_amb);
-        while (!lane.finished) lane.step(env);
+        SearchEnv e1 = env;
+        e1.Q = Q.data(); e1.W = W.data(); e1.strideQ = strideQ; e1.strideW = strideW;
+        e1.recs = recs.data(); e1.rec_cap = rec_cap; e1.ent = ent.data(); e1.arena_cap = arena_cap;
+        lane.begin(e1, make_heads<Heads>(hstore), gs, 0, 0, 0, len, md[len], n_amb);
+        while (!lane.finished) lane.step(e1);
         if (lane.status != LANE_OK && big_cap) {
             /* the product's large pass: widths rebuilt (the aborted pass shadowed them), free-list arena */
             ++n_status;
@@ -81,9 +83,10 @@ static int64_t run(const SearchEnv &env, const std::vector<int> &md, int n_reads
             n_amb = width_pass(fm[0], fwd, len, 0, comp, seed_len, W.data(), Q.data());
             width_pass(fm[1], fwd, len, 1, comp, seed_len, W.data() + strideW, Q.data() + strideQ);
             SearchLane<HeadsWide32, true> big;
-            Arena ar2; ar2.ent = ent2.data(); ar2.cap = big_cap;
-            big.begin(env, ar2, make_heads<HeadsWide32>(hstore), gs, Q.data(), W.data(), strideQ, strideW, recs2.data(), 1 << 16, len, md[len], n_amb);
-            while (!big.finished) big.step(env);
+            SearchEnv e2 = e1;
+            e2.recs = recs2.data(); e2.rec_cap = 1 << 16; e2.ent = ent2.data(); e2.arena_cap = big_cap;
+            big.begin(e2, make_heads<HeadsWide32>(hstore), gs, 0, 0, 0, len, md[len], n_amb);
+            while (!big.finished) big.step(e2);
             if (big.status != LANE_OK) { n_aln[r] = -big.status; continue; }
             n_aln[r] = big.n_aln;
             all.insert(all.end(), recs2.begin(), recs2.begin() + big.n_aln);

@@ -27,6 +27,7 @@
 
 #include "../../include/b200aln.h"
 #include "aln_core.cuh"
+#include "alngrp_core.cuh"
 #include "fm_layout.cuh"
 #include "host_params.h"
 
@@ -339,6 +340,33 @@ __global__ void __launch_bounds__(256) k_compact(int n, const int32_t *n_aln, co
 /* random sector gather: the roofline denominator.  span = 1: independent random
  * 32-byte sectors; span = 2: random 64-byte aligned pairs of sectors (tells whether the memory
  * system moves 64 B per miss anyway). */
+/* row N4: one thread per read merges the read's alignments from every stream (alngrp_core.cuh) */
+#define B2_MAX_STREAMS 16
+struct GrpArgs {
+    int n_streams, s_mm;
+    int64_t n_reads;
+    const int32_t *n_aln[B2_MAX_STREAMS];
+    const int64_t *rec_off[B2_MAX_STREAMS];
+    const Rec *recs[B2_MAX_STREAMS];
+    const int64_t *out_off;
+    int32_t *out_n;
+    Rec *out_rec;
+    uint32_t *out_db;
+};
+__global__ void __launch_bounds__(128) k_alngrp_totals(const __grid_constant__ GrpArgs A, int32_t *tot)
+{
+    for (int64_t r = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; r < A.n_reads; r += (int64_t)gridDim.x * blockDim.x) {
+        int32_t t = 0;
+        for (int s = 0; s < A.n_streams; ++s) t += A.n_aln[s][r];
+        tot[r] = t;
+    }
+}
+__global__ void __launch_bounds__(128) k_alngrp(const __grid_constant__ GrpArgs A)
+{
+    for (int64_t r = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; r < A.n_reads; r += (int64_t)gridDim.x * blockDim.x)
+        A.out_n[r] = alngrp_merge_one(A.n_streams, r, A.n_aln, A.rec_off, A.recs, A.s_mm, A.out_off[r], A.out_rec, A.out_db);
+}
+
 __global__ void __launch_bounds__(256) k_sector_gather(const OccBlk *blk, uint64_t n_blocks, uint64_t loads_per_thread,
                                                        int span, unsigned long long *sink)
 {
@@ -444,7 +472,7 @@ struct b200aln_ctx {
     int batch_max_len = 0; /* > 0: the reference batch this call is a shard of has this longest read */
     /* device buffers */
     DevBuf lens, offs, codes, md, Q, W, n_amb, ent, recs, n_aln, over_slot, over_list, misc, off64,
-        blk_tot, packed, ent_big, recs_big, heads_wide, heads_wide_big, ent_mid, recs_mid, over_list2, sa_in, sa_out;
+        blk_tot, packed, ent_big, recs_big, heads_wide, heads_wide_big, ent_mid, recs_mid, over_list2, sa_in, sa_out, grp_in, grp_out;
     HostBuf h_in, h_out, h_misc;
     b200aln_stats_t stats;
 };
@@ -678,6 +706,7 @@ extern "C" void b200aln_close(b200aln_ctx *c)
                       &c->packed, &c->ent_big, &c->recs_big, &c->heads_wide, &c->heads_wide_big, &c->ent_mid, &c->recs_mid,
                       &c->over_list2, &c->sa_in, &c->sa_out};
     for (DevBuf *b : bufs) b->release();
+    c->grp_in.release(); c->grp_out.release();
     c->h_in.release(); c->h_out.release(); c->h_misc.release();
     if (c->owns_index) {
         for (int i = 0; i < 2; ++i) if (c->d_sa[i]) cudaFree(c->d_sa[i]);
@@ -1085,6 +1114,76 @@ extern "C" void b200aln_sa2seq(b200aln_ctx *c, int64_t n, const uint8_t *strand,
     CK(cudaGetLastError());
     CK(cudaMemcpyAsync(pos, c->sa_out.p, (size_t)n * 8, cudaMemcpyDeviceToHost, c->st));
     CK(cudaStreamSynchronize(c->st));
+}
+
+static void scan_i32(b200aln_ctx *c, const int32_t *in, int n, int64_t *out, int64_t *total_dev)
+{ /* exclusive prefix sum on the engine's stream (the three scan kernels of the batch path) */
+    const int nscan = (n + SCAN_ITEMS - 1) / SCAN_ITEMS;
+    c->blk_tot.need((size_t)nscan * 8 + 8);
+    k_scan_totals<<<nscan, 256, 0, c->st>>>(in, n, c->blk_tot.as<int64_t>());
+    k_scan_blocks<<<1, 32, 0, c->st>>>(c->blk_tot.as<int64_t>(), nscan, total_dev);
+    k_scan_apply<<<nscan, 256, 0, c->st>>>(in, n, c->blk_tot.as<int64_t>(), out);
+    CK(cudaGetLastError());
+}
+
+extern "C" int64_t b200aln_alngrp_merge(b200aln_ctx *c, int n_streams, int n_reads, const int32_t *const *n_aln,
+                                        const b200aln_rec_t *const *recs, int s_mm, int64_t *out_off, int32_t *out_n,
+                                        b200aln_rec_t *out_recs, uint32_t *out_dbidx)
+{
+    CK(cudaSetDevice(c->device));
+    if (n_streams < 1 || n_streams > B2_MAX_STREAMS) die("b200aln_alngrp_merge", "1 to %d streams, got %d.", B2_MAX_STREAMS, n_streams);
+    if (n_reads <= 0) return 0;
+    std::vector<int64_t> tot(n_streams, 0);
+    int64_t all = 0;
+    for (int s = 0; s < n_streams; ++s) {
+        for (int r = 0; r < n_reads; ++r) {
+            if (n_aln[s][r] < 0) die("b200aln_alngrp_merge", "stream %d read %d: negative count.", s, r);
+            tot[s] += n_aln[s][r];
+        }
+        all += tot[s];
+    }
+    /* device input: per stream [n_aln | offsets | records], then the per-read totals; output: offsets | n | records | db */
+    const size_t nr = (size_t)n_reads;
+    size_t in_bytes = 0;
+    std::vector<size_t> at_n(n_streams), at_off(n_streams), at_rec(n_streams);
+    auto take = [&](size_t bytes) { size_t at = in_bytes; in_bytes += (bytes + 63) & ~(size_t)63; return at; };
+    for (int s = 0; s < n_streams; ++s) {
+        at_n[s] = take(nr * 4);
+        at_off[s] = take(nr * 8);
+        at_rec[s] = take((size_t)tot[s] * 16 + 16);
+    }
+    const size_t at_tot = take(nr * 4), at_sum = take(64);
+    c->grp_in.need(in_bytes);
+    size_t out_bytes = 0;
+    auto take_o = [&](size_t bytes) { size_t at = out_bytes; out_bytes += (bytes + 63) & ~(size_t)63; return at; };
+    const size_t o_off = take_o(nr * 8), o_n = take_o(nr * 4), o_rec = take_o((size_t)all * 16 + 16), o_db = take_o((size_t)all * 4 + 16);
+    c->grp_out.need(out_bytes);
+    char *din = c->grp_in.as<char>(), *dout = c->grp_out.as<char>();
+    GrpArgs A;
+    A.n_streams = n_streams; A.s_mm = s_mm; A.n_reads = n_reads;
+    for (int s = 0; s < n_streams; ++s) {
+        CK(cudaMemcpyAsync(din + at_n[s], n_aln[s], nr * 4, cudaMemcpyHostToDevice, c->st));
+        if (tot[s]) CK(cudaMemcpyAsync(din + at_rec[s], recs[s], (size_t)tot[s] * 16, cudaMemcpyHostToDevice, c->st));
+        A.n_aln[s] = (const int32_t *)(din + at_n[s]);
+        A.rec_off[s] = (const int64_t *)(din + at_off[s]);
+        A.recs[s] = (const Rec *)(din + at_rec[s]);
+        scan_i32(c, A.n_aln[s], n_reads, (int64_t *)(din + at_off[s]), (int64_t *)(din + at_sum));
+    }
+    A.out_off = (const int64_t *)(dout + o_off); A.out_n = (int32_t *)(dout + o_n);
+    A.out_rec = (Rec *)(dout + o_rec); A.out_db = (uint32_t *)(dout + o_db);
+    k_alngrp_totals<<<c->n_sm * 4, 128, 0, c->st>>>(A, (int32_t *)(din + at_tot));
+    CK(cudaGetLastError());
+    scan_i32(c, (const int32_t *)(din + at_tot), n_reads, (int64_t *)(dout + o_off), (int64_t *)(din + at_sum));
+    k_alngrp<<<c->n_sm * 8, 128, 0, c->st>>>(A);
+    CK(cudaGetLastError());
+    CK(cudaMemcpyAsync(out_off, dout + o_off, nr * 8, cudaMemcpyDeviceToHost, c->st));
+    CK(cudaMemcpyAsync(out_n, dout + o_n, nr * 4, cudaMemcpyDeviceToHost, c->st));
+    if (all) {
+        CK(cudaMemcpyAsync(out_recs, dout + o_rec, (size_t)all * 16, cudaMemcpyDeviceToHost, c->st));
+        CK(cudaMemcpyAsync(out_dbidx, dout + o_db, (size_t)all * 4, cudaMemcpyDeviceToHost, c->st));
+    }
+    CK(cudaStreamSynchronize(c->st));
+    return all;
 }
 
 extern "C" double b200aln_sector_roofline(b200aln_ctx *c, uint64_t n_loads, int repeats)

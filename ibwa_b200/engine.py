@@ -51,7 +51,7 @@ class SeqLayout(ctypes.Structure):
 EXPORTS = ["b200aln_version", "b200aln_opt_init", "b200aln_cal_maxdiff", "b200aln_device_count", "b200aln_open",
            "b200aln_open_prefix", "b200aln_clone", "b200aln_close", "b200aln_batch", "b200aln_batch_device", "b200aln_last_stats",
            "b200aln_set_int", "b200aln_timer_start", "b200aln_timer_stop", "b200aln_cal_sa_reg_gap", "b200aln_seq_layout", "b200aln_aln_core", "b200aln_aln_main", "b200aln_reader_open", "b200aln_reader_next", "b200aln_reader_close",
-           "b200aln_sector_roofline", "b200aln_sa_load", "b200aln_bwt_sa", "b200aln_sa2seq"]
+           "b200aln_sector_roofline", "b200aln_sa_load", "b200aln_bwt_sa", "b200aln_sa2seq", "b200aln_alngrp_merge"]
 
 _lib = None
 
@@ -97,6 +97,9 @@ def load_library():
     L.b200aln_bwt_sa.argtypes = [ctypes.c_void_p, ctypes.c_int, ctypes.c_int64, ctypes.c_void_p, ctypes.c_void_p]
     L.b200aln_sa2seq.argtypes = [ctypes.c_void_p, ctypes.c_int64, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p,
                                  ctypes.c_void_p]
+    L.b200aln_alngrp_merge.restype = ctypes.c_int64
+    L.b200aln_alngrp_merge.argtypes = [ctypes.c_void_p, ctypes.c_int, ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p,
+                                       ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p]
     L.b200aln_reader_open.restype = ctypes.c_void_p
     L.b200aln_reader_open.argtypes = [ctypes.c_char_p, ctypes.c_int]
     L.b200aln_reader_next.restype = ctypes.c_int
@@ -219,6 +222,24 @@ class Engine:
         self._L.b200aln_sa2seq(self._ctx, len(rows), strand.ctypes.data, rows.ctypes.data, lens.ctypes.data,
                                out.ctypes.data)
         return out
+
+    def alngrp_merge(self, n_alns, recs, s_mm: int):
+        """alngrp_create (saiset.c:45-78) for a batch: n_alns[s] / recs[s] = stream s as cal_sa_reg_gap returns it.
+        Returns (out_off int64[n], out_n int32[n], records ALN_DTYPE[total], dbidx uint32[total])."""
+        ns, n = len(n_alns), len(n_alns[0])
+        n_alns = [np.ascontiguousarray(a, dtype=np.int32) for a in n_alns]
+        recs = [np.ascontiguousarray(r, dtype=ALN_DTYPE) for r in recs]
+        total = int(sum(int(a.sum()) for a in n_alns))
+        pn = (ctypes.c_void_p * ns)(*[a.ctypes.data for a in n_alns])
+        pr = (ctypes.c_void_p * ns)(*[r.ctypes.data for r in recs])
+        out_off = np.zeros(n, dtype=np.int64)
+        out_n = np.zeros(n, dtype=np.int32)
+        out_rec = np.zeros(max(total, 1), dtype=ALN_DTYPE)
+        out_db = np.zeros(max(total, 1), dtype=np.uint32)
+        got = self._L.b200aln_alngrp_merge(self._ctx, ns, n, pn, pr, int(s_mm), out_off.ctypes.data, out_n.ctypes.data,
+                                           out_rec.ctypes.data, out_db.ctypes.data)
+        assert got == total
+        return out_off, out_n, out_rec[:total], out_db[:total]
 
     def timer_start(self) -> None:
         self._L.b200aln_timer_start(self._ctx)

@@ -208,6 +208,21 @@ void b200aln_bwt_sa(b200aln_ctx *ctx, int which, int64_t n, const uint32_t *rows
 void b200aln_sa2seq(b200aln_ctx *ctx, int64_t n, const uint8_t *strand, const uint32_t *rows, const int32_t *lens,
                     uint64_t *pos);
 
+/*
+ * Scope row N4: the per-read merge of several .sai streams (primary + alt indexes), i.e. alngrp_create
+ * (saiset.c:45-78) for a whole batch: per read the alignments of stream 0, 1, ... in that order; with more
+ * than one stream they are sorted by score exactly like the reference's ks_introsort(alignment)
+ * (ksort.h:172-224 — not stable, equal scores come out in the reference's order) and cut at the first
+ * score > best + s_mm.
+ *   n_aln[s][r], recs[s]   stream s as b200aln_batch returns it (records packed in read order), host buffers
+ *   out_off[r]             first slot of read r's group = sum of the unmerged group sizes of reads < r
+ *   out_n[r]               size of the merged group;  out_recs / out_dbidx: records and the stream each came from
+ * out_recs / out_dbidx must hold the sum of all counts, which is also the return value.
+ */
+int64_t b200aln_alngrp_merge(b200aln_ctx *ctx, int n_streams, int n_reads, const int32_t *const *n_aln,
+                             const b200aln_rec_t *const *recs, int s_mm, int64_t *out_off, int32_t *out_n,
+                             b200aln_rec_t *out_recs, uint32_t *out_dbidx);
+
 /* Random 32-byte-sector gather micro-benchmark over the device index (the
  * roofline denominator of SURVEY.md §8d): n_loads independent uniformly random
  * sector reads; returns GB/s (sectors * 32 B / CUDA-event time). */

@@ -584,3 +584,112 @@ uint64_t orc_sa2seq(const orc_bwt_t *bwt, const orc_sa_t *sa, const orc_bwt_t *r
     if (strand) return (uint64_t)orc_bwt_sa(bwt, sa, row);
     return (uint64_t)(uint32_t)(rbwt->seq_len - (orc_bwt_sa(rbwt, rsa, row) + (uint32_t)seq_len));
 }
+
+/* ---------------------------------- multi-.sai merge (N4) ---- */
+/* TEST INFRASTRUCTURE.  alngrp_create (saiset.c:45-78) for one read: the alignments of every stream, stream by
+ * stream; with more than one stream they are sorted with klib's introsort (ksort.h:172-224, comparator
+ * a.score < b.score, saiset.c:8-10) and cut at the first score > best + s_mm.  The sort is not stable, so it
+ * is restated step by step (same comparisons, same exchanges).  Pinned against the reference's own
+ * saiset.c through oracle/_ref/alngrp_dump (tests/test_alngrp.py). */
+typedef struct { orc_aln_t aln; uint32_t dbidx; } orc_galn_t;
+
+#define G_LT(a, b) ((a).aln.score < (b).aln.score)
+
+static void g_insertsort(orc_galn_t *s, orc_galn_t *t) /* ksort.h:142-149 */
+{
+    orc_galn_t *i, *j, tmp;
+    for (i = s + 1; i < t; ++i)
+        for (j = i; j > s && G_LT(*j, *(j - 1)); --j) { tmp = *j; *j = *(j - 1); *(j - 1) = tmp; }
+}
+
+static void g_combsort(size_t n, orc_galn_t *a) /* ksort.h:150-171 */
+{
+    const double shrink_factor = 1.2473309501039786540366528676643;
+    int do_swap;
+    size_t gap = n;
+    orc_galn_t tmp, *i, *j;
+    do {
+        if (gap > 2) {
+            gap = (size_t)(gap / shrink_factor);
+            if (gap == 9 || gap == 10) gap = 11;
+        }
+        do_swap = 0;
+        for (i = a; i < a + n - gap; ++i) {
+            j = i + gap;
+            if (G_LT(*j, *i)) { tmp = *i; *i = *j; *j = tmp; do_swap = 1; }
+        }
+    } while (do_swap || gap > 2);
+    if (gap != 1) g_insertsort(a, a + n);
+}
+
+static void g_introsort(size_t n, orc_galn_t *a) /* ksort.h:172-224 */
+{
+    struct { orc_galn_t *left, *right; int depth; } stack[8 * 66 + 2], *top = stack;
+    orc_galn_t rp, tmp, *s, *t, *i, *j, *k;
+    int d;
+    if (n < 1) return;
+    if (n == 2) {
+        if (G_LT(a[1], a[0])) { tmp = a[0]; a[0] = a[1]; a[1] = tmp; }
+        return;
+    }
+    for (d = 2; 1ul << d < n; ++d) {}
+    s = a; t = a + (n - 1); d <<= 1;
+    for (;;) {
+        if (s < t) {
+            if (--d == 0) { g_combsort(t - s + 1, s); t = s; continue; }
+            i = s; j = t; k = i + ((j - i) >> 1) + 1;
+            if (G_LT(*k, *i)) { if (G_LT(*k, *j)) k = j; }
+            else k = G_LT(*j, *i) ? i : j;
+            rp = *k;
+            if (k != t) { tmp = *k; *k = *t; *t = tmp; }
+            for (;;) {
+                do ++i; while (G_LT(*i, rp));
+                do --j; while (i <= j && G_LT(rp, *j));
+                if (j <= i) break;
+                tmp = *i; *i = *j; *j = tmp;
+            }
+            tmp = *i; *i = *t; *t = tmp;
+            if (i - s > t - i) {
+                if (i - s > 16) { top->left = s; top->right = i - 1; top->depth = d; ++top; }
+                s = t - i > 16 ? i + 1 : t;
+            } else {
+                if (t - i > 16) { top->left = i + 1; top->right = t; top->depth = d; ++top; }
+                t = i - s > 16 ? i - 1 : s;
+            }
+        } else {
+            if (top == stack) { g_insertsort(a, a + n); return; }
+            --top; s = top->left; t = top->right; d = top->depth;
+        }
+    }
+}
+
+/* whole batch: n_aln[s][r], recs[s] packed in read order; out_* sized for the sum of all counts;
+ * out_off[r] = first slot of read r (sum of the unmerged totals before it), out_n[r] = merged size */
+int64_t orc_alngrp_merge(int n_streams, int n_reads, const int32_t *const *n_aln, const orc_aln_t *const *recs, int s_mm,
+                         int64_t *out_off, int32_t *out_n, orc_aln_t *out_recs, uint32_t *out_dbidx)
+{
+    int64_t *pos = (int64_t *)calloc((size_t)n_streams, sizeof(int64_t)), at = 0;
+    orc_galn_t *g = NULL;
+    size_t cap = 0;
+    for (int r = 0; r < n_reads; ++r) {
+        size_t n = 0, i;
+        for (int s = 0; s < n_streams; ++s) n += (size_t)n_aln[s][r];
+        if (n > cap) { cap = n * 2 + 16; g = (orc_galn_t *)realloc(g, cap * sizeof *g); }
+        n = 0;
+        for (int s = 0; s < n_streams; ++s) /* saiset.c:51-62 */
+            for (int j = 0; j < n_aln[s][r]; ++j) { g[n].aln = recs[s][pos[s]++]; g[n].dbidx = (uint32_t)s; ++n; }
+        const size_t total = n;
+        if (n_streams > 1 && n > 0) { /* saiset.c:64-76 */
+            g_introsort(n, g);
+            const int best = g[0].aln.score;
+            for (i = 0; i < n; ++i)
+                if (g[i].aln.score > best + s_mm) { n = i; break; }
+        }
+        out_off[r] = at;
+        out_n[r] = (int32_t)n;
+        for (i = 0; i < n; ++i) { out_recs[at + (int64_t)i] = g[i].aln; out_dbidx[at + (int64_t)i] = g[i].dbidx; }
+        at += (int64_t)total;
+    }
+    free(g); free(pos);
+    return at;
+}

@@ -102,6 +102,27 @@ def bwt_sa(ob: OrcBwt, osa: OrcSa, rows) -> np.ndarray:
                     dtype=np.uint32)
 
 
+def alngrp_merge(n_alns, recs, s_mm: int):
+    """orc_alngrp_merge: (out_off, out_n, records, dbidx) — the layout of Engine.alngrp_merge."""
+    L = lib()
+    L.orc_alngrp_merge.restype = ctypes.c_int64
+    ns, n = len(n_alns), len(n_alns[0])
+    n_alns = [np.ascontiguousarray(a, dtype=np.int32) for a in n_alns]
+    recs = [np.ascontiguousarray(r, dtype=ALN_DTYPE) for r in recs]
+    total = int(sum(int(a.sum()) for a in n_alns))
+    pn = (ctypes.c_void_p * ns)(*[a.ctypes.data for a in n_alns])
+    pr = (ctypes.c_void_p * ns)(*[r.ctypes.data for r in recs])
+    out_off = np.zeros(n, dtype=np.int64)
+    out_n = np.zeros(n, dtype=np.int32)
+    out_rec = np.zeros(max(total, 1), dtype=ALN_DTYPE)
+    out_db = np.zeros(max(total, 1), dtype=np.uint32)
+    got = L.orc_alngrp_merge(ctypes.c_int(ns), ctypes.c_int(n), pn, pr, ctypes.c_int(int(s_mm)),
+                             ctypes.c_void_p(out_off.ctypes.data), ctypes.c_void_p(out_n.ctypes.data),
+                             ctypes.c_void_p(out_rec.ctypes.data), ctypes.c_void_p(out_db.ctypes.data))
+    assert got == total
+    return out_off, out_n, out_rec[:total], out_db[:total]
+
+
 def occ(ob: OrcBwt, k: int, c: int) -> int:
     return lib().orc_occ(ctypes.byref(ob), k & 0xFFFFFFFF, c)
 

@@ -15,6 +15,7 @@ extern "C" uint64_t *hh_dbg() { return b2::b2_dbg; }
 #endif
 #include "../../include/b200aln.h"
 #include "../../ibwa_b200/csrc/aln_core.cuh"
+#include "../../ibwa_b200/csrc/alngrp_core.cuh"
 #include "../../ibwa_b200/csrc/fm_layout.cuh"
 #include "../../ibwa_b200/csrc/host_params.h"
 
@@ -162,6 +163,27 @@ extern "C" void hh_bwt_sa(const b200aln_bwt_view_t *bwt, const uint32_t *sa, uin
     FmView f;
     f.blk = idx.data(); f.primary = bwt->primary; f.seq_len = bwt->seq_len; f.lut = nullptr; f.lut_k = 0; f.lut_w = 0;
     for (int64_t i = 0; i < n; ++i) out[i] = sa_of_row(f, sa, sa_intv, rows[i]);
+}
+
+/* row N4: the device merge code (alngrp_core.cuh) on the CPU, read by read */
+extern "C" int64_t hh_alngrp_merge(int n_streams, int n_reads, const int32_t *const *n_aln, const Rec *const *recs, int s_mm,
+                                   int64_t *out_off, int32_t *out_n, Rec *out_recs, uint32_t *out_db)
+{
+    std::vector<std::vector<int64_t>> off(n_streams, std::vector<int64_t>(n_reads));
+    std::vector<const int64_t *> offp(n_streams);
+    std::vector<int32_t> tot(n_reads, 0);
+    for (int s = 0; s < n_streams; ++s) {
+        int64_t at = 0;
+        for (int r = 0; r < n_reads; ++r) { off[s][r] = at; at += n_aln[s][r]; tot[r] += n_aln[s][r]; }
+        offp[s] = off[s].data();
+    }
+    int64_t at = 0;
+    for (int r = 0; r < n_reads; ++r) {
+        out_off[r] = at;
+        out_n[r] = alngrp_merge_one(n_streams, r, n_aln, offp.data(), recs, s_mm, at, out_recs, out_db);
+        at += tot[r];
+    }
+    return at;
 }
 
 extern "C" void hh_free(void *p) { free(p); }

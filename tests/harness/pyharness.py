@@ -10,6 +10,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.dirname(os.path.dirname(HERE))
 LIB = os.path.join(HERE, "libhostharness.so")
 SRCS = [os.path.join(HERE, "host_harness.cpp"), os.path.join(ROOT, "ibwa_b200", "csrc", "aln_core.cuh"),
+        os.path.join(ROOT, "ibwa_b200", "csrc", "alngrp_core.cuh"),
         os.path.join(ROOT, "ibwa_b200", "csrc", "fm_layout.cuh"), os.path.join(ROOT, "ibwa_b200", "csrc", "host_params.h")]
 ALN_DTYPE = np.dtype([("packed", "<u4"), ("k", "<u4"), ("l", "<u4"), ("score", "<i4")])
 
@@ -82,3 +83,24 @@ def bwt_sa(bwt, sa, rows):
     L.hh_bwt_sa(ctypes.byref(v), ctypes.c_void_p(arr.ctypes.data), ctypes.c_uint32(sa.sa_intv),
                 ctypes.c_int64(len(rows)), ctypes.c_void_p(rows.ctypes.data), ctypes.c_void_p(out.ctypes.data))
     return out
+
+
+def alngrp_merge(n_alns, recs, s_mm):
+    """alngrp_core.cuh (scope row N4) on the CPU; same layout as Engine.alngrp_merge."""
+    L = lib()
+    L.hh_alngrp_merge.restype = ctypes.c_int64
+    ns, n = len(n_alns), len(n_alns[0])
+    n_alns = [np.ascontiguousarray(a, dtype=np.int32) for a in n_alns]
+    recs = [np.ascontiguousarray(r, dtype=ALN_DTYPE) for r in recs]
+    total = int(sum(int(a.sum()) for a in n_alns))
+    pn = (ctypes.c_void_p * ns)(*[a.ctypes.data for a in n_alns])
+    pr = (ctypes.c_void_p * ns)(*[r.ctypes.data for r in recs])
+    out_off = np.zeros(n, np.int64)
+    out_n = np.zeros(n, np.int32)
+    out_rec = np.zeros(max(total, 1), ALN_DTYPE)
+    out_db = np.zeros(max(total, 1), np.uint32)
+    got = L.hh_alngrp_merge(ctypes.c_int(ns), ctypes.c_int(n), pn, pr, ctypes.c_int(int(s_mm)),
+                            ctypes.c_void_p(out_off.ctypes.data), ctypes.c_void_p(out_n.ctypes.data),
+                            ctypes.c_void_p(out_rec.ctypes.data), ctypes.c_void_p(out_db.ctypes.data))
+    assert got == total
+    return out_off, out_n, out_rec[:total], out_db[:total]

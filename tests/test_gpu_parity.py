@@ -105,8 +105,12 @@ def test_random_genome_vs_oracle(rand_index, model, args, length, n):
     offs = np.arange(n, dtype=np.int64) * length
     opt, _, _, _ = parse_aln_args(args + ["p", "q"])
     with engine.Engine(bwt, rbwt, 0) as e:
+        e.set("count", 1)      # fast pass with its pop counter
         n_aln, rec = e.cal_sa_reg_gap(lens, offs, reads.reshape(-1), opt)
         st = e.stats()
+        e.set("count", 0)      # and the product configuration (no counters) on the same reads
+        n_aln2, rec2 = e.cal_sa_reg_gap(lens, offs, reads.reshape(-1), opt)
+        assert np.array_equal(n_aln, n_aln2) and rec.tobytes() == rec2.tobytes()
     o_n, o_rec, ost = pyoracle.aln_batch(pyoracle.as_orc_bwt(bwt), pyoracle.as_orc_bwt(rbwt), lens, offs,
                                          reads.reshape(-1), opt.to_c())
     assert np.array_equal(n_aln, o_n)

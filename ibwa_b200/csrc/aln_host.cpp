@@ -14,16 +14,23 @@
 #include <ctype.h>
 #include <stdint.h>
 #include <stdio.h>
+#include <fcntl.h>
 #include <stdlib.h>
 #include <string.h>
+#include <sys/mman.h>
+#include <sys/stat.h>
 #include <time.h>
 #include <unistd.h>
 #include <zlib.h>
 
 #include <algorithm>
+#include <chrono>
+#include <condition_variable>
 #include <deque>
+#include <functional>
 #include <future>
 #include <memory>
+#include <mutex>
 #include <string>
 #include <thread>
 #include <vector>
@@ -32,6 +39,7 @@
 #include "host_params.h"
 
 struct b200aln_reader;
+extern "C" void b200aln_warm_device(int device); /* b200aln.cu: creates the CUDA context */
 
 namespace {
 
@@ -55,19 +63,134 @@ struct Nt4Table {
 };
 const Nt4Table g_nt4;
 
+/* conversion table of the fast path: nt4 code in the low bits, bit 7 set for a character the fast path must
+ * not accept in a sequence line (not graphic, or one of '>', '+', '@' which end the sequence in kseq.h:167) */
+struct SeqClassTable {
+    uint8_t t[256];
+    SeqClassTable()
+    {
+        for (int c = 0; c < 256; ++c) {
+            const bool bad = c <= 32 || c >= 127 || c == '>' || c == '+' || c == '@';
+            t[c] = (uint8_t)(g_nt4.t[c] | (bad ? 0x80 : 0));
+        }
+    }
+};
+const SeqClassTable g_seqclass;
+
+/* persistent worker threads for the record conversion (one pool per process) */
+class ParsePool {
+  public:
+    static ParsePool &get()
+    {
+        static ParsePool p;
+        return p;
+    }
+    unsigned size() const { return n_; }
+    /* runs fn(0..size-1), fn(0) on the caller */
+    void run(const std::function<void(unsigned)> &fn)
+    {
+        if (n_ == 1) { fn(0); return; }
+        std::lock_guard<std::mutex> one_at_a_time(run_m_); /* several readers may share the pool */
+        {
+            std::lock_guard<std::mutex> g(m_);
+            fn_ = &fn;
+            pending_ = n_ - 1;
+            ++epoch_;
+        }
+        cv_.notify_all();
+        fn(0);
+        std::unique_lock<std::mutex> g(m_);
+        done_.wait(g, [&] { return pending_ == 0; });
+        fn_ = nullptr;
+    }
+
+  private:
+    ParsePool()
+    {
+        const char *e = getenv("B200ALN_PARSE_THREADS");
+        unsigned t = e ? (unsigned)atoi(e) : std::thread::hardware_concurrency();
+        n_ = t < 1 ? 1u : (t > 32 ? 32u : t);
+        for (unsigned i = 1; i < n_; ++i) th_.emplace_back([this, i] { loop(i); });
+    }
+    ~ParsePool()
+    {
+        {
+            std::lock_guard<std::mutex> g(m_);
+            stop_ = true;
+            ++epoch_;
+        }
+        cv_.notify_all();
+        for (auto &t : th_) t.join();
+    }
+    void loop(unsigned id)
+    {
+        uint64_t seen = 0;
+        for (;;) {
+            const std::function<void(unsigned)> *fn;
+            {
+                std::unique_lock<std::mutex> g(m_);
+                cv_.wait(g, [&] { return epoch_ != seen; });
+                seen = epoch_;
+                if (stop_) return;
+                fn = fn_;
+            }
+            (*fn)(id);
+            std::lock_guard<std::mutex> g(m_);
+            if (--pending_ == 0) done_.notify_one();
+        }
+    }
+    unsigned n_ = 1;
+    std::vector<std::thread> th_;
+    std::mutex m_, run_m_;
+    std::condition_variable cv_, done_;
+    const std::function<void(unsigned)> *fn_ = nullptr;
+    unsigned pending_ = 0;
+    uint64_t epoch_ = 0;
+    bool stop_ = false;
+};
+
 /* buffered reader + record parser with the reference parser's observable
  * behaviour (kseq.h:60-71,150-194): multi-line records, name = first
  * whitespace-delimited token, only isgraph() characters enter the sequence,
  * reading stops at the first truncated record. */
 class SeqReader {
   public:
-    explicit SeqReader(const char *fn) : buf_((size_t)160 << 20)
+    explicit SeqReader(const char *fn)
     {
-        if (strcmp(fn, "-") == 0) f_ = gzdopen(fileno(stdin), "r"); /* utils.c:56-66 */
-        else f_ = gzopen(fn, "r");
-        if (!f_) b2host::fatal("b200aln_aln_core", (std::string("fail to open file '") + fn + "'.").c_str());
+        /* A plain (not gzip) regular file is mapped: the whole file is "the buffer", nothing is copied.
+         * Everything else — gzip, stdin, pipes — goes through zlib like the reference (utils.c:56-66). */
+        if (strcmp(fn, "-") != 0 && !getenv("B200ALN_NO_MMAP")) {
+            const int fd = open(fn, O_RDONLY);
+            struct stat st;
+            if (fd >= 0 && fstat(fd, &st) == 0 && S_ISREG(st.st_mode) && st.st_size > 0) {
+                unsigned char magic[2] = {0, 0};
+                if (pread(fd, magic, 2, 0) == 2 && !(magic[0] == 0x1f && magic[1] == 0x8b)) {
+                    void *m = mmap(nullptr, (size_t)st.st_size, PROT_READ, MAP_PRIVATE, fd, 0);
+                    if (m != MAP_FAILED) {
+                        madvise(m, (size_t)st.st_size, MADV_SEQUENTIAL);
+                        map_ = (unsigned char *)m;
+                        map_len_ = (size_t)st.st_size;
+                        data_ = map_;
+                        end_ = (int64_t)map_len_;
+                        is_eof_ = true;
+                    }
+                }
+            }
+            if (fd >= 0) close(fd);
+        }
+        if (!map_) {
+            if (strcmp(fn, "-") == 0) f_ = gzdopen(fileno(stdin), "r"); /* utils.c:56-66 */
+            else f_ = gzopen(fn, "r");
+            if (!f_) b2host::fatal("b200aln_aln_core", (std::string("fail to open file '") + fn + "'.").c_str());
+            buf_.resize((size_t)160 << 20);
+            data_ = buf_.data();
+        }
     }
-    ~SeqReader() { if (f_) gzclose(f_); }
+    ~SeqReader()
+    {
+        if (f_) gzclose(f_);
+        if (map_) munmap(map_, map_len_);
+    }
 
     /* returns sequence length, -1 at end of file, -2 on a truncated quality string */
     int read_record()
@@ -86,29 +209,30 @@ class SeqReader {
     {
         if (last_char_ != 0) return -3;
         refill_keep_tail(1 << 16);
-        const unsigned char *b = buf_.data();
-        const int e = end_;
-        int p = begin_;
+        const unsigned char *b = data_;
+        const int64_t e = end_;
+        int64_t p = begin_;
         if (p >= e || b[p] != '@') return -3;
         const unsigned char *nl1 = (const unsigned char *)memchr(b + p + 1, '\n', (size_t)(e - p - 1));
         if (!nl1) return -3;
-        int name_end = p + 1;
-        while (name_end < (int)(nl1 - b) && !isspace(b[name_end])) ++name_end;
+        int64_t name_end = p + 1;
+        while (name_end < (int64_t)(nl1 - b) && !isspace(b[name_end])) ++name_end;
         if (name_end == p + 1) return -3; /* empty name: let the exact parser decide */
-        const int s0 = (int)(nl1 - b) + 1;
+        const int64_t s0 = (int64_t)(nl1 - b) + 1;
         const unsigned char *nl2 = (const unsigned char *)memchr(b + s0, '\n', (size_t)(e - s0));
         if (!nl2) return -3;
-        const int L = (int)(nl2 - b) - s0;
+        if ((int64_t)(nl2 - b) - s0 > 0x3fffffff) return -3;
+        const int L = (int)((int64_t)(nl2 - b) - s0);
         if (L <= 0) return -3;
         for (int i = 0; i < L; ++i) {
             const unsigned char ch = b[s0 + i];
             if (ch <= 32 || ch >= 127 || ch == '>' || ch == '+' || ch == '@') return -3;
         }
-        const int q_plus = s0 + L + 1;
+        const int64_t q_plus = s0 + L + 1;
         if (q_plus >= e || b[q_plus] != '+') return -3;
         const unsigned char *nl3 = (const unsigned char *)memchr(b + q_plus, '\n', (size_t)(e - q_plus));
         if (!nl3) return -3;
-        const int q0 = (int)(nl3 - b) + 1;
+        const int64_t q0 = (int64_t)(nl3 - b) + 1;
         if (q0 + L >= e) return -3; /* need the byte after the quality string too */
         for (int i = 0; i < L; ++i) {
             const unsigned char ch = b[q0 + i];
@@ -151,7 +275,7 @@ class SeqReader {
     }
 
     /* One ordinary 4-line record found by the structural scan: offsets into the buffer. */
-    struct Extent { int start, seq, len, qual, next; };
+    struct Extent { int64_t start, seq, qual, next; int len; };
 
     /* Structural scan (newline positions only) of up to max_records consecutive ordinary records from the
      * cursor.  Does NOT move the cursor and does not look at the characters: convert_extent() validates them.
@@ -161,46 +285,57 @@ class SeqReader {
         out.clear();
         if (last_char_ != 0) return 0;
         refill_keep_tail(1 << 26);
-        const unsigned char *b = buf_.data();
-        const int e = end_;
-        int p = begin_;
+        const unsigned char *b = data_;
+        const int64_t e = end_;
+        int64_t p = begin_;
+        int guess = -1; /* sequence length of the previous record: most files have one length */
         while ((int)out.size() < max_records) {
             if (p >= e || b[p] != '@') break;
             const unsigned char *nl1 = (const unsigned char *)memchr(b + p + 1, '\n', (size_t)(e - p - 1));
             if (!nl1 || nl1 == b + p + 1 || isspace(b[p + 1])) break;
-            const int s0 = (int)(nl1 - b) + 1;
-            const unsigned char *nl2 = (const unsigned char *)memchr(b + s0, '\n', (size_t)(e - s0));
-            if (!nl2) break;
-            const int L = (int)(nl2 - b) - s0;
-            const int q_plus = s0 + L + 1;
+            const int64_t s0 = (int64_t)(nl1 - b) + 1;
+            /* the sequence line ends at s0 + L.  Guessing L costs nothing when wrong in the safe direction: a
+             * newline INSIDE the guessed region is a character <= 32, which convert_extent() refuses, and the
+             * record then goes through the exact parser; a longer line fails the test below. */
+            int L;
+            if (guess > 0 && s0 + guess < e && b[s0 + guess] == '\n') L = guess;
+            else {
+                const unsigned char *nl2 = (const unsigned char *)memchr(b + s0, '\n', (size_t)(e - s0));
+                if (!nl2 || (int64_t)(nl2 - b) - s0 > 0x3fffffff) break;
+                L = (int)((int64_t)(nl2 - b) - s0);
+            }
+            const int64_t q_plus = s0 + L + 1;
             if (L <= 0 || q_plus >= e || b[q_plus] != '+') break;
-            const unsigned char *nl3 = (const unsigned char *)memchr(b + q_plus, '\n', (size_t)(e - q_plus));
-            if (!nl3) break;
-            const int q0 = (int)(nl3 - b) + 1;
-            if (q0 + L >= e || b[q0 + L] != '\n') break;
+            int64_t q0;
+            if (q_plus + 1 < e && b[q_plus + 1] == '\n') q0 = q_plus + 2;
+            else {
+                const unsigned char *nl3 = (const unsigned char *)memchr(b + q_plus, '\n', (size_t)(e - q_plus));
+                if (!nl3) break;
+                q0 = (int64_t)(nl3 - b) + 1;
+            }
+            if (q0 + L >= e || b[q0 + L] != '\n') break; /* (a newline inside the quality string is refused by convert_extent) */
             Extent x;
             x.start = p; x.seq = s0; x.len = L; x.qual = q0; x.next = q0 + L + 1;
             out.push_back(x);
             p = x.next;
+            guess = L;
         }
         return (int)out.size();
     }
     /* character checks of the fast path (see read_record_fast) + conversion; false = let the exact parser decide */
     bool convert_extent(const Extent &x, uint8_t *codes, bool is_64, int trim_qual, int *len_out) const
     {
-        const unsigned char *b = buf_.data();
-        unsigned bad = 0;
+        const unsigned char *b = data_;
+        const unsigned char *sq = b + x.seq, *ql = b + x.qual;
+        unsigned acc = 0;
         for (int i = 0; i < x.len; ++i) {
-            const unsigned char ch = b[x.seq + i];
-            bad |= (unsigned)(ch <= 32) | (unsigned)(ch >= 127) | (unsigned)(ch == '>') | (unsigned)(ch == '+') |
-                   (unsigned)(ch == '@');
-            codes[i] = g_nt4.t[ch];
+            const uint8_t v = g_seqclass.t[sq[i]];
+            acc |= v;
+            codes[i] = (uint8_t)(v & 7);
         }
-        for (int i = 0; i < x.len; ++i) {
-            const unsigned char ch = b[x.qual + i];
-            bad |= (unsigned)(ch < 33) | (unsigned)(ch > 127);
-        }
-        if (bad) return false;
+        unsigned badq = 0;
+        for (int i = 0; i < x.len; ++i) badq |= (unsigned)((unsigned char)(ql[i] - 33) > 94); /* outside 33..127 */
+        if ((acc & 0x80u) | badq) return false;
         int len = x.len;
         if (trim_qual >= 1) { /* bwa_trim_read on the (offset-corrected) qualities */
             int sc = 0, best = 0, best_l = x.len - 1;
@@ -215,7 +350,7 @@ class SeqReader {
         *len_out = len;
         return true;
     }
-    void set_cursor(int pos) { begin_ = pos; }
+    void set_cursor(int64_t pos) { begin_ = pos; }
 
     const std::string &seq() const { return seq_; }
     std::string &seq_mut() { return seq_; }
@@ -227,11 +362,11 @@ class SeqReader {
     void refill_keep_tail(int want_bytes)
     {
         if (is_eof_ || end_ - begin_ >= want_bytes) return;
-        const int tail = end_ - begin_;
+        const int64_t tail = end_ - begin_;
         if (tail > 0 && begin_ > 0) memmove(buf_.data(), buf_.data() + begin_, (size_t)tail);
         begin_ = 0;
         end_ = tail;
-        const int want = (int)buf_.size() - end_;
+        const int want = (int)((int64_t)buf_.size() - end_);
         const int got = gzread(f_, buf_.data() + end_, (unsigned)want);
         if (got < want) is_eof_ = true;
         if (got > 0) end_ += got;
@@ -242,10 +377,10 @@ class SeqReader {
         if (begin_ >= end_) {
             begin_ = 0;
             end_ = gzread(f_, buf_.data(), (unsigned)buf_.size());
-            if (end_ < (int)buf_.size()) is_eof_ = true;
+            if (end_ < (int64_t)buf_.size()) is_eof_ = true;
             if (end_ <= 0) { end_ = 0; return -1; }
         }
-        return (int)buf_[begin_++];
+        return (int)data_[begin_++];
     }
     int get_until(int delim, std::string &str, int *dret)
     {
@@ -257,16 +392,16 @@ class SeqReader {
                 if (is_eof_) break;
                 begin_ = 0;
                 end_ = gzread(f_, buf_.data(), (unsigned)buf_.size());
-                if (end_ < (int)buf_.size()) is_eof_ = true;
+                if (end_ < (int64_t)buf_.size()) is_eof_ = true;
                 if (end_ <= 0) { end_ = 0; break; }
             }
-            int i = begin_;
-            if (delim) while (i < end_ && buf_[i] != delim) ++i;
-            else while (i < end_ && !isspace(buf_[i])) ++i;
-            str.append((const char *)buf_.data() + begin_, (size_t)(i - begin_));
+            int64_t i = begin_;
+            if (delim) while (i < end_ && data_[i] != delim) ++i;
+            else while (i < end_ && !isspace(data_[i])) ++i;
+            str.append((const char *)data_ + begin_, (size_t)(i - begin_));
             begin_ = i + 1;
             if (i < end_) {
-                if (dret) *dret = buf_[i];
+                if (dret) *dret = data_[i];
                 break;
             }
         }
@@ -274,8 +409,11 @@ class SeqReader {
     }
 
     gzFile f_ = nullptr;
-    std::vector<unsigned char> buf_;
-    int begin_ = 0, end_ = 0;
+    std::vector<unsigned char> buf_;   /* zlib mode: the stream buffer */
+    unsigned char *map_ = nullptr;     /* mapped mode: the file */
+    size_t map_len_ = 0;
+    const unsigned char *data_ = nullptr; /* buf_.data() or map_ */
+    int64_t begin_ = 0, end_ = 0;
     bool is_eof_ = false;
     int last_char_ = 0;
     std::string name_, seq_, qual_;
@@ -294,10 +432,20 @@ int trim_len(int trim_qual, int len, const char *qual)
     return best_l + 1;
 }
 
+/* std::allocator that leaves trivially constructible elements uninitialised: resize() of a code buffer that
+ * is about to be overwritten by the converters does not have to zero it first */
+template <class T> struct NoInitAlloc : std::allocator<T> {
+    template <class U> struct rebind { typedef NoInitAlloc<U> other; };
+    NoInitAlloc() = default;
+    template <class U> NoInitAlloc(const NoInitAlloc<U> &) {}
+    template <class U> void construct(U *p) noexcept { ::new ((void *)p) U; }
+    template <class U, class... A> void construct(U *p, A &&...a) { ::new ((void *)p) U(std::forward<A>(a)...); }
+};
+
 struct PackedBatch {
-    std::vector<int32_t> lens;
-    std::vector<int64_t> offs;
-    std::vector<uint8_t> codes;
+    std::vector<int32_t, NoInitAlloc<int32_t>> lens;
+    std::vector<int64_t, NoInitAlloc<int64_t>> offs;
+    std::vector<uint8_t, NoInitAlloc<uint8_t>> codes;
     long n_trimmed = 0, n_tot = 0;
     void clear() { lens.clear(); offs.clear(); codes.clear(); n_trimmed = n_tot = 0; }
 };
@@ -341,11 +489,8 @@ int next_batch(SeqReader &rd, int n_needed, int mode, int trim_qual, PackedBatch
         fprintf(stderr, "[bwa_read_seq] the maximum barcode length is 15.\n");
         return 0;
     }
-    static const unsigned n_workers = [] {
-        const char *e = getenv("B200ALN_PARSE_THREADS");
-        unsigned t = e ? (unsigned)atoi(e) : std::thread::hardware_concurrency();
-        return t < 1 ? 1u : (t > 16 ? 16u : t);
-    }();
+    ParsePool &pool = ParsePool::get();
+    const unsigned n_workers = pool.size();
     std::vector<SeqReader::Extent> ext;
     bool eof = false;
     while (!eof && (int)b.lens.size() < n_needed) {
@@ -370,10 +515,7 @@ int next_batch(SeqReader &rd, int n_needed, int mode, int trim_qual, PackedBatch
                     b.lens[base_reads + i] = len;
                 }
             };
-            std::vector<std::thread> th;
-            for (unsigned t = 1; t < n_workers; ++t) th.emplace_back(work, t);
-            work(0);
-            for (auto &x : th) x.join();
+            pool.run(work);
             int ok = n;
             for (unsigned t = 0; t < n_workers; ++t) if (first_bad[t] < ok) ok = first_bad[t];
             /* keep records [0, ok); the one at `ok` (if any) goes to the exact parser below */
@@ -617,6 +759,7 @@ namespace {
 struct BatchResult {
     std::vector<int32_t> n_aln;
     std::vector<b200aln_rec_t> recs;
+    std::vector<char> sai; /* the batch as it goes to the .sai file (bwtaln.c:227-231): per read n_aln, then its records */
     double seconds = 0;
 };
 
@@ -652,6 +795,21 @@ BatchResult process_batch(const std::vector<b200aln_ctx *> &ctxs, const PackedBa
         for (auto &t : th) t.join();
     }
     for (int gi = 0; gi < g; ++gi) out.recs.insert(out.recs.end(), part[gi].begin(), part[gi].end());
+    out.sai.resize((size_t)n * 4 + out.recs.size() * sizeof(b200aln_rec_t));
+    {
+        char *w = out.sai.data();
+        const b200aln_rec_t *rec = out.recs.data();
+        for (int r = 0; r < n; ++r) {
+            const int32_t c = out.n_aln[(size_t)r];
+            memcpy(w, &c, 4);
+            w += 4;
+            if (c) {
+                memcpy(w, rec, (size_t)c * sizeof(b200aln_rec_t));
+                w += (size_t)c * sizeof(b200aln_rec_t);
+                rec += c;
+            }
+        }
+    }
     clock_gettime(CLOCK_MONOTONIC, &t1);
     out.seconds = (t1.tv_sec - t0.tv_sec) + 1e-9 * (t1.tv_nsec - t0.tv_nsec);
     return out;
@@ -662,6 +820,15 @@ BatchResult process_batch(const std::vector<b200aln_ctx *> &ctxs, const PackedBa
 extern "C" int64_t b200aln_aln_core(const char *prefix, const char *fn_fa, const b200aln_opt_t *opt, int out_fd,
                                     int device)
 {
+    const bool trace = getenv("B200ALN_TRACE") != nullptr; /* wall-clock timeline of the driver on stderr */
+    struct timespec tr0;
+    clock_gettime(CLOCK_MONOTONIC, &tr0);
+    auto stamp = [&](const char *what, long long n) {
+        if (!trace) return;
+        struct timespec t;
+        clock_gettime(CLOCK_MONOTONIC, &t);
+        fprintf(stderr, "[trace] %8.3f s  %s %lld\n", (t.tv_sec - tr0.tv_sec) + 1e-9 * (t.tv_nsec - tr0.tv_nsec), what, n);
+    };
     b200aln_reader rd(fn_fa, opt->mode);
     /* devices: one, or all visible; per device two contexts (index shared) so that two batches are in
      * flight: the copies and host work of one overlap the kernels of the other */
@@ -677,29 +844,44 @@ extern "C" int64_t b200aln_aln_core(const char *prefix, const char *fn_fa, const
         if (n_slots > 8) n_slots = 8;
     }
     std::vector<std::vector<b200aln_ctx *>> slot_ctx((size_t)n_slots);
-    {   /* bwt_restore_bwt x2 once (bwtio.c:51-70), then one upload per GPU in parallel */
-        std::vector<uint32_t> w[2];
+    {   /* bwt_restore_bwt x2 once (bwtio.c:51-70) — both files at the same time, while the CUDA contexts come
+         * up on another thread — then one upload per GPU in parallel */
+        struct Raw { uint32_t *w = nullptr; size_t nw = 0; uint32_t hdr[5]; };
+        Raw raw[2];
         b200aln_bwt_view_t v[2];
         const char *ext[2] = {".bwt", ".rbwt"};
-        for (int j = 0; j < 2; ++j) {
+        auto load = [&](int j) {
             const std::string fn = std::string(prefix) + ext[j];
-            FILE *fp = fopen(fn.c_str(), "rb");
-            if (!fp) b2host::fatal("b200aln_aln_core", (std::string("fail to open file '") + fn + "'.").c_str());
-            fseek(fp, 0, SEEK_END);
-            const long sz = ftell(fp);
-            fseek(fp, 0, SEEK_SET);
-            uint32_t hdr[5];
-            if (sz < 20 || fread(hdr, 4, 5, fp) != 5) b2host::fatal("b200aln_aln_core", "truncated BWT file.");
-            const size_t nw = ((size_t)sz - 20) >> 2;
-            w[j].resize(nw);
-            if (nw && fread(w[j].data(), 4, nw, fp) != nw) b2host::fatal("b200aln_aln_core", "truncated BWT file.");
-            fclose(fp);
-            v[j].primary = hdr[0];
+            const int fd = open(fn.c_str(), O_RDONLY);
+            if (fd < 0) b2host::fatal("b200aln_aln_core", (std::string("fail to open file '") + fn + "'.").c_str());
+            struct stat st;
+            if (fstat(fd, &st) != 0 || st.st_size < 20 || pread(fd, raw[j].hdr, 20, 0) != 20)
+                b2host::fatal("b200aln_aln_core", "truncated BWT file.");
+            const size_t nw = ((size_t)st.st_size - 20) >> 2;
+            raw[j].nw = nw;
+            raw[j].w = (uint32_t *)malloc(nw * 4 + 16);
+            if (!raw[j].w) b2host::fatal("b200aln_aln_core", "out of memory reading the BWT.");
+            size_t got = 0;
+            while (got < nw * 4) {
+                const ssize_t k = pread(fd, (char *)raw[j].w + got, nw * 4 - got, (off_t)(20 + got));
+                if (k <= 0) b2host::fatal("b200aln_aln_core", "truncated BWT file.");
+                got += (size_t)k;
+            }
+            close(fd);
+        };
+        std::thread warm([&]() { for (int d : devs) b200aln_warm_device(d); });
+        std::thread t1([&]() { load(1); });
+        load(0);
+        t1.join();
+        warm.join();
+        stamp("index files read", 2);
+        for (int j = 0; j < 2; ++j) {
+            v[j].primary = raw[j].hdr[0];
             v[j].L2[0] = 0;
-            for (int i = 0; i < 4; ++i) v[j].L2[i + 1] = hdr[1 + i];
+            for (int i = 0; i < 4; ++i) v[j].L2[i + 1] = raw[j].hdr[1 + i];
             v[j].seq_len = v[j].L2[4];
-            v[j].bwt_size = nw;
-            v[j].bwt = w[j].data();
+            v[j].bwt_size = raw[j].nw;
+            v[j].bwt = raw[j].w;
         }
         for (auto &sc : slot_ctx) sc.resize(devs.size());
         std::vector<std::thread> th;
@@ -709,6 +891,8 @@ extern "C" int64_t b200aln_aln_core(const char *prefix, const char *fn_fa, const
                 for (int sl = 1; sl < n_slots; ++sl) slot_ctx[(size_t)sl][i] = b200aln_clone(slot_ctx[0][i]);
             });
         for (auto &t : th) t.join();
+        free(raw[0].w);
+        free(raw[1].w);
     }
     FILE *out = fdopen(dup(out_fd), "wb");
     if (!out) b2host::fatal("b200aln_aln_core", "cannot open the output descriptor.");
@@ -716,39 +900,96 @@ extern "C" int64_t b200aln_aln_core(const char *prefix, const char *fn_fa, const
 
     int64_t tot_seqs = 0, written = 0;
     std::deque<std::future<BatchResult>> inflight;
+    stamp("index resident on devices", (long long)devs.size());
     auto drain_one = [&]() {
+        stamp("waiting for launch, reads so far", (long long)written);
         BatchResult r = inflight.front().get();
         inflight.pop_front();
+        stamp("launch finished, reads", (long long)r.n_aln.size());
         fprintf(stderr, "[bwa_aln_core] calculate SA coordinate... %.2f sec\n", r.seconds);
         fprintf(stderr, "[bwa_aln_core] write to the disk... ");
         struct timespec t0, t1;
         clock_gettime(CLOCK_MONOTONIC, &t0);
-        size_t at = 0;
-        for (size_t i = 0; i < r.n_aln.size(); ++i) { /* bwtaln.c:227-231 */
-            fwrite(&r.n_aln[i], 4, 1, out);
-            if (r.n_aln[i]) fwrite(r.recs.data() + at, sizeof(b200aln_rec_t), (size_t)r.n_aln[i], out);
-            at += (size_t)r.n_aln[i];
-        }
+        if (!r.sai.empty() && fwrite(r.sai.data(), 1, r.sai.size(), out) != r.sai.size())
+            b2host::fatal("b200aln_aln_core", "short write on the .sai output.");
         clock_gettime(CLOCK_MONOTONIC, &t1);
         written += (int64_t)r.n_aln.size();
         fprintf(stderr, "%.2f sec\n", (t1.tv_sec - t0.tv_sec) + 1e-9 * (t1.tv_nsec - t0.tv_nsec));
         fprintf(stderr, "[bwa_aln_core] %lld sequences have been processed.\n", (long long)written);
     };
+    /* The reference works in batches of 0x40000 reads (bwtaln.c:193), and one thing is decided per batch: the
+     * max_gapo clamp from the batch's longest read (bwtaln.c:89-92).  Consecutive reference batches that agree
+     * on it are handed to the GPUs as ONE launch (up to B200ALN_MERGE of them, default 4 per GPU): 0x40000 reads
+     * are only two per lane.  A launch goes out as soon as a slot is free, so short inputs are not held back. */
+    int merge = 4 * (int)devs.size(); /* a launch is cut into one shard per GPU */
+    {
+        const char *e = getenv("B200ALN_MERGE");
+        if (e) merge = atoi(e);
+        if (merge < 1) merge = 1;
+        if (merge > 64) merge = 64;
+    }
+    if (merge > 1) /* buffers sized once for the largest launch */
+        for (auto &sc : slot_ctx)
+            for (b200aln_ctx *c : sc) b200aln_set_int(c, "reserve_reads", (int64_t)merge * 0x40000 / (int64_t)devs.size() + 1);
+    auto clamp_key = [&](int max_len) { /* what make_params derives from the batch's longest read */
+        int gapo = opt->max_gapo;
+        if (opt->fnr > 0.0f) {
+            const int d = b2host::cal_maxdiff(max_len, BWA_AVG_ERR, opt->fnr);
+            if (d < gapo) gapo = d;
+        }
+        return gapo;
+    };
+    std::shared_ptr<PackedBatch> super;
+    int super_batches = 0, super_max_len = 0, super_key = 0;
     int seq = 0;
+    auto flush = [&]() {
+        if (!super || super->lens.empty()) return;
+        const std::vector<b200aln_ctx *> *ctxs = &slot_ctx[(size_t)(seq % n_slots)];
+        if ((int)inflight.size() == n_slots) drain_one(); /* the slot's previous launch is finished and written */
+        std::shared_ptr<PackedBatch> b = super;
+        stamp("launch of reads", (long long)b->lens.size());
+        inflight.push_back(std::async(std::launch::async, [ctxs, b, opt]() { return process_batch(*ctxs, *b, opt); }));
+        ++seq;
+        super.reset();
+        super_batches = 0;
+    };
     for (;;) {
         auto b = std::make_shared<PackedBatch>();
         const int n = rd.next(0x40000, opt->mode, opt->trim_qual, *b);
         if (n == 0) break;
         tot_seqs += n;
-        const std::vector<b200aln_ctx *> *ctxs = &slot_ctx[(size_t)(seq % n_slots)];
-        if ((int)inflight.size() == n_slots) drain_one(); /* the slot's previous batch is finished and written */
-        inflight.push_back(std::async(std::launch::async, [ctxs, b, opt]() { return process_batch(*ctxs, *b, opt); }));
-        ++seq;
+        stamp("parsed reads", (long long)tot_seqs);
+        int max_len = 0;
+        for (int32_t l : b->lens) if (l > max_len) max_len = l;
+        const int key = clamp_key(max_len);
+        if (super_batches) {
+            const int joint = max_len > super_max_len ? max_len : super_max_len;
+            if (super_batches >= merge || key != super_key || clamp_key(joint) != super_key) flush();
+        }
+        if (!super_batches) {
+            super = b;
+            super_max_len = max_len;
+            super_key = key;
+        } else {
+            const int64_t shift = (int64_t)super->codes.size();
+            const size_t at = super->lens.size();
+            super->lens.insert(super->lens.end(), b->lens.begin(), b->lens.end());
+            super->offs.resize(at + b->offs.size());
+            for (size_t i = 0; i < b->offs.size(); ++i) super->offs[at + i] = b->offs[i] + shift;
+            super->codes.insert(super->codes.end(), b->codes.begin(), b->codes.end());
+            if (max_len > super_max_len) super_max_len = max_len;
+        }
+        ++super_batches;
+        while (!inflight.empty() && inflight.front().wait_for(std::chrono::seconds(0)) == std::future_status::ready) drain_one();
+        if ((int)inflight.size() < n_slots) flush();
     }
+    flush();
     while (!inflight.empty()) drain_one();
     fclose(out);
+    stamp("output closed, reads", (long long)tot_seqs);
     for (size_t i = 0; i < devs.size(); ++i)
         for (int sl = n_slots - 1; sl >= 0; --sl) b200aln_close(slot_ctx[(size_t)sl][i]);
+    stamp("contexts closed", (long long)devs.size());
     return tot_seqs;
 }
 

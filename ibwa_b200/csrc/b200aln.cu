@@ -404,6 +404,7 @@ struct DevBuf {
         if (p) CK(cudaFree(p));
         p = nullptr;
         size_t want = bytes + bytes / 8 + 256;
+        if (want < cap + cap / 2) want = cap + cap / 2; /* grow geometrically: freeing and allocating synchronise the device */
         cudaError_t e = cudaMalloc(&p, want);
         if (e != cudaSuccess) {
             size_t fr = 0, tot = 0;
@@ -431,6 +432,7 @@ struct HostBuf {
         if (bytes <= cap) return;
         if (p) CK(cudaFreeHost(p));
         size_t want = bytes + bytes / 8 + 256;
+        if (want < cap + cap / 2) want = cap + cap / 2;
         CK(cudaHostAlloc(&p, want, cudaHostAllocDefault));
         cap = want;
     }
@@ -460,6 +462,7 @@ struct b200aln_ctx {
     uint32_t arena_cap_mid = 8192; /* middle pass: 16-bit heads in shared memory, free-list arena */
     int rec_cap_mid = 512, mid_lanes = 148 * 128 * 2;
     int prefetch_fast = 0, prefetch_mid = 1; /* L2 prefetch of the next pop candidate, per pass */
+    int reserve_reads = 0; /* size the per-batch buffers for at least this many reads */
     int count = 0;         /* 1: fast pass with the pop / sector counters (b200aln_stats_t pops, occ_lookups) */
     int pop_batch = 1;     /* memory pops are taken when this many lanes of a warp wait for one */
     int lut_k = 14;        /* levels of the path-k-mer interval table (0 = off) */
@@ -511,6 +514,13 @@ extern "C" int b200aln_device_count(void)
     int n = 0;
     if (cudaGetDeviceCount(&n) != cudaSuccess) return 0;
     return n;
+}
+
+/* creates the device's CUDA context (first-call cost) — the CLI driver does this while it reads the index files */
+extern "C" void b200aln_warm_device(int device)
+{
+    if (cudaSetDevice(device) == cudaSuccess) (void)cudaFree(nullptr);
+    (void)cudaGetLastError();
 }
 
 static void upload_index(b200aln_ctx *c, int which, const b200aln_bwt_view_t *v)
@@ -653,7 +663,7 @@ extern "C" b200aln_ctx *b200aln_clone(b200aln_ctx *p)
     c->arena_cap = p->arena_cap; c->arena_cap_big = p->arena_cap_big;
     c->rec_cap = p->rec_cap; c->rec_cap_big = p->rec_cap_big; c->big_lanes = p->big_lanes;
     c->arena_cap_mid = p->arena_cap_mid; c->rec_cap_mid = p->rec_cap_mid; c->mid_lanes = p->mid_lanes;
-    c->pop_batch = p->pop_batch; c->count = p->count;
+    c->pop_batch = p->pop_batch; c->count = p->count; c->reserve_reads = p->reserve_reads;
     c->prefetch_fast = p->prefetch_fast; c->prefetch_mid = p->prefetch_mid;
     CK(cudaStreamCreateWithFlags(&c->st, cudaStreamNonBlocking));
     for (int i = 0; i < 8; ++i) CK(cudaEventCreate(&c->ev[i]));
@@ -730,6 +740,7 @@ extern "C" void b200aln_set_int(b200aln_ctx *c, const char *key, int64_t v)
     else if (!strcmp(key, "big_lanes")) c->big_lanes = (int)v;
     else if (!strcmp(key, "pop_batch")) c->pop_batch = (int)v;
     else if (!strcmp(key, "count")) c->count = (int)v;
+    else if (!strcmp(key, "reserve_reads")) c->reserve_reads = (int)v;
     else if (!strcmp(key, "prefetch_fast")) c->prefetch_fast = (int)v;
     else if (!strcmp(key, "prefetch_mid")) c->prefetch_mid = (int)v;
     else if (!strcmp(key, "arena_cap_mid")) c->arena_cap_mid = (uint32_t)v;
@@ -825,16 +836,19 @@ static void run_batch_device(b200aln_ctx *c, int n_reads, int max_len, const int
     const size_t lanes = (size_t)sblocks * 128;
 
     c->md.need(md.size() * 4);
-    c->Q.need((size_t)n_reads * 2 * strideQ * sizeof(QRec) + 64);
-    c->W.need((size_t)n_reads * 2 * strideW * 4 + 64);
-    c->n_amb.need((size_t)n_reads * 4);
+    /* buffers are sized for at least reserve_reads reads, so that a driver whose launches vary in size does not
+     * keep growing them (freeing and allocating synchronise the device) */
+    const size_t n_alloc = (size_t)(n_reads > c->reserve_reads ? n_reads : c->reserve_reads);
+    c->Q.need(n_alloc * 2 * strideQ * sizeof(QRec) + 64);
+    c->W.need(n_alloc * 2 * strideW * 4 + 64);
+    c->n_amb.need(n_alloc * 4);
     c->ent.need(lanes * c->arena_cap * sizeof(StackRec));
-    c->recs.need((size_t)n_reads * c->rec_cap * 16);
-    c->n_aln.need((size_t)n_reads * 4);
-    c->over_slot.need((size_t)n_reads * 4);
-    c->over_list.need((size_t)n_reads * 4);
+    c->recs.need(n_alloc * c->rec_cap * 16);
+    c->n_aln.need(n_alloc * 4);
+    c->over_slot.need(n_alloc * 4);
+    c->over_list.need(n_alloc * 4);
     c->misc.need(sizeof(Misc));
-    c->off64.need((size_t)n_reads * 8);
+    c->off64.need(n_alloc * 8);
     const int nscan = (n_reads + SCAN_ITEMS - 1) / SCAN_ITEMS;
     c->blk_tot.need((size_t)nscan * 8 + 8);
     c->h_misc.need(sizeof(Misc));
@@ -1021,9 +1035,10 @@ extern "C" const b200aln_rec_t *b200aln_batch(b200aln_ctx *c, int n_reads, const
     b2host::make_params(*opt, c->batch_max_len > 0 ? c->batch_max_len : max_len, lens, n_reads, P, md);
     if ((int)md.size() < max_len + 1) md.resize((size_t)max_len + 1, opt->max_diff);
 
-    c->lens.need((size_t)n_reads * 4);
-    c->offs.need((size_t)n_reads * 8);
-    c->codes.need((size_t)end + 16);
+    const size_t n_alloc = (size_t)(n_reads > c->reserve_reads ? n_reads : c->reserve_reads);
+    c->lens.need(n_alloc * 4);
+    c->offs.need(n_alloc * 8);
+    c->codes.need((size_t)((double)end * ((double)n_alloc / (double)n_reads)) + 16);
     CK(cudaEventRecord(c->ev[0], c->st));
     CK(cudaMemcpyAsync(c->lens.p, lens, (size_t)n_reads * 4, cudaMemcpyHostToDevice, c->st));
     CK(cudaMemcpyAsync(c->offs.p, offs, (size_t)n_reads * 8, cudaMemcpyHostToDevice, c->st));

@@ -138,6 +138,7 @@ double b200aln_timer_stop(b200aln_ctx *ctx);
  *   search_blocks_per_sm, width_blocks_per_sm, arena_cap, arena_cap_mid, arena_cap_big, rec_cap, rec_cap_mid,
  *   rec_cap_big, mid_lanes, big_lanes:
  *                  launch geometry and per-lane capacities; arena capacities count 64-byte records.
+ *   reserve_reads  size the per-batch device buffers for at least this many reads (drivers whose launches vary in size).
  *   count          1: the fast pass runs with its pop / sector counters (b200aln_stats_t pops, occ_lookups). */
 void b200aln_set_int(b200aln_ctx *ctx, const char *key, int64_t value);
 
@@ -183,6 +184,10 @@ b200aln_reader *b200aln_reader_open(const char *fn, int mode); /* mode & BWA_MOD
 int b200aln_reader_next(b200aln_reader *r, int n_needed, int mode, int trim_qual, const int32_t **lens,
                         const int64_t **offs, const uint8_t **codes, int64_t *codes_bytes);
 void b200aln_reader_close(b200aln_reader *r);
+
+/* Creates the CUDA context of a device (the first CUDA call of a process takes a few hundred ms); the
+ * CLI driver calls it on a side thread while it reads the index files.  No reference counterpart. */
+void b200aln_warm_device(int device);
 
 /* Replaces bwa_aln (bwtaln.c:243-328): same getopt string and semantics. */
 int b200aln_aln_main(int argc, char *argv[]);

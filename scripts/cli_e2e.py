@@ -28,11 +28,20 @@ def main():
     bench.write_fastq(fq_ref, reads[:n_ref])
     exe = os.path.join(ROOT, "ibwa_b200", "b200aln")
     cores = os.cpu_count()
+    empty = "/tmp/cli_e2e_empty.fq"
+    open(empty, "w").close()
+    t0 = time.perf_counter()
+    subprocess.run([exe, "aln", "-f", "/tmp/gpu_empty.sai", prefix, empty], stderr=subprocess.DEVNULL, check=True)
+    t_load = time.perf_counter() - t0
+    print(f"b200aln aln (empty input): {t_load:.2f} s wall = index load + device layout + interval table")
     for label, path, cnt in (("full", fq, n), ("ref-sized", fq_ref, n_ref)):
-        t0 = time.perf_counter()
-        subprocess.run([exe, "aln", "-f", f"/tmp/gpu_{label}.sai", prefix, path], stderr=subprocess.DEVNULL, check=True)
-        dt = time.perf_counter() - t0
-        print(f"b200aln aln ({label}: {cnt} reads): {dt:.2f} s wall = {cnt / dt / 1e6:.2f} M reads/s incl. index load")
+        for env in ({}, {"B200ALN_MERGE": "1"}) if label == "full" else ({},):
+            t0 = time.perf_counter()
+            subprocess.run([exe, "aln", "-f", f"/tmp/gpu_{label}.sai", prefix, path], stderr=subprocess.DEVNULL, check=True,
+                           env=dict(os.environ, **env))
+            dt = time.perf_counter() - t0
+            print(f"b200aln aln ({label}: {cnt} reads{', no batch merging' if env else ''}): {dt:.2f} s wall = "
+                  f"{cnt / dt / 1e6:.2f} M reads/s incl. index load, {cnt / max(dt - t_load, 1e-9) / 1e6:.2f} M reads/s without")
     t0 = time.perf_counter()
     with open("/tmp/ref.sai", "wb") as fo:
         subprocess.run([bench.REF_BIN, "aln", "-t", str(cores), prefix, fq_ref], stdout=fo, stderr=subprocess.DEVNULL,

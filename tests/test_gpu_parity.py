@@ -165,6 +165,46 @@ def test_reference_binary_on_box(rand_index, tmp_path):
     a, b = open(ref_out, "rb").read(), open(out, "rb").read()
     assert a[:52] == b[:52] and a[56:] == b[56:]      # byte 52..55 = n_threads
 
+def test_cli_merges_reference_batches_only_when_allowed(rand_index, tmp_path):
+    """The CLI driver hands several 0x40000-read reference batches to the GPU as one launch, but only batches
+    that agree on the batch-level max_gapo clamp (bwtaln.c:89-92).  Input: one whole batch of reads < 38 bp
+    (with -o 3 the clamp bites), then 100 bp reads, then a short tail — against the unmodified reference
+    binary, with merging on (default), off, and with one batch in flight."""
+    if not pyoracle.have_ref():
+        pytest.skip("oracle/_ref/ibwa not present")
+    g, bwt, rbwt = rand_index
+    prefix = str(tmp_path / "r2m")
+    bwt_dump_bwt(prefix + ".bwt", bwt)
+    bwt_dump_bwt(prefix + ".rbwt", rbwt)
+    rng = np.random.default_rng(8)
+    nt = np.frombuffer(b"ACGT", dtype=np.uint8)
+    fq = str(tmp_path / "mixed.fq")
+    with open(fq, "wb") as f:
+        def emit(count, lo, hi, tag):
+            lens = rng.integers(lo, hi + 1, size=count)
+            starts = rng.integers(0, len(g) - 300, size=count)
+            out = []
+            for i in range(count):
+                r = g[starts[i]:starts[i] + lens[i]].copy()
+                if i % 3 == 0:
+                    r[int(rng.integers(0, lens[i]))] ^= 1
+                out.append(b"@" + tag + b"%d\n" % i + nt[r].tobytes() + b"\n+\n" + b"I" * int(lens[i]) + b"\n")
+            f.write(b"".join(out))
+        emit(0x40000, 20, 37, b"s")        # exactly one reference batch of short reads
+        emit(0x40000 + 5000, 100, 100, b"l")   # one full batch and the start of the next ...
+        emit(3000, 25, 36, b"t")           # ... which ends with short reads (max_len 100: no clamp)
+    args = ["-o", "3"]
+    ref_out = str(tmp_path / "ref.sai")
+    pyoracle.run_ref(["aln", "-t", str(os.cpu_count() or 4)] + args + [prefix, fq], stdout_path=ref_out)
+    want = open(ref_out, "rb").read()
+    exe = os.path.join(ROOT, "ibwa_b200", "b200aln")
+    for env in ({}, {"B200ALN_MERGE": "1"}, {"B200ALN_INFLIGHT": "1", "B200ALN_MERGE": "64"}):
+        out = str(tmp_path / "gpu.sai")
+        subprocess.check_call([exe, "aln"] + args + ["-f", out, prefix, fq], stderr=subprocess.DEVNULL,
+                              env=dict(os.environ, **env))
+        got = open(out, "rb").read()
+        assert len(got) == len(want) and got[:52] == want[:52] and got[56:] == want[56:], env
+
 
 def _ref_index(tmp_path, genome, name, contig_len=None):
     """Index a synthetic genome with the unmodified reference (`ibwa index -a is`)."""

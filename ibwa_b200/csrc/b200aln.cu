@@ -458,9 +458,9 @@ struct b200aln_ctx {
     /* tuning */
     int search_blocks_per_sm = 6, width_blocks_per_sm = 5;
     uint32_t arena_cap = 2048, arena_cap_big = 0; /* 64-byte records per lane; big 0: max_entries + 64 */
-    int rec_cap = 8, rec_cap_big = 1 << 13, big_lanes = 256; /* wide pass: 256 lanes x (max_entries+64) x 32 B = 16 GB */
-    uint32_t arena_cap_mid = 8192; /* middle pass: 16-bit heads in shared memory, free-list arena */
-    int rec_cap_mid = 512, mid_lanes = 148 * 128 * 2;
+    int rec_cap = 8, rec_cap_big = 1 << 13, big_lanes = 128; /* wide pass: 128 lanes x (max_entries+64) x 64 B = 16 GB */
+    uint32_t arena_cap_mid = 12288; /* middle pass: 16-bit heads in shared memory, free-list arena */
+    int rec_cap_mid = 512, mid_lanes = 148 * 192; /* x 12288 records x 64 B = 22 GB, allocated when a batch first needs it */
     int prefetch_fast = 0, prefetch_mid = 1; /* L2 prefetch of the next pop candidate, per pass */
     int reserve_reads = 0; /* size the per-batch buffers for at least this many reads */
     int count = 0;         /* 1: fast pass with the pop / sector counters (b200aln_stats_t pops, occ_lookups) */

@@ -42,18 +42,52 @@ HOSTILE = {
 }
 
 
+def _guess_traps():
+    """Runs of ordinary 100-bp records (long enough for the structural scan, which guesses each sequence line's
+    length from the previous record) with records in between that make the guess land on a newline although
+    the line is shorter, or that differ in other ways only the character checks / the exact parser can see."""
+    rng = np.random.default_rng(12)
+    nt = np.frombuffer(b"ACGT", dtype=np.uint8)
+    out = []
+
+    def rec(i, L, plus=b"+", qual=None, seq=None):
+        sq = nt[rng.integers(0, 4, size=L)].tobytes() if seq is None else seq
+        return b"@t%d\n" % i + sq + b"\n" + plus + b"\n" + (b"I" * L if qual is None else qual) + b"\n"
+
+    for i in range(400):
+        k = i % 40
+        if k == 11:      # 48 + 1 + 3 + 48 = 100: the byte at seq + 100 is the newline after the quality string
+            out.append(rec(i, 48, plus=b"+x"))
+        elif k == 17:    # two-line sequence whose first line is 100 long: fine for the guess, not a 4-line record
+            out.append(b"@t%d\n" % i + b"A" * 100 + b"\n" + b"C" * 20 + b"\n+\n" + b"I" * 120 + b"\n")
+        elif k == 23:    # quality string with a newline inside the guessed region
+            out.append(b"@t%d\n" % i + b"G" * 100 + b"\n+\n" + b"I" * 60 + b"\n" + b"I" * 40 + b"\n")
+        elif k == 29:    # shorter read, then the ordinary length again
+            out.append(rec(i, 36))
+        elif k == 31:    # '>' inside the sequence line ends the sequence for the reference parser
+            out.append(rec(i, 100, seq=b"ACGT" * 10 + b">" + b"ACGT" * 14 + b"ACG"))
+        else:
+            out.append(rec(i, 100))
+    return b"".join(out)
+
+
+HOSTILE["guess_traps"] = _guess_traps()
+
+
 @pytest.mark.parametrize("name", sorted(HOSTILE))
 @pytest.mark.parametrize("gz", [False, True])
 def test_hostile_inputs(tmp_path, name, gz):
     p = str(tmp_path / (name + (".gz" if gz else "")))
     data = HOSTILE[name]
-    (gzip.open(p, "wb") if gz else open(p, "wb")).write(data)
+    with (gzip.open(p, "wb") if gz else open(p, "wb")) as f:
+        f.write(data)
     both(p)
 
 
 def test_barcode_and_il13(tmp_path):
     p = str(tmp_path / "bc.fq")
-    open(p, "wb").write(b"@r1\nACGTACGTAC\n+\nhhhhhhhhhh\n@r2\nAC\n+\nhh\n@r3\nACGTA\n+\nhhhhh\n")
+    with open(p, "wb") as f:
+        f.write(b"@r1\nACGTACGTAC\n+\nhhhhhhhhhh\n@r2\nAC\n+\nhh\n@r3\nACGTA\n+\nhhhhh\n")
     both(p, mode=3 | (3 << 24))
     both(p, mode=3 | 0x200, trim_qual=5)
 
@@ -84,7 +118,8 @@ def test_hostile_inputs_against_reference_binary(tmp_path, golden_dir, g1_index,
     os.symlink(os.path.join(golden_dir, "g1.bwt"), prefix + ".bwt")
     os.symlink(os.path.join(golden_dir, "g1.rbwt"), prefix + ".rbwt")
     p = str(tmp_path / (name + ".fq"))
-    open(p, "wb").write(HOSTILE[name])
+    with open(p, "wb") as f:
+        f.write(HOSTILE[name])
     ref_sai = str(tmp_path / "ref.sai")
     pyoracle.run_ref(["aln", prefix, p], stdout_path=ref_sai)
     opt = gap_init_opt()

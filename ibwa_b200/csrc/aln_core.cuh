@@ -102,19 +102,51 @@ B2_D OccBlk ld_blk(const OccBlk *p)
     return r;
 }
 B2_D void ld8cg(const uint32_t *p, uint32_t v[8])
-{ /* stack records: written once, read at most twice -> L2 only */
+{ /* stack records: written once, read at most twice -> L2 only, first in line for eviction */
+#if defined(B2_L2_HINTS) && defined(B2_HINT_REC)
+    asm volatile("ld.global.cg.L2::cache_hint.v8.u32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8], %9;"
+                 : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7])
+                 : "l"(p), "l"(pol_evict_first()) : "memory");
+#else
     asm volatile("ld.global.cg.v8.u32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
                  : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7])
                  : "l"(p) : "memory");
+#endif
+}
+B2_D void st8rec(uint32_t *p, const uint32_t v[8])
+{ /* one sector of a stack record */
+#if defined(B2_L2_HINTS) && defined(B2_HINT_REC)
+    asm volatile("st.global.cg.L2::cache_hint.v8.u32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8}, %9;"
+                 :: "l"(p), "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7]),
+                    "l"(pol_evict_first()) : "memory");
+#else
+    asm volatile("st.global.cg.v8.u32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};"
+                 :: "l"(p), "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7]) : "memory");
+#endif
 }
 struct alignas(32) U8x { uint32_t v[8]; };
-B2_D U8x ld_lut8(const void *p)
-{ /* the four children intervals of a node: one sector of the interval table (hot levels live in L2) */
+B2_D U8x ld_lut8(const void *p, bool keep = false)
+{ /* the four children intervals of a node: one sector of the interval table.  keep: a shallow level, which
+     all reads share and which should stay in L2; deep levels are touched once per chain */
     U8x r;
+#if defined(B2_L2_HINTS) && defined(B2_HINT_LUT)
+    if (keep)
+        asm volatile("ld.global.nc.L1::no_allocate.L2::cache_hint.v8.u32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8], %9;"
+                     : "=r"(r.v[0]), "=r"(r.v[1]), "=r"(r.v[2]), "=r"(r.v[3]), "=r"(r.v[4]), "=r"(r.v[5]), "=r"(r.v[6]),
+                       "=r"(r.v[7])
+                     : "l"(p), "l"(pol_evict_last()));
+    else
+        asm volatile("ld.global.nc.L1::no_allocate.L2::cache_hint.v8.u32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8], %9;"
+                     : "=r"(r.v[0]), "=r"(r.v[1]), "=r"(r.v[2]), "=r"(r.v[3]), "=r"(r.v[4]), "=r"(r.v[5]), "=r"(r.v[6]),
+                       "=r"(r.v[7])
+                     : "l"(p), "l"(pol_evict_first()));
+#else
+    (void)keep;
     asm volatile("ld.global.nc.L1::no_allocate.v8.u32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
                  : "=r"(r.v[0]), "=r"(r.v[1]), "=r"(r.v[2]), "=r"(r.v[3]), "=r"(r.v[4]), "=r"(r.v[5]), "=r"(r.v[6]),
                    "=r"(r.v[7])
                  : "l"(p));
+#endif
     return r;
 }
 B2_D void st8(uint32_t *p, const uint32_t v[8])
@@ -152,8 +184,9 @@ inline uint32_t ld_q(const uint32_t *p) { return *p; }
 inline void st8(uint32_t *p, const uint32_t v[8]) { for (int i = 0; i < 8; ++i) p[i] = v[i]; }
 inline OccBlk ld_blk(const OccBlk *p) { return *p; }
 inline void ld8cg(const uint32_t *p, uint32_t v[8]) { for (int i = 0; i < 8; ++i) v[i] = p[i]; }
+inline void st8rec(uint32_t *p, const uint32_t v[8]) { for (int i = 0; i < 8; ++i) p[i] = v[i]; }
 struct alignas(32) U8x { uint32_t v[8]; };
-inline U8x ld_lut8(const void *p) { return *reinterpret_cast<const U8x *>(p); }
+inline U8x ld_lut8(const void *p, bool = false) { return *reinterpret_cast<const U8x *>(p); }
 inline int popc32(uint32_t v) { return __builtin_popcount(v); }
 inline int ctz32(uint32_t v) { return __builtin_ctz(v); }
 #endif
@@ -327,7 +360,7 @@ B2_HD void children4(const FmView &f, uint32_t path, uint32_t k, uint32_t l, uin
     const uint32_t d = path & 31u;
     if (d != B2_PATH_DEAD && (int)d < f.lut_k) {
         const uint32_t *p = f.lut + 2 * lut_pair(f.lut_w, (int)d + 1, (uint64_t)(path >> 5) << 2);
-        const U8x v = ld_lut8(p);
+        const U8x v = ld_lut8(p, d < 11u); /* levels <= 11: 90 MB for both indexes */
         nk[0] = v.v[0]; nl[0] = v.v[1]; nk[1] = v.v[2]; nl[1] = v.v[3];
         nk[2] = v.v[4]; nl[2] = v.v[5]; nk[3] = v.v[6]; nl[3] = v.v[7];
         n_sectors = 1;
@@ -731,10 +764,10 @@ struct SearchLane {
         h[4] = (uint32_t)cmm | (uint32_t)cgo << 8 | (uint32_t)cge << 16;
         h[5] = ck; h[6] = cl; h[7] = 0;
         uint32_t *rec = ent[slot].w;
-        st8(rec, h);
+        st8rec(rec, h);
         if ((gmask & 15u) | xmask) { /* a lone insertion does not need the children's sector */
             uint32_t c8[8] = {nk4[0], nl4[0], nk4[1], nl4[1], nk4[2], nl4[2], nk4[3], nl4[3]};
-            st8(rec + 8, c8);
+            st8rec(rec + 8, c8);
         }
         n_entries += popc32(gmask) + popc32(xmask);
     }

@@ -305,7 +305,7 @@ def main():
     ap.add_argument("--model", default="default", choices=["default", "stress"],
                     help="read model (SURVEY §8d); 'stress' + --read-len 150 + --aln-args = BASELINE configs[2]")
     ap.add_argument("--aln-args", default="", help="aln options for the run, e.g. '-n 4 -o 2 -e 10 -l 32 -k 2'")
-    ap.add_argument("--in-flight", type=int, default=2,
+    ap.add_argument("--in-flight", type=int, default=3,
                     help="batches in flight in the e2e measurement (contexts sharing the device index)")
     ap.add_argument("--set", action="append", default=[], help="engine knob key=value")
     args = ap.parse_args()
@@ -422,7 +422,7 @@ def main():
         eng.batch_device(d_lens.data_ptr(), d_offs.data_ptr(), d_codes.data_ptr(), n, L, opt)
         return eng.stats()
 
-    # end-to-end: two batches in flight (engine + clone sharing the device index, one host thread each),
+    # end-to-end: --in-flight batches in flight (engine + clones sharing the device index, one host thread each),
     # so the H2D / D2H copies of one step overlap the kernels of the other (double buffering)
     K = max(1, args.in_flight)
     engines = [eng] + [eng.clone() for _ in range(K - 1)]

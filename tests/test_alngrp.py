@@ -127,3 +127,58 @@ def test_gpu_merge_matches_oracle_and_golden(golden_dir, g1_index):
         assert np.array_equal(got[0], want[0]) and np.array_equal(got[1], want[1])
         a, b = packed(*got), packed(*want)
         assert a[0].tobytes() == b[0].tobytes() and np.array_equal(a[1], b[1])
+
+
+@pytest.mark.gpu
+def test_gpu_merge_of_primary_and_alt_sai_against_reference_saiset(tmp_path):
+    """BASELINE config 5 shape: the same reads aligned against a primary index and an index of alt contigs cut
+    from it, the two .sai streams merged per read — engine (`b200aln_alngrp_merge`) against the reference's own
+    saiset.c reading the same two files (oracle/_ref/alngrp_dump)."""
+    from ibwa_b200 import engine, fmbuild, gap_init_opt, synth
+    if not os.path.exists(gold.DUMP):
+        pytest.skip("oracle/_ref/alngrp_dump not present")
+    rng = np.random.default_rng(5)
+    pri = synth.random_genome(300_000, 20260105)
+    alts = []
+    for j in range(150):
+        s0 = int(rng.integers(0, len(pri) - 2100))
+        a = pri[s0:s0 + 2000].copy()
+        snp = np.arange(150, 2000, 300)
+        a[snp] = (a[snp] + 1) & 3
+        alts.append(a)
+    alt = np.concatenate(alts)
+    reads = np.concatenate([synth.simulate_reads_fast(pri, 3000, 100, 1), synth.simulate_reads_fast(alt, 3000, 100, 2)])
+    n, L = reads.shape
+    lens = np.full(n, L, np.int32)
+    offs = np.arange(n, dtype=np.int64) * L
+    opt = gap_init_opt()
+    n_alns, recs, paths = [], [], []
+    for tag, g in (("pri", pri), ("alt", alt)):
+        bwt, _ = fmbuild.build_bwt_sa_numpy(g)
+        rbwt, _ = fmbuild.build_bwt_sa_numpy(np.ascontiguousarray(g[::-1]))
+        with engine.Engine(bwt, rbwt, 0) as e:
+            na, rc = e.cal_sa_reg_gap(lens, offs, reads.reshape(-1), opt)
+        n_alns.append(na)
+        recs.append(rc)
+        p = str(tmp_path / f"{tag}.sai")
+        with open(p, "wb") as f:
+            sai.write_header(f, opt)
+            sai.write_batch(f, na, rc)
+        paths.append(p)
+    import subprocess
+    out = subprocess.run([gold.DUMP, str(n)] + paths, stdout=subprocess.PIPE, check=True).stdout
+    w = np.frombuffer(out, dtype=np.uint32)
+    want_n = np.zeros(n, np.int32)
+    want_db, want_rec, p = [], [], 0
+    for r in range(n):
+        c = int(w[p]); p += 1
+        want_n[r] = c
+        blk = w[p:p + 5 * c].reshape(c, 5); p += 5 * c
+        want_db.append(blk[:, 0]); want_rec.append(blk[:, 1:])
+    want_db = np.concatenate(want_db)
+    want_rec = np.concatenate(want_rec).reshape(-1).view(sai.ALN_DTYPE)
+    with engine.Engine(bwt, rbwt, 0) as e:
+        got = e.alngrp_merge(n_alns, recs, opt.s_mm)
+    same(got, want_n, want_rec, want_db)
+    assert ((n_alns[0] > 0) & (n_alns[1] > 0)).mean() > 0.3      # many reads hit both indexes
+    assert len(np.unique(want_db)) == 2

@@ -532,6 +532,14 @@ def main():
                            "random_sector_roof_gbs": sector_roof, "random_64B_pair_roof_gbs": pair_roof,
                            "frac_of_random_sector_roof": achieved / sector_roof if sector_roof else None,
                            "occ_sectors_per_s": counted["occ_lookups"] / (ms_search * 1e-3)}
+        if traffic and sector_roof:
+            # the memory system's limit for this access pattern is a transaction rate: DRAM moves the
+            # kernel's traffic in 64-byte transactions; the gather roof counts random 32-byte requests per second
+            tx = traffic / 64.0
+            out["roofline"]["dram_transactions_per_read"] = tx / n
+            out["roofline"]["dram_transactions_per_s"] = tx / (ms_search * 1e-3)
+            out["roofline"]["random_requests_roof_per_s"] = sector_roof * 1e9 / 32.0
+            out["roofline"]["frac_of_transaction_roof"] = (tx / (ms_search * 1e-3)) / (sector_roof * 1e9 / 32.0)
         # parity of this very run against the oracle port on the sample
         m = port["n"]
         n_aln_d, rec_d = eng.cal_sa_reg_gap(np.full(m, L, np.int32), np.arange(m, dtype=np.int64) * L,

@@ -149,6 +149,199 @@ class ParsePool {
     bool stop_ = false;
 };
 
+/*
+ * Sequential source of decompressed bytes with gzread()'s contract (utils.c:56-66 opens every input
+ * through zlib, "-" = stdin; plain data passes through unchanged).
+ *   BGZF files (BAM, bgzip: every gzip member carries its size in a 'BC' extra field) are inflated block-parallel
+ *   on the parse pool, a window of blocks at a time;
+ *   every other stream goes through zlib's gzread on a helper thread that stays one buffer ahead of the parser.
+ * The bytes delivered are the ones gzread would deliver; only who inflates them, and when, differs.
+ */
+class InflateSource {
+  public:
+    explicit InflateSource(const char *fn)
+    {
+        const bool is_stdin = strcmp(fn, "-") == 0;
+        if (!is_stdin && !getenv("B200ALN_NO_BGZF")) {
+            fd_ = open(fn, O_RDONLY);
+            unsigned char h[18];
+            if (fd_ >= 0 && pread(fd_, h, 18, 0) == 18 && h[0] == 0x1f && h[1] == 0x8b && h[2] == 8 && (h[3] & 4) &&
+                h[12] == 'B' && h[13] == 'C' && h[14] == 2 && h[15] == 0)
+                bgzf_ = true;
+            else if (fd_ >= 0) { close(fd_); fd_ = -1; }
+        }
+        if (!bgzf_) {
+            gz_ = is_stdin ? gzdopen(fileno(stdin), "r") : gzopen(fn, "r");
+            if (!gz_) b2host::fatal("b200aln_aln_core", (std::string("fail to open file '") + fn + "'.").c_str());
+            gzbuffer(gz_, 1 << 20);
+            for (auto &b : ring_) b.data.resize(kChunk);
+            th_ = std::thread([this] { producer(); });
+        }
+    }
+    ~InflateSource()
+    {
+        if (th_.joinable()) {
+            {
+                std::lock_guard<std::mutex> g(m_);
+                stop_ = true;
+            }
+            cv_.notify_all();
+            th_.join();
+        }
+        if (gz_) gzclose(gz_);
+        if (fd_ >= 0) close(fd_);
+    }
+    /* like gzread: the number of bytes delivered, less than n only at the end of the stream */
+    int read(void *dst, unsigned n)
+    {
+        unsigned char *d = (unsigned char *)dst;
+        unsigned got = 0;
+        while (got < n) {
+            if (bgzf_) {
+                if (out_pos_ == out_.size() && !refill_bgzf()) break;
+                const size_t k = std::min<size_t>(n - got, out_.size() - out_pos_);
+                memcpy(d + got, out_.data() + out_pos_, k);
+                out_pos_ += k;
+                got += (unsigned)k;
+            } else {
+                Chunk &c = ring_[rd_idx_ % kRing];
+                {
+                    std::unique_lock<std::mutex> g(m_);
+                    cv_.wait(g, [&] { return c.full; });
+                }
+                if (c.len == 0) break; /* end of stream (stays "full": further reads return 0 too) */
+                const size_t k = std::min<size_t>(n - got, c.len - c.pos);
+                memcpy(d + got, c.data.data() + c.pos, k);
+                c.pos += k;
+                got += (unsigned)k;
+                if (c.pos == c.len) {
+                    {
+                        std::lock_guard<std::mutex> g(m_);
+                        c.full = false;
+                    }
+                    cv_.notify_all();
+                    ++rd_idx_;
+                }
+            }
+        }
+        return (int)got;
+    }
+
+  private:
+    /* ---- zlib stream, one helper thread ahead ---- */
+    static const size_t kChunk = (size_t)16 << 20;
+    static const int kRing = 3;
+    struct Chunk { std::vector<unsigned char> data; size_t len = 0, pos = 0; bool full = false; };
+    void producer()
+    {
+        for (uint64_t i = 0;; ++i) {
+            Chunk &c = ring_[i % kRing];
+            {
+                std::unique_lock<std::mutex> g(m_);
+                cv_.wait(g, [&] { return !c.full || stop_; });
+                if (stop_) return;
+            }
+            const int k = gzread(gz_, c.data.data(), (unsigned)kChunk);
+            c.len = k > 0 ? (size_t)k : 0;
+            c.pos = 0;
+            {
+                std::lock_guard<std::mutex> g(m_);
+                c.full = true;
+            }
+            cv_.notify_all();
+            if (c.len == 0) return; /* end of stream or error: the zero-length chunk tells the reader */
+        }
+    }
+    /* ---- BGZF, block-parallel ---- */
+    struct Block { size_t in_off, in_len, out_off, out_len; uint32_t crc; };
+    bool refill_bgzf()
+    {
+        if (bgzf_eof_) return false;
+        static const size_t kWindow = [] { /* compressed bytes per round (B200ALN_BGZF_WINDOW: tests shrink it) */
+            const char *e = getenv("B200ALN_BGZF_WINDOW");
+            const long v = e ? atol(e) : 0;
+            return v >= 1024 ? (size_t)v : (size_t)24 << 20;
+        }();
+        cbuf_.resize(kWindow + 65536 + 64);
+        const ssize_t have = pread(fd_, cbuf_.data(), cbuf_.size(), (off_t)file_pos_);
+        if (have <= 0) { bgzf_eof_ = true; return false; }
+        std::vector<Block> blocks;
+        size_t at = 0, out_total = 0;
+        while (at + 18 <= (size_t)have && at < kWindow) {
+            const unsigned char *h = cbuf_.data() + at;
+            if (!(h[0] == 0x1f && h[1] == 0x8b && h[2] == 8 && (h[3] & 4)))
+                b2host::fatal("b200aln_reader", "corrupt BGZF stream (bad member header).");
+            const unsigned xlen = h[10] | h[11] << 8;
+            if (at + 12 + xlen > (size_t)have) break;
+            int bsize = -1;
+            for (unsigned x = 0; x + 4 <= xlen;) { /* the BC subfield holds (block size - 1) */
+                const unsigned char *f = h + 12 + x;
+                const unsigned slen = f[2] | f[3] << 8;
+                if (f[0] == 'B' && f[1] == 'C' && slen == 2 && x + 6 <= xlen) bsize = (f[4] | f[5] << 8) + 1;
+                x += 4 + slen;
+            }
+            if (bsize < 0 || (size_t)bsize < 12 + xlen + 8) b2host::fatal("b200aln_reader", "corrupt BGZF stream (no block size).");
+            if (at + (size_t)bsize > (size_t)have) break; /* the block continues beyond what was read */
+            const unsigned char *tail = h + bsize - 8;
+            Block b;
+            b.in_off = at + 12 + xlen;
+            b.in_len = (size_t)bsize - 12 - xlen - 8;
+            b.crc = tail[0] | tail[1] << 8 | tail[2] << 16 | (uint32_t)tail[3] << 24;
+            b.out_len = tail[4] | tail[5] << 8 | tail[6] << 16 | (uint32_t)tail[7] << 24;
+            b.out_off = out_total;
+            out_total += b.out_len;
+            blocks.push_back(b);
+            at += (size_t)bsize;
+        }
+        if (blocks.empty()) {
+            if ((size_t)have >= 18) b2host::fatal("b200aln_reader", "truncated BGZF block.");
+            bgzf_eof_ = true;
+            return false;
+        }
+        file_pos_ += at;
+        out_.resize(out_total);
+        out_pos_ = 0;
+        ParsePool &pool = ParsePool::get();
+        const unsigned nw = pool.size();
+        std::vector<int> bad(nw, 0);
+        pool.run([&](unsigned t) {
+            z_stream zs;
+            for (size_t i = t; i < blocks.size(); i += nw) {
+                const Block &b = blocks[i];
+                if (b.out_len == 0) continue;
+                memset(&zs, 0, sizeof zs);
+                if (inflateInit2(&zs, -15) != Z_OK) { bad[t] = 1; return; }
+                zs.next_in = cbuf_.data() + b.in_off;
+                zs.avail_in = (uInt)b.in_len;
+                zs.next_out = out_.data() + b.out_off;
+                zs.avail_out = (uInt)b.out_len;
+                const int rc = inflate(&zs, Z_FINISH);
+                inflateEnd(&zs);
+                if (rc != Z_STREAM_END || zs.avail_out != 0 ||
+                    crc32(crc32(0L, Z_NULL, 0), out_.data() + b.out_off, (uInt)b.out_len) != b.crc) {
+                    bad[t] = 1;
+                    return;
+                }
+            }
+        });
+        for (int x : bad) if (x) b2host::fatal("b200aln_reader", "corrupt BGZF block (inflate or CRC error).");
+        return out_total > 0 ? true : refill_bgzf(); /* a window of empty blocks (the EOF marker): look further */
+    }
+
+    bool bgzf_ = false, bgzf_eof_ = false;
+    int fd_ = -1;
+    uint64_t file_pos_ = 0;
+    std::vector<unsigned char> cbuf_, out_;
+    size_t out_pos_ = 0;
+    gzFile gz_ = nullptr;
+    std::thread th_;
+    std::mutex m_;
+    std::condition_variable cv_;
+    Chunk ring_[kRing];
+    uint64_t rd_idx_ = 0;
+    bool stop_ = false;
+};
+
 /* buffered reader + record parser with the reference parser's observable
  * behaviour (kseq.h:60-71,150-194): multi-line records, name = first
  * whitespace-delimited token, only isgraph() characters enter the sequence,
@@ -179,16 +372,13 @@ class SeqReader {
             if (fd >= 0) close(fd);
         }
         if (!map_) {
-            if (strcmp(fn, "-") == 0) f_ = gzdopen(fileno(stdin), "r"); /* utils.c:56-66 */
-            else f_ = gzopen(fn, "r");
-            if (!f_) b2host::fatal("b200aln_aln_core", (std::string("fail to open file '") + fn + "'.").c_str());
+            f_.reset(new InflateSource(fn));
             buf_.resize((size_t)160 << 20);
             data_ = buf_.data();
         }
     }
     ~SeqReader()
     {
-        if (f_) gzclose(f_);
         if (map_) munmap(map_, map_len_);
     }
 
@@ -367,7 +557,7 @@ class SeqReader {
         begin_ = 0;
         end_ = tail;
         const int want = (int)((int64_t)buf_.size() - end_);
-        const int got = gzread(f_, buf_.data() + end_, (unsigned)want);
+        const int got = f_->read(buf_.data() + end_, (unsigned)want);
         if (got < want) is_eof_ = true;
         if (got > 0) end_ += got;
     }
@@ -376,7 +566,7 @@ class SeqReader {
         if (is_eof_ && begin_ >= end_) return -1;
         if (begin_ >= end_) {
             begin_ = 0;
-            end_ = gzread(f_, buf_.data(), (unsigned)buf_.size());
+            end_ = f_->read(buf_.data(), (unsigned)buf_.size());
             if (end_ < (int64_t)buf_.size()) is_eof_ = true;
             if (end_ <= 0) { end_ = 0; return -1; }
         }
@@ -391,7 +581,7 @@ class SeqReader {
             if (begin_ >= end_) {
                 if (is_eof_) break;
                 begin_ = 0;
-                end_ = gzread(f_, buf_.data(), (unsigned)buf_.size());
+                end_ = f_->read(buf_.data(), (unsigned)buf_.size());
                 if (end_ < (int64_t)buf_.size()) is_eof_ = true;
                 if (end_ <= 0) { end_ = 0; break; }
             }
@@ -408,7 +598,7 @@ class SeqReader {
         return (int)str.size();
     }
 
-    gzFile f_ = nullptr;
+    std::unique_ptr<InflateSource> f_; /* zlib mode: where the bytes come from */
     std::vector<unsigned char> buf_;   /* zlib mode: the stream buffer */
     unsigned char *map_ = nullptr;     /* mapped mode: the file */
     size_t map_len_ = 0;
@@ -547,12 +737,10 @@ class BamReader {
   public:
     BamReader(const char *fn, int which) : which_(which ? which : 7)
     {
-        f_ = strcmp(fn, "-") == 0 ? gzdopen(fileno(stdin), "r") : gzopen(fn, "r");
-        if (!f_) b2host::fatal("b200aln_aln_core", (std::string("fail to open file '") + fn + "'.").c_str());
-        gzbuffer(f_, 1 << 20);
+        f_.reset(new InflateSource(fn));
         char magic[4];
         int32_t l_text = 0, n_ref = 0;
-        if (gzread(f_, magic, 4) != 4 || memcmp(magic, "BAM\001", 4) != 0)
+        if (f_->read(magic, 4) != 4 || memcmp(magic, "BAM\001", 4) != 0)
             b2host::fatal("bam_header_read", "invalid BAM binary header (this is not a BAM file).");
         rd(&l_text, 4);
         skip(l_text);
@@ -564,7 +752,6 @@ class BamReader {
             rd(&l_ref, 4);
         }
     }
-    ~BamReader() { if (f_) gzclose(f_); }
 
     /* bwa_read_bam: up to n_needed reads into the packed form */
     int next_batch(int n_needed, int trim_qual, PackedBatch &b)
@@ -573,12 +760,12 @@ class BamReader {
         b.clear();
         for (;;) {
             int32_t block_len;
-            if (gzread(f_, &block_len, 4) != 4) break;
+            if (f_->read(&block_len, 4) != 4) break;
             uint32_t x[8];
-            if (gzread(f_, x, 32) != 32) break;
+            if (f_->read(x, 32) != 32) break;
             const int data_len = block_len - 32;
             data_.resize((size_t)(data_len > 0 ? data_len : 0));
-            if (data_len > 0 && gzread(f_, data_.data(), (unsigned)data_len) != data_len) break;
+            if (data_len > 0 && f_->read(data_.data(), (unsigned)data_len) != data_len) break;
             const uint32_t flag = x[3] >> 16, n_cigar = x[3] & 0xffff, l_qname = x[2] & 0xff;
             const int l = (int)x[4];
             bool go = false;
@@ -619,7 +806,7 @@ class BamReader {
     }
 
   private:
-    void rd(void *p, int n) { if (gzread(f_, p, (unsigned)n) != n) b2host::fatal("bam_header_read", "truncated BAM header."); }
+    void rd(void *p, int n) { if (f_->read(p, (unsigned)n) != n) b2host::fatal("bam_header_read", "truncated BAM header."); }
     void skip(int n)
     {
         char tmp[4096];
@@ -629,7 +816,7 @@ class BamReader {
             n -= k;
         }
     }
-    gzFile f_ = nullptr;
+    std::unique_ptr<InflateSource> f_;
     int which_;
     std::vector<uint8_t> data_, seq_, qual_;
 };

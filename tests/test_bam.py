@@ -25,7 +25,7 @@ def bam_record(name, codes, quals, flag):
     return struct.pack("<i", len(body)) + body
 
 
-def make_bam(path, genome, rng, n=400):
+def make_bam(path, genome, rng, n=400, bgzf=False):
     out = io.BytesIO()
     text = b"@HD\tVN:1.0\n"
     out.write(b"BAM\1" + struct.pack("<i", len(text)) + text + struct.pack("<i", 1))
@@ -46,13 +46,19 @@ def make_bam(path, genome, rng, n=400):
             r = np.array([3 - c if c < 4 else c for c in r[::-1]], dtype=np.uint8)
             q = q[::-1]
         out.write(bam_record(f"q{i}", r, q, flag))
-    with gzip.open(path, "wb") as f:
-        f.write(out.getvalue())
+    if bgzf:      # the real container: BGZF blocks (inflated block-parallel by the native reader)
+        from test_reader import bgzf_bytes
+        with open(path, "wb") as f:
+            f.write(bgzf_bytes(out.getvalue(), block=3000))
+    else:         # any gzip stream is accepted, like the reference (gzread)
+        with gzip.open(path, "wb") as f:
+            f.write(out.getvalue())
 
 
+@pytest.mark.parametrize("bgzf", [False, True])
 @pytest.mark.parametrize("flags", [["-b"], ["-b", "-1"], ["-b", "-2"], ["-b", "-0"], ["-b", "-1", "-2"],
                                    ["-b", "-q", "15"]])
-def test_bam_reader_matches_reference(tmp_path, golden_dir, g1_index, flags):
+def test_bam_reader_matches_reference(tmp_path, golden_dir, g1_index, flags, bgzf):
     if not pyoracle.have_ref():
         pytest.skip("oracle/_ref/ibwa not present")
     import gzip as gz
@@ -60,7 +66,7 @@ def test_bam_reader_matches_reference(tmp_path, golden_dir, g1_index, flags):
     txt = gz.open(os.path.join(golden_dir, "g1.fa.gz")).read().split(b"\n", 1)[1].replace(b"\n", b"")
     genome = seqio.NT4[np.frombuffer(txt, dtype=np.uint8)]
     bam = str(tmp_path / "in.bam")
-    make_bam(bam, genome, np.random.default_rng(7))
+    make_bam(bam, genome, np.random.default_rng(7), bgzf=bgzf)
     prefix = str(tmp_path / "g1")
     os.symlink(os.path.join(golden_dir, "g1.bwt"), prefix + ".bwt")
     os.symlink(os.path.join(golden_dir, "g1.rbwt"), prefix + ".rbwt")

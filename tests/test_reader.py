@@ -151,3 +151,42 @@ def test_parallel_path_falls_back_on_odd_records(tmp_path):
     assert both(p) > 30000
     assert both(p, trim_qual=25) > 30000
     assert both(p, mode=3 | 0x200, trim_qual=10, n_needed=9973) > 30000
+
+
+def bgzf_bytes(data: bytes, block=60000, level=6) -> bytes:
+    """`data` as a BGZF stream (SAM spec 4.1): gzip members of <= 64 KB that carry their size in a 'BC' extra
+    field, then the empty end-of-file member."""
+    import struct
+    import zlib
+    out = []
+    for off in list(range(0, len(data), block)) + [None]:
+        chunk = b"" if off is None else data[off:off + block]
+        co = zlib.compressobj(level, zlib.DEFLATED, -15)
+        comp = co.compress(chunk) + co.flush()
+        bsize = 12 + 6 + len(comp) + 8
+        out.append(b"\x1f\x8b\x08\x04\0\0\0\0\0\xff" + struct.pack("<H", 6) + b"BC" + struct.pack("<HH", 2, bsize - 1) +
+                   comp + struct.pack("<II", zlib.crc32(chunk) & 0xFFFFFFFF, len(chunk)))
+    return b"".join(out)
+
+
+@pytest.mark.parametrize("block", [60000, 777, 65280])
+def test_bgzf_fastq_is_inflated_block_parallel(tmp_path, block):
+    """A bgzip-compressed FASTQ goes through the block-parallel inflater; the records must be the ones the
+    zlib path (B200ALN_NO_BGZF) and the Python mirror deliver — across block and window boundaries."""
+    rng = np.random.default_rng(3)
+    nt = np.frombuffer(b"ACGTN", dtype=np.uint8)
+    recs = []
+    for i in range(30000):
+        L = int(rng.integers(30, 160))
+        recs.append(b"@read%d/1\n" % i + nt[rng.integers(0, 5, size=L)].tobytes() + b"\n+\n" + b"I" * L + b"\n")
+    data = b"".join(recs) + HOSTILE["multiline_fastq"]
+    p = str(tmp_path / "r.fq.gz")
+    with open(p, "wb") as f:
+        f.write(bgzf_bytes(data, block=block, level=1))
+    assert both(p) == 30002
+    assert both(p, n_needed=4099) == 30002
+    os.environ["B200ALN_NO_BGZF"] = "1"
+    try:
+        assert both(p) == 30002
+    finally:
+        del os.environ["B200ALN_NO_BGZF"]

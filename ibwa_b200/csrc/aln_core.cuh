@@ -937,14 +937,18 @@ struct SearchLane {
     /* true when the next entry does not have to come from memory */
     B2_HD bool ready() const { return have_cur || extending || og != 0; }
 
-    /* pop until something needs a lookup; returns its kind, or NONE when the search ended
+    /* max_rounds: how many pruned pops (a run of group members, or a single entry failing the width bound) the
+     * lane may go through before it gives the warp's iteration back without a lookup — the other lanes do not
+     * wait while one lane prunes its way through a bucket (measured: 1 is best).
+     * pop until something needs a lookup; returns its kind, or NONE when the search ended
      * (finished is set) or when the next entry has to come from memory and allow_pop is false:
      * the kernel lets the lanes of a warp take their memory pops in batches, so that the extra
      * dependent load and the pop code are paid once for several lanes instead of every iteration. */
-    B2_HD int prepare(const SearchEnv &E, bool allow_pop = true)
+    B2_HD int prepare(const SearchEnv &E, bool allow_pop = true, int max_rounds = 1 << 30)
     {
         const Params *P = &E.P;
         const bool gape_mode = P->mode & MODE_GAPE, nonstop = P->mode & MODE_NONSTOP;
+        int round = 0;
         for (;;) {
             if (extending) { pq = ld_q(qrow(E, ca) + (ci - 1)); return EXTEND; }
             if (n_entries == 0) { finished = true; return NONE; }
@@ -954,7 +958,10 @@ struct SearchLane {
                     if (!allow_pop) return NONE;
                     pop_group(E);
                 }
-                if (!take_member(E)) continue;
+                if (!take_member(E)) { /* a whole run pruned */
+                    if (++round >= max_rounds) return NONE; /* the warp moves on; this lane goes on in the next iteration */
+                    continue;
+                }
             } else { /* held exact child: same accounting as a push followed by a pop */
                 --n_entries;
                 if (STATS) ++n_pops;
@@ -964,7 +971,10 @@ struct SearchLane {
             if (!nonstop && cscore > best_score + P->s_mm) { finished = true; return NONE; }
             pm = max_diff - cmm - cgo - (gape_mode ? cge : 0);
             if (pm < 0) { B2_DBG(8); continue; }
-            if (ci > 0 && pm < q_bid(pq)) { B2_DBG(9); continue; } /* pq = record of position ci - 1 */
+            if (ci > 0 && pm < q_bid(pq)) { /* pq = record of position ci - 1 */
+                if (++round >= max_rounds) return NONE;
+                continue;
+            }
             if (ci == 0) {
                 if (!on_hit(E)) { finished = true; return NONE; }
                 continue;

@@ -124,6 +124,7 @@ struct SearchArgs {
     uint32_t *heads_wide;     /* HeadsWide32 only: per lane n_buckets heads + mask words */
     int heads_wide_stride;
     int pop_batch; /* lanes of a warp that must wait for a memory pop before the warp takes them */
+    int prep_rounds; /* pops / prunes a lane may go through per warp iteration before the warp moves on */
 };
 
 template <class Heads> struct HeadsFactory;
@@ -227,7 +228,7 @@ __global__ void __launch_bounds__(128, MINB) k_search(const __grid_constant__ Se
         /* memory pops are taken in batches: when enough lanes wait for one, or nobody else can move */
         const bool allow_pop = __popc(wait_mask) >= A.pop_batch || ready_mask == 0;
         int mode = L.NONE;
-        if (running && (ready || allow_pop)) mode = L.prepare(A.env, allow_pop);
+        if (running && (ready || allow_pop)) mode = L.prepare(A.env, allow_pop, A.prep_rounds);
         __syncwarp();
         uint32_t nk4[4], nl4[4], ns = 0;
         if (mode != L.NONE) children4(A.env.fm[1 - L.ca], L.cpath, L.ck, L.cl, nk4, nl4, ns);
@@ -462,6 +463,7 @@ struct b200aln_ctx {
     uint32_t arena_cap_mid = 12288; /* middle pass: 16-bit heads in shared memory, free-list arena */
     int rec_cap_mid = 512, mid_lanes = 148 * 192; /* x 12288 records x 64 B = 22 GB, allocated when a batch first needs it */
     int prefetch_fast = 0, prefetch_mid = 1; /* L2 prefetch of the next pop candidate, per pass */
+    int prep_rounds = 1;   /* pruned pops a lane may go through per warp iteration before the warp moves on */
     int reserve_reads = 0; /* size the per-batch buffers for at least this many reads */
     int count = 0;         /* 1: fast pass with the pop / sector counters (b200aln_stats_t pops, occ_lookups) */
     int pop_batch = 1;     /* memory pops are taken when this many lanes of a warp wait for one */
@@ -663,7 +665,7 @@ extern "C" b200aln_ctx *b200aln_clone(b200aln_ctx *p)
     c->arena_cap = p->arena_cap; c->arena_cap_big = p->arena_cap_big;
     c->rec_cap = p->rec_cap; c->rec_cap_big = p->rec_cap_big; c->big_lanes = p->big_lanes;
     c->arena_cap_mid = p->arena_cap_mid; c->rec_cap_mid = p->rec_cap_mid; c->mid_lanes = p->mid_lanes;
-    c->pop_batch = p->pop_batch; c->count = p->count; c->reserve_reads = p->reserve_reads;
+    c->pop_batch = p->pop_batch; c->count = p->count; c->reserve_reads = p->reserve_reads; c->prep_rounds = p->prep_rounds;
     c->prefetch_fast = p->prefetch_fast; c->prefetch_mid = p->prefetch_mid;
     CK(cudaStreamCreateWithFlags(&c->st, cudaStreamNonBlocking));
     for (int i = 0; i < 8; ++i) CK(cudaEventCreate(&c->ev[i]));
@@ -741,6 +743,7 @@ extern "C" void b200aln_set_int(b200aln_ctx *c, const char *key, int64_t v)
     else if (!strcmp(key, "pop_batch")) c->pop_batch = (int)v;
     else if (!strcmp(key, "count")) c->count = (int)v;
     else if (!strcmp(key, "reserve_reads")) c->reserve_reads = (int)v;
+    else if (!strcmp(key, "prep_rounds")) c->prep_rounds = (int)v;
     else if (!strcmp(key, "prefetch_fast")) c->prefetch_fast = (int)v;
     else if (!strcmp(key, "prefetch_mid")) c->prefetch_mid = (int)v;
     else if (!strcmp(key, "arena_cap_mid")) c->arena_cap_mid = (uint32_t)v;
@@ -884,6 +887,7 @@ static void run_batch_device(b200aln_ctx *c, int n_reads, int max_len, const int
     SA.stat = dm->stat;
     SA.heads_wide = nullptr; SA.heads_wide_stride = 0;
     SA.pop_batch = c->pop_batch;
+    SA.prep_rounds = c->prep_rounds;
     launch_search_fast(c, SA, sblocks);
     ++launches;
     CK(cudaEventRecord(c->ev[3], c->st));
@@ -926,6 +930,7 @@ static void run_batch_device(b200aln_ctx *c, int n_reads, int max_len, const int
         SM.env.recs = c->recs_mid.as<Rec>(); SM.env.rec_cap = c->rec_cap_mid; SM.recs_by_work = 1;
         SM.over_slot = c->over_slot.as<int32_t>(); SM.slot_tag = 0;
         SM.env.prefetch_next = c->prefetch_mid;
+        SM.prep_rounds = 1 << 30; /* few lanes are busy here: a lane should not wait for the others to prune */
         SM.counter = &dm->counter_mid; SM.n_over = &dm->n_over2; SM.over_list = c->over_list2.as<int32_t>();
         launch_search_mid(c, SM, mblocks);
         ++launches;
@@ -953,6 +958,7 @@ static void run_batch_device(b200aln_ctx *c, int n_reads, int max_len, const int
         SB.env.recs = c->recs_big.as<Rec>(); SB.env.rec_cap = c->rec_cap_big; SB.recs_by_work = 1;
         SB.over_slot = c->over_slot.as<int32_t>(); SB.slot_tag = WIDE_TAG;
         SB.env.prefetch_next = c->prefetch_mid;
+        SB.prep_rounds = 1 << 30;
         SB.counter = &dm->counter_big; SB.n_over = nullptr; SB.over_list = nullptr;
         launch_search_big(c, SB, bblocks);
         ++launches;

@@ -138,6 +138,7 @@ double b200aln_timer_stop(b200aln_ctx *ctx);
  *   search_blocks_per_sm, width_blocks_per_sm, arena_cap, arena_cap_mid, arena_cap_big, rec_cap, rec_cap_mid,
  *   rec_cap_big, mid_lanes, big_lanes:
  *                  launch geometry and per-lane capacities; arena capacities count 64-byte records.
+ *   prep_rounds    pruned pops a lane may go through per warp iteration before the warp moves on (default 1).
  *   reserve_reads  size the per-batch device buffers for at least this many reads (drivers whose launches vary in size).
  *   count          1: the fast pass runs with its pop / sector counters (b200aln_stats_t pops, occ_lookups). */
 void b200aln_set_int(b200aln_ctx *ctx, const char *key, int64_t value);

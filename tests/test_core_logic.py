@@ -129,3 +129,65 @@ def test_equal_penalties_share_a_bucket(args, golden_dir, g1_index):
     reads = [batch.codes[o:o + l] for o, l in zip(batch.offs[:500], batch.lens[:500])]
     _vs_oracle(g1_index[0], g1_index[1], reads, args, arena_cap=1 << 22, rec_cap=4096, reuse=True, lut_k=4)
     _vs_oracle(g1_index[0], g1_index[1], reads[:200], args, arena_cap=1 << 22, rec_cap=4096, lut_k=2)
+
+
+def _random_option_sets(n, seed):
+    rng = np.random.default_rng(seed)
+    out = []
+    for _ in range(n):
+        a = []
+        if rng.random() < 0.7:
+            a += ["-n", str(int(rng.integers(0, 7)))] if rng.random() < 0.6 else ["-n", f"{rng.choice([0.01, 0.04, 0.1, 0.2])}"]
+        if rng.random() < 0.6:
+            a += ["-o", str(int(rng.integers(0, 4)))]
+        if rng.random() < 0.5:
+            a += ["-e", str(int(rng.integers(-1, 8)))]
+        if rng.random() < 0.4:
+            a += ["-i", str(int(rng.integers(0, 8)))]
+        if rng.random() < 0.3:
+            a += ["-d", str(int(rng.integers(0, 20)))]
+        if rng.random() < 0.5:
+            a += ["-l", str(int(rng.choice([10, 20, 32, 50, 1000])))]
+        if rng.random() < 0.5:
+            a += ["-k", str(int(rng.integers(0, 4)))]
+        if rng.random() < 0.3:
+            a += ["-m", str(int(rng.choice([50, 500, 5000, 200000])))]
+        if rng.random() < 0.5:
+            a += ["-M", str(int(rng.integers(1, 6)))]
+        if rng.random() < 0.5:
+            a += ["-O", str(int(rng.integers(1, 13)))]
+        if rng.random() < 0.5:
+            a += ["-E", str(int(rng.integers(1, 6)))]
+        if rng.random() < 0.3:
+            a += ["-R", str(int(rng.integers(1, 40)))]
+        if rng.random() < 0.15:
+            a += ["-N"]
+        if rng.random() < 0.25:
+            a += ["-L"]
+        if rng.random() < 0.2:
+            a += ["-c"]
+        out.append(a)
+    return out
+
+
+@pytest.mark.parametrize("k,args", list(enumerate(_random_option_sets(24, 20261018))))
+def test_random_option_sets_against_the_oracle(k, args, golden_dir, g1_index):
+    """The expansion-record state machine under option mixes nobody chose by hand (penalties that make buckets
+    coincide, tiny and huge budgets, seeding on and off, -N, -L, -c): device code on the CPU == oracle, on the
+    bump arena, the free-list arena and through the two-pass flow."""
+    opt, _, _, _ = parse_aln_args(args + ["p", "q"])
+    fq = "g1_short.fq.gz" if k % 4 == 3 else "g1_reads.fq.gz"
+    batch = next(seqio.read_batches(os.path.join(golden_dir, fq), opt.mode, opt.trim_qual))
+    lo = (k * 97) % max(1, len(batch.lens) - 160)
+    reads = [batch.codes[o:o + l] for o, l in zip(batch.offs[lo:lo + 160], batch.lens[lo:lo + 160])]
+    _vs_oracle(g1_index[0], g1_index[1], reads, args, arena_cap=1 << 21, rec_cap=1 << 14, reuse=bool(k & 1), lut_k=k % 5)
+    if k % 3 == 0:
+        from oracle import pyoracle
+        lens = np.array([len(r) for r in reads], np.int32)
+        offs = np.concatenate([[0], np.cumsum(lens)[:-1]]).astype(np.int64)
+        codes = np.concatenate(reads)
+        o_n, o_rec, _ = pyoracle.aln_batch(pyoracle.as_orc_bwt(g1_index[0]), pyoracle.as_orc_bwt(g1_index[1]), lens, offs,
+                                           codes, opt.to_c())
+        h_n, h_rec, nov, _ = pyharness.aln_batch(g1_index[0], g1_index[1], lens, offs, codes, opt.to_c(), arena_cap=48,
+                                                 rec_cap=2, big_cap=1 << 21)
+        assert np.array_equal(o_n, h_n) and o_rec.tobytes() == h_rec.tobytes()

@@ -334,3 +334,25 @@ def test_long_reads_wide_heads_and_empty_read(g1_index, golden_dir):
         o_n, o_rec, _ = pyoracle.aln_batch(pyoracle.as_orc_bwt(g1_index[0]), pyoracle.as_orc_bwt(g1_index[1]), lens, offs,
                                            codes, opt.to_c())
         assert np.array_equal(n_aln, o_n) and rec.tobytes() == o_rec.tobytes()
+
+
+def test_random_option_sets_on_the_gpu(g1_index, golden_dir):
+    """The option mixes of tests/test_core_logic.py::test_random_option_sets_against_the_oracle through the CUDA
+    kernels (all three passes reachable: small fast arena), records compared with the oracle."""
+    from test_core_logic import _random_option_sets
+    with engine.Engine(g1_index[0], g1_index[1], 0) as e:
+        e.set("arena_cap", 512)
+        for k, args in enumerate(_random_option_sets(24, 20261018)):
+            if k % 2:           # every other set: the CPU oracle is what takes the time here
+                continue
+            opt, _, _, _ = parse_aln_args(args + ["p", "q"])
+            fq = "g1_short.fq.gz" if k % 4 == 2 else "g1_reads.fq.gz"
+            batch = next(seqio.read_batches(os.path.join(golden_dir, fq), opt.mode, opt.trim_qual))
+            n = min(250, len(batch.lens))
+            lens, offs = batch.lens[:n], batch.offs[:n]
+            codes = batch.codes[:int(offs[n - 1] + lens[n - 1])]
+            n_aln, rec = e.cal_sa_reg_gap(lens, offs, codes, opt)
+            o_n, o_rec, _ = pyoracle.aln_batch(pyoracle.as_orc_bwt(g1_index[0]), pyoracle.as_orc_bwt(g1_index[1]), lens, offs,
+                                               codes, opt.to_c())
+            assert np.array_equal(n_aln, o_n), args
+            assert rec.tobytes() == o_rec.tobytes(), args

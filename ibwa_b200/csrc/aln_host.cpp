@@ -467,49 +467,107 @@ class SeqReader {
     /* One ordinary 4-line record found by the structural scan: offsets into the buffer. */
     struct Extent { int64_t start, seq, qual, next; int len; };
 
-    /* Structural scan (newline positions only) of up to max_records consecutive ordinary records from the
-     * cursor.  Does NOT move the cursor and does not look at the characters: convert_extent() validates them.
-     * Stops at the first record that is not of the plain 4-line shape or not wholly in the buffer. */
+    /* One ordinary 4-line record at p, located by its newlines only (convert_extent() validates the characters).
+     * `guess` = sequence length of the previous record (most files have one length): the sequence line is
+     * taken to end at seq + guess when a newline sits there.  Guessing costs nothing when wrong in the safe
+     * direction: a newline INSIDE the guessed region is a character <= 32, which convert_extent() refuses, and
+     * the record then goes through the exact parser; a longer line fails the test. */
+    bool walk_one(int64_t p, int &guess, Extent &x) const
+    {
+        const unsigned char *b = data_;
+        const int64_t e = end_;
+        if (p >= e || b[p] != '@') return false;
+        const unsigned char *nl1 = (const unsigned char *)memchr(b + p + 1, '\n', (size_t)(e - p - 1));
+        if (!nl1 || nl1 == b + p + 1 || isspace(b[p + 1])) return false;
+        const int64_t s0 = (int64_t)(nl1 - b) + 1;
+        int L;
+        if (guess > 0 && s0 + guess < e && b[s0 + guess] == '\n') L = guess;
+        else {
+            const unsigned char *nl2 = (const unsigned char *)memchr(b + s0, '\n', (size_t)(e - s0));
+            if (!nl2 || (int64_t)(nl2 - b) - s0 > 0x3fffffff) return false;
+            L = (int)((int64_t)(nl2 - b) - s0);
+        }
+        const int64_t q_plus = s0 + L + 1;
+        if (L <= 0 || q_plus >= e || b[q_plus] != '+') return false;
+        int64_t q0;
+        if (q_plus + 1 < e && b[q_plus + 1] == '\n') q0 = q_plus + 2;
+        else {
+            const unsigned char *nl3 = (const unsigned char *)memchr(b + q_plus, '\n', (size_t)(e - q_plus));
+            if (!nl3) return false;
+            q0 = (int64_t)(nl3 - b) + 1;
+        }
+        if (q0 + L >= e || b[q0 + L] != '\n') return false; /* (a newline inside the quality string is refused by convert_extent) */
+        x.start = p; x.seq = s0; x.len = L; x.qual = q0; x.next = q0 + L + 1;
+        guess = L;
+        return true;
+    }
+    /* consecutive ordinary records from p while they start before `limit`, at most max_records */
+    void walk(int64_t p, int64_t limit, size_t max_records, std::vector<Extent> &out) const
+    {
+        int guess = -1;
+        Extent x;
+        while (out.size() < max_records && p < limit && walk_one(p, guess, x)) {
+            out.push_back(x);
+            p = x.next;
+        }
+    }
+
+    /* Structural scan of up to max_records consecutive ordinary records from the cursor.  Does NOT move the
+     * cursor.  Stops at the first record that is not of the plain 4-line shape or not wholly in the buffer.
+     * Large requests are scanned in parallel: the byte range is cut into one slice per worker, every worker
+     * but the first looks for a place in its slice where two ordinary records follow a newline and walks on
+     * from there, and the pieces are joined only where one piece ends exactly where the next begins — so the
+     * joined list is a chain of consecutive records from the cursor, like the serial walk's (a piece that does
+     * not fit is dropped together with everything after it and scanned again by the next call). */
     int scan_fast(int max_records, std::vector<Extent> &out)
     {
         out.clear();
         if (last_char_ != 0) return 0;
         refill_keep_tail(1 << 26);
-        const unsigned char *b = data_;
-        const int64_t e = end_;
-        int64_t p = begin_;
-        int guess = -1; /* sequence length of the previous record: most files have one length */
-        while ((int)out.size() < max_records) {
-            if (p >= e || b[p] != '@') break;
-            const unsigned char *nl1 = (const unsigned char *)memchr(b + p + 1, '\n', (size_t)(e - p - 1));
-            if (!nl1 || nl1 == b + p + 1 || isspace(b[p + 1])) break;
-            const int64_t s0 = (int64_t)(nl1 - b) + 1;
-            /* the sequence line ends at s0 + L.  Guessing L costs nothing when wrong in the safe direction: a
-             * newline INSIDE the guessed region is a character <= 32, which convert_extent() refuses, and the
-             * record then goes through the exact parser; a longer line fails the test below. */
-            int L;
-            if (guess > 0 && s0 + guess < e && b[s0 + guess] == '\n') L = guess;
-            else {
-                const unsigned char *nl2 = (const unsigned char *)memchr(b + s0, '\n', (size_t)(e - s0));
-                if (!nl2 || (int64_t)(nl2 - b) - s0 > 0x3fffffff) break;
-                L = (int)((int64_t)(nl2 - b) - s0);
+        ParsePool &pool = ParsePool::get();
+        const unsigned T = pool.size();
+        const int64_t avail = end_ - begin_;
+        int64_t span = (int64_t)((double)max_records * avg_record_bytes_ * 1.03) + 4096;
+        if (span > avail) span = avail;
+        static const int64_t min_span = [] { /* B200ALN_PAR_SCAN_MIN: tests lower it to push small inputs through the parallel scan */
+            const char *e = getenv("B200ALN_PAR_SCAN_MIN");
+            return e ? (int64_t)atol(e) : (int64_t)1 << 20;
+        }();
+        if (T < 2 || max_records < 8192 || span < min_span || span < (int64_t)T * 64 || getenv("B200ALN_SERIAL_SCAN")) {
+            walk(begin_, end_, (size_t)max_records, out);
+        } else {
+            std::vector<std::vector<Extent>> piece(T);
+            const int64_t lo = begin_;
+            pool.run([&](unsigned t) {
+                const int64_t from = lo + span * (int64_t)t / (int64_t)T, to = lo + span * (int64_t)(t + 1) / (int64_t)T;
+                int64_t p = from;
+                if (t > 0) { /* the first position at or after `from` where two ordinary records follow a newline */
+                    const unsigned char *b = data_;
+                    p = -1;
+                    for (int64_t q = from; q < to;) {
+                        const unsigned char *nl = (const unsigned char *)memchr(b + q - 1, '\n', (size_t)(to - q + 1));
+                        if (!nl) break;
+                        const int64_t c = (int64_t)(nl - b) + 1;
+                        int g = -1;
+                        Extent x1, x2;
+                        if (c < to && walk_one(c, g, x1) && (x1.next >= end_ || walk_one(x1.next, g, x2))) { p = c; break; }
+                        q = c + 1;
+                    }
+                    if (p < 0) return;
+                }
+                piece[t].reserve((size_t)((to - from) / 64 + 16));
+                walk(p, to, (size_t)max_records, piece[t]);
+            });
+            int64_t expect = begin_;
+            for (unsigned t = 0; t < T; ++t) {
+                if (piece[t].empty() || piece[t][0].start != expect) break;
+                out.insert(out.end(), piece[t].begin(), piece[t].end());
+                expect = out.back().next;
             }
-            const int64_t q_plus = s0 + L + 1;
-            if (L <= 0 || q_plus >= e || b[q_plus] != '+') break;
-            int64_t q0;
-            if (q_plus + 1 < e && b[q_plus + 1] == '\n') q0 = q_plus + 2;
-            else {
-                const unsigned char *nl3 = (const unsigned char *)memchr(b + q_plus, '\n', (size_t)(e - q_plus));
-                if (!nl3) break;
-                q0 = (int64_t)(nl3 - b) + 1;
-            }
-            if (q0 + L >= e || b[q0 + L] != '\n') break; /* (a newline inside the quality string is refused by convert_extent) */
-            Extent x;
-            x.start = p; x.seq = s0; x.len = L; x.qual = q0; x.next = q0 + L + 1;
-            out.push_back(x);
-            p = x.next;
-            guess = L;
+            if ((int)out.size() > max_records) out.resize((size_t)max_records);
+            if (out.empty()) walk(begin_, end_, (size_t)max_records, out); /* (the first record is odd, or a tiny span) */
         }
+        if (out.size() >= 64) avg_record_bytes_ = (double)(out.back().next - begin_) / (double)out.size();
         return (int)out.size();
     }
     /* character checks of the fast path (see read_record_fast) + conversion; false = let the exact parser decide */
@@ -604,6 +662,7 @@ class SeqReader {
     size_t map_len_ = 0;
     const unsigned char *data_ = nullptr; /* buf_.data() or map_ */
     int64_t begin_ = 0, end_ = 0;
+    double avg_record_bytes_ = 300.0; /* of the records scanned last: sizes the parallel scan's byte range */
     bool is_eof_ = false;
     int last_char_ = 0;
     std::string name_, seq_, qual_;

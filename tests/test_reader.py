@@ -190,3 +190,18 @@ def test_bgzf_fastq_is_inflated_block_parallel(tmp_path, block):
         assert both(p) == 30002
     finally:
         del os.environ["B200ALN_NO_BGZF"]
+
+
+def test_parallel_scan_joins_only_matching_pieces(tmp_path):
+    """Large enough for the parallel structural scan (one slice of the byte range per worker): the trap records
+    of `guess_traps` every few hundred records — odd records end a worker's piece early, so the pieces after it
+    must be dropped and scanned again — plus a quality line that looks like a header at a likely slice border."""
+    unit = HOSTILE["guess_traps"]
+    evil = b"@e\n" + b"ACGT" * 25 + b"\n+\n" + b"@" + b"I" * 99 + b"\n"      # quality starts with '@'
+    data = b"".join(unit + evil * 3 for _ in range(60))
+    p = str(tmp_path / "par.fq")
+    with open(p, "wb") as f:
+        f.write(data)
+    assert len(data) > (4 << 20)
+    assert both(p) == 60 * 403
+    assert both(p, trim_qual=20) == 60 * 403

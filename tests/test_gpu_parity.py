@@ -169,7 +169,7 @@ def test_cli_merges_reference_batches_only_when_allowed(rand_index, tmp_path):
     """The CLI driver hands several 0x40000-read reference batches to the GPU as one launch, but only batches
     that agree on the batch-level max_gapo clamp (bwtaln.c:89-92).  Input: one whole batch of reads < 38 bp
     (with -o 3 the clamp bites), then 100 bp reads, then a short tail — against the unmodified reference
-    binary, with merging on (default), off, and with one batch in flight."""
+    binary, with the default (one reference batch per GPU and launch), four and up to 64 merged, one batch in flight."""
     if not pyoracle.have_ref():
         pytest.skip("oracle/_ref/ibwa not present")
     g, bwt, rbwt = rand_index
@@ -198,7 +198,7 @@ def test_cli_merges_reference_batches_only_when_allowed(rand_index, tmp_path):
     pyoracle.run_ref(["aln", "-t", str(os.cpu_count() or 4)] + args + [prefix, fq], stdout_path=ref_out)
     want = open(ref_out, "rb").read()
     exe = os.path.join(ROOT, "ibwa_b200", "b200aln")
-    for env in ({}, {"B200ALN_MERGE": "1"}, {"B200ALN_INFLIGHT": "1", "B200ALN_MERGE": "64"}):
+    for env in ({}, {"B200ALN_MERGE": "4"}, {"B200ALN_INFLIGHT": "1", "B200ALN_MERGE": "64"}):
         out = str(tmp_path / "gpu.sai")
         subprocess.check_call([exe, "aln"] + args + ["-f", out, prefix, fq], stderr=subprocess.DEVNULL,
                               env=dict(os.environ, **env))

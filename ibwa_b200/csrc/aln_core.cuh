@@ -1069,9 +1069,9 @@ struct SearchLane {
         }
     }
 
-    B2_HD void step(const SearchEnv &E)
+    B2_HD void step(const SearchEnv &E, int max_rounds = 1 << 30)
     {
-        const int mode = prepare(E);
+        const int mode = prepare(E, true, max_rounds);
         if (mode == NONE) return;
         uint32_t nk4[4], nl4[4], ns;
         children4(E.fm[1 - ca], cpath, ck, cl, nk4, nl4, ns);

@@ -21,6 +21,9 @@ extern "C" uint64_t *hh_dbg() { return b2::b2_dbg; }
 
 using namespace b2;
 
+static int g_rounds = 1 << 30; /* SearchLane::prepare's max_rounds (the fast kernel runs with 1) */
+extern "C" void hh_set_rounds(int r) { g_rounds = r > 0 ? r : 1 << 30; }
+
 static std::vector<OccBlk> convert(const b200aln_bwt_view_t *v)
 {
     RefBwt r;
@@ -76,7 +79,7 @@ static int64_t run(const SearchEnv &env, const std::vector<int> &md, int n_reads
         e1.Q = Q.data(); e1.W = W.data(); e1.strideQ = strideQ; e1.strideW = strideW;
         e1.recs = recs.data(); e1.rec_cap = rec_cap; e1.ent = ent.data(); e1.arena_cap = arena_cap;
         lane.begin(e1, make_heads<Heads>(hstore), gs, 0, 0, 0, len, md[len], n_amb);
-        while (!lane.finished) lane.step(e1);
+        while (!lane.finished) lane.step(e1, g_rounds);
         if (lane.status != LANE_OK && big_cap) {
             /* the product's large pass: widths rebuilt (the aborted pass shadowed them), free-list arena */
             ++n_status;
@@ -87,7 +90,7 @@ static int64_t run(const SearchEnv &env, const std::vector<int> &md, int n_reads
             SearchEnv e2 = e1;
             e2.recs = recs2.data(); e2.rec_cap = 1 << 16; e2.ent = ent2.data(); e2.arena_cap = big_cap;
             big.begin(e2, make_heads<HeadsWide32>(hstore), gs, 0, 0, 0, len, md[len], n_amb);
-            while (!big.finished) big.step(e2);
+            while (!big.finished) big.step(e2, g_rounds);
             if (big.status != LANE_OK) { n_aln[r] = -big.status; continue; }
             n_aln[r] = big.n_aln;
             all.insert(all.end(), recs2.begin(), recs2.begin() + big.n_aln);

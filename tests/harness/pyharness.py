@@ -52,9 +52,10 @@ def lib():
 
 
 def aln_batch(bwt, rbwt, lens, offs, codes, opt_c, arena_cap=1 << 16, rec_cap=256, reuse=False, big_cap=0, batch_max_len=0,
-              lut_k=0):
+              lut_k=0, rounds=0):
     L = lib()
     L.hh_set_lut_k(ctypes.c_int(lut_k))
+    L.hh_set_rounds(ctypes.c_int(rounds))   # 0 = unlimited; the fast kernel runs with 1
     lens = np.ascontiguousarray(lens, np.int32)
     offs = np.ascontiguousarray(offs, np.int64)
     codes = np.ascontiguousarray(codes, np.uint8)

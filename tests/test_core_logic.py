@@ -28,7 +28,7 @@ def harness_sai(bwt, rbwt, args, fq, **kw):
 def test_core_matches_reference(tag, golden_dir, g1_index):
     args, fq = CASES[tag]
     got, nov = harness_sai(g1_index[0], g1_index[1], args, os.path.join(golden_dir, fq + ".fq.gz"),
-                           arena_cap=32000, rec_cap=4096)
+                           arena_cap=32000, rec_cap=4096, rounds=1)      # one pruned pop per step, like the fast kernel
     want = open(os.path.join(golden_dir, f"g1_{tag}.sai"), "rb").read()
     assert nov == 0
     assert got == want
@@ -180,7 +180,8 @@ def test_random_option_sets_against_the_oracle(k, args, golden_dir, g1_index):
     batch = next(seqio.read_batches(os.path.join(golden_dir, fq), opt.mode, opt.trim_qual))
     lo = (k * 97) % max(1, len(batch.lens) - 160)
     reads = [batch.codes[o:o + l] for o, l in zip(batch.offs[lo:lo + 160], batch.lens[lo:lo + 160])]
-    _vs_oracle(g1_index[0], g1_index[1], reads, args, arena_cap=1 << 21, rec_cap=1 << 14, reuse=bool(k & 1), lut_k=k % 5)
+    _vs_oracle(g1_index[0], g1_index[1], reads, args, arena_cap=1 << 21, rec_cap=1 << 14, reuse=bool(k & 1), lut_k=k % 5,
+               rounds=(k // 2) % 3)     # 0 = unlimited, 1 = the fast kernel's setting, 2
     if k % 3 == 0:
         from oracle import pyoracle
         lens = np.array([len(r) for r in reads], np.int32)

@@ -3,7 +3,7 @@
 buffers, on the bench genome (default 3.1 Gbp), rows taken from the engine's own best hits of synthetic reads
 plus uniformly random rows.  Prints one JSON line.
 
-  python scripts/bench_sa.py [--genome-bp N] [--rows N] [--steps K]
+  python tests/tools/bench_sa.py [--genome-bp N] [--rows N] [--steps K]
 
 Work per row: bwt_sa walks inverse-Psi steps until a sampled row (sa_intv = 32: 15.5 steps on average), each step
 one 32-byte sector of the occ layout -> algorithmic bytes = 32 x steps.  CPU beside it: oracle port, one core."""
@@ -15,7 +15,7 @@ import time
 
 import numpy as np
 
-ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 sys.path.insert(0, ROOT)
 
 

@@ -2,13 +2,13 @@
 """Process-seam end-to-end check on the GPU box: `b200aln aln` vs `ibwa aln -t <cores>` on the same FASTQ
 and the cached 3.1 Gbp bench index (run bench.py once before).  Wall clock includes index load, parsing,
 the search and writing the .sai; the outputs must be byte-identical except header bytes 52..55.
-usage: python scripts/cli_e2e.py [n_reads] [ref_reads]"""
+usage: python tests/tools/cli_e2e.py [n_reads] [ref_reads]"""
 import os
 import subprocess
 import sys
 import time
 
-ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 sys.path.insert(0, ROOT)
 import bench  # noqa: E402
 

@@ -1,7 +1,7 @@
 #!/usr/bin/env python
 """Config-3 spot check on the GPU box: 150 bp stress reads (2 % substitutions + indels) with
 `-n 4 -o 2 -e 10 -l 32 -k 2` against the cached 3.1 Gbp bench index; engine vs the reference binary.
-usage: python scripts/stress_check.py [n_reads]   (run bench.py once before: it builds the index cache)"""
+usage: python tests/tools/stress_check.py [n_reads]   (run bench.py once before: it builds the index cache)"""
 import os
 import subprocess
 import sys
@@ -9,7 +9,7 @@ import time
 
 import numpy as np
 
-ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 sys.path.insert(0, ROOT)
 import bench  # noqa: E402
 from ibwa_b200 import engine, parse_aln_args, sai, synth  # noqa: E402

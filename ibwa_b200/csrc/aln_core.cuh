@@ -149,6 +149,10 @@ B2_D U8x ld_lut8(const void *p, bool keep = false)
 #endif
     return r;
 }
+B2_D void ld_lut_pair(const uint32_t *p, uint32_t &k, uint32_t &l)
+{ /* one (k, l) pair of the interval table */
+    asm volatile("ld.global.nc.L1::no_allocate.v2.u32 {%0,%1}, [%2];" : "=r"(k), "=r"(l) : "l"(p));
+}
 B2_D void st8(uint32_t *p, const uint32_t v[8])
 { /* eight consecutive words as one full 32-byte sector (p is 32-byte aligned) */
     asm volatile("st.global.cg.v8.u32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};"
@@ -187,6 +191,7 @@ inline void ld8cg(const uint32_t *p, uint32_t v[8]) { for (int i = 0; i < 8; ++i
 inline void st8rec(uint32_t *p, const uint32_t v[8]) { for (int i = 0; i < 8; ++i) p[i] = v[i]; }
 struct alignas(32) U8x { uint32_t v[8]; };
 inline U8x ld_lut8(const void *p, bool = false) { return *reinterpret_cast<const U8x *>(p); }
+inline void ld_lut_pair(const uint32_t *p, uint32_t &k, uint32_t &l) { k = p[0]; l = p[1]; }
 inline int popc32(uint32_t v) { return __builtin_popcount(v); }
 inline int ctz32(uint32_t v) { return __builtin_ctz(v); }
 #endif
@@ -471,7 +476,7 @@ B2_HD int round_up8(int v) { return (v + 7) & ~7; }
  * Returns the number of ambiguous symbols in the strand.
  */
 B2_HD int width_pass(const FmView &f, const uint8_t *fwd, int len, int a, bool comp, int seed_len, uint32_t *W,
-                     QRec *Q)
+                     QRec *Q, int *last_bid = nullptr)
 {
     const bool use_seed = len > seed_len;
     const int shift = len - seed_len; /* ii = j - shift */
@@ -521,7 +526,26 @@ B2_HD int width_pass(const FmView &f, const uint8_t *fwd, int len, int a, bool c
         if (j0 < len) st8(Q + j0, qb);
         st8(W + j0, wb); /* includes the W[len] = 0 sentinel */
     }
+    if (last_bid) *last_bid = m.bid; /* D(len - 1): the lower bound on the differences of the whole strand */
     return n_amb;
+}
+
+/*
+ * Work class of a read from its two strands' lower bounds D = width[len-1].bid (bwtaln.c:54-78) and its
+ * max_diff: how far the search has to go correlates with min(D0, D1) — reads with an exact occurrence
+ * (D = 0) all take the same short course, reads with D > max_diff are pruned at the root (bwtgap.c:155),
+ * D == max_diff leaves no freedom, and in between the work grows with D.  Classes are processed from the
+ * highest to the lowest: long searches start first, and the lanes of a warp work on reads of one class
+ * (the north star's "bucketed by mismatch budget").  Only the ORDER of processing depends on it.
+ */
+#define B2_N_CLASSES 16
+B2_HD int work_class(int d0, int d1, int max_diff)
+{
+    const int d = d0 < d1 ? d0 : d1;
+    if (d > max_diff) return 0;
+    if (d == 0) return 1;
+    if (d == max_diff) return 2;
+    return d + 2 > B2_N_CLASSES - 1 ? B2_N_CLASSES - 1 : d + 2;
 }
 
 /* gap_shadow (bwtgap.c:81-91) on the split representation (bid lives in Q, w in W), fused with the
@@ -930,9 +954,38 @@ struct SearchLane {
      * the kernel can re-converge the warp between them (all lanes issue their lookup loads
      * together); step() chains them for callers that do not care (CPU logic tests).
      */
-    enum { NONE = -1, EXPAND = 0, EXTEND = 1 };
-    QRec pq; /* width record of the position being worked on (prepare -> apply) */
-    int pm;  /* differences still allowed for the current entry */
+    enum { NONE = -1, EXPAND = 0, EXTEND = 1, JUMP = 2 };
+    QRec pq; /* width record of the position being worked on (prepare -> apply); JUMP: the target node's k-mer */
+    int pm;  /* differences still allowed for the current entry; JUMP: the number of symbols it consumes */
+
+    /*
+     * bwt_match_exact_alt (bwt.c:235-250) only reports the final interval, or failure at the first ambiguous
+     * symbol / empty interval.  While the chain is inside the interval table, the node reached after the next
+     * n symbols is ONE table entry away (descendants of an empty node are stored empty), so n steps of the
+     * chain cost one request and one warp iteration instead of n.  Sets up the jump (pq = k-mer of the target
+     * node, pm = n) and returns JUMP; returns EXTEND when the chain is outside the table or only one level
+     * is left (the ordinary step reads the children's sector then); returns NONE after ending a chain that
+     * runs into an ambiguous symbol (bwt.c:241: the reference returns 0 there, whatever came before).
+     */
+    B2_HD int extend_mode(const SearchEnv &E)
+    {
+        const int K = E.fm[0].lut_k;
+        const uint32_t d = cpath & 31u;
+        int n = K - (int)d; /* B2_PATH_DEAD = 31 >= any K: n <= 0 */
+        if (n > ci) n = ci;
+        if (n < 2) { pq = ld_q(qrow(E, ca) + (ci - 1)); return EXTEND; }
+        const QRec *q = qrow(E, ca) + ci;
+        uint32_t X = cpath >> 5, amb = 0;
+        for (int j = 1; j <= n; ++j) {
+            const uint32_t b = (uint32_t)q_base(ld_q(q - j));
+            amb |= b >> 2;
+            X = X << 2 | (b & 3u);
+        }
+        if (amb) { extending = false; return NONE; }
+        pq = X;
+        pm = n;
+        return JUMP;
+    }
 
     /* true when the next entry does not have to come from memory */
     B2_HD bool ready() const { return have_cur || extending || og != 0; }
@@ -950,7 +1003,11 @@ struct SearchLane {
         const bool gape_mode = P->mode & MODE_GAPE, nonstop = P->mode & MODE_NONSTOP;
         int round = 0;
         for (;;) {
-            if (extending) { pq = ld_q(qrow(E, ca) + (ci - 1)); return EXTEND; }
+            if (extending) {
+                const int em = extend_mode(E);
+                if (em != NONE) return em;
+                continue; /* the chain met an ambiguous symbol */
+            }
             if (n_entries == 0) { finished = true; return NONE; }
             if (n_entries > P->max_entries) { finished = true; return NONE; } /* bwtgap.c:139 */
             if (!have_cur) {
@@ -979,9 +1036,28 @@ struct SearchLane {
                 if (!on_hit(E)) { finished = true; return NONE; }
                 continue;
             }
-            if (pm == 0 && (cstate == ST_M || gape_mode || cge == P->max_gape)) { B2_DBG(10); extending = true; return EXTEND; }
+            if (pm == 0 && (cstate == ST_M || gape_mode || cge == P->max_gape)) {
+                B2_DBG(10);
+                extending = true;
+                const int em = extend_mode(E);
+                if (em != NONE) return em;
+                continue;
+            }
             return EXPAND;
         }
+    }
+
+    /* the memory access of a step: the children of the current entry, or the table entry a JUMP lands on
+     * (returned in nk4[0], nl4[0]) */
+    B2_HD void lookup(const SearchEnv &E, int mode, uint32_t nk4[4], uint32_t nl4[4], uint32_t &ns) const
+    {
+        const FmView &f = E.fm[1 - ca];
+        if (mode == JUMP) {
+            ld_lut_pair(f.lut + 2 * lut_pair(f.lut_w, (int)(cpath & 31u) + pm, (uint64_t)pq), nk4[0], nl4[0]);
+            ns = 1;
+            return;
+        }
+        children4(f, cpath, ck, cl, nk4, nl4, ns);
     }
 
     /* consume the children intervals (children4) of the current entry [ck, cl] on fm[1 - ca] */
@@ -990,14 +1066,29 @@ struct SearchLane {
         const Params *P = &E.P;
         const int K = E.fm[0].lut_k; /* same for both indexes */
         const bool gape_mode = P->mode & MODE_GAPE;
+        if (STATS) n_lookups += ns;
+        if (mode == JUMP) { /* pm steps of bwt_match_exact_alt at once */
+            B2_DBG(7);
+            if (nk4[0] > nl4[0]) { extending = false; return; }
+            const uint32_t d = (cpath & 31u) + (uint32_t)pm;
+            ck = nk4[0];
+            cl = nl4[0];
+            cpath = (int)d >= K ? B2_PATH_DEAD : (d | pq << 5);
+            ci -= pm;
+            if (ci == 0) {
+                extending = false;
+                if (!on_hit(E)) finished = true;
+            }
+            return;
+        }
         const QRec q = pq;
         const int m = pm;
-        if (STATS) n_lookups += ns;
 
         const int i = ci - 1;
         const int base = q_base(q);
         if (mode == EXTEND) { /* one step of bwt_match_exact_alt (bwt.c:235-250) */
             B2_DBG(5);
+            if ((cpath & 31u) != B2_PATH_DEAD) B2_DBG(11);
             if (base > 3) { extending = false; return; }
             ck = pick4(nk4, base);
             cl = pick4(nl4, base);
@@ -1012,6 +1103,7 @@ struct SearchLane {
         }
 
         B2_DBG(6);
+        if ((cpath & 31u) != B2_PATH_DEAD) B2_DBG(13);
         const uint32_t occ = cl - ck + 1u;
         bool allow_diff = true, allow_M = true;
         if (i > 0) { /* bwtgap.c:205-214, written without short-circuits to keep the lanes together */
@@ -1074,7 +1166,7 @@ struct SearchLane {
         const int mode = prepare(E, true, max_rounds);
         if (mode == NONE) return;
         uint32_t nk4[4], nl4[4], ns;
-        children4(E.fm[1 - ca], cpath, ck, cl, nk4, nl4, ns);
+        lookup(E, mode, nk4, nl4, ns);
         apply(E, mode, nk4, nl4, ns);
     }
 };

@@ -89,6 +89,7 @@ struct WidthArgs {
     QRec *Q;
     uint32_t *W;
     int32_t *n_amb;
+    uint8_t *dkey; /* [2 * read + strand]: the strand's lower bound on differences, saturated (null: not wanted) */
 };
 
 __global__ void __launch_bounds__(128) k_width(const __grid_constant__ WidthArgs A)
@@ -98,9 +99,60 @@ __global__ void __launch_bounds__(128) k_width(const __grid_constant__ WidthArgs
         const int wi = (int)(t >> 1), a = (int)(t & 1);
         const int r = A.work_list ? A.work_list[wi] : wi;
         const size_t slot = (size_t)2 * r + a;
+        int bid = 0;
         int n = width_pass(A.fm[a], A.codes + A.offs[r], A.lens[r], a, A.comp != 0, A.seed_len,
-                           A.W + slot * A.strideW, A.Q + slot * A.strideQ);
+                           A.W + slot * A.strideW, A.Q + slot * A.strideQ, &bid);
         if (a == 0) A.n_amb[r] = n;
+        if (A.dkey) A.dkey[slot] = (uint8_t)(bid > 255 ? 255 : bid);
+    }
+}
+
+/* Work order of the fast pass: a counting sort of the reads by work class (aln_core.cuh: work_class), highest
+ * class first.  k_class_count: histogram; k_class_scatter: every block reserves its share of each class's
+ * range and places its reads there (the order inside a class is whatever the atomics give: results do not
+ * depend on the order reads are searched in). */
+struct OrderArgs {
+    int n_reads;
+    const int32_t *lens;
+    const int32_t *md;
+    const uint8_t *dkey;
+    unsigned int *cnt;  /* [B2_N_CLASSES] reads per class */
+    unsigned int *fill; /* [B2_N_CLASSES] slots handed out so far */
+    int32_t *order;
+};
+__device__ __forceinline__ int class_of_read(const OrderArgs &A, int r)
+{
+    return work_class(A.dkey[2 * (size_t)r], A.dkey[2 * (size_t)r + 1], A.md[A.lens[r]]);
+}
+__global__ void __launch_bounds__(256) k_class_count(const __grid_constant__ OrderArgs A)
+{
+    __shared__ unsigned int h[B2_N_CLASSES];
+    if (threadIdx.x < B2_N_CLASSES) h[threadIdx.x] = 0;
+    __syncthreads();
+    for (int r = blockIdx.x * blockDim.x + threadIdx.x; r < A.n_reads; r += gridDim.x * blockDim.x)
+        atomicAdd(&h[class_of_read(A, r)], 1u);
+    __syncthreads();
+    if (threadIdx.x < B2_N_CLASSES && h[threadIdx.x]) atomicAdd(&A.cnt[threadIdx.x], h[threadIdx.x]);
+}
+__global__ void __launch_bounds__(256) k_class_scatter(const __grid_constant__ OrderArgs A)
+{
+    __shared__ unsigned int h[B2_N_CLASSES], base[B2_N_CLASSES];
+    const int per = (A.n_reads + gridDim.x - 1) / gridDim.x; /* a contiguous slice per block */
+    const int lo = blockIdx.x * per, hi = lo + per < A.n_reads ? lo + per : A.n_reads;
+    if (threadIdx.x < B2_N_CLASSES) h[threadIdx.x] = 0;
+    __syncthreads();
+    for (int r = lo + threadIdx.x; r < hi; r += blockDim.x) atomicAdd(&h[class_of_read(A, r)], 1u);
+    __syncthreads();
+    if (threadIdx.x < B2_N_CLASSES) {
+        unsigned int start = 0; /* classes above this one come first */
+        for (int c = B2_N_CLASSES - 1; c > (int)threadIdx.x; --c) start += A.cnt[c];
+        base[threadIdx.x] = start + (h[threadIdx.x] ? atomicAdd(&A.fill[threadIdx.x], h[threadIdx.x]) : 0u);
+        h[threadIdx.x] = 0;
+    }
+    __syncthreads();
+    for (int r = lo + threadIdx.x; r < hi; r += blockDim.x) {
+        const int c = class_of_read(A, r);
+        A.order[base[c] + atomicAdd(&h[c], 1u)] = r;
     }
 }
 
@@ -231,7 +283,7 @@ __global__ void __launch_bounds__(128, MINB) k_search(const __grid_constant__ Se
         if (running && (ready || allow_pop)) mode = L.prepare(A.env, allow_pop, A.prep_rounds);
         __syncwarp();
         uint32_t nk4[4], nl4[4], ns = 0;
-        if (mode != L.NONE) children4(A.env.fm[1 - L.ca], L.cpath, L.ck, L.cl, nk4, nl4, ns);
+        if (mode != L.NONE) L.lookup(A.env, mode, nk4, nl4, ns);
         __syncwarp();
         if (mode != L.NONE) L.apply(A.env, mode, nk4, nl4, ns);
         __syncwarp();
@@ -463,6 +515,7 @@ struct b200aln_ctx {
     uint32_t arena_cap_mid = 12288; /* middle pass: 16-bit heads in shared memory, free-list arena */
     int rec_cap_mid = 512, mid_lanes = 148 * 192; /* x 12288 records x 64 B = 22 GB, allocated when a batch first needs it */
     int prefetch_fast = 0, prefetch_mid = 1; /* L2 prefetch of the next pop candidate, per pass */
+    int order = 1;         /* fast pass takes the reads by work class, longest searches first (0: arrival order) */
     int prep_rounds = 1;   /* pruned pops a lane may go through per warp iteration before the warp moves on */
     int reserve_reads = 0; /* size the per-batch buffers for at least this many reads */
     int count = 0;         /* 1: fast pass with the pop / sector counters (b200aln_stats_t pops, occ_lookups) */
@@ -477,7 +530,7 @@ struct b200aln_ctx {
     int batch_max_len = 0; /* > 0: the reference batch this call is a shard of has this longest read */
     /* device buffers */
     DevBuf lens, offs, codes, md, Q, W, n_amb, ent, recs, n_aln, over_slot, over_list, misc, off64,
-        blk_tot, packed, ent_big, recs_big, heads_wide, heads_wide_big, ent_mid, recs_mid, over_list2, sa_in, sa_out, grp_in, grp_out;
+        blk_tot, packed, dkey, order_buf, ent_big, recs_big, heads_wide, heads_wide_big, ent_mid, recs_mid, over_list2, sa_in, sa_out, grp_in, grp_out;
     HostBuf h_in, h_out, h_misc;
     b200aln_stats_t stats;
 };
@@ -666,7 +719,7 @@ extern "C" b200aln_ctx *b200aln_clone(b200aln_ctx *p)
     c->rec_cap = p->rec_cap; c->rec_cap_big = p->rec_cap_big; c->big_lanes = p->big_lanes;
     c->arena_cap_mid = p->arena_cap_mid; c->rec_cap_mid = p->rec_cap_mid; c->mid_lanes = p->mid_lanes;
     c->pop_batch = p->pop_batch; c->count = p->count; c->reserve_reads = p->reserve_reads; c->prep_rounds = p->prep_rounds;
-    c->prefetch_fast = p->prefetch_fast; c->prefetch_mid = p->prefetch_mid;
+    c->prefetch_fast = p->prefetch_fast; c->prefetch_mid = p->prefetch_mid; c->order = p->order;
     CK(cudaStreamCreateWithFlags(&c->st, cudaStreamNonBlocking));
     for (int i = 0; i < 8; ++i) CK(cudaEventCreate(&c->ev[i]));
     for (int i = 0; i < 2; ++i) CK(cudaEventCreate(&c->tm[i]));
@@ -715,7 +768,7 @@ extern "C" void b200aln_close(b200aln_ctx *c)
     cudaStreamSynchronize(c->st);
     DevBuf *bufs[] = {&c->lens, &c->offs, &c->codes, &c->md, &c->Q, &c->W, &c->n_amb, &c->ent,
                       &c->recs, &c->n_aln, &c->over_slot, &c->over_list, &c->misc, &c->off64, &c->blk_tot,
-                      &c->packed, &c->ent_big, &c->recs_big, &c->heads_wide, &c->heads_wide_big, &c->ent_mid, &c->recs_mid,
+                      &c->packed, &c->dkey, &c->order_buf, &c->ent_big, &c->recs_big, &c->heads_wide, &c->heads_wide_big, &c->ent_mid, &c->recs_mid,
                       &c->over_list2, &c->sa_in, &c->sa_out};
     for (DevBuf *b : bufs) b->release();
     c->grp_in.release(); c->grp_out.release();
@@ -744,6 +797,7 @@ extern "C" void b200aln_set_int(b200aln_ctx *c, const char *key, int64_t v)
     else if (!strcmp(key, "count")) c->count = (int)v;
     else if (!strcmp(key, "reserve_reads")) c->reserve_reads = (int)v;
     else if (!strcmp(key, "prep_rounds")) c->prep_rounds = (int)v;
+    else if (!strcmp(key, "order")) c->order = (int)v;
     else if (!strcmp(key, "prefetch_fast")) c->prefetch_fast = (int)v;
     else if (!strcmp(key, "prefetch_mid")) c->prefetch_mid = (int)v;
     else if (!strcmp(key, "arena_cap_mid")) c->arena_cap_mid = (uint32_t)v;
@@ -781,6 +835,7 @@ struct Misc {
     unsigned int counter, n_over, counter_big, counter_mid, n_over2, pad[3];
     unsigned long long stat[2];
     long long total;
+    unsigned int class_cnt[B2_N_CLASSES], class_fill[B2_N_CLASSES];
 };
 
 /* fast pass: 16-bit heads in shared memory when the score range and the arena allow it */
@@ -845,6 +900,11 @@ static void run_batch_device(b200aln_ctx *c, int n_reads, int max_len, const int
     c->Q.need(n_alloc * 2 * strideQ * sizeof(QRec) + 64);
     c->W.need(n_alloc * 2 * strideW * 4 + 64);
     c->n_amb.need(n_alloc * 4);
+    const bool ordered = c->order != 0 && n_reads > 1;
+    if (ordered) {
+        c->dkey.need(n_alloc * 2);
+        c->order_buf.need(n_alloc * 4);
+    }
     c->ent.need(lanes * c->arena_cap * sizeof(StackRec));
     c->recs.need(n_alloc * c->rec_cap * 16);
     c->n_aln.need(n_alloc * 4);
@@ -869,15 +929,26 @@ static void run_batch_device(b200aln_ctx *c, int n_reads, int max_len, const int
     WA.strideQ = strideQ; WA.strideW = strideW;
     WA.Q = c->Q.as<QRec>(); WA.W = c->W.as<uint32_t>();
     WA.n_amb = c->n_amb.as<int32_t>();
+    WA.dkey = ordered ? c->dkey.as<uint8_t>() : nullptr;
     k_width<<<wblocks, 128, 0, c->st>>>(WA);
     CK(cudaGetLastError());
     ++launches;
+    if (ordered) { /* part of the width stage's time */
+        OrderArgs OA;
+        OA.n_reads = n_reads; OA.lens = d_lens; OA.md = c->md.as<int32_t>(); OA.dkey = c->dkey.as<uint8_t>();
+        OA.cnt = dm->class_cnt; OA.fill = dm->class_fill; OA.order = c->order_buf.as<int32_t>();
+        const int oblocks = (n_reads + 2047) / 2048 < c->n_sm * 8 ? (n_reads + 2047) / 2048 : c->n_sm * 8;
+        k_class_count<<<oblocks, 256, 0, c->st>>>(OA);
+        k_class_scatter<<<oblocks, 256, 0, c->st>>>(OA);
+        CK(cudaGetLastError());
+        launches += 2;
+    }
     CK(cudaEventRecord(c->ev[2], c->st));
 
     SearchArgs SA;
     SA.env.fm[0] = c->fm[0]; SA.env.fm[1] = c->fm[1]; SA.env.P = P;
     SA.env.prefetch_next = c->prefetch_fast;
-    SA.n_work = n_reads; SA.work_list = nullptr;
+    SA.n_work = n_reads; SA.work_list = ordered ? c->order_buf.as<int32_t>() : nullptr;
     SA.lens = d_lens; SA.n_amb = c->n_amb.as<int32_t>(); SA.md = c->md.as<int32_t>();
     SA.env.Q = WA.Q; SA.env.W = WA.W; SA.env.strideQ = strideQ; SA.env.strideW = strideW;
     SA.env.ent = c->ent.as<StackRec>(); SA.env.arena_cap = c->arena_cap;
@@ -920,6 +991,7 @@ static void run_batch_device(b200aln_ctx *c, int n_reads, int max_len, const int
         c->recs_mid.need((size_t)n_over * c->rec_cap_mid * 16);
         c->over_list2.need((size_t)n_over * 4);
         WidthArgs WM = WA;
+        WM.dkey = nullptr;
         WM.n_reads = (int)n_over; WM.work_list = c->over_list.as<int32_t>();
         k_width<<<wblocks, 128, 0, c->st>>>(WM);
         CK(cudaGetLastError());
@@ -948,6 +1020,7 @@ static void run_batch_device(b200aln_ctx *c, int n_reads, int max_len, const int
         c->ent_big.need((size_t)bblocks * 128 * cap_big * sizeof(StackRec));
         c->recs_big.need((size_t)n_wide * c->rec_cap_big * 16);
         WidthArgs WB = WA;
+        WB.dkey = nullptr;
         WB.n_reads = (int)n_wide; WB.work_list = wide_list;
         k_width<<<wblocks, 128, 0, c->st>>>(WB);
         CK(cudaGetLastError());

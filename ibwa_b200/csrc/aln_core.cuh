@@ -473,10 +473,13 @@ B2_HD int round_up8(int v) { return (v + 7) & ~7; }
  * as the tail of the main chain, so both advance in the same iteration: no scratch, and
  * their lookups overlap.  Rows are written eight words (one sector) at a time; W and Q rows
  * must be 32-byte aligned with a stride that is a multiple of 8.
- * Returns the number of ambiguous symbols in the strand.
  */
-B2_HD int width_pass(const FmView &f, const uint8_t *fwd, int len, int a, bool comp, int seed_len, uint32_t *W,
-                     QRec *Q, int *last_bid = nullptr)
+struct WidthOut {
+    int n_amb; /* ambiguous symbols in the strand */
+    int bid;   /* D(len - 1): the lower bound on the differences of the whole strand */
+};
+B2_HD WidthOut width_pass(const FmView &f, const uint8_t *fwd, int len, int a, bool comp, int seed_len, uint32_t *W,
+                          QRec *Q)
 {
     const bool use_seed = len > seed_len;
     const int shift = len - seed_len; /* ii = j - shift */
@@ -526,8 +529,10 @@ B2_HD int width_pass(const FmView &f, const uint8_t *fwd, int len, int a, bool c
         if (j0 < len) st8(Q + j0, qb);
         st8(W + j0, wb); /* includes the W[len] = 0 sentinel */
     }
-    if (last_bid) *last_bid = m.bid; /* D(len - 1): the lower bound on the differences of the whole strand */
-    return n_amb;
+    WidthOut o;
+    o.n_amb = n_amb;
+    o.bid = m.bid;
+    return o;
 }
 
 /*
@@ -723,6 +728,8 @@ struct SearchLane {
     B2_HD const QRec *qrow(const SearchEnv &E, int a) const { return E.Q + (size_t)(row + (uint32_t)a) * E.strideQ; }
     B2_HD StackRec *arena(const SearchEnv &E) const { return E.ent + (size_t)lane_no * E.arena_cap; }
     B2_HD Rec *records(const SearchEnv &E) const { return E.recs + (size_t)slab * E.rec_cap; }
+    /* the width record of position p (0 <= p < len) of strand a */
+    B2_HD QRec fetch_q(const SearchEnv &E, int a, int p) const { return ld_q(qrow(E, a) + p); }
 
     /* heads_clean: the caller has already emptied the bucket heads (the kernel does it with the whole warp) */
     B2_HD void begin(const SearchEnv &E, Heads heads_, GroupStore gs_, uint32_t lane_no_, uint32_t read, uint32_t slab_,
@@ -867,17 +874,16 @@ struct SearchLane {
             og = 0;
             ck = 0; cl = E.fm[0].seq_len; ci = len; cldp = 0; cmm = cgo = cge = 0; cstate = ST_M; ca = 0; cscore = 0;
             cpath = path_root();
-            if (len > 0) pq = ld_q(qrow(E, 0) + len - 1);
+            if (len > 0) pq = fetch_q(E, 0, len - 1);
             --n_entries;
             if (STATS) ++n_pops;
             return true;
         }
-        const QRec *q = qrow(E, ca);
         const uint32_t run = mask & 15u; /* members that are child intervals: mismatches, or deletions */
         const int m = max_diff - cmm - cgo - ((P->mode & MODE_GAPE) ? cge : 0);
         if (run) {
             const int pos = kind == GRP_X ? i : i + 1; /* their position; pos > 0 for deletions */
-            if (pos > 0) pq = ld_q(q + pos - 1);
+            if (pos > 0) pq = fetch_q(E, ca, pos - 1);
             const bool stop = !(P->mode & MODE_NONSTOP) && cscore > best_score + P->s_mm; /* bwtgap.c:143: the first one ends the search */
             if (!stop && (m < 0 || (pos > 0 && m < q_bid(pq)))) {
                 const int n = popc32(run);
@@ -912,7 +918,7 @@ struct SearchLane {
             ck = gs.get(OG_PK); cl = gs.get(OG_PL);
             cpath = gs.get(OG_PATH);
             ci = i; cldp = i; cstate = ST_I;
-            if (i > 0) pq = ld_q(q + i - 1);
+            if (i > 0) pq = fetch_q(E, ca, i - 1);
         }
         --n_entries;
         if (STATS) ++n_pops;
@@ -973,11 +979,10 @@ struct SearchLane {
         const uint32_t d = cpath & 31u;
         int n = K - (int)d; /* B2_PATH_DEAD = 31 >= any K: n <= 0 */
         if (n > ci) n = ci;
-        if (n < 2) { pq = ld_q(qrow(E, ca) + (ci - 1)); return EXTEND; }
-        const QRec *q = qrow(E, ca) + ci;
+        if (n < 2) { pq = fetch_q(E, ca, ci - 1); return EXTEND; }
         uint32_t X = cpath >> 5, amb = 0;
         for (int j = 1; j <= n; ++j) {
-            const uint32_t b = (uint32_t)q_base(ld_q(q - j));
+            const uint32_t b = (uint32_t)q_base(fetch_q(E, ca, ci - j));
             amb |= b >> 2;
             X = X << 2 | (b & 3u);
         }
@@ -1023,7 +1028,7 @@ struct SearchLane {
                 --n_entries;
                 if (STATS) ++n_pops;
                 have_cur = false;
-                if (ci > 0) pq = ld_q(qrow(E, ca) + (ci - 1));
+                if (ci > 0) pq = fetch_q(E, ca, ci - 1);
             }
             if (!nonstop && cscore > best_score + P->s_mm) { finished = true; return NONE; }
             pm = max_diff - cmm - cgo - (gape_mode ? cge : 0);

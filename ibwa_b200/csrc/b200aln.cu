@@ -22,7 +22,13 @@
 #include <string.h>
 #include <time.h>
 
+#include <atomic>
+#include <chrono>
+#include <condition_variable>
+#include <mutex>
+#include <shared_mutex>
 #include <string>
+#include <thread>
 #include <vector>
 
 #include "../../include/b200aln.h"
@@ -90,20 +96,20 @@ struct WidthArgs {
     uint32_t *W;
     int32_t *n_amb;
     uint8_t *dkey; /* [2 * read + strand]: the strand's lower bound on differences, saturated (null: not wanted) */
+    int rows_by_work; /* rows of Q / W are numbered by work item (the re-run passes) instead of by read */
 };
 
-__global__ void __launch_bounds__(128) k_width(const __grid_constant__ WidthArgs A)
+__global__ void __launch_bounds__(128, 5) k_width(const __grid_constant__ WidthArgs A)
 {
     const int nthreads = gridDim.x * blockDim.x, tid = blockIdx.x * blockDim.x + threadIdx.x;
     for (int64_t t = tid; t < 2 * (int64_t)A.n_reads; t += nthreads) {
         const int wi = (int)(t >> 1), a = (int)(t & 1);
         const int r = A.work_list ? A.work_list[wi] : wi;
-        const size_t slot = (size_t)2 * r + a;
-        int bid = 0;
-        int n = width_pass(A.fm[a], A.codes + A.offs[r], A.lens[r], a, A.comp != 0, A.seed_len,
-                           A.W + slot * A.strideW, A.Q + slot * A.strideQ, &bid);
-        if (a == 0) A.n_amb[r] = n;
-        if (A.dkey) A.dkey[slot] = (uint8_t)(bid > 255 ? 255 : bid);
+        const size_t slot = (size_t)2 * (A.rows_by_work ? wi : r) + a;
+        const WidthOut o = width_pass(A.fm[a], A.codes + A.offs[r], A.lens[r], a, A.comp != 0, A.seed_len,
+                                      A.W + slot * A.strideW, A.Q + slot * A.strideQ);
+        if (a == 0) A.n_amb[r] = o.n_amb;
+        if (A.dkey) A.dkey[(size_t)2 * r + a] = (uint8_t)(o.bid > 255 ? 255 : o.bid);
     }
 }
 
@@ -166,6 +172,7 @@ struct SearchArgs {
     const int32_t *n_amb;
     const int32_t *md; /* max_diff by read length */
     int recs_by_work; /* slab index: work item (large pass) or read (fast pass) */
+    int rows_by_work; /* rows of Q / W: by work item (the re-run passes) or by read */
     int32_t *n_aln;
     int32_t *over_slot; /* re-run passes: over_slot[r] = work item | slot_tag */
     int32_t slot_tag;   /* 0 = middle pass, WIDE_TAG = wide pass */
@@ -175,6 +182,8 @@ struct SearchArgs {
     unsigned long long *stat; /* [0] pops, [1] sectors */
     uint32_t *heads_wide;     /* HeadsWide32 only: per lane n_buckets heads + mask words */
     int heads_wide_stride;
+    int arena_by_work;        /* arenas are indexed by work item (passes with fewer work items than lanes) instead of by lane */
+    unsigned int *n_rec_full; /* counts the reads that ran out of record slab (null: not wanted) */
     int pop_batch; /* lanes of a warp that must wait for a memory pop before the warp takes them */
     int prep_rounds; /* pops / prunes a lane may go through per warp iteration before the warp moves on */
 };
@@ -265,8 +274,8 @@ __global__ void __launch_bounds__(128, MINB) k_search(const __grid_constant__ Se
                 if (w < (unsigned)A.n_work) {
                     r = A.work_list ? A.work_list[w] : (int)w;
                     const int len = A.lens[r];
-                    L.begin(A.env, heads, gs, (uint32_t)gl, (uint32_t)r, A.recs_by_work ? w : (uint32_t)r, len, A.md[len],
-                            A.n_amb[r], HeadsClear<Heads>::cooperative);
+                    L.begin(A.env, heads, gs, A.arena_by_work ? w : (uint32_t)gl, A.rows_by_work ? w : (uint32_t)r, A.recs_by_work ? w : (uint32_t)r,
+                            len, A.md[len], A.n_amb[r], HeadsClear<Heads>::cooperative);
                     active = true;
                 } else alive = false;
             }
@@ -294,11 +303,12 @@ __global__ void __launch_bounds__(128, MINB) k_search(const __grid_constant__ Se
                     sectors += L.n_lookups;
                 }
                 if (L.status != LANE_OK) {
-                    A.n_aln[r] = 0;
+                    A.n_aln[r] = -L.status; /* counts as no records until a later pass succeeds; the host dies on what is left */
                     if (A.over_list) {
                         unsigned idx = atomicAdd(A.n_over, 1u);
                         A.over_list[idx] = r;
-                    } else A.n_aln[r] = -L.status; /* the large pass overflowed too: reported by the host */
+                    }
+                    if (A.n_rec_full && L.status == LANE_REC_FULL) atomicAdd(A.n_rec_full, 1u);
                 } else {
                     A.n_aln[r] = L.n_aln;
                     if (A.over_slot) A.over_slot[r] = (int32_t)w | A.slot_tag;
@@ -315,14 +325,17 @@ __global__ void __launch_bounds__(128, MINB) k_search(const __grid_constant__ Se
 
 /* exclusive prefix sum of n_aln (int32) into int64 offsets: block totals, their scan, then local scans */
 #define SCAN_ITEMS 2048
-__global__ void __launch_bounds__(256) k_scan_totals(const int32_t *in, int n, int64_t *block_tot)
-{
+__global__ void __launch_bounds__(256) k_scan_totals(const int32_t *in, int n, int64_t *block_tot, unsigned int *n_bad)
+{ /* n_bad (optional): counts negative entries — reads that no pass could hold (k_search leaves -status) */
     __shared__ int64_t sh[256];
     int64_t s = 0;
     const int base = blockIdx.x * SCAN_ITEMS;
     for (int i = threadIdx.x; i < SCAN_ITEMS; i += 256) {
         int idx = base + i;
-        if (idx < n) s += in[idx] > 0 ? in[idx] : 0;
+        if (idx < n) {
+            s += in[idx] > 0 ? in[idx] : 0;
+            if (n_bad && in[idx] < 0) atomicAdd(n_bad, 1u);
+        }
     }
     sh[threadIdx.x] = s;
     __syncthreads();
@@ -530,9 +543,17 @@ struct b200aln_ctx {
     int batch_max_len = 0; /* > 0: the reference batch this call is a shard of has this longest read */
     /* device buffers */
     DevBuf lens, offs, codes, md, Q, W, n_amb, ent, recs, n_aln, over_slot, over_list, misc, off64,
-        blk_tot, packed, dkey, order_buf, ent_big, recs_big, heads_wide, heads_wide_big, ent_mid, recs_mid, over_list2, sa_in, sa_out, grp_in, grp_out;
-    HostBuf h_in, h_out, h_misc;
+        blk_tot, packed, dkey, order_buf, Q_re, W_re, ent_big, recs_big, heads_wide, heads_wide_big, ent_mid, recs_mid, over_list2, over_list3, sa_in, sa_out, grp_in, grp_out;
+    HostBuf h_in, h_out, h_misc, h_nout;
     b200aln_stats_t stats;
+    /* chunk pipeline: a call with more than chunk_reads * 1.5 reads is cut into chunks that run on
+     * `slots` sibling contexts (own stream, pinned staging and scratch; slot 0 is this context), so that the copies,
+     * the width pass and the drain of one chunk's search overlap the search of the others */
+    int chunk_reads = 1 << 20, slots = 3;
+    b200aln_ctx *parent = nullptr;   /* clones: the context that owns the index */
+    int n_clones = 0;                /* owner: live clones (public and internal) */
+    std::vector<b200aln_ctx *> slot; /* internal siblings 1 .. slots-1 */
+    DevBuf asm_n_aln, asm_packed;    /* assembled results of a pipelined device-resident call */
 };
 
 [[noreturn]] static void die(const char *func, const char *fmt, ...)
@@ -705,6 +726,9 @@ extern "C" b200aln_ctx *b200aln_clone(b200aln_ctx *p)
     c->device = p->device;
     c->n_sm = p->n_sm;
     c->owns_index = false;
+    c->parent = p->parent ? p->parent : p;
+    ++c->parent->n_clones;
+    c->chunk_reads = p->chunk_reads; c->slots = p->slots;
     CK(cudaSetDevice(c->device));
     for (int i = 0; i < 2; ++i) {
         c->fm[i] = p->fm[i];
@@ -764,15 +788,21 @@ extern "C" b200aln_ctx *b200aln_open_prefix(const char *prefix, int device)
 extern "C" void b200aln_close(b200aln_ctx *c)
 {
     if (!c) return;
+    for (b200aln_ctx *s : c->slot) b200aln_close(s);
+    c->slot.clear();
+    if (c->parent) --c->parent->n_clones;
+    else if (c->n_clones > 0)
+        fprintf(stderr, "[b200aln_close] warning: %d clones of this context are still open; they must be closed first\n", c->n_clones);
     cudaSetDevice(c->device);
     cudaStreamSynchronize(c->st);
     DevBuf *bufs[] = {&c->lens, &c->offs, &c->codes, &c->md, &c->Q, &c->W, &c->n_amb, &c->ent,
                       &c->recs, &c->n_aln, &c->over_slot, &c->over_list, &c->misc, &c->off64, &c->blk_tot,
-                      &c->packed, &c->dkey, &c->order_buf, &c->ent_big, &c->recs_big, &c->heads_wide, &c->heads_wide_big, &c->ent_mid, &c->recs_mid,
-                      &c->over_list2, &c->sa_in, &c->sa_out};
+                      &c->packed, &c->dkey, &c->order_buf, &c->Q_re, &c->W_re, &c->ent_big, &c->recs_big, &c->heads_wide, &c->heads_wide_big, &c->ent_mid, &c->recs_mid,
+                      &c->over_list2, &c->over_list3, &c->sa_in, &c->sa_out};
     for (DevBuf *b : bufs) b->release();
     c->grp_in.release(); c->grp_out.release();
-    c->h_in.release(); c->h_out.release(); c->h_misc.release();
+    c->asm_n_aln.release(); c->asm_packed.release();
+    c->h_in.release(); c->h_out.release(); c->h_misc.release(); c->h_nout.release();
     if (c->owns_index) {
         for (int i = 0; i < 2; ++i) if (c->d_sa[i]) cudaFree(c->d_sa[i]);
         for (int i = 0; i < 2; ++i) if (c->d_idx[i]) cudaFree(c->d_idx[i]);
@@ -786,6 +816,16 @@ extern "C" void b200aln_close(b200aln_ctx *c)
 
 extern "C" void b200aln_set_int(b200aln_ctx *c, const char *key, int64_t v)
 {
+    if (!strcmp(key, "chunk_reads")) { c->chunk_reads = (int)v; return; }
+    if (!strcmp(key, "slots")) {
+        if (v < 1 || v > 8) die("b200aln_set_int", "slots must be 1..8.");
+        for (b200aln_ctx *s : c->slot) b200aln_close(s); /* re-created with the next pipelined call */
+        c->slot.clear();
+        c->slots = (int)v;
+        return;
+    }
+    if (strcmp(key, "lut_k") && strcmp(key, "batch_max_len"))
+        for (b200aln_ctx *s : c->slot) b200aln_set_int(s, key, v); /* the pipeline's siblings follow their context's knobs */
     if (!strcmp(key, "search_blocks_per_sm")) c->search_blocks_per_sm = (int)v;
     else if (!strcmp(key, "width_blocks_per_sm")) c->width_blocks_per_sm = (int)v;
     else if (!strcmp(key, "arena_cap")) c->arena_cap = (uint32_t)v;
@@ -806,6 +846,9 @@ extern "C" void b200aln_set_int(b200aln_ctx *c, const char *key, int64_t v)
     else if (!strcmp(key, "batch_max_len")) c->batch_max_len = (int)v;
     else if (!strcmp(key, "lut_k")) {
         if (!c->owns_index) die("b200aln_set_int", "lut_k must be set on the context that owns the index.");
+        for (b200aln_ctx *s : c->slot) b200aln_close(s); /* internal siblings hold pointers into the table */
+        c->slot.clear();
+        if (c->n_clones > 0) die("b200aln_set_int", "lut_k cannot change while %d clones share the interval table; close them first.", c->n_clones);
         c->lut_k = (int)v;
         build_luts(c);
     }
@@ -832,7 +875,7 @@ extern "C" void b200aln_last_stats(const b200aln_ctx *c, b200aln_stats_t *out) {
 
 /* device-side counters of one batch */
 struct Misc {
-    unsigned int counter, n_over, counter_big, counter_mid, n_over2, pad[3];
+    unsigned int counter, n_over, counter_big, counter_mid, n_over2, n_over3, n_rec_full, n_bad;
     unsigned long long stat[2];
     long long total;
     unsigned int class_cnt[B2_N_CLASSES], class_fill[B2_N_CLASSES];
@@ -867,18 +910,18 @@ static void launch_search_fast(b200aln_ctx *c, SearchArgs &A, int blocks)
     CK(cudaGetLastError());
 }
 
-static void launch_search_big(b200aln_ctx *c, SearchArgs &A, int blocks)
+static void launch_search_big(b200aln_ctx *c, SearchArgs &A, int blocks, int threads)
 {
-    const size_t smem32 = (size_t)A.env.P.n_buckets * 128 * sizeof(uint32_t);
-    if (smem32 + OG_WORDS * 128 * sizeof(uint32_t) <= 48 * 1024) { /* 32-bit heads still fit in shared memory (next to the open groups) */
-        k_search<HeadsStrided32, true, 1, true><<<blocks, 128, smem32, c->st>>>(A);
+    const size_t smem32 = (size_t)A.env.P.n_buckets * threads * sizeof(uint32_t);
+    if ((size_t)A.env.P.n_buckets * 128 * sizeof(uint32_t) + OG_WORDS * 128 * sizeof(uint32_t) <= 48 * 1024) { /* 32-bit heads still fit in shared memory (next to the open groups) */
+        k_search<HeadsStrided32, true, 1, true><<<blocks, threads, smem32, c->st>>>(A);
         CK(cudaGetLastError());
         return;
     }
     A.heads_wide_stride = A.env.P.n_buckets + (A.env.P.n_buckets + 31) / 32;
-    c->heads_wide_big.need((size_t)blocks * 128 * A.heads_wide_stride * 4);
+    c->heads_wide_big.need((size_t)blocks * threads * A.heads_wide_stride * 4);
     A.heads_wide = c->heads_wide_big.as<uint32_t>();
-    k_search<HeadsWide32, true, 1, true><<<blocks, 128, 0, c->st>>>(A);
+    k_search<HeadsWide32, true, 1, true><<<blocks, threads, 0, c->st>>>(A);
     CK(cudaGetLastError());
 }
 
@@ -928,6 +971,7 @@ static void run_batch_device(b200aln_ctx *c, int n_reads, int max_len, const int
     WA.comp = (opt->mode & MODE_COMPREAD) ? 1 : 0; WA.seed_len = opt->seed_len;
     WA.strideQ = strideQ; WA.strideW = strideW;
     WA.Q = c->Q.as<QRec>(); WA.W = c->W.as<uint32_t>();
+    WA.rows_by_work = 0;
     WA.n_amb = c->n_amb.as<int32_t>();
     WA.dkey = ordered ? c->dkey.as<uint8_t>() : nullptr;
     k_width<<<wblocks, 128, 0, c->st>>>(WA);
@@ -951,12 +995,14 @@ static void run_batch_device(b200aln_ctx *c, int n_reads, int max_len, const int
     SA.n_work = n_reads; SA.work_list = ordered ? c->order_buf.as<int32_t>() : nullptr;
     SA.lens = d_lens; SA.n_amb = c->n_amb.as<int32_t>(); SA.md = c->md.as<int32_t>();
     SA.env.Q = WA.Q; SA.env.W = WA.W; SA.env.strideQ = strideQ; SA.env.strideW = strideW;
+    SA.rows_by_work = 0;
     SA.env.ent = c->ent.as<StackRec>(); SA.env.arena_cap = c->arena_cap;
     SA.env.recs = c->recs.as<Rec>(); SA.env.rec_cap = c->rec_cap; SA.recs_by_work = 0;
     SA.n_aln = c->n_aln.as<int32_t>(); SA.over_slot = nullptr; SA.slot_tag = 0;
     SA.counter = &dm->counter; SA.n_over = &dm->n_over; SA.over_list = c->over_list.as<int32_t>();
     SA.stat = dm->stat;
     SA.heads_wide = nullptr; SA.heads_wide_stride = 0;
+    SA.arena_by_work = 0; SA.n_rec_full = nullptr;
     SA.pop_batch = c->pop_batch;
     SA.prep_rounds = c->prep_rounds;
     launch_search_fast(c, SA, sblocks);
@@ -990,13 +1036,17 @@ static void run_batch_device(b200aln_ctx *c, int n_reads, int max_len, const int
         c->ent_mid.need((size_t)mblocks * 128 * c->arena_cap_mid * sizeof(StackRec));
         c->recs_mid.need((size_t)n_over * c->rec_cap_mid * 16);
         c->over_list2.need((size_t)n_over * 4);
+        c->Q_re.need((size_t)n_over * 2 * strideQ * sizeof(QRec) + 64);
+        c->W_re.need((size_t)n_over * 2 * strideW * 4 + 64);
         WidthArgs WM = WA;
-        WM.dkey = nullptr;
+        WM.dkey = nullptr; WM.rows_by_work = 1;
+        WM.Q = c->Q_re.as<QRec>(); WM.W = c->W_re.as<uint32_t>();
         WM.n_reads = (int)n_over; WM.work_list = c->over_list.as<int32_t>();
         k_width<<<wblocks, 128, 0, c->st>>>(WM);
         CK(cudaGetLastError());
         ++launches;
         SearchArgs SM = SA;
+        SM.env.Q = WM.Q; SM.env.W = WM.W; SM.rows_by_work = 1;
         SM.n_work = (int)n_over; SM.work_list = c->over_list.as<int32_t>();
         SM.env.ent = c->ent_mid.as<StackRec>(); SM.env.arena_cap = c->arena_cap_mid;
         SM.env.recs = c->recs_mid.as<Rec>(); SM.env.rec_cap = c->rec_cap_mid; SM.recs_by_work = 1;
@@ -1013,36 +1063,56 @@ static void run_batch_device(b200aln_ctx *c, int n_reads, int max_len, const int
         if (verbose) fprintf(stderr, "[b200aln] middle pass %.1f ms (%d lanes), %u reads left for the wide pass\n", since(), lanes_mid, n_wide);
     }
     if (n_wide) {
-        uint32_t cap_big = c->arena_cap_big ? c->arena_cap_big : (uint32_t)opt->max_entries + 64u;
-        int big_lanes = c->big_lanes;
-        if ((unsigned)big_lanes > ((n_wide + 127u) / 128u) * 128u) big_lanes = (int)(((n_wide + 127u) / 128u) * 128u);
-        int bblocks = (big_lanes + 127) / 128;
-        c->ent_big.need((size_t)bblocks * 128 * cap_big * sizeof(StackRec));
-        c->recs_big.need((size_t)n_wide * c->rec_cap_big * 16);
-        WidthArgs WB = WA;
-        WB.dkey = nullptr;
-        WB.n_reads = (int)n_wide; WB.work_list = wide_list;
-        k_width<<<wblocks, 128, 0, c->st>>>(WB);
-        CK(cudaGetLastError());
-        ++launches;
-        SearchArgs SB = SA;
-        SB.n_work = (int)n_wide; SB.work_list = wide_list;
-        SB.env.ent = c->ent_big.as<StackRec>(); SB.env.arena_cap = cap_big;
-        SB.env.recs = c->recs_big.as<Rec>(); SB.env.rec_cap = c->rec_cap_big; SB.recs_by_work = 1;
-        SB.over_slot = c->over_slot.as<int32_t>(); SB.slot_tag = WIDE_TAG;
-        SB.env.prefetch_next = c->prefetch_mid;
-        SB.prep_rounds = 1 << 30;
-        SB.counter = &dm->counter_big; SB.n_over = nullptr; SB.over_list = nullptr;
-        launch_search_big(c, SB, bblocks);
-        ++launches;
-        if (verbose) {
+        /* The reference's hit array grows without limit (bwtgap.c:187-191) and its stack holds max_entries entries:
+         * the wide pass gives every read an arena of max_entries + 64 records (arenas only for the reads that need
+         * one) and a record slab that is enlarged, and the pass repeated, until every read fits. */
+        const uint32_t cap_big = c->arena_cap_big ? c->arena_cap_big : (uint32_t)opt->max_entries + 64u;
+        c->over_list3.need((size_t)n_wide * 4);
+        for (int attempt = 0;; ++attempt) {
+            int big_lanes = c->big_lanes;
+            if ((unsigned)big_lanes > ((n_wide + 31u) / 32u) * 32u) big_lanes = (int)(((n_wide + 31u) / 32u) * 32u);
+            const int bthreads = big_lanes < 128 ? big_lanes : 128, bblocks = (big_lanes + bthreads - 1) / bthreads;
+            const bool by_work = n_wide <= (unsigned)(bblocks * bthreads);
+            c->ent_big.need((size_t)(by_work ? n_wide : (unsigned)(bblocks * bthreads)) * cap_big * sizeof(StackRec));
+            c->recs_big.need((size_t)n_wide * c->rec_cap_big * 16);
+            c->Q_re.need((size_t)n_wide * 2 * strideQ * sizeof(QRec) + 64);
+            c->W_re.need((size_t)n_wide * 2 * strideW * 4 + 64);
+            WidthArgs WB = WA;
+            WB.dkey = nullptr; WB.rows_by_work = 1;
+            WB.Q = c->Q_re.as<QRec>(); WB.W = c->W_re.as<uint32_t>();
+            WB.n_reads = (int)n_wide; WB.work_list = wide_list;
+            k_width<<<wblocks, 128, 0, c->st>>>(WB);
+            CK(cudaGetLastError());
+            ++launches;
+            SearchArgs SB = SA;
+            SB.env.Q = WB.Q; SB.env.W = WB.W; SB.rows_by_work = 1;
+            SB.n_work = (int)n_wide; SB.work_list = wide_list;
+            SB.env.ent = c->ent_big.as<StackRec>(); SB.env.arena_cap = cap_big; SB.arena_by_work = by_work ? 1 : 0;
+            SB.env.recs = c->recs_big.as<Rec>(); SB.env.rec_cap = c->rec_cap_big; SB.recs_by_work = 1;
+            SB.over_slot = c->over_slot.as<int32_t>(); SB.slot_tag = WIDE_TAG;
+            SB.env.prefetch_next = c->prefetch_mid;
+            SB.prep_rounds = 1 << 30;
+            SB.counter = &dm->counter_big; SB.n_over = &dm->n_over3; SB.over_list = c->over_list3.as<int32_t>();
+            SB.n_rec_full = &dm->n_rec_full;
+            launch_search_big(c, SB, bblocks, bthreads);
+            ++launches;
+            CK(cudaMemcpyAsync(c->h_misc.p, c->misc.p, sizeof(Misc), cudaMemcpyDeviceToHost, c->st));
             CK(cudaStreamSynchronize(c->st));
-            fprintf(stderr, "[b200aln] wide pass done at %.1f ms (%d lanes)\n", since(), bblocks * 128);
+            const Misc hw = *c->h_misc.as<Misc>();
+            if (verbose) fprintf(stderr, "[b200aln] wide pass done at %.1f ms (%d lanes, %d records per read), %u reads do not fit\n", since(), bblocks * bthreads, c->rec_cap_big, hw.n_over3);
+            if (!hw.n_over3) break;
+            if (hw.n_over3 > hw.n_rec_full)
+                die("b200aln_batch", "%u reads exceeded the large per-read arena of %u records (knob arena_cap_big; the default holds max_entries).",
+                    hw.n_over3 - hw.n_rec_full, cap_big);
+            if (c->rec_cap_big > (1 << 26) || attempt > 16) die("b200aln_batch", "a read has more than %d hits.", c->rec_cap_big);
+            c->rec_cap_big *= 4; /* everything the pass produced is redone with the larger slabs */
+            CK(cudaMemsetAsync(&dm->counter_big, 0, 4, c->st));
+            CK(cudaMemsetAsync(&dm->n_over3, 0, 8, c->st)); /* n_over3, n_rec_full */
         }
     }
     CK(cudaEventRecord(c->ev[4], c->st));
 
-    k_scan_totals<<<nscan, 256, 0, c->st>>>(c->n_aln.as<int32_t>(), n_reads, c->blk_tot.as<int64_t>());
+    k_scan_totals<<<nscan, 256, 0, c->st>>>(c->n_aln.as<int32_t>(), n_reads, c->blk_tot.as<int64_t>(), &dm->n_bad);
     k_scan_blocks<<<1, 32, 0, c->st>>>(c->blk_tot.as<int64_t>(), nscan, (int64_t *)&dm->total);
     k_scan_apply<<<nscan, 256, 0, c->st>>>(c->n_aln.as<int32_t>(), n_reads, c->blk_tot.as<int64_t>(),
                                            c->off64.as<int64_t>());
@@ -1051,6 +1121,8 @@ static void run_batch_device(b200aln_ctx *c, int n_reads, int max_len, const int
     CK(cudaMemcpyAsync(c->h_misc.p, c->misc.p, sizeof(Misc), cudaMemcpyDeviceToHost, c->st));
     CK(cudaStreamSynchronize(c->st));
     const Misc hm = *c->h_misc.as<Misc>();
+    if (hm.n_bad) /* never a partial result (include/b200aln.h); the wide pass already grows what it can */
+        die("b200aln_batch", "%u reads exceeded the per-read arena or record capacity of every pass (knobs arena_cap_big / rec_cap_big).", hm.n_bad);
     const int64_t total = hm.total;
     c->packed.need((size_t)(total > 0 ? total : 1) * 16);
     k_compact<<<c->n_sm * 4, 256, 0, c->st>>>(n_reads, c->n_aln.as<int32_t>(), c->off64.as<int64_t>(),
@@ -1083,13 +1155,132 @@ static void finish_stats(b200aln_ctx *c, bool with_copies)
     }
 }
 
-static void check_overflow_of_large_pass(b200aln_ctx *c, int n_reads, const int32_t *h_n_aln)
+static bool host_pinned(const void *p)
+{ /* page-locked (cudaHostAlloc / cudaHostRegister) memory can be the end point of an asynchronous copy */
+    cudaPointerAttributes a;
+    if (cudaPointerGetAttributes(&a, p) != cudaSuccess) { (void)cudaGetLastError(); return false; }
+    return a.type == cudaMemoryTypeHost || a.type == cudaMemoryTypeManaged;
+}
+
+static void add_stats(b200aln_stats_t &acc, const b200aln_stats_t &s)
 {
-    (void)c;
-    for (int r = 0; r < n_reads; ++r)
-        if (h_n_aln[r] < 0)
-            die("b200aln_batch",
-                "read %d exceeded the large per-read arena or record capacity (raise arena_cap_big / rec_cap_big).", r);
+    acc.ms_h2d += s.ms_h2d; acc.ms_width += s.ms_width; acc.ms_search += s.ms_search; acc.ms_compact += s.ms_compact;
+    acc.ms_d2h += s.ms_d2h; acc.kernel_launches += s.kernel_launches; acc.overflow_reads += s.overflow_reads;
+    acc.pops += s.pops; acc.occ_lookups += s.occ_lookups;
+}
+
+/* the siblings a pipelined call runs its chunks on (created once, kept) */
+static void ensure_slots(b200aln_ctx *c)
+{
+    while ((int)c->slot.size() < c->slots - 1) {
+        b200aln_ctx *s = b200aln_clone(c);
+        s->slots = 1; /* a sibling never splits further */
+        c->slot.push_back(s);
+    }
+}
+
+static int pipeline_chunks(const b200aln_ctx *c, int n_reads)
+{
+    if (c->slots < 2 || c->chunk_reads <= 0 || (int64_t)n_reads <= (int64_t)c->chunk_reads + c->chunk_reads / 2) return 1;
+    return (int)(((int64_t)n_reads + c->chunk_reads - 1) / c->chunk_reads);
+}
+
+/* In-order hand-over of the chunks' results: a chunk learns where its records go once every earlier chunk has
+ * reported its total.  Copies into the assembled buffer hold `grow` shared; enlarging the buffer holds it exclusive. */
+struct ChunkOrder {
+    std::mutex mu;
+    std::condition_variable cv;
+    std::vector<int64_t> tot;
+    std::shared_mutex grow;
+    std::atomic<int> next{0};
+    explicit ChunkOrder(int n) : tot((size_t)n, -1) {}
+    int64_t report(int ci, int64_t t)
+    { /* returns the record offset of chunk ci */
+        std::unique_lock<std::mutex> lk(mu);
+        tot[(size_t)ci] = t;
+        cv.notify_all();
+        int64_t off = 0;
+        for (int j = 0; j < ci; ++j) {
+            cv.wait(lk, [&] { return tot[(size_t)j] >= 0; });
+            off += tot[(size_t)j];
+        }
+        return off;
+    }
+};
+
+/* one chunk of host buffers on context s: H2D (through s's pinned staging when the caller's memory is pageable),
+ * the device passes; leaves n_aln / packed records on the device; returns the number of records */
+static int64_t run_chunk_host(b200aln_ctx *s, int n, const int32_t *lens, const int64_t *offs, const uint8_t *codes,
+                              const b200aln_opt_t *opt, const Params &P, const std::vector<int> &md, bool pinned_in)
+{
+    int max_len = 0;
+    int64_t lo = INT64_MAX, hi = 0;
+    for (int r = 0; r < n; ++r) {
+        if (lens[r] > max_len) max_len = lens[r];
+        if (offs[r] < lo) lo = offs[r];
+        if (offs[r] + lens[r] > hi) hi = offs[r] + lens[r];
+    }
+    if (lo > hi) lo = hi;
+    const size_t nb = (size_t)(hi - lo);
+    const size_t n_alloc = (size_t)(n > s->reserve_reads ? n : s->reserve_reads);
+    s->lens.need(n_alloc * 4);
+    s->offs.need(n_alloc * 8);
+    s->codes.need((size_t)((double)nb * ((double)n_alloc / (double)n)) + 16);
+    const void *h_lens = lens, *h_offs = offs, *h_codes = codes + lo;
+    if (!pinned_in) { /* pageable caller memory: through this context's page-locked staging buffer */
+        const size_t at_offs = ((size_t)n * 4 + 63) & ~(size_t)63, at_codes = (at_offs + (size_t)n * 8 + 63) & ~(size_t)63;
+        s->h_in.need(at_codes + nb + 64);
+        char *st = s->h_in.as<char>();
+        memcpy(st, lens, (size_t)n * 4);
+        memcpy(st + at_offs, offs, (size_t)n * 8);
+        memcpy(st + at_codes, codes + lo, nb);
+        h_lens = st; h_offs = st + at_offs; h_codes = st + at_codes;
+    }
+    CK(cudaEventRecord(s->ev[0], s->st));
+    CK(cudaMemcpyAsync(s->lens.p, h_lens, (size_t)n * 4, cudaMemcpyHostToDevice, s->st));
+    CK(cudaMemcpyAsync(s->offs.p, h_offs, (size_t)n * 8, cudaMemcpyHostToDevice, s->st));
+    if (nb) CK(cudaMemcpyAsync(s->codes.p, h_codes, nb, cudaMemcpyHostToDevice, s->st));
+    int64_t tot = 0;
+    /* offs stay absolute: the kernels address codes_base + offs[r] */
+    run_batch_device(s, n, max_len, s->lens.as<int32_t>(), s->offs.as<int64_t>(), s->codes.as<uint8_t>() - lo, opt, md, P, &tot);
+    return tot;
+}
+
+/* D2H of a finished chunk: records to rec_dst (page-locked), counts to the caller's n_aln (staged when pageable) */
+static void fetch_chunk_host(b200aln_ctx *s, int n, int64_t tot, b200aln_rec_t *rec_dst, int32_t *n_aln, bool pinned_out)
+{
+    int32_t *dst_n = n_aln;
+    if (!pinned_out) {
+        s->h_nout.need((size_t)n * 4);
+        dst_n = s->h_nout.as<int32_t>();
+    }
+    CK(cudaMemcpyAsync(dst_n, s->n_aln.p, (size_t)n * 4, cudaMemcpyDeviceToHost, s->st));
+    if (tot) CK(cudaMemcpyAsync(rec_dst, s->packed.p, (size_t)tot * 16, cudaMemcpyDeviceToHost, s->st));
+    CK(cudaEventRecord(s->ev[6], s->st));
+    CK(cudaStreamSynchronize(s->st));
+    if (!pinned_out) memcpy(n_aln, dst_n, (size_t)n * 4);
+    finish_stats(s, true);
+}
+
+static void grow_host_keep(HostBuf &b, size_t bytes)
+{ /* like need(), but the contents survive */
+    if (bytes <= b.cap) return;
+    void *np = nullptr;
+    size_t want = bytes + bytes / 2 + 256;
+    CK(cudaHostAlloc(&np, want, cudaHostAllocDefault));
+    if (b.p) { memcpy(np, b.p, b.cap); CK(cudaFreeHost(b.p)); }
+    b.p = np;
+    b.cap = want;
+}
+static void grow_dev_keep(DevBuf &b, size_t bytes)
+{
+    if (bytes <= b.cap) return;
+    void *np = nullptr;
+    size_t want = bytes + bytes / 2 + 256;
+    CK(cudaMalloc(&np, want));
+    if (b.p) { CK(cudaMemcpy(np, b.p, b.cap, cudaMemcpyDeviceToDevice)); CK(cudaFree(b.p)); }
+    b.p = np;
+    b.cap = want;
 }
 
 extern "C" const b200aln_rec_t *b200aln_batch(b200aln_ctx *c, int n_reads, const int32_t *lens, const int64_t *offs,
@@ -1100,11 +1291,9 @@ extern "C" const b200aln_rec_t *b200aln_batch(b200aln_ctx *c, int n_reads, const
     *total = 0;
     if (n_reads <= 0) return c->h_out.as<b200aln_rec_t>();
     int max_len = 0;
-    int64_t end = 0;
     for (int r = 0; r < n_reads; ++r) {
         if (lens[r] < 0) die("b200aln_batch", "read %d has negative length %d.", r, lens[r]);
         if (lens[r] > max_len) max_len = lens[r];
-        if (offs[r] + lens[r] > end) end = offs[r] + lens[r];
     }
     Params P;
     std::vector<int> md;
@@ -1113,26 +1302,56 @@ extern "C" const b200aln_rec_t *b200aln_batch(b200aln_ctx *c, int n_reads, const
     /* a shard of a larger reference batch: the batch-level clamp (bwtaln.c:89-92) uses the whole batch's longest read */
     b2host::make_params(*opt, c->batch_max_len > 0 ? c->batch_max_len : max_len, lens, n_reads, P, md);
     if ((int)md.size() < max_len + 1) md.resize((size_t)max_len + 1, opt->max_diff);
+    const bool pinned_in = host_pinned(lens) && host_pinned(offs) && host_pinned(codes), pinned_out = host_pinned(n_aln);
 
-    const size_t n_alloc = (size_t)(n_reads > c->reserve_reads ? n_reads : c->reserve_reads);
-    c->lens.need(n_alloc * 4);
-    c->offs.need(n_alloc * 8);
-    c->codes.need((size_t)((double)end * ((double)n_alloc / (double)n_reads)) + 16);
-    CK(cudaEventRecord(c->ev[0], c->st));
-    CK(cudaMemcpyAsync(c->lens.p, lens, (size_t)n_reads * 4, cudaMemcpyHostToDevice, c->st));
-    CK(cudaMemcpyAsync(c->offs.p, offs, (size_t)n_reads * 8, cudaMemcpyHostToDevice, c->st));
-    CK(cudaMemcpyAsync(c->codes.p, codes, (size_t)end, cudaMemcpyHostToDevice, c->st));
-    int64_t tot = 0;
-    run_batch_device(c, n_reads, max_len, c->lens.as<int32_t>(), c->offs.as<int64_t>(), c->codes.as<uint8_t>(), opt,
-                     md, P, &tot);
-    c->h_out.need((size_t)(tot > 0 ? tot : 1) * 16);
-    CK(cudaMemcpyAsync(n_aln, c->n_aln.p, (size_t)n_reads * 4, cudaMemcpyDeviceToHost, c->st));
-    if (tot) CK(cudaMemcpyAsync(c->h_out.p, c->packed.p, (size_t)tot * 16, cudaMemcpyDeviceToHost, c->st));
-    CK(cudaEventRecord(c->ev[6], c->st));
-    CK(cudaStreamSynchronize(c->st));
-    finish_stats(c, true);
-    check_overflow_of_large_pass(c, n_reads, n_aln);
-    *total = tot;
+    const int n_chunks = pipeline_chunks(c, n_reads);
+    if (n_chunks == 1) {
+        const int64_t tot = run_chunk_host(c, n_reads, lens, offs, codes, opt, P, md, pinned_in);
+        c->h_out.need((size_t)(tot > 0 ? tot : 1) * 16);
+        fetch_chunk_host(c, n_reads, tot, c->h_out.as<b200aln_rec_t>(), n_aln, pinned_out);
+        *total = tot;
+        return c->h_out.as<b200aln_rec_t>();
+    }
+
+    /* pipelined: chunks of the call on this context and its siblings, results assembled in read order */
+    ensure_slots(c);
+    const auto t0 = std::chrono::steady_clock::now();
+    const int per = (n_reads + n_chunks - 1) / n_chunks, n_workers = c->slots < n_chunks ? c->slots : n_chunks;
+    if (c->h_out.cap < (size_t)n_reads * 24) c->h_out.need((size_t)n_reads * 24); /* grown below when the hits outnumber that */
+    ChunkOrder ord(n_chunks);
+    b200aln_stats_t acc;
+    memset(&acc, 0, sizeof acc);
+    std::mutex acc_mu;
+    auto worker = [&](int si) {
+        b200aln_ctx *s = si == 0 ? c : c->slot[(size_t)si - 1];
+        CK(cudaSetDevice(s->device));
+        for (;;) {
+            const int ci = ord.next.fetch_add(1);
+            if (ci >= n_chunks) break;
+            const int lo = ci * per, n = (lo + per < n_reads ? lo + per : n_reads) - lo;
+            const int64_t tot = run_chunk_host(s, n, lens + lo, offs + lo, codes, opt, P, md, pinned_in);
+            const int64_t off = ord.report(ci, tot);
+            if ((size_t)(off + tot) * 16 > c->h_out.cap) {
+                std::unique_lock<std::shared_mutex> g(ord.grow); /* no copy into the buffer is in flight now */
+                grow_host_keep(c->h_out, (size_t)(off + tot) * 16);
+            }
+            {
+                std::shared_lock<std::shared_mutex> g(ord.grow);
+                fetch_chunk_host(s, n, tot, c->h_out.as<b200aln_rec_t>() + off, n_aln + lo, pinned_out);
+            }
+            std::lock_guard<std::mutex> lk(acc_mu);
+            add_stats(acc, s->stats);
+        }
+    };
+    std::vector<std::thread> th;
+    for (int si = 1; si < n_workers; ++si) th.emplace_back(worker, si);
+    worker(0);
+    for (auto &t : th) t.join();
+    int64_t tot_all = 0;
+    for (int64_t t : ord.tot) tot_all += t;
+    acc.ms_total = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
+    c->stats = acc;
+    *total = tot_all;
     return c->h_out.as<b200aln_rec_t>();
 }
 
@@ -1146,14 +1365,64 @@ extern "C" void b200aln_batch_device(b200aln_ctx *c, int n_reads, int max_len, c
     std::vector<int32_t> one(1, max_len);
     /* all lengths up to max_len are tabulated; reads longer than 1024 bp need the host-buffer entry point */
     if (max_len > 1024) die("b200aln_batch_device", "max_len > 1024 needs b200aln_batch (per-length max_diff table).");
-    b2host::make_params(*opt, max_len, one.data(), 1, P, md);
-    int64_t tot = 0;
-    run_batch_device(c, n_reads, max_len, d_lens, d_offs, d_codes, opt, md, P, &tot);
-    CK(cudaStreamSynchronize(c->st));
-    finish_stats(c, false);
-    *d_n_aln = c->n_aln.as<int32_t>();
-    *d_recs = c->packed.as<b200aln_rec_t>();
-    *total = tot;
+    b2host::make_params(*opt, c->batch_max_len > 0 ? c->batch_max_len : max_len, one.data(), 1, P, md);
+    if ((int)md.size() < max_len + 1) md.resize((size_t)max_len + 1, opt->max_diff);
+    const int n_chunks = n_reads > 0 ? pipeline_chunks(c, n_reads) : 1;
+    if (n_chunks == 1) {
+        int64_t tot = 0;
+        run_batch_device(c, n_reads, max_len, d_lens, d_offs, d_codes, opt, md, P, &tot);
+        CK(cudaStreamSynchronize(c->st));
+        finish_stats(c, false);
+        *d_n_aln = c->n_aln.as<int32_t>();
+        *d_recs = c->packed.as<b200aln_rec_t>();
+        *total = tot;
+        return;
+    }
+    ensure_slots(c);
+    const auto t0 = std::chrono::steady_clock::now();
+    const int per = (n_reads + n_chunks - 1) / n_chunks, n_workers = c->slots < n_chunks ? c->slots : n_chunks;
+    c->asm_n_aln.need((size_t)n_reads * 4);
+    if (c->asm_packed.cap < (size_t)n_reads * 24) c->asm_packed.need((size_t)n_reads * 24);
+    ChunkOrder ord(n_chunks);
+    b200aln_stats_t acc;
+    memset(&acc, 0, sizeof acc);
+    std::mutex acc_mu;
+    auto worker = [&](int si) {
+        b200aln_ctx *s = si == 0 ? c : c->slot[(size_t)si - 1];
+        CK(cudaSetDevice(s->device));
+        for (;;) {
+            const int ci = ord.next.fetch_add(1);
+            if (ci >= n_chunks) break;
+            const int lo = ci * per, n = (lo + per < n_reads ? lo + per : n_reads) - lo;
+            int64_t tot = 0;
+            run_batch_device(s, n, max_len, d_lens + lo, d_offs + lo, d_codes, opt, md, P, &tot);
+            const int64_t off = ord.report(ci, tot);
+            if ((size_t)(off + tot) * 16 > c->asm_packed.cap) {
+                std::unique_lock<std::shared_mutex> g(ord.grow);
+                grow_dev_keep(c->asm_packed, (size_t)(off + tot) * 16);
+            }
+            {
+                std::shared_lock<std::shared_mutex> g(ord.grow);
+                CK(cudaMemcpyAsync(c->asm_n_aln.as<int32_t>() + lo, s->n_aln.p, (size_t)n * 4, cudaMemcpyDeviceToDevice, s->st));
+                if (tot) CK(cudaMemcpyAsync(c->asm_packed.as<b200aln_rec_t>() + off, s->packed.p, (size_t)tot * 16, cudaMemcpyDeviceToDevice, s->st));
+                CK(cudaStreamSynchronize(s->st));
+            }
+            finish_stats(s, false);
+            std::lock_guard<std::mutex> lk(acc_mu);
+            add_stats(acc, s->stats);
+        }
+    };
+    std::vector<std::thread> th;
+    for (int si = 1; si < n_workers; ++si) th.emplace_back(worker, si);
+    worker(0);
+    for (auto &t : th) t.join();
+    int64_t tot_all = 0;
+    for (int64_t t : ord.tot) tot_all += t;
+    acc.ms_total = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
+    c->stats = acc;
+    *d_n_aln = c->asm_n_aln.as<int32_t>();
+    *d_recs = c->asm_packed.as<b200aln_rec_t>();
+    *total = tot_all;
 }
 
 /* ---- row N2: SA row -> position ---------------------------------------------------------------------- */
@@ -1162,6 +1431,7 @@ extern "C" void b200aln_sa_load(b200aln_ctx *c, int which, const b200aln_sa_view
 { /* bwt_restore_sa (bwtio.c:29-49) onto the device */
     CK(cudaSetDevice(c->device));
     if (which < 0 || which > 1) die("b200aln_sa_load", "which must be 0 (.sa) or 1 (.rsa).");
+    if (c->parent) die("b200aln_sa_load", "load the suffix arrays on the context that owns the index (clones see them).");
     if (v->primary != c->fm[which].primary) die("b200aln_sa_load", "SA-BWT inconsistency: primary is not the same.");
     if (v->seq_len != c->fm[which].seq_len) die("b200aln_sa_load", "SA-BWT inconsistency: seq_len is not the same.");
     if (v->sa_intv <= 0) die("b200aln_sa_load", "bad SA interval.");
@@ -1177,12 +1447,13 @@ extern "C" void b200aln_sa_load(b200aln_ctx *c, int which, const b200aln_sa_view
 extern "C" void b200aln_bwt_sa(b200aln_ctx *c, int which, int64_t n, const uint32_t *rows, uint32_t *pos)
 {
     CK(cudaSetDevice(c->device));
-    if (which < 0 || which > 1 || !c->d_sa[which]) die("b200aln_bwt_sa", "no suffix array loaded for index %d.", which);
+    const b200aln_ctx *o = c->parent ? c->parent : c; /* suffix arrays live with the owner of the index */
+    if (which < 0 || which > 1 || !o->d_sa[which]) die("b200aln_bwt_sa", "no suffix array loaded for index %d.", which);
     if (n <= 0) return;
     c->sa_in.need((size_t)n * 4);
     c->sa_out.need((size_t)n * 8);
     CK(cudaMemcpyAsync(c->sa_in.p, rows, (size_t)n * 4, cudaMemcpyHostToDevice, c->st));
-    k_bwt_sa<<<c->n_sm * 8, 256, 0, c->st>>>(c->fm[which], c->d_sa[which], c->sa_intv[which], n, c->sa_in.as<uint32_t>(),
+    k_bwt_sa<<<c->n_sm * 8, 256, 0, c->st>>>(c->fm[which], o->d_sa[which], o->sa_intv[which], n, c->sa_in.as<uint32_t>(),
                                             c->sa_out.as<uint32_t>());
     CK(cudaGetLastError());
     CK(cudaMemcpyAsync(pos, c->sa_out.p, (size_t)n * 4, cudaMemcpyDeviceToHost, c->st));
@@ -1193,7 +1464,8 @@ extern "C" void b200aln_sa2seq(b200aln_ctx *c, int64_t n, const uint8_t *strand,
                                uint64_t *pos)
 {
     CK(cudaSetDevice(c->device));
-    if (!c->d_sa[0] || !c->d_sa[1]) die("b200aln_sa2seq", "both suffix arrays (.sa and .rsa) must be loaded.");
+    const b200aln_ctx *o = c->parent ? c->parent : c;
+    if (!o->d_sa[0] || !o->d_sa[1]) die("b200aln_sa2seq", "both suffix arrays (.sa and .rsa) must be loaded.");
     if (n <= 0) return;
     c->sa_in.need((size_t)n * 9 + 64);
     c->sa_out.need((size_t)n * 8);
@@ -1203,7 +1475,7 @@ extern "C" void b200aln_sa2seq(b200aln_ctx *c, int64_t n, const uint8_t *strand,
     CK(cudaMemcpyAsync(d_rows, rows, (size_t)n * 4, cudaMemcpyHostToDevice, c->st));
     CK(cudaMemcpyAsync(d_lens, lens, (size_t)n * 4, cudaMemcpyHostToDevice, c->st));
     CK(cudaMemcpyAsync(d_strand, strand, (size_t)n, cudaMemcpyHostToDevice, c->st));
-    k_sa2seq<<<c->n_sm * 8, 256, 0, c->st>>>(c->fm[0], c->d_sa[0], c->fm[1], c->d_sa[1], c->sa_intv[0], c->sa_intv[1], n,
+    k_sa2seq<<<c->n_sm * 8, 256, 0, c->st>>>(c->fm[0], o->d_sa[0], c->fm[1], o->d_sa[1], o->sa_intv[0], o->sa_intv[1], n,
                                             d_strand, d_rows, d_lens, c->sa_out.as<uint64_t>());
     CK(cudaGetLastError());
     CK(cudaMemcpyAsync(pos, c->sa_out.p, (size_t)n * 8, cudaMemcpyDeviceToHost, c->st));
@@ -1214,7 +1486,7 @@ static void scan_i32(b200aln_ctx *c, const int32_t *in, int n, int64_t *out, int
 { /* exclusive prefix sum on the engine's stream (the three scan kernels of the batch path) */
     const int nscan = (n + SCAN_ITEMS - 1) / SCAN_ITEMS;
     c->blk_tot.need((size_t)nscan * 8 + 8);
-    k_scan_totals<<<nscan, 256, 0, c->st>>>(in, n, c->blk_tot.as<int64_t>());
+    k_scan_totals<<<nscan, 256, 0, c->st>>>(in, n, c->blk_tot.as<int64_t>(), nullptr);
     k_scan_blocks<<<1, 32, 0, c->st>>>(c->blk_tot.as<int64_t>(), nscan, total_dev);
     k_scan_apply<<<nscan, 256, 0, c->st>>>(in, n, c->blk_tot.as<int64_t>(), out);
     CK(cudaGetLastError());

@@ -72,7 +72,7 @@ static int64_t run(const SearchEnv &env, const std::vector<int> &md, int n_reads
         const uint8_t *fwd = codes + offs[r];
         int len = lens[r];
         const FmView *fm = env.fm;
-        int n_amb = width_pass(fm[0], fwd, len, 0, comp, seed_len, W.data(), Q.data());
+        int n_amb = width_pass(fm[0], fwd, len, 0, comp, seed_len, W.data(), Q.data()).n_amb;
         width_pass(fm[1], fwd, len, 1, comp, seed_len, W.data() + strideW, Q.data() + strideQ);
         SearchLane<Heads, REUSE> lane;
         SearchEnv e1 = env;
@@ -84,7 +84,7 @@ static int64_t run(const SearchEnv &env, const std::vector<int> &md, int n_reads
             /* the product's large pass: widths rebuilt (the aborted pass shadowed them), free-list arena */
             ++n_status;
             if (ent2.size() < big_cap) { ent2.resize(big_cap); recs2.resize(1 << 16); }
-            n_amb = width_pass(fm[0], fwd, len, 0, comp, seed_len, W.data(), Q.data());
+            n_amb = width_pass(fm[0], fwd, len, 0, comp, seed_len, W.data(), Q.data()).n_amb;
             width_pass(fm[1], fwd, len, 1, comp, seed_len, W.data() + strideW, Q.data() + strideQ);
             SearchLane<HeadsWide32, true> big;
             SearchEnv e2 = e1;

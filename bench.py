@@ -1,24 +1,32 @@
 #!/usr/bin/env python
 """bench.py — `bwa aln` reads/s on B200 (BASELINE.json metric), one process per GPU.
 
-Workload (config.workload): BASELINE.json configs[1] — N simulated 100 bp reads
-vs a 3.1 Gbp synthetic genome, defaults (-n 0.04), index replicated on every
-GPU, reads sharded (weak scaling: every rank aligns --reads reads of its own).
-The genome is i.i.d. uniform ACGT generated on the GPU from a seed; its .bwt /
-.rbwt are built on the GPU by ibwa_b200.fmbuild (bit-identical to what the
-reference's `index` writes, tests/test_fmbuild.py) and cached under
-/tmp/b200aln_bench so the reference arm and this arm read the same files.
+Workloads (--config, BASELINE.json `configs`, numbered from 1):
+  1  100 k x 100 bp vs 5 Mbp, defaults                       (the reference's own CPU-sized case)
+  2  10 M x 100 bp vs 3.1 Gbp, defaults                      (the headline; default)
+  3  stress: 150 bp reads, -n 4 -o 2 -e 10 -l 32 -k 2, 2 % substitutions + indels, 3.1 Gbp
+  4  paired end: 2 x 5 M x 100 bp, both mates through the engine; parity = .sai identity and the SAM of the
+     UNCHANGED `ibwa sampe -R` on engine vs reference .sai
+  5  dbset: primary + 200 ALT contigs with a .remap file, 25 % of the pairs from ALT sequence; both mates against
+     both indexes; parity = four .sai and `sampe -R <pri> .. <alt> ..` SAM (ZR:Z tags) equality
+The genome is i.i.d. uniform ACGT generated on the GPU from a seed; its index files are built on the GPU by
+ibwa_b200.fmbuild / refdata (byte-identical to what the reference's `index` writes, tests/test_fmbuild.py,
+tests/test_refdata.py) and cached under /tmp/b200aln_bench so that the reference binary reads the same files.
 
-A step = one pass of the hot path (bwa_cal_sa_reg_gap) over the rank's reads.
+A step = one pass of the hot path (bwa_cal_sa_reg_gap) over the step's reads (every stream of the config).
+  --scaling strong (default): the step's --reads are cut into contiguous per-rank shards
+  --scaling weak            : every rank aligns --reads reads of its own
   value : reads resident in HBM before the timed region (b200aln_batch_device)
   e2e   : the same reads from pinned HOST buffers through b200aln_batch
           (H2D of reads and D2H of n_aln + records inside the timed region)
-Timing: CUDA events on the engine's launch stream (b200aln_timer_*), barrier +
-synchronize on both sides, max over ranks.  Index (3.1 GB) and per-read state
+Both are throughputs of K steps with --in-flight steps in flight on contexts that share the device index (the
+engine's double buffering); `sequential` holds the same steps one at a time on one context, which is also where
+the per-kernel times of the roofline come from.  Timing: CUDA events on the engine's launch stream
+(b200aln_timer_*), barrier + synchronize on both sides, max over ranks.  Index (3.1 GB) and per-read state
 (> 10 GB) are far larger than L2, so no L2 flush is needed between steps.
 
-`--impl reference` times the unmodified reference binary (oracle/_ref/ibwa aln
--t <all cores>) on a bounded sample of the same reads on the host cores.
+`--impl reference` times the unmodified reference binary (oracle/_ref/ibwa aln -t <all cores>) on a bounded
+sample of the same reads on the host cores.
 """
 from __future__ import annotations
 
@@ -145,45 +153,79 @@ def cache_dir(genome_bp: int, seed: int) -> str:
     return os.path.join(CACHE_ROOT, f"g{genome_bp}_s{seed}")
 
 
-def load_or_build_index(genome_bp: int, seed: int, device, is_writer: bool):
-    """Returns (bwt, rbwt, text).  The text is always regenerated from the seed on the GPU."""
+def contig_layout(genome_bp: int):
+    """contigs chr1.. of 100 Mbp (a contig must stay below 2^31 bp, bntseq.h:42); the text is one stream."""
+    step = 100_000_000
+    lens = [step] * (genome_bp // step)
+    if genome_bp % step:
+        lens.append(genome_bp % step)
+    return [f"chr{i + 1}" for i in range(len(lens))], lens
+
+
+def load_or_build_index(genome_bp: int, seed: int, device, is_writer: bool, with_sa: bool = False):
+    """Returns (bwt, rbwt, text, prefix).  The text is always regenerated from the seed on the GPU.  with_sa: also
+    the files the downstream `sampe` opens (.sa .rsa .pac .ann .amb), written by ibwa_b200.refdata."""
     import torch
-    from ibwa_b200 import fmbuild
-    from ibwa_b200.bwtio import bwt_dump_bwt, bwt_restore_bwt
+    from ibwa_b200 import fmbuild, refdata
+    from ibwa_b200.bwtio import bwt_dump_bwt, bwt_dump_sa, bwt_restore_bwt
     d = cache_dir(genome_bp, seed)
     prefix = os.path.join(d, "ref")
     text = gen_text(genome_bp, seed, device)
-    done = os.path.join(d, "DONE")
-    if os.path.exists(done):
+    done = os.path.join(d, "DONE_SA" if with_sa else "DONE")
+    if os.path.exists(done) or (not with_sa and os.path.exists(os.path.join(d, "DONE_SA"))):
         return bwt_restore_bwt(prefix + ".bwt"), bwt_restore_bwt(prefix + ".rbwt"), text, prefix
     t0 = time.time()
-    bwt = fmbuild.build_bwt_torch(text)
+    if with_sa:
+        bwt, sa = fmbuild.build_bwt_torch(text, sa_intv=32)
+        torch.cuda.empty_cache()
+        rbwt, rsa = fmbuild.build_bwt_torch(torch.flip(text, dims=[0]), sa_intv=32)
+    else:
+        bwt = fmbuild.build_bwt_torch(text)
+        torch.cuda.empty_cache()
+        rbwt = fmbuild.build_bwt_torch(torch.flip(text, dims=[0]))
     torch.cuda.empty_cache()
-    rbwt = fmbuild.build_bwt_torch(torch.flip(text, dims=[0]))
-    torch.cuda.empty_cache()
-    log(f"[bench] built .bwt/.rbwt for {genome_bp} bp on the GPU in {time.time() - t0:.1f} s")
+    log(f"[bench] built .bwt/.rbwt{'/.sa/.rsa' if with_sa else ''} for {genome_bp} bp on the GPU in {time.time() - t0:.1f} s")
     if is_writer:
         os.makedirs(d, exist_ok=True)
         bwt_dump_bwt(prefix + ".bwt", bwt)
         bwt_dump_bwt(prefix + ".rbwt", rbwt)
+        if with_sa:
+            bwt_dump_sa(prefix + ".sa", sa)
+            bwt_dump_sa(prefix + ".rsa", rsa)
+            names, lens = contig_layout(genome_bp)
+            refdata.write_pac_ann_amb(prefix, text, names, lens)
         open(done, "w").write("ok\n")
     return bwt, rbwt, text, prefix
 
 
-def write_fastq(path: str, reads: np.ndarray) -> None:
+def load_or_build_alt(text, genome_bp: int, seed: int, is_writer: bool):
+    """Config 5's ALT index: 200 contigs cut from the primary (refdata.make_alt_contigs), all index files and the
+    .remap file (bwaremap.cpp:42-132).  Returns (bwt, rbwt, alt_text uint8 numpy, alt_lens, prefix)."""
+    from ibwa_b200 import refdata
+    from ibwa_b200.bwtio import bwt_restore_bwt
+    d = cache_dir(genome_bp, seed)
+    prefix = os.path.join(d, "alt")
+    names, lens = contig_layout(genome_bp)
+    alt_text, a_names, a_lens, remap = refdata.make_alt_contigs(
+        lambda lo, hi: text[lo:hi].cpu().numpy(), names, lens, 200, 20260105)
+    if not os.path.exists(prefix + ".DONE"):
+        if is_writer:
+            os.makedirs(d, exist_ok=True)
+            refdata.write_index(prefix, alt_text, a_names, a_lens)
+            open(prefix + ".remap", "w").write(remap)
+            open(prefix + ".DONE", "w").write("ok\n")
+    return bwt_restore_bwt(prefix + ".bwt"), bwt_restore_bwt(prefix + ".rbwt"), alt_text, a_lens, prefix
+
+
+def write_fastq(path: str, reads: np.ndarray, name_fmt: bytes = b"@r%d\n") -> None:
     nt = np.frombuffer(b"ACGTN-", dtype=np.uint8)
     n, L = reads.shape
-    width = len(f"@r{n}") + 1
+    tail = b"\n+\n" + b"I" * L + b"\n"
     with open(path, "wb") as f:
         CH = 200000
         for s in range(0, n, CH):
-            blk = reads[s:s + CH]
-            lines = []
-            seqs = nt[blk]
-            for i in range(len(blk)):
-                lines.append(b"@r%d\n" % (s + i) + seqs[i].tobytes() + b"\n+\n" + b"I" * L + b"\n")
-            f.write(b"".join(lines))
-    del width
+            seqs = nt[reads[s:s + CH]]
+            f.write(b"".join(name_fmt % (s + i) + seqs[i].tobytes() + tail for i in range(len(seqs))))
 
 
 # -------------------------------------------------------------- clocks -------
@@ -235,34 +277,53 @@ class ClockSampler(threading.Thread):
 
 # ------------------------------------------------------ reference (CPU) ------
 
-def time_reference(prefix: str, reads: np.ndarray, threads: int, work_dir: str, target_s: float = 15.0,
-                   max_reads: int = 2_000_000, aln_args=()):
-    """Times `ibwa aln -t threads` on a bounded sample; returns dict(reads/s, sample, sai path, ...)."""
+def _ref_aln(prefix, fq, out, threads, aln_args):
+    t0 = time.perf_counter()
+    with open(out, "wb") as fo:
+        subprocess.run([REF_BIN, "aln", "-t", str(threads)] + list(aln_args) + [prefix, fq], stdout=fo,
+                       stderr=subprocess.DEVNULL, check=True)
+    return time.perf_counter() - t0
+
+
+def time_reference(streams, threads: int, work_dir: str, target_s: float = 15.0, max_reads: int = 2_000_000,
+                   aln_args=(), tag: str = "sample"):
+    """Times `ibwa aln -t threads` on a bounded sample of every stream of the workload.
+    streams: list of dict(prefix=, reads=ndarray[n, L], name_fmt=bytes, first=bool) — `first` marks the streams
+    that carry distinct reads (cfg 5 aligns the same reads against two indexes: they count once).
+    Returns reads/s (distinct reads / summed wall minus index load), the sample size and the .sai / .fq paths."""
     os.makedirs(work_dir, exist_ok=True)
     empty = os.path.join(work_dir, "empty.fq")
     open(empty, "w").close()
-
-    def run(fq, out):
-        t0 = time.perf_counter()
-        with open(out, "wb") as fo:
-            subprocess.run([REF_BIN, "aln", "-t", str(threads)] + list(aln_args) + [prefix, fq], stdout=fo,
-                           stderr=subprocess.DEVNULL, check=True)
-        return time.perf_counter() - t0
-
-    run(empty, os.path.join(work_dir, "empty.sai"))          # page cache warm
-    t_load = run(empty, os.path.join(work_dir, "empty.sai"))
-    n0 = min(len(reads), 20000)
+    loads = {}
+    for st in streams:
+        if st["prefix"] not in loads:
+            _ref_aln(st["prefix"], empty, os.path.join(work_dir, "empty.sai"), threads, aln_args)   # page cache warm
+            loads[st["prefix"]] = _ref_aln(st["prefix"], empty, os.path.join(work_dir, "empty.sai"), threads, aln_args)
+    s0 = streams[0]
+    n_all = len(s0["reads"])
+    n0 = min(n_all, 20000)
     fq0 = os.path.join(work_dir, "probe.fq")
-    write_fastq(fq0, reads[:n0])
-    t_probe = run(fq0, os.path.join(work_dir, "probe.sai"))
-    rate = n0 / max(t_probe - t_load, 1e-3)
-    n1 = int(min(len(reads), max_reads, max(n0, rate * target_s)))
-    fq1 = os.path.join(work_dir, "sample.fq")
-    write_fastq(fq1, reads[:n1])
-    sai1 = os.path.join(work_dir, "sample.sai")
-    t1 = run(fq1, sai1)
-    return {"reads_per_s": n1 / max(t1 - t_load, 1e-3), "n": n1, "wall_s": t1, "index_load_s": t_load,
-            "threads": threads, "sai": sai1, "fq": fq1}
+    write_fastq(fq0, s0["reads"][:n0], s0["name_fmt"])
+    t_probe = _ref_aln(s0["prefix"], fq0, os.path.join(work_dir, "probe.sai"), threads, aln_args)
+    rate = n0 / max(t_probe - loads[s0["prefix"]], 1e-3)
+    n1 = int(min(n_all, max_reads, max(n0, rate * target_s / len(streams))))
+    wall = net = 0.0
+    sais, fqs = [], []
+    for i, st in enumerate(streams):
+        fq = os.path.join(work_dir, f"{tag}_{i}.fq")
+        if st.get("fq_of") is not None:
+            fq = fqs[st["fq_of"]]                                   # same reads, another index
+        else:
+            write_fastq(fq, st["reads"][:n1], st["name_fmt"])
+        sai_path = os.path.join(work_dir, f"{tag}_{i}.sai")
+        t = _ref_aln(st["prefix"], fq, sai_path, threads, aln_args)
+        wall += t
+        net += t - loads[st["prefix"]]
+        sais.append(sai_path)
+        fqs.append(fq)
+    distinct = n1 * sum(1 for st in streams if st.get("first", True))
+    return {"reads_per_s": distinct / max(net, 1e-3), "n": n1, "distinct_reads": distinct, "wall_s": wall,
+            "index_load_s": sum(loads.values()), "threads": threads, "sais": sais, "fqs": fqs}
 
 
 def time_port(bwt, rbwt, reads: np.ndarray, opt, n: int = 3000):
@@ -281,6 +342,23 @@ def time_port(bwt, rbwt, reads: np.ndarray, opt, n: int = 3000):
 
 # ----------------------------------------------------------------- main ------
 
+CONFIGS = {
+    1: dict(genome_bp=5_000_000, reads=100_000, read_len=100, model="default", aln_args="", pairs=False, alt=False,
+            seed=20260101, name="configs[0]: 100 k x 100 bp vs 5 Mbp, defaults"),
+    2: dict(genome_bp=3_100_000_000, reads=10_000_000, read_len=100, model="default", aln_args="", pairs=False,
+            alt=False, seed=20260102, name="configs[1]: 10 M x 100 bp vs 3.1 Gbp, defaults"),
+    3: dict(genome_bp=3_100_000_000, reads=2_000_000, read_len=150, model="stress",
+            aln_args="-n 4 -o 2 -e 10 -l 32 -k 2", pairs=False, alt=False, seed=20260102,
+            name="configs[2]: gapped stress, 150 bp, 2 % substitutions + indels vs 3.1 Gbp"),
+    4: dict(genome_bp=3_100_000_000, reads=10_000_000, read_len=100, model="default", aln_args="", pairs=True,
+            alt=False, seed=20260102, name="configs[3]: paired end 2 x 5 M x 100 bp vs 3.1 Gbp, .sai -> sampe -R"),
+    5: dict(genome_bp=3_100_000_000, reads=10_000_000, read_len=100, model="default", aln_args="", pairs=True,
+            alt=True, seed=20260102,
+            name="configs[4]: dbset primary 3.1 Gbp + 200 ALT contigs (.remap), 2 x 5 M x 100 bp, 25 % of pairs from ALT"),
+}
+METRIC = "bwa aln reads/sec (100bp, 3.1Gbp ref)"
+
+
 def _claim_stdout():
     """Libraries (NCCL's version banner, for one) print to stdout; the contract is ONE JSON line there.
     Keep the real stdout for that line and send everything else written to fd 1 to stderr."""
@@ -290,6 +368,24 @@ def _claim_stdout():
     return os.fdopen(real, "w", buffering=1)
 
 
+def _md5(path):
+    h = hashlib.md5()
+    with open(path, "rb") as f:
+        for blk in iter(lambda: f.read(1 << 22), b""):
+            h.update(blk)
+    return h.hexdigest()
+
+
+def _sampe(pri, sais_pri, fqs, alt, sais_alt, out, threads):
+    cmd = [REF_BIN, "sampe", "-R", "-t", str(threads), pri, sais_pri[0], sais_pri[1], fqs[0], fqs[1]]
+    if alt:
+        cmd += [alt, sais_alt[0], sais_alt[1]]
+    t0 = time.perf_counter()
+    with open(out, "wb") as fo:
+        subprocess.run(cmd, stdout=fo, stderr=subprocess.DEVNULL, check=True)
+    return time.perf_counter() - t0
+
+
 def main():
     json_out = _claim_stdout()
     ap = argparse.ArgumentParser()
@@ -297,18 +393,26 @@ def main():
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--genome-bp", type=int, default=3_100_000_000)
-    ap.add_argument("--reads", type=int, default=10_000_000, help="reads per GPU per step")
-    ap.add_argument("--read-len", type=int, default=100)
-    ap.add_argument("--seed", type=int, default=20260102)
+    ap.add_argument("--config", type=int, default=2, choices=sorted(CONFIGS), help="BASELINE.json configs, from 1")
+    ap.add_argument("--scaling", default="strong", choices=["strong", "weak"],
+                    help="strong: --reads per step in total, sharded over the ranks; weak: --reads per rank")
+    ap.add_argument("--genome-bp", type=int, default=None)
+    ap.add_argument("--reads", type=int, default=None, help="reads per step (strong: all ranks together)")
+    ap.add_argument("--read-len", type=int, default=None)
+    ap.add_argument("--seed", type=int, default=None)
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--model", default="default", choices=["default", "stress"],
-                    help="read model (SURVEY §8d); 'stress' + --read-len 150 + --aln-args = BASELINE configs[2]")
-    ap.add_argument("--aln-args", default="", help="aln options for the run, e.g. '-n 4 -o 2 -e 10 -l 32 -k 2'")
+    ap.add_argument("--model", default=None, choices=["default", "stress"], help="read model (SURVEY 8d)")
+    ap.add_argument("--aln-args", default=None, help="aln options for the run, e.g. '-n 4 -o 2 -e 10 -l 32 -k 2'")
     ap.add_argument("--in-flight", type=int, default=3,
-                    help="batches in flight in the e2e measurement (contexts sharing the device index)")
+                    help="steps in flight (contexts sharing the device index) in the value / e2e measurements")
+    ap.add_argument("--parity-pairs", type=int, default=200_000, help="configs 4/5: pairs through sampe -R")
     ap.add_argument("--set", action="append", default=[], help="engine knob key=value")
     args = ap.parse_args()
+    cfg = dict(CONFIGS[args.config])
+    for k in ("genome_bp", "reads", "read_len", "seed", "model", "aln_args"):
+        v = getattr(args, k)
+        if v is not None:
+            cfg[k] = v
 
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -331,64 +435,101 @@ def main():
     if use_dist:
         dist.init_process_group("nccl", device_id=dev)
 
-    from ibwa_b200 import engine, gap_init_opt
+    from ibwa_b200 import engine, gap_init_opt, refdata, sai
+    from ibwa_b200.shard import shard_range
 
     opt = gap_init_opt()
-    aln_args = args.aln_args.split()
+    aln_args = cfg["aln_args"].split()
     if aln_args:
         from ibwa_b200 import parse_aln_args
         opt, _, _, _ = parse_aln_args(aln_args + ["prefix", "reads"])
-    workload = (f"bwa aln {args.reads} simulated {args.read_len}bp reads/GPU ({args.model} model) vs "
-                f"{args.genome_bp / 1e9:.2f} Gbp synthetic genome, {args.aln_args or 'defaults (-n 0.04)'}, "
-                f"index replicated")
-    config = {"workload": workload, "genome_bp": args.genome_bp, "reads_per_gpu": args.reads,
-              "read_len": args.read_len, "parallelism": f"replicated index, reads sharded x{world}",
+    L = cfg["read_len"]
+    n_step = cfg["reads"]                         # distinct reads of one step, all ranks (strong) / this rank (weak)
+    if cfg["pairs"]:
+        n_step -= n_step % 2
+    weak = args.scaling == "weak" and world > 1
+    unit = 2 if cfg["pairs"] else 1               # sharding unit: a read, or a pair (mates stay together)
+    lo, hi = (0, n_step // unit) if weak or world == 1 else shard_range(n_step // unit, world, rank)
+    config = {"workload": f"{cfg['name']} [{cfg['aln_args'] or 'defaults (-n 0.04)'}; {cfg['model']} read model; "
+                          f"{n_step} reads per step {'per GPU' if weak else 'in total'}; index replicated]",
+              "config_no": args.config, "genome_bp": cfg["genome_bp"], "reads_per_step": n_step,
+              "reads_per_gpu_per_step": (hi - lo) * unit, "read_len": L,
+              "parallelism": f"replicated index, reads sharded x{world} ({'weak' if weak else 'strong'}), no collective",
               "l2": "inputs larger than L2 (index 3.1 GB + per-read state); no flush"}
 
     # ---- inputs -----------------------------------------------------------
     t_setup = time.time()
+    need_sa = cfg["pairs"] and os.path.exists(REF_BIN) and world == 1 and args.impl == "ours" and not args.no_cpu_baseline
     if use_dist and local_rank != 0:
         dist.barrier()                      # rank 0 builds and writes the cache first
-    bwt, rbwt, text, prefix = load_or_build_index(args.genome_bp, args.seed, dev, is_writer=(local_rank == 0))
+    bwt, rbwt, text, prefix = load_or_build_index(cfg["genome_bp"], cfg["seed"], dev, is_writer=(local_rank == 0),
+                                                  with_sa=need_sa)
+    alt = None
+    if cfg["alt"]:
+        a_bwt, a_rbwt, alt_text, alt_lens, alt_prefix = load_or_build_alt(text, cfg["genome_bp"], cfg["seed"],
+                                                                          is_writer=(local_rank == 0))
+        alt = dict(bwt=a_bwt, rbwt=a_rbwt, prefix=alt_prefix)
     if use_dist and local_rank == 0:
         dist.barrier()
-    synth_fn = synth_reads_torch if args.model == "default" else synth_stress_reads_torch
-    reads_d = synth_fn(text, args.reads, args.read_len, args.seed + 1000 + rank)
+    rseed = cfg["seed"] + 1000 + (rank if weak else 0)
+    if cfg["pairs"]:
+        n_pairs = n_step // 2
+        kw = {}
+        if cfg["alt"]:
+            kw = dict(alt_text=torch.from_numpy(alt_text).to(dev), alt_lens=alt_lens, alt_frac=0.25)
+        r1, r2 = refdata.synth_pairs(text, n_pairs, L, rseed, **kw)
+        sets = [r1[lo:hi].contiguous(), r2[lo:hi].contiguous()]
+        del r1, r2
+        fmts = [b"@p%d/1\n", b"@p%d/2\n"]
+    else:
+        synth_fn = synth_reads_torch if cfg["model"] == "default" else synth_stress_reads_torch
+        allr = synth_fn(text, n_step, L, rseed)
+        sets = [allr[lo:hi].contiguous()]
+        del allr
+        fmts = [b"@r%d\n"]
     del text
     torch.cuda.empty_cache()
-    log(f"[bench r{rank}] inputs ready in {time.time() - t_setup:.1f} s")
+    # streams of one step: (index, read set)
+    streams = [("pri", i) for i in range(len(sets))] + ([("alt", i) for i in range(len(sets))] if alt else [])
+    n_rank = sum(int(s.shape[0]) for s in sets)   # distinct reads this rank aligns per step
+    log(f"[bench r{rank}] inputs ready in {time.time() - t_setup:.1f} s ({n_rank} reads per step on this rank)")
 
     nproc = os.cpu_count() or 1
-    work_dir = os.path.join(cache_dir(args.genome_bp, args.seed), f"work_r{rank}")
+    work_dir = os.path.join(cache_dir(cfg["genome_bp"], cfg["seed"]), f"work_c{args.config}_r{rank}")
+
+    def ref_streams(samples):
+        out = [dict(prefix=prefix, reads=s, name_fmt=f, first=True) for s, f in zip(samples, fmts)]
+        if alt:
+            out += [dict(prefix=alt["prefix"], reads=s, name_fmt=f, first=False, fq_of=i)
+                    for i, (s, f) in enumerate(zip(samples, fmts))]
+        return out
 
     # ---- reference arm ------------------------------------------------------
     if args.impl == "reference":
-        sample_h = reads_d[: min(args.reads, 2_000_000)].cpu().numpy()
-        del reads_d
+        samples = [s[: min(int(s.shape[0]), 2_000_000)].cpu().numpy() for s in sets]
+        del sets
         torch.cuda.empty_cache()
         if os.path.exists(REF_BIN):
             kind = "reference"
             vals = []
             res = None
             for i in range(args.warmup + args.steps):
-                res = time_reference(prefix, sample_h, nproc, work_dir, target_s=8.0, aln_args=aln_args)
+                res = time_reference(ref_streams(samples), nproc, work_dir, target_s=8.0, aln_args=aln_args)
                 if i >= args.warmup:
                     vals.append(res["reads_per_s"])
-                if i == 0 and args.warmup > 1:
-                    pass
             v = float(np.mean(vals))
-            sample = (f"{res['n']} of the workload's reads per step, `ibwa aln -t {nproc}`, wall minus "
-                      f"{res['index_load_s']:.2f} s index load")
-            ms = 1e3 * res["n"] / v
+            sample = (f"{res['distinct_reads']} of the workload's reads per step ({len(streams)} `ibwa aln -t {nproc}` "
+                      f"runs), wall minus {res['index_load_s']:.2f} s index load")
+            ms = 1e3 * res["distinct_reads"] / v
         else:
             kind = "port"
-            pr = time_port(bwt, rbwt, sample_h, opt, n=5000)
+            pr = time_port(bwt, rbwt, samples[0], opt, n=5000)
             v, nproc, ms = pr["reads_per_s"], 1, 1e3 * pr["n"] / pr["reads_per_s"]
             sample = f"{pr['n']} reads, single-thread CPU restatement (oracle port)"
-        line = {"metric": "bwa aln reads/sec (100bp, 3.1Gbp ref)", "value": v, "unit": "reads/s", "n_gpus": args.gpus,
+        line = {"metric": METRIC, "value": v, "unit": "reads/s", "n_gpus": args.gpus,
                 "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True,
-                "scaling": "weak", "vs_baseline": None, "dtype": "u32", "data": "synthetic", "config": config,
-                "impl": "reference",
+                "scaling": "weak" if weak else "strong", "vs_baseline": None, "dtype": "u32", "data": "synthetic",
+                "config": config, "impl": "reference",
                 "cpu_baseline": {"value": v, "unit": "reads/s", "cores": nproc, "kind": kind, "sample": sample},
                 "e2e": {"value": v, "unit": "reads/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
                 "gpu_launches": 0}
@@ -396,20 +537,32 @@ def main():
         return 0
 
     # ---- our arm ------------------------------------------------------------
+    K = max(1, args.in_flight)
     eng = engine.Engine(bwt, rbwt, local_rank)
-    for kv in args.set:
-        k, v = kv.split("=")
+    knobs = [kv.split("=") for kv in args.set]
+    for k, v in knobs:
         eng.set(k, int(v))
-    n, L = args.reads, args.read_len
-    d_lens = torch.full((n,), L, dtype=torch.int32, device=dev)
-    d_offs = torch.arange(n, dtype=torch.int64, device=dev) * L
-    d_codes = reads_d.reshape(-1)
-    # pinned host copies for the end-to-end path
-    h_lens = torch.full((n,), L, dtype=torch.int32).pin_memory()
-    h_offs = (torch.arange(n, dtype=torch.int64) * L).pin_memory()
-    h_codes = torch.empty(n * L, dtype=torch.uint8).pin_memory()
-    h_codes.copy_(d_codes)
-    h_naln = torch.empty(n, dtype=torch.int32).pin_memory()
+    eng.set("slots", 1)                     # steps in flight come from the clones below, not from chunks of a call
+    engs = {"pri": [eng] + [eng.clone() for _ in range(K - 1)]}
+    if alt:
+        a_eng = engine.Engine(alt["bwt"], alt["rbwt"], local_rank)
+        for k, v in knobs:
+            a_eng.set(k, int(v))
+        a_eng.set("slots", 1)
+        engs["alt"] = [a_eng] + [a_eng.clone() for _ in range(K - 1)]
+
+    dsets, hsets = [], []
+    for s in sets:
+        n = int(s.shape[0])
+        d = dict(n=n, lens=torch.full((n,), L, dtype=torch.int32, device=dev),
+                 offs=torch.arange(n, dtype=torch.int64, device=dev) * L, codes=s.reshape(-1))
+        h = dict(lens=torch.full((n,), L, dtype=torch.int32).pin_memory(),
+                 offs=(torch.arange(n, dtype=torch.int64) * L).pin_memory(),
+                 codes=torch.empty(n * L, dtype=torch.uint8).pin_memory())
+        h["codes"].copy_(d["codes"])
+        dsets.append(d)
+        hsets.append(h)
+    h_out = [[torch.empty(dsets[i]["n"], dtype=torch.int32).pin_memory() for (_, i) in streams] for _ in range(K)]
     torch.cuda.synchronize()
 
     def barrier():
@@ -418,35 +571,46 @@ def main():
             dist.barrier()
             torch.cuda.synchronize()
 
-    def step_device():
-        eng.batch_device(d_lens.data_ptr(), d_offs.data_ptr(), d_codes.data_ptr(), n, L, opt)
-        return eng.stats()
+    def step_device(w=0):
+        out = []
+        for (ix, i) in streams:
+            d = dsets[i]
+            e = engs[ix][w]
+            if d["n"]:
+                e.batch_device(d["lens"].data_ptr(), d["offs"].data_ptr(), d["codes"].data_ptr(), d["n"], L, opt)
+            out.append(e.stats())
+        return out
 
-    # end-to-end: --in-flight batches in flight (engine + clones sharing the device index, one host thread each),
-    # so the H2D / D2H copies of one step overlap the kernels of the other (double buffering)
-    K = max(1, args.in_flight)
-    engines = [eng] + [eng.clone() for _ in range(K - 1)]
-    outs = [h_naln] + [torch.empty(n, dtype=torch.int32).pin_memory() for _ in range(K - 1)]
+    def step_e2e(w=0):
+        out = []
+        for j, (ix, i) in enumerate(streams):
+            h = hsets[i]
+            e = engs[ix][w]
+            total = 0
+            if dsets[i]["n"]:
+                _, total = e.batch_pinned(h["lens"].data_ptr(), h["offs"].data_ptr(), h["codes"].data_ptr(),
+                                          dsets[i]["n"], opt, h_out[w][j].data_ptr())
+            out.append((total, e.stats()))
+        return out
 
-    def step_e2e(which=0):
-        e, out = engines[which], outs[which]
-        _, total = e.batch_pinned(h_lens.data_ptr(), h_offs.data_ptr(), h_codes.data_ptr(), n, opt, out.data_ptr())
-        return total, e.stats()
-
-    def timed_e2e(steps):
+    def timed(fn, steps, k):
+        """`steps` steps, k in flight (host thread w runs steps w, w + k, ...); ms by CUDA events, max over ranks"""
         results = [None] * steps
 
-        def worker(which):
-            for i in range(which, steps, K):
-                results[i] = step_e2e(which)
+        def worker(w):
+            for i in range(w, steps, k):
+                results[i] = fn(w)
 
         barrier()
         eng.timer_start()
-        th = [threading.Thread(target=worker, args=(w,)) for w in range(K)]
-        for t in th:
-            t.start()
-        for t in th:
-            t.join()
+        if k == 1:
+            worker(0)
+        else:
+            th = [threading.Thread(target=worker, args=(w,)) for w in range(k)]
+            for t in th:
+                t.start()
+            for t in th:
+                t.join()
         ms = eng.timer_stop()
         barrier()
         if use_dist:
@@ -455,125 +619,162 @@ def main():
             ms = float(t.item())
         return ms, results
 
-    def timed(fn, steps):
-        barrier()
-        eng.timer_start()
-        stats = []
-        for _ in range(steps):
-            stats.append(fn())
-        ms = eng.timer_stop()
-        barrier()
-        if use_dist:
-            t = torch.tensor([ms], dtype=torch.float64, device=dev)
-            dist.all_reduce(t, op=dist.ReduceOp.MAX)
-            ms = float(t.item())
-        return ms, stats
-
-    for _ in range(args.warmup):
-        step_device()
+    for w in range(K):                      # every context allocates its buffers outside the timed regions
+        for _ in range(max(1, (args.warmup + K - 1) // K)):
+            step_device(w)
     sampler = ClockSampler(local_rank)
     sampler.start()
-    ms_dev, st_dev = timed(step_device, args.steps)
+    ms_seq, st_seq = timed(step_device, args.steps, 1)
+    ms_dev, _ = timed(step_device, args.steps, K) if K > 1 else (ms_seq, None)
     clocks = sampler.stop()
-    for w in range(K):          # every in-flight engine allocates its buffers outside the timed region
+    for w in range(K):
         step_e2e(w)
-    ms_e2e, st_e2e = timed_e2e(args.steps)
+    ms_e2e, st_e2e = timed(step_e2e, args.steps, K)
 
-    eng.set("count", 1)         # one untimed step with the pop / sector counters compiled in
-    counted = step_device()
-    eng.set("count", 0)
+    for e in engs["pri"][:1]:
+        e.set("count", 1)                   # one untimed step with the pop / sector counters compiled in
+    counted = step_device(0)
+    engs["pri"][0].set("count", 0)
 
-    total_reads = world * n * args.steps
+    n_glob = (world * n_rank) if weak else n_step          # distinct reads of one step, all ranks
+    total_reads = n_glob * args.steps
     value = total_reads / (ms_dev * 1e-3)
     e2e_value = total_reads / (ms_e2e * 1e-3)
-    last = st_dev[-1]
-    total_rec = st_e2e[-1][0]
-    launches = int(sum(s["kernel_launches"] for s in st_dev))
+    total_rec = sum(t for (t, _) in st_e2e[-1])
+    launches = int(sum(s["kernel_launches"] for step in st_seq for s in step))
+    pri_ix = [j for j, (ix, _) in enumerate(streams) if ix == "pri"]
+    n_pri = sum(dsets[i]["n"] for (ix, i) in streams if ix == "pri")
 
-    out = {"metric": "bwa aln reads/sec (100bp, 3.1Gbp ref)", "value": value, "unit": "reads/s", "n_gpus": world,
+    def kms(key):                           # per step: summed over the step's streams
+        return [float(sum(s[key] for s in step)) for step in st_seq]
+
+    step_ms = kms("ms_total")
+    h2d = int(sum((12 + L) * dsets[i]["n"] for (_, i) in streams))
+    out = {"metric": METRIC, "value": value, "unit": "reads/s", "n_gpus": world,
            "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_dev / args.steps,
-           "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u32", "data": "synthetic",
-           "config": config, "clocks": clocks,
-           "e2e": {"value": e2e_value, "unit": "reads/s", "h2d_bytes_per_step": int(n * 12 + n * L),
-                   "d2h_bytes_per_step": int(n * 4 + total_rec * 16), "ms_per_step": ms_e2e / args.steps,
-                   "in_flight": K},
+           "higher_is_better": True, "scaling": "weak" if weak else "strong", "vs_baseline": None, "dtype": "u32",
+           "data": "synthetic", "config": config, "clocks": clocks, "in_flight": K,
+           "sequential": {"value": total_reads / (ms_seq * 1e-3), "ms_per_step": ms_seq / args.steps,
+                          "best_step_ms": float(np.min(step_ms)), "median_step_ms": float(np.median(step_ms)),
+                          "note": "the same steps one at a time on one context (rank 0's device times)"},
+           "e2e": {"value": e2e_value, "unit": "reads/s", "h2d_bytes_per_step": h2d,
+                   "d2h_bytes_per_step": int(4 * sum(dsets[i]["n"] for (_, i) in streams) + total_rec * 16),
+                   "ms_per_step": ms_e2e / args.steps, "in_flight": K},
            "gpu_launches": launches,
-           "kernel_ms": {k: float(np.mean([s[k] for s in st_dev])) for k in
-                         ("ms_width", "ms_search", "ms_compact", "ms_total")},
-           "overflow_reads_per_step": int(last["overflow_reads"]),
-           "device_pops_per_read": counted["pops"] / n, "device_sectors_per_read": counted["occ_lookups"] / n}
+           "kernel_ms": {k: float(np.mean(kms(k))) for k in ("ms_width", "ms_search", "ms_compact", "ms_total")},
+           "overflow_reads_per_step": int(sum(s["overflow_reads"] for s in st_seq[-1])),
+           "device_pops_per_read": sum(counted[j]["pops"] for j in pri_ix) / max(n_pri, 1),
+           "device_sectors_per_read": sum(counted[j]["occ_lookups"] for j in pri_ix) / max(n_pri, 1)}
 
+    ok = True
     if rank == 0:
         # roofline: algorithmic bytes = 32 B x occ lookups of the REFERENCE algorithm (oracle-counted on a sample)
-        sample_h = reads_d[: min(n, 2_000_000)].cpu().numpy()
-        port = time_port(bwt, rbwt, sample_h, opt, n=3000)
+        samples = [s[: min(int(s.shape[0]), 2_000_000)].cpu().numpy() for s in sets]
+        port = time_port(bwt, rbwt, samples[0], opt, n=3000)
         lookups_per_read = port["stats"]["lookups"] / port["n"]
         bytes_per_read = 32.0 * lookups_per_read
-        ms_search = out["kernel_ms"]["ms_search"]
-        achieved = bytes_per_read * n / (ms_search * 1e-3) / 1e9
+        ms_search = float(np.mean([sum(step[j]["ms_search"] for j in pri_ix) for step in st_seq]))
+        achieved = bytes_per_read * n_pri / (ms_search * 1e-3) / 1e9
         peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
         if os.path.exists(peaks_path):
             peak, which = float(json.load(open(peaks_path))["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
         else:
             peak, which = 6650.0, "fallback (B200_PROFILING.md)"
-        traffic = None                      # DRAM bytes of the dominant kernel per launch, from the committed ncu capture
-        tpath = os.path.join(ROOT, "profiles", "r1_traffic.json")
+        traffic = traffic_src = None        # DRAM bytes of the dominant kernel per launch, from the committed ncu capture
+        tpath = os.path.join(ROOT, "profiles", "r2_traffic.json")
         if os.path.exists(tpath):
-            traffic = float(json.load(open(tpath))["k_search"]["dram_bytes_per_read"]) * n
+            tj = json.load(open(tpath)).get(f"config{args.config}")
+            if tj:
+                traffic = float(tj["k_search"]["dram_bytes_per_read"]) * n_pri
+                traffic_src = (f"profiles/r2_traffic.json: ncu dram__bytes_read+write of k_search per read, captured "
+                               f"at {tj['capture_reads']} reads per launch, x the reads of this launch")
         sector_roof = eng.sector_roofline(1 << 28, 3)
         pair_roof = eng.sector_roofline(1 << 27, -3)
         out["roofline"] = {"bound": "hbm", "kernel": "k_search", "achieved": achieved, "peak": peak, "unit": "GB/s",
                            "frac": achieved / peak, "traffic": traffic, "peak_source": which,
-                           "traffic_source": "profiles/r1_traffic.json (ncu dram__bytes_read+write per read x reads)",
-                           "algorithmic_bytes": bytes_per_read * n,
+                           "traffic_source": traffic_src,
+                           "algorithmic_bytes": bytes_per_read * n_pri,
                            "algorithmic_bytes_per_read": bytes_per_read,
                            "oracle_lookups_per_read": lookups_per_read,
                            "oracle_pops_per_read": port["stats"]["pops"] / port["n"],
+                           "kernel_ms_per_launch": ms_search, "reads_per_launch": n_pri,
                            "random_sector_roof_gbs": sector_roof, "random_64B_pair_roof_gbs": pair_roof,
+                           "random_sector_roof_note": "k_sector_gather over BOTH device indexes (3.1 GB)",
                            "frac_of_random_sector_roof": achieved / sector_roof if sector_roof else None,
-                           "occ_sectors_per_s": counted["occ_lookups"] / (ms_search * 1e-3)}
-        if traffic and sector_roof:
-            # the memory system's limit for this access pattern is a transaction rate: DRAM moves the
-            # kernel's traffic in 64-byte transactions; the gather roof counts random 32-byte requests per second
-            tx = traffic / 64.0
-            out["roofline"]["dram_transactions_per_read"] = tx / n
-            out["roofline"]["dram_transactions_per_s"] = tx / (ms_search * 1e-3)
-            out["roofline"]["random_requests_roof_per_s"] = sector_roof * 1e9 / 32.0
-            out["roofline"]["frac_of_transaction_roof"] = (tx / (ms_search * 1e-3)) / (sector_roof * 1e9 / 32.0)
+                           "occ_sectors_per_s": sum(counted[j]["occ_lookups"] for j in pri_ix) / (ms_search * 1e-3)}
         # parity of this very run against the oracle port on the sample
         m = port["n"]
         n_aln_d, rec_d = eng.cal_sa_reg_gap(np.full(m, L, np.int32), np.arange(m, dtype=np.int64) * L,
-                                            sample_h[:m].reshape(-1), opt)
+                                            samples[0][:m].reshape(-1), opt)
         parity = {"oracle_port_reads": m,
                   "oracle_port_identical": bool(np.array_equal(n_aln_d, port["n_aln"]) and
                                                 rec_d.tobytes() == port["rec"].tobytes())}
+        ok = parity["oracle_port_identical"]
         if world == 1 and not args.no_cpu_baseline:
             if os.path.exists(REF_BIN):
-                res = time_reference(prefix, sample_h, nproc, work_dir, target_s=15.0, aln_args=aln_args)
+                cap = args.parity_pairs if cfg["pairs"] else 2_000_000
+                res = time_reference(ref_streams(samples), nproc, work_dir, target_s=15.0, max_reads=cap,
+                                     aln_args=aln_args)
                 out["cpu_baseline"] = {"value": res["reads_per_s"], "unit": "reads/s", "cores": nproc,
                                        "kind": "reference",
-                                       "sample": f"{res['n']} reads of the workload, `ibwa aln -t {nproc}`, wall "
-                                                 f"{res['wall_s']:.2f} s minus {res['index_load_s']:.2f} s index load"}
-                from ibwa_b200 import sai
-                _, r_n, r_rec = sai.read_sai(res["sai"])
-                r_n = r_n[:res["n"]]
+                                       "sample": f"{res['distinct_reads']} reads of the workload, {len(streams)} x "
+                                                 f"`ibwa aln -t {nproc}`, wall {res['wall_s']:.2f} s minus "
+                                                 f"{res['index_load_s']:.2f} s index load"}
+                t1 = time_reference(ref_streams(samples)[:1], 1, work_dir, target_s=6.0, max_reads=200_000,
+                                    aln_args=aln_args, tag="t1")
+                out["cpu_baseline"]["t1_value"] = t1["reads_per_s"]
+                out["cpu_baseline"]["t1_sample"] = f"{t1['n']} reads, `ibwa aln -t 1`"
+                out["cpu_baseline"]["ideal_all_core_bound"] = t1["reads_per_s"] * nproc
                 k = res["n"]
-                g_n, g_rec = eng.cal_sa_reg_gap(np.full(k, L, np.int32), np.arange(k, dtype=np.int64) * L,
-                                                sample_h[:k].reshape(-1), opt)
-                parity["reference_binary_reads"] = k
-                parity["reference_binary_identical"] = bool(np.array_equal(g_n, r_n) and
-                                                            g_rec.tobytes() == r_rec.tobytes())
+                same = True
+                eng_sais = []
+                for j, (ix, i) in enumerate(streams):
+                    e = engs[ix][0]
+                    g_n, g_rec = e.cal_sa_reg_gap(np.full(k, L, np.int32), np.arange(k, dtype=np.int64) * L,
+                                                  samples[i][:k].reshape(-1), opt)
+                    _, r_n, r_rec = sai.read_sai(res["sais"][j])
+                    same = same and bool(np.array_equal(g_n, r_n[:k]) and g_rec.tobytes() == r_rec.tobytes())
+                    if cfg["pairs"]:
+                        p = os.path.join(work_dir, f"engine_{j}.sai")
+                        with open(p, "wb") as f:
+                            sai.write_header(f, opt)
+                            sai.write_batch(f, g_n, g_rec)
+                        eng_sais.append(p)
+                parity["reference_binary_reads"] = k * len(streams)
+                parity["reference_binary_identical"] = same
+                ok = ok and same
+                if cfg["pairs"]:            # downstream: the unchanged `sampe -R` on engine vs reference .sai
+                    np_ = len(sets)
+                    sam_e, sam_r = os.path.join(work_dir, "engine.sam"), os.path.join(work_dir, "reference.sam")
+                    t_s = _sampe(prefix, eng_sais[:np_], res["fqs"][:np_], alt["prefix"] if alt else None,
+                                 eng_sais[np_:], sam_e, nproc)
+                    _sampe(prefix, res["sais"][:np_], res["fqs"][:np_], alt["prefix"] if alt else None,
+                           res["sais"][np_:], sam_r, nproc)
+                    md_e, md_r = _md5(sam_e), _md5(sam_r)
+                    body = [ln for ln in open(sam_e, "rb") if not ln.startswith(b"@")]
+                    parity["sampe"] = {"pairs": k, "sam_lines": len(body), "sam_md5_engine": md_e,
+                                       "sam_md5_reference": md_r, "sam_identical": md_e == md_r,
+                                       "mapped": sum(1 for ln in body if not int(ln.split(b"\t")[1]) & 4),
+                                       "zr_tags": sum(1 for ln in body if b"ZR:Z" in ln), "sampe_wall_s": t_s,
+                                       "command": "ibwa sampe -R -t N <pri> e1.sai e2.sai r1.fq r2.fq"
+                                                  + (" <alt> a1.sai a2.sai (with <alt>.remap)" if alt else "")}
+                    ok = ok and md_e == md_r and len(body) == 2 * k
             else:
                 out["cpu_baseline"] = {"value": port["reads_per_s"], "unit": "reads/s", "cores": 1, "kind": "port",
                                        "sample": f"{port['n']} reads, single-thread oracle port"}
         out["parity"] = parity
+        if not ok:                          # a wrong result has no throughput
+            out["value"] = None
+            out["e2e"]["value"] = None
+            out["error"] = "parity failed: engine output differs from the checker's"
         print(json.dumps(out), file=json_out, flush=True)
-    for e in engines[1:]:
-        e.close()
-    eng.close()
+    for lst in engs.values():
+        for e in lst[1:]:
+            e.close()
+        lst[0].close()
     if use_dist:
         dist.destroy_process_group()
-    return 0
+    return 0 if ok else 3
 
 
 if __name__ == "__main__":

@@ -172,6 +172,26 @@ B2_D uint32_t ld_q(const uint32_t *p)
     return *p;
 #endif
 }
+B2_D uint32_t ld_q(const uint16_t *p)
+{ /* 16-bit width records (QF<16>), same cache policy */
+    uint16_t v;
+#if defined(B2_Q_EVICT_LAST) && defined(B2_L2_HINTS)
+    asm volatile("ld.global.L1::evict_last.L2::cache_hint.u16 %0, [%1], %2;" : "=h"(v) : "l"(p), "l"(pol_evict_last()) : "memory");
+#elif defined(B2_Q_EVICT_LAST)
+    asm volatile("ld.global.L1::evict_last.u16 %0, [%1];" : "=h"(v) : "l"(p) : "memory");
+#else
+    v = *p;
+#endif
+    return v;
+}
+B2_D void ld4(const uint32_t *p, uint32_t v[4])
+{ /* four consecutive words of a 16-byte aligned row piece */
+    asm volatile("ld.global.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]) : "l"(p) : "memory");
+}
+B2_D void st4(uint32_t *p, const uint32_t v[4])
+{
+    asm volatile("st.global.cg.v4.u32 [%0], {%1,%2,%3,%4};" :: "l"(p), "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]) : "memory");
+}
 B2_D void prefetch_l2(const void *p) { asm volatile("prefetch.global.L2 [%0];" :: "l"(p)); }
 B2_D void ld8(const uint32_t *p, uint32_t v[8])
 { /* eight consecutive words of a 32-byte aligned row */
@@ -185,6 +205,9 @@ B2_D int ctz32(uint32_t v) { return __ffs((int)v) - 1; }
 inline void ld8(const uint32_t *p, uint32_t v[8]) { for (int i = 0; i < 8; ++i) v[i] = p[i]; }
 inline void prefetch_l2(const void *) {}
 inline uint32_t ld_q(const uint32_t *p) { return *p; }
+inline uint32_t ld_q(const uint16_t *p) { return *p; }
+inline void ld4(const uint32_t *p, uint32_t v[4]) { for (int i = 0; i < 4; ++i) v[i] = p[i]; }
+inline void st4(uint32_t *p, const uint32_t v[4]) { for (int i = 0; i < 4; ++i) p[i] = v[i]; }
 inline void st8(uint32_t *p, const uint32_t v[8]) { for (int i = 0; i < 8; ++i) p[i] = v[i]; }
 inline OccBlk ld_blk(const OccBlk *p) { return *p; }
 inline void ld8cg(const uint32_t *p, uint32_t v[8]) { for (int i = 0; i < 8; ++i) v[i] = p[i]; }
@@ -251,7 +274,7 @@ struct SearchEnv {
     FmView fm[2]; /* fm[0] = bwt, fm[1] = rbwt */
     Params P;
     int prefetch_next; /* 1: prefetch the next pop candidate into L2 (helps when few, long reads are left) */
-    uint32_t *Q;  /* width records: row 2 * read + strand, strideQ words each (QRec) */
+    uint32_t *Q;  /* width records: row 2 * read + strand, strideQ records each (QF<32> words or QF<16> halfwords) */
     uint32_t *W;  /* widths: row 2 * read + strand, strideW words each */
     int strideQ, strideW;
     Rec *recs;    /* record slabs, rec_cap each */
@@ -261,26 +284,76 @@ struct SearchEnv {
 };
 
 /* ---- packed per-position record Q[a][j] (built by the width pass) -------- */
-/* bits 0-2 base code | 3 eq(w[j-1]==w[j]) | 4 seed eq | 5 seed active (ii>0)
- * 6-10 seed bid[ii] | 11-15 seed bid[ii-1] | 16-23 bid[j] | 24-31 bid[j-1]
- * The bid fields saturate (255 / 31); every comparison in the search is against
- * m <= max_diff resp. m_seed <= max_seed_diff, so saturation is exact as long as
- * max_diff < 255 and max_seed_diff < 31 (checked by the host).                  */
-typedef uint32_t QRec;
-B2_HD QRec q_pack(uint32_t base, uint32_t eq, uint32_t seq, uint32_t sact, uint32_t sb, uint32_t sbp, uint32_t bid,
-                  uint32_t bidp)
-{
-    return (base & 7u) | (eq & 1u) << 3 | (seq & 1u) << 4 | (sact & 1u) << 5 | (sb > 31u ? 31u : sb) << 6 |
-           (sbp > 31u ? 31u : sbp) << 11 | (bid > 255u ? 255u : bid) << 16 | (bidp > 255u ? 255u : bidp) << 24;
-}
+/* Everything the search asks about position j of a strand in one record: base code, bid[j], bid[j-1],
+ * w[j-1]==w[j], and the seed-width equivalents (bwtgap.c:155,205-213).  The bid fields saturate; every
+ * comparison in the search is against m <= max_diff resp. m_seed <= max_seed_diff, so a field that
+ * saturates above those bounds is exact.  Two formats (QF<bits>):
+ *   QF<32>  bits 0-2 base | 3 eq | 4 seed eq | 5 seed active (ii>0) | 6-10 seed bid[ii] | 11-15 seed bid[ii-1]
+ *           | 16-23 bid[j] | 24-31 bid[j-1]            exact for max_diff < 255, max_seed_diff < 31
+ *   QF<16>  bits 0-2 base | 3 eq | 4 seed eq | 5 seed active | 6-7 seed bid[ii] | 8-9 seed bid[ii-1]
+ *           | 10-12 bid[j] | 13-15 bid[j-1]            exact for max_diff < 7, max_seed_diff < 3
+ * The 16-bit records halve the per-read state the fast pass re-reads along its chains (the rows of the
+ * lanes in flight then stay in L2); the host picks the format per launch (b200aln.cu: q16_ok). */
+typedef uint32_t QRec; /* a record of either format, widened */
+template <int QB> struct QF;
+template <> struct QF<32> {
+    typedef uint32_t T;
+    enum { PER_SECTOR = 8 };
+    static B2_HD uint32_t pack(uint32_t base, uint32_t eq, uint32_t seq, uint32_t sact, uint32_t sb, uint32_t sbp,
+                               uint32_t bid, uint32_t bidp)
+    {
+        return (base & 7u) | (eq & 1u) << 3 | (seq & 1u) << 4 | (sact & 1u) << 5 | (sb > 31u ? 31u : sb) << 6 |
+               (sbp > 31u ? 31u : sbp) << 11 | (bid > 255u ? 255u : bid) << 16 | (bidp > 255u ? 255u : bidp) << 24;
+    }
+    static B2_HD int sbid(QRec q) { return (int)(q >> 6 & 31u); }
+    static B2_HD int sbidp(QRec q) { return (int)(q >> 11 & 31u); }
+    static B2_HD int bid(QRec q) { return (int)(q >> 16 & 255u); }
+    static B2_HD int bidp(QRec q) { return (int)(q >> 24); }
+    static B2_HD QRec with_bid(QRec q, uint32_t v) { return (q & ~(0xffu << 16)) | v << 16; }
+    static B2_HD QRec with_prev(QRec q, uint32_t prev_bid, uint32_t eq)
+    {
+        return (q & ~(0xffu << 24 | 1u << 3)) | prev_bid << 24 | eq << 3;
+    }
+};
+template <> struct QF<16> {
+    typedef uint16_t T;
+    enum { PER_SECTOR = 16 };
+    static B2_HD uint32_t pack(uint32_t base, uint32_t eq, uint32_t seq, uint32_t sact, uint32_t sb, uint32_t sbp,
+                               uint32_t bid, uint32_t bidp)
+    {
+        return (base & 7u) | (eq & 1u) << 3 | (seq & 1u) << 4 | (sact & 1u) << 5 | (sb > 3u ? 3u : sb) << 6 |
+               (sbp > 3u ? 3u : sbp) << 8 | (bid > 7u ? 7u : bid) << 10 | (bidp > 7u ? 7u : bidp) << 13;
+    }
+    static B2_HD int sbid(QRec q) { return (int)(q >> 6 & 3u); }
+    static B2_HD int sbidp(QRec q) { return (int)(q >> 8 & 3u); }
+    static B2_HD int bid(QRec q) { return (int)(q >> 10 & 7u); }
+    static B2_HD int bidp(QRec q) { return (int)(q >> 13 & 7u); }
+    static B2_HD QRec with_bid(QRec q, uint32_t v) { return (q & ~(7u << 10)) | v << 10; }
+    static B2_HD QRec with_prev(QRec q, uint32_t prev_bid, uint32_t eq)
+    {
+        return (q & ~(7u << 13 | 1u << 3)) | prev_bid << 13 | eq << 3;
+    }
+};
+/* the low six bits are common to both formats */
 B2_HD int q_base(QRec q) { return (int)(q & 7u); }
 B2_HD int q_eq(QRec q) { return (int)(q >> 3 & 1u); }
 B2_HD int q_seq(QRec q) { return (int)(q >> 4 & 1u); }
 B2_HD int q_sact(QRec q) { return (int)(q >> 5 & 1u); }
-B2_HD int q_sbid(QRec q) { return (int)(q >> 6 & 31u); }
-B2_HD int q_sbidp(QRec q) { return (int)(q >> 11 & 31u); }
-B2_HD int q_bid(QRec q) { return (int)(q >> 16 & 255u); }
-B2_HD int q_bidp(QRec q) { return (int)(q >> 24); }
+/* eight consecutive records of a row (8-aligned position) <-> eight widened values */
+B2_HD void q_load8(const uint32_t *row, int j0, uint32_t q[8]) { ld8(row + j0, q); }
+B2_HD void q_store8(uint32_t *row, int j0, const uint32_t q[8]) { st8(row + j0, q); }
+B2_HD void q_load8(const uint16_t *row, int j0, uint32_t q[8])
+{
+    uint32_t v[4];
+    ld4(reinterpret_cast<const uint32_t *>(row + j0), v);
+    for (int t = 0; t < 4; ++t) { q[2 * t] = v[t] & 0xffffu; q[2 * t + 1] = v[t] >> 16; }
+}
+B2_HD void q_store8(uint16_t *row, int j0, const uint32_t q[8])
+{
+    uint32_t v[4];
+    for (int t = 0; t < 4; ++t) v[t] = (q[2 * t] & 0xffffu) | q[2 * t + 1] << 16;
+    st4(reinterpret_cast<uint32_t *>(row + j0), v);
+}
 
 /* ------------------------------------------------------------- occ -------- */
 
@@ -478,8 +551,9 @@ struct WidthOut {
     int n_amb; /* ambiguous symbols in the strand */
     int bid;   /* D(len - 1): the lower bound on the differences of the whole strand */
 };
+template <int QB>
 B2_HD WidthOut width_pass(const FmView &f, const uint8_t *fwd, int len, int a, bool comp, int seed_len, uint32_t *W,
-                          QRec *Q)
+                          typename QF<QB>::T *Q)
 {
     const bool use_seed = len > seed_len;
     const int shift = len - seed_len; /* ii = j - shift */
@@ -519,14 +593,14 @@ B2_HD WidthOut width_pass(const FmView &f, const uint8_t *fwd, int len, int a, b
                     sw_prev = sw;
                     sbid_prev = s.bid;
                 }
-                qb[t] = q_pack((uint32_t)c, j > 0 && w == w_prev, seq, sact, sb2, sbp, (uint32_t)m.bid,
-                               (uint32_t)bid_prev);
+                qb[t] = QF<QB>::pack((uint32_t)c, j > 0 && w == w_prev, seq, sact, sb2, sbp, (uint32_t)m.bid,
+                                     (uint32_t)bid_prev);
                 wb[t] = w;
                 w_prev = w;
                 bid_prev = m.bid;
             }
         }
-        if (j0 < len) st8(Q + j0, qb);
+        if (j0 < len) q_store8(Q, j0, qb);
         st8(W + j0, wb); /* includes the W[len] = 0 sentinel */
     }
     WidthOut o;
@@ -557,7 +631,8 @@ B2_HD int work_class(int d0, int d1, int max_diff)
  * refresh of the packed fields it invalidates (bid[j-1] and w[j-1]==w[j] of records 1..last_diff_pos).
  * Rows are walked one 32-byte sector at a time: W and Q rows are 32-byte aligned and padded to a
  * multiple of eight entries, so whole sectors can be read and written back. */
-B2_HD void shadow_update(uint32_t x, uint32_t max, int last_diff_pos, int len, uint32_t *W, QRec *Q)
+template <int QB>
+B2_HD void shadow_update(uint32_t x, uint32_t max, int last_diff_pos, int len, uint32_t *W, typename QF<QB>::T *Q)
 {
     if (last_diff_pos <= 0) return;
     const int last = last_diff_pos < len ? last_diff_pos : len - 1; /* last record whose packed fields can change */
@@ -566,7 +641,7 @@ B2_HD void shadow_update(uint32_t x, uint32_t max, int last_diff_pos, int len, u
     for (int i0 = 0; i0 <= last; i0 += 8) {
         uint32_t w8[8], q8[8];
         ld8(W + i0, w8);
-        ld8(Q + i0, q8);
+        q_load8(Q, i0, q8);
 #if defined(__CUDA_ARCH__)
 #pragma unroll
 #endif
@@ -577,18 +652,18 @@ B2_HD void shadow_update(uint32_t x, uint32_t max, int last_diff_pos, int len, u
                 if (w > x) w -= x;
                 else if (w == x) {
                     w = max - (uint32_t)(++j);
-                    q = (q & ~(0xffu << 16)) | 1u << 16; /* bid[i] = 1 */
+                    q = QF<QB>::with_bid(q, 1u); /* bid[i] = 1 */
                 }
             }
             if (i >= 1 && i <= last) /* bid[i-1] and the equal-width flag as the search reads them */
-                q = (q & ~(0xffu << 24 | 1u << 3)) | prev_bid << 24 | (uint32_t)(w == prev_w) << 3;
+                q = QF<QB>::with_prev(q, prev_bid, (uint32_t)(w == prev_w));
             prev_w = w;
-            prev_bid = q >> 16 & 0xffu;
+            prev_bid = (uint32_t)QF<QB>::bid(q);
             w8[t] = w;
             q8[t] = q;
         }
         st8(W + i0, w8);
-        st8(Q + i0, q8);
+        q_store8(Q, i0, q8);
     }
 }
 
@@ -690,8 +765,10 @@ enum LaneStatus { LANE_OK = 0, LANE_ARENA_FULL = 1, LANE_REC_FULL = 2 };
  *  - last_diff_pos: inherited from the parent on non-diff pushes (the slot reuse of bwtgap.c:60),
  *    which requires positive penalties (checked by the host before launch).
  */
-template <class Heads, bool REUSE, bool STATS = true>
+template <class Heads, bool REUSE, bool STATS = true, int QB = 32>
 struct SearchLane {
+    typedef QF<QB> Qf;
+    typedef typename QF<QB>::T QT;
     /* constant per read */
     GroupStore gs;
     uint32_t lane_no; /* which arena */
@@ -725,7 +802,7 @@ struct SearchLane {
 
     /* E: the launch constants, passed by reference at every call so that on the device they stay
      * in the kernel-parameter constant bank instead of being re-loaded through a pointer */
-    B2_HD const QRec *qrow(const SearchEnv &E, int a) const { return E.Q + (size_t)(row + (uint32_t)a) * E.strideQ; }
+    B2_HD QT *qrow(const SearchEnv &E, int a) const { return reinterpret_cast<QT *>(E.Q) + (size_t)(row + (uint32_t)a) * E.strideQ; }
     B2_HD StackRec *arena(const SearchEnv &E) const { return E.ent + (size_t)lane_no * E.arena_cap; }
     B2_HD Rec *records(const SearchEnv &E) const { return E.recs + (size_t)slab * E.rec_cap; }
     /* the width record of position p (0 <= p < len) of strand a */
@@ -885,7 +962,7 @@ struct SearchLane {
             const int pos = kind == GRP_X ? i : i + 1; /* their position; pos > 0 for deletions */
             if (pos > 0) pq = fetch_q(E, ca, pos - 1);
             const bool stop = !(P->mode & MODE_NONSTOP) && cscore > best_score + P->s_mm; /* bwtgap.c:143: the first one ends the search */
-            if (!stop && (m < 0 || (pos > 0 && m < q_bid(pq)))) {
+            if (!stop && (m < 0 || (pos > 0 && m < Qf::bid(pq)))) {
                 const int n = popc32(run);
                 n_entries -= n;
                 if (STATS) n_pops += (uint32_t)n;
@@ -944,8 +1021,7 @@ struct SearchLane {
             for (int j = 0; j < n_aln; ++j)
                 if (recs[j].k == ck && recs[j].l == cl) { add = false; break; }
         if (add) {
-            shadow_update(cl - ck + 1u, f.seq_len, cldp, len, E.W + (size_t)(row + (uint32_t)ca) * E.strideW,
-                          E.Q + (size_t)(row + (uint32_t)ca) * E.strideQ);
+            shadow_update<QB>(cl - ck + 1u, f.seq_len, cldp, len, E.W + (size_t)(row + (uint32_t)ca) * E.strideW, qrow(E, ca));
             if (n_aln >= E.rec_cap) { status = LANE_REC_FULL; return false; }
             Rec r;
             r.packed = (uint32_t)cmm | (uint32_t)cgo << 8 | (uint32_t)cge << 16 | (uint32_t)ca << 24;
@@ -1033,7 +1109,7 @@ struct SearchLane {
             if (!nonstop && cscore > best_score + P->s_mm) { finished = true; return NONE; }
             pm = max_diff - cmm - cgo - (gape_mode ? cge : 0);
             if (pm < 0) { B2_DBG(8); continue; }
-            if (ci > 0 && pm < q_bid(pq)) { /* pq = record of position ci - 1 */
+            if (ci > 0 && pm < Qf::bid(pq)) { /* pq = record of position ci - 1 */
                 if (++round >= max_rounds) return NONE;
                 continue;
             }
@@ -1112,11 +1188,11 @@ struct SearchLane {
         const uint32_t occ = cl - ck + 1u;
         bool allow_diff = true, allow_M = true;
         if (i > 0) { /* bwtgap.c:205-214, written without short-circuits to keep the lanes together */
-            const int bp = q_bidp(q), bd = q_bid(q);
+            const int bp = Qf::bidp(q), bd = Qf::bid(q);
             const bool d1 = bp > m - 1;
             const bool e1 = (bp == m - 1) & (bd == m - 1) & (q_eq(q) != 0);
             const int m_seed = P->max_seed_diff - cmm - cgo - (gape_mode ? cge : 0);
-            const int sp = q_sbidp(q), sd = q_sbid(q);
+            const int sp = Qf::sbidp(q), sd = Qf::sbid(q);
             const bool sa = q_sact(q) != 0;
             const bool d2 = sa & (sp > m_seed - 1);
             const bool e2 = sa & (sp == m_seed - 1) & (sd == m_seed - 1) & (q_seq(q) != 0);

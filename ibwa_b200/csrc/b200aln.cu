@@ -92,22 +92,24 @@ struct WidthArgs {
     const int64_t *offs;
     const uint8_t *codes;
     int comp, seed_len, strideQ, strideW;
-    QRec *Q;
+    uint32_t *Q; /* QF<QB>::T records */
     uint32_t *W;
     int32_t *n_amb;
     uint8_t *dkey; /* [2 * read + strand]: the strand's lower bound on differences, saturated (null: not wanted) */
     int rows_by_work; /* rows of Q / W are numbered by work item (the re-run passes) instead of by read */
 };
 
+template <int QB>
 __global__ void __launch_bounds__(128, 5) k_width(const __grid_constant__ WidthArgs A)
 {
+    typedef typename QF<QB>::T QT;
     const int nthreads = gridDim.x * blockDim.x, tid = blockIdx.x * blockDim.x + threadIdx.x;
     for (int64_t t = tid; t < 2 * (int64_t)A.n_reads; t += nthreads) {
         const int wi = (int)(t >> 1), a = (int)(t & 1);
         const int r = A.work_list ? A.work_list[wi] : wi;
         const size_t slot = (size_t)2 * (A.rows_by_work ? wi : r) + a;
-        const WidthOut o = width_pass(A.fm[a], A.codes + A.offs[r], A.lens[r], a, A.comp != 0, A.seed_len,
-                                      A.W + slot * A.strideW, A.Q + slot * A.strideQ);
+        const WidthOut o = width_pass<QB>(A.fm[a], A.codes + A.offs[r], A.lens[r], a, A.comp != 0, A.seed_len,
+                                          A.W + slot * A.strideW, reinterpret_cast<QT *>(A.Q) + slot * A.strideQ);
         if (a == 0) A.n_amb[r] = o.n_amb;
         if (A.dkey) A.dkey[(size_t)2 * r + a] = (uint8_t)(o.bid > 255 ? 255 : o.bid);
     }
@@ -239,19 +241,21 @@ template <> struct HeadsClear<HeadsStrided32> {
     static constexpr bool cooperative = true;
 };
 
-template <class Heads, bool REUSE, int MINB, bool STATS>
-__global__ void __launch_bounds__(128, MINB) k_search(const __grid_constant__ SearchArgs A)
+/* BLK: lanes per block.  128 (four warps) is the default; 32 makes the warp the unit that leaves the SM when the
+ * work queue has run dry, so that the next launch's blocks (another stream) move in while stragglers finish. */
+template <class Heads, bool REUSE, int MINB, bool STATS, int BLK = 128, int QB = 32>
+__global__ void __launch_bounds__(BLK, MINB * (128 / BLK)) k_search(const __grid_constant__ SearchArgs A)
 {
     const unsigned FULL = 0xffffffffu;
     const int lane = threadIdx.x & 31;
     const size_t gl = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-    SearchLane<Heads, REUSE, STATS> L;
+    SearchLane<Heads, REUSE, STATS, QB> L;
     L.finished = true;
     const Heads heads = HeadsFactory<Heads>::make(A, gl);
-    __shared__ uint32_t sm_group[OG_WORDS * 128]; /* the lanes' open groups, one conflict-free column each */
+    __shared__ uint32_t sm_group[OG_WORDS * BLK]; /* the lanes' open groups, one conflict-free column each */
     GroupStore gs;
     gs.p = sm_group + threadIdx.x;
-    gs.stride = 128;
+    gs.stride = BLK;
     bool alive = true, active = false;
     int r = -1;
     unsigned w = 0;
@@ -433,25 +437,26 @@ __global__ void __launch_bounds__(128) k_alngrp(const __grid_constant__ GrpArgs 
         A.out_n[r] = alngrp_merge_one(A.n_streams, r, A.n_aln, A.rec_off, A.recs, A.s_mm, A.out_off[r], A.out_rec, A.out_db);
 }
 
-__global__ void __launch_bounds__(256) k_sector_gather(const OccBlk *blk, uint64_t n_blocks, uint64_t loads_per_thread,
-                                                       int span, unsigned long long *sink)
-{
+__global__ void __launch_bounds__(256) k_sector_gather(const OccBlk *blk0, uint64_t n0, const OccBlk *blk1, uint64_t n1,
+                                                       uint64_t loads_per_thread, int span, unsigned long long *sink)
+{ /* uniformly random sectors over BOTH device indexes (the footprint the search gathers from) */
     uint64_t s = (blockIdx.x * (uint64_t)blockDim.x + threadIdx.x) * 0x9E3779B97F4A7C15ull + 0x1234567ull;
     uint32_t acc = 0;
-    const uint64_t units = n_blocks / (uint64_t)span;
+    const uint64_t u0 = n0 / (uint64_t)span, units = u0 + n1 / (uint64_t)span;
     for (uint64_t i = 0; i < loads_per_thread; i += 8) {
-        uint64_t idx[8];
+        const OccBlk *ptr[8];
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
             s ^= s << 13; s ^= s >> 7; s ^= s << 17;
-            idx[j] = (uint64_t)(((unsigned __int128)(s >> 11) * units) >> 53) * (uint64_t)span;
+            const uint64_t u = (uint64_t)(((unsigned __int128)(s >> 11) * units) >> 53);
+            ptr[j] = u < u0 ? blk0 + u * (uint64_t)span : blk1 + (u - u0) * (uint64_t)span;
         }
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
-            OccBlk a = ld_blk(blk + idx[j]);
+            OccBlk a = ld_blk(ptr[j]);
             acc += a.cnt.x ^ a.bits.w;
             if (span == 2) {
-                OccBlk b = ld_blk(blk + idx[j] + 1);
+                OccBlk b = ld_blk(ptr[j] + 1);
                 acc += b.cnt.y ^ b.bits.z;
             }
         }
@@ -529,6 +534,8 @@ struct b200aln_ctx {
     int rec_cap_mid = 512, mid_lanes = 148 * 192; /* x 12288 records x 64 B = 22 GB, allocated when a batch first needs it */
     int prefetch_fast = 0, prefetch_mid = 1; /* L2 prefetch of the next pop candidate, per pass */
     int order = 1;         /* fast pass takes the reads by work class, longest searches first (0: arrival order) */
+    int search_block = 128; /* lanes per block of the fast pass (128 or 32) */
+    int q16 = 1;            /* 16-bit width records in the fast pass when the options allow them (0: always 32-bit) */
     int prep_rounds = 1;   /* pruned pops a lane may go through per warp iteration before the warp moves on */
     int reserve_reads = 0; /* size the per-batch buffers for at least this many reads */
     int count = 0;         /* 1: fast pass with the pop / sector counters (b200aln_stats_t pops, occ_lookups) */
@@ -549,7 +556,8 @@ struct b200aln_ctx {
     /* chunk pipeline: a call with more than chunk_reads * 1.5 reads is cut into chunks that run on
      * `slots` sibling contexts (own stream, pinned staging and scratch; slot 0 is this context), so that the copies,
      * the width pass and the drain of one chunk's search overlap the search of the others */
-    int chunk_reads = 1 << 20, slots = 3;
+    int chunk_reads = 1 << 22, slots = 3;
+    int chunk_reads_device = 0; /* device-resident calls: 0 = one launch (nothing to overlap, and large launches are the efficient ones) */
     b200aln_ctx *parent = nullptr;   /* clones: the context that owns the index */
     int n_clones = 0;                /* owner: live clones (public and internal) */
     std::vector<b200aln_ctx *> slot; /* internal siblings 1 .. slots-1 */
@@ -728,7 +736,7 @@ extern "C" b200aln_ctx *b200aln_clone(b200aln_ctx *p)
     c->owns_index = false;
     c->parent = p->parent ? p->parent : p;
     ++c->parent->n_clones;
-    c->chunk_reads = p->chunk_reads; c->slots = p->slots;
+    c->chunk_reads = p->chunk_reads; c->chunk_reads_device = p->chunk_reads_device; c->slots = p->slots;
     CK(cudaSetDevice(c->device));
     for (int i = 0; i < 2; ++i) {
         c->fm[i] = p->fm[i];
@@ -743,7 +751,7 @@ extern "C" b200aln_ctx *b200aln_clone(b200aln_ctx *p)
     c->rec_cap = p->rec_cap; c->rec_cap_big = p->rec_cap_big; c->big_lanes = p->big_lanes;
     c->arena_cap_mid = p->arena_cap_mid; c->rec_cap_mid = p->rec_cap_mid; c->mid_lanes = p->mid_lanes;
     c->pop_batch = p->pop_batch; c->count = p->count; c->reserve_reads = p->reserve_reads; c->prep_rounds = p->prep_rounds;
-    c->prefetch_fast = p->prefetch_fast; c->prefetch_mid = p->prefetch_mid; c->order = p->order;
+    c->prefetch_fast = p->prefetch_fast; c->prefetch_mid = p->prefetch_mid; c->order = p->order; c->search_block = p->search_block; c->q16 = p->q16;
     CK(cudaStreamCreateWithFlags(&c->st, cudaStreamNonBlocking));
     for (int i = 0; i < 8; ++i) CK(cudaEventCreate(&c->ev[i]));
     for (int i = 0; i < 2; ++i) CK(cudaEventCreate(&c->tm[i]));
@@ -817,6 +825,7 @@ extern "C" void b200aln_close(b200aln_ctx *c)
 extern "C" void b200aln_set_int(b200aln_ctx *c, const char *key, int64_t v)
 {
     if (!strcmp(key, "chunk_reads")) { c->chunk_reads = (int)v; return; }
+    if (!strcmp(key, "chunk_reads_device")) { c->chunk_reads_device = (int)v; return; }
     if (!strcmp(key, "slots")) {
         if (v < 1 || v > 8) die("b200aln_set_int", "slots must be 1..8.");
         for (b200aln_ctx *s : c->slot) b200aln_close(s); /* re-created with the next pipelined call */
@@ -838,6 +847,8 @@ extern "C" void b200aln_set_int(b200aln_ctx *c, const char *key, int64_t v)
     else if (!strcmp(key, "reserve_reads")) c->reserve_reads = (int)v;
     else if (!strcmp(key, "prep_rounds")) c->prep_rounds = (int)v;
     else if (!strcmp(key, "order")) c->order = (int)v;
+    else if (!strcmp(key, "search_block")) c->search_block = (int)v;
+    else if (!strcmp(key, "q16")) c->q16 = (int)v;
     else if (!strcmp(key, "prefetch_fast")) c->prefetch_fast = (int)v;
     else if (!strcmp(key, "prefetch_mid")) c->prefetch_mid = (int)v;
     else if (!strcmp(key, "arena_cap_mid")) c->arena_cap_mid = (uint32_t)v;
@@ -892,14 +903,20 @@ static void launch_search_mid(b200aln_ctx *c, SearchArgs &A, int blocks)
     CK(cudaGetLastError());
 }
 
-static void launch_search_fast(b200aln_ctx *c, SearchArgs &A, int blocks)
+static void launch_search_fast(b200aln_ctx *c, SearchArgs &A, int blocks, bool q16)
 {
     if (fast_heads_ok(A.env.P, A.env.arena_cap)) {
         const size_t smem = (size_t)A.env.P.n_buckets * 128 * sizeof(uint16_t);
-        if (c->count) k_search<HeadsStrided16, false, 6, true><<<blocks, 128, smem, c->st>>>(A); /* with pop / sector counters */
-        else if (c->search_blocks_per_sm > 7) k_search<HeadsStrided16, false, 8, false><<<blocks, 128, smem, c->st>>>(A);
-        else if (c->search_blocks_per_sm == 7) k_search<HeadsStrided16, false, 7, false><<<blocks, 128, smem, c->st>>>(A);
-        else if (c->search_blocks_per_sm == 6) k_search<HeadsStrided16, false, 6, false><<<blocks, 128, smem, c->st>>>(A);
+        const bool six = c->search_blocks_per_sm == 6;
+        if (q16) { /* 16-bit width records (run_batch_device: q16_ok) */
+            if (c->count) k_search<HeadsStrided16, false, 6, true, 128, 16><<<blocks, 128, smem, c->st>>>(A);
+            else if (c->search_block == 32 && six) k_search<HeadsStrided16, false, 6, false, 32, 16><<<blocks * 4, 32, smem / 4, c->st>>>(A);
+            else if (six) k_search<HeadsStrided16, false, 6, false, 128, 16><<<blocks, 128, smem, c->st>>>(A);
+            else k_search<HeadsStrided16, false, 1, false, 128, 16><<<blocks, 128, smem, c->st>>>(A);
+        } else if (c->count) k_search<HeadsStrided16, false, 6, true><<<blocks, 128, smem, c->st>>>(A); /* with pop / sector counters */
+        else if (c->search_block == 32 && six) /* same lanes, one warp per block */
+            k_search<HeadsStrided16, false, 6, false, 32><<<blocks * 4, 32, smem / 4, c->st>>>(A);
+        else if (six) k_search<HeadsStrided16, false, 6, false><<<blocks, 128, smem, c->st>>>(A);
         else k_search<HeadsStrided16, false, 1, false><<<blocks, 128, smem, c->st>>>(A);
     } else {
         A.heads_wide_stride = A.env.P.n_buckets + (A.env.P.n_buckets + 31) / 32;
@@ -931,7 +948,12 @@ static void run_batch_device(b200aln_ctx *c, int n_reads, int max_len, const int
                              const Params &P, int64_t *total_out)
 {
     uint64_t launches = 0;
-    const int strideQ = round_up8(max_len > 0 ? max_len : 1), strideW = round_up8(max_len + 1); /* 32-byte aligned rows */
+    /* 16-bit width records when every field fits (aln_core.cuh: QF<16>) and the fast pass runs the kernel built for them */
+    int md_max = 0;
+    for (int l = 0; l <= max_len && l < (int)md.size(); ++l) md_max = md[l] > md_max ? md[l] : md_max;
+    const bool q16 = c->q16 != 0 && md_max < 7 && P.max_seed_diff < 3 && fast_heads_ok(P, c->arena_cap);
+    const int strideQ32 = round_up8(max_len > 0 ? max_len : 1), strideW = round_up8(max_len + 1); /* 32-byte aligned rows */
+    const int strideQ = q16 ? ((max_len > 0 ? max_len : 1) + 15) & ~15 : strideQ32; /* the fast pass's rows; re-runs use QF<32> */
     const int wblocks = c->n_sm * c->width_blocks_per_sm;
     const int sblocks = c->n_sm * c->search_blocks_per_sm;
     const size_t lanes = (size_t)sblocks * 128;
@@ -940,7 +962,7 @@ static void run_batch_device(b200aln_ctx *c, int n_reads, int max_len, const int
     /* buffers are sized for at least reserve_reads reads, so that a driver whose launches vary in size does not
      * keep growing them (freeing and allocating synchronise the device) */
     const size_t n_alloc = (size_t)(n_reads > c->reserve_reads ? n_reads : c->reserve_reads);
-    c->Q.need(n_alloc * 2 * strideQ * sizeof(QRec) + 64);
+    c->Q.need(n_alloc * 2 * strideQ * (q16 ? 2 : 4) + 64);
     c->W.need(n_alloc * 2 * strideW * 4 + 64);
     c->n_amb.need(n_alloc * 4);
     const bool ordered = c->order != 0 && n_reads > 1;
@@ -970,11 +992,12 @@ static void run_batch_device(b200aln_ctx *c, int n_reads, int max_len, const int
     WA.n_reads = n_reads; WA.work_list = nullptr; WA.lens = d_lens; WA.offs = d_offs; WA.codes = d_codes;
     WA.comp = (opt->mode & MODE_COMPREAD) ? 1 : 0; WA.seed_len = opt->seed_len;
     WA.strideQ = strideQ; WA.strideW = strideW;
-    WA.Q = c->Q.as<QRec>(); WA.W = c->W.as<uint32_t>();
+    WA.Q = c->Q.as<uint32_t>(); WA.W = c->W.as<uint32_t>();
     WA.rows_by_work = 0;
     WA.n_amb = c->n_amb.as<int32_t>();
     WA.dkey = ordered ? c->dkey.as<uint8_t>() : nullptr;
-    k_width<<<wblocks, 128, 0, c->st>>>(WA);
+    if (q16) k_width<16><<<wblocks, 128, 0, c->st>>>(WA);
+    else k_width<32><<<wblocks, 128, 0, c->st>>>(WA);
     CK(cudaGetLastError());
     ++launches;
     if (ordered) { /* part of the width stage's time */
@@ -1005,7 +1028,7 @@ static void run_batch_device(b200aln_ctx *c, int n_reads, int max_len, const int
     SA.arena_by_work = 0; SA.n_rec_full = nullptr;
     SA.pop_batch = c->pop_batch;
     SA.prep_rounds = c->prep_rounds;
-    launch_search_fast(c, SA, sblocks);
+    launch_search_fast(c, SA, sblocks, q16);
     ++launches;
     CK(cudaEventRecord(c->ev[3], c->st));
 
@@ -1036,17 +1059,17 @@ static void run_batch_device(b200aln_ctx *c, int n_reads, int max_len, const int
         c->ent_mid.need((size_t)mblocks * 128 * c->arena_cap_mid * sizeof(StackRec));
         c->recs_mid.need((size_t)n_over * c->rec_cap_mid * 16);
         c->over_list2.need((size_t)n_over * 4);
-        c->Q_re.need((size_t)n_over * 2 * strideQ * sizeof(QRec) + 64);
+        c->Q_re.need((size_t)n_over * 2 * strideQ32 * 4 + 64);
         c->W_re.need((size_t)n_over * 2 * strideW * 4 + 64);
         WidthArgs WM = WA;
-        WM.dkey = nullptr; WM.rows_by_work = 1;
-        WM.Q = c->Q_re.as<QRec>(); WM.W = c->W_re.as<uint32_t>();
+        WM.dkey = nullptr; WM.rows_by_work = 1; WM.strideQ = strideQ32;
+        WM.Q = c->Q_re.as<uint32_t>(); WM.W = c->W_re.as<uint32_t>();
         WM.n_reads = (int)n_over; WM.work_list = c->over_list.as<int32_t>();
-        k_width<<<wblocks, 128, 0, c->st>>>(WM);
+        k_width<32><<<wblocks, 128, 0, c->st>>>(WM);
         CK(cudaGetLastError());
         ++launches;
         SearchArgs SM = SA;
-        SM.env.Q = WM.Q; SM.env.W = WM.W; SM.rows_by_work = 1;
+        SM.env.Q = WM.Q; SM.env.W = WM.W; SM.env.strideQ = strideQ32; SM.rows_by_work = 1;
         SM.n_work = (int)n_over; SM.work_list = c->over_list.as<int32_t>();
         SM.env.ent = c->ent_mid.as<StackRec>(); SM.env.arena_cap = c->arena_cap_mid;
         SM.env.recs = c->recs_mid.as<Rec>(); SM.env.rec_cap = c->rec_cap_mid; SM.recs_by_work = 1;
@@ -1075,17 +1098,17 @@ static void run_batch_device(b200aln_ctx *c, int n_reads, int max_len, const int
             const bool by_work = n_wide <= (unsigned)(bblocks * bthreads);
             c->ent_big.need((size_t)(by_work ? n_wide : (unsigned)(bblocks * bthreads)) * cap_big * sizeof(StackRec));
             c->recs_big.need((size_t)n_wide * c->rec_cap_big * 16);
-            c->Q_re.need((size_t)n_wide * 2 * strideQ * sizeof(QRec) + 64);
+            c->Q_re.need((size_t)n_wide * 2 * strideQ32 * 4 + 64);
             c->W_re.need((size_t)n_wide * 2 * strideW * 4 + 64);
             WidthArgs WB = WA;
-            WB.dkey = nullptr; WB.rows_by_work = 1;
-            WB.Q = c->Q_re.as<QRec>(); WB.W = c->W_re.as<uint32_t>();
+            WB.dkey = nullptr; WB.rows_by_work = 1; WB.strideQ = strideQ32;
+            WB.Q = c->Q_re.as<uint32_t>(); WB.W = c->W_re.as<uint32_t>();
             WB.n_reads = (int)n_wide; WB.work_list = wide_list;
-            k_width<<<wblocks, 128, 0, c->st>>>(WB);
+            k_width<32><<<wblocks, 128, 0, c->st>>>(WB);
             CK(cudaGetLastError());
             ++launches;
             SearchArgs SB = SA;
-            SB.env.Q = WB.Q; SB.env.W = WB.W; SB.rows_by_work = 1;
+            SB.env.Q = WB.Q; SB.env.W = WB.W; SB.env.strideQ = strideQ32; SB.rows_by_work = 1;
             SB.n_work = (int)n_wide; SB.work_list = wide_list;
             SB.env.ent = c->ent_big.as<StackRec>(); SB.env.arena_cap = cap_big; SB.arena_by_work = by_work ? 1 : 0;
             SB.env.recs = c->recs_big.as<Rec>(); SB.env.rec_cap = c->rec_cap_big; SB.recs_by_work = 1;
@@ -1179,10 +1202,10 @@ static void ensure_slots(b200aln_ctx *c)
     }
 }
 
-static int pipeline_chunks(const b200aln_ctx *c, int n_reads)
+static int pipeline_chunks(const b200aln_ctx *c, int n_reads, int chunk_reads)
 {
-    if (c->slots < 2 || c->chunk_reads <= 0 || (int64_t)n_reads <= (int64_t)c->chunk_reads + c->chunk_reads / 2) return 1;
-    return (int)(((int64_t)n_reads + c->chunk_reads - 1) / c->chunk_reads);
+    if (c->slots < 2 || chunk_reads <= 0 || (int64_t)n_reads <= (int64_t)chunk_reads + chunk_reads / 2) return 1;
+    return (int)(((int64_t)n_reads + chunk_reads - 1) / chunk_reads);
 }
 
 /* In-order hand-over of the chunks' results: a chunk learns where its records go once every earlier chunk has
@@ -1304,7 +1327,7 @@ extern "C" const b200aln_rec_t *b200aln_batch(b200aln_ctx *c, int n_reads, const
     if ((int)md.size() < max_len + 1) md.resize((size_t)max_len + 1, opt->max_diff);
     const bool pinned_in = host_pinned(lens) && host_pinned(offs) && host_pinned(codes), pinned_out = host_pinned(n_aln);
 
-    const int n_chunks = pipeline_chunks(c, n_reads);
+    const int n_chunks = pipeline_chunks(c, n_reads, c->chunk_reads);
     if (n_chunks == 1) {
         const int64_t tot = run_chunk_host(c, n_reads, lens, offs, codes, opt, P, md, pinned_in);
         c->h_out.need((size_t)(tot > 0 ? tot : 1) * 16);
@@ -1367,7 +1390,7 @@ extern "C" void b200aln_batch_device(b200aln_ctx *c, int n_reads, int max_len, c
     if (max_len > 1024) die("b200aln_batch_device", "max_len > 1024 needs b200aln_batch (per-length max_diff table).");
     b2host::make_params(*opt, c->batch_max_len > 0 ? c->batch_max_len : max_len, one.data(), 1, P, md);
     if ((int)md.size() < max_len + 1) md.resize((size_t)max_len + 1, opt->max_diff);
-    const int n_chunks = n_reads > 0 ? pipeline_chunks(c, n_reads) : 1;
+    const int n_chunks = n_reads > 0 ? pipeline_chunks(c, n_reads, c->chunk_reads_device) : 1;
     if (n_chunks == 1) {
         int64_t tot = 0;
         run_batch_device(c, n_reads, max_len, d_lens, d_offs, d_codes, opt, md, P, &tot);
@@ -1566,7 +1589,7 @@ extern "C" double b200aln_sector_roofline(b200aln_ctx *c, uint64_t n_loads, int 
     double best = 0;
     for (int it = 0; it < repeats + 1; ++it) {
         CK(cudaEventRecord(c->ev[0], c->st));
-        k_sector_gather<<<blocks, threads, 0, c->st>>>(c->d_idx[it & 1], c->n_blk[it & 1], per, span,
+        k_sector_gather<<<blocks, threads, 0, c->st>>>(c->d_idx[0], c->n_blk[0], c->d_idx[1], c->n_blk[1], per, span,
                                                        (unsigned long long *)c->misc.p);
         CK(cudaGetLastError());
         CK(cudaEventRecord(c->ev[1], c->st));

@@ -50,15 +50,22 @@ template <> HeadsWide32 make_heads<HeadsWide32>(std::vector<uint32_t> &store)
     return hd;
 }
 
-template <class Heads, bool REUSE>
+static int g_q16 = 0; /* 1: the first pass uses the 16-bit width records when the options allow them (like the product) */
+extern "C" void hh_set_q16(int v) { g_q16 = v; }
+static int g_last_q16 = 0; /* whether the last hh_aln_batch call really ran on the 16-bit records */
+extern "C" int hh_last_q16() { return g_last_q16; }
+
+template <class Heads, bool REUSE, int QB>
 static int64_t run(const SearchEnv &env, const std::vector<int> &md, int n_reads, const int32_t *lens,
                    const int64_t *offs, const uint8_t *codes, bool comp, int seed_len, uint32_t arena_cap, int rec_cap,
                    int32_t *n_aln, std::vector<Rec> &all, uint64_t *counters, uint32_t big_cap)
 {
     int max_len = 0;
     for (int r = 0; r < n_reads; ++r) if (lens[r] > max_len) max_len = lens[r];
-    const int strideQ = round_up8(max_len), strideW = round_up8(max_len + 1);
-    std::vector<QRec> Q(2 * (size_t)strideQ + 8);
+    typedef typename QF<QB>::T QT;
+    const int strideQ = (max_len + 15) & ~15, strideW = round_up8(max_len + 1);
+    std::vector<uint32_t> Q(2 * (size_t)strideQ + 8); /* room for either format */
+    QT *Qt = reinterpret_cast<QT *>(Q.data());
     std::vector<uint32_t> W(2 * (size_t)strideW + 8);
     std::vector<StackRec> ent(arena_cap);
     std::vector<Rec> recs(rec_cap);
@@ -72,9 +79,9 @@ static int64_t run(const SearchEnv &env, const std::vector<int> &md, int n_reads
         const uint8_t *fwd = codes + offs[r];
         int len = lens[r];
         const FmView *fm = env.fm;
-        int n_amb = width_pass(fm[0], fwd, len, 0, comp, seed_len, W.data(), Q.data()).n_amb;
-        width_pass(fm[1], fwd, len, 1, comp, seed_len, W.data() + strideW, Q.data() + strideQ);
-        SearchLane<Heads, REUSE> lane;
+        int n_amb = width_pass<QB>(fm[0], fwd, len, 0, comp, seed_len, W.data(), Qt).n_amb;
+        width_pass<QB>(fm[1], fwd, len, 1, comp, seed_len, W.data() + strideW, Qt + strideQ);
+        SearchLane<Heads, REUSE, true, QB> lane;
         SearchEnv e1 = env;
         e1.Q = Q.data(); e1.W = W.data(); e1.strideQ = strideQ; e1.strideW = strideW;
         e1.recs = recs.data(); e1.rec_cap = rec_cap; e1.ent = ent.data(); e1.arena_cap = arena_cap;
@@ -84,8 +91,8 @@ static int64_t run(const SearchEnv &env, const std::vector<int> &md, int n_reads
             /* the product's large pass: widths rebuilt (the aborted pass shadowed them), free-list arena */
             ++n_status;
             if (ent2.size() < big_cap) { ent2.resize(big_cap); recs2.resize(1 << 16); }
-            n_amb = width_pass(fm[0], fwd, len, 0, comp, seed_len, W.data(), Q.data()).n_amb;
-            width_pass(fm[1], fwd, len, 1, comp, seed_len, W.data() + strideW, Q.data() + strideQ);
+            n_amb = width_pass<32>(fm[0], fwd, len, 0, comp, seed_len, W.data(), Q.data()).n_amb;
+            width_pass<32>(fm[1], fwd, len, 1, comp, seed_len, W.data() + strideW, Q.data() + strideQ);
             SearchLane<HeadsWide32, true> big;
             SearchEnv e2 = e1;
             e2.recs = recs2.data(); e2.rec_cap = 1 << 16; e2.ent = ent2.data(); e2.arena_cap = big_cap;
@@ -144,13 +151,19 @@ extern "C" int64_t hh_aln_batch(const b200aln_bwt_view_t *bwt, const b200aln_bwt
     std::vector<Rec> all;
     bool comp = opt->mode & MODE_COMPREAD;
     int64_t ov;
+    int md_max = 0;
+    for (int l = 0; l <= max_len && l < (int)md.size(); ++l) md_max = md[l] > md_max ? md[l] : md_max;
+    const bool q16 = g_q16 && md_max < 7 && P.max_seed_diff < 3;
+    g_last_q16 = q16;
+#define HH_RUN(H, R, QB) run<H, R, QB>(env, md, n_reads, lens, offs, codes, comp, opt->seed_len, arena_cap, rec_cap, n_aln, all, counters, big_cap)
     if (P.n_buckets <= 128 && arena_cap <= 32767) {
-        ov = reuse ? run<HeadsStrided16, true>(env, md, n_reads, lens, offs, codes, comp, opt->seed_len, arena_cap, rec_cap, n_aln, all, counters, big_cap)
-                   : run<HeadsStrided16, false>(env, md, n_reads, lens, offs, codes, comp, opt->seed_len, arena_cap, rec_cap, n_aln, all, counters, big_cap);
+        if (q16) ov = reuse ? HH_RUN(HeadsStrided16, true, 16) : HH_RUN(HeadsStrided16, false, 16);
+        else ov = reuse ? HH_RUN(HeadsStrided16, true, 32) : HH_RUN(HeadsStrided16, false, 32);
     } else {
-        ov = reuse ? run<HeadsWide32, true>(env, md, n_reads, lens, offs, codes, comp, opt->seed_len, arena_cap, rec_cap, n_aln, all, counters, big_cap)
-                   : run<HeadsWide32, false>(env, md, n_reads, lens, offs, codes, comp, opt->seed_len, arena_cap, rec_cap, n_aln, all, counters, big_cap);
+        if (q16) ov = reuse ? HH_RUN(HeadsWide32, true, 16) : HH_RUN(HeadsWide32, false, 16);
+        else ov = reuse ? HH_RUN(HeadsWide32, true, 32) : HH_RUN(HeadsWide32, false, 32);
     }
+#undef HH_RUN
     *n_overflow = ov;
     Rec *out = (Rec *)malloc(sizeof(Rec) * (all.size() + 1));
     memcpy(out, all.data(), sizeof(Rec) * all.size());

@@ -97,6 +97,41 @@ def _vs_oracle(bwt, rbwt, reads, args, **kw):
     return o_n
 
 
+@pytest.mark.parametrize("tag", ["stress", "N_n2", "short_o3", "short_default"])
+def test_q16_width_records_on_golden(tag, golden_dir, g1_index):
+    """The fast pass's 16-bit width records (aln_core.cuh QF<16>) on the fixtures whose options allow them for the
+    whole batch (max_diff < 7, max_seed_diff < 3): bytes must equal the reference's."""
+    args, fq = CASES[tag]
+    got, nov = harness_sai(g1_index[0], g1_index[1], args, os.path.join(golden_dir, fq + ".fq.gz"),
+                           arena_cap=32000, rec_cap=4096, rounds=1, q16=True, lut_k=3)
+    assert nov == 0 and pyharness.lib().hh_last_q16() == 1
+    assert got == open(os.path.join(golden_dir, f"g1_{tag}.sai"), "rb").read()
+
+
+@pytest.mark.parametrize("args", [[], ["-o", "3"], ["-L", "-o", "2", "-e", "3"], ["-R", "2"], ["-m", "200"],
+                                  ["-l", "20", "-k", "1"], ["-i", "0", "-d", "3", "-o", "2"], ["-c"], ["-n", "6", "-k", "2"]])
+def test_q16_width_records_vs_oracle(args, golden_dir, g1_index):
+    """Default-style option sets on the repeat-rich fixture's reads of at most 150 bp (so that max_diff stays below
+    7 and the 16-bit records are what runs): gap_shadow's edits, the seed fields and the saturating bid fields
+    against the oracle, on the bump arena, the free-list arena and through the two-pass flow."""
+    opt, _, _, _ = parse_aln_args(args + ["p", "q"])
+    batch = next(seqio.read_batches(os.path.join(golden_dir, "g1_reads.fq.gz"), opt.mode, opt.trim_qual))
+    reads = [batch.codes[o:o + l] for o, l in zip(batch.offs, batch.lens) if l <= 150][:1500]
+    assert len(reads) > 800
+    _vs_oracle(g1_index[0], g1_index[1], reads, args, arena_cap=1 << 20, rec_cap=4096, q16=True, rounds=1, lut_k=4)
+    assert pyharness.lib().hh_last_q16() == 1
+    _vs_oracle(g1_index[0], g1_index[1], reads[:400], args, arena_cap=1 << 20, rec_cap=4096, q16=True, reuse=True)
+    from oracle import pyoracle
+    lens = np.array([len(r) for r in reads[:300]], np.int32)
+    offs = np.concatenate([[0], np.cumsum(lens)[:-1]]).astype(np.int64)
+    codes = np.concatenate(reads[:300])
+    o_n, o_rec, _ = pyoracle.aln_batch(pyoracle.as_orc_bwt(g1_index[0]), pyoracle.as_orc_bwt(g1_index[1]), lens, offs,
+                                       codes, opt.to_c())
+    h_n, h_rec, nov, _ = pyharness.aln_batch(g1_index[0], g1_index[1], lens, offs, codes, opt.to_c(), arena_cap=48,
+                                             rec_cap=2, big_cap=1 << 21, q16=True)
+    assert nov > 0 and np.array_equal(o_n, h_n) and o_rec.tobytes() == h_rec.tobytes()
+
+
 def test_long_reads_and_wide_score_ranges(golden_dir, g1_index):
     """1 kbp and 3 kbp reads: max_diff 23 / 75, i.e. 143 and 275 score buckets (the second needs the wide
     heads); also an empty read, which BAM input can deliver (the reference then reports the whole index)."""
@@ -181,7 +216,8 @@ def test_random_option_sets_against_the_oracle(k, args, golden_dir, g1_index):
     lo = (k * 97) % max(1, len(batch.lens) - 160)
     reads = [batch.codes[o:o + l] for o, l in zip(batch.offs[lo:lo + 160], batch.lens[lo:lo + 160])]
     _vs_oracle(g1_index[0], g1_index[1], reads, args, arena_cap=1 << 21, rec_cap=1 << 14, reuse=bool(k & 1), lut_k=k % 5,
-               rounds=(k // 2) % 3)     # 0 = unlimited, 1 = the fast kernel's setting, 2
+               rounds=(k // 2) % 3,     # 0 = unlimited, 1 = the fast kernel's setting, 2
+               q16=k % 3 != 1)          # 16-bit width records wherever the option set allows them
     if k % 3 == 0:
         from oracle import pyoracle
         lens = np.array([len(r) for r in reads], np.int32)

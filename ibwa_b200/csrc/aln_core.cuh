@@ -35,7 +35,46 @@
 #define B2_D inline
 #endif
 
+#if defined(B2_CHECKED) && !defined(__CUDACC__)
+#include <stdio.h>
+#include <stdlib.h>
+#endif
+
 namespace b2 {
+
+/*
+ * Bounds-checked build (-DB2_CHECKED; libb200aln_checked.so and the CPU harness's checked variant): every
+ * index the state machines derive from data in memory — arena slots, bucket numbers, width-record positions,
+ * record-slab fills, interval-table and occ-block addresses, work items — is tested before it is used.  Stands
+ * in for compute-sanitizer, which the GPU pool does not allow.  On the device the first violation is recorded
+ * (code, read row, the two values) and the lane ends with LANE_CHECK; the host reports it and aborts.  On the
+ * CPU it aborts on the spot.  The product build compiles the checks away.
+ */
+enum { CHK_ARENA_SLOT = 1, CHK_BUCKET = 2, CHK_POP_EMPTY = 3, CHK_Q_POS = 4, CHK_REC_FILL = 5, CHK_LUT = 6,
+       CHK_BLK = 7, CHK_MEMBER = 8, CHK_WORK = 9, CHK_ENTRIES = 10 };
+#ifdef B2_CHECKED
+#if defined(__CUDACC__)
+__device__ unsigned int b2_check_rec[4]; /* code (0 = clean), row, a, b of the first violation */
+__host__ __device__ __forceinline__ bool b2_check_fail(int code, uint32_t row, uint32_t a, uint32_t b)
+{
+#if defined(__CUDA_ARCH__)
+    if (atomicCAS(&b2_check_rec[0], 0u, (unsigned)code) == 0u) { b2_check_rec[1] = row; b2_check_rec[2] = a; b2_check_rec[3] = b; }
+#else
+    (void)code; (void)row; (void)a; (void)b; /* host pass of nvcc: never called */
+#endif
+    return false;
+}
+#else
+inline bool b2_check_fail(int code, uint32_t row, uint32_t a, uint32_t b)
+{
+    fprintf(stderr, "[B2_CHECKED] violation %d at row %u: %u vs %u\n", code, row, a, b);
+    abort();
+}
+#endif
+#define B2_CHECK(cond, code, row, a, b) ((cond) || b2_check_fail((code), (uint32_t)(row), (uint32_t)(a), (uint32_t)(b)))
+#else
+#define B2_CHECK(cond, code, row, a, b) (true)
+#endif
 
 struct alignas(16) U4 {
     uint32_t x, y, z, w;
@@ -242,6 +281,7 @@ B2_HD uint64_t lut_level_off(int level) { return (0x5555555555555555ull >> (64 -
 /* pair index of node X of `level` for index half w.  The levels of BOTH indexes are interleaved so that
  * the small, hot top of the table is one contiguous range (pinned in L2 with an access-policy window). */
 B2_HD uint64_t lut_pair(int w, int level, uint64_t X) { return 2u * lut_level_off(level) + ((uint64_t)w << (2 * level)) + X; }
+B2_HD uint64_t lut_total_pairs(int lut_k) { return lut_k > 0 ? 2u * lut_level_off(lut_k + 1) : 0; } /* both indexes */
 B2_HD uint32_t path_root() { return 0u; }
 /* path of the child reached by prepending character c to a node with path p */
 B2_HD uint32_t path_ext(uint32_t p, int c, int lut_k)
@@ -385,6 +425,7 @@ B2_HD void occ_count4(U4 c, U4 b, uint32_t r, uint32_t o[4])
 B2_HD void occ2x4(const FmView &f, uint32_t k, uint32_t l, uint32_t ck[4], uint32_t cl[4], uint32_t &n_sectors)
 {
     uint32_t qa = q_lower(f, k), qb = q_upper(f, l);
+    if (!B2_CHECK(qa <= f.seq_len && qb <= f.seq_len && k <= l, CHK_BLK, k, qa, qb)) { qa = qb = 0; }
     const OccBlk *pa = f.blk + (qa >> 6), *pb = f.blk + (qb >> 6);
     OccBlk ba = ld_blk(pa), bb = ba;
     n_sectors = 1;
@@ -438,6 +479,8 @@ B2_HD void children4(const FmView &f, uint32_t path, uint32_t k, uint32_t l, uin
     const uint32_t d = path & 31u;
     if (d != B2_PATH_DEAD && (int)d < f.lut_k) {
         const uint32_t *p = f.lut + 2 * lut_pair(f.lut_w, (int)d + 1, (uint64_t)(path >> 5) << 2);
+        if (!B2_CHECK((uint64_t)(path >> 5) < ((uint64_t)1 << (2 * d)) && lut_pair(f.lut_w, (int)d + 1, (uint64_t)(path >> 5) << 2) + 4 <= lut_total_pairs(f.lut_k),
+                      CHK_LUT, d, path >> 5, f.lut_k)) { for (int c = 0; c < 4; ++c) { nk[c] = 1u; nl[c] = 0u; } n_sectors = 0; return; }
         const U8x v = ld_lut8(p, d < 11u); /* levels <= 11: 90 MB for both indexes */
         nk[0] = v.v[0]; nl[0] = v.v[1]; nk[1] = v.v[2]; nl[1] = v.v[3];
         nk[2] = v.v[4]; nl[2] = v.v[5]; nk[3] = v.v[6]; nl[3] = v.v[7];
@@ -468,7 +511,6 @@ B2_HD void lut_build_node(const FmView &f, uint32_t *lut, int level, uint64_t X)
         for (int c = 0; c < 4; ++c) { o[2 * c] = 1u; o[2 * c + 1] = 0u; }
     }
 }
-B2_HD uint64_t lut_total_pairs(int lut_k) { return lut_k > 0 ? 2u * lut_level_off(lut_k + 1) : 0; } /* both indexes */
 
 /* ---------------------------------------------------------- width pass ---- */
 
@@ -742,7 +784,7 @@ struct HeadsWide32 {
     B2_HD void set(int sc, uint32_t slot) { h[sc] = slot; }
 };
 
-enum LaneStatus { LANE_OK = 0, LANE_ARENA_FULL = 1, LANE_REC_FULL = 2 };
+enum LaneStatus { LANE_OK = 0, LANE_ARENA_FULL = 1, LANE_REC_FULL = 2, LANE_CHECK = 3 /* B2_CHECKED: a violation */ };
 
 /*
  * One read's best-first search (bwt_match_gap), advanced one occ lookup per
@@ -806,7 +848,11 @@ struct SearchLane {
     B2_HD StackRec *arena(const SearchEnv &E) const { return E.ent + (size_t)lane_no * E.arena_cap; }
     B2_HD Rec *records(const SearchEnv &E) const { return E.recs + (size_t)slab * E.rec_cap; }
     /* the width record of position p (0 <= p < len) of strand a */
-    B2_HD QRec fetch_q(const SearchEnv &E, int a, int p) const { return ld_q(qrow(E, a) + p); }
+    B2_HD QRec fetch_q(const SearchEnv &E, int a, int p) const
+    {
+        if (!B2_CHECK(p >= 0 && p < len && p < E.strideQ && (a == 0 || a == 1), CHK_Q_POS, row, p, len)) return 0;
+        return ld_q(qrow(E, a) + p);
+    }
 
     /* heads_clean: the caller has already emptied the bucket heads (the kernel does it with the whole warp) */
     B2_HD void begin(const SearchEnv &E, Heads heads_, GroupStore gs_, uint32_t lane_no_, uint32_t read, uint32_t slab_,
@@ -853,6 +899,9 @@ struct SearchLane {
             if (top >= E.arena_cap) { status = LANE_ARENA_FULL; finished = true; return; }
             slot = top++;
         }
+        if (!B2_CHECK(slot < E.arena_cap && slot < top, CHK_ARENA_SLOT, row, slot, top) ||
+            !B2_CHECK((!gmask || (sg >= 0 && sg < E.P.n_buckets)) && (!xmask || (sx >= 0 && sx < E.P.n_buckets)), CHK_BUCKET, row,
+                      gmask ? sg : sx, E.P.n_buckets)) { status = LANE_CHECK; finished = true; return; }
         uint32_t h[8];
         h[0] = h[1] = Heads::nil();
         if (gmask) { /* gap group first: when both share a bucket the mismatches are on top (pushed later) */
@@ -885,8 +934,12 @@ struct SearchLane {
     {
         B2_DBG(0);
         const int b = best;
+        if (!B2_CHECK(b >= 0 && b < E.P.n_buckets && n_mem > 0, CHK_BUCKET, row, b, n_mem)) { status = LANE_CHECK; finished = true; og = 0; return; }
         const uint32_t ref = bk.get(b);
         const uint32_t slot = ref >> 1, which = ref & 1u;
+        if (!B2_CHECK(ref != Heads::nil(), CHK_POP_EMPTY, row, b, ref) || !B2_CHECK(slot < top, CHK_ARENA_SLOT, row, slot, top)) {
+            status = LANE_CHECK; finished = true; og = 0; return;
+        }
         uint32_t h[8], c8[8];
         StackRec *ent = arena(E);
         const uint32_t *rec = ent[slot].w;
@@ -900,7 +953,10 @@ struct SearchLane {
             if (n_mem == 0) best = E.P.n_buckets;
             else {
                 int nb = b + 1;
-                while ((next_top = bk.get(nb)) == Heads::nil()) ++nb;
+                while ((next_top = bk.get(nb)) == Heads::nil()) {
+                    ++nb;
+                    if (!B2_CHECK(nb < E.P.n_buckets, CHK_BUCKET, row, nb, n_mem)) { status = LANE_CHECK; finished = true; og = 0; return; }
+                }
                 best = nb;
             }
         }
@@ -955,6 +1011,9 @@ struct SearchLane {
             --n_entries;
             if (STATS) ++n_pops;
             return true;
+        }
+        if (!B2_CHECK(mask != 0 && i <= len && (kind == GRP_X || kind == GRP_G) && n_entries > 0, CHK_MEMBER, row, og, n_entries)) {
+            status = LANE_CHECK; finished = true; og = 0; return false;
         }
         const uint32_t run = mask & 15u; /* members that are child intervals: mismatches, or deletions */
         const int m = max_diff - cmm - cgo - ((P->mode & MODE_GAPE) ? cge : 0);
@@ -1023,6 +1082,7 @@ struct SearchLane {
         if (add) {
             shadow_update<QB>(cl - ck + 1u, f.seq_len, cldp, len, E.W + (size_t)(row + (uint32_t)ca) * E.strideW, qrow(E, ca));
             if (n_aln >= E.rec_cap) { status = LANE_REC_FULL; return false; }
+            if (!B2_CHECK(n_aln >= 0 && cldp >= 0 && cldp <= len, CHK_REC_FILL, row, n_aln, cldp)) { status = LANE_CHECK; return false; }
             Rec r;
             r.packed = (uint32_t)cmm | (uint32_t)cgo << 8 | (uint32_t)cge << 16 | (uint32_t)ca << 24;
             r.k = ck; r.l = cl; r.score = cscore;
@@ -1090,11 +1150,15 @@ struct SearchLane {
                 continue; /* the chain met an ambiguous symbol */
             }
             if (n_entries == 0) { finished = true; return NONE; }
+            if (!B2_CHECK(n_entries > 0, CHK_ENTRIES, row, n_entries, n_mem)) { status = LANE_CHECK; finished = true; return NONE; }
             if (n_entries > P->max_entries) { finished = true; return NONE; } /* bwtgap.c:139 */
             if (!have_cur) {
                 if (og == 0) {
                     if (!allow_pop) return NONE;
                     pop_group(E);
+#ifdef B2_CHECKED
+                    if (finished) return NONE;
+#endif
                 }
                 if (!take_member(E)) { /* a whole run pruned */
                     if (++round >= max_rounds) return NONE; /* the warp moves on; this lane goes on in the next iteration */
@@ -1134,6 +1198,8 @@ struct SearchLane {
     {
         const FmView &f = E.fm[1 - ca];
         if (mode == JUMP) {
+            if (!B2_CHECK((int)(cpath & 31u) + pm <= f.lut_k && (uint64_t)pq < ((uint64_t)1 << (2 * ((cpath & 31u) + (uint32_t)pm))), CHK_LUT, row,
+                          (cpath & 31u) + (uint32_t)pm, pq)) { nk4[0] = 1u; nl4[0] = 0u; ns = 0; return; }
             ld_lut_pair(f.lut + 2 * lut_pair(f.lut_w, (int)(cpath & 31u) + pm, (uint64_t)pq), nk4[0], nl4[0]);
             ns = 1;
             return;

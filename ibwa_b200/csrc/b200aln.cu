@@ -277,6 +277,7 @@ __global__ void __launch_bounds__(BLK, MINB * (128 / BLK)) k_search(const __grid
                 w = base + (unsigned)__popc(m & ((1u << lane) - 1u));
                 if (w < (unsigned)A.n_work) {
                     r = A.work_list ? A.work_list[w] : (int)w;
+                    if (!B2_CHECK(r >= 0 && (A.work_list || r < A.n_work), CHK_WORK, w, r, A.n_work)) r = 0;
                     const int len = A.lens[r];
                     L.begin(A.env, heads, gs, A.arena_by_work ? w : (uint32_t)gl, A.rows_by_work ? w : (uint32_t)r, A.recs_by_work ? w : (uint32_t)r,
                             len, A.md[len], A.n_amb[r], HeadsClear<Heads>::cooperative);
@@ -564,6 +565,8 @@ struct b200aln_ctx {
     DevBuf asm_n_aln, asm_packed;    /* assembled results of a pipelined device-resident call */
 };
 
+static cudaEvent_t g_origin = nullptr; /* B200ALN_TIMELINE: common clock of the stage timeline (see timeline()) */
+
 [[noreturn]] static void die(const char *func, const char *fmt, ...)
 {
     va_list ap;
@@ -575,7 +578,24 @@ struct b200aln_ctx {
     abort();
 }
 
-extern "C" const char *b200aln_version(void) { return "b200aln 0.1 (sm_100a; device occ block 32 B / 64 bp)"; }
+#ifdef B2_CHECKED
+extern "C" const char *b200aln_version(void) { return "b200aln 0.2 (sm_100a; device occ block 32 B / 64 bp; B2_CHECKED bounds-checked build)"; }
+/* the first violation the device recorded (aln_core.cuh: B2_CHECK), reported like any fatal error */
+static void report_device_checks(const char *where)
+{
+    unsigned int rec[4] = {0, 0, 0, 0};
+    CK(cudaMemcpyFromSymbol(rec, b2::b2_check_rec, sizeof rec));
+    if (rec[0]) {
+        fprintf(stderr, "[%s] B2_CHECKED: violation %u (1 arena slot, 2 bucket, 3 empty pop, 4 width-record position, 5 record fill, "
+                        "6 interval table, 7 occ block, 8 group member, 9 work item, 10 entry count) at row %u (read %u): %u vs %u. Abort!\n",
+                where, rec[0], rec[1], rec[1] / 2, rec[2], rec[3]);
+        abort();
+    }
+}
+#else
+extern "C" const char *b200aln_version(void) { return "b200aln 0.2 (sm_100a; device occ block 32 B / 64 bp)"; }
+static inline void report_device_checks(const char *) {}
+#endif
 
 extern "C" void b200aln_opt_init(b200aln_opt_t *o)
 { /* gap_init_opt, bwtaln.c:21-37 */
@@ -685,6 +705,11 @@ extern "C" b200aln_ctx *b200aln_open(const b200aln_bwt_view_t *bwt, const b200al
     CK(cudaStreamCreateWithFlags(&c->st, cudaStreamNonBlocking));
     for (int i = 0; i < 8; ++i) CK(cudaEventCreate(&c->ev[i]));
     for (int i = 0; i < 2; ++i) CK(cudaEventCreate(&c->tm[i]));
+    if (!g_origin && getenv("B200ALN_TIMELINE")) {
+        CK(cudaEventCreate(&g_origin));
+        CK(cudaEventRecord(g_origin, c->st));
+        CK(cudaEventSynchronize(g_origin));
+    }
     upload_index(c, 0, bwt);
     upload_index(c, 1, rbwt);
     {
@@ -1144,6 +1169,7 @@ static void run_batch_device(b200aln_ctx *c, int n_reads, int max_len, const int
     CK(cudaMemcpyAsync(c->h_misc.p, c->misc.p, sizeof(Misc), cudaMemcpyDeviceToHost, c->st));
     CK(cudaStreamSynchronize(c->st));
     const Misc hm = *c->h_misc.as<Misc>();
+    report_device_checks("b200aln_batch");
     if (hm.n_bad) /* never a partial result (include/b200aln.h); the wide pass already grows what it can */
         die("b200aln_batch", "%u reads exceeded the per-read arena or record capacity of every pass (knobs arena_cap_big / rec_cap_big).", hm.n_bad);
     const int64_t total = hm.total;
@@ -1161,10 +1187,22 @@ static void run_batch_device(b200aln_ctx *c, int n_reads, int max_len, const int
     *total_out = total;
 }
 
+/* B200ALN_TIMELINE=1: where each batch's stages fall on a common clock (an event recorded when the first context
+ * was opened) — shows how the launches of contexts that share a GPU interleave */
+static void timeline(b200aln_ctx *c)
+{
+    static const bool on = getenv("B200ALN_TIMELINE") != nullptr;
+    if (!on || !g_origin) return;
+    float t[6];
+    for (int i = 1; i <= 5; ++i) CK(cudaEventElapsedTime(&t[i], g_origin, c->ev[i]));
+    fprintf(stderr, "[timeline] ctx %p width %.2f-%.2f fast %.2f-%.2f passes-end %.2f compact-end %.2f\n", (void *)c, t[1], t[2], t[2], t[3], t[4], t[5]);
+}
+
 static void finish_stats(b200aln_ctx *c, bool with_copies)
 {
     float ms = 0;
     CK(cudaEventSynchronize(c->ev[with_copies ? 6 : 5]));
+    timeline(c);
     CK(cudaEventElapsedTime(&ms, c->ev[1], c->ev[2])); c->stats.ms_width = ms;
     CK(cudaEventElapsedTime(&ms, c->ev[2], c->ev[4])); c->stats.ms_search = ms;
     CK(cudaEventElapsedTime(&ms, c->ev[4], c->ev[5])); c->stats.ms_compact = ms;

@@ -40,11 +40,28 @@ def build():
     return LIB
 
 
+LIB_CHECKED = os.path.join(HERE, "libhostharness_checked.so")
+
+
+def build_checked():
+    """The same sources with -DB2_CHECKED (aln_core.cuh): every derived index is tested, a violation aborts."""
+    if not os.path.exists(LIB_CHECKED) or any(os.path.getmtime(s) > os.path.getmtime(LIB_CHECKED) for s in SRCS):
+        subprocess.check_call(["g++", "-O1", "-g", "-std=c++17", "-fPIC", "-shared", "-DB200ALN_COUNTERS", "-DB2_CHECKED",
+                               "-o", LIB_CHECKED, SRCS[0]])
+    return LIB_CHECKED
+
+
 _lib = None
+_lib_checked = None
 
 
-def lib():
-    global _lib
+def lib(checked=False):
+    global _lib, _lib_checked
+    if checked:
+        if _lib_checked is None:
+            _lib_checked = ctypes.CDLL(build_checked())
+            _lib_checked.hh_aln_batch.restype = ctypes.c_int64
+        return _lib_checked
     if _lib is None:
         _lib = ctypes.CDLL(build())
         _lib.hh_aln_batch.restype = ctypes.c_int64
@@ -52,8 +69,8 @@ def lib():
 
 
 def aln_batch(bwt, rbwt, lens, offs, codes, opt_c, arena_cap=1 << 16, rec_cap=256, reuse=False, big_cap=0, batch_max_len=0,
-              lut_k=0, rounds=0, q16=False):
-    L = lib()
+              lut_k=0, rounds=0, q16=False, checked=False):
+    L = lib(checked)
     L.hh_set_q16(ctypes.c_int(int(q16)))    # the product's fast pass: 16-bit width records when the options allow
     L.hh_set_lut_k(ctypes.c_int(lut_k))
     L.hh_set_rounds(ctypes.c_int(rounds))   # 0 = unlimited; the fast kernel runs with 1

@@ -132,6 +132,19 @@ def test_q16_width_records_vs_oracle(args, golden_dir, g1_index):
     assert nov > 0 and np.array_equal(o_n, h_n) and o_rec.tobytes() == h_rec.tobytes()
 
 
+@pytest.mark.parametrize("tag,kw", [("default", dict(arena_cap=32000, rec_cap=4096, rounds=1, lut_k=4)),
+                                    ("stress", dict(arena_cap=32000, rec_cap=4096, q16=True, lut_k=2)),
+                                    ("m200", dict(arena_cap=1 << 22, rec_cap=4096, reuse=True)),
+                                    ("N_n2", dict(arena_cap=32000, rec_cap=4096, reuse=True, q16=True)),
+                                    ("L_e3", dict(arena_cap=48, rec_cap=2, big_cap=1 << 21))])
+def test_bounds_checked_state_machines(tag, kw, golden_dir, g1_index):
+    """The state machines compiled with -DB2_CHECKED (every arena slot, bucket, width-record position, table and
+    block address tested before use; a violation aborts the process) over the golden set's main variants."""
+    args, fq = CASES[tag]
+    got, _ = harness_sai(g1_index[0], g1_index[1], args, os.path.join(golden_dir, fq + ".fq.gz"), checked=True, **kw)
+    assert got == open(os.path.join(golden_dir, f"g1_{tag}.sai"), "rb").read()
+
+
 def test_long_reads_and_wide_score_ranges(golden_dir, g1_index):
     """1 kbp and 3 kbp reads: max_diff 23 / 75, i.e. 143 and 275 score buckets (the second needs the wide
     heads); also an empty read, which BAM input can deliver (the reference then reports the whole index)."""

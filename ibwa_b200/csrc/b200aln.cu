@@ -524,7 +524,8 @@ struct b200aln_ctx {
     FmView fm[2];
     OccBlk *d_idx[2] = {nullptr, nullptr};
     uint64_t n_blk[2] = {0, 0};
-    cudaStream_t st = nullptr;
+    cudaStream_t st = nullptr;    /* everything but the fast search pass; highest priority (see make_streams) */
+    cudaStream_t st_lo = nullptr; /* the fast pass of k_search: lowest priority */
     cudaEvent_t ev[8];
     cudaEvent_t tm[2];
     /* tuning */
@@ -627,6 +628,21 @@ extern "C" void b200aln_warm_device(int device)
     (void)cudaGetLastError();
 }
 
+/* Two streams per context.  The long kernel of a batch (the fast search pass) runs on a low-priority stream, all
+ * the short work (copies, width pass, ordering, re-run passes, scan, compact) on a high-priority one: when several
+ * contexts share a GPU, the block scheduler then hands SM slots that a draining search kernel frees to the
+ * pending short kernels of every batch first, instead of queueing them behind the whole grid of the next search
+ * kernel (measured: a 0.1 ms compaction waited 35-94 ms that way, profiles/README.md). */
+static void make_streams(b200aln_ctx *c)
+{
+    int least = 0, greatest = 0;
+    CK(cudaDeviceGetStreamPriorityRange(&least, &greatest));
+    const char *e = getenv("B200ALN_PRIO");
+    const bool on = !e || atoi(e) != 0;
+    CK(cudaStreamCreateWithPriority(&c->st, cudaStreamNonBlocking, on ? greatest : least));
+    CK(cudaStreamCreateWithPriority(&c->st_lo, cudaStreamNonBlocking, least));
+}
+
 static void upload_index(b200aln_ctx *c, int which, const b200aln_bwt_view_t *v)
 {
     const uint64_t expect = ((uint64_t)v->seq_len + 15) / 16 + 4 * (((uint64_t)v->seq_len + 127) / 128 + 1);
@@ -674,6 +690,7 @@ static void apply_l2_window(b200aln_ctx *c)
     attr.accessPolicyWindow.hitProp = cudaAccessPropertyPersisting;
     attr.accessPolicyWindow.missProp = cudaAccessPropertyStreaming;
     if (cudaStreamSetAttribute(c->st, cudaStreamAttributeAccessPolicyWindow, &attr) != cudaSuccess) (void)cudaGetLastError();
+    if (c->st_lo && cudaStreamSetAttribute(c->st_lo, cudaStreamAttributeAccessPolicyWindow, &attr) != cudaSuccess) (void)cudaGetLastError();
     if (getenv("B200ALN_VERBOSE"))
         fprintf(stderr, "[b200aln] L2 window: %.1f MB of the interval table persisting (carve-out %.1f MB)\n", bytes / 1e6, carve / 1e6);
 }
@@ -702,7 +719,7 @@ extern "C" b200aln_ctx *b200aln_open(const b200aln_bwt_view_t *bwt, const b200al
                 fprintf(stderr, "[b200aln_open] L2 fetch granularity: asked %zu, device reports %zu\n", gran, got);
         }
     }
-    CK(cudaStreamCreateWithFlags(&c->st, cudaStreamNonBlocking));
+    make_streams(c);
     for (int i = 0; i < 8; ++i) CK(cudaEventCreate(&c->ev[i]));
     for (int i = 0; i < 2; ++i) CK(cudaEventCreate(&c->tm[i]));
     if (!g_origin && getenv("B200ALN_TIMELINE")) {
@@ -777,7 +794,7 @@ extern "C" b200aln_ctx *b200aln_clone(b200aln_ctx *p)
     c->arena_cap_mid = p->arena_cap_mid; c->rec_cap_mid = p->rec_cap_mid; c->mid_lanes = p->mid_lanes;
     c->pop_batch = p->pop_batch; c->count = p->count; c->reserve_reads = p->reserve_reads; c->prep_rounds = p->prep_rounds;
     c->prefetch_fast = p->prefetch_fast; c->prefetch_mid = p->prefetch_mid; c->order = p->order; c->search_block = p->search_block; c->q16 = p->q16;
-    CK(cudaStreamCreateWithFlags(&c->st, cudaStreamNonBlocking));
+    make_streams(c);
     for (int i = 0; i < 8; ++i) CK(cudaEventCreate(&c->ev[i]));
     for (int i = 0; i < 2; ++i) CK(cudaEventCreate(&c->tm[i]));
     memset(&c->stats, 0, sizeof c->stats);
@@ -844,6 +861,7 @@ extern "C" void b200aln_close(b200aln_ctx *c)
     for (int i = 0; i < 8; ++i) cudaEventDestroy(c->ev[i]);
     for (int i = 0; i < 2; ++i) cudaEventDestroy(c->tm[i]);
     cudaStreamDestroy(c->st);
+    cudaStreamDestroy(c->st_lo);
     delete c;
 }
 
@@ -934,20 +952,20 @@ static void launch_search_fast(b200aln_ctx *c, SearchArgs &A, int blocks, bool q
         const size_t smem = (size_t)A.env.P.n_buckets * 128 * sizeof(uint16_t);
         const bool six = c->search_blocks_per_sm == 6;
         if (q16) { /* 16-bit width records (run_batch_device: q16_ok) */
-            if (c->count) k_search<HeadsStrided16, false, 6, true, 128, 16><<<blocks, 128, smem, c->st>>>(A);
-            else if (c->search_block == 32 && six) k_search<HeadsStrided16, false, 6, false, 32, 16><<<blocks * 4, 32, smem / 4, c->st>>>(A);
-            else if (six) k_search<HeadsStrided16, false, 6, false, 128, 16><<<blocks, 128, smem, c->st>>>(A);
-            else k_search<HeadsStrided16, false, 1, false, 128, 16><<<blocks, 128, smem, c->st>>>(A);
-        } else if (c->count) k_search<HeadsStrided16, false, 6, true><<<blocks, 128, smem, c->st>>>(A); /* with pop / sector counters */
+            if (c->count) k_search<HeadsStrided16, false, 6, true, 128, 16><<<blocks, 128, smem, c->st_lo>>>(A);
+            else if (c->search_block == 32 && six) k_search<HeadsStrided16, false, 6, false, 32, 16><<<blocks * 4, 32, smem / 4, c->st_lo>>>(A);
+            else if (six) k_search<HeadsStrided16, false, 6, false, 128, 16><<<blocks, 128, smem, c->st_lo>>>(A);
+            else k_search<HeadsStrided16, false, 1, false, 128, 16><<<blocks, 128, smem, c->st_lo>>>(A);
+        } else if (c->count) k_search<HeadsStrided16, false, 6, true><<<blocks, 128, smem, c->st_lo>>>(A); /* with pop / sector counters */
         else if (c->search_block == 32 && six) /* same lanes, one warp per block */
-            k_search<HeadsStrided16, false, 6, false, 32><<<blocks * 4, 32, smem / 4, c->st>>>(A);
-        else if (six) k_search<HeadsStrided16, false, 6, false><<<blocks, 128, smem, c->st>>>(A);
-        else k_search<HeadsStrided16, false, 1, false><<<blocks, 128, smem, c->st>>>(A);
+            k_search<HeadsStrided16, false, 6, false, 32><<<blocks * 4, 32, smem / 4, c->st_lo>>>(A);
+        else if (six) k_search<HeadsStrided16, false, 6, false><<<blocks, 128, smem, c->st_lo>>>(A);
+        else k_search<HeadsStrided16, false, 1, false><<<blocks, 128, smem, c->st_lo>>>(A);
     } else {
         A.heads_wide_stride = A.env.P.n_buckets + (A.env.P.n_buckets + 31) / 32;
         c->heads_wide.need((size_t)blocks * 128 * A.heads_wide_stride * 4);
         A.heads_wide = c->heads_wide.as<uint32_t>();
-        k_search<HeadsWide32, false, 1, true><<<blocks, 128, 0, c->st>>>(A);
+        k_search<HeadsWide32, false, 1, true><<<blocks, 128, 0, c->st_lo>>>(A);
     }
     CK(cudaGetLastError());
 }
@@ -1053,9 +1071,11 @@ static void run_batch_device(b200aln_ctx *c, int n_reads, int max_len, const int
     SA.arena_by_work = 0; SA.n_rec_full = nullptr;
     SA.pop_batch = c->pop_batch;
     SA.prep_rounds = c->prep_rounds;
+    CK(cudaStreamWaitEvent(c->st_lo, c->ev[2], 0)); /* the fast pass: on the low-priority stream, fenced on both sides */
     launch_search_fast(c, SA, sblocks, q16);
     ++launches;
-    CK(cudaEventRecord(c->ev[3], c->st));
+    CK(cudaEventRecord(c->ev[3], c->st_lo));
+    CK(cudaStreamWaitEvent(c->st, c->ev[3], 0));
 
     /* Reads whose stack or record slab outgrew the fast pass are searched again from scratch:
      * middle pass = the same fast kernel with a larger arena / record slab (repeat-rich reads with

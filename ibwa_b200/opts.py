@@ -112,14 +112,14 @@ def parse_aln_args(argv):
     opte = -1
     out = None
     try:
-        pairs, rest = getopt.getopt(list(argv), ALN_GETOPT)
+        pairs, rest = getopt.gnu_getopt(list(argv), ALN_GETOPT)   # glibc getopt permutes: options may follow operands
     except getopt.GetoptError as e:  # reference: `default: return 1`
         raise UsageError(str(e))
     for flag, val in pairs:
         f = flag[1]
         if f == "n":
             if "." in val:
-                opt.fnr, opt.max_diff = float(val), -1
+                opt.fnr, opt.max_diff = _atof(val), -1
             else:
                 opt.max_diff, opt.fnr = _atoi(val), -1.0
         elif f == "o": opt.max_gapo = _atoi(val)
@@ -153,6 +153,13 @@ def parse_aln_args(argv):
     if len(rest) < 2:
         raise UsageError("Usage:   bwa aln [options] <prefix> <in.fq>")
     return opt, rest[0], rest[1], out
+
+
+def _atof(s: str) -> float:
+    """C atof: the longest numeric prefix (sign, digits, fraction, exponent), 0.0 when there is none."""
+    import re
+    m = re.match(r"\s*[+-]?(\d+\.?\d*([eE][+-]?\d+)?|\.\d+([eE][+-]?\d+)?)", s)
+    return float(m.group(0)) if m else 0.0
 
 
 def _atoi(s: str) -> int:

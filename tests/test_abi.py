@@ -63,3 +63,15 @@ def test_bwa_seq_layout_against_reference_header(tmp_path):
     engine.load_library().b200aln_seq_layout(ctypes.byref(lay))
     assert got == [lay.size, lay.off_name, lay.off_seq, lay.off_rseq, lay.off_qual, lay.off_n_aln, lay.off_aln,
                    lay.off_sa]
+
+
+def test_python_option_parser_follows_glibc_getopt_and_atof():
+    """bwa_aln parses with glibc getopt (options may follow operands) and atof / atoi (numeric prefix, 0 when there is
+    none; bwtaln.c:249-284): the Python mirror used by tests and bench.py must read the same command lines alike."""
+    from ibwa_b200 import parse_aln_args
+    o, prefix, reads, _ = parse_aln_args(["pfx", "-n", "0.01x", "reads.fq", "-o", "2junk", "-e", "abc"])
+    assert (prefix, reads) == ("pfx", "reads.fq")
+    assert abs(o.fnr - 0.01) < 1e-9 and o.max_diff == -1 and o.max_gapo == 2
+    assert o.max_gape == 6 and o.mode & 1            # -e 0 (atoi of "abc") leaves the defaults
+    o, _, _, _ = parse_aln_args(["-n", "3", "p", "r"])
+    assert o.max_diff == 3 and o.fnr == -1.0

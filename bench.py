@@ -403,8 +403,10 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--model", default=None, choices=["default", "stress"], help="read model (SURVEY 8d)")
     ap.add_argument("--aln-args", default=None, help="aln options for the run, e.g. '-n 4 -o 2 -e 10 -l 32 -k 2'")
-    ap.add_argument("--in-flight", type=int, default=3,
-                    help="steps in flight (contexts sharing the device index) in the value / e2e measurements")
+    ap.add_argument("--in-flight", type=int, default=None,
+                    help="steps in flight (contexts sharing the device index) in the value / e2e measurements; default "
+                         "3 for >= 8 M reads per GPU and step, 4 from 4 M, else 6 (small launches need a deeper pipeline: "
+                         "the engine then parks the stragglers of a draining launch, DESIGN.md)")
     ap.add_argument("--parity-pairs", type=int, default=200_000, help="configs 4/5: pairs through sampe -R")
     ap.add_argument("--set", action="append", default=[], help="engine knob key=value")
     args = ap.parse_args()
@@ -537,6 +539,8 @@ def main():
         return 0
 
     # ---- our arm ------------------------------------------------------------
+    if args.in_flight is None:
+        args.in_flight = 3 if n_rank >= 8_000_000 or args.config == 3 else 4 if n_rank >= 4_000_000 else 6   # config 3: its re-run arenas are large
     K = max(1, args.in_flight)
     eng = engine.Engine(bwt, rbwt, local_rank)
     knobs = [kv.split("=") for kv in args.set]

@@ -784,6 +784,7 @@ struct HeadsWide32 {
     B2_HD void set(int sc, uint32_t slot) { h[sc] = slot; }
 };
 
+#define B2_SAVE_WORDS 36 /* SearchLane::save_state: 33 words used, + the read and the work item of the kernel's lane */
 enum LaneStatus { LANE_OK = 0, LANE_ARENA_FULL = 1, LANE_REC_FULL = 2, LANE_CHECK = 3 /* B2_CHECKED: a violation */ };
 
 /*
@@ -1130,6 +1131,36 @@ struct SearchLane {
 
     /* true when the next entry does not have to come from memory */
     B2_HD bool ready() const { return have_cur || extending || og != 0; }
+
+    /*
+     * Suspension (b200aln.cu: stragglers of a draining launch are parked and resumed in dense warps): the
+     * lane's whole state between two steps, as B2_SAVE_WORDS words.  Everything else a search owns lives in
+     * memory already (arena, width rows, record slab) and stays where it is — lane_no keeps naming the arena —
+     * except the bucket heads and the open group, which the caller saves next to these words and puts back
+     * (bk, gs are re-pointed by the caller after load_state).
+     */
+    B2_HD void save_state(uint32_t *d) const
+    {
+        d[0] = lane_no; d[1] = row; d[2] = slab; d[3] = (uint32_t)len; d[4] = (uint32_t)opt_max_diff;
+        d[5] = top; d[6] = free_head; d[7] = (uint32_t)best; d[8] = (uint32_t)n_mem;
+        d[9] = (uint32_t)prefetch_next | (uint32_t)finished << 1 | (uint32_t)have_cur << 2 | (uint32_t)extending << 3;
+        d[10] = (uint32_t)n_entries; d[11] = (uint32_t)max_diff; d[12] = (uint32_t)best_score; d[13] = (uint32_t)best_diff;
+        d[14] = (uint32_t)best_cnt; d[15] = (uint32_t)n_aln; d[16] = (uint32_t)status;
+        d[17] = ck; d[18] = cl; d[19] = (uint32_t)ci; d[20] = (uint32_t)cldp; d[21] = (uint32_t)cmm; d[22] = (uint32_t)cgo;
+        d[23] = (uint32_t)cge; d[24] = (uint32_t)cstate; d[25] = (uint32_t)ca; d[26] = (uint32_t)cscore; d[27] = cpath;
+        d[28] = og; d[29] = n_pops; d[30] = n_lookups; d[31] = pq; d[32] = (uint32_t)pm;
+    }
+    B2_HD void load_state(const uint32_t *d)
+    {
+        lane_no = d[0]; row = d[1]; slab = d[2]; len = (int)d[3]; opt_max_diff = (int)d[4];
+        top = d[5]; free_head = d[6]; best = (int)d[7]; n_mem = (int)d[8];
+        prefetch_next = d[9] & 1u; finished = d[9] >> 1 & 1u; have_cur = d[9] >> 2 & 1u; extending = d[9] >> 3 & 1u;
+        n_entries = (int)d[10]; max_diff = (int)d[11]; best_score = (int)d[12]; best_diff = (int)d[13];
+        best_cnt = (int)d[14]; n_aln = (int)d[15]; status = (int)d[16];
+        ck = d[17]; cl = d[18]; ci = (int)d[19]; cldp = (int)d[20]; cmm = (int)d[21]; cgo = (int)d[22];
+        cge = (int)d[23]; cstate = (int)d[24]; ca = (int)d[25]; cscore = (int)d[26]; cpath = d[27];
+        og = d[28]; n_pops = d[29]; n_lookups = d[30]; pq = d[31]; pm = (int)d[32];
+    }
 
     /* max_rounds: how many pruned pops (a run of group members, or a single entry failing the width bound) the
      * lane may go through before it gives the warp's iteration back without a lookup — the other lanes do not

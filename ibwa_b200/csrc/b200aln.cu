@@ -188,7 +188,19 @@ struct SearchArgs {
     unsigned int *n_rec_full; /* counts the reads that ran out of record slab (null: not wanted) */
     int pop_batch; /* lanes of a warp that must wait for a memory pop before the warp takes them */
     int prep_rounds; /* pops / prunes a lane may go through per warp iteration before the warp moves on */
+    /* Parking: once the work queue is dry, a warp in which at most susp_thresh lanes are still
+     * searching writes their state out (SearchLane::save_state + bucket heads + open group, SUSP_STRIDE words per
+     * lane) and leaves the SM; a following launch with resume_in set picks the parked searches up again, 32 to a
+     * warp.  A launch's stragglers then cost the slots of a few dense warps instead of one sparse warp each. */
+    int susp_thresh;
+    uint32_t *susp_out;
+    unsigned int *n_susp;
+    const uint32_t *resume_in; /* non-null: work item w is parked lane w of this buffer */
 };
+#define SUSP_GROUP_AT B2_SAVE_WORDS             /* open group words */
+#define SUSP_HEADS_AT 48                        /* bucket heads, two 16-bit heads per word */
+#define SUSP_STRIDE (SUSP_HEADS_AT + 80)        /* words per parked lane (n_buckets <= 160: fast_heads_ok) */
+static_assert(B2_SAVE_WORDS + OG_WORDS <= SUSP_HEADS_AT, "parked-lane layout");
 
 template <class Heads> struct HeadsFactory;
 template <> struct HeadsFactory<HeadsStrided16> {
@@ -275,7 +287,17 @@ __global__ void __launch_bounds__(BLK, MINB * (128 / BLK)) k_search(const __grid
             }
             if (need) {
                 w = base + (unsigned)__popc(m & ((1u << lane) - 1u));
-                if (w < (unsigned)A.n_work) {
+                if (w < (unsigned)A.n_work && A.resume_in) { /* a parked search goes on in this lane */
+                    const uint32_t *sv = A.resume_in + (size_t)w * SUSP_STRIDE;
+                    L.load_state(sv);
+                    L.bk = heads;
+                    L.gs = gs;
+                    r = (int)sv[B2_SAVE_WORDS - 3];
+                    w = sv[B2_SAVE_WORDS - 2];
+                    for (int i = 0; i < OG_WORDS; ++i) gs.set(i, sv[SUSP_GROUP_AT + i]);
+                    for (int b = 0; b < A.env.P.n_buckets; ++b) L.bk.set(b, sv[SUSP_HEADS_AT + (b >> 1)] >> (16 * (b & 1)) & 0xffffu);
+                    active = true;
+                } else if (w < (unsigned)A.n_work) {
                     r = A.work_list ? A.work_list[w] : (int)w;
                     if (!B2_CHECK(r >= 0 && (A.work_list || r < A.n_work), CHK_WORK, w, r, A.n_work)) r = 0;
                     const int len = A.lens[r];
@@ -319,6 +341,27 @@ __global__ void __launch_bounds__(BLK, MINB * (128 / BLK)) k_search(const __grid
                     if (A.over_slot) A.over_slot[r] = (int32_t)w | A.slot_tag;
                 }
                 active = false;
+            }
+        }
+        if (A.susp_thresh > 0) { /* the queue is dry and this warp has become sparse: park what is left, leave */
+            const unsigned dry = __ballot_sync(FULL, !alive), act = __ballot_sync(FULL, active);
+            if (dry && act && __popc(act) <= A.susp_thresh) {
+                const int leader = __ffs((int)act) - 1;
+                unsigned base = 0;
+                if (lane == leader) base = atomicAdd(A.n_susp, (unsigned)__popc(act));
+                base = __shfl_sync(FULL, base, leader);
+                if (active) {
+                    uint32_t *sv = A.susp_out + (size_t)(base + (unsigned)__popc(act & ((1u << lane) - 1u))) * SUSP_STRIDE;
+                    L.save_state(sv);
+                    sv[B2_SAVE_WORDS - 3] = (uint32_t)r;
+                    sv[B2_SAVE_WORDS - 2] = w;
+                    for (int i = 0; i < OG_WORDS; ++i) sv[SUSP_GROUP_AT + i] = gs.get(i);
+                    const int nb = A.env.P.n_buckets;
+                    for (int b = 0; b < nb; b += 2)
+                        sv[SUSP_HEADS_AT + (b >> 1)] = (L.bk.get(b) & 0xffffu) | (b + 1 < nb ? L.bk.get(b + 1) : 0xffffu) << 16;
+                    active = false;
+                }
+                alive = false;
             }
         }
     }
@@ -538,6 +581,12 @@ struct b200aln_ctx {
     int order = 1;         /* fast pass takes the reads by work class, longest searches first (0: arrival order) */
     int search_block = 128; /* lanes per block of the fast pass (128 or 32) */
     int q16 = 1;            /* 16-bit width records in the fast pass when the options allow them (0: always 32-bit) */
+    int susp = -16;         /* fast pass: a warp with at most |susp| lanes still searching once the queue is dry parks them.  > 0: always;
+                             * < 0: only while at least susp_calls batches are in flight on this device index (parking trades a batch's
+                             * latency for SM slots, which pays when other batches are there to use them); 0: never */
+    int susp_calls = 4;
+    std::atomic<int> active_calls{0}; /* owner: batch calls in flight on this index (all contexts sharing it) */
+    int susp_min = 4096;    /* resume rounds park again only while more than this many searches are left */
     int prep_rounds = 1;   /* pruned pops a lane may go through per warp iteration before the warp moves on */
     int reserve_reads = 0; /* size the per-batch buffers for at least this many reads */
     int count = 0;         /* 1: fast pass with the pop / sector counters (b200aln_stats_t pops, occ_lookups) */
@@ -564,6 +613,7 @@ struct b200aln_ctx {
     int n_clones = 0;                /* owner: live clones (public and internal) */
     std::vector<b200aln_ctx *> slot; /* internal siblings 1 .. slots-1 */
     DevBuf asm_n_aln, asm_packed;    /* assembled results of a pipelined device-resident call */
+    DevBuf susp_buf[2];              /* parked lanes (SUSP_STRIDE words each), ping-pong between resume rounds */
 };
 
 static cudaEvent_t g_origin = nullptr; /* B200ALN_TIMELINE: common clock of the stage timeline (see timeline()) */
@@ -793,7 +843,7 @@ extern "C" b200aln_ctx *b200aln_clone(b200aln_ctx *p)
     c->rec_cap = p->rec_cap; c->rec_cap_big = p->rec_cap_big; c->big_lanes = p->big_lanes;
     c->arena_cap_mid = p->arena_cap_mid; c->rec_cap_mid = p->rec_cap_mid; c->mid_lanes = p->mid_lanes;
     c->pop_batch = p->pop_batch; c->count = p->count; c->reserve_reads = p->reserve_reads; c->prep_rounds = p->prep_rounds;
-    c->prefetch_fast = p->prefetch_fast; c->prefetch_mid = p->prefetch_mid; c->order = p->order; c->search_block = p->search_block; c->q16 = p->q16;
+    c->prefetch_fast = p->prefetch_fast; c->prefetch_mid = p->prefetch_mid; c->order = p->order; c->search_block = p->search_block; c->q16 = p->q16; c->susp = p->susp; c->susp_min = p->susp_min; c->susp_calls = p->susp_calls;
     make_streams(c);
     for (int i = 0; i < 8; ++i) CK(cudaEventCreate(&c->ev[i]));
     for (int i = 0; i < 2; ++i) CK(cudaEventCreate(&c->tm[i]));
@@ -852,6 +902,7 @@ extern "C" void b200aln_close(b200aln_ctx *c)
     for (DevBuf *b : bufs) b->release();
     c->grp_in.release(); c->grp_out.release();
     c->asm_n_aln.release(); c->asm_packed.release();
+    c->susp_buf[0].release(); c->susp_buf[1].release();
     c->h_in.release(); c->h_out.release(); c->h_misc.release(); c->h_nout.release();
     if (c->owns_index) {
         for (int i = 0; i < 2; ++i) if (c->d_sa[i]) cudaFree(c->d_sa[i]);
@@ -892,6 +943,9 @@ extern "C" void b200aln_set_int(b200aln_ctx *c, const char *key, int64_t v)
     else if (!strcmp(key, "order")) c->order = (int)v;
     else if (!strcmp(key, "search_block")) c->search_block = (int)v;
     else if (!strcmp(key, "q16")) c->q16 = (int)v;
+    else if (!strcmp(key, "susp")) c->susp = (int)v;
+    else if (!strcmp(key, "susp_calls")) c->susp_calls = (int)v;
+    else if (!strcmp(key, "susp_min")) c->susp_min = (int)v;
     else if (!strcmp(key, "prefetch_fast")) c->prefetch_fast = (int)v;
     else if (!strcmp(key, "prefetch_mid")) c->prefetch_mid = (int)v;
     else if (!strcmp(key, "arena_cap_mid")) c->arena_cap_mid = (uint32_t)v;
@@ -930,6 +984,7 @@ extern "C" void b200aln_last_stats(const b200aln_ctx *c, b200aln_stats_t *out) {
 /* device-side counters of one batch */
 struct Misc {
     unsigned int counter, n_over, counter_big, counter_mid, n_over2, n_over3, n_rec_full, n_bad;
+    unsigned int n_susp[2], counter_res; /* parked lanes of the current / the next resume round; the resume rounds' work counter */
     unsigned long long stat[2];
     long long total;
     unsigned int class_cnt[B2_N_CLASSES], class_fill[B2_N_CLASSES];
@@ -946,26 +1001,26 @@ static void launch_search_mid(b200aln_ctx *c, SearchArgs &A, int blocks)
     CK(cudaGetLastError());
 }
 
-static void launch_search_fast(b200aln_ctx *c, SearchArgs &A, int blocks, bool q16)
+static void launch_search_fast(b200aln_ctx *c, SearchArgs &A, int blocks, bool q16, cudaStream_t st)
 {
     if (fast_heads_ok(A.env.P, A.env.arena_cap)) {
         const size_t smem = (size_t)A.env.P.n_buckets * 128 * sizeof(uint16_t);
         const bool six = c->search_blocks_per_sm == 6;
         if (q16) { /* 16-bit width records (run_batch_device: q16_ok) */
-            if (c->count) k_search<HeadsStrided16, false, 6, true, 128, 16><<<blocks, 128, smem, c->st_lo>>>(A);
-            else if (c->search_block == 32 && six) k_search<HeadsStrided16, false, 6, false, 32, 16><<<blocks * 4, 32, smem / 4, c->st_lo>>>(A);
-            else if (six) k_search<HeadsStrided16, false, 6, false, 128, 16><<<blocks, 128, smem, c->st_lo>>>(A);
-            else k_search<HeadsStrided16, false, 1, false, 128, 16><<<blocks, 128, smem, c->st_lo>>>(A);
-        } else if (c->count) k_search<HeadsStrided16, false, 6, true><<<blocks, 128, smem, c->st_lo>>>(A); /* with pop / sector counters */
+            if (c->count) k_search<HeadsStrided16, false, 6, true, 128, 16><<<blocks, 128, smem, st>>>(A);
+            else if (c->search_block == 32 && six) k_search<HeadsStrided16, false, 6, false, 32, 16><<<blocks * 4, 32, smem / 4, st>>>(A);
+            else if (six) k_search<HeadsStrided16, false, 6, false, 128, 16><<<blocks, 128, smem, st>>>(A);
+            else k_search<HeadsStrided16, false, 1, false, 128, 16><<<blocks, 128, smem, st>>>(A);
+        } else if (c->count) k_search<HeadsStrided16, false, 6, true><<<blocks, 128, smem, st>>>(A); /* with pop / sector counters */
         else if (c->search_block == 32 && six) /* same lanes, one warp per block */
-            k_search<HeadsStrided16, false, 6, false, 32><<<blocks * 4, 32, smem / 4, c->st_lo>>>(A);
-        else if (six) k_search<HeadsStrided16, false, 6, false><<<blocks, 128, smem, c->st_lo>>>(A);
-        else k_search<HeadsStrided16, false, 1, false><<<blocks, 128, smem, c->st_lo>>>(A);
+            k_search<HeadsStrided16, false, 6, false, 32><<<blocks * 4, 32, smem / 4, st>>>(A);
+        else if (six) k_search<HeadsStrided16, false, 6, false><<<blocks, 128, smem, st>>>(A);
+        else k_search<HeadsStrided16, false, 1, false><<<blocks, 128, smem, st>>>(A);
     } else {
         A.heads_wide_stride = A.env.P.n_buckets + (A.env.P.n_buckets + 31) / 32;
         c->heads_wide.need((size_t)blocks * 128 * A.heads_wide_stride * 4);
         A.heads_wide = c->heads_wide.as<uint32_t>();
-        k_search<HeadsWide32, false, 1, true><<<blocks, 128, 0, c->st_lo>>>(A);
+        k_search<HeadsWide32, false, 1, true><<<blocks, 128, 0, st>>>(A);
     }
     CK(cudaGetLastError());
 }
@@ -1071,11 +1126,42 @@ static void run_batch_device(b200aln_ctx *c, int n_reads, int max_len, const int
     SA.arena_by_work = 0; SA.n_rec_full = nullptr;
     SA.pop_batch = c->pop_batch;
     SA.prep_rounds = c->prep_rounds;
+    /* parking of sparse warps (SearchArgs): only the shared-memory-heads kernels, and not the counting instance */
+    const b200aln_ctx *owner = c->parent ? c->parent : c;
+    const int park_at = c->susp > 0 ? c->susp : (c->susp < 0 && owner->active_calls.load() >= c->susp_calls ? -c->susp : 0);
+    const bool parking = park_at > 0 && !c->count && fast_heads_ok(P, c->arena_cap);
+    SA.susp_thresh = 0; SA.susp_out = nullptr; SA.n_susp = nullptr; SA.resume_in = nullptr;
+    if (parking) {
+        for (int i = 0; i < 2; ++i) c->susp_buf[i].need(lanes * SUSP_STRIDE * 4);
+        SA.susp_thresh = park_at; SA.susp_out = c->susp_buf[0].as<uint32_t>(); SA.n_susp = &dm->n_susp[0];
+    }
     CK(cudaStreamWaitEvent(c->st_lo, c->ev[2], 0)); /* the fast pass: on the low-priority stream, fenced on both sides */
-    launch_search_fast(c, SA, sblocks, q16);
+    launch_search_fast(c, SA, sblocks, q16, c->st_lo);
     ++launches;
     CK(cudaEventRecord(c->ev[3], c->st_lo));
     CK(cudaStreamWaitEvent(c->st, c->ev[3], 0));
+    if (parking) { /* resume rounds: the parked searches, dense again, on the high-priority stream */
+        int cur = 0;
+        for (int round = 0;; ++round) {
+            CK(cudaMemcpyAsync(c->h_misc.p, c->misc.p, sizeof(Misc), cudaMemcpyDeviceToHost, c->st));
+            CK(cudaStreamSynchronize(c->st));
+            const unsigned n_parked = c->h_misc.as<Misc>()->n_susp[cur];
+            if (!n_parked) break;
+            if (n_parked > lanes) die("b200aln_batch", "internal: %u parked lanes of %zu.", n_parked, lanes);
+            SearchArgs SR = SA;
+            SR.resume_in = c->susp_buf[cur].as<uint32_t>(); SR.n_work = (int)n_parked; SR.work_list = nullptr;
+            SR.counter = &dm->counter_res;
+            SR.susp_out = c->susp_buf[cur ^ 1].as<uint32_t>(); SR.n_susp = &dm->n_susp[cur ^ 1];
+            SR.susp_thresh = n_parked > (unsigned)c->susp_min && round < 24 ? park_at : 0;
+            CK(cudaMemsetAsync(&dm->counter_res, 0, 4, c->st));
+            CK(cudaMemsetAsync(&dm->n_susp[cur ^ 1], 0, 4, c->st));
+            int rblocks = (int)((n_parked + 127) / 128);
+            if (rblocks > sblocks) rblocks = sblocks;
+            launch_search_fast(c, SR, rblocks, q16, c->st);
+            ++launches;
+            cur ^= 1;
+        }
+    }
 
     /* Reads whose stack or record slab outgrew the fast pass are searched again from scratch:
      * middle pass = the same fast kernel with a larger arena / record slab (repeat-rich reads with
@@ -1114,6 +1200,7 @@ static void run_batch_device(b200aln_ctx *c, int n_reads, int max_len, const int
         CK(cudaGetLastError());
         ++launches;
         SearchArgs SM = SA;
+        SM.susp_thresh = 0; SM.resume_in = nullptr; /* the re-run passes run every search to its end */
         SM.env.Q = WM.Q; SM.env.W = WM.W; SM.env.strideQ = strideQ32; SM.rows_by_work = 1;
         SM.n_work = (int)n_over; SM.work_list = c->over_list.as<int32_t>();
         SM.env.ent = c->ent_mid.as<StackRec>(); SM.env.arena_cap = c->arena_cap_mid;
@@ -1153,6 +1240,7 @@ static void run_batch_device(b200aln_ctx *c, int n_reads, int max_len, const int
             CK(cudaGetLastError());
             ++launches;
             SearchArgs SB = SA;
+            SB.susp_thresh = 0; SB.resume_in = nullptr;
             SB.env.Q = WB.Q; SB.env.W = WB.W; SB.env.strideQ = strideQ32; SB.rows_by_work = 1;
             SB.n_work = (int)n_wide; SB.work_list = wide_list;
             SB.env.ent = c->ent_big.as<StackRec>(); SB.env.arena_cap = cap_big; SB.arena_by_work = by_work ? 1 : 0;
@@ -1249,6 +1337,13 @@ static void add_stats(b200aln_stats_t &acc, const b200aln_stats_t &s)
     acc.ms_d2h += s.ms_d2h; acc.kernel_launches += s.kernel_launches; acc.overflow_reads += s.overflow_reads;
     acc.pops += s.pops; acc.occ_lookups += s.occ_lookups;
 }
+
+/* counts a public batch call in on its device index for its duration (SearchArgs parking: `susp` < 0) */
+struct CallInFlight {
+    b200aln_ctx *o;
+    explicit CallInFlight(b200aln_ctx *c) : o(c->parent ? c->parent : c) { o->active_calls.fetch_add(1); }
+    ~CallInFlight() { o->active_calls.fetch_sub(1); }
+};
 
 /* the siblings a pipelined call runs its chunks on (created once, kept) */
 static void ensure_slots(b200aln_ctx *c)
@@ -1369,6 +1464,7 @@ extern "C" const b200aln_rec_t *b200aln_batch(b200aln_ctx *c, int n_reads, const
                                               int64_t *total)
 {
     CK(cudaSetDevice(c->device));
+    CallInFlight in_flight(c);
     *total = 0;
     if (n_reads <= 0) return c->h_out.as<b200aln_rec_t>();
     int max_len = 0;
@@ -1441,6 +1537,7 @@ extern "C" void b200aln_batch_device(b200aln_ctx *c, int n_reads, int max_len, c
                                      const int32_t **d_n_aln, const b200aln_rec_t **d_recs, int64_t *total)
 {
     CK(cudaSetDevice(c->device));
+    CallInFlight in_flight(c);
     Params P;
     std::vector<int> md;
     std::vector<int32_t> one(1, max_len);

@@ -50,6 +50,41 @@ template <> HeadsWide32 make_heads<HeadsWide32>(std::vector<uint32_t> &store)
     return hd;
 }
 
+static int g_susp = 0; /* > 0: park the lane every g_susp steps and resume it in a fresh SearchLane (save_state / load_state) */
+extern "C" void hh_set_suspend_every(int n) { g_susp = n; }
+
+/* runs `lane` to the end; with g_susp the search is interrupted every g_susp steps exactly as the kernel parks a
+ * straggler: state words, bucket heads and open group copied out, the originals scribbled over, a new lane loaded */
+template <class Lane, class Heads>
+static void run_lane(Lane &lane, const SearchEnv &e, Heads heads, std::vector<uint32_t> &hstore, GroupStore gs, int n_buckets)
+{
+    if (g_susp <= 0) {
+        while (!lane.finished) lane.step(e, g_rounds);
+        return;
+    }
+    std::vector<uint32_t> words(B2_SAVE_WORDS), hcopy, gcopy(OG_WORDS);
+    int steps = 0;
+    while (!lane.finished) {
+        lane.step(e, g_rounds);
+        if (++steps % g_susp == 0 && !lane.finished) {
+            lane.save_state(words.data());
+            hcopy.assign(hstore.begin(), hstore.end());
+            for (int w = 0; w < OG_WORDS; ++w) gcopy[w] = gs.get(w);
+            for (auto &x : hstore) x = 0xA5A5A5A5u;
+            for (int w = 0; w < OG_WORDS; ++w) gs.set(w, 0xDEADBEEFu);
+            Lane fresh;
+            memset((void *)&fresh, 0x5A, sizeof fresh);
+            fresh.load_state(words.data());
+            fresh.bk = heads;
+            fresh.gs = gs;
+            hstore.assign(hcopy.begin(), hcopy.end());
+            for (int w = 0; w < OG_WORDS; ++w) gs.set(w, gcopy[w]);
+            lane = fresh;
+        }
+    }
+    (void)n_buckets;
+}
+
 static int g_q16 = 0; /* 1: the first pass uses the 16-bit width records when the options allow them (like the product) */
 extern "C" void hh_set_q16(int v) { g_q16 = v; }
 static int g_last_q16 = 0; /* whether the last hh_aln_batch call really ran on the 16-bit records */
@@ -86,7 +121,7 @@ static int64_t run(const SearchEnv &env, const std::vector<int> &md, int n_reads
         e1.Q = Q.data(); e1.W = W.data(); e1.strideQ = strideQ; e1.strideW = strideW;
         e1.recs = recs.data(); e1.rec_cap = rec_cap; e1.ent = ent.data(); e1.arena_cap = arena_cap;
         lane.begin(e1, make_heads<Heads>(hstore), gs, 0, 0, 0, len, md[len], n_amb);
-        while (!lane.finished) lane.step(e1, g_rounds);
+        run_lane(lane, e1, make_heads<Heads>(hstore), hstore, gs, env.P.n_buckets);
         if (lane.status != LANE_OK && big_cap) {
             /* the product's large pass: widths rebuilt (the aborted pass shadowed them), free-list arena */
             ++n_status;
@@ -97,7 +132,7 @@ static int64_t run(const SearchEnv &env, const std::vector<int> &md, int n_reads
             SearchEnv e2 = e1;
             e2.recs = recs2.data(); e2.rec_cap = 1 << 16; e2.ent = ent2.data(); e2.arena_cap = big_cap;
             big.begin(e2, make_heads<HeadsWide32>(hstore), gs, 0, 0, 0, len, md[len], n_amb);
-            while (!big.finished) big.step(e2, g_rounds);
+            run_lane(big, e2, make_heads<HeadsWide32>(hstore), hstore, gs, env.P.n_buckets);
             if (big.status != LANE_OK) { n_aln[r] = -big.status; continue; }
             n_aln[r] = big.n_aln;
             all.insert(all.end(), recs2.begin(), recs2.begin() + big.n_aln);

@@ -69,8 +69,9 @@ def lib(checked=False):
 
 
 def aln_batch(bwt, rbwt, lens, offs, codes, opt_c, arena_cap=1 << 16, rec_cap=256, reuse=False, big_cap=0, batch_max_len=0,
-              lut_k=0, rounds=0, q16=False, checked=False):
+              lut_k=0, rounds=0, q16=False, checked=False, suspend_every=0):
     L = lib(checked)
+    L.hh_set_suspend_every(ctypes.c_int(suspend_every))   # > 0: park / resume the lane every so many steps
     L.hh_set_q16(ctypes.c_int(int(q16)))    # the product's fast pass: 16-bit width records when the options allow
     L.hh_set_lut_k(ctypes.c_int(lut_k))
     L.hh_set_rounds(ctypes.c_int(rounds))   # 0 = unlimited; the fast kernel runs with 1

@@ -145,6 +145,20 @@ def test_bounds_checked_state_machines(tag, kw, golden_dir, g1_index):
     assert got == open(os.path.join(golden_dir, f"g1_{tag}.sai"), "rb").read()
 
 
+@pytest.mark.parametrize("tag,kw", [("default", dict(arena_cap=32000, rec_cap=4096, rounds=1, suspend_every=1)),
+                                    ("stress", dict(arena_cap=32000, rec_cap=4096, q16=True, lut_k=3, suspend_every=7)),
+                                    ("m200", dict(arena_cap=32000, rec_cap=4096, reuse=True, suspend_every=3)),
+                                    ("N_n2", dict(arena_cap=1 << 22, rec_cap=4096, reuse=True, suspend_every=50)),
+                                    ("short_o3", dict(arena_cap=32000, rec_cap=4096, q16=True, suspend_every=2, checked=True))])
+def test_parked_and_resumed_lanes_are_exact(tag, kw, golden_dir, g1_index):
+    """A search interrupted between any two steps and continued by another lane from the saved words (the kernel
+    parks the stragglers of a draining launch this way, SearchLane::save_state / load_state) gives the same bytes."""
+    args, fq = CASES[tag]
+    got, nov = harness_sai(g1_index[0], g1_index[1], args, os.path.join(golden_dir, fq + ".fq.gz"), **kw)
+    assert nov == 0
+    assert got == open(os.path.join(golden_dir, f"g1_{tag}.sai"), "rb").read()
+
+
 def test_long_reads_and_wide_score_ranges(golden_dir, g1_index):
     """1 kbp and 3 kbp reads: max_diff 23 / 75, i.e. 143 and 275 score buckets (the second needs the wide
     heads); also an empty read, which BAM input can deliver (the reference then reports the whole index)."""

@@ -55,6 +55,23 @@ def test_overflow_path_is_exact(tag, g1_index, golden_dir):
     assert got == open(os.path.join(golden_dir, f"g1_{tag}.sai"), "rb").read()
 
 
+@pytest.mark.parametrize("tag", sorted(CASES))
+@pytest.mark.parametrize("knobs", [dict(susp=31, susp_min=0), dict(susp=8, susp_min=64, search_block=32), dict(susp=0)],
+                         ids=["park_at_once", "park_sparse_warps", "never_park"])
+def test_parked_searches_are_exact(tag, knobs, g1_index, golden_dir):
+    """Stragglers of a draining launch are parked (SearchLane::save_state, bucket heads, open group) and resumed in
+    dense warps by follow-up launches: whatever the threshold and however many rounds, the bytes are the reference's."""
+    args, fq = CASES[tag]
+    with engine.Engine(g1_index[0], g1_index[1], 0) as e:
+        for k, v in knobs.items():
+            e.set(k, v)
+        got = engine_sai(e, args, os.path.join(golden_dir, fq + ".fq.gz"))
+        launches = e.stats()["kernel_launches"]
+    assert got == open(os.path.join(golden_dir, f"g1_{tag}.sai"), "rb").read()
+    if knobs.get("susp") == 31:
+        assert launches > 10          # the resume rounds really ran
+
+
 @pytest.mark.parametrize("tag", ["default", "stress"])
 def test_all_three_passes_are_exact(tag, g1_index, golden_dir):
     """Tiny fast AND middle capacities: some reads need the wide pass (32-bit heads in memory)."""
@@ -84,6 +101,26 @@ def test_cli_binary(tag, golden_dir, tmp_path):
     p = subprocess.run([exe, "aln"] + args + [prefix, os.path.join(golden_dir, fq + ".fq.gz")],
                        stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, check=True)
     assert p.stdout == open(os.path.join(golden_dir, f"g1_{tag}.sai"), "rb").read()
+
+
+@pytest.mark.parametrize("gz", [True, False], ids=["gzip_stream", "plain_stream"])
+def test_cli_reads_from_stdin(gz, golden_dir, tmp_path):
+    """`aln <prefix> -` reads the FASTQ from standard input (utils.c:56-66: xzopen("-") = gzdopen(stdin), which
+    takes plain and gzip streams alike); the reference binary fed the same pipe writes the same bytes."""
+    import gzip
+    prefix = str(tmp_path / "g1")
+    os.symlink(os.path.join(golden_dir, "g1.bwt"), prefix + ".bwt")
+    os.symlink(os.path.join(golden_dir, "g1.rbwt"), prefix + ".rbwt")
+    data = open(os.path.join(golden_dir, "g1_reads.fq.gz"), "rb").read()
+    if not gz:
+        data = gzip.decompress(data)
+    exe = os.path.join(ROOT, "ibwa_b200", "b200aln")
+    p = subprocess.run([exe, "aln", prefix, "-"], input=data, stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, check=True)
+    assert p.stdout == open(os.path.join(golden_dir, "g1_default.sai"), "rb").read()
+    if pyoracle.have_ref():
+        q = subprocess.run([pyoracle.REF_BIN, "aln", prefix, "-"], input=data, stdout=subprocess.PIPE,
+                           stderr=subprocess.DEVNULL, check=True)
+        assert q.stdout == p.stdout
 
 
 @pytest.fixture(scope="module")
@@ -145,6 +182,38 @@ def test_device_resident_entry_point(rand_index):
         torch.cuda.synchronize()
         assert np.array_equal(out_n.cpu().numpy(), n_aln)
         assert out_r.cpu().numpy().tobytes() == rec.tobytes()
+
+
+def test_chunk_pipeline_inside_one_call(rand_index):
+    """A call cut into chunks that run on the context's sibling contexts (own stream, pinned staging, in-order
+    assembly): host-buffer and device-resident entry points give what the single launch gives."""
+    import torch
+    import ibwa_b200.devcopy as devcopy
+    g, bwt, rbwt = rand_index
+    n, length = 20_000, 100
+    reads = synth.simulate_reads_fast(g, n, length, 7)
+    lens = np.full(n, length, np.int32)
+    offs = np.arange(n, dtype=np.int64) * length
+    opt = gap_init_opt()
+    with engine.Engine(bwt, rbwt, 0) as e:
+        e.set("slots", 1)
+        n_aln, rec = e.cal_sa_reg_gap(lens, offs, reads.reshape(-1), opt)
+        e.set("slots", 3)
+        e.set("chunk_reads", 3000)                  # 7 chunks on 3 contexts
+        e.set("chunk_reads_device", 3000)
+        n2, rec2 = e.cal_sa_reg_gap(lens, offs, reads.reshape(-1), opt)
+        assert np.array_equal(n_aln, n2) and rec.tobytes() == rec2.tobytes()
+        d_l, d_o, d_c = (torch.from_numpy(x).cuda() for x in (lens, offs, reads.reshape(-1)))
+        torch.cuda.synchronize()
+        pn, pr, total = e.batch_device(d_l.data_ptr(), d_o.data_ptr(), d_c.data_ptr(), n, length, opt)
+        assert total == len(rec)
+        out_n = torch.empty(n, dtype=torch.int32, device="cuda")
+        out_r = torch.empty(total * 4, dtype=torch.int32, device="cuda")
+        torch.cuda.synchronize()
+        devcopy.d2d(out_n.data_ptr(), pn, n * 4)
+        devcopy.d2d(out_r.data_ptr(), pr, total * 16)
+        torch.cuda.synchronize()
+        assert np.array_equal(out_n.cpu().numpy(), n_aln) and out_r.cpu().numpy().tobytes() == rec.tobytes()
 
 
 def test_reference_binary_on_box(rand_index, tmp_path):

@@ -43,7 +43,10 @@ def main():
              ({"arena_cap": 64, "rec_cap": 1}, ["default", "stress", "N_n2", "m200"]),
              ({"arena_cap": 64, "rec_cap": 1, "arena_cap_mid": 256, "rec_cap_mid": 3}, ["default", "stress"]),
              ({"search_block": 32, "q16": 0}, ["default", "stress", "short_o3"]),
-             ({"lut_k": 3}, ["default", "L_e3"])]
+             ({"lut_k": 3}, ["default", "L_e3"]),
+             # parking: every warp gives up as soon as one of its lanes is done, 24 rounds of save / resume
+             ({"susp": 31, "susp_min": 0}, ["default", "stress", "m200", "short_o3"]),
+             ({"susp": 0}, ["default", "stress"])]
     for knobs, tags in plans:
         with engine.Engine(bwt, rbwt, 0) as e:
             for k, v in knobs.items():

@@ -190,13 +190,18 @@ struct SearchArgs {
     int prep_rounds; /* pops / prunes a lane may go through per warp iteration before the warp moves on */
     /* Parking: once the work queue is dry, a warp in which at most susp_thresh lanes are still
      * searching writes their state out (SearchLane::save_state + bucket heads + open group, SUSP_STRIDE words per
-     * lane) and leaves the SM; a following launch with resume_in set picks the parked searches up again, 32 to a
-     * warp.  A launch's stragglers then cost the slots of a few dense warps instead of one sparse warp each. */
+     * lane) into a ring of tickets and then tries to take 32 parked searches back out of it: stragglers keep
+     * running in full warps, sparse warps leave the SM.  What a launch leaves in the ring (fewer than 32 at the
+     * time the last warps looked) is picked up by a following launch with resume_base set.  A launch's
+     * stragglers then cost the slots of a few dense warps instead of one sparse warp each. */
     int susp_thresh;
-    uint32_t *susp_out;
-    unsigned int *n_susp;
-    const uint32_t *resume_in; /* non-null: work item w is parked lane w of this buffer */
+    uint32_t *park_buf;        /* [PARK_CAP][SUSP_STRIDE] */
+    uint32_t *park_flag;       /* [PARK_CAP]: ticket + 1 once the slot holds that ticket's search */
+    unsigned int *park_ring;   /* [0] tail: tickets handed to parking lanes, [1] head: tickets taken back, [2] error flag */
+    int resume;                /* 1: work item w of this launch is the parked search with ticket resume_base + w */
+    unsigned int resume_base;
 };
+#define PARK_CAP (1u << 17)    /* ring slots; parked searches never outnumber the lanes of the launch (113 664) */
 #define SUSP_GROUP_AT B2_SAVE_WORDS             /* open group words */
 #define SUSP_HEADS_AT 48                        /* bucket heads, two 16-bit heads per word */
 #define SUSP_STRIDE (SUSP_HEADS_AT + 80)        /* words per parked lane (n_buckets <= 160: fast_heads_ok) */
@@ -253,6 +258,30 @@ template <> struct HeadsClear<HeadsStrided32> {
     static constexpr bool cooperative = true;
 };
 
+/* takes the parked search with `ticket` out of the ring into this lane; false (and an error flag for the host) when
+ * its slot was never published — the wait is bounded so that a bug cannot hang the GPU */
+template <class Lane, class Heads>
+__device__ __forceinline__ bool unpark(const SearchArgs &A, unsigned ticket, Lane &L, const Heads &heads, GroupStore gs, int &r, unsigned &w)
+{
+    const unsigned slot = ticket & (PARK_CAP - 1u);
+    const volatile uint32_t *flag = A.park_flag + slot;
+    unsigned spins = 0;
+    while (*flag != ticket + 1u) { /* the parking lane reserved the ticket and is still writing */
+        __nanosleep(200);
+        if (++spins > (1u << 24)) { atomicExch(A.park_ring + 2, 1u); return false; }
+    }
+    __threadfence(); /* also drops this SM's L1 lines (CCTL.IVALL): the search may have run here before and been edited elsewhere since */
+    const uint32_t *sv = A.park_buf + (size_t)slot * SUSP_STRIDE;
+    L.load_state(sv);
+    L.bk = heads;
+    L.gs = gs;
+    r = (int)sv[B2_SAVE_WORDS - 3];
+    w = sv[B2_SAVE_WORDS - 2];
+    for (int i = 0; i < OG_WORDS; ++i) gs.set(i, sv[SUSP_GROUP_AT + i]);
+    for (int b = 0; b < A.env.P.n_buckets; ++b) L.bk.set(b, sv[SUSP_HEADS_AT + (b >> 1)] >> (16 * (b & 1)) & 0xffffu);
+    return true;
+}
+
 /* BLK: lanes per block.  128 (four warps) is the default; 32 makes the warp the unit that leaves the SM when the
  * work queue has run dry, so that the next launch's blocks (another stream) move in while stragglers finish. */
 template <class Heads, bool REUSE, int MINB, bool STATS, int BLK = 128, int QB = 32>
@@ -287,16 +316,8 @@ __global__ void __launch_bounds__(BLK, MINB * (128 / BLK)) k_search(const __grid
             }
             if (need) {
                 w = base + (unsigned)__popc(m & ((1u << lane) - 1u));
-                if (w < (unsigned)A.n_work && A.resume_in) { /* a parked search goes on in this lane */
-                    const uint32_t *sv = A.resume_in + (size_t)w * SUSP_STRIDE;
-                    L.load_state(sv);
-                    L.bk = heads;
-                    L.gs = gs;
-                    r = (int)sv[B2_SAVE_WORDS - 3];
-                    w = sv[B2_SAVE_WORDS - 2];
-                    for (int i = 0; i < OG_WORDS; ++i) gs.set(i, sv[SUSP_GROUP_AT + i]);
-                    for (int b = 0; b < A.env.P.n_buckets; ++b) L.bk.set(b, sv[SUSP_HEADS_AT + (b >> 1)] >> (16 * (b & 1)) & 0xffffu);
-                    active = true;
+                if (w < (unsigned)A.n_work && A.resume) { /* a parked search goes on in this lane */
+                    active = unpark(A, A.resume_base + w, L, heads, gs, r, w);
                 } else if (w < (unsigned)A.n_work) {
                     r = A.work_list ? A.work_list[w] : (int)w;
                     if (!B2_CHECK(r >= 0 && (A.work_list || r < A.n_work), CHK_WORK, w, r, A.n_work)) r = 0;
@@ -343,15 +364,16 @@ __global__ void __launch_bounds__(BLK, MINB * (128 / BLK)) k_search(const __grid
                 active = false;
             }
         }
-        if (A.susp_thresh > 0) { /* the queue is dry and this warp has become sparse: park what is left, leave */
+        if (A.susp_thresh > 0) { /* the queue is dry and this warp has become sparse: park what is left, refill or leave */
             const unsigned dry = __ballot_sync(FULL, !alive), act = __ballot_sync(FULL, active);
             if (dry && act && __popc(act) <= A.susp_thresh) {
                 const int leader = __ffs((int)act) - 1;
                 unsigned base = 0;
-                if (lane == leader) base = atomicAdd(A.n_susp, (unsigned)__popc(act));
+                if (lane == leader) base = atomicAdd(A.park_ring + 0, (unsigned)__popc(act));
                 base = __shfl_sync(FULL, base, leader);
                 if (active) {
-                    uint32_t *sv = A.susp_out + (size_t)(base + (unsigned)__popc(act & ((1u << lane) - 1u))) * SUSP_STRIDE;
+                    const unsigned ticket = base + (unsigned)__popc(act & ((1u << lane) - 1u));
+                    uint32_t *sv = A.park_buf + (size_t)(ticket & (PARK_CAP - 1u)) * SUSP_STRIDE;
                     L.save_state(sv);
                     sv[B2_SAVE_WORDS - 3] = (uint32_t)r;
                     sv[B2_SAVE_WORDS - 2] = w;
@@ -359,9 +381,26 @@ __global__ void __launch_bounds__(BLK, MINB * (128 / BLK)) k_search(const __grid
                     const int nb = A.env.P.n_buckets;
                     for (int b = 0; b < nb; b += 2)
                         sv[SUSP_HEADS_AT + (b >> 1)] = (L.bk.get(b) & 0xffffu) | (b + 1 < nb ? L.bk.get(b + 1) : 0xffffu) << 16;
+                    __threadfence();
+                    *(volatile uint32_t *)(A.park_flag + (ticket & (PARK_CAP - 1u))) = ticket + 1u; /* published */
                     active = false;
                 }
                 alive = false;
+                __syncwarp();
+                /* a full warp's worth of parked searches waiting?  take them (lane 0 moves the head) */
+                unsigned got = 0xffffffffu;
+                if (lane == 0) {
+                    for (;;) {
+                        const unsigned h = *(volatile unsigned int *)(A.park_ring + 1), t = *(volatile unsigned int *)(A.park_ring + 0);
+                        if (t - h < 32u) break;
+                        if (atomicCAS(A.park_ring + 1, h, h + 32u) == h) { got = h; break; }
+                    }
+                }
+                got = __shfl_sync(FULL, got, 0);
+                if (got != 0xffffffffu) { /* every lane of the warp continues one of them */
+                    active = unpark(A, got + (unsigned)lane, L, heads, gs, r, w);
+                    alive = active;
+                }
             }
         }
     }
@@ -571,6 +610,7 @@ struct b200aln_ctx {
     cudaStream_t st_lo = nullptr; /* the fast pass of k_search: lowest priority */
     cudaEvent_t ev[8];
     cudaEvent_t tm[2];
+    cudaEvent_t ev_wait = nullptr; /* blocking-sync event: host waits sleep instead of spinning (wait_stream) */
     /* tuning */
     int search_blocks_per_sm = 6, width_blocks_per_sm = 5;
     uint32_t arena_cap = 2048, arena_cap_big = 0; /* 64-byte records per lane; big 0: max_entries + 64 */
@@ -602,7 +642,7 @@ struct b200aln_ctx {
     /* device buffers */
     DevBuf lens, offs, codes, md, Q, W, n_amb, ent, recs, n_aln, over_slot, over_list, misc, off64,
         blk_tot, packed, dkey, order_buf, Q_re, W_re, ent_big, recs_big, heads_wide, heads_wide_big, ent_mid, recs_mid, over_list2, over_list3, sa_in, sa_out, grp_in, grp_out;
-    HostBuf h_in, h_out, h_misc, h_nout;
+    HostBuf h_in, h_out, h_misc, h_nout, h_ring;
     b200aln_stats_t stats;
     /* chunk pipeline: a call with more than chunk_reads * 1.5 reads is cut into chunks that run on
      * `slots` sibling contexts (own stream, pinned staging and scratch; slot 0 is this context), so that the copies,
@@ -613,7 +653,7 @@ struct b200aln_ctx {
     int n_clones = 0;                /* owner: live clones (public and internal) */
     std::vector<b200aln_ctx *> slot; /* internal siblings 1 .. slots-1 */
     DevBuf asm_n_aln, asm_packed;    /* assembled results of a pipelined device-resident call */
-    DevBuf susp_buf[2];              /* parked lanes (SUSP_STRIDE words each), ping-pong between resume rounds */
+    DevBuf park_buf, park_flag, park_ring; /* parked searches: ring of PARK_CAP slots, their published flags, {tail, head, error} (never reset: tickets do not repeat) */
 };
 
 static cudaEvent_t g_origin = nullptr; /* B200ALN_TIMELINE: common clock of the stage timeline (see timeline()) */
@@ -691,6 +731,16 @@ static void make_streams(b200aln_ctx *c)
     const bool on = !e || atoi(e) != 0;
     CK(cudaStreamCreateWithPriority(&c->st, cudaStreamNonBlocking, on ? greatest : least));
     CK(cudaStreamCreateWithPriority(&c->st_lo, cudaStreamNonBlocking, least));
+    CK(cudaEventCreateWithFlags(&c->ev_wait, cudaEventBlockingSync | cudaEventDisableTiming));
+}
+
+/* The host side of a batch waits for its stream several times (counters back, records back).  With many contexts
+ * on few cores (eight ranks x several batches in flight) spinning waiters starve the threads that feed the GPUs:
+ * wait on an event created with cudaEventBlockingSync, which puts the thread to sleep. */
+static void wait_stream(b200aln_ctx *c, cudaStream_t st)
+{
+    CK(cudaEventRecord(c->ev_wait, st));
+    CK(cudaEventSynchronize(c->ev_wait));
 }
 
 static void upload_index(b200aln_ctx *c, int which, const b200aln_bwt_view_t *v)
@@ -902,8 +952,8 @@ extern "C" void b200aln_close(b200aln_ctx *c)
     for (DevBuf *b : bufs) b->release();
     c->grp_in.release(); c->grp_out.release();
     c->asm_n_aln.release(); c->asm_packed.release();
-    c->susp_buf[0].release(); c->susp_buf[1].release();
-    c->h_in.release(); c->h_out.release(); c->h_misc.release(); c->h_nout.release();
+    c->park_buf.release(); c->park_flag.release(); c->park_ring.release();
+    c->h_in.release(); c->h_out.release(); c->h_misc.release(); c->h_nout.release(); c->h_ring.release();
     if (c->owns_index) {
         for (int i = 0; i < 2; ++i) if (c->d_sa[i]) cudaFree(c->d_sa[i]);
         for (int i = 0; i < 2; ++i) if (c->d_idx[i]) cudaFree(c->d_idx[i]);
@@ -913,6 +963,7 @@ extern "C" void b200aln_close(b200aln_ctx *c)
     for (int i = 0; i < 2; ++i) cudaEventDestroy(c->tm[i]);
     cudaStreamDestroy(c->st);
     cudaStreamDestroy(c->st_lo);
+    cudaEventDestroy(c->ev_wait);
     delete c;
 }
 
@@ -984,7 +1035,7 @@ extern "C" void b200aln_last_stats(const b200aln_ctx *c, b200aln_stats_t *out) {
 /* device-side counters of one batch */
 struct Misc {
     unsigned int counter, n_over, counter_big, counter_mid, n_over2, n_over3, n_rec_full, n_bad;
-    unsigned int n_susp[2], counter_res; /* parked lanes of the current / the next resume round; the resume rounds' work counter */
+    unsigned int counter_res; /* the resume rounds' work counter */
     unsigned long long stat[2];
     long long total;
     unsigned int class_cnt[B2_N_CLASSES], class_fill[B2_N_CLASSES];
@@ -1130,36 +1181,47 @@ static void run_batch_device(b200aln_ctx *c, int n_reads, int max_len, const int
     const b200aln_ctx *owner = c->parent ? c->parent : c;
     const int park_at = c->susp > 0 ? c->susp : (c->susp < 0 && owner->active_calls.load() >= c->susp_calls ? -c->susp : 0);
     const bool parking = park_at > 0 && !c->count && fast_heads_ok(P, c->arena_cap);
-    SA.susp_thresh = 0; SA.susp_out = nullptr; SA.n_susp = nullptr; SA.resume_in = nullptr;
+    SA.susp_thresh = 0; SA.park_buf = nullptr; SA.park_flag = nullptr; SA.park_ring = nullptr; SA.resume = 0; SA.resume_base = 0;
+    if (c->susp != 0 && !c->park_ring.p && fast_heads_ok(P, c->arena_cap)) { /* with the first batch, not with the first parked one: allocating synchronises the device */
+            c->park_buf.need((size_t)PARK_CAP * SUSP_STRIDE * 4);
+            c->park_flag.need((size_t)PARK_CAP * 4);
+            c->park_ring.need(64);
+            CK(cudaMemsetAsync(c->park_flag.p, 0, (size_t)PARK_CAP * 4, c->st));
+            CK(cudaMemsetAsync(c->park_ring.p, 0, 64, c->st));
+    }
     if (parking) {
-        for (int i = 0; i < 2; ++i) c->susp_buf[i].need(lanes * SUSP_STRIDE * 4);
-        SA.susp_thresh = park_at; SA.susp_out = c->susp_buf[0].as<uint32_t>(); SA.n_susp = &dm->n_susp[0];
+        if (lanes > PARK_CAP) die("b200aln_batch", "internal: %zu lanes exceed the parking ring.", lanes);
+        SA.susp_thresh = park_at; SA.park_buf = c->park_buf.as<uint32_t>(); SA.park_flag = c->park_flag.as<uint32_t>();
+        SA.park_ring = c->park_ring.as<unsigned int>();
     }
     CK(cudaStreamWaitEvent(c->st_lo, c->ev[2], 0)); /* the fast pass: on the low-priority stream, fenced on both sides */
     launch_search_fast(c, SA, sblocks, q16, c->st_lo);
     ++launches;
     CK(cudaEventRecord(c->ev[3], c->st_lo));
     CK(cudaStreamWaitEvent(c->st, c->ev[3], 0));
-    if (parking) { /* resume rounds: the parked searches, dense again, on the high-priority stream */
-        int cur = 0;
+    if (parking) { /* what the launch left in the ring: dense again, on the high-priority stream, until nothing is left */
+        c->h_ring.need(64);
+        unsigned int *ring = c->h_ring.as<unsigned int>();
+        unsigned last_parked = 0xffffffffu;
         for (int round = 0;; ++round) {
-            CK(cudaMemcpyAsync(c->h_misc.p, c->misc.p, sizeof(Misc), cudaMemcpyDeviceToHost, c->st));
-            CK(cudaStreamSynchronize(c->st));
-            const unsigned n_parked = c->h_misc.as<Misc>()->n_susp[cur];
+            CK(cudaMemcpyAsync(ring, c->park_ring.p, 12, cudaMemcpyDeviceToHost, c->st));
+            wait_stream(c, c->st);
+            const unsigned tail = ring[0], head = ring[1], n_parked = tail - head;
+            if (ring[2]) die("b200aln_batch", "internal: a parked search was never published (ring tail %u head %u).", tail, head);
             if (!n_parked) break;
-            if (n_parked > lanes) die("b200aln_batch", "internal: %u parked lanes of %zu.", n_parked, lanes);
+            if (n_parked > lanes || round > 64) die("b200aln_batch", "internal: %u parked searches of %zu lanes after %d rounds.", n_parked, lanes, round);
             SearchArgs SR = SA;
-            SR.resume_in = c->susp_buf[cur].as<uint32_t>(); SR.n_work = (int)n_parked; SR.work_list = nullptr;
+            SR.resume = 1; SR.resume_base = head; SR.n_work = (int)n_parked; SR.work_list = nullptr;
             SR.counter = &dm->counter_res;
-            SR.susp_out = c->susp_buf[cur ^ 1].as<uint32_t>(); SR.n_susp = &dm->n_susp[cur ^ 1];
-            SR.susp_thresh = n_parked > (unsigned)c->susp_min && round < 24 ? park_at : 0;
+            /* park again only while that can still pack warps: enough searches left, and fewer than last time */
+            SR.susp_thresh = n_parked > (unsigned)(c->susp_min > 64 ? c->susp_min : 64) && n_parked < last_parked ? park_at : 0;
+            last_parked = n_parked;
             CK(cudaMemsetAsync(&dm->counter_res, 0, 4, c->st));
-            CK(cudaMemsetAsync(&dm->n_susp[cur ^ 1], 0, 4, c->st));
+            CK(cudaMemcpyAsync(c->park_ring.as<unsigned int>() + 1, &ring[0], 4, cudaMemcpyHostToDevice, c->st)); /* head = tail: the launch owns [head, tail) */
             int rblocks = (int)((n_parked + 127) / 128);
             if (rblocks > sblocks) rblocks = sblocks;
             launch_search_fast(c, SR, rblocks, q16, c->st);
             ++launches;
-            cur ^= 1;
         }
     }
 
@@ -1168,7 +1230,7 @@ static void run_batch_device(b200aln_ctx *c, int n_reads, int max_len, const int
      * many hits land here), then the wide pass (arena of max_entries, 32-bit heads in memory).
      * An aborted attempt may have edited W/Q in place (gap_shadow), so the widths are rebuilt first. */
     CK(cudaMemcpyAsync(c->h_misc.p, c->misc.p, sizeof(Misc), cudaMemcpyDeviceToHost, c->st));
-    CK(cudaStreamSynchronize(c->st));
+    wait_stream(c, c->st);
     unsigned n_over = c->h_misc.as<Misc>()->n_over;
     c->stats.overflow_reads = n_over;
     const bool verbose = getenv("B200ALN_VERBOSE") != nullptr;
@@ -1200,7 +1262,7 @@ static void run_batch_device(b200aln_ctx *c, int n_reads, int max_len, const int
         CK(cudaGetLastError());
         ++launches;
         SearchArgs SM = SA;
-        SM.susp_thresh = 0; SM.resume_in = nullptr; /* the re-run passes run every search to its end */
+        SM.susp_thresh = 0; SM.resume = 0; /* the re-run passes run every search to its end */
         SM.env.Q = WM.Q; SM.env.W = WM.W; SM.env.strideQ = strideQ32; SM.rows_by_work = 1;
         SM.n_work = (int)n_over; SM.work_list = c->over_list.as<int32_t>();
         SM.env.ent = c->ent_mid.as<StackRec>(); SM.env.arena_cap = c->arena_cap_mid;
@@ -1212,7 +1274,7 @@ static void run_batch_device(b200aln_ctx *c, int n_reads, int max_len, const int
         launch_search_mid(c, SM, mblocks);
         ++launches;
         CK(cudaMemcpyAsync(c->h_misc.p, c->misc.p, sizeof(Misc), cudaMemcpyDeviceToHost, c->st));
-        CK(cudaStreamSynchronize(c->st));
+        wait_stream(c, c->st);
         n_wide = c->h_misc.as<Misc>()->n_over2;
         wide_list = c->over_list2.as<int32_t>();
         if (verbose) fprintf(stderr, "[b200aln] middle pass %.1f ms (%d lanes), %u reads left for the wide pass\n", since(), lanes_mid, n_wide);
@@ -1240,7 +1302,7 @@ static void run_batch_device(b200aln_ctx *c, int n_reads, int max_len, const int
             CK(cudaGetLastError());
             ++launches;
             SearchArgs SB = SA;
-            SB.susp_thresh = 0; SB.resume_in = nullptr;
+            SB.susp_thresh = 0; SB.resume = 0;
             SB.env.Q = WB.Q; SB.env.W = WB.W; SB.env.strideQ = strideQ32; SB.rows_by_work = 1;
             SB.n_work = (int)n_wide; SB.work_list = wide_list;
             SB.env.ent = c->ent_big.as<StackRec>(); SB.env.arena_cap = cap_big; SB.arena_by_work = by_work ? 1 : 0;
@@ -1253,7 +1315,7 @@ static void run_batch_device(b200aln_ctx *c, int n_reads, int max_len, const int
             launch_search_big(c, SB, bblocks, bthreads);
             ++launches;
             CK(cudaMemcpyAsync(c->h_misc.p, c->misc.p, sizeof(Misc), cudaMemcpyDeviceToHost, c->st));
-            CK(cudaStreamSynchronize(c->st));
+            wait_stream(c, c->st);
             const Misc hw = *c->h_misc.as<Misc>();
             if (verbose) fprintf(stderr, "[b200aln] wide pass done at %.1f ms (%d lanes, %d records per read), %u reads do not fit\n", since(), bblocks * bthreads, c->rec_cap_big, hw.n_over3);
             if (!hw.n_over3) break;
@@ -1275,7 +1337,7 @@ static void run_batch_device(b200aln_ctx *c, int n_reads, int max_len, const int
     CK(cudaGetLastError());
     launches += 3;
     CK(cudaMemcpyAsync(c->h_misc.p, c->misc.p, sizeof(Misc), cudaMemcpyDeviceToHost, c->st));
-    CK(cudaStreamSynchronize(c->st));
+    wait_stream(c, c->st);
     const Misc hm = *c->h_misc.as<Misc>();
     report_device_checks("b200aln_batch");
     if (hm.n_bad) /* never a partial result (include/b200aln.h); the wide pass already grows what it can */
@@ -1433,7 +1495,7 @@ static void fetch_chunk_host(b200aln_ctx *s, int n, int64_t tot, b200aln_rec_t *
     CK(cudaMemcpyAsync(dst_n, s->n_aln.p, (size_t)n * 4, cudaMemcpyDeviceToHost, s->st));
     if (tot) CK(cudaMemcpyAsync(rec_dst, s->packed.p, (size_t)tot * 16, cudaMemcpyDeviceToHost, s->st));
     CK(cudaEventRecord(s->ev[6], s->st));
-    CK(cudaStreamSynchronize(s->st));
+    wait_stream(s, s->st);
     if (!pinned_out) memcpy(n_aln, dst_n, (size_t)n * 4);
     finish_stats(s, true);
 }
@@ -1549,7 +1611,7 @@ extern "C" void b200aln_batch_device(b200aln_ctx *c, int n_reads, int max_len, c
     if (n_chunks == 1) {
         int64_t tot = 0;
         run_batch_device(c, n_reads, max_len, d_lens, d_offs, d_codes, opt, md, P, &tot);
-        CK(cudaStreamSynchronize(c->st));
+        wait_stream(c, c->st);
         finish_stats(c, false);
         *d_n_aln = c->n_aln.as<int32_t>();
         *d_recs = c->packed.as<b200aln_rec_t>();
@@ -1583,7 +1645,7 @@ extern "C" void b200aln_batch_device(b200aln_ctx *c, int n_reads, int max_len, c
                 std::shared_lock<std::shared_mutex> g(ord.grow);
                 CK(cudaMemcpyAsync(c->asm_n_aln.as<int32_t>() + lo, s->n_aln.p, (size_t)n * 4, cudaMemcpyDeviceToDevice, s->st));
                 if (tot) CK(cudaMemcpyAsync(c->asm_packed.as<b200aln_rec_t>() + off, s->packed.p, (size_t)tot * 16, cudaMemcpyDeviceToDevice, s->st));
-                CK(cudaStreamSynchronize(s->st));
+                wait_stream(s, s->st);
             }
             finish_stats(s, false);
             std::lock_guard<std::mutex> lk(acc_mu);
@@ -1635,7 +1697,7 @@ extern "C" void b200aln_bwt_sa(b200aln_ctx *c, int which, int64_t n, const uint3
                                             c->sa_out.as<uint32_t>());
     CK(cudaGetLastError());
     CK(cudaMemcpyAsync(pos, c->sa_out.p, (size_t)n * 4, cudaMemcpyDeviceToHost, c->st));
-    CK(cudaStreamSynchronize(c->st));
+    wait_stream(c, c->st);
 }
 
 extern "C" void b200aln_sa2seq(b200aln_ctx *c, int64_t n, const uint8_t *strand, const uint32_t *rows, const int32_t *lens,
@@ -1657,7 +1719,7 @@ extern "C" void b200aln_sa2seq(b200aln_ctx *c, int64_t n, const uint8_t *strand,
                                             d_strand, d_rows, d_lens, c->sa_out.as<uint64_t>());
     CK(cudaGetLastError());
     CK(cudaMemcpyAsync(pos, c->sa_out.p, (size_t)n * 8, cudaMemcpyDeviceToHost, c->st));
-    CK(cudaStreamSynchronize(c->st));
+    wait_stream(c, c->st);
 }
 
 static void scan_i32(b200aln_ctx *c, const int32_t *in, int n, int64_t *out, int64_t *total_dev)
@@ -1726,7 +1788,7 @@ extern "C" int64_t b200aln_alngrp_merge(b200aln_ctx *c, int n_streams, int n_rea
         CK(cudaMemcpyAsync(out_recs, dout + o_rec, (size_t)all * 16, cudaMemcpyDeviceToHost, c->st));
         CK(cudaMemcpyAsync(out_dbidx, dout + o_db, (size_t)all * 4, cudaMemcpyDeviceToHost, c->st));
     }
-    CK(cudaStreamSynchronize(c->st));
+    wait_stream(c, c->st);
     return all;
 }
 

@@ -69,7 +69,7 @@ def test_parked_searches_are_exact(tag, knobs, g1_index, golden_dir):
         launches = e.stats()["kernel_launches"]
     assert got == open(os.path.join(golden_dir, f"g1_{tag}.sai"), "rb").read()
     if knobs.get("susp") == 31:
-        assert launches > 10          # the resume rounds really ran
+        assert launches > 8           # width, order x 2, fast pass, scan x 3, compact + at least one resume launch
 
 
 @pytest.mark.parametrize("tag", ["default", "stress"])

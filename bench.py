@@ -63,6 +63,8 @@ def gen_text(genome_bp: int, seed: int, device):
     for s in range(0, genome_bp, step):
         e = min(genome_bp, s + step)
         t[s:e] = torch.randint(0, 4, (e - s,), dtype=torch.uint8, device=device, generator=g)
+    if REPEATS:
+        plant_repeats(t, REPEATS, seed)
     return t
 
 
@@ -149,8 +151,33 @@ def synth_stress_reads_torch(text, n_reads: int, length: int, seed: int):
     return torch.where(rc[:, None], rcv, out)
 
 
+REPEATS = 0.0      # --repeats: fraction of the genome's bases planted as 40-copy families (set by main)
+
+
 def cache_dir(genome_bp: int, seed: int) -> str:
-    return os.path.join(CACHE_ROOT, f"g{genome_bp}_s{seed}")
+    return os.path.join(CACHE_ROOT, f"g{genome_bp}_s{seed}" + (f"_rep{REPEATS:g}" if REPEATS else ""))
+
+
+def plant_repeats(text, frac: float, seed: int):
+    """SURVEY.md §4 F2 at scale: families of 40 copies of a random 300-bp unit, every copy diverged by 2 %
+    substitutions, at random places, until `frac` of the bases lie in them (real genomes' repeats are what an
+    i.i.d. text lacks: many near-equal hits per read, deep ties in the suffix order)."""
+    import torch
+    dev = text.device
+    n = text.numel()
+    g = torch.Generator(device=dev)
+    g.manual_seed(seed + 77)
+    n_fam = int(frac * n / (40 * 300))
+    ar = torch.arange(300, device=dev)
+    for s in range(0, n_fam, 1024):
+        f = min(1024, n_fam - s)
+        unit = torch.randint(0, 4, (f, 1, 300), dtype=torch.uint8, device=dev, generator=g).expand(f, 40, 300)
+        mut = torch.rand((f, 40, 300), device=dev, generator=g) < 0.02
+        inc = torch.randint(1, 4, (f, 40, 300), dtype=torch.uint8, device=dev, generator=g)
+        cp = torch.where(mut, (unit + inc) & 3, unit).reshape(-1, 300)
+        at = torch.randint(0, n - 300, (f * 40,), device=dev, generator=g)
+        text[(at[:, None] + ar[None, :]).reshape(-1)] = cp.reshape(-1)
+    return text
 
 
 def contig_layout(genome_bp: int):
@@ -409,7 +436,11 @@ def main():
                          "the engine then parks the stragglers of a draining launch, DESIGN.md)")
     ap.add_argument("--parity-pairs", type=int, default=200_000, help="configs 4/5: pairs through sampe -R")
     ap.add_argument("--set", action="append", default=[], help="engine knob key=value")
+    ap.add_argument("--repeats", type=float, default=0.0,
+                    help="fraction of the genome's bases in 40-copy families of diverged 300-bp units (0 = i.i.d. text)")
     args = ap.parse_args()
+    global REPEATS
+    REPEATS = args.repeats
     cfg = dict(CONFIGS[args.config])
     for k in ("genome_bp", "reads", "read_len", "seed", "model", "aln_args"):
         v = getattr(args, k)
@@ -454,7 +485,7 @@ def main():
     lo, hi = (0, n_step // unit) if weak or world == 1 else shard_range(n_step // unit, world, rank)
     config = {"workload": f"{cfg['name']} [{cfg['aln_args'] or 'defaults (-n 0.04)'}; {cfg['model']} read model; "
                           f"{n_step} reads per step {'per GPU' if weak else 'in total'}; index replicated]",
-              "config_no": args.config, "genome_bp": cfg["genome_bp"], "reads_per_step": n_step,
+              "config_no": args.config, "genome_bp": cfg["genome_bp"], "repeats": args.repeats, "reads_per_step": n_step,
               "reads_per_gpu_per_step": (hi - lo) * unit, "read_len": L,
               "parallelism": f"replicated index, reads sharded x{world} ({'weak' if weak else 'strong'}), no collective",
               "l2": "inputs larger than L2 (index 3.1 GB + per-read state); no flush"}

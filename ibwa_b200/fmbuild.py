@@ -174,36 +174,100 @@ def build_bwt_torch(t, bucket_bits: int = 4, chunk: int = 1 << 26, sa_intv: int 
     return bwt
 
 
-def _fix_ties(t, seg, skeys, n):
-    """Re-sorts exactly the members of every run of equal keys, and every suffix shorter than
-    31 bases together with the run of keys equal to its (zero padded) own."""
+def _kmer31_at(t, pos, n: int, chunk: int = 1 << 24):
+    """62-bit keys of the 31-mers starting at arbitrary positions `pos` (int64 tensor, all pos + 31 <= n)."""
+    import torch
+    out = torch.empty(pos.numel(), dtype=torch.int64, device=t.device)
+    ar = torch.arange(31, device=t.device)
+    sh = (2 * (30 - ar)).to(torch.int64)
+    for s in range(0, pos.numel(), chunk):
+        p = pos[s:s + chunk]
+        out[s:s + chunk] = (t[p[:, None] + ar[None, :]].to(torch.int64) << sh[None, :]).sum(dim=1)
+    return out
+
+
+def _fix_ties_exact(t, seg, a: int, b: int, n: int):
+    """Sorts seg[a:b] (suffix starts) exactly on the host: for the handful of runs the vector path leaves."""
+    import torch
+
+    def suffix_key(s):
+        # +1 so that the end of the text (shorter suffix) sorts first
+        return bytes((t[s:min(n, s + 65536)] + 1).cpu().numpy())
+
+    members = [int(x) for x in seg[a:b].cpu().numpy()]
+    keyed = sorted((suffix_key(s), s) for s in members)
+    for (ka, _), (kb, _) in zip(keyed, keyed[1:]):
+        assert ka != kb, "text too repetitive for the 31-mer builder; use build_bwt_numpy"
+    seg[a:b] = torch.tensor([s for _, s in keyed], dtype=seg.dtype, device=seg.device)
+
+
+def _fix_ties(t, seg, skeys, n, max_depth: int = 31 * 4096):
+    """Orders the members of every run of equal 31-mer keys.  On the device: the tied suffixes are compared on
+    their next 31 bases (one stable sort by key, one by run), the runs that are still tied go one more round, 31
+    bases deeper — repeats resolve within a few rounds of their length / 31.  Runs that touch the end of the text
+    (a suffix shorter than the compared depth sorts first) and whatever is left at max_depth are ordered exactly
+    on the host, a handful of suffixes."""
     import torch
     m = seg.numel()
     if m < 2:
         return seg
-    tie = skeys[1:] == skeys[:-1]
-    flag = seg >= n - 31
-    flag[1:] |= tie
-    flag[:-1] |= tie
-    pos = torch.nonzero(flag).reshape(-1)
-    if pos.numel() == 0:
-        return seg
-    uk = torch.unique(skeys[pos])
-    lo = torch.searchsorted(skeys, uk, right=False).cpu().numpy()
-    hi = torch.searchsorted(skeys, uk, right=True).cpu().numpy()
-
-    def suffix_key(s):
-        # +1 so that the end of the text (shorter suffix) sorts first
-        return bytes((t[s:min(n, s + 4096)] + 1).cpu().numpy())
-
-    for a, b in zip(lo, hi):
-        if b - a < 2:
-            continue
-        members = [int(x) for x in seg[a:b].cpu().numpy()]
-        keyed = sorted((suffix_key(s), s) for s in members)
-        for (ka, _), (kb, _) in zip(keyed, keyed[1:]):
-            assert ka != kb, "text too repetitive for the 31-mer builder; use build_bwt_numpy"
-        seg[a:b] = torch.tensor([s for _, s in keyed], dtype=seg.dtype, device=seg.device)
+    dev = seg.device
+    start = torch.ones(m, dtype=torch.bool, device=dev)
+    start[1:] = skeys[1:] != skeys[:-1]
+    gid = torch.cumsum(start.to(torch.int64), 0) - 1            # run number of every element
+    tie = ~start
+    in_tie = tie.clone()
+    in_tie[:-1] |= tie[1:]
+    near_end = seg >= n - 31                                     # zero-padded keys: equal to a real key of A's
+    host_runs = set(int(g) for g in gid[near_end].cpu().numpy())
+    # a run with a near-end suffix must also pull in the run whose key equals the padded key: same gid by construction
+    P = torch.nonzero(in_tie).reshape(-1)                        # slots of seg that take part, ascending
+    depth = 31
+    while P.numel() > 0:
+        pos = seg[P]
+        g = gid[P]
+        over = pos + depth + 31 > n                              # would read past the end: to the host path
+        if bool(over.any()) or depth >= max_depth:
+            bad = torch.unique(g if depth >= max_depth else g[over])
+            host_runs.update(int(x) for x in bad.cpu().numpy())
+            keep = ~torch.isin(g, bad)
+            P, pos, g = P[keep], pos[keep], g[keep]
+            if P.numel() == 0:
+                break
+        key = _kmer31_at(t, pos + depth, n)
+        o1 = torch.argsort(key, stable=True)
+        o2 = torch.argsort(g[o1], stable=True)
+        perm = o1[o2]                                            # by (run, next 31 bases)
+        pos_s, key_s, g_s = pos[perm], key[perm], g[perm]        # g_s == g: P is grouped by run already
+        seg[P] = pos_s
+        same = (g_s[1:] == g_s[:-1]) & (key_s[1:] == key_s[:-1])
+        still = torch.zeros(P.numel(), dtype=torch.bool, device=dev)
+        still[1:] |= same
+        still[:-1] |= same
+        # new run numbers: a run splits wherever the next 31 bases differ
+        brk = torch.ones(P.numel(), dtype=torch.bool, device=dev)
+        brk[1:] = ~same
+        new_g = torch.cumsum(brk.to(torch.int64), 0) - 1
+        keep_host = torch.isin(g_s, torch.tensor(sorted(host_runs), dtype=torch.int64, device=dev)) if host_runs else None
+        gid_new = new_g + (int(gid.max().item()) + 1)            # fresh numbers, disjoint from the old ones
+        if keep_host is not None and bool(keep_host.any()):
+            gid_new = torch.where(keep_host, g_s, gid_new)       # runs destined for the host keep their identity
+            still = still & ~keep_host
+        gid[P] = gid_new
+        P = P[still]
+        depth += 31
+    if host_runs:
+        hr = torch.tensor(sorted(host_runs), dtype=torch.int64, device=dev)
+        sel = torch.nonzero(torch.isin(gid, hr)).reshape(-1)
+        if sel.numel():
+            gs = gid[sel].cpu().numpy()
+            sl = sel.cpu().numpy()
+            # the slots of one run are contiguous
+            cut = np.nonzero(np.diff(gs) != 0)[0] + 1
+            for grp in np.split(np.arange(len(sl)), cut):
+                a, b = int(sl[grp[0]]), int(sl[grp[-1]]) + 1
+                if b - a >= 2:
+                    _fix_ties_exact(t, seg, a, b, n)
     return seg
 
 

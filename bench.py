@@ -737,6 +737,19 @@ def main():
                            "random_sector_roof_note": "k_sector_gather over BOTH device indexes (3.1 GB)",
                            "frac_of_random_sector_roof": achieved / sector_roof if sector_roof else None,
                            "occ_sectors_per_s": sum(counted[j]["occ_lookups"] for j in pri_ix) / (ms_search * 1e-3)}
+        if traffic and sector_roof:
+            # What binds this access pattern is a transaction rate, not bytes: DRAM moves the kernel's
+            # traffic in 64-byte transactions, and the gather microbenchmark counts how many random ones it serves.
+            tj = json.load(open(tpath))[f"config{args.config}"]["k_search"]
+            rd_tx = tj["dram_read_bytes_per_read"] / 64.0
+            wr_tx = tj["dram_write_bytes_per_read"] / 64.0
+            rate = n_pri / (ms_search * 1e-3)
+            out["roofline"].update({
+                "dram_read_transactions_per_read": rd_tx, "dram_write_transactions_per_read": wr_tx,
+                "dram_read_transactions_per_s": rd_tx * rate,
+                "random_requests_roof_per_s": sector_roof * 1e9 / 32.0,
+                "frac_of_transaction_roof_reads": rd_tx * rate / (sector_roof * 1e9 / 32.0),
+                "frac_of_transaction_roof_reads_and_writebacks": (rd_tx + wr_tx) * rate / (sector_roof * 1e9 / 32.0)})
         # parity of this very run against the oracle port on the sample
         m = port["n"]
         n_aln_d, rec_d = eng.cal_sa_reg_gap(np.full(m, L, np.int32), np.arange(m, dtype=np.int64) * L,

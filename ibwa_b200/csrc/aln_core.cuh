@@ -829,6 +829,8 @@ struct SearchLane {
     bool finished;
     /* current entry */
     bool have_cur, extending;
+    bool qe; /* pq already holds the width record of position ci - 1: loaded at the end of the previous step, so
+                that its latency runs under the rest of the warp's iteration instead of in front of the next lookup */
     uint32_t ck, cl;
     int ci, cldp, cmm, cgo, cge, cstate, ca, cscore;
     uint32_t cpath; /* position of the current entry in the interval table */
@@ -869,7 +871,7 @@ struct SearchLane {
         best_score = score_of(E.P, max_diff_ + 1, P->max_gapo + 1, P->max_gape + 1);
         best_diff = max_diff_ + 1;
         best_cnt = 0; n_aln = 0; status = LANE_OK;
-        finished = false; have_cur = false; extending = false;
+        finished = false; have_cur = false; extending = false; qe = false;
         og = 0;
         pq = 0;
         top = 0; free_head = B2_NIL; n_entries = 0;
@@ -1116,7 +1118,12 @@ struct SearchLane {
         const uint32_t d = cpath & 31u;
         int n = K - (int)d; /* B2_PATH_DEAD = 31 >= any K: n <= 0 */
         if (n > ci) n = ci;
-        if (n < 2) { pq = fetch_q(E, ca, ci - 1); return EXTEND; }
+        if (n < 2) {
+            if (!qe) pq = fetch_q(E, ca, ci - 1);
+            qe = false;
+            return EXTEND;
+        }
+        qe = false;
         uint32_t X = cpath >> 5, amb = 0;
         for (int j = 1; j <= n; ++j) {
             const uint32_t b = (uint32_t)q_base(fetch_q(E, ca, ci - j));
@@ -1143,7 +1150,7 @@ struct SearchLane {
     {
         d[0] = lane_no; d[1] = row; d[2] = slab; d[3] = (uint32_t)len; d[4] = (uint32_t)opt_max_diff;
         d[5] = top; d[6] = free_head; d[7] = (uint32_t)best; d[8] = (uint32_t)n_mem;
-        d[9] = (uint32_t)prefetch_next | (uint32_t)finished << 1 | (uint32_t)have_cur << 2 | (uint32_t)extending << 3;
+        d[9] = (uint32_t)prefetch_next | (uint32_t)finished << 1 | (uint32_t)have_cur << 2 | (uint32_t)extending << 3 | (uint32_t)qe << 4;
         d[10] = (uint32_t)n_entries; d[11] = (uint32_t)max_diff; d[12] = (uint32_t)best_score; d[13] = (uint32_t)best_diff;
         d[14] = (uint32_t)best_cnt; d[15] = (uint32_t)n_aln; d[16] = (uint32_t)status;
         d[17] = ck; d[18] = cl; d[19] = (uint32_t)ci; d[20] = (uint32_t)cldp; d[21] = (uint32_t)cmm; d[22] = (uint32_t)cgo;
@@ -1154,7 +1161,7 @@ struct SearchLane {
     {
         lane_no = d[0]; row = d[1]; slab = d[2]; len = (int)d[3]; opt_max_diff = (int)d[4];
         top = d[5]; free_head = d[6]; best = (int)d[7]; n_mem = (int)d[8];
-        prefetch_next = d[9] & 1u; finished = d[9] >> 1 & 1u; have_cur = d[9] >> 2 & 1u; extending = d[9] >> 3 & 1u;
+        prefetch_next = d[9] & 1u; finished = d[9] >> 1 & 1u; have_cur = d[9] >> 2 & 1u; extending = d[9] >> 3 & 1u; qe = d[9] >> 4 & 1u;
         n_entries = (int)d[10]; max_diff = (int)d[11]; best_score = (int)d[12]; best_diff = (int)d[13];
         best_cnt = (int)d[14]; n_aln = (int)d[15]; status = (int)d[16];
         ck = d[17]; cl = d[18]; ci = (int)d[19]; cldp = (int)d[20]; cmm = (int)d[21]; cgo = (int)d[22];
@@ -1199,7 +1206,8 @@ struct SearchLane {
                 --n_entries;
                 if (STATS) ++n_pops;
                 have_cur = false;
-                if (ci > 0) pq = fetch_q(E, ca, ci - 1);
+                if (ci > 0 && !qe) pq = fetch_q(E, ca, ci - 1);
+                qe = false;
             }
             if (!nonstop && cscore > best_score + P->s_mm) { finished = true; return NONE; }
             pm = max_diff - cmm - cgo - (gape_mode ? cge : 0);
@@ -1277,6 +1285,9 @@ struct SearchLane {
                 extending = false;
                 if (!on_hit(E)) finished = true;
             }
+#ifdef B2_EARLY_Q
+            else if ((cpath & 31u) == B2_PATH_DEAD) { pq = fetch_q(E, ca, ci - 1); qe = true; } /* next chain step: outside the table */
+#endif
             return;
         }
 
@@ -1335,6 +1346,9 @@ struct SearchLane {
                 cpath = path_ext(cpath, base, K);
                 have_cur = true;
                 ++n_entries;
+#ifdef B2_EARLY_Q
+                if (ci > 0) { pq = fetch_q(E, ca, ci - 1); qe = true; } /* the next step's width record, early */
+#endif
             }
         }
     }

@@ -35,7 +35,7 @@ def view(b):
 
 def build():
     if not os.path.exists(LIB) or any(os.path.getmtime(s) > os.path.getmtime(LIB) for s in SRCS):
-        subprocess.check_call(["g++", "-O2", "-g", "-std=c++17", "-fPIC", "-shared", "-DB200ALN_COUNTERS", "-o", LIB,
+        subprocess.check_call(["g++", "-O2", "-g", "-std=c++17", "-fPIC", "-shared", "-DB200ALN_COUNTERS", "-DB2_EARLY_Q", "-o", LIB,
                                SRCS[0]])
     return LIB
 
@@ -46,7 +46,7 @@ LIB_CHECKED = os.path.join(HERE, "libhostharness_checked.so")
 def build_checked():
     """The same sources with -DB2_CHECKED (aln_core.cuh): every derived index is tested, a violation aborts."""
     if not os.path.exists(LIB_CHECKED) or any(os.path.getmtime(s) > os.path.getmtime(LIB_CHECKED) for s in SRCS):
-        subprocess.check_call(["g++", "-O1", "-g", "-std=c++17", "-fPIC", "-shared", "-DB200ALN_COUNTERS", "-DB2_CHECKED",
+        subprocess.check_call(["g++", "-O1", "-g", "-std=c++17", "-fPIC", "-shared", "-DB200ALN_COUNTERS", "-DB2_EARLY_Q", "-DB2_CHECKED",
                                "-o", LIB_CHECKED, SRCS[0]])
     return LIB_CHECKED
 

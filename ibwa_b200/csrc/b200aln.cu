@@ -1186,6 +1186,7 @@ static void run_batch_device(b200aln_ctx *c, int n_reads, int max_len, const int
             c->park_buf.need((size_t)PARK_CAP * SUSP_STRIDE * 4);
             c->park_flag.need((size_t)PARK_CAP * 4);
             c->park_ring.need(64);
+            c->h_ring.need(64);
             CK(cudaMemsetAsync(c->park_flag.p, 0, (size_t)PARK_CAP * 4, c->st));
             CK(cudaMemsetAsync(c->park_ring.p, 0, 64, c->st));
     }

@@ -140,7 +140,18 @@ double b200aln_timer_stop(b200aln_ctx *ctx);
  *                  launch geometry and per-lane capacities; arena capacities count 64-byte records.
  *   prep_rounds    pruned pops a lane may go through per warp iteration before the warp moves on (default 1).
  *   reserve_reads  size the per-batch device buffers for at least this many reads (drivers whose launches vary in size).
- *   count          1: the fast pass runs with its pop / sector counters (b200aln_stats_t pops, occ_lookups). */
+ *   count          1: the fast pass runs with its pop / sector counters (b200aln_stats_t pops, occ_lookups).
+ *   chunk_reads, slots, chunk_reads_device
+ *                  a host-buffer call of more than 1.5 x chunk_reads reads (default 4 Mi) is cut into chunks that run
+ *                  on `slots` sibling contexts (default 3; 1 = never), so that copies and kernels of different
+ *                  chunks overlap; device-resident calls are one launch unless chunk_reads_device is set.
+ *   q16            1 (default): 16-bit width records in the fast pass whenever max_diff < 7 and max_seed_diff < 3.
+ *   order          1 (default): the fast pass takes the reads by work class, longest searches first.
+ *   susp, susp_calls, susp_min
+ *                  parking of a draining launch's stragglers: |susp| = lanes per warp at or below
+ *                  which a warp parks what it has left once the work queue is dry; > 0 always, < 0 (default -16)
+ *                  only while at least susp_calls (4) batches are in flight on this device index, 0 never.
+ *   search_block   lanes per block of the fast pass: 128 (default) or 32. */
 void b200aln_set_int(b200aln_ctx *ctx, const char *key, int64_t value);
 
 /*

@@ -790,6 +790,15 @@ def main():
                         eng_sais.append(p)
                 parity["reference_binary_reads"] = k * len(streams)
                 parity["reference_binary_identical"] = same
+                # the same reads once more with parking forced on (budget parking, heavy warps, drain parking, resume
+                # launches): in the timed runs it switches itself on only while four or more batches are in flight
+                eng.set("susp", 16)
+                p_n, p_rec = eng.cal_sa_reg_gap(np.full(k, L, np.int32), np.arange(k, dtype=np.int64) * L,
+                                                samples[0][:k].reshape(-1), opt)
+                eng.set("susp", -16)
+                _, r_n, r_rec = sai.read_sai(res["sais"][0])
+                parity["parked_identical"] = bool(np.array_equal(p_n, r_n[:k]) and p_rec.tobytes() == r_rec.tobytes())
+                same = same and parity["parked_identical"]
                 ok = ok and same
                 if cfg["pairs"]:            # downstream: the unchanged `sampe -R` on engine vs reference .sai
                     np_ = len(sets)

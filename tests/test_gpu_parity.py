@@ -56,8 +56,9 @@ def test_overflow_path_is_exact(tag, g1_index, golden_dir):
 
 
 @pytest.mark.parametrize("tag", sorted(CASES))
-@pytest.mark.parametrize("knobs", [dict(susp=31, susp_min=0), dict(susp=8, susp_min=64, search_block=32), dict(susp=0)],
-                         ids=["park_at_once", "park_sparse_warps", "never_park"])
+@pytest.mark.parametrize("knobs", [dict(susp=31, susp_min=0), dict(susp=8, susp_min=64, search_block=32), dict(susp=0),
+                                   dict(susp=16, search_blocks_per_sm=1)],
+                         ids=["park_at_once", "park_sparse_warps", "never_park", "park_small_grid"])
 def test_parked_searches_are_exact(tag, knobs, g1_index, golden_dir):
     """Stragglers of a draining launch are parked (SearchLane::save_state, bucket heads, open group) and resumed in
     dense warps by follow-up launches: whatever the threshold and however many rounds, the bytes are the reference's."""

@@ -631,10 +631,12 @@ def main():
     def timed(fn, steps, k):
         """`steps` steps, k in flight (host thread w runs steps w, w + k, ...); ms by CUDA events, max over ranks"""
         results = [None] * steps
+        done_at = [0.0] * steps
 
         def worker(w):
             for i in range(w, steps, k):
                 results[i] = fn(w)
+                done_at[i] = time.perf_counter()
 
         barrier()
         eng.timer_start()
@@ -652,7 +654,16 @@ def main():
             t = torch.tensor([ms], dtype=torch.float64, device=dev)
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
             ms = float(t.item())
+        timed.done_at = sorted(done_at)
         return ms, results
+
+    def steady_ms(done):
+        """median spacing of step completions over the middle half of a pipelined run (host clock): what the pipeline
+        sustains between its fill and its drain — informational, the timed region is what `value` is"""
+        if len(done) < 8:
+            return None
+        a, b = len(done) // 4, len(done) - len(done) // 4
+        return 1e3 * float(np.median(np.diff(done[a:b])))
 
     for w in range(K):                      # every context allocates its buffers outside the timed regions
         for _ in range(max(1, (args.warmup + K - 1) // K)):
@@ -661,11 +672,14 @@ def main():
     sampler.start()
     ms_seq, st_seq = timed(step_device, args.steps, 1)
     ms_dev, _ = timed(step_device, args.steps, K) if K > 1 else (ms_seq, None)
+    steady_dev = steady_ms(timed.done_at)
     clocks = sampler.stop()
     for w in range(K):
         step_e2e(w)
     ms_e2e, st_e2e = timed(step_e2e, args.steps, K)
 
+    free_b, total_b = torch.cuda.mem_get_info(dev)
+    hbm_in_use = (total_b - free_b) / 2**30     # index, tables and every in-flight context's per-read state and arenas
     for e in engs["pri"][:1]:
         e.set("count", 1)                   # one untimed step with the pop / sector counters compiled in
     counted = step_device(0)
@@ -689,6 +703,10 @@ def main():
            "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_dev / args.steps,
            "higher_is_better": True, "scaling": "weak" if weak else "strong", "vs_baseline": None, "dtype": "u32",
            "data": "synthetic", "config": config, "clocks": clocks, "in_flight": K,
+           "steady_state": None if not steady_dev else {
+               "ms_between_steps": steady_dev, "reads_per_s_this_rank": n_rank / (steady_dev * 1e-3),
+               "note": "median spacing of step completions over the middle half of the pipelined run on this rank: the "
+                       "rate between the pipeline's fill and drain (informational)"},
            "sequential": {"value": total_reads / (ms_seq * 1e-3), "ms_per_step": ms_seq / args.steps,
                           "best_step_ms": float(np.min(step_ms)), "median_step_ms": float(np.median(step_ms)),
                           "note": "the same steps one at a time on one context (rank 0's device times)"},
@@ -698,6 +716,7 @@ def main():
            "gpu_launches": launches,
            "kernel_ms": {k: float(np.mean(kms(k))) for k in ("ms_width", "ms_search", "ms_compact", "ms_total")},
            "overflow_reads_per_step": int(sum(s["overflow_reads"] for s in st_seq[-1])),
+           "hbm_in_use_gib": hbm_in_use,
            "device_pops_per_read": sum(counted[j]["pops"] for j in pri_ix) / max(n_pri, 1),
            "device_sectors_per_read": sum(counted[j]["occ_lookups"] for j in pri_ix) / max(n_pri, 1)}
 

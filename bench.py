@@ -658,12 +658,12 @@ def main():
         return ms, results
 
     def steady_ms(done):
-        """median spacing of step completions over the middle half of a pipelined run (host clock): what the pipeline
+        """mean spacing of step completions over the middle half of a pipelined run (host clock): what the pipeline
         sustains between its fill and its drain — informational, the timed region is what `value` is"""
-        if len(done) < 8:
+        if len(done) < 12:
             return None
         a, b = len(done) // 4, len(done) - len(done) // 4
-        return 1e3 * float(np.median(np.diff(done[a:b])))
+        return 1e3 * float(done[b - 1] - done[a]) / (b - 1 - a)
 
     for w in range(K):                      # every context allocates its buffers outside the timed regions
         for _ in range(max(1, (args.warmup + K - 1) // K)):
@@ -705,7 +705,7 @@ def main():
            "data": "synthetic", "config": config, "clocks": clocks, "in_flight": K,
            "steady_state": None if not steady_dev else {
                "ms_between_steps": steady_dev, "reads_per_s_this_rank": n_rank / (steady_dev * 1e-3),
-               "note": "median spacing of step completions over the middle half of the pipelined run on this rank: the "
+               "note": "mean spacing of step completions over the middle half of the pipelined run on this rank: the "
                        "rate between the pipeline's fill and drain (informational)"},
            "sequential": {"value": total_reads / (ms_seq * 1e-3), "ms_per_step": ms_seq / args.steps,
                           "best_step_ms": float(np.min(step_ms)), "median_step_ms": float(np.median(step_ms)),

@@ -22,6 +22,9 @@
 #include <time.h>
 #include <unistd.h>
 #include <zlib.h>
+#if defined(__x86_64__) && defined(__GNUC__)
+#include <immintrin.h>
+#endif
 
 #include <algorithm>
 #include <chrono>
@@ -40,6 +43,8 @@
 
 struct b200aln_reader;
 extern "C" void b200aln_warm_device(int device); /* b200aln.cu: creates the CUDA context */
+extern "C" int b200aln_pin(void *p, size_t bytes);
+extern "C" void b200aln_unpin(void *p);
 
 namespace {
 
@@ -76,6 +81,64 @@ struct SeqClassTable {
     }
 };
 const SeqClassTable g_seqclass;
+
+/* Sequence line -> nt4 codes and the character checks of the fast path, on L characters: false when the
+ * sequence holds a character the fast path must not accept (SeqClassTable) or the quality string one outside
+ * 33..127 (kseq.h:185).  The table version, and an AVX2 version of the same function picked at run time. */
+static bool convert_scalar(const unsigned char *sq, const unsigned char *ql, int L, uint8_t *codes)
+{
+    unsigned acc = 0, badq = 0;
+    for (int i = 0; i < L; ++i) {
+        const uint8_t v = g_seqclass.t[sq[i]];
+        acc |= v;
+        codes[i] = (uint8_t)(v & 7);
+    }
+    for (int i = 0; i < L; ++i) badq |= (unsigned)((unsigned char)(ql[i] - 33) > 94);
+    return !((acc & 0x80u) | badq);
+}
+#if defined(__x86_64__) && defined(__GNUC__)
+__attribute__((target("avx2"))) static inline __m256i nt4_avx2(__m256i v, __m256i &bad)
+{
+    /* a letter of ACGT in either case has a low nibble of 1, 3, 7, 4: the nibble selects the code and the lower-case
+     * letter the character has to be; everything else is 4, '-' is 5 (bntseq.c:39-56) */
+    const __m256i lut_code = _mm256_setr_epi8(4, 0, 4, 1, 3, 4, 4, 2, 4, 4, 4, 4, 4, 4, 4, 4, 4, 0, 4, 1, 3, 4, 4, 2, 4, 4, 4, 4, 4, 4, 4, 4);
+    const __m256i lut_chr = _mm256_setr_epi8(0, 'a', 0, 'c', 't', 0, 0, 'g', 0, 0, 0, 0, 0, 0, 0, 0, 0, 'a', 0, 'c', 't', 0, 0, 'g', 0, 0, 0, 0, 0, 0, 0, 0);
+    const __m256i low = _mm256_and_si256(v, _mm256_set1_epi8(0x0f));
+    const __m256i is_nt = _mm256_cmpeq_epi8(_mm256_or_si256(v, _mm256_set1_epi8(0x20)), _mm256_shuffle_epi8(lut_chr, low));
+    __m256i code = _mm256_blendv_epi8(_mm256_set1_epi8(4), _mm256_shuffle_epi8(lut_code, low), is_nt);
+    code = _mm256_blendv_epi8(code, _mm256_set1_epi8(5), _mm256_cmpeq_epi8(v, _mm256_set1_epi8('-')));
+    /* not graphic (<= 32, >= 127: as signed bytes everything below 33, and 127), or one of '>', '+', '@' */
+    __m256i b = _mm256_cmpgt_epi8(_mm256_set1_epi8(33), v);
+    b = _mm256_or_si256(b, _mm256_cmpeq_epi8(v, _mm256_set1_epi8(127)));
+    b = _mm256_or_si256(b, _mm256_cmpeq_epi8(v, _mm256_set1_epi8('>')));
+    b = _mm256_or_si256(b, _mm256_cmpeq_epi8(v, _mm256_set1_epi8('+')));
+    b = _mm256_or_si256(b, _mm256_cmpeq_epi8(v, _mm256_set1_epi8('@')));
+    bad = _mm256_or_si256(bad, b);
+    return code;
+}
+__attribute__((target("avx2"))) static bool convert_avx2(const unsigned char *sq, const unsigned char *ql, int L, uint8_t *codes)
+{
+    if (L < 32) return convert_scalar(sq, ql, L, codes);
+    __m256i bad = _mm256_setzero_si256();
+    int i = 0;
+    for (; i + 32 <= L; i += 32) {
+        _mm256_storeu_si256((__m256i *)(codes + i), nt4_avx2(_mm256_loadu_si256((const __m256i *)(sq + i)), bad));
+        bad = _mm256_or_si256(bad, _mm256_cmpgt_epi8(_mm256_set1_epi8(33), _mm256_loadu_si256((const __m256i *)(ql + i))));
+    }
+    if (i < L) { /* the last 32 characters once more, overlapping what is done */
+        i = L - 32;
+        _mm256_storeu_si256((__m256i *)(codes + i), nt4_avx2(_mm256_loadu_si256((const __m256i *)(sq + i)), bad));
+        bad = _mm256_or_si256(bad, _mm256_cmpgt_epi8(_mm256_set1_epi8(33), _mm256_loadu_si256((const __m256i *)(ql + i))));
+    }
+    return _mm256_testz_si256(bad, bad) != 0;
+}
+static bool (*const g_convert)(const unsigned char *, const unsigned char *, int, uint8_t *) = [] {
+    __builtin_cpu_init();
+    return (getenv("B200ALN_NO_SIMD") == nullptr && __builtin_cpu_supports("avx2")) ? convert_avx2 : convert_scalar;
+}();
+#else
+static bool (*const g_convert)(const unsigned char *, const unsigned char *, int, uint8_t *) = convert_scalar;
+#endif
 
 /* persistent worker threads for the record conversion (one pool per process) */
 class ParsePool {
@@ -464,8 +527,13 @@ class SeqReader {
         return (int)seq_.size();
     }
 
-    /* One ordinary 4-line record found by the structural scan: offsets into the buffer. */
-    struct Extent { int64_t start, seq, qual, next; int len; };
+    /* One ordinary 4-line record found by the structural scan: where it starts in the buffer, and its sequence and
+     * quality strings relative to that. */
+    struct Extent {
+        int64_t start;
+        int32_t seq, qual, len; /* offsets from start; the record ends at start + qual + len + 1 */
+        int64_t next() const { return start + qual + len + 1; }
+    };
 
     /* One ordinary 4-line record at p, located by its newlines only (convert_extent() validates the characters).
      * `guess` = sequence length of the previous record (most files have one length): the sequence line is
@@ -480,11 +548,12 @@ class SeqReader {
         const unsigned char *nl1 = (const unsigned char *)memchr(b + p + 1, '\n', (size_t)(e - p - 1));
         if (!nl1 || nl1 == b + p + 1 || isspace(b[p + 1])) return false;
         const int64_t s0 = (int64_t)(nl1 - b) + 1;
+        if (s0 - p > 0x3fffffff) return false;
         int L;
         if (guess > 0 && s0 + guess < e && b[s0 + guess] == '\n') L = guess;
         else {
             const unsigned char *nl2 = (const unsigned char *)memchr(b + s0, '\n', (size_t)(e - s0));
-            if (!nl2 || (int64_t)(nl2 - b) - s0 > 0x3fffffff) return false;
+            if (!nl2 || (int64_t)(nl2 - b) - s0 > 0x1fffffff) return false;
             L = (int)((int64_t)(nl2 - b) - s0);
         }
         const int64_t q_plus = s0 + L + 1;
@@ -496,49 +565,66 @@ class SeqReader {
             if (!nl3) return false;
             q0 = (int64_t)(nl3 - b) + 1;
         }
-        if (q0 + L >= e || b[q0 + L] != '\n') return false; /* (a newline inside the quality string is refused by convert_extent) */
-        x.start = p; x.seq = s0; x.len = L; x.qual = q0; x.next = q0 + L + 1;
+        if (q0 - p > 0x7fffffff || q0 + L >= e || b[q0 + L] != '\n') return false; /* (a newline inside the quality string is refused by convert_extent) */
+        x.start = p; x.seq = (int32_t)(s0 - p); x.len = L; x.qual = (int32_t)(q0 - p);
         guess = L;
         return true;
     }
-    /* consecutive ordinary records from p while they start before `limit`, at most max_records */
-    void walk(int64_t p, int64_t limit, size_t max_records, std::vector<Extent> &out) const
+    /* consecutive ordinary records from p while they start before `limit`, at most max_records; returns their bases */
+    int64_t walk(int64_t p, int64_t limit, size_t max_records, std::vector<Extent> &out) const
     {
         int guess = -1;
+        int64_t bases = 0;
         Extent x;
         while (out.size() < max_records && p < limit && walk_one(p, guess, x)) {
             out.push_back(x);
-            p = x.next;
+            bases += x.len;
+            p = x.next();
         }
+        return bases;
     }
 
-    /* Structural scan of up to max_records consecutive ordinary records from the cursor.  Does NOT move the
-     * cursor.  Stops at the first record that is not of the plain 4-line shape or not wholly in the buffer.
+    /* What one worker of the structural scan found in its slice of the byte range (kept between calls: no
+     * allocation per batch).  The first `n` records of `ext` are the piece's share of the scan's result. */
+    struct Piece {
+        std::vector<Extent> ext;
+        size_t n = 0;
+        int64_t bases = 0; /* sum of len over the first n records */
+    };
+    const std::vector<Piece> &pieces() const { return pieces_; }
+    unsigned n_pieces() const { return n_pieces_; }
+
+    /* Structural scan of up to max_records consecutive ordinary records from the cursor; returns how many it found
+     * and leaves them in pieces()[0 .. n_pieces()), in order.  Does NOT move the cursor.  Stops at the first record
+     * that is not of the plain 4-line shape or not wholly in the buffer.
      * Large requests are scanned in parallel: the byte range is cut into one slice per worker, every worker
      * but the first looks for a place in its slice where two ordinary records follow a newline and walks on
-     * from there, and the pieces are joined only where one piece ends exactly where the next begins — so the
-     * joined list is a chain of consecutive records from the cursor, like the serial walk's (a piece that does
-     * not fit is dropped together with everything after it and scanned again by the next call). */
-    int scan_fast(int max_records, std::vector<Extent> &out)
+     * from there, and a piece is accepted only when it begins exactly where the piece before it ended — so the
+     * result is a chain of consecutive records from the cursor, like the serial walk's (a piece that does not fit is
+     * dropped together with everything after it and scanned again by the next call). */
+    int scan_fast(int max_records)
     {
-        out.clear();
+        n_pieces_ = 0;
         if (last_char_ != 0) return 0;
         refill_keep_tail(1 << 26);
         ParsePool &pool = ParsePool::get();
         const unsigned T = pool.size();
+        if (pieces_.size() < T) pieces_.resize(T);
         const int64_t avail = end_ - begin_;
-        int64_t span = (int64_t)((double)max_records * avg_record_bytes_ * 1.03) + 4096;
+        int64_t span = (int64_t)((double)max_records * avg_record_bytes_ * 1.02) + 4096;
         if (span > avail) span = avail;
         static const int64_t min_span = [] { /* B200ALN_PAR_SCAN_MIN: tests lower it to push small inputs through the parallel scan */
             const char *e = getenv("B200ALN_PAR_SCAN_MIN");
             return e ? (int64_t)atol(e) : (int64_t)1 << 20;
         }();
-        if (T < 2 || max_records < 8192 || span < min_span || span < (int64_t)T * 64 || getenv("B200ALN_SERIAL_SCAN")) {
-            walk(begin_, end_, (size_t)max_records, out);
-        } else {
-            std::vector<std::vector<Extent>> piece(T);
+        int64_t total = 0;
+        if (!(T < 2 || max_records < 8192 || span < min_span || span < (int64_t)T * 64 || getenv("B200ALN_SERIAL_SCAN"))) {
             const int64_t lo = begin_;
             pool.run([&](unsigned t) {
+                Piece &pc = pieces_[t];
+                pc.ext.clear();
+                pc.n = 0;
+                pc.bases = 0;
                 const int64_t from = lo + span * (int64_t)t / (int64_t)T, to = lo + span * (int64_t)(t + 1) / (int64_t)T;
                 int64_t p = from;
                 if (t > 0) { /* the first position at or after `from` where two ordinary records follow a newline */
@@ -550,45 +636,53 @@ class SeqReader {
                         const int64_t c = (int64_t)(nl - b) + 1;
                         int g = -1;
                         Extent x1, x2;
-                        if (c < to && walk_one(c, g, x1) && (x1.next >= end_ || walk_one(x1.next, g, x2))) { p = c; break; }
+                        if (c < to && walk_one(c, g, x1) && (x1.next() >= end_ || walk_one(x1.next(), g, x2))) { p = c; break; }
                         q = c + 1;
                     }
                     if (p < 0) return;
                 }
-                piece[t].reserve((size_t)((to - from) / 64 + 16));
-                walk(p, to, (size_t)max_records, piece[t]);
+                pc.bases = walk(p, to, (size_t)max_records, pc.ext);
             });
             int64_t expect = begin_;
-            for (unsigned t = 0; t < T; ++t) {
-                if (piece[t].empty() || piece[t][0].start != expect) break;
-                out.insert(out.end(), piece[t].begin(), piece[t].end());
-                expect = out.back().next;
+            for (unsigned t = 0; t < T && total < max_records; ++t) {
+                Piece &pc = pieces_[t];
+                if (pc.ext.empty() || pc.ext[0].start != expect) break;
+                pc.n = pc.ext.size();
+                if ((int64_t)pc.n > max_records - total) { /* the request is full inside this piece */
+                    pc.n = (size_t)(max_records - total);
+                    pc.bases = 0;
+                    for (size_t i = 0; i < pc.n; ++i) pc.bases += pc.ext[i].len;
+                }
+                total += (int64_t)pc.n;
+                expect = pc.ext[pc.n - 1].next();
+                ++n_pieces_;
             }
-            if ((int)out.size() > max_records) out.resize((size_t)max_records);
-            if (out.empty()) walk(begin_, end_, (size_t)max_records, out); /* (the first record is odd, or a tiny span) */
         }
-        if (out.size() >= 64) avg_record_bytes_ = (double)(out.back().next - begin_) / (double)out.size();
-        return (int)out.size();
+        if (total == 0) { /* a small request, or the first record is odd */
+            Piece &pc = pieces_[0];
+            pc.ext.clear();
+            pc.bases = walk(begin_, end_, (size_t)max_records, pc.ext);
+            pc.n = pc.ext.size();
+            n_pieces_ = 1;
+            total = (int64_t)pc.n;
+        }
+        if (total >= 64) {
+            const Piece &last = pieces_[n_pieces_ - 1];
+            avg_record_bytes_ = (double)(last.ext[last.n - 1].next() - begin_) / (double)total;
+        }
+        return (int)total;
     }
     /* character checks of the fast path (see read_record_fast) + conversion; false = let the exact parser decide */
     bool convert_extent(const Extent &x, uint8_t *codes, bool is_64, int trim_qual, int *len_out) const
     {
         const unsigned char *b = data_;
-        const unsigned char *sq = b + x.seq, *ql = b + x.qual;
-        unsigned acc = 0;
-        for (int i = 0; i < x.len; ++i) {
-            const uint8_t v = g_seqclass.t[sq[i]];
-            acc |= v;
-            codes[i] = (uint8_t)(v & 7);
-        }
-        unsigned badq = 0;
-        for (int i = 0; i < x.len; ++i) badq |= (unsigned)((unsigned char)(ql[i] - 33) > 94); /* outside 33..127 */
-        if ((acc & 0x80u) | badq) return false;
+        const unsigned char *sq = b + x.start + x.seq, *ql = b + x.start + x.qual;
+        if (!g_convert(sq, ql, x.len, codes)) return false;
         int len = x.len;
         if (trim_qual >= 1) { /* bwa_trim_read on the (offset-corrected) qualities */
             int sc = 0, best = 0, best_l = x.len - 1;
             for (int l = x.len - 1; l >= BWA_MIN_RDLEN - 1; --l) {
-                const int q = (int)(unsigned char)(char)(b[x.qual + l] - (is_64 ? 31 : 0));
+                const int q = (int)(unsigned char)(char)(ql[l] - (is_64 ? 31 : 0));
                 sc += trim_qual - (q - 33);
                 if (sc < 0) break;
                 if (sc > best) { best = sc; best_l = l; }
@@ -663,6 +757,8 @@ class SeqReader {
     const unsigned char *data_ = nullptr; /* buf_.data() or map_ */
     int64_t begin_ = 0, end_ = 0;
     double avg_record_bytes_ = 300.0; /* of the records scanned last: sizes the parallel scan's byte range */
+    std::vector<Piece> pieces_;        /* scan_fast's result, one piece per worker */
+    unsigned n_pieces_ = 0;
     bool is_eof_ = false;
     int last_char_ = 0;
     std::string name_, seq_, qual_;
@@ -729,65 +825,92 @@ static void append_current(SeqReader &rd, bool is_64, int l_bc, int trim_qual, P
  * validated + converted by worker threads; any record that is not provably parsed identically by the
  * reference's state machine (kseq.h:150-194) goes through the exact parser, one record at a time.
  */
-int next_batch(SeqReader &rd, int n_needed, int mode, int trim_qual, PackedBatch &b)
+int next_batch(SeqReader &rd, int n_needed, int mode, int trim_qual, PackedBatch &b, bool append = false)
 {
     const bool is_64 = mode & BWA_MODE_IL13;
     const int l_bc = (mode >> 24) & 0xff;
-    b.clear();
+    if (!append) b.clear();
+    b.n_trimmed = b.n_tot = 0;
+    const size_t batch_base = b.lens.size(); /* append: the batch is what this call adds */
     if (l_bc > 15) {
         fprintf(stderr, "[bwa_read_seq] the maximum barcode length is 15.\n");
         return 0;
     }
     ParsePool &pool = ParsePool::get();
-    const unsigned n_workers = pool.size();
-    std::vector<SeqReader::Extent> ext;
     bool eof = false;
-    while (!eof && (int)b.lens.size() < n_needed) {
-        int n = l_bc == 0 ? rd.scan_fast(n_needed - (int)b.lens.size(), ext) : 0;
+    while (!eof && (int)(b.lens.size() - batch_base) < n_needed) {
+        const int n = l_bc == 0 ? rd.scan_fast(n_needed - (int)(b.lens.size() - batch_base)) : 0;
         if (n >= 64) {
-            const size_t base_reads = b.lens.size();
-            size_t total = b.codes.size();
-            b.offs.resize(base_reads + (size_t)n);
-            b.lens.resize(base_reads + (size_t)n);
-            for (int i = 0; i < n; ++i) { b.offs[base_reads + i] = (int64_t)total; total += (size_t)ext[i].len; }
-            const size_t codes_base = b.codes.size();
-            b.codes.resize(total);
-            std::vector<int> first_bad(n_workers, n);
-            auto work = [&](unsigned t) {
-                const int lo = (int)((int64_t)n * t / n_workers), hi = (int)((int64_t)n * (t + 1) / n_workers);
-                for (int i = lo; i < hi; ++i) {
-                    int len;
-                    if (!rd.convert_extent(ext[i], b.codes.data() + b.offs[base_reads + i], is_64, trim_qual, &len)) {
-                        first_bad[t] = i;
-                        return;
-                    }
-                    b.lens[base_reads + i] = len;
-                }
-            };
-            pool.run(work);
-            int ok = n;
-            for (unsigned t = 0; t < n_workers; ++t) if (first_bad[t] < ok) ok = first_bad[t];
-            /* keep records [0, ok); the one at `ok` (if any) goes to the exact parser below */
-            size_t kept_codes = codes_base;
-            for (int i = 0; i < ok; ++i) {
-                kept_codes += (size_t)ext[i].len;
-                b.n_tot += ext[i].len;
-                b.n_trimmed += ext[i].len - b.lens[base_reads + i];
+            /* every piece of the scan is converted by the worker that found it, straight into its place */
+            const std::vector<SeqReader::Piece> &pc = rd.pieces();
+            const unsigned np = rd.n_pieces();
+            const size_t base_reads = b.lens.size(), codes_base = b.codes.size();
+            size_t first_read[33], first_code[33];
+            first_read[0] = base_reads;
+            first_code[0] = codes_base;
+            for (unsigned t = 0; t < np; ++t) {
+                first_read[t + 1] = first_read[t] + pc[t].n;
+                first_code[t + 1] = first_code[t] + (size_t)pc[t].bases;
             }
-            b.offs.resize(base_reads + (size_t)ok);
-            b.lens.resize(base_reads + (size_t)ok);
-            b.codes.resize(kept_codes);
-            rd.set_cursor(ok > 0 ? ext[ok - 1].next : ext[0].start);
-            if (ok == n) continue;
+            b.offs.resize(first_read[np]);
+            b.lens.resize(first_read[np]);
+            b.codes.resize(first_code[np]);
+            long bad_at[32], trimmed[32]; /* per piece: the first record the fast path refuses (-1: none), bases trimmed */
+            auto work = [&](unsigned t) {
+                if (t >= np) return;
+                bad_at[t] = -1;
+                long tr = 0;
+                size_t at = first_code[t];
+                for (size_t i = 0; i < pc[t].n; ++i) {
+                    const SeqReader::Extent &x = pc[t].ext[i];
+                    int len;
+                    if (!rd.convert_extent(x, b.codes.data() + at, is_64, trim_qual, &len)) {
+                        bad_at[t] = (long)i;
+                        break;
+                    }
+                    b.offs[first_read[t] + i] = (int64_t)at;
+                    b.lens[first_read[t] + i] = len;
+                    tr += x.len - len;
+                    at += (size_t)x.len;
+                }
+                trimmed[t] = tr;
+            };
+            if (np == 1) work(0);
+            else pool.run(work);
+            /* keep the records before the first refused one; that one goes to the exact parser below */
+            bool all = true;
+            for (unsigned t = 0; t < np && all; ++t) {
+                if (bad_at[t] < 0) {
+                    b.n_tot += pc[t].bases;
+                    b.n_trimmed += trimmed[t];
+                    continue;
+                }
+                all = false;
+                size_t kept_codes = first_code[t];
+                for (long i = 0; i < bad_at[t]; ++i) {
+                    kept_codes += (size_t)pc[t].ext[(size_t)i].len;
+                    b.n_tot += pc[t].ext[(size_t)i].len;
+                    b.n_trimmed += pc[t].ext[(size_t)i].len - b.lens[first_read[t] + (size_t)i];
+                }
+                b.offs.resize(first_read[t] + (size_t)bad_at[t]);
+                b.lens.resize(first_read[t] + (size_t)bad_at[t]);
+                b.codes.resize(kept_codes);
+                rd.set_cursor(pc[t].ext[(size_t)bad_at[t]].start);
+            }
+            if (all) {
+                const SeqReader::Piece &last = pc[np - 1];
+                rd.set_cursor(last.ext[last.n - 1].next());
+                continue;
+            }
         }
         /* one record through the reference-exact path (also refills the buffer / detects the end) */
         const int l = rd.read_record();
         if (l < 0) eof = true;
         else append_current(rd, is_64, l_bc, trim_qual, b);
     }
-    if (!b.lens.empty() && trim_qual >= 1)
+    if (b.lens.size() > batch_base && trim_qual >= 1)
         fprintf(stderr, "[bwa_read_seq] %.1f%% bases are trimmed.\n", 100.0f * b.n_trimmed / b.n_tot);
-    return (int)b.lens.size();
+    return (int)(b.lens.size() - batch_base);
 }
 
 /* BAM input (bwa_bam_open / bwa_read_bam, bwaseqio.c:21-31,89-141; record layout bamlite.c:76-104).
@@ -813,10 +936,12 @@ class BamReader {
     }
 
     /* bwa_read_bam: up to n_needed reads into the packed form */
-    int next_batch(int n_needed, int trim_qual, PackedBatch &b)
+    int next_batch(int n_needed, int trim_qual, PackedBatch &b, bool append = false)
     {
         static const uint8_t nt16_nt4[16] = {4, 0, 1, 4, 2, 4, 4, 4, 3, 4, 4, 4, 4, 4, 4, 4}; /* bwaseqio.c:11 */
-        b.clear();
+        if (!append) b.clear();
+        b.n_trimmed = b.n_tot = 0;
+        const size_t base = b.lens.size();
         for (;;) {
             int32_t block_len;
             if (f_->read(&block_len, 4) != 4) break;
@@ -857,11 +982,11 @@ class BamReader {
             b.offs.push_back((int64_t)b.codes.size());
             b.lens.push_back(len);
             b.codes.insert(b.codes.end(), seq_.begin(), seq_.end());
-            if ((int)b.lens.size() == n_needed) break;
+            if ((int)(b.lens.size() - base) == n_needed) break;
         }
-        if (!b.lens.empty() && trim_qual >= 1)
+        if (b.lens.size() > base && trim_qual >= 1)
             fprintf(stderr, "[bwa_read_seq] %.1f%% bases are trimmed.\n", 100.0f * b.n_trimmed / b.n_tot);
-        return (int)b.lens.size();
+        return (int)(b.lens.size() - base);
     }
 
   private:
@@ -927,16 +1052,17 @@ struct b200aln_reader {
             bam.reset(new BamReader(fn, which));
         } else fq.reset(new SeqReader(fn));
     }
-    int next(int n_needed, int mode, int trim_qual, PackedBatch &b)
+    /* the next n_needed reads into b, or (append) behind what b holds; returns how many were read */
+    int next(int n_needed, int mode, int trim_qual, PackedBatch &b, bool append = false)
     {
         if (bam) {
             if ((mode >> 24 & 0xff) > 15) {
                 fprintf(stderr, "[bwa_read_seq] the maximum barcode length is 15.\n");
                 return 0;
             }
-            return bam->next_batch(n_needed, trim_qual, b);
+            return bam->next_batch(n_needed, trim_qual, b, append);
         }
-        return next_batch(*fq, n_needed, mode, trim_qual, b);
+        return next_batch(*fq, n_needed, mode, trim_qual, b, append);
     }
 };
 
@@ -1002,64 +1128,41 @@ extern "C" void b200aln_cal_sa_reg_gap(b200aln_ctx *ctx, int n_seqs, void *seqs_
 
 namespace {
 
-struct BatchResult {
-    std::vector<int32_t> n_aln;
-    std::vector<b200aln_rec_t> recs;
-    std::vector<char> sai; /* the batch as it goes to the .sai file (bwtaln.c:227-231): per read n_aln, then its records */
-    double seconds = 0;
-};
-
-/* one reference batch on `ctxs` (one context per GPU): contiguous shards, concatenated in input order */
-BatchResult process_batch(const std::vector<b200aln_ctx *> &ctxs, const PackedBatch &b, const b200aln_opt_t *opt)
-{
-    struct timespec t0, t1;
-    clock_gettime(CLOCK_MONOTONIC, &t0);
-    const int n = (int)b.lens.size(), g = (int)ctxs.size();
-    int max_len = 0;
-    for (int r = 0; r < n; ++r) if (b.lens[r] > max_len) max_len = b.lens[r];
-    BatchResult out;
-    out.n_aln.resize((size_t)n);
-    std::vector<std::vector<b200aln_rec_t>> part((size_t)g);
-    auto run = [&](int gi) {
-        const int base = n / g, rem = n % g;
-        const int lo = gi * base + (gi < rem ? gi : rem), hi = lo + base + (gi < rem ? 1 : 0);
-        if (hi <= lo) return;
-        /* shards keep the batch-level max_gapo clamp of the whole batch (bwtaln.c:89-92) */
-        b200aln_set_int(ctxs[gi], "batch_max_len", max_len);
-        const int64_t start = b.offs[lo];
-        std::vector<int64_t> offs((size_t)(hi - lo));
-        for (int r = lo; r < hi; ++r) offs[r - lo] = b.offs[r] - start;
-        int64_t total = 0;
-        const b200aln_rec_t *rec = b200aln_batch(ctxs[gi], hi - lo, b.lens.data() + lo, offs.data(),
-                                                 b.codes.data() + start, opt, out.n_aln.data() + lo, &total);
-        part[gi].assign(rec, rec + total);
-    };
-    if (g == 1) run(0);
-    else {
-        std::vector<std::thread> th;
-        for (int gi = 0; gi < g; ++gi) th.emplace_back(run, gi);
-        for (auto &t : th) t.join();
-    }
-    for (int gi = 0; gi < g; ++gi) out.recs.insert(out.recs.end(), part[gi].begin(), part[gi].end());
-    out.sai.resize((size_t)n * 4 + out.recs.size() * sizeof(b200aln_rec_t));
-    {
-        char *w = out.sai.data();
-        const b200aln_rec_t *rec = out.recs.data();
-        for (int r = 0; r < n; ++r) {
-            const int32_t c = out.n_aln[(size_t)r];
-            memcpy(w, &c, 4);
-            w += 4;
-            if (c) {
-                memcpy(w, rec, (size_t)c * sizeof(b200aln_rec_t));
-                w += (size_t)c * sizeof(b200aln_rec_t);
-                rec += c;
+/* A parse unit of the driver: up to B200ALN_MERGE consecutive reference batches (0x40000 reads each, bwtaln.c:193)
+ * parsed into one set of arrays, which are page-locked so that the batch call copies straight from them.  The arrays
+ * are recycled through a pool: no allocation and no page faults per batch. */
+struct ParseUnit {
+    PackedBatch b;
+    const void *pin_p[3] = {nullptr, nullptr, nullptr};
+    size_t pin_bytes[3] = {0, 0, 0};
+    std::atomic<int> launches_left{0}; /* launches cut from this unit that are not finished yet */
+    void repin(bool pin)
+    { /* page-lock what the vectors own now (their whole capacity); a no-op while they have not moved */
+        const void *p[3] = {b.lens.data(), b.offs.data(), b.codes.data()};
+        const size_t n[3] = {b.lens.capacity() * 4, b.offs.capacity() * 8, b.codes.capacity()};
+        for (int i = 0; i < 3; ++i) {
+            if (p[i] == pin_p[i] && n[i] == pin_bytes[i]) continue;
+            if (pin_p[i]) b200aln_unpin(const_cast<void *>(pin_p[i]));
+            pin_p[i] = nullptr;
+            pin_bytes[i] = 0;
+            if (pin && p[i] && n[i] && b200aln_pin(const_cast<void *>(p[i]), n[i]) == 0) {
+                pin_p[i] = p[i];
+                pin_bytes[i] = n[i];
             }
         }
     }
-    clock_gettime(CLOCK_MONOTONIC, &t1);
-    out.seconds = (t1.tv_sec - t0.tv_sec) + 1e-9 * (t1.tv_nsec - t0.tv_nsec);
-    return out;
-}
+    ~ParseUnit()
+    {
+        for (int i = 0; i < 3; ++i) if (pin_p[i]) b200aln_unpin(const_cast<void *>(pin_p[i]));
+    }
+};
+
+/* One launch: reads [lo, hi) of a unit — whole reference batches that agree on the batch-level max_gapo clamp. */
+struct Launch {
+    ParseUnit *unit = nullptr;
+    int lo = 0, hi = 0;
+    int64_t seq = 0; /* position in the output */
+};
 
 } // namespace
 
@@ -1082,7 +1185,8 @@ extern "C" int64_t b200aln_aln_core(const char *prefix, const char *fn_fa, const
     if (device >= 0) devs.push_back(device);
     else for (int d = 0; d < b200aln_device_count(); ++d) devs.push_back(d);
     if (devs.empty()) b2host::fatal("b200aln_aln_core", "no CUDA device available; this engine has no CPU fallback.");
-    int n_slots = 2; /* batches in flight per GPU; more hide the long tail of heavy option sets (B200ALN_INFLIGHT) */
+    int n_slots = 4; /* launches in flight per GPU (B200ALN_INFLIGHT): the copies, the width pass and the drain of one
+                      * launch's search overlap the search of the others; from four the engine parks stragglers */
     {
         const char *e = getenv("B200ALN_INFLIGHT");
         if (e) n_slots = atoi(e);
@@ -1143,41 +1247,31 @@ extern "C" int64_t b200aln_aln_core(const char *prefix, const char *fn_fa, const
     FILE *out = fdopen(dup(out_fd), "wb");
     if (!out) b2host::fatal("b200aln_aln_core", "cannot open the output descriptor.");
     fwrite(opt, sizeof(b200aln_opt_t), 1, out); /* bwtaln.c:192 */
-
-    int64_t tot_seqs = 0, written = 0;
-    std::deque<std::future<BatchResult>> inflight;
     stamp("index resident on devices", (long long)devs.size());
-    auto drain_one = [&]() {
-        stamp("waiting for launch, reads so far", (long long)written);
-        BatchResult r = inflight.front().get();
-        inflight.pop_front();
-        stamp("launch finished, reads", (long long)r.n_aln.size());
-        fprintf(stderr, "[bwa_aln_core] calculate SA coordinate... %.2f sec\n", r.seconds);
-        fprintf(stderr, "[bwa_aln_core] write to the disk... ");
-        struct timespec t0, t1;
-        clock_gettime(CLOCK_MONOTONIC, &t0);
-        if (!r.sai.empty() && fwrite(r.sai.data(), 1, r.sai.size(), out) != r.sai.size())
-            b2host::fatal("b200aln_aln_core", "short write on the .sai output.");
-        clock_gettime(CLOCK_MONOTONIC, &t1);
-        written += (int64_t)r.n_aln.size();
-        fprintf(stderr, "%.2f sec\n", (t1.tv_sec - t0.tv_sec) + 1e-9 * (t1.tv_nsec - t0.tv_nsec));
-        fprintf(stderr, "[bwa_aln_core] %lld sequences have been processed.\n", (long long)written);
-    };
+
     /* The reference works in batches of 0x40000 reads (bwtaln.c:193), and one thing is decided per batch: the
-     * max_gapo clamp from the batch's longest read (bwtaln.c:89-92).  Consecutive reference batches that agree
-     * on it are handed to the GPUs as ONE launch (up to B200ALN_MERGE of them, default one per GPU): 0x40000 reads
-     * are only two per lane.  A launch goes out as soon as a slot is free, so short inputs are not held back. */
-    int merge = (int)devs.size(); /* a launch is cut into one shard per GPU: about one reference batch each (measured on
-                                   * one GPU: 10 M reads in 1.12 s unmerged, 1.37 s with four batches per launch) */
+     * max_gapo clamp from the batch's longest read (bwtaln.c:89-92).  0x40000 reads are only two per lane of one
+     * GPU, so consecutive reference batches that agree on the clamp go out as ONE launch (up to B200ALN_MERGE of
+     * them).  Three stages run side by side:
+     *   this thread parses units of up to B200ALN_MERGE batches into recycled page-locked arrays (the first units
+     *   are smaller, so that the GPUs start at once and short inputs are not held back) and cuts them into launches;
+     *   one worker thread per (GPU, slot) takes the next launch, runs the operator — which returns the launch as
+     *   the bytes of the .sai stream, formatted on the device — and
+     *   writes them when every earlier launch has been written. */
+    /* reads per reference batch: 0x40000 (bwtaln.c:193).  B200ALN_BATCH_READS is a hook for tests of this driver, which
+     * cannot afford a quarter of a million reads per batch on the CPU; the output then equals the reference's only
+     * for inputs whose batches all agree on the clamp. */
+    const int batch_reads = getenv("B200ALN_BATCH_READS") ? std::max(1, atoi(getenv("B200ALN_BATCH_READS"))) : 0x40000;
+    int merge = 8;
     {
         const char *e = getenv("B200ALN_MERGE");
         if (e) merge = atoi(e);
         if (merge < 1) merge = 1;
         if (merge > 64) merge = 64;
     }
-    if (merge > 1) /* buffers sized once for the largest launch */
-        for (auto &sc : slot_ctx)
-            for (b200aln_ctx *c : sc) b200aln_set_int(c, "reserve_reads", (int64_t)merge * 0x40000 / (int64_t)devs.size() + 1);
+    const bool pin = getenv("B200ALN_NO_PIN") == nullptr;
+    for (auto &sc : slot_ctx)
+        for (b200aln_ctx *c : sc) b200aln_set_int(c, "reserve_reads", (int64_t)merge * batch_reads + 1);
     auto clamp_key = [&](int max_len) { /* what make_params derives from the batch's longest read */
         int gapo = opt->max_gapo;
         if (opt->fnr > 0.0f) {
@@ -1186,56 +1280,144 @@ extern "C" int64_t b200aln_aln_core(const char *prefix, const char *fn_fa, const
         }
         return gapo;
     };
-    std::shared_ptr<PackedBatch> super;
-    int super_batches = 0, super_max_len = 0, super_key = 0;
-    int seq = 0;
-    auto flush = [&]() {
-        if (!super || super->lens.empty()) return;
-        const std::vector<b200aln_ctx *> *ctxs = &slot_ctx[(size_t)(seq % n_slots)];
-        if ((int)inflight.size() == n_slots) drain_one(); /* the slot's previous launch is finished and written */
-        std::shared_ptr<PackedBatch> b = super;
-        stamp("launch of reads", (long long)b->lens.size());
-        inflight.push_back(std::async(std::launch::async, [ctxs, b, opt]() { return process_batch(*ctxs, *b, opt); }));
-        ++seq;
-        super.reset();
-        super_batches = 0;
+
+    const int n_workers = (int)devs.size() * n_slots;
+    std::mutex mu;
+    std::condition_variable cv_work, cv_unit, cv_turn;
+    std::deque<Launch> queue;           /* launches waiting for a worker, in output order */
+    std::vector<ParseUnit *> free_units; /* the pool */
+    std::vector<std::unique_ptr<ParseUnit>> units;
+    bool no_more = false;
+    int64_t next_write = 0, written = 0;
+    /* the pool's arrays are allocated and page-locked by a helper thread, one unit after the other, while the
+     * first units are already at work */
+    for (int i = 0; i < n_workers + 2; ++i) units.emplace_back(new ParseUnit);
+    std::thread pool_maker([&]() {
+        for (auto &u : units) {
+            u->b.lens.reserve((size_t)merge * batch_reads);
+            u->b.offs.reserve((size_t)merge * batch_reads);
+            u->b.codes.reserve((size_t)merge * batch_reads * 104);
+            u->repin(pin);
+            std::lock_guard<std::mutex> lk(mu);
+            free_units.push_back(u.get());
+            cv_unit.notify_one();
+        }
+    });
+    auto worker = [&](int w) {
+        b200aln_ctx *ctx = slot_ctx[(size_t)(w / (int)devs.size())][(size_t)(w % (int)devs.size())];
+        for (;;) {
+            Launch L;
+            {
+                std::unique_lock<std::mutex> lk(mu);
+                cv_work.wait(lk, [&] { return !queue.empty() || no_more; });
+                if (queue.empty()) return;
+                L = queue.front();
+                queue.pop_front();
+            }
+            struct timespec t0, t1, t2;
+            clock_gettime(CLOCK_MONOTONIC, &t0);
+            const PackedBatch &b = L.unit->b;
+            int max_len = 0;
+            for (int r = L.lo; r < L.hi; ++r) if (b.lens[(size_t)r] > max_len) max_len = b.lens[(size_t)r];
+            b200aln_set_int(ctx, "batch_max_len", max_len);
+            int64_t n_bytes = 0;
+            const void *sai = b200aln_batch_sai(ctx, L.hi - L.lo, b.lens.data() + L.lo, b.offs.data() + L.lo, b.codes.data(),
+                                                opt, &n_bytes);
+            clock_gettime(CLOCK_MONOTONIC, &t1);
+            std::unique_lock<std::mutex> lk(mu);
+            if (--L.unit->launches_left == 0) { /* the unit's arrays are free again */
+                free_units.push_back(L.unit);
+                cv_unit.notify_one();
+            }
+            cv_turn.wait(lk, [&] { return next_write == L.seq; });
+            lk.unlock(); /* (only the launch whose turn it is gets here) */
+            stamp("launch finished, reads", (long long)(L.hi - L.lo));
+            if (n_bytes && fwrite(sai, 1, (size_t)n_bytes, out) != (size_t)n_bytes)
+                b2host::fatal("b200aln_aln_core", "short write on the .sai output.");
+            clock_gettime(CLOCK_MONOTONIC, &t2);
+            written += L.hi - L.lo;
+            fprintf(stderr, "[bwa_aln_core] calculate SA coordinate... %.2f sec\n", (t1.tv_sec - t0.tv_sec) + 1e-9 * (t1.tv_nsec - t0.tv_nsec));
+            fprintf(stderr, "[bwa_aln_core] write to the disk... %.2f sec\n", (t2.tv_sec - t1.tv_sec) + 1e-9 * (t2.tv_nsec - t1.tv_nsec));
+            fprintf(stderr, "[bwa_aln_core] %lld sequences have been processed.\n", (long long)written);
+            lk.lock();
+            ++next_write;
+            cv_turn.notify_all();
+        }
     };
-    for (;;) {
-        auto b = std::make_shared<PackedBatch>();
-        const int n = rd.next(0x40000, opt->mode, opt->trim_qual, *b);
-        if (n == 0) break;
-        tot_seqs += n;
-        stamp("parsed reads", (long long)tot_seqs);
-        int max_len = 0;
-        for (int32_t l : b->lens) if (l > max_len) max_len = l;
-        const int key = clamp_key(max_len);
-        if (super_batches) {
-            const int joint = max_len > super_max_len ? max_len : super_max_len;
-            if (super_batches >= merge || key != super_key || clamp_key(joint) != super_key) flush();
+    std::vector<std::thread> workers;
+    for (int w = 0; w < n_workers; ++w) workers.emplace_back(worker, w);
+
+    int64_t tot_seqs = 0, seq = 0;
+    int unit_batches = 1;
+    for (bool eof = false; !eof;) {
+        ParseUnit *u;
+        {
+            std::unique_lock<std::mutex> lk(mu);
+            cv_unit.wait(lk, [&] { return !free_units.empty(); });
+            u = free_units.front(); /* (oldest first: the ones the helper has prepared come before recycled ones) */
+            free_units.erase(free_units.begin());
         }
-        if (!super_batches) {
-            super = b;
-            super_max_len = max_len;
-            super_key = key;
-        } else {
-            const int64_t shift = (int64_t)super->codes.size();
-            const size_t at = super->lens.size();
-            super->lens.insert(super->lens.end(), b->lens.begin(), b->lens.end());
-            super->offs.resize(at + b->offs.size());
-            for (size_t i = 0; i < b->offs.size(); ++i) super->offs[at + i] = b->offs[i] + shift;
-            super->codes.insert(super->codes.end(), b->codes.begin(), b->codes.end());
-            if (max_len > super_max_len) super_max_len = max_len;
+        PackedBatch &b = u->b;
+        b.clear();
+        /* consecutive reference batches; a launch is cut where the batch-level clamp changes */
+        std::vector<Launch> cut;
+        int cur_lo = 0, cur_key = 0, cur_max = 0;
+        for (int k = 0; k < unit_batches; ++k) {
+            const int at = (int)b.lens.size();
+            const int n = rd.next(batch_reads, opt->mode, opt->trim_qual, b, true);
+            if (n == 0) { eof = true; break; }
+            tot_seqs += n;
+            stamp("parsed reads", (long long)tot_seqs);
+            int max_len = 0;
+            for (int r = at; r < at + n; ++r) if (b.lens[(size_t)r] > max_len) max_len = b.lens[(size_t)r];
+            const int key = clamp_key(max_len);
+            if (at > cur_lo) {
+                const int joint = max_len > cur_max ? max_len : cur_max;
+                if (key != cur_key || clamp_key(joint) != cur_key) {
+                    Launch L;
+                    L.unit = u; L.lo = cur_lo; L.hi = at;
+                    cut.push_back(L);
+                    cur_lo = at;
+                }
+            }
+            if (at == cur_lo) { cur_key = key; cur_max = max_len; }
+            else if (max_len > cur_max) cur_max = max_len;
+            if (n < batch_reads) { eof = true; break; }
         }
-        ++super_batches;
-        while (!inflight.empty() && inflight.front().wait_for(std::chrono::seconds(0)) == std::future_status::ready) drain_one();
-        if ((int)inflight.size() < n_slots) flush();
+        if ((int)b.lens.size() > cur_lo) {
+            Launch L;
+            L.unit = u; L.lo = cur_lo; L.hi = (int)b.lens.size();
+            cut.push_back(L);
+        }
+        std::unique_lock<std::mutex> lk(mu);
+        if (cut.empty()) free_units.push_back(u);
+        else {
+            lk.unlock();
+            u->repin(pin);
+            lk.lock();
+            u->launches_left = (int)cut.size();
+            for (Launch &L : cut) {
+                L.seq = seq++;
+                stamp("launch of reads", (long long)(L.hi - L.lo));
+                queue.push_back(L);
+            }
+            cv_work.notify_all();
+        }
+        if (unit_batches < merge) unit_batches = unit_batches * 2 < merge ? unit_batches * 2 : merge;
     }
-    flush();
-    while (!inflight.empty()) drain_one();
+    {
+        std::lock_guard<std::mutex> lk(mu);
+        no_more = true;
+    }
+    cv_work.notify_all();
+    for (auto &t : workers) t.join();
+    pool_maker.join();
     fclose(out);
     stamp("output closed, reads", (long long)tot_seqs);
-    for (size_t i = 0; i < devs.size(); ++i)
-        for (int sl = n_slots - 1; sl >= 0; --sl) b200aln_close(slot_ctx[(size_t)sl][i]);
+    units.clear();
+    if (!getenv("B200ALN_FAST_EXIT")) /* (the command line: the process ends here, the driver's teardown frees the device) */
+        for (size_t i = 0; i < devs.size(); ++i)
+            for (int sl = n_slots - 1; sl >= 0; --sl) b200aln_close(slot_ctx[(size_t)sl][i]);
     stamp("contexts closed", (long long)devs.size());
     return tot_seqs;
 }

@@ -490,6 +490,20 @@ __global__ void __launch_bounds__(256) k_compact(int n, const int32_t *n_aln, co
     }
 }
 
+/* The batch as the bytes bwa_aln_core writes for it (bwtaln.c:227-231): per read n_aln, then its records.
+ * Read r's part starts at word r + 4 * off[r] of the stream; one thread per read (most reads have one or two records). */
+__global__ void __launch_bounds__(256) k_sai_pack(int n, const int32_t *n_aln, const int64_t *off, const Rec *packed,
+                                                  uint32_t *out)
+{
+    for (int r = blockIdx.x * blockDim.x + threadIdx.x; r < n; r += gridDim.x * blockDim.x) {
+        const int c = n_aln[r] > 0 ? n_aln[r] : 0;
+        uint32_t *dst = out + (size_t)r + 4 * (size_t)off[r];
+        const uint32_t *src = reinterpret_cast<const uint32_t *>(packed + off[r]);
+        dst[0] = (uint32_t)c;
+        for (int j = 0; j < 4 * c; ++j) dst[1 + j] = src[j];
+    }
+}
+
 /* random sector gather: the roofline denominator.  span = 1: independent random
  * 32-byte sectors; span = 2: random 64-byte aligned pairs of sectors (tells whether the memory
  * system moves 64 B per miss anyway). */
@@ -627,6 +641,7 @@ struct b200aln_ctx {
     int susp_calls = 4;
     std::atomic<int> active_calls{0}; /* owner: batch calls in flight on this index (all contexts sharing it) */
     int susp_min = 4096;    /* resume rounds park again only while more than this many searches are left */
+    int lane_reads = 8;     /* fast pass: lanes = reads / lane_reads for batches too small to give the full grid that many (0: always the full grid) */
     int prep_rounds = 1;   /* pruned pops a lane may go through per warp iteration before the warp moves on */
     int reserve_reads = 0; /* size the per-batch buffers for at least this many reads */
     int count = 0;         /* 1: fast pass with the pop / sector counters (b200aln_stats_t pops, occ_lookups) */
@@ -641,7 +656,7 @@ struct b200aln_ctx {
     int batch_max_len = 0; /* > 0: the reference batch this call is a shard of has this longest read */
     /* device buffers */
     DevBuf lens, offs, codes, md, Q, W, n_amb, ent, recs, n_aln, over_slot, over_list, misc, off64,
-        blk_tot, packed, dkey, order_buf, Q_re, W_re, ent_big, recs_big, heads_wide, heads_wide_big, ent_mid, recs_mid, over_list2, over_list3, sa_in, sa_out, grp_in, grp_out;
+        blk_tot, packed, dkey, order_buf, Q_re, W_re, ent_big, recs_big, heads_wide, heads_wide_big, ent_mid, recs_mid, over_list2, over_list3, sa_in, sa_out, grp_in, grp_out, sai;
     HostBuf h_in, h_out, h_misc, h_nout, h_ring;
     b200aln_stats_t stats;
     /* chunk pipeline: a call with more than chunk_reads * 1.5 reads is cut into chunks that run on
@@ -893,7 +908,7 @@ extern "C" b200aln_ctx *b200aln_clone(b200aln_ctx *p)
     c->rec_cap = p->rec_cap; c->rec_cap_big = p->rec_cap_big; c->big_lanes = p->big_lanes;
     c->arena_cap_mid = p->arena_cap_mid; c->rec_cap_mid = p->rec_cap_mid; c->mid_lanes = p->mid_lanes;
     c->pop_batch = p->pop_batch; c->count = p->count; c->reserve_reads = p->reserve_reads; c->prep_rounds = p->prep_rounds;
-    c->prefetch_fast = p->prefetch_fast; c->prefetch_mid = p->prefetch_mid; c->order = p->order; c->search_block = p->search_block; c->q16 = p->q16; c->susp = p->susp; c->susp_min = p->susp_min; c->susp_calls = p->susp_calls;
+    c->prefetch_fast = p->prefetch_fast; c->prefetch_mid = p->prefetch_mid; c->order = p->order; c->search_block = p->search_block; c->q16 = p->q16; c->susp = p->susp; c->susp_min = p->susp_min; c->susp_calls = p->susp_calls; c->lane_reads = p->lane_reads;
     make_streams(c);
     for (int i = 0; i < 8; ++i) CK(cudaEventCreate(&c->ev[i]));
     for (int i = 0; i < 2; ++i) CK(cudaEventCreate(&c->tm[i]));
@@ -950,7 +965,7 @@ extern "C" void b200aln_close(b200aln_ctx *c)
                       &c->packed, &c->dkey, &c->order_buf, &c->Q_re, &c->W_re, &c->ent_big, &c->recs_big, &c->heads_wide, &c->heads_wide_big, &c->ent_mid, &c->recs_mid,
                       &c->over_list2, &c->over_list3, &c->sa_in, &c->sa_out};
     for (DevBuf *b : bufs) b->release();
-    c->grp_in.release(); c->grp_out.release();
+    c->grp_in.release(); c->grp_out.release(); c->sai.release();
     c->asm_n_aln.release(); c->asm_packed.release();
     c->park_buf.release(); c->park_flag.release(); c->park_ring.release();
     c->h_in.release(); c->h_out.release(); c->h_misc.release(); c->h_nout.release(); c->h_ring.release();
@@ -997,6 +1012,7 @@ extern "C" void b200aln_set_int(b200aln_ctx *c, const char *key, int64_t v)
     else if (!strcmp(key, "susp")) c->susp = (int)v;
     else if (!strcmp(key, "susp_calls")) c->susp_calls = (int)v;
     else if (!strcmp(key, "susp_min")) c->susp_min = (int)v;
+    else if (!strcmp(key, "lane_reads")) c->lane_reads = (int)v;
     else if (!strcmp(key, "prefetch_fast")) c->prefetch_fast = (int)v;
     else if (!strcmp(key, "prefetch_mid")) c->prefetch_mid = (int)v;
     else if (!strcmp(key, "arena_cap_mid")) c->arena_cap_mid = (uint32_t)v;
@@ -1104,7 +1120,14 @@ static void run_batch_device(b200aln_ctx *c, int n_reads, int max_len, const int
     const int strideQ32 = round_up8(max_len > 0 ? max_len : 1), strideW = round_up8(max_len + 1); /* 32-byte aligned rows */
     const int strideQ = q16 ? ((max_len > 0 ? max_len : 1) + 15) & ~15 : strideQ32; /* the fast pass's rows; re-runs use QF<32> */
     const int wblocks = c->n_sm * c->width_blocks_per_sm;
-    const int sblocks = c->n_sm * c->search_blocks_per_sm;
+    /* The fast pass's grid: every resident slot for a large batch; for a small one only as many lanes as give each
+     * about lane_reads reads (a lane with two reads is idle half the launch, waiting for the batch's longest), so
+     * that several small batches in flight share the SMs side by side, each with the arenas of its own lanes only. */
+    int sblocks = c->n_sm * c->search_blocks_per_sm;
+    if (c->lane_reads > 0) {
+        const int64_t want = ((int64_t)n_reads + (int64_t)c->lane_reads * 128 - 1) / ((int64_t)c->lane_reads * 128);
+        if (want < sblocks) sblocks = (int)(want > c->n_sm ? want : c->n_sm);
+    }
     const size_t lanes = (size_t)sblocks * 128;
 
     c->md.need(md.size() * 4);
@@ -1593,6 +1616,54 @@ extern "C" const b200aln_rec_t *b200aln_batch(b200aln_ctx *c, int n_reads, const
     c->stats = acc;
     *total = tot_all;
     return c->h_out.as<b200aln_rec_t>();
+}
+
+extern "C" const void *b200aln_batch_sai(b200aln_ctx *c, int n_reads, const int32_t *lens, const int64_t *offs,
+                                         const uint8_t *codes, const b200aln_opt_t *opt, int64_t *n_bytes)
+{
+    CK(cudaSetDevice(c->device));
+    CallInFlight in_flight(c);
+    *n_bytes = 0;
+    if (n_reads <= 0) return c->h_out.p;
+    int max_len = 0;
+    for (int r = 0; r < n_reads; ++r) {
+        if (lens[r] < 0) die("b200aln_batch_sai", "read %d has negative length %d.", r, lens[r]);
+        if (lens[r] > max_len) max_len = lens[r];
+    }
+    Params P;
+    std::vector<int> md;
+    if (c->batch_max_len > 0 && c->batch_max_len < max_len)
+        die("b200aln_batch_sai", "batch_max_len %d is smaller than a read of this shard (%d).", c->batch_max_len, max_len);
+    b2host::make_params(*opt, c->batch_max_len > 0 ? c->batch_max_len : max_len, lens, n_reads, P, md);
+    if ((int)md.size() < max_len + 1) md.resize((size_t)max_len + 1, opt->max_diff);
+    const bool pinned_in = host_pinned(lens) && host_pinned(offs) && host_pinned(codes);
+    const int64_t tot = run_chunk_host(c, n_reads, lens, offs, codes, opt, P, md, pinned_in);
+    const size_t bytes = (size_t)n_reads * 4 + (size_t)tot * 16;
+    c->sai.need(bytes);
+    c->h_out.need(bytes);
+    k_sai_pack<<<c->n_sm * 4, 256, 0, c->st>>>(n_reads, c->n_aln.as<int32_t>(), c->off64.as<int64_t>(), c->packed.as<Rec>(),
+                                               c->sai.as<uint32_t>());
+    CK(cudaGetLastError());
+    CK(cudaMemcpyAsync(c->h_out.p, c->sai.p, bytes, cudaMemcpyDeviceToHost, c->st));
+    CK(cudaEventRecord(c->ev[6], c->st));
+    wait_stream(c, c->st);
+    finish_stats(c, true);
+    c->stats.kernel_launches += 1;
+    *n_bytes = (int64_t)bytes;
+    return c->h_out.p;
+}
+
+/* page-locks caller memory (and releases it) so that b200aln_batch / b200aln_batch_sai copy straight from it */
+extern "C" int b200aln_pin(void *p, size_t bytes)
+{
+    if (!p || !bytes) return 0;
+    const cudaError_t e = cudaHostRegister(p, bytes, cudaHostRegisterPortable);
+    if (e != cudaSuccess) { (void)cudaGetLastError(); return -1; }
+    return 0;
+}
+extern "C" void b200aln_unpin(void *p)
+{
+    if (p && cudaHostUnregister(p) != cudaSuccess) (void)cudaGetLastError();
 }
 
 extern "C" void b200aln_batch_device(b200aln_ctx *c, int n_reads, int max_len, const int32_t *d_lens,

@@ -49,7 +49,7 @@ class SeqLayout(ctypes.Structure):
 
 
 EXPORTS = ["b200aln_version", "b200aln_opt_init", "b200aln_cal_maxdiff", "b200aln_device_count", "b200aln_open",
-           "b200aln_open_prefix", "b200aln_clone", "b200aln_close", "b200aln_batch", "b200aln_batch_device", "b200aln_last_stats",
+           "b200aln_open_prefix", "b200aln_clone", "b200aln_close", "b200aln_batch", "b200aln_batch_sai", "b200aln_pin", "b200aln_unpin", "b200aln_batch_device", "b200aln_last_stats",
            "b200aln_set_int", "b200aln_timer_start", "b200aln_timer_stop", "b200aln_cal_sa_reg_gap", "b200aln_seq_layout", "b200aln_aln_core", "b200aln_aln_main", "b200aln_reader_open", "b200aln_reader_next", "b200aln_reader_close",
            "b200aln_sector_roofline", "b200aln_sa_load", "b200aln_bwt_sa", "b200aln_sa2seq", "b200aln_alngrp_merge", "b200aln_warm_device"]
 
@@ -79,6 +79,12 @@ def load_library():
     L.b200aln_batch.restype = ctypes.c_void_p
     L.b200aln_batch.argtypes = [ctypes.c_void_p, ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p,
                                 ctypes.POINTER(GapOptC), ctypes.c_void_p, ctypes.POINTER(ctypes.c_int64)]
+    L.b200aln_batch_sai.restype = ctypes.c_void_p
+    L.b200aln_batch_sai.argtypes = [ctypes.c_void_p, ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p,
+                                    ctypes.POINTER(GapOptC), ctypes.POINTER(ctypes.c_int64)]
+    L.b200aln_pin.restype = ctypes.c_int
+    L.b200aln_pin.argtypes = [ctypes.c_void_p, ctypes.c_size_t]
+    L.b200aln_unpin.argtypes = [ctypes.c_void_p]
     L.b200aln_batch_device.argtypes = [ctypes.c_void_p, ctypes.c_int, ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p,
                                        ctypes.c_void_p, ctypes.POINTER(GapOptC), ctypes.POINTER(ctypes.c_void_p),
                                        ctypes.POINTER(ctypes.c_void_p), ctypes.POINTER(ctypes.c_int64)]
@@ -180,6 +186,27 @@ class Engine:
         else:
             rec = np.empty(0, dtype=ALN_DTYPE)
         return n_aln, rec
+
+    def cal_sa_reg_gap_sai(self, lens, offs, codes, opt: GapOpt, pin: bool = False) -> bytes:
+        """One reference batch -> the bytes bwa_aln_core writes for it (bwtaln.c:227-231), formatted on the device
+        (b200aln_batch_sai).  pin: page-lock the input arrays for the call (b200aln_pin / b200aln_unpin)."""
+        lens = np.ascontiguousarray(lens, dtype=np.int32)
+        offs = np.ascontiguousarray(offs, dtype=np.int64)
+        codes = np.ascontiguousarray(codes, dtype=np.uint8)
+        nb = ctypes.c_int64()
+        oc = opt.to_c()
+        pinned = []
+        if pin:
+            for a in (lens, offs, codes):
+                if a.nbytes and self._L.b200aln_pin(a.ctypes.data, a.nbytes) == 0:
+                    pinned.append(a)
+        try:
+            p = self._L.b200aln_batch_sai(self._ctx, len(lens), lens.ctypes.data, offs.ctypes.data, codes.ctypes.data,
+                                          ctypes.byref(oc), ctypes.byref(nb))
+            return bytes((ctypes.c_uint8 * nb.value).from_address(p)) if nb.value else b""
+        finally:
+            for a in pinned:
+                self._L.b200aln_unpin(a.ctypes.data)
 
     def batch_pinned(self, lens_ptr: int, offs_ptr: int, codes_ptr: int, n: int, opt: GapOpt, n_aln_ptr: int):
         """Same call on raw host pointers (pinned buffers owned by the caller); returns (records ptr, total)."""

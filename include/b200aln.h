@@ -115,6 +115,25 @@ void b200aln_batch_device(b200aln_ctx *ctx, int n_reads, int max_len, const int3
                           const uint8_t *d_codes, const b200aln_opt_t *opt, const int32_t **d_n_aln,
                           const b200aln_rec_t **d_recs, int64_t *total);
 
+/*
+ * b200aln_batch with the result formatted on the device as the bytes
+ * bwa_aln_core writes for the batch (the fwrite loop of bwtaln.c:227-231): per
+ * read its n_aln (int32) followed by its records.  Returns the context's
+ * page-locked output buffer (valid until the next batch call on it) and its
+ * size in *n_bytes; the driver only has to write() it.
+ */
+const void *b200aln_batch_sai(b200aln_ctx *ctx, int n_reads, const int32_t *lens, const int64_t *offs,
+                              const uint8_t *codes, const b200aln_opt_t *opt, int64_t *n_bytes);
+
+/*
+ * Page-locks caller memory (cudaHostRegister) / releases it.  The batch calls
+ * copy straight from page-locked input arrays; pageable ones go through the
+ * context's staging buffer first.  b200aln_pin returns 0, or -1 when the range
+ * cannot be locked (the memory then simply stays pageable).
+ */
+int b200aln_pin(void *p, size_t bytes);
+void b200aln_unpin(void *p);
+
 /* Per-call counters of the last batch on this context (instrumentation). */
 typedef struct {
     double ms_h2d, ms_width, ms_search, ms_compact, ms_d2h, ms_total; /* CUDA-event times */

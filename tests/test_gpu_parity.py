@@ -43,6 +43,21 @@ def test_golden_sai(tag, eng, golden_dir):
     assert got == want
 
 
+@pytest.mark.parametrize("tag", ["default", "N_n2", "q20", "short_o3"])
+@pytest.mark.parametrize("pin", [False, True], ids=["pageable", "page_locked"])
+def test_sai_bytes_formatted_on_the_device(tag, pin, eng, golden_dir):
+    """b200aln_batch_sai: the batch as the bytes of the reference's fwrite loop (bwtaln.c:227-231), from pageable input
+    arrays (through the context's staging buffer) and from arrays page-locked with b200aln_pin"""
+    args, fq = CASES[tag]
+    path = os.path.join(golden_dir, fq + ".fq.gz")
+    opt, _, _, _ = parse_aln_args(args + ["prefix", path])
+    buf = io.BytesIO()
+    sai.write_header(buf, opt)
+    for batch in seqio.read_batches(path, opt.mode, opt.trim_qual):
+        buf.write(eng.cal_sa_reg_gap_sai(batch.lens, batch.offs, batch.codes, opt, pin=pin))
+    assert buf.getvalue() == open(os.path.join(golden_dir, f"g1_{tag}.sai"), "rb").read()
+
+
 @pytest.mark.parametrize("tag", ["default", "stress", "N_n2"])
 def test_overflow_path_is_exact(tag, g1_index, golden_dir):
     """Tiny fast arenas force most reads through the large-arena pass; bytes must not change."""
@@ -239,7 +254,8 @@ def test_cli_merges_reference_batches_only_when_allowed(rand_index, tmp_path):
     """The CLI driver hands several 0x40000-read reference batches to the GPU as one launch, but only batches
     that agree on the batch-level max_gapo clamp (bwtaln.c:89-92).  Input: one whole batch of reads < 38 bp
     (with -o 3 the clamp bites), then 100 bp reads, then a short tail — against the unmodified reference
-    binary, with the default (one reference batch per GPU and launch), four and up to 64 merged, one batch in flight."""
+    binary, with the default (up to eight reference batches per launch), no merging, up to 64 merged with one launch
+    in flight, and pageable parse buffers."""
     if not pyoracle.have_ref():
         pytest.skip("oracle/_ref/ibwa not present")
     g, bwt, rbwt = rand_index
@@ -268,7 +284,7 @@ def test_cli_merges_reference_batches_only_when_allowed(rand_index, tmp_path):
     pyoracle.run_ref(["aln", "-t", str(os.cpu_count() or 4)] + args + [prefix, fq], stdout_path=ref_out)
     want = open(ref_out, "rb").read()
     exe = os.path.join(ROOT, "ibwa_b200", "b200aln")
-    for env in ({}, {"B200ALN_MERGE": "4"}, {"B200ALN_INFLIGHT": "1", "B200ALN_MERGE": "64"}):
+    for env in ({}, {"B200ALN_MERGE": "1"}, {"B200ALN_INFLIGHT": "1", "B200ALN_MERGE": "64"}, {"B200ALN_NO_PIN": "1", "B200ALN_MERGE": "2"}):
         out = str(tmp_path / "gpu.sai")
         subprocess.check_call([exe, "aln"] + args + ["-f", out, prefix, fq], stderr=subprocess.DEVNULL,
                               env=dict(os.environ, **env))

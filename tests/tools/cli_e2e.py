@@ -26,6 +26,7 @@ def main():
     fq, fq_ref = "/tmp/cli_e2e.fq", "/tmp/cli_e2e_ref.fq"
     bench.write_fastq(fq, reads)
     bench.write_fastq(fq_ref, reads[:n_ref])
+    os.sync()  # the write-back of 2 GB of dirty pages would otherwise run next to the first timed process
     exe = os.path.join(ROOT, "ibwa_b200", "b200aln")
     cores = os.cpu_count()
     def run_cli(path, env):
@@ -35,7 +36,7 @@ def main():
         p = subprocess.run([exe, "aln", "-f", "/tmp/gpu_out.sai", prefix, path], stderr=subprocess.PIPE, check=True,
                            env=dict(os.environ, B200ALN_TRACE="1", **env))
         dt = time.perf_counter() - t0
-        t_load = t_done = None
+        t_load = t_done = t_parsed = None
         for line in p.stderr.decode(errors="replace").splitlines():
             if line.startswith("[trace]"):
                 sec = float(line.split()[1])
@@ -43,16 +44,43 @@ def main():
                     t_load = sec
                 elif "output closed" in line:
                     t_done = sec
-        return dt, t_load, t_done
+                elif "parsed reads" in line:
+                    t_parsed = sec
+        return dt, t_load, t_done, t_parsed
+
+    # the reader alone (parse only, results dropped), for comparison with the whole pipeline
+    import ctypes
+    from ibwa_b200 import engine
+    L = engine.load_library()
+    for rep in range(2):
+        t0 = time.perf_counter()
+        r = L.b200aln_reader_open(fq.encode(), 0)
+        pl, po, pc, nb = ctypes.c_void_p(), ctypes.c_void_p(), ctypes.c_void_p(), ctypes.c_int64()
+        tot = 0
+        while True:
+            k = L.b200aln_reader_next(r, 0x40000, 0, 0, ctypes.byref(pl), ctypes.byref(po), ctypes.byref(pc), ctypes.byref(nb))
+            if k == 0:
+                break
+            tot += k
+        L.b200aln_reader_close(r)
+        dt = time.perf_counter() - t0
+        print(f"reader alone ({tot} reads, {cores} cores): {dt:.2f} s = {tot / dt / 1e6:.2f} M reads/s", flush=True)
 
     for label, path, cnt in (("full", fq, n), ("ref-sized", fq_ref, n_ref)):
-        for env in ({}, {"B200ALN_MERGE": "1"}) if label == "full" else ({},):
-            dt, t_load, t_done = run_cli(path, env)
+        full_md5 = set()
+        for env in ({}, {}, {"B200ALN_MERGE": "1"}, {"B200ALN_MERGE": "16"}, {"B200ALN_NO_PIN": "1"},
+                    {"B200ALN_INFLIGHT": "6"}) if label == "full" else ({},):
+            dt, t_load, t_done, t_parsed = run_cli(path, env)
             if label == "ref-sized":
                 os.replace("/tmp/gpu_out.sai", "/tmp/gpu_ref-sized.sai")
-            print(f"b200aln aln ({label}: {cnt} reads{', no batch merging' if env else ''}): {dt:.2f} s wall = "
+            else:
+                full_md5.add(subprocess.run(["md5sum", "/tmp/gpu_out.sai"], stdout=subprocess.PIPE, check=True).stdout.split()[0])
+            print(f"b200aln aln ({label}: {cnt} reads{', ' + str(env) if env else ''}): {dt:.2f} s wall = "
                   f"{cnt / dt / 1e6:.2f} M reads/s incl. index load ({t_load:.2f} s); parse + search + write "
-                  f"{t_done - t_load:.2f} s = {cnt / (t_done - t_load) / 1e6:.2f} M reads/s")
+                  f"{t_done - t_load:.2f} s = {cnt / (t_done - t_load) / 1e6:.2f} M reads/s (last batch parsed "
+                  f"{t_parsed - t_load:.2f} s after the index was resident)", flush=True)
+        if label == "full":
+            print("all runs of the full input wrote the same bytes:", len(full_md5) == 1)
     t0 = time.perf_counter()
     with open("/tmp/ref.sai", "wb") as fo:
         subprocess.run([bench.REF_BIN, "aln", "-t", str(cores), prefix, fq_ref], stdout=fo, stderr=subprocess.DEVNULL,

@@ -45,6 +45,7 @@ struct b200aln_reader;
 extern "C" void b200aln_warm_device(int device); /* b200aln.cu: creates the CUDA context */
 extern "C" int b200aln_pin(void *p, size_t bytes);
 extern "C" void b200aln_unpin(void *p);
+extern "C" void b200aln_prealloc(int device, int n_contexts, int n_reads, int max_len);
 
 namespace {
 
@@ -1193,9 +1194,49 @@ extern "C" int64_t b200aln_aln_core(const char *prefix, const char *fn_fa, const
         if (n_slots < 1) n_slots = 1;
         if (n_slots > 8) n_slots = 8;
     }
+    /* reads per reference batch: 0x40000 (bwtaln.c:193).  B200ALN_BATCH_READS is a hook for tests of this driver, which
+     * cannot afford a quarter of a million reads per batch on the CPU; the output then equals the reference's only
+     * for inputs whose batches all agree on the clamp. */
+    const int batch_reads = getenv("B200ALN_BATCH_READS") ? std::max(1, atoi(getenv("B200ALN_BATCH_READS"))) : 0x40000;
+    int merge = 8;
+    {
+        const char *e = getenv("B200ALN_MERGE");
+        if (e) merge = atoi(e);
+        if (merge < 1) merge = 1;
+        if (merge > 64) merge = 64;
+    }
+    const bool pin = getenv("B200ALN_NO_PIN") == nullptr;
+    const int n_workers = (int)devs.size() * n_slots;
+    std::mutex mu;
+    std::condition_variable cv_work, cv_unit, cv_turn;
+    std::deque<Launch> queue;           /* launches waiting for a worker, in output order */
+    std::vector<ParseUnit *> free_units; /* the pool */
+    std::vector<std::unique_ptr<ParseUnit>> units;
+    bool no_more = false;
+    int64_t next_write = 0, written = 0;
+    /* the pool's arrays are allocated and page-locked by a helper thread, one unit after the other, while the
+     * first units are already at work */
+    for (int i = 0; i < n_workers + 2; ++i) units.emplace_back(new ParseUnit);
+    std::thread pool_maker([&]() {
+        for (auto &u : units) {
+            u->b.lens.reserve((size_t)merge * batch_reads);
+            u->b.offs.reserve((size_t)merge * batch_reads);
+            u->b.codes.reserve((size_t)merge * batch_reads * 104);
+            u->repin(pin);
+            stamp("unit ready (arrays reserved and page-locked), MB", (long long)((u->pin_bytes[0] + u->pin_bytes[1] + u->pin_bytes[2]) >> 20));
+            std::lock_guard<std::mutex> lk(mu);
+            free_units.push_back(u.get());
+            cv_unit.notify_one();
+        }
+    });
     std::vector<std::vector<b200aln_ctx *>> slot_ctx((size_t)n_slots);
-    {   /* bwt_restore_bwt x2 once (bwtio.c:51-70) — both files at the same time, while the CUDA contexts come
-         * up on another thread — then one upload per GPU in parallel */
+    /* what the scratch allocated ahead of the contexts is sized by: the longest read of the first batch, known to
+     * the setup thread once this thread has parsed it (-1: not yet, 0: there are no reads) */
+    int first_max_len = -1;
+    std::condition_variable cv_first;
+    auto load_index = [&]() {
+        /* bwt_restore_bwt x2 once (bwtio.c:51-70) — both files at the same time, while the CUDA contexts come up
+         * and the contexts' device buffers are allocated on other threads — then one upload per GPU in parallel */
         struct Raw { uint32_t *w = nullptr; size_t nw = 0; uint32_t hdr[5]; };
         Raw raw[2];
         b200aln_bwt_view_t v[2];
@@ -1219,12 +1260,24 @@ extern "C" int64_t b200aln_aln_core(const char *prefix, const char *fn_fa, const
             }
             close(fd);
         };
-        std::thread warm([&]() { for (int d : devs) b200aln_warm_device(d); });
+        std::thread warm([&]() {
+            for (int d : devs) b200aln_warm_device(d);
+            int ml;
+            {
+                std::unique_lock<std::mutex> lk(mu);
+                cv_first.wait(lk, [&] { return first_max_len >= 0; });
+                ml = first_max_len;
+            }
+            if (ml > 0 && !getenv("B200ALN_NO_PREALLOC")) {
+                for (int d : devs) b200aln_prealloc(d, n_slots, merge * batch_reads + 1, ml);
+                stamp("device buffers of the contexts allocated ahead, contexts", (long long)devs.size() * n_slots);
+            }
+        });
         std::thread t1([&]() { load(1); });
         load(0);
         t1.join();
-        warm.join();
         stamp("index files read", 2);
+        warm.join();
         for (int j = 0; j < 2; ++j) {
             v[j].primary = raw[j].hdr[0];
             v[j].L2[0] = 0;
@@ -1243,35 +1296,37 @@ extern "C" int64_t b200aln_aln_core(const char *prefix, const char *fn_fa, const
         for (auto &t : th) t.join();
         free(raw[0].w);
         free(raw[1].w);
-    }
+        for (auto &sc : slot_ctx)
+            for (b200aln_ctx *c : sc) {
+                b200aln_set_int(c, "reserve_reads", (int64_t)merge * batch_reads + 1);
+                if (const char *e = getenv("B200ALN_SET")) { /* engine knobs for experiments: "key=value,key=value" (b200aln_set_int) */
+                    std::string kv(e);
+                    for (size_t at = 0; at < kv.size();) {
+                        size_t end = kv.find(',', at);
+                        if (end == std::string::npos) end = kv.size();
+                        const std::string one = kv.substr(at, end - at);
+                        const size_t eq = one.find('=');
+                        if (eq != std::string::npos) b200aln_set_int(c, one.substr(0, eq).c_str(), atoll(one.c_str() + eq + 1));
+                        at = end + 1;
+                    }
+                }
+            }
+        stamp("index resident on devices", (long long)devs.size());
+    };
     FILE *out = fdopen(dup(out_fd), "wb");
     if (!out) b2host::fatal("b200aln_aln_core", "cannot open the output descriptor.");
     fwrite(opt, sizeof(b200aln_opt_t), 1, out); /* bwtaln.c:192 */
-    stamp("index resident on devices", (long long)devs.size());
 
     /* The reference works in batches of 0x40000 reads (bwtaln.c:193), and one thing is decided per batch: the
      * max_gapo clamp from the batch's longest read (bwtaln.c:89-92).  0x40000 reads are only two per lane of one
      * GPU, so consecutive reference batches that agree on the clamp go out as ONE launch (up to B200ALN_MERGE of
      * them).  Three stages run side by side:
      *   this thread parses units of up to B200ALN_MERGE batches into recycled page-locked arrays (the first units
-     *   are smaller, so that the GPUs start at once and short inputs are not held back) and cuts them into launches;
+     *   are smaller, so that the GPUs start at once and short inputs are not held back) and cuts them into launches
+     *   — from the start, while a setup thread is still reading the index files and opening the contexts;
      *   one worker thread per (GPU, slot) takes the next launch, runs the operator — which returns the launch as
      *   the bytes of the .sai stream, formatted on the device — and
      *   writes them when every earlier launch has been written. */
-    /* reads per reference batch: 0x40000 (bwtaln.c:193).  B200ALN_BATCH_READS is a hook for tests of this driver, which
-     * cannot afford a quarter of a million reads per batch on the CPU; the output then equals the reference's only
-     * for inputs whose batches all agree on the clamp. */
-    const int batch_reads = getenv("B200ALN_BATCH_READS") ? std::max(1, atoi(getenv("B200ALN_BATCH_READS"))) : 0x40000;
-    int merge = 8;
-    {
-        const char *e = getenv("B200ALN_MERGE");
-        if (e) merge = atoi(e);
-        if (merge < 1) merge = 1;
-        if (merge > 64) merge = 64;
-    }
-    const bool pin = getenv("B200ALN_NO_PIN") == nullptr;
-    for (auto &sc : slot_ctx)
-        for (b200aln_ctx *c : sc) b200aln_set_int(c, "reserve_reads", (int64_t)merge * batch_reads + 1);
     auto clamp_key = [&](int max_len) { /* what make_params derives from the batch's longest read */
         int gapo = opt->max_gapo;
         if (opt->fnr > 0.0f) {
@@ -1281,28 +1336,6 @@ extern "C" int64_t b200aln_aln_core(const char *prefix, const char *fn_fa, const
         return gapo;
     };
 
-    const int n_workers = (int)devs.size() * n_slots;
-    std::mutex mu;
-    std::condition_variable cv_work, cv_unit, cv_turn;
-    std::deque<Launch> queue;           /* launches waiting for a worker, in output order */
-    std::vector<ParseUnit *> free_units; /* the pool */
-    std::vector<std::unique_ptr<ParseUnit>> units;
-    bool no_more = false;
-    int64_t next_write = 0, written = 0;
-    /* the pool's arrays are allocated and page-locked by a helper thread, one unit after the other, while the
-     * first units are already at work */
-    for (int i = 0; i < n_workers + 2; ++i) units.emplace_back(new ParseUnit);
-    std::thread pool_maker([&]() {
-        for (auto &u : units) {
-            u->b.lens.reserve((size_t)merge * batch_reads);
-            u->b.offs.reserve((size_t)merge * batch_reads);
-            u->b.codes.reserve((size_t)merge * batch_reads * 104);
-            u->repin(pin);
-            std::lock_guard<std::mutex> lk(mu);
-            free_units.push_back(u.get());
-            cv_unit.notify_one();
-        }
-    });
     auto worker = [&](int w) {
         b200aln_ctx *ctx = slot_ctx[(size_t)(w / (int)devs.size())][(size_t)(w % (int)devs.size())];
         for (;;) {
@@ -1316,6 +1349,7 @@ extern "C" int64_t b200aln_aln_core(const char *prefix, const char *fn_fa, const
             }
             struct timespec t0, t1, t2;
             clock_gettime(CLOCK_MONOTONIC, &t0);
+            stamp("worker takes launch", (long long)L.seq);
             const PackedBatch &b = L.unit->b;
             int max_len = 0;
             for (int r = L.lo; r < L.hi; ++r) if (b.lens[(size_t)r] > max_len) max_len = b.lens[(size_t)r];
@@ -1324,6 +1358,13 @@ extern "C" int64_t b200aln_aln_core(const char *prefix, const char *fn_fa, const
             const void *sai = b200aln_batch_sai(ctx, L.hi - L.lo, b.lens.data() + L.lo, b.offs.data() + L.lo, b.codes.data(),
                                                 opt, &n_bytes);
             clock_gettime(CLOCK_MONOTONIC, &t1);
+            if (trace) {
+                b200aln_stats_t st;
+                b200aln_last_stats(ctx, &st);
+                fprintf(stderr, "[trace]            launch %lld on worker %d: %d reads, call %.1f ms (h2d %.1f width %.1f search %.1f compact %.1f d2h %.1f)\n",
+                        (long long)L.seq, w, L.hi - L.lo, 1e3 * ((t1.tv_sec - t0.tv_sec) + 1e-9 * (t1.tv_nsec - t0.tv_nsec)),
+                        st.ms_h2d, st.ms_width, st.ms_search, st.ms_compact, st.ms_d2h);
+            }
             std::unique_lock<std::mutex> lk(mu);
             if (--L.unit->launches_left == 0) { /* the unit's arrays are free again */
                 free_units.push_back(L.unit);
@@ -1345,7 +1386,10 @@ extern "C" int64_t b200aln_aln_core(const char *prefix, const char *fn_fa, const
         }
     };
     std::vector<std::thread> workers;
-    for (int w = 0; w < n_workers; ++w) workers.emplace_back(worker, w);
+    std::thread setup([&]() {
+        load_index();
+        for (int w = 0; w < n_workers; ++w) workers.emplace_back(worker, w);
+    });
 
     int64_t tot_seqs = 0, seq = 0;
     int unit_batches = 1;
@@ -1353,6 +1397,7 @@ extern "C" int64_t b200aln_aln_core(const char *prefix, const char *fn_fa, const
         ParseUnit *u;
         {
             std::unique_lock<std::mutex> lk(mu);
+            if (free_units.empty()) stamp("parser waits for a free unit, reads so far", (long long)tot_seqs);
             cv_unit.wait(lk, [&] { return !free_units.empty(); });
             u = free_units.front(); /* (oldest first: the ones the helper has prepared come before recycled ones) */
             free_units.erase(free_units.begin());
@@ -1384,6 +1429,11 @@ extern "C" int64_t b200aln_aln_core(const char *prefix, const char *fn_fa, const
             else if (max_len > cur_max) cur_max = max_len;
             if (n < batch_reads) { eof = true; break; }
         }
+        if (first_max_len < 0) { /* the setup thread sizes the contexts' buffers by the first batch */
+            std::lock_guard<std::mutex> lk(mu);
+            first_max_len = b.lens.empty() ? 0 : cur_max;
+            cv_first.notify_all();
+        }
         if ((int)b.lens.size() > cur_lo) {
             Launch L;
             L.unit = u; L.lo = cur_lo; L.hi = (int)b.lens.size();
@@ -1409,6 +1459,7 @@ extern "C" int64_t b200aln_aln_core(const char *prefix, const char *fn_fa, const
         std::lock_guard<std::mutex> lk(mu);
         no_more = true;
     }
+    setup.join();
     cv_work.notify_all();
     for (auto &t : workers) t.join();
     pool_maker.join();

@@ -641,7 +641,7 @@ struct b200aln_ctx {
     int susp_calls = 4;
     std::atomic<int> active_calls{0}; /* owner: batch calls in flight on this index (all contexts sharing it) */
     int susp_min = 4096;    /* resume rounds park again only while more than this many searches are left */
-    int lane_reads = 8;     /* fast pass: lanes = reads / lane_reads for batches too small to give the full grid that many (0: always the full grid) */
+    int lane_reads = 0;     /* fast pass: lanes = reads / lane_reads for batches too small to give the full grid that many (0: always the full grid) */
     int prep_rounds = 1;   /* pruned pops a lane may go through per warp iteration before the warp moves on */
     int reserve_reads = 0; /* size the per-batch buffers for at least this many reads */
     int count = 0;         /* 1: fast pass with the pop / sector counters (b200aln_stats_t pops, occ_lookups) */
@@ -810,6 +810,74 @@ static void apply_l2_window(b200aln_ctx *c)
         fprintf(stderr, "[b200aln] L2 window: %.1f MB of the interval table persisting (carve-out %.1f MB)\n", bytes / 1e6, carve / 1e6);
 }
 
+/* ---- scratch allocated ahead of the contexts (b200aln_prealloc) ------------------------------------------------
+ * Allocating a context's per-batch buffers takes a few hundred milliseconds (the fast pass's arena alone is
+ * 15 GB), and the first batch on a fresh context used to pay for it.  A driver that knows how many contexts it is
+ * going to use can have the buffers allocated while it is still reading the index files: the sets wait in a
+ * per-process pool, and b200aln_open / b200aln_clone hand one to every new context of that device. */
+struct ScratchSet {
+    int device = 0;
+    DevBuf ent, W, Q, recs, n_aln, over_slot, over_list, off64, n_amb, dkey, order_buf, lens, offs, codes, sai, packed;
+    HostBuf h_out, h_nout;
+};
+static std::mutex g_scratch_mu;
+static std::vector<ScratchSet *> g_scratch;
+
+extern "C" void b200aln_prealloc(int device, int n_contexts, int n_reads, int max_len)
+{
+    if (n_contexts <= 0 || n_reads <= 0 || cudaSetDevice(device) != cudaSuccess) { (void)cudaGetLastError(); return; }
+    cudaDeviceProp prop;
+    CK(cudaGetDeviceProperties(&prop, device));
+    const b200aln_ctx defaults{};
+    if (max_len < 1) max_len = 1;
+    const size_t n = (size_t)n_reads, lanes = (size_t)prop.multiProcessorCount * defaults.search_blocks_per_sm * 128;
+    const int strideQ = (max_len + 15) & ~15, strideW = round_up8(max_len + 1);
+    for (int i = 0; i < n_contexts; ++i) {
+        ScratchSet *s = new ScratchSet;
+        s->device = device;
+        s->ent.need(lanes * defaults.arena_cap * sizeof(StackRec));
+        s->W.need(n * 2 * strideW * 4 + 64);
+        s->Q.need(n * 2 * strideQ * 2 + 64); /* the 16-bit records of the default options; grows for others */
+        s->recs.need(n * defaults.rec_cap * 16);
+        s->n_aln.need(n * 4);
+        s->over_slot.need(n * 4);
+        s->over_list.need(n * 4);
+        s->off64.need(n * 8);
+        s->n_amb.need(n * 4);
+        s->dkey.need(n * 2);
+        s->order_buf.need(n * 4);
+        s->lens.need(n * 4);
+        s->offs.need(n * 8);
+        s->codes.need(n * (size_t)max_len + 16);
+        s->sai.need(n * 28);
+        s->packed.need(n * 24);
+        s->h_out.need(n * 28);
+        s->h_nout.need(n * 4);
+        std::lock_guard<std::mutex> g(g_scratch_mu);
+        g_scratch.push_back(s);
+    }
+}
+
+static void adopt_scratch(b200aln_ctx *c)
+{
+    ScratchSet *s = nullptr;
+    {
+        std::lock_guard<std::mutex> g(g_scratch_mu);
+        for (size_t i = 0; i < g_scratch.size(); ++i)
+            if (g_scratch[i]->device == c->device) {
+                s = g_scratch[i];
+                g_scratch.erase(g_scratch.begin() + (long)i);
+                break;
+            }
+    }
+    if (!s) return;
+    c->ent = s->ent; c->W = s->W; c->Q = s->Q; c->recs = s->recs; c->n_aln = s->n_aln; c->over_slot = s->over_slot;
+    c->over_list = s->over_list; c->off64 = s->off64; c->n_amb = s->n_amb; c->dkey = s->dkey; c->order_buf = s->order_buf;
+    c->lens = s->lens; c->offs = s->offs; c->codes = s->codes; c->sai = s->sai; c->packed = s->packed;
+    c->h_out = s->h_out; c->h_nout = s->h_nout;
+    delete s; /* (the buffers have no destructor: they live on in the context) */
+}
+
 extern "C" b200aln_ctx *b200aln_open(const b200aln_bwt_view_t *bwt, const b200aln_bwt_view_t *rbwt, int device)
 {
     int n = b200aln_device_count();
@@ -835,6 +903,7 @@ extern "C" b200aln_ctx *b200aln_open(const b200aln_bwt_view_t *bwt, const b200al
         }
     }
     make_streams(c);
+    adopt_scratch(c);
     for (int i = 0; i < 8; ++i) CK(cudaEventCreate(&c->ev[i]));
     for (int i = 0; i < 2; ++i) CK(cudaEventCreate(&c->tm[i]));
     if (!g_origin && getenv("B200ALN_TIMELINE")) {
@@ -910,6 +979,7 @@ extern "C" b200aln_ctx *b200aln_clone(b200aln_ctx *p)
     c->pop_batch = p->pop_batch; c->count = p->count; c->reserve_reads = p->reserve_reads; c->prep_rounds = p->prep_rounds;
     c->prefetch_fast = p->prefetch_fast; c->prefetch_mid = p->prefetch_mid; c->order = p->order; c->search_block = p->search_block; c->q16 = p->q16; c->susp = p->susp; c->susp_min = p->susp_min; c->susp_calls = p->susp_calls; c->lane_reads = p->lane_reads;
     make_streams(c);
+    adopt_scratch(c);
     for (int i = 0; i < 8; ++i) CK(cudaEventCreate(&c->ev[i]));
     for (int i = 0; i < 2; ++i) CK(cudaEventCreate(&c->tm[i]));
     memset(&c->stats, 0, sizeof c->stats);
@@ -1153,6 +1223,19 @@ static void run_batch_device(b200aln_ctx *c, int n_reads, int max_len, const int
     c->blk_tot.need((size_t)nscan * 8 + 8);
     c->h_misc.need(sizeof(Misc));
 
+    if (c->susp != 0 && !c->park_ring.p && fast_heads_ok(P, c->arena_cap)) {
+        /* The parking ring, with the first batch (not with the first parked one: allocating synchronises the device).
+         * Cleared HERE, ahead of ev[2]: the fast pass runs on another stream and waits for that event only — cleared
+         * after it (as this once was), the memsets could land in the middle of the first launch and wipe the
+         * tickets of searches already parked, whose reads then came back without hits. */
+        c->park_buf.need((size_t)PARK_CAP * SUSP_STRIDE * 4);
+        c->park_flag.need((size_t)PARK_CAP * 4);
+        c->park_ring.need(64);
+        c->h_ring.need(64);
+        CK(cudaMemsetAsync(c->park_flag.p, 0, (size_t)PARK_CAP * 4, c->st));
+        CK(cudaMemsetAsync(c->park_ring.p, 0, 64, c->st));
+    }
+
     CK(cudaMemcpyAsync(c->md.p, md.data(), md.size() * 4, cudaMemcpyHostToDevice, c->st));
     CK(cudaMemsetAsync(c->misc.p, 0, sizeof(Misc), c->st));
     CK(cudaMemsetAsync(c->over_slot.p, 0xff, (size_t)n_reads * 4, c->st));
@@ -1205,14 +1288,6 @@ static void run_batch_device(b200aln_ctx *c, int n_reads, int max_len, const int
     const int park_at = c->susp > 0 ? c->susp : (c->susp < 0 && owner->active_calls.load() >= c->susp_calls ? -c->susp : 0);
     const bool parking = park_at > 0 && !c->count && fast_heads_ok(P, c->arena_cap);
     SA.susp_thresh = 0; SA.park_buf = nullptr; SA.park_flag = nullptr; SA.park_ring = nullptr; SA.resume = 0; SA.resume_base = 0;
-    if (c->susp != 0 && !c->park_ring.p && fast_heads_ok(P, c->arena_cap)) { /* with the first batch, not with the first parked one: allocating synchronises the device */
-            c->park_buf.need((size_t)PARK_CAP * SUSP_STRIDE * 4);
-            c->park_flag.need((size_t)PARK_CAP * 4);
-            c->park_ring.need(64);
-            c->h_ring.need(64);
-            CK(cudaMemsetAsync(c->park_flag.p, 0, (size_t)PARK_CAP * 4, c->st));
-            CK(cudaMemsetAsync(c->park_ring.p, 0, 64, c->st));
-    }
     if (parking) {
         if (lanes > PARK_CAP) die("b200aln_batch", "internal: %zu lanes exceed the parking ring.", lanes);
         SA.susp_thresh = park_at; SA.park_buf = c->park_buf.as<uint32_t>(); SA.park_flag = c->park_flag.as<uint32_t>();
@@ -1639,8 +1714,9 @@ extern "C" const void *b200aln_batch_sai(b200aln_ctx *c, int n_reads, const int3
     const bool pinned_in = host_pinned(lens) && host_pinned(offs) && host_pinned(codes);
     const int64_t tot = run_chunk_host(c, n_reads, lens, offs, codes, opt, P, md, pinned_in);
     const size_t bytes = (size_t)n_reads * 4 + (size_t)tot * 16;
-    c->sai.need(bytes);
-    c->h_out.need(bytes);
+    const size_t reserve = (size_t)c->reserve_reads * 28; /* (a driver whose launches vary in size: sized once) */
+    c->sai.need(bytes > reserve ? bytes : reserve);
+    c->h_out.need(bytes > reserve ? bytes : reserve);
     k_sai_pack<<<c->n_sm * 4, 256, 0, c->st>>>(n_reads, c->n_aln.as<int32_t>(), c->off64.as<int64_t>(), c->packed.as<Rec>(),
                                                c->sai.as<uint32_t>());
     CK(cudaGetLastError());

@@ -134,6 +134,15 @@ const void *b200aln_batch_sai(b200aln_ctx *ctx, int n_reads, const int32_t *lens
 int b200aln_pin(void *p, size_t bytes);
 void b200aln_unpin(void *p);
 
+/*
+ * Allocates, ahead of time, the per-batch device and staging buffers of n_contexts contexts that are going to be
+ * opened or cloned on `device`, sized for calls of up to n_reads reads of up to max_len bases with the default
+ * knobs.  b200aln_open / b200aln_clone hand one such set to every new context of that device, so the first batch
+ * on it does not wait for 15+ GB of allocations; a driver calls this on a thread of its own while it is still
+ * reading the index files.  Sets that no context picks up stay allocated until the process ends.
+ */
+void b200aln_prealloc(int device, int n_contexts, int n_reads, int max_len);
+
 /* Per-call counters of the last batch on this context (instrumentation). */
 typedef struct {
     double ms_h2d, ms_width, ms_search, ms_compact, ms_d2h, ms_total; /* CUDA-event times */

@@ -55,6 +55,7 @@ extern "C" int b200aln_device_count(void)
 extern "C" void b200aln_warm_device(int) {}
 extern "C" int b200aln_pin(void *, size_t) { return -1; }
 extern "C" void b200aln_unpin(void *) {}
+extern "C" void b200aln_prealloc(int, int, int, int) {}
 
 extern "C" b200aln_ctx *b200aln_open(const b200aln_bwt_view_t *bwt, const b200aln_bwt_view_t *rbwt, int device)
 {
@@ -77,6 +78,7 @@ extern "C" b200aln_ctx *b200aln_clone(b200aln_ctx *p)
     return c;
 }
 extern "C" void b200aln_close(b200aln_ctx *c) { delete c; }
+extern "C" void b200aln_last_stats(const b200aln_ctx *, b200aln_stats_t *out) { memset(out, 0, sizeof *out); }
 extern "C" void b200aln_set_int(b200aln_ctx *c, const char *key, int64_t v)
 {
     if (!strcmp(key, "batch_max_len")) c->batch_max_len = (int)v;

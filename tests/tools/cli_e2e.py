@@ -39,13 +39,19 @@ def main():
         t_load = t_done = t_parsed = None
         for line in p.stderr.decode(errors="replace").splitlines():
             if line.startswith("[trace]"):
-                sec = float(line.split()[1])
+                try:
+                    sec = float(line.split()[1])
+                except ValueError:
+                    continue
                 if "index resident" in line:
                     t_load = sec
                 elif "output closed" in line:
                     t_done = sec
                 elif "parsed reads" in line:
                     t_parsed = sec
+        if os.environ.get("CLI_E2E_TRACE"):  # the driver's whole timeline of this run, for a look at the stages
+            with open(os.environ["CLI_E2E_TRACE"], "ab") as f:
+                f.write(b"==== " + path.encode() + b" " + repr(env).encode() + b"\n" + p.stderr)
         return dt, t_load, t_done, t_parsed
 
     # the reader alone (parse only, results dropped), for comparison with the whole pipeline
@@ -68,19 +74,46 @@ def main():
 
     for label, path, cnt in (("full", fq, n), ("ref-sized", fq_ref, n_ref)):
         full_md5 = set()
-        for env in ({}, {}, {"B200ALN_MERGE": "1"}, {"B200ALN_MERGE": "16"}, {"B200ALN_NO_PIN": "1"},
-                    {"B200ALN_INFLIGHT": "6"}) if label == "full" else ({},):
+        for env in ({}, {}, {"B200ALN_NO_PREALLOC": "1"}, {"B200ALN_MERGE": "16"}, {"B200ALN_INFLIGHT": "3"},
+                    {"B200ALN_MERGE": "1"}) if label == "full" else ({},):
             dt, t_load, t_done, t_parsed = run_cli(path, env)
             if label == "ref-sized":
                 os.replace("/tmp/gpu_out.sai", "/tmp/gpu_ref-sized.sai")
             else:
-                full_md5.add(subprocess.run(["md5sum", "/tmp/gpu_out.sai"], stdout=subprocess.PIPE, check=True).stdout.split()[0])
+                md5 = subprocess.run(["md5sum", "/tmp/gpu_out.sai"], stdout=subprocess.PIPE, check=True).stdout.split()[0]
+                full_md5.add(md5)
+                print("  md5", md5.decode(), os.path.getsize("/tmp/gpu_out.sai"))
+                if len(full_md5) == 1 and not os.path.exists("/tmp/gpu_first.sai"):
+                    os.replace("/tmp/gpu_out.sai", "/tmp/gpu_first.sai")
+                elif os.path.exists("/tmp/gpu_out.sai"):
+                    import numpy as np
+                    a = np.fromfile("/tmp/gpu_first.sai", dtype=np.uint8)
+                    b = np.fromfile("/tmp/gpu_out.sai", dtype=np.uint8)
+                    m = min(len(a), len(b))
+                    d = np.flatnonzero(a[:m] != b[:m])
+                    if len(d) or len(a) != len(b):
+                        print(f"  DIFFERS from the first run: sizes {len(a)} / {len(b)}, {len(d)} differing bytes, first at "
+                              f"{d[0] if len(d) else m}, last at {d[-1] if len(d) else m}", flush=True)
             print(f"b200aln aln ({label}: {cnt} reads{', ' + str(env) if env else ''}): {dt:.2f} s wall = "
                   f"{cnt / dt / 1e6:.2f} M reads/s incl. index load ({t_load:.2f} s); parse + search + write "
                   f"{t_done - t_load:.2f} s = {cnt / (t_done - t_load) / 1e6:.2f} M reads/s (last batch parsed "
                   f"{t_parsed - t_load:.2f} s after the index was resident)", flush=True)
         if label == "full":
             print("all runs of the full input wrote the same bytes:", len(full_md5) == 1)
+    # a longer input (the same reads four times over): what the pipeline does once it is full
+    big = "/tmp/cli_e2e_big.fq"
+    with open(big, "wb") as fo:
+        for _ in range(4):
+            subprocess.run(["cat", fq], stdout=fo, check=True)
+    os.sync()
+    for env in ({}, {"B200ALN_MERGE": "16"}):
+        if os.environ.get("CLI_E2E_QUICK"):
+            break
+        dt, t_load, t_done, t_parsed = run_cli(big, env)
+        print(f"b200aln aln (4 x full: {4 * n} reads{', ' + str(env) if env else ''}): {dt:.2f} s wall = "
+              f"{4 * n / dt / 1e6:.2f} M reads/s incl. index load ({t_load:.2f} s); parse + search + write "
+              f"{t_done - t_load:.2f} s = {4 * n / (t_done - t_load) / 1e6:.2f} M reads/s", flush=True)
+    os.remove(big)
     t0 = time.perf_counter()
     with open("/tmp/ref.sai", "wb") as fo:
         subprocess.run([bench.REF_BIN, "aln", "-t", str(cores), prefix, fq_ref], stdout=fo, stderr=subprocess.DEVNULL,

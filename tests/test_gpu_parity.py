@@ -232,6 +232,41 @@ def test_chunk_pipeline_inside_one_call(rand_index):
         assert np.array_equal(out_n.cpu().numpy(), n_aln) and out_r.cpu().numpy().tobytes() == rec.tobytes()
 
 
+def test_first_batches_of_fresh_contexts_in_flight_together(rand_index):
+    """Six fresh contexts on one index, every one's FIRST batch (the one that sets up its parking ring) in flight at
+    the same time with parking on: the persistent blocks of six launches leave no room on the SMs, which is when a
+    ring cleared on the wrong stream used to lose parked searches.  Every context must return what one batch on
+    its own returns.  Repeated, since the interleaving is the point."""
+    import threading
+    g, bwt, rbwt = rand_index
+    n, length = 150_000, 100
+    reads = synth.simulate_reads_fast(g, n, length, 11)
+    lens = np.full(n, length, np.int32)
+    offs = np.arange(n, dtype=np.int64) * length
+    opt = gap_init_opt()
+    with engine.Engine(bwt, rbwt, 0) as e:
+        e.set("susp", 0)
+        want_n, want_rec = e.cal_sa_reg_gap(lens, offs, reads.reshape(-1), opt)
+        for rep in range(3):
+            clones = [e.clone() for _ in range(6)]
+            got = [None] * len(clones)
+
+            def run(i):
+                clones[i].set("susp", 16)  # park whenever a warp is down to 16 searches, whatever else is in flight
+                got[i] = clones[i].cal_sa_reg_gap(lens, offs, reads.reshape(-1), opt)
+
+            th = [threading.Thread(target=run, args=(i,)) for i in range(len(clones))]
+            for t in th:
+                t.start()
+            for t in th:
+                t.join()
+            for c in clones:
+                c.close()
+            for i, (n_aln, rec) in enumerate(got):
+                assert np.array_equal(n_aln, want_n), (rep, i, int((n_aln != want_n).sum()))
+                assert rec.tobytes() == want_rec.tobytes(), (rep, i)
+
+
 def test_reference_binary_on_box(rand_index, tmp_path):
     """If the unmodified reference binary travelled with the repo, run it here on fresh inputs."""
     if not pyoracle.have_ref():

@@ -27,6 +27,7 @@
 #endif
 
 #include <algorithm>
+#include <atomic>
 #include <chrono>
 #include <condition_variable>
 #include <deque>
@@ -1217,8 +1218,10 @@ extern "C" int64_t b200aln_aln_core(const char *prefix, const char *fn_fa, const
     /* the pool's arrays are allocated and page-locked by a helper thread, one unit after the other, while the
      * first units are already at work */
     for (int i = 0; i < n_workers + 2; ++i) units.emplace_back(new ParseUnit);
+    std::atomic<bool> parsed_all{false};
     std::thread pool_maker([&]() {
         for (auto &u : units) {
+            if (parsed_all.load()) break; /* the input has ended: what is not prepared yet is not needed */
             u->b.lens.reserve((size_t)merge * batch_reads);
             u->b.offs.reserve((size_t)merge * batch_reads);
             u->b.codes.reserve((size_t)merge * batch_reads * 104);
@@ -1455,6 +1458,7 @@ extern "C" int64_t b200aln_aln_core(const char *prefix, const char *fn_fa, const
         }
         if (unit_batches < merge) unit_batches = unit_batches * 2 < merge ? unit_batches * 2 : merge;
     }
+    parsed_all.store(true);
     {
         std::lock_guard<std::mutex> lk(mu);
         no_more = true;

@@ -204,9 +204,15 @@ void b200aln_seq_layout(b200aln_seq_layout_t *out);
 /*
  * Replaces bwa_aln_core (bwtaln.c:173-241, declared bwtaln.h:138): reads
  * `fn_fa` (FASTA/FASTQ, plain or gzip, "-" = stdin), writes the 64-byte header
- * and the per-read records to `out_fd` in 0x40000-read batches.  `device` < 0
- * uses every visible GPU with the index replicated and each batch sharded.
- * Returns the number of reads processed.
+ * and the per-read records to `out_fd`.  The reference's batches of 0x40000
+ * reads (bwtaln.c:193) keep their meaning — the max_gapo clamp of a batch
+ * comes from its longest read (bwtaln.c:89-92) — but consecutive batches that
+ * agree on it go to a GPU as one launch (B200ALN_MERGE, default 8), several
+ * launches are in flight per GPU (B200ALN_INFLIGHT, default 4), parsing runs
+ * ahead in page-locked arrays and the .sai bytes are formatted on the device
+ * (INTEGRATION.md section 1).  `device` < 0 uses every visible GPU with the
+ * index replicated, launches going round the GPUs.  Returns the number of
+ * reads processed.
  */
 int64_t b200aln_aln_core(const char *prefix, const char *fn_fa, const b200aln_opt_t *opt, int out_fd, int device);
 

@@ -1236,7 +1236,7 @@ extern "C" int64_t b200aln_aln_core(const char *prefix, const char *fn_fa, const
     /* what the scratch allocated ahead of the contexts is sized by: the longest read of the first batch, known to
      * the setup thread once this thread has parsed it (-1: not yet, 0: there are no reads) */
     int first_max_len = -1;
-    std::condition_variable cv_first;
+    std::vector<std::thread> prealloc;
     auto load_index = [&]() {
         /* bwt_restore_bwt x2 once (bwtio.c:51-70) — both files at the same time, while the CUDA contexts come up
          * and the contexts' device buffers are allocated on other threads — then one upload per GPU in parallel */
@@ -1263,19 +1263,7 @@ extern "C" int64_t b200aln_aln_core(const char *prefix, const char *fn_fa, const
             }
             close(fd);
         };
-        std::thread warm([&]() {
-            for (int d : devs) b200aln_warm_device(d);
-            int ml;
-            {
-                std::unique_lock<std::mutex> lk(mu);
-                cv_first.wait(lk, [&] { return first_max_len >= 0; });
-                ml = first_max_len;
-            }
-            if (ml > 0 && !getenv("B200ALN_NO_PREALLOC")) {
-                for (int d : devs) b200aln_prealloc(d, n_slots, merge * batch_reads + 1, ml);
-                stamp("device buffers of the contexts allocated ahead, contexts", (long long)devs.size() * n_slots);
-            }
-        });
+        std::thread warm([&]() { for (int d : devs) b200aln_warm_device(d); });
         std::thread t1([&]() { load(1); });
         load(0);
         t1.join();
@@ -1432,10 +1420,16 @@ extern "C" int64_t b200aln_aln_core(const char *prefix, const char *fn_fa, const
             else if (max_len > cur_max) cur_max = max_len;
             if (n < batch_reads) { eof = true; break; }
         }
-        if (first_max_len < 0) { /* the setup thread sizes the contexts' buffers by the first batch */
-            std::lock_guard<std::mutex> lk(mu);
+        if (first_max_len < 0) {
+            /* the contexts' device buffers, sized by the first batch and allocated ahead on one thread per device while
+             * the setup thread is still reading the index files (a context takes its set with its first launch) */
             first_max_len = b.lens.empty() ? 0 : cur_max;
-            cv_first.notify_all();
+            if (first_max_len > 0 && !getenv("B200ALN_NO_PREALLOC"))
+                for (int d : devs)
+                    prealloc.emplace_back([&, d]() {
+                        b200aln_prealloc(d, n_slots, merge * batch_reads + 1, first_max_len);
+                        stamp("device buffers of the contexts allocated ahead, device", (long long)d);
+                    });
         }
         if ((int)b.lens.size() > cur_lo) {
             Launch L;
@@ -1466,9 +1460,11 @@ extern "C" int64_t b200aln_aln_core(const char *prefix, const char *fn_fa, const
     setup.join();
     cv_work.notify_all();
     for (auto &t : workers) t.join();
+    for (auto &t : prealloc) t.join();
     pool_maker.join();
     fclose(out);
     stamp("output closed, reads", (long long)tot_seqs);
+    if (getenv("B200ALN_FAST_EXIT")) for (auto &u : units) (void)u.release(); /* (unlocking 0.2 GB per unit takes 0.1 s) */
     units.clear();
     if (!getenv("B200ALN_FAST_EXIT")) /* (the command line: the process ends here, the driver's teardown frees the device) */
         for (size_t i = 0; i < devs.size(); ++i)

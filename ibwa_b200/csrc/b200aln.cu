@@ -644,6 +644,7 @@ struct b200aln_ctx {
     int lane_reads = 0;     /* fast pass: lanes = reads / lane_reads for batches too small to give the full grid that many (0: always the full grid) */
     int prep_rounds = 1;   /* pruned pops a lane may go through per warp iteration before the warp moves on */
     int reserve_reads = 0; /* size the per-batch buffers for at least this many reads */
+    bool scratch_checked = false; /* the pool of b200aln_prealloc has been asked once (with the first batch) */
     int count = 0;         /* 1: fast pass with the pop / sector counters (b200aln_stats_t pops, occ_lookups) */
     int pop_batch = 1;     /* memory pops are taken when this many lanes of a warp wait for one */
     int lut_k = 14;        /* levels of the path-k-mer interval table (0 = off) */
@@ -814,14 +815,16 @@ static void apply_l2_window(b200aln_ctx *c)
  * Allocating a context's per-batch buffers takes a few hundred milliseconds (the fast pass's arena alone is
  * 15 GB), and the first batch on a fresh context used to pay for it.  A driver that knows how many contexts it is
  * going to use can have the buffers allocated while it is still reading the index files: the sets wait in a
- * per-process pool, and b200aln_open / b200aln_clone hand one to every new context of that device. */
+ * per-process pool, and a context of that device takes one with its first batch. */
 struct ScratchSet {
     int device = 0;
     DevBuf ent, W, Q, recs, n_aln, over_slot, over_list, off64, n_amb, dkey, order_buf, lens, offs, codes, sai, packed;
     HostBuf h_out, h_nout;
 };
 static std::mutex g_scratch_mu;
+static std::condition_variable g_scratch_cv;
 static std::vector<ScratchSet *> g_scratch;
+static int g_scratch_pending[64]; /* per device: sets being allocated right now */
 
 extern "C" void b200aln_prealloc(int device, int n_contexts, int n_reads, int max_len)
 {
@@ -835,6 +838,10 @@ extern "C" void b200aln_prealloc(int device, int n_contexts, int n_reads, int ma
     for (int i = 0; i < n_contexts; ++i) {
         ScratchSet *s = new ScratchSet;
         s->device = device;
+        {
+            std::lock_guard<std::mutex> g(g_scratch_mu);
+            ++g_scratch_pending[device & 63];
+        }
         s->ent.need(lanes * defaults.arena_cap * sizeof(StackRec));
         s->W.need(n * 2 * strideW * 4 + 64);
         s->Q.need(n * 2 * strideQ * 2 + 64); /* the 16-bit records of the default options; grows for others */
@@ -855,22 +862,40 @@ extern "C" void b200aln_prealloc(int device, int n_contexts, int n_reads, int ma
         s->h_nout.need(n * 4);
         std::lock_guard<std::mutex> g(g_scratch_mu);
         g_scratch.push_back(s);
+        --g_scratch_pending[device & 63];
+        g_scratch_cv.notify_all();
     }
 }
 
+/* With a context's first batch: takes a set allocated ahead for its device, waiting for one that is being allocated
+ * right now (allocating a second one next to it would take as long and leave the first without an owner). */
 static void adopt_scratch(b200aln_ctx *c)
 {
+    if (c->scratch_checked) return;
+    c->scratch_checked = true;
     ScratchSet *s = nullptr;
     {
-        std::lock_guard<std::mutex> g(g_scratch_mu);
-        for (size_t i = 0; i < g_scratch.size(); ++i)
-            if (g_scratch[i]->device == c->device) {
-                s = g_scratch[i];
-                g_scratch.erase(g_scratch.begin() + (long)i);
-                break;
-            }
+        std::unique_lock<std::mutex> g(g_scratch_mu);
+        auto find = [&]() -> long {
+            for (size_t i = 0; i < g_scratch.size(); ++i)
+                if (g_scratch[i]->device == c->device) return (long)i;
+            return -1;
+        };
+        g_scratch_cv.wait(g, [&] { return find() >= 0 || g_scratch_pending[c->device & 63] == 0; });
+        const long i = find();
+        if (i >= 0) {
+            s = g_scratch[(size_t)i];
+            g_scratch.erase(g_scratch.begin() + i);
+        }
     }
-    if (!s) return;
+    if (!s || c->ent.p) { /* (a context that already has buffers keeps them; the set goes back) */
+        if (s) {
+            std::lock_guard<std::mutex> g(g_scratch_mu);
+            g_scratch.push_back(s);
+            g_scratch_cv.notify_all();
+        }
+        return;
+    }
     c->ent = s->ent; c->W = s->W; c->Q = s->Q; c->recs = s->recs; c->n_aln = s->n_aln; c->over_slot = s->over_slot;
     c->over_list = s->over_list; c->off64 = s->off64; c->n_amb = s->n_amb; c->dkey = s->dkey; c->order_buf = s->order_buf;
     c->lens = s->lens; c->offs = s->offs; c->codes = s->codes; c->sai = s->sai; c->packed = s->packed;
@@ -903,7 +928,6 @@ extern "C" b200aln_ctx *b200aln_open(const b200aln_bwt_view_t *bwt, const b200al
         }
     }
     make_streams(c);
-    adopt_scratch(c);
     for (int i = 0; i < 8; ++i) CK(cudaEventCreate(&c->ev[i]));
     for (int i = 0; i < 2; ++i) CK(cudaEventCreate(&c->tm[i]));
     if (!g_origin && getenv("B200ALN_TIMELINE")) {
@@ -979,7 +1003,6 @@ extern "C" b200aln_ctx *b200aln_clone(b200aln_ctx *p)
     c->pop_batch = p->pop_batch; c->count = p->count; c->reserve_reads = p->reserve_reads; c->prep_rounds = p->prep_rounds;
     c->prefetch_fast = p->prefetch_fast; c->prefetch_mid = p->prefetch_mid; c->order = p->order; c->search_block = p->search_block; c->q16 = p->q16; c->susp = p->susp; c->susp_min = p->susp_min; c->susp_calls = p->susp_calls; c->lane_reads = p->lane_reads;
     make_streams(c);
-    adopt_scratch(c);
     for (int i = 0; i < 8; ++i) CK(cudaEventCreate(&c->ev[i]));
     for (int i = 0; i < 2; ++i) CK(cudaEventCreate(&c->tm[i]));
     memset(&c->stats, 0, sizeof c->stats);
@@ -1182,6 +1205,7 @@ static void run_batch_device(b200aln_ctx *c, int n_reads, int max_len, const int
                              const uint8_t *d_codes, const b200aln_opt_t *opt, const std::vector<int> &md,
                              const Params &P, int64_t *total_out)
 {
+    adopt_scratch(c);
     uint64_t launches = 0;
     /* 16-bit width records when every field fits (aln_core.cuh: QF<16>) and the fast pass runs the kernel built for them */
     int md_max = 0;
@@ -1550,6 +1574,7 @@ struct ChunkOrder {
 static int64_t run_chunk_host(b200aln_ctx *s, int n, const int32_t *lens, const int64_t *offs, const uint8_t *codes,
                               const b200aln_opt_t *opt, const Params &P, const std::vector<int> &md, bool pinned_in)
 {
+    adopt_scratch(s);
     int max_len = 0;
     int64_t lo = INT64_MAX, hi = 0;
     for (int r = 0; r < n; ++r) {

@@ -137,9 +137,10 @@ void b200aln_unpin(void *p);
 /*
  * Allocates, ahead of time, the per-batch device and staging buffers of n_contexts contexts that are going to be
  * opened or cloned on `device`, sized for calls of up to n_reads reads of up to max_len bases with the default
- * knobs.  b200aln_open / b200aln_clone hand one such set to every new context of that device, so the first batch
- * on it does not wait for 15+ GB of allocations; a driver calls this on a thread of its own while it is still
- * reading the index files.  Sets that no context picks up stay allocated until the process ends.
+ * knobs.  A context of that device takes one such set with its first batch (waiting for one that is still being
+ * allocated), so that batch does not start with 15+ GB of allocations of its own; a driver calls this on a thread
+ * of its own while it is still reading the index files.  Sets that no context picks up stay allocated until the
+ * process ends.
  */
 void b200aln_prealloc(int device, int n_contexts, int n_reads, int max_len);
 

@@ -47,6 +47,7 @@ extern "C" void b200aln_warm_device(int device); /* b200aln.cu: creates the CUDA
 extern "C" int b200aln_pin(void *p, size_t bytes);
 extern "C" void b200aln_unpin(void *p);
 extern "C" void b200aln_prealloc(int device, int n_contexts, int n_reads, int max_len);
+extern "C" void b200aln_prealloc_release(int device);
 
 namespace {
 
@@ -1424,7 +1425,8 @@ extern "C" int64_t b200aln_aln_core(const char *prefix, const char *fn_fa, const
             /* the contexts' device buffers, sized by the first batch and allocated ahead on one thread per device while
              * the setup thread is still reading the index files (a context takes its set with its first launch) */
             first_max_len = b.lens.empty() ? 0 : cur_max;
-            if (first_max_len > 0 && !getenv("B200ALN_NO_PREALLOC"))
+            /* (an input that ends inside its first batch is one launch on one context: nothing to allocate ahead) */
+            if (first_max_len > 0 && !eof && !getenv("B200ALN_NO_PREALLOC"))
                 for (int d : devs)
                     prealloc.emplace_back([&, d]() {
                         b200aln_prealloc(d, n_slots, merge * batch_reads + 1, first_max_len);
@@ -1461,6 +1463,7 @@ extern "C" int64_t b200aln_aln_core(const char *prefix, const char *fn_fa, const
     cv_work.notify_all();
     for (auto &t : workers) t.join();
     for (auto &t : prealloc) t.join();
+    if (!getenv("B200ALN_FAST_EXIT")) for (int d : devs) b200aln_prealloc_release(d); /* sets no launch came to use */
     pool_maker.join();
     fclose(out);
     stamp("output closed, reads", (long long)tot_seqs);

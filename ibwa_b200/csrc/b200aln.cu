@@ -867,6 +867,29 @@ extern "C" void b200aln_prealloc(int device, int n_contexts, int n_reads, int ma
     }
 }
 
+extern "C" void b200aln_prealloc_release(int device)
+{ /* frees the sets of `device` that no context has taken (device < 0: of every device) */
+    std::vector<ScratchSet *> mine;
+    {
+        std::unique_lock<std::mutex> g(g_scratch_mu);
+        if (device >= 0) g_scratch_cv.wait(g, [&] { return g_scratch_pending[device & 63] == 0; });
+        for (size_t i = 0; i < g_scratch.size();)
+            if (device < 0 || g_scratch[i]->device == device) {
+                mine.push_back(g_scratch[i]);
+                g_scratch.erase(g_scratch.begin() + (long)i);
+            } else ++i;
+    }
+    for (ScratchSet *s : mine) {
+        if (cudaSetDevice(s->device) != cudaSuccess) { (void)cudaGetLastError(); continue; }
+        DevBuf *d[] = {&s->ent, &s->W, &s->Q, &s->recs, &s->n_aln, &s->over_slot, &s->over_list, &s->off64, &s->n_amb,
+                       &s->dkey, &s->order_buf, &s->lens, &s->offs, &s->codes, &s->sai, &s->packed};
+        for (DevBuf *b : d) b->release();
+        s->h_out.release();
+        s->h_nout.release();
+        delete s;
+    }
+}
+
 /* With a context's first batch: takes a set allocated ahead for its device, waiting for one that is being allocated
  * right now (allocating a second one next to it would take as long and leave the first without an owner). */
 static void adopt_scratch(b200aln_ctx *c)

@@ -49,7 +49,7 @@ class SeqLayout(ctypes.Structure):
 
 
 EXPORTS = ["b200aln_version", "b200aln_opt_init", "b200aln_cal_maxdiff", "b200aln_device_count", "b200aln_open",
-           "b200aln_open_prefix", "b200aln_clone", "b200aln_close", "b200aln_batch", "b200aln_batch_sai", "b200aln_pin", "b200aln_unpin", "b200aln_prealloc", "b200aln_batch_device", "b200aln_last_stats",
+           "b200aln_open_prefix", "b200aln_clone", "b200aln_close", "b200aln_batch", "b200aln_batch_sai", "b200aln_pin", "b200aln_unpin", "b200aln_prealloc", "b200aln_prealloc_release", "b200aln_batch_device", "b200aln_last_stats",
            "b200aln_set_int", "b200aln_timer_start", "b200aln_timer_stop", "b200aln_cal_sa_reg_gap", "b200aln_seq_layout", "b200aln_aln_core", "b200aln_aln_main", "b200aln_reader_open", "b200aln_reader_next", "b200aln_reader_close",
            "b200aln_sector_roofline", "b200aln_sa_load", "b200aln_bwt_sa", "b200aln_sa2seq", "b200aln_alngrp_merge", "b200aln_warm_device"]
 
@@ -86,6 +86,7 @@ def load_library():
     L.b200aln_pin.argtypes = [ctypes.c_void_p, ctypes.c_size_t]
     L.b200aln_unpin.argtypes = [ctypes.c_void_p]
     L.b200aln_prealloc.argtypes = [ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int]
+    L.b200aln_prealloc_release.argtypes = [ctypes.c_int]
     L.b200aln_batch_device.argtypes = [ctypes.c_void_p, ctypes.c_int, ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p,
                                        ctypes.c_void_p, ctypes.POINTER(GapOptC), ctypes.POINTER(ctypes.c_void_p),
                                        ctypes.POINTER(ctypes.c_void_p), ctypes.POINTER(ctypes.c_int64)]

@@ -139,10 +139,12 @@ void b200aln_unpin(void *p);
  * opened or cloned on `device`, sized for calls of up to n_reads reads of up to max_len bases with the default
  * knobs.  A context of that device takes one such set with its first batch (waiting for one that is still being
  * allocated), so that batch does not start with 15+ GB of allocations of its own; a driver calls this on a thread
- * of its own while it is still reading the index files.  Sets that no context picks up stay allocated until the
- * process ends.
+ * of its own while it is still reading the index files.  Sets that no context picks up stay allocated until
+ * b200aln_prealloc_release.
  */
 void b200aln_prealloc(int device, int n_contexts, int n_reads, int max_len);
+/* Frees the sets of `device` (< 0: of every device) that no context has taken. */
+void b200aln_prealloc_release(int device);
 
 /* Per-call counters of the last batch on this context (instrumentation). */
 typedef struct {

@@ -56,6 +56,7 @@ extern "C" void b200aln_warm_device(int) {}
 extern "C" int b200aln_pin(void *, size_t) { return -1; }
 extern "C" void b200aln_unpin(void *) {}
 extern "C" void b200aln_prealloc(int, int, int, int) {}
+extern "C" void b200aln_prealloc_release(int) {}
 
 extern "C" b200aln_ctx *b200aln_open(const b200aln_bwt_view_t *bwt, const b200aln_bwt_view_t *rbwt, int device)
 {

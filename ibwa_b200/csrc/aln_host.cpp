@@ -780,12 +780,45 @@ int trim_len(int trim_qual, int len, const char *qual)
     return best_l + 1;
 }
 
+/* The blocks of batch arrays that the driver has page-locked (ParseUnit::repin): a vector that grows gives its old
+ * block back while it is still locked, so the allocator unlocks it first (cudaHostUnregister before free). */
+struct PinRegistry {
+    std::mutex mu;
+    std::vector<const void *> blocks;
+    static PinRegistry &get()
+    {
+        static PinRegistry r;
+        return r;
+    }
+    void add(const void *p)
+    {
+        std::lock_guard<std::mutex> g(mu);
+        blocks.push_back(p);
+    }
+    bool take(const void *p)
+    { /* true: p was registered (and no longer is) */
+        std::lock_guard<std::mutex> g(mu);
+        for (size_t i = 0; i < blocks.size(); ++i)
+            if (blocks[i] == p) {
+                blocks[i] = blocks.back();
+                blocks.pop_back();
+                return true;
+            }
+        return false;
+    }
+};
+
 /* std::allocator that leaves trivially constructible elements uninitialised: resize() of a code buffer that
  * is about to be overwritten by the converters does not have to zero it first */
 template <class T> struct NoInitAlloc : std::allocator<T> {
     template <class U> struct rebind { typedef NoInitAlloc<U> other; };
     NoInitAlloc() = default;
     template <class U> NoInitAlloc(const NoInitAlloc<U> &) {}
+    void deallocate(T *p, size_t n)
+    {
+        if (p && PinRegistry::get().take(p)) b200aln_unpin(p);
+        std::allocator<T>::deallocate(p, n);
+    }
     template <class U> void construct(U *p) noexcept { ::new ((void *)p) U; }
     template <class U, class... A> void construct(U *p, A &&...a) { ::new ((void *)p) U(std::forward<A>(a)...); }
 };
@@ -1145,19 +1178,18 @@ struct ParseUnit {
         const size_t n[3] = {b.lens.capacity() * 4, b.offs.capacity() * 8, b.codes.capacity()};
         for (int i = 0; i < 3; ++i) {
             if (p[i] == pin_p[i] && n[i] == pin_bytes[i]) continue;
-            if (pin_p[i]) b200aln_unpin(const_cast<void *>(pin_p[i]));
+            /* (a block the vector has given back was unlocked by the allocator: PinRegistry) */
+            if (pin_p[i] && PinRegistry::get().take(pin_p[i])) b200aln_unpin(const_cast<void *>(pin_p[i]));
             pin_p[i] = nullptr;
             pin_bytes[i] = 0;
             if (pin && p[i] && n[i] && b200aln_pin(const_cast<void *>(p[i]), n[i]) == 0) {
                 pin_p[i] = p[i];
                 pin_bytes[i] = n[i];
+                PinRegistry::get().add(p[i]);
             }
         }
     }
-    ~ParseUnit()
-    {
-        for (int i = 0; i < 3; ++i) if (pin_p[i]) b200aln_unpin(const_cast<void *>(pin_p[i]));
-    }
+    /* (the vectors' allocator unlocks the blocks when they are freed) */
 };
 
 /* One launch: reads [lo, hi) of a unit — whole reference batches that agree on the batch-level max_gapo clamp. */

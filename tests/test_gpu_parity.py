@@ -327,6 +327,33 @@ def test_cli_merges_reference_batches_only_when_allowed(rand_index, tmp_path):
         assert len(got) == len(want) and got[:52] == want[:52] and got[56:] == want[56:], env
 
 
+def test_cli_parse_arrays_grow_while_page_locked(rand_index, tmp_path):
+    """150 bp reads outgrow the driver's parse arrays (reserved for 104 bases per read), so the vectors move while
+    their old blocks are page-locked: the allocator unlocks them first.  Small reference batches (the test hook
+    B200ALN_BATCH_READS; every batch has the same longest read, so the clamp is the same) make units of up to eight
+    batches that all have to grow; the output equals one batch through the operator."""
+    g, bwt, rbwt = rand_index
+    prefix = str(tmp_path / "grow")
+    bwt_dump_bwt(prefix + ".bwt", bwt)
+    bwt_dump_bwt(prefix + ".rbwt", rbwt)
+    n, length = 120_000, 150
+    reads = synth.simulate_reads_fast(g, n, length, 13)
+    fq = str(tmp_path / "long.fq")
+    synth.write_fastq(fq, reads)
+    opt = gap_init_opt()
+    with engine.Engine(bwt, rbwt, 0) as e:
+        n_aln, rec = e.cal_sa_reg_gap(np.full(n, length, np.int32), np.arange(n, dtype=np.int64) * length, reads.reshape(-1), opt)
+    buf = io.BytesIO()
+    sai.write_header(buf, opt)
+    sai.write_batch(buf, n_aln, rec)
+    want = buf.getvalue()
+    exe = os.path.join(ROOT, "ibwa_b200", "b200aln")
+    for env in ({"B200ALN_BATCH_READS": "5000"}, {"B200ALN_BATCH_READS": "7000", "B200ALN_INFLIGHT": "2"}):
+        out = str(tmp_path / "gpu.sai")
+        subprocess.check_call([exe, "aln", "-f", out, prefix, fq], stderr=subprocess.DEVNULL, env=dict(os.environ, **env))
+        assert open(out, "rb").read() == want, env
+
+
 def _ref_index(tmp_path, genome, name, contig_len=None):
     """Index a synthetic genome with the unmodified reference (`ibwa index -a is`)."""
     fa = str(tmp_path / f"{name}.fa")

@@ -205,3 +205,48 @@ def test_parallel_scan_joins_only_matching_pieces(tmp_path):
     assert len(data) > (4 << 20)
     assert both(p) == 60 * 403
     assert both(p, trim_qual=20) == 60 * 403
+
+
+def _random_character_fastq(path, seed):
+    """4-line records whose sequence and quality lines hold every byte the fast path has to classify: letters of both
+    cases, '-', '.', digits, DEL, bytes >= 128, and now and then one of the characters the fast path must refuse
+    ('>', '+', '@', a blank); lengths around the 32-byte vector width and the 35-base trimming floor"""
+    rng = np.random.default_rng(seed)
+    ok = np.array([c for c in range(33, 127) if c not in b">+@"], dtype=np.uint8)
+    common = np.frombuffer(b"ACGTacgtNn-.", dtype=np.uint8)
+    out = []
+    for i in range(6000):
+        L = int(rng.choice([1, 2, 15, 31, 32, 33, 34, 35, 36, 63, 64, 65, 95, 96, 97, 100, 127, 128, 129, 250]))
+        s = np.where(rng.random(L) < 0.8, rng.choice(common, L), rng.choice(ok, L)).astype(np.uint8)
+        q = rng.integers(33, 128, size=L).astype(np.uint8)            # 127 is a legal quality character (kseq.h:185)
+        k = rng.random()
+        if k < 0.02:
+            s[int(rng.integers(0, L))] = int(rng.choice(np.frombuffer(b">+@ \t", dtype=np.uint8)))
+        elif k < 0.04:
+            s[int(rng.integers(0, L))] = int(rng.choice([127, 128, 200, 255, 1, 31]))
+        elif k < 0.06:
+            q[int(rng.integers(0, L))] = int(rng.choice([32, 128, 255, 10 if L > 1 else 32]))
+        out.append(b"@r%d x\n" % i + s.tobytes() + b"\n+\n" + q.tobytes() + b"\n")
+    with open(path, "wb") as f:
+        f.write(b"".join(out))
+
+
+@pytest.mark.parametrize("simd", [True, False], ids=["avx2", "table"])
+def test_every_character_class_vectorised_and_not(tmp_path, simd):
+    """the vectorised conversion of the fast path (nibble table + class checks) and the table version give what the
+    reference's parser gives, on every byte value and on lengths around the vector width; each in a process of its
+    own, since the choice is made once per process (B200ALN_NO_SIMD)"""
+    import subprocess
+    import sys
+    p = str(tmp_path / "chars.fq")
+    _random_character_fastq(p, 5)
+    code = ("import sys; sys.path.insert(0, %r); sys.path.insert(0, %r); import test_reader as t; "
+            "print(t.both(%r), t.both(%r, trim_qual=25), t.both(%r, mode=3 | 0x200, trim_qual=10))"
+            % (os.path.dirname(os.path.dirname(os.path.abspath(__file__))), os.path.dirname(os.path.abspath(__file__)), p, p, p))
+    env = dict(os.environ, B200ALN_PAR_SCAN_MIN="4096")
+    if not simd:
+        env["B200ALN_NO_SIMD"] = "1"
+    r = subprocess.run([sys.executable, "-c", code], env=env, stdout=subprocess.PIPE, stderr=subprocess.PIPE)
+    assert r.returncode == 0, r.stderr.decode()[-2000:]
+    counts = r.stdout.decode().split()
+    assert len(counts) == 3 and int(counts[0]) > 1000

@@ -572,7 +572,7 @@ def main():
     # ---- our arm ------------------------------------------------------------
     if args.in_flight is None:
         # config 3: its re-run arenas are large; config 5 runs two indexes, each with its own contexts
-        args.in_flight = 3 if n_rank >= 8_000_000 or args.config == 3 else 4 if n_rank >= 4_000_000 else 6 if cfg["alt"] or n_rank >= 2_000_000 else 8
+        args.in_flight = 3 if n_rank >= 8_000_000 or args.config == 3 else 4 if n_rank >= 4_000_000 else 8 if not cfg["alt"] and 1_000_000 <= n_rank < 2_000_000 else 6
     K = max(1, args.in_flight)
     eng = engine.Engine(bwt, rbwt, local_rank)
     knobs = [kv.split("=") for kv in args.set]

@@ -41,6 +41,7 @@
 
 #include "../../include/b200aln.h"
 #include "host_params.h"
+#include "fast_inflate.h"
 
 struct b200aln_reader;
 extern "C" void b200aln_warm_device(int device); /* b200aln.cu: creates the CUDA context */
@@ -237,11 +238,27 @@ class InflateSource {
             else if (fd_ >= 0) { close(fd_); fd_ = -1; }
         }
         if (!bgzf_) {
-            gz_ = is_stdin ? gzdopen(fileno(stdin), "r") : gzopen(fn, "r");
-            if (!gz_) b2host::fatal("b200aln_aln_core", (std::string("fail to open file '") + fn + "'.").c_str());
-            gzbuffer(gz_, 1 << 20);
-            for (auto &b : ring_) b.data.resize(kChunk);
-            th_ = std::thread([this] { producer(); });
+            fn_ = fn;
+            /* a gzip file on disk is mapped and decoded by fast_inflate.h; everything else (stdin, pipes, plain data)
+             * and anything that decoder does not take goes through zlib */
+            if (!is_stdin && !getenv("B200ALN_NO_FAST_INFLATE")) {
+                const int fd = open(fn, O_RDONLY);
+                struct stat st;
+                unsigned char h[2] = {0, 0};
+                if (fd >= 0 && fstat(fd, &st) == 0 && S_ISREG(st.st_mode) && st.st_size > 18 && pread(fd, h, 2, 0) == 2 &&
+                    h[0] == 0x1f && h[1] == 0x8b) {
+                    void *m = mmap(nullptr, (size_t)st.st_size, PROT_READ, MAP_PRIVATE, fd, 0);
+                    if (m != MAP_FAILED) {
+                        madvise(m, (size_t)st.st_size, MADV_SEQUENTIAL);
+                        zmap_ = (const unsigned char *)m;
+                        zmap_len_ = (size_t)st.st_size;
+                    }
+                }
+                if (fd >= 0) close(fd);
+            }
+            if (!zmap_) open_zlib(is_stdin);
+            for (auto &b : ring_) b.data.resize(kHist + kChunk);
+            th_ = std::thread([this] { if (zmap_) producer_fast(); else producer(); });
         }
     }
     ~InflateSource()
@@ -256,6 +273,7 @@ class InflateSource {
         }
         if (gz_) gzclose(gz_);
         if (fd_ >= 0) close(fd_);
+        if (zmap_) munmap(const_cast<unsigned char *>(zmap_), zmap_len_);
     }
     /* like gzread: the number of bytes delivered, less than n only at the end of the stream */
     int read(void *dst, unsigned n)
@@ -296,11 +314,114 @@ class InflateSource {
   private:
     /* ---- zlib stream, one helper thread ahead ---- */
     static const size_t kChunk = (size_t)16 << 20;
+    static const size_t kHist = 32768; /* fast decoder: the 32 KB before a chunk's data, for matches that reach back */
     static const int kRing = 3;
     struct Chunk { std::vector<unsigned char> data; size_t len = 0, pos = 0; bool full = false; };
-    void producer()
+    void open_zlib(bool is_stdin)
     {
-        for (uint64_t i = 0;; ++i) {
+        gz_ = is_stdin ? gzdopen(fileno(stdin), "r") : gzopen(fn_.c_str(), "r");
+        if (!gz_) b2host::fatal("b200aln_aln_core", (std::string("fail to open file '") + fn_ + "'.").c_str());
+        gzbuffer(gz_, 1 << 20);
+    }
+    /* waits for ring slot i to be free; false when the reader is gone */
+    bool claim(uint64_t i)
+    {
+        Chunk &c = ring_[i % kRing];
+        std::unique_lock<std::mutex> g(m_);
+        cv_.wait(g, [&] { return !c.full || stop_; });
+        return !stop_;
+    }
+    void publish(uint64_t i, size_t pos, size_t len)
+    {
+        Chunk &c = ring_[i % kRing];
+        c.pos = pos;
+        c.len = len;
+        {
+            std::lock_guard<std::mutex> g(m_);
+            c.full = true;
+        }
+        cv_.notify_all();
+    }
+    /* The mapped gzip file through fast_inflate.h, member by member (RFC 1952), chunk by chunk; the CRC and the
+     * length of every member are checked like gzread does.  Whatever this path does not take for granted — a member
+     * the decoder refuses, a check that fails, bytes after a member that are not another member — is left to zlib:
+     * the stream is opened with gzopen, wound forward to the byte this path has delivered last, and goes on there,
+     * so the bytes and the end of the stream are what gzread gives. */
+    void producer_fast()
+    {
+        std::unique_ptr<fastinflate::Decoder> dec(new fastinflate::Decoder);
+        size_t at = 0;          /* in the compressed file */
+        uint64_t delivered = 0; /* plain bytes published so far */
+        uint64_t i = 0;
+        bool handed_over = false;
+        while (at < zmap_len_ && !handed_over) {
+            const size_t hl = fastinflate::gzip_header_len(zmap_ + at, zmap_len_ - at);
+            if (!hl) { handed_over = true; break; }
+            dec->start(zmap_ + at + hl, zmap_len_ - at - hl);
+            /* the member's CRC: every chunk's on a thread of its own while the next chunk is decoded, put together with
+             * crc32_combine; at most two are outstanding, so a ring slot is never reused under a running one */
+            uLong crc = crc32(0L, Z_NULL, 0);
+            std::deque<std::pair<std::future<uLong>, size_t>> crcs;
+            auto settle = [&](size_t keep) {
+                while (crcs.size() > keep) {
+                    crc = crc32_combine(crc, crcs.front().first.get(), (z_off_t)crcs.front().second);
+                    crcs.pop_front();
+                }
+            };
+            uint64_t member_bytes = 0;
+            size_t hist = 0; /* bytes of this member's output in front of the current chunk's data */
+            const unsigned char *prev_tail = nullptr;
+            for (;;) {
+                settle(1);
+                if (!claim(i)) { settle(0); return; }
+                Chunk &c = ring_[i % kRing];
+                unsigned char *base = c.data.data() + kHist;
+                if (hist) memcpy(base - hist, prev_tail - hist, hist);
+                uint8_t *out = base;
+                const fastinflate::Status st = dec->run(base - hist, &out, base + kChunk);
+                if (st == fastinflate::FI_ERROR) { settle(0); handed_over = true; break; }
+                const size_t got = (size_t)(out - base);
+                if (got)
+                    crcs.emplace_back(std::async(std::launch::async, [base, got] { return crc32(crc32(0L, Z_NULL, 0), base, (uInt)got); }), got);
+                member_bytes += got;
+                if (st == fastinflate::FI_DONE) {
+                    settle(0);
+                    const unsigned char *t = dec->in_pos();
+                    if (t + 8 > zmap_ + zmap_len_) { handed_over = true; break; }
+                    const uint32_t want_crc = t[0] | t[1] << 8 | t[2] << 16 | (uint32_t)t[3] << 24;
+                    const uint32_t want_len = t[4] | t[5] << 8 | t[6] << 16 | (uint32_t)t[7] << 24;
+                    if (want_crc != (uint32_t)crc || want_len != (uint32_t)member_bytes) { handed_over = true; break; }
+                    at = (size_t)(t + 8 - zmap_);
+                }
+                if (got) {
+                    delivered += got;
+                    publish(i, kHist, kHist + got);
+                    ++i;
+                }
+                if (st == fastinflate::FI_DONE) break;
+                hist = got < kHist ? std::min(kHist, hist + got) : kHist;
+                if (got < kHist && hist > got) { /* (a short chunk: part of the history is the history of before) */
+                    settle(0);
+                    handed_over = true; /* does not happen with 16 MB chunks; leave it to zlib rather than stitch */
+                    break;
+                }
+                prev_tail = base + got;
+            }
+        }
+        if (handed_over) {
+            open_zlib(false);
+            if (delivered && gzseek(gz_, (z_off_t)delivered, SEEK_SET) < 0) { /* zlib cannot get there either: end of stream */
+                if (claim(i)) publish(i, 0, 0);
+                return;
+            }
+            producer(i);
+            return;
+        }
+        if (claim(i)) publish(i, 0, 0); /* end of stream */
+    }
+    void producer(uint64_t first = 0)
+    {
+        for (uint64_t i = first;; ++i) {
             Chunk &c = ring_[i % kRing];
             {
                 std::unique_lock<std::mutex> g(m_);
@@ -370,11 +491,24 @@ class InflateSource {
         ParsePool &pool = ParsePool::get();
         const unsigned nw = pool.size();
         std::vector<int> bad(nw, 0);
+        const bool fast = getenv("B200ALN_NO_FAST_INFLATE") == nullptr;
         pool.run([&](unsigned t) {
             z_stream zs;
+            std::unique_ptr<fastinflate::Decoder> dec(fast ? new fastinflate::Decoder : nullptr);
+            std::vector<unsigned char> scratch(fast ? 65536 + 1024 : 0); /* (the decoder keeps 320 bytes of room) */
             for (size_t i = t; i < blocks.size(); i += nw) {
                 const Block &b = blocks[i];
                 if (b.out_len == 0) continue;
+                if (fast && b.out_len <= 65536) { /* fast_inflate.h first; what it refuses goes to zlib below */
+                    dec->start(cbuf_.data() + b.in_off, b.in_len + 8); /* (the 8-byte trailer is slack for the bit reader) */
+                    uint8_t *p = scratch.data();
+                    if (dec->run(scratch.data(), &p, scratch.data() + scratch.size()) == fastinflate::FI_DONE &&
+                        (size_t)(p - scratch.data()) == b.out_len &&
+                        crc32(crc32(0L, Z_NULL, 0), scratch.data(), (uInt)b.out_len) == b.crc) {
+                        memcpy(out_.data() + b.out_off, scratch.data(), b.out_len);
+                        continue;
+                    }
+                }
                 memset(&zs, 0, sizeof zs);
                 if (inflateInit2(&zs, -15) != Z_OK) { bad[t] = 1; return; }
                 zs.next_in = cbuf_.data() + b.in_off;
@@ -400,6 +534,9 @@ class InflateSource {
     std::vector<unsigned char> cbuf_, out_;
     size_t out_pos_ = 0;
     gzFile gz_ = nullptr;
+    std::string fn_;
+    const unsigned char *zmap_ = nullptr; /* fast path: the compressed file */
+    size_t zmap_len_ = 0;
     std::thread th_;
     std::mutex m_;
     std::condition_variable cv_;

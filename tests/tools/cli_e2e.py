@@ -72,6 +72,33 @@ def main():
         dt = time.perf_counter() - t0
         print(f"reader alone ({tot} reads, {cores} cores): {dt:.2f} s = {tot / dt / 1e6:.2f} M reads/s", flush=True)
 
+    # gzip input: the first 2 M reads, compressed like most FASTQ files are (gzip -6); reader alone with the decoder of
+    # this library and with zlib, then the whole command line
+    n_gz = min(n, 2_000_000)
+    fq_gz = "/tmp/cli_e2e_gz.fq.gz"
+    bench.write_fastq("/tmp/cli_e2e_gz.fq", reads[:n_gz])
+    subprocess.run("gzip -6 -c /tmp/cli_e2e_gz.fq > " + fq_gz, shell=True, check=True)
+    os.sync()
+    for env_name, tag in ((None, "fast_inflate.h"), ("B200ALN_NO_FAST_INFLATE", "zlib")):
+        if env_name:
+            os.environ[env_name] = "1"
+        t0 = time.perf_counter()
+        r = L.b200aln_reader_open(fq_gz.encode(), 0)
+        tot = 0
+        while True:
+            k = L.b200aln_reader_next(r, 0x40000, 0, 0, ctypes.byref(pl), ctypes.byref(po), ctypes.byref(pc), ctypes.byref(nb))
+            if k == 0:
+                break
+            tot += k
+        L.b200aln_reader_close(r)
+        dt = time.perf_counter() - t0
+        if env_name:
+            del os.environ[env_name]
+        print(f"reader alone, gzip input ({tot} reads, {tag}): {dt:.2f} s = {tot / dt / 1e6:.2f} M reads/s", flush=True)
+    dt, t_load, t_done, t_parsed = run_cli(fq_gz, {})
+    print(f"b200aln aln (gzip input, {n_gz} reads): {dt:.2f} s wall incl. index load ({t_load:.2f} s); parse + search + write "
+          f"{t_done - t_load:.2f} s = {n_gz / (t_done - t_load) / 1e6:.2f} M reads/s", flush=True)
+
     for label, path, cnt in (("full", fq, n), ("ref-sized", fq_ref, n_ref)):
         full_md5 = set()
         for env in ({}, {}, {"B200ALN_NO_PREALLOC": "1"}, {"B200ALN_MERGE": "16"}, {"B200ALN_INFLIGHT": "3"},

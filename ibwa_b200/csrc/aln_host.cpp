@@ -1351,8 +1351,8 @@ extern "C" int64_t b200aln_aln_core(const char *prefix, const char *fn_fa, const
         fprintf(stderr, "[trace] %8.3f s  %s %lld\n", (t.tv_sec - tr0.tv_sec) + 1e-9 * (t.tv_nsec - tr0.tv_nsec), what, n);
     };
     b200aln_reader rd(fn_fa, opt->mode);
-    /* devices: one, or all visible; per device two contexts (index shared) so that two batches are in
-     * flight: the copies and host work of one overlap the kernels of the other */
+    /* devices: one, or all visible; per device n_slots contexts that share the device index (b200aln_clone), one
+     * launch in flight on each */
     std::vector<int> devs;
     if (device >= 0) devs.push_back(device);
     else for (int d = 0; d < b200aln_device_count(); ++d) devs.push_back(d);

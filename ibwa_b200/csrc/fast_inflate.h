@@ -30,7 +30,8 @@ enum { LITLEN_BITS = 11, OFF_BITS = 8, MAX_CODE_LEN = 15, N_LITLEN = 288, N_OFF 
  * bits 4-7 kind, bits 8-12 extra bits (or second-level index bits), bits 16-31 value (literal, length base,
  * distance base, or start of the second-level table) */
 enum { K_LITERAL = 1, K_LENGTH = 2, K_EOB = 3, K_SUB = 4, K_INVALID = 5, K_DIST = 6,
-       K_LIT2 = 7 /* two literals whose codes fit the primary index together: value = first | second << 8 */ };
+       K_LIT2 = 7, K_LIT3 = 8 /* two / three literals whose codes fit the primary index together */ };
+/* literal entries (K_LITERAL, K_LIT2, K_LIT3) hold their bytes in bits 8-15, 16-23, 24-31 instead */
 
 static inline uint32_t entry(unsigned len, unsigned kind, unsigned extra, unsigned value)
 {
@@ -128,7 +129,7 @@ struct Decoder {
             if (is_dist) {
                 if (s >= 30) e = entry((unsigned)l, K_INVALID, 0, 0);
                 else e = entry(0, K_DIST, dist_extra[s], dist_base[s]);
-            } else if (s < 256) e = entry(0, K_LITERAL, 0, (unsigned)s);
+            } else if (s < 256) e = (uint32_t)K_LITERAL << 4 | (uint32_t)s << 8;
             else if (s == 256) e = entry(0, K_EOB, 0, 0);
             else if (s < 286) e = entry(0, K_LENGTH, len_extra[s - 257], len_base[s - 257]);
             else e = entry(0, K_INVALID, 0, 0);
@@ -157,8 +158,14 @@ struct Decoder {
                 if ((a >> 4 & 15u) != K_LITERAL) continue;
                 const unsigned la = a & 15u;
                 const uint32_t b = one[i >> la];
-                if ((b >> 4 & 15u) != K_LITERAL || la + (b & 15u) > (unsigned)primary_bits) continue;
-                tab[i] = entry(la + (b & 15u), K_LIT2, 0, (a >> 16) | (b >> 16) << 8);
+                const unsigned lb = b & 15u;
+                if ((b >> 4 & 15u) != K_LITERAL || la + lb > (unsigned)primary_bits) continue;
+                const uint32_t c = one[i >> (la + lb)];
+                const unsigned lc = c & 15u;
+                if ((c >> 4 & 15u) == K_LITERAL && la + lb + lc <= (unsigned)primary_bits)
+                    tab[i] = (la + lb + lc) | (uint32_t)K_LIT3 << 4 | (a >> 8 & 255u) << 8 | (b >> 8 & 255u) << 16 | (c >> 8 & 255u) << 24;
+                else
+                    tab[i] = (la + lb) | (uint32_t)K_LIT2 << 4 | (a >> 8 & 255u) << 8 | (b >> 8 & 255u) << 16;
             }
         }
         return true;
@@ -348,20 +355,23 @@ struct Decoder {
                 }
                 FI_DROP(e & 15u);
                 const unsigned kind = e >> 4 & 15u;
-                if (kind == K_LITERAL || kind == K_LIT2) {
-                    out[0] = (uint8_t)(e >> 16);
-                    out[1] = (uint8_t)(e >> 24); /* (room is kept: the byte is overwritten when it is not a literal) */
-                    out += 1 + (kind == K_LIT2);
-                    /* more literals from the same refill: a primary-table entry takes at most 11 bits, and 40 bits
-                     * are kept for whatever comes next */
+                if (kind == K_LITERAL || kind >= K_LIT2) {
+                    /* one to three literals: all three bytes are stored (room is kept), the pointer moves by the count */
+                    out[0] = (uint8_t)(e >> 8);
+                    out[1] = (uint8_t)(e >> 16);
+                    out[2] = (uint8_t)(e >> 24);
+                    out += kind == K_LITERAL ? 1 : (int)kind - (K_LIT2 - 2);
+                    /* more literals from the same refill: a primary-table entry takes at most LITLEN_BITS bits, and 40
+                     * bits are kept for whatever comes next */
                     while (bl >= 40) {
                         const uint32_t e2 = lt[bb & ((1u << LITLEN_BITS) - 1u)];
                         const unsigned k2 = e2 >> 4 & 15u;
-                        if (k2 != K_LITERAL && k2 != K_LIT2) break;
+                        if (k2 != K_LITERAL && k2 < K_LIT2) break;
                         FI_DROP(e2 & 15u);
-                        out[0] = (uint8_t)(e2 >> 16);
-                        out[1] = (uint8_t)(e2 >> 24);
-                        out += 1 + (k2 == K_LIT2);
+                        out[0] = (uint8_t)(e2 >> 8);
+                        out[1] = (uint8_t)(e2 >> 16);
+                        out[2] = (uint8_t)(e2 >> 24);
+                        out += k2 == K_LITERAL ? 1 : (int)k2 - (K_LIT2 - 2);
                     }
                     if (bl < 0) FI_LEAVE(FI_ERROR);
                     continue;

@@ -355,6 +355,42 @@ struct Decoder {
                 }
                 FI_DROP(e & 15u);
                 const unsigned kind = e >> 4 & 15u;
+                if (__builtin_expect(kind == K_LENGTH, 1)) {
+                    const unsigned lx = e >> 8 & 31u;
+                    const unsigned length = (e >> 16) + (unsigned)(bb & ((1u << lx) - 1u));
+                    FI_DROP(lx);
+                    if (__builtin_expect(bl < 28, 0)) FI_REFILL(); /* 15 bits of distance code + 13 extra */
+                    uint32_t d = dt[bb & ((1u << OFF_BITS) - 1u)];
+                    if (__builtin_expect((d >> 4 & 15u) == K_SUB, 0)) {
+                        const unsigned sb = d >> 8 & 31u;
+                        d = dt[(d >> 16) + (unsigned)(bb >> OFF_BITS & ((1u << sb) - 1u))];
+                        FI_DROP(OFF_BITS);
+                    }
+                    FI_DROP(d & 15u);
+                    if (__builtin_expect((d >> 4 & 15u) != K_DIST, 0)) FI_LEAVE(FI_ERROR);
+                    const unsigned dx = d >> 8 & 31u;
+                    const unsigned distance = (d >> 16) + (unsigned)(bb & ((1u << dx) - 1u));
+                    FI_DROP(dx);
+                    if (__builtin_expect(bl < 0 || distance > (size_t)(out - out_base), 0)) FI_LEAVE(FI_ERROR);
+                    const uint8_t *src = out - distance;
+                    uint8_t *dst = out;
+                    out += length;
+                    if (__builtin_expect(distance >= 16, 1)) { /* sixteen bytes at a time; writes up to 15 bytes past the match (room is kept) */
+                        memcpy(dst, src, 16);
+                        if (__builtin_expect(length > 16, 0)) {
+                            do {
+                                dst += 16;
+                                src += 16;
+                                memcpy(dst, src, 16);
+                            } while (dst + 16 < out);
+                        }
+                    } else if (distance == 1) {
+                        memset(dst, *src, length);
+                    } else {
+                        do *dst++ = *src++; while (dst < out);
+                    }
+                    continue;
+                }
                 if (kind == K_LITERAL || kind >= K_LIT2) {
                     /* one to three literals: all three bytes are stored (room is kept), the pointer moves by the count */
                     out[0] = (uint8_t)(e >> 8);
@@ -380,37 +416,7 @@ struct Decoder {
                     if (bl < 0) FI_LEAVE(FI_ERROR);
                     break;
                 }
-                if (kind != K_LENGTH) FI_LEAVE(FI_ERROR);
-                const unsigned lx = e >> 8 & 31u;
-                const unsigned length = (e >> 16) + (unsigned)(bb & ((1u << lx) - 1u));
-                FI_DROP(lx);
-                if (bl < 28) FI_REFILL(); /* 15 bits of distance code + 13 extra */
-                uint32_t d = dt[bb & ((1u << OFF_BITS) - 1u)];
-                if ((d >> 4 & 15u) == K_SUB) {
-                    const unsigned sb = d >> 8 & 31u;
-                    d = dt[(d >> 16) + (unsigned)(bb >> OFF_BITS & ((1u << sb) - 1u))];
-                    FI_DROP(OFF_BITS);
-                }
-                FI_DROP(d & 15u);
-                if ((d >> 4 & 15u) != K_DIST) FI_LEAVE(FI_ERROR);
-                const unsigned dx = d >> 8 & 31u;
-                const unsigned distance = (d >> 16) + (unsigned)(bb & ((1u << dx) - 1u));
-                FI_DROP(dx);
-                if (bl < 0 || distance > (size_t)(out - out_base)) FI_LEAVE(FI_ERROR);
-                const uint8_t *src = out - distance;
-                uint8_t *dst = out;
-                out += length;
-                if (distance >= 16) { /* sixteen bytes at a time; writes up to 15 bytes past the match (room is kept) */
-                    do {
-                        memcpy(dst, src, 16);
-                        dst += 16;
-                        src += 16;
-                    } while (dst < out);
-                } else if (distance == 1) {
-                    memset(dst, *src, length);
-                } else {
-                    do *dst++ = *src++; while (dst < out);
-                }
+                FI_LEAVE(FI_ERROR);
             }
             in = ip;
             bitbuf = bb;

@@ -237,6 +237,7 @@ class InflateSource {
                 bgzf_ = true;
             else if (fd_ >= 0) { close(fd_); fd_ = -1; }
         }
+        if (bgzf_) th_ = std::thread([this] { producer_bgzf(); });
         if (!bgzf_) {
             fn_ = fn;
             /* a gzip file on disk is mapped and decoded by fast_inflate.h; everything else (stdin, pipes, plain data)
@@ -281,13 +282,7 @@ class InflateSource {
         unsigned char *d = (unsigned char *)dst;
         unsigned got = 0;
         while (got < n) {
-            if (bgzf_) {
-                if (out_pos_ == out_.size() && !refill_bgzf()) break;
-                const size_t k = std::min<size_t>(n - got, out_.size() - out_pos_);
-                memcpy(d + got, out_.data() + out_pos_, k);
-                out_pos_ += k;
-                got += (unsigned)k;
-            } else {
+            {
                 Chunk &c = ring_[rd_idx_ % kRing];
                 {
                     std::unique_lock<std::mutex> g(m_);
@@ -439,19 +434,30 @@ class InflateSource {
             if (c.len == 0) return; /* end of stream or error: the zero-length chunk tells the reader */
         }
     }
-    /* ---- BGZF, block-parallel ---- */
+    /* ---- BGZF, block-parallel, one window ahead of the parser ---- */
     struct Block { size_t in_off, in_len, out_off, out_len; uint32_t crc; };
-    bool refill_bgzf()
+    void producer_bgzf()
     {
-        if (bgzf_eof_) return false;
+        for (uint64_t i = 0;; ++i) {
+            if (!claim(i)) return;
+            size_t n = 0;
+            while (!bgzf_eof_ && n == 0) n = fill_bgzf(ring_[i % kRing].data); /* (a window of empty blocks — the EOF marker: look further) */
+            publish(i, 0, n);
+            if (n == 0) return;
+        }
+    }
+    /* the next window of whole blocks, inflated into `out` by threads of this source's own (the parse pool is busy
+     * with the window before); returns the plain bytes, 0 with bgzf_eof_ at the end of the file */
+    size_t fill_bgzf(std::vector<unsigned char> &out)
+    {
         static const size_t kWindow = [] { /* compressed bytes per round (B200ALN_BGZF_WINDOW: tests shrink it) */
             const char *e = getenv("B200ALN_BGZF_WINDOW");
             const long v = e ? atol(e) : 0;
-            return v >= 1024 ? (size_t)v : (size_t)24 << 20;
+            return v >= 1024 ? (size_t)v : (size_t)8 << 20;
         }();
         cbuf_.resize(kWindow + 65536 + 64);
         const ssize_t have = pread(fd_, cbuf_.data(), cbuf_.size(), (off_t)file_pos_);
-        if (have <= 0) { bgzf_eof_ = true; return false; }
+        if (have <= 0) { bgzf_eof_ = true; return 0; }
         std::vector<Block> blocks;
         size_t at = 0, out_total = 0;
         while (at + 18 <= (size_t)have && at < kWindow) {
@@ -483,16 +489,15 @@ class InflateSource {
         if (blocks.empty()) {
             if ((size_t)have >= 18) b2host::fatal("b200aln_reader", "truncated BGZF block.");
             bgzf_eof_ = true;
-            return false;
+            return 0;
         }
         file_pos_ += at;
-        out_.resize(out_total);
-        out_pos_ = 0;
-        ParsePool &pool = ParsePool::get();
-        const unsigned nw = pool.size();
+        if (out.size() < out_total) out.resize(out_total);
+        const unsigned hw = std::thread::hardware_concurrency();
+        const unsigned nw = std::max(1u, std::min<unsigned>({8u, hw ? hw / 2 : 1u, (unsigned)blocks.size()}));
         std::vector<int> bad(nw, 0);
         const bool fast = getenv("B200ALN_NO_FAST_INFLATE") == nullptr;
-        pool.run([&](unsigned t) {
+        auto work = [&](unsigned t) {
             z_stream zs;
             std::unique_ptr<fastinflate::Decoder> dec(fast ? new fastinflate::Decoder : nullptr);
             std::vector<unsigned char> scratch(fast ? 65536 + 1024 : 0); /* (the decoder keeps 320 bytes of room) */
@@ -505,7 +510,7 @@ class InflateSource {
                     if (dec->run(scratch.data(), &p, scratch.data() + scratch.size()) == fastinflate::FI_DONE &&
                         (size_t)(p - scratch.data()) == b.out_len &&
                         crc32(crc32(0L, Z_NULL, 0), scratch.data(), (uInt)b.out_len) == b.crc) {
-                        memcpy(out_.data() + b.out_off, scratch.data(), b.out_len);
+                        memcpy(out.data() + b.out_off, scratch.data(), b.out_len);
                         continue;
                     }
                 }
@@ -513,26 +518,29 @@ class InflateSource {
                 if (inflateInit2(&zs, -15) != Z_OK) { bad[t] = 1; return; }
                 zs.next_in = cbuf_.data() + b.in_off;
                 zs.avail_in = (uInt)b.in_len;
-                zs.next_out = out_.data() + b.out_off;
+                zs.next_out = out.data() + b.out_off;
                 zs.avail_out = (uInt)b.out_len;
                 const int rc = inflate(&zs, Z_FINISH);
                 inflateEnd(&zs);
                 if (rc != Z_STREAM_END || zs.avail_out != 0 ||
-                    crc32(crc32(0L, Z_NULL, 0), out_.data() + b.out_off, (uInt)b.out_len) != b.crc) {
+                    crc32(crc32(0L, Z_NULL, 0), out.data() + b.out_off, (uInt)b.out_len) != b.crc) {
                     bad[t] = 1;
                     return;
                 }
             }
-        });
+        };
+        std::vector<std::thread> th;
+        for (unsigned t = 1; t < nw; ++t) th.emplace_back(work, t);
+        work(0);
+        for (auto &x : th) x.join();
         for (int x : bad) if (x) b2host::fatal("b200aln_reader", "corrupt BGZF block (inflate or CRC error).");
-        return out_total > 0 ? true : refill_bgzf(); /* a window of empty blocks (the EOF marker): look further */
+        return out_total;
     }
 
     bool bgzf_ = false, bgzf_eof_ = false;
     int fd_ = -1;
     uint64_t file_pos_ = 0;
-    std::vector<unsigned char> cbuf_, out_;
-    size_t out_pos_ = 0;
+    std::vector<unsigned char> cbuf_;
     gzFile gz_ = nullptr;
     std::string fn_;
     const unsigned char *zmap_ = nullptr; /* fast path: the compressed file */
